@@ -1,0 +1,272 @@
+/*
+ * t3dgeo.h -- C ABI of libt3dgeo, the B200-native geometry stage for Tetra3D.
+ *
+ * The reference (SolarLune/tetra3d, pure Go) has no plugin / FFI interface for this path: the whole
+ * geometry stage is the body of Model.ProcessVertices (model.go:600-995) plus the two
+ * globalSortingTriangleBucket.ForEach loops of the `render` closure in Camera.Render
+ * (camera.go:1610-1644 lighting, camera.go:1646-1820 emit), communicating through package globals
+ * (tetra3d.go:21-35).  This header is the seam a cgo shim binds: Go keeps the
+ * scene graph, the render-pair list and `flush` (camera.go:1829-2048); everything between "render
+ * pairs are known" (camera.go:1457) and "flush consumes colorVertexList[:n]" runs on the GPU.
+ *
+ * Conventions
+ *  - Plain C: pointers + sizes only.  Inputs are borrowed for the duration of the call (copied into
+ *    library-owned pinned staging), so Go may move/free them afterwards (cgo pointer rules hold).
+ *  - Outputs are library-owned buffers, valid until the next t3d_frame_begin on the same context.
+ *  - Every function returns T3D_OK (0) or a negative T3D_E_* code; t3d_last_error gives the text.
+ *    Nothing aborts.  Features that need host callbacks (Model.VertexTransformFunction model.go:47,
+ *    Model.VertexClipFunction model.go:53, Material.CustomDepthFunction material.go:129, auto-subdivision
+ *    model.go:729-739, LightVolumeCell.useLights light.go:652-654) cannot run on the device: the shim
+ *    must not submit such draws (it keeps the Go path for them) -- there is no CPU fallback in here.
+ *  - One context per GPU, single caller at a time (the reference path is single-goroutine, non
+ *    re-entrant: tetra3d.go:21-35, sortingTriangles.go:164).
+ *  - All matrices are Tetra3D Matrix4: row-major float32[16], row-vector convention, translation in
+ *    row 3 (matrix.go:9-10, 619-627).
+ */
+#ifndef T3DGEO_H
+#define T3DGEO_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T3D_ABI_VERSION 1
+
+enum {
+    T3D_OK            =  0,
+    T3D_E_INVALID     = -1,   /* bad argument / out-of-range index */
+    T3D_E_CUDA        = -2,   /* CUDA runtime error (text in t3d_last_error) */
+    T3D_E_UNSUPPORTED = -3,   /* feature needs a host callback (see header comment) */
+    T3D_E_NOMEM       = -4,
+    T3D_E_STATE       = -5,   /* call order violated (e.g. submit outside begin/execute) */
+    T3D_E_NOTFOUND    = -6    /* unknown mesh / volume id */
+};
+
+/* Material.TriangleSortMode (material.go:9-13) */
+enum { T3D_SORT_BACK_TO_FRONT = 0, T3D_SORT_FRONT_TO_BACK = 1, T3D_SORT_NONE = 2 };
+/* Material.LightingMode (material.go:34-38) */
+enum { T3D_LIGHTING_DEFAULT = 0, T3D_LIGHTING_FIXED_NORMALS = 1, T3D_LIGHTING_DOUBLE_SIDED = 2 };
+/* Material.LightVolumeShadingMode (material.go:50-55) */
+enum { T3D_LV_PER_VERTEX_WITHOUT_NORMAL = 0, T3D_LV_PER_VERTEX_WITH_NORMAL = 1, T3D_LV_PER_OBJECT = 2, T3D_LV_OFF = 3 };
+/* World.FogMode (world.go:7-11) */
+enum { T3D_FOG_ADD = 0, T3D_FOG_SUB = 1, T3D_FOG_OVERWRITE = 2 };
+/* ILight implementations (light.go:80, 137, 290, 377) */
+enum { T3D_LIGHT_AMBIENT = 0, T3D_LIGHT_POINT = 1, T3D_LIGHT_DIRECTIONAL = 2, T3D_LIGHT_VOLUME = 3 };
+
+/* t3d_camera.flags */
+enum {
+    T3D_CAM_PERSPECTIVE      = 1u << 0,  /* camera.perspective */
+    T3D_CAM_RENDER_DEPTH     = 1u << 1,  /* Camera.RenderDepth (camera.go:1744) */
+    T3D_CAM_RENDER_NORMALS   = 1u << 2,  /* Camera.RenderNormals (camera.go:1710) */
+    T3D_CAM_PERSP_CORRECT_UV = 1u << 3   /* Camera.PerspectiveCorrectedTextureMapping (camera.go:1689) */
+};
+
+/* t3d_draw.flags */
+enum {
+    T3D_DRAW_HAS_MATERIAL        = 1u << 0,   /* meshPart.Material != nil */
+    T3D_DRAW_BACKFACE_CULLING    = 1u << 1,   /* Material.BackfaceCulling (model.go:902) */
+    T3D_DRAW_LIT                 = 1u << 2,   /* `lighting` of camera.go:1521-1528 */
+    T3D_DRAW_SKINNED             = 1u << 3,   /* model.skinned (model.go:715) */
+    T3D_DRAW_BILLBOARD           = 1u << 4,   /* Material.BillboardEnabled (model.go:634) */
+    T3D_DRAW_BILLBOARD_LOCK_X    = 1u << 5,
+    T3D_DRAW_BILLBOARD_LOCK_Y    = 1u << 6,
+    T3D_DRAW_BILLBOARD_LOCK_Z    = 1u << 7,
+    T3D_DRAW_BILLBOARD_CAMERA_UP = 1u << 8,   /* BillboardUpDirection == BillboardYUpCameraY (model.go:639) */
+    T3D_DRAW_DEPTH_UNBILLBOARDED = 1u << 9,   /* BillboardedDepthMode == DepthModeUnbillboarded (model.go:700) */
+    T3D_DRAW_CONTINUE_FLUSH      = 1u << 10   /* dynamic batch child after the first: appends to the same
+                                                 flush as the previous draw (camera.go:2082-2100) */
+};
+
+/* ebiten.Vertex (github.com/hajimehoshi/ebiten/v2 v2.9.7, go.mod:6): what colorVertexList /
+ * depthVertexList / normalVertexList (tetra3d.go:21-23) hold.  Layout-identical so Go can
+ * unsafe.Slice the returned pointer straight into DrawTriangles. */
+typedef struct t3d_vertex {
+    float DstX, DstY, SrcX, SrcY;
+    float ColorR, ColorG, ColorB, ColorA;
+    float Custom0, Custom1, Custom2, Custom3;
+} t3d_vertex;
+
+/* MeshPart (mesh.go:2183-2190).  tri_end is EXCLUSIVE here (Go's TriangleEnd is inclusive: pass
+ * TriangleEnd+1).  The vertex range is informational; the library derives the range the part's
+ * triangles actually reference. */
+typedef struct t3d_part_range {
+    uint32_t vtx_start, vtx_end;
+    uint32_t tri_start, tri_end;
+} t3d_part_range;
+
+/* Mesh SoA arrays (mesh.go:260-302), uploaded once and whenever Go bumps `generation`. */
+typedef struct t3d_mesh_desc {
+    uint32_t        n_verts;
+    const float*    positions;      /* 3*n  Mesh.VertexPositions                                     */
+    const float*    normals;        /* 3*n  Mesh.VertexNormals                                       */
+    const float*    uvs;            /* 2*n  Mesh.VertexUVs                                           */
+    const float*    colors;         /* 4*n  Mesh.VertexColors[VertexActiveColorChannel] or NULL      */
+    const float*    weights;        /* 4*n  Mesh.VertexWeights padded to 4 per vertex, or NULL       */
+    const uint16_t* bones;          /* 4*n  Mesh.VertexBones padded to 4 per vertex, or NULL         */
+    const uint8_t*  n_influences;   /* n    len(VertexWeights[v]) (<=4, gltf.go:675-700), or NULL=4  */
+    uint32_t        n_tris;
+    const uint32_t* indices;        /* 3*t  Triangle.VertexIndexA/B/C (mesh.go:1697-1699)            */
+    const float*    centers;        /* 3*t  Triangle.Center (mesh.go:1980-1982)                      */
+    uint32_t        n_parts;
+    const t3d_part_range* parts;
+    float           max_span;       /* Mesh.Dimensions.MaxSpan() (mesh.go:41-43; camera.go:1592)     */
+    uint32_t        n_shape_keys;   /* mesh.shapeKeys (mesh.go:796-822)                              */
+    const float*    key_positions;  /* k*n*3 */
+    const float*    key_normals;    /* k*n*3 */
+} t3d_mesh_desc;
+
+/* Per-frame camera uniforms (camera.go:1329-1341, 1471-1472, 1603). */
+typedef struct t3d_camera {
+    float    vp[16];          /* camera.ViewMatrix().Mult(camera.Projection())  (camera.go:1329)   */
+    float    view[16];        /* camera.ViewMatrix() (model.go:707, RenderNormals only)            */
+    float    position[3];     /* camera.WorldPosition() (model.go:624)                             */
+    float    up[3];           /* camera.cameraUp (camera.go:1088; model.go:640)                    */
+    float    near_plane, far_plane;   /* camera.near / camera.far (model.go:713-714)               */
+    int32_t  width, height;   /* resultColorTexture bounds (camera.go:1471-1472)                   */
+    float    depth_margin;    /* Camera.DepthMargin (camera.go:1339)                               */
+    float    vertex_snapping; /* Camera.VertexSnapping (model.go:716, 807-812)                     */
+    uint32_t flags;           /* T3D_CAM_*                                                          */
+} t3d_camera;
+
+/* scene.World fields the emit loop reads (camera.go:1784-1812). */
+typedef struct t3d_world {
+    int32_t present;          /* scene.World != nil */
+    int32_t fog_on;
+    int32_t fog_mode;
+    float   fog_color[3];
+    float   fog_range[2];
+} t3d_world;
+
+/* One entry of a light list as seen by one draw.  World-space data only: the per-model working
+ * position / rotation of beginModel (light.go:175-189, 326-330) is derived on the device. */
+typedef struct t3d_light {
+    uint32_t type;            /* T3D_LIGHT_* */
+    float    color[3];        /* LightBase.color RGB (light.go:34) */
+    float    energy;          /* LightBase.energy */
+    float    position[3];     /* light.WorldPosition() (point; light.go:184) */
+    float    range;           /* PointLight.lightRange (light.go:141) */
+    float    forward[3];      /* sun.WorldRotation().Forward() (light.go:323) */
+    uint32_t volume;          /* handle from t3d_volume_upload (light volume) */
+} t3d_light;
+
+/* LightVolume lookup data (light.go:376-396, 583-663, 717-728, 1267-1272). */
+typedef struct t3d_volume_desc {
+    float    dim_min[3], dim_max[3];   /* l.dimensions */
+    float    cell_size[3];
+    uint32_t cell_count[3];
+    float    offset[3];
+    float    light_bias[3];
+    const float* cell_colors;          /* 3 * cx*cy*cz, index x + y*cx + z*cx*cy (light.go:1271) */
+} t3d_volume_desc;
+
+/* One render(rp) call (camera.go:1507): Model x MeshPart, in render order. */
+typedef struct t3d_draw {
+    uint64_t mesh_id;
+    uint32_t part;
+    uint32_t flags;                 /* T3D_DRAW_* */
+    float    transform[16];         /* model.Transform() (model.go:616) */
+    float    world_rotation[16];    /* model.WorldRotation() (light.go:328); used when lit by a sun */
+    float    color[4];              /* mpColor = model.Color x Material.Color (camera.go:1597-1601) */
+    float    src_w, src_h;          /* texture size or 0 (camera.go:1560-1566) */
+    uint8_t  sort_mode;             /* T3D_SORT_* (camera.go:1540-1543; BackToFront when no material) */
+    uint8_t  lighting_mode;         /* T3D_LIGHTING_* */
+    uint8_t  light_volume_mode;     /* T3D_LV_* */
+    uint8_t  reserved0;
+    uint32_t bone_offset;           /* first matrix of this model in the t3d_submit_bones arena */
+    uint32_t bone_count;
+    uint32_t light_list;            /* handle returned by t3d_submit_lights */
+    uint32_t reserved1;
+} t3d_draw;
+
+/* Per-draw result; `first_vertex` indexes the concatenated lists. */
+typedef struct t3d_draw_result {
+    uint64_t first_vertex;
+    uint32_t vertex_count;          /* 3 * drawn triangles: what flush passes as list[:n] */
+    uint32_t total_tris;            /* meshPart.TriangleCount() (camera.go:1532) */
+    float    min_depth, max_depth;  /* model.go:710-711, 962-967 (+-MaxFloat32 when nothing survived) */
+} t3d_draw_result;
+
+/* CUDA-event timings of the last executed frame, milliseconds (DebugInfo mirrors, camera.go:41-48). */
+typedef struct t3d_timings {
+    float upload_ms;    /* H2D of the frame's uniforms */
+    float prep_ms;      /* K0 per-draw uniforms */
+    float vertex_ms;    /* K1 fused skin/transform/light */
+    float cull_ms;      /* K2 cull + depth + min/max */
+    float sort_ms;      /* key + radix sort */
+    float emit_ms;      /* K4 emit */
+    float download_ms;  /* D2H of results (0 when results stayed on device) */
+    float total_ms;     /* first kernel to last kernel */
+} t3d_timings;
+
+typedef struct t3d_frame_output {
+    uint64_t            n_vertices;     /* total emitted vertices over all draws */
+    uint32_t            n_draws;
+    const t3d_vertex*   color_list;     /* colorVertexList  (tetra3d.go:21) */
+    const t3d_vertex*   depth_list;     /* depthVertexList  (tetra3d.go:23) */
+    const t3d_vertex*   normal_list;    /* normalVertexList (tetra3d.go:22); NULL unless RENDER_NORMALS */
+    const uint16_t*     index_list;     /* indexList (tetra3d.go:24): identity, uint16 wrap (camera.go:1816);
+                                           a static table -- slice it [0, flush vertex count) */
+    const uint32_t*     tri_ids;        /* n_vertices/3: mesh triangle index of each emitted triangle */
+    const t3d_draw_result* draws;       /* n_draws, submit order */
+} t3d_frame_output;
+
+typedef struct t3d_ctx t3d_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int         t3d_abi_version(void);
+int         t3d_create(t3d_ctx** out, int device_id);
+void        t3d_destroy(t3d_ctx* ctx);
+const char* t3d_last_error(t3d_ctx* ctx);           /* ctx may be NULL (creation errors) */
+
+/* ---- residency ---------------------------------------------------------------------------------- */
+/* Replaces: the implicit "mesh lives in Go slices" of mesh.go:260-302.  Re-upload when dirty. */
+int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t3d_mesh_desc* desc);
+/* Updates only MeshShapeKey.weight values (mesh.go:796-822); k must equal n_shape_keys. */
+int t3d_mesh_set_shape_key_weights(t3d_ctx* ctx, uint64_t mesh_id, const float* weights, uint32_t k);
+int t3d_mesh_release(t3d_ctx* ctx, uint64_t mesh_id);
+/* LightVolume grids (light.go:376-396). */
+int t3d_volume_upload(t3d_ctx* ctx, uint32_t volume_id, const t3d_volume_desc* desc);
+int t3d_volume_release(t3d_ctx* ctx, uint32_t volume_id);
+
+/* ---- per frame ---------------------------------------------------------------------------------- */
+/* Replaces: the prologue of Camera.Render that fixes vpMatrix / camera constants (camera.go:1329-1341). */
+int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world);
+/* Replaces: building sceneLights / LightGroup.Lights (camera.go:1275-1303, 1576-1581).  Returns a
+ * light-list handle in *list_id; list 0 is always the empty list. */
+int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id);
+/* Replaces: reading bone.boneInfluence per vertex (model.go:574-580, node.go:592-594).  Appends n
+ * matrices to the frame's bone arena and returns the offset of the first in *offset. */
+int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset);
+/* Replaces: one render(rp) call (camera.go:1507-1827) per element, in render order. */
+int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
+/* Replaces: Model.ProcessVertices + the lighting and emit loops for all submitted draws.
+ * Asynchronous: returns after enqueueing on the context's stream. */
+int t3d_frame_execute(t3d_ctx* ctx);
+/* Waits for the frame and returns host-visible (pinned) result lists: what flush() consumes. */
+int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
+/* Waits for the frame and returns DEVICE pointers (no D2H of the lists; `draws` is still host memory).
+ * For device-resident consumers (NCCL gather, interop rasterisers). */
+int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
+
+/* ---- introspection (tests, profiling) ------------------------------------------------------------ */
+/* Copies the per-vertex intermediates of draw `draw` (globalVertexTransforms tetra3d.go:30 and
+ * mesh.vertexLights) for mesh vertices [vtx_start, vtx_end) of its part into clip4 / light4
+ * (4 floats per vertex each; either may be NULL). */
+int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end,
+                                 float* clip4, float* light4);
+/* Number of kernels launched by the last t3d_frame_execute. */
+int t3d_debug_last_launch_count(t3d_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
+void* t3d_debug_stream(t3d_ctx* ctx);
+/* Algorithmic bytes of the fused vertex kernel for the last frame (DESIGN.md roofline figure). */
+uint64_t t3d_debug_vertex_kernel_bytes(t3d_ctx* ctx);
+/* Bytes copied host->device by the last t3d_frame_execute and device->host by the last t3d_frame_results*. */
+int t3d_debug_frame_bytes(t3d_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T3DGEO_H */

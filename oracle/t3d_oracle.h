@@ -1,0 +1,257 @@
+/*
+ * t3d_oracle.h -- CPU oracle for the Tetra3D software geometry stage.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's
+ * Go algorithm (SolarLune/tetra3d, Camera.Render -> Model.ProcessVertices ->
+ * light.Light -> emit).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product (libt3dgeo.so,
+ * libt3dhost.so) never links, loads or calls anything in oracle/.
+ *
+ * PARITY STATUS: "parity unpinned" for the hot path itself.  The reference holds
+ * no golden vectors for ProcessVertices / lighting / sorting;
+ * the only assertion-bearing test in the reference, TestMatrixInversion
+ * (matrix_test.go:36-55), is reproduced as a known-answer test against
+ * orc_mat4_* (tests/test_oracle_kat.py).  No Go toolchain exists in the build
+ * image, so the reference cannot be executed here.  Everything else follows the
+ * cited reference lines operation by operation: float32 everywhere, no FMA
+ * contraction (-ffp-contract=off), left-to-right evaluation as Go/amd64
+ * (GOAMD64=v1) does.
+ *
+ * All file:line citations are relative to the reference tree.
+ */
+#ifndef T3D_ORACLE_H
+#define T3D_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (material.go:9-55, world.go:7-11) ------------------------------ */
+enum { ORC_SORT_BACK_TO_FRONT = 0, ORC_SORT_FRONT_TO_BACK = 1, ORC_SORT_NONE = 2 };
+enum { ORC_TRANSPARENCY_AUTO = 0, ORC_TRANSPARENCY_OPAQUE = 1, ORC_TRANSPARENCY_ALPHA_CLIP = 2,
+       ORC_TRANSPARENCY_TRANSPARENT = 3 };
+enum { ORC_BILLBOARD_Y_UP_GLOBAL_Y = 0, ORC_BILLBOARD_Y_UP_CAMERA_Y = 1 };
+enum { ORC_LIGHTING_DEFAULT = 0, ORC_LIGHTING_FIXED_NORMALS = 1, ORC_LIGHTING_DOUBLE_SIDED = 2 };
+enum { ORC_DEPTH_MODE_DEFAULT = 0, ORC_DEPTH_MODE_UNBILLBOARDED = 1 };
+enum { ORC_LV_PER_VERTEX_WITHOUT_NORMAL = 0, ORC_LV_PER_VERTEX_WITH_NORMAL = 1, ORC_LV_PER_OBJECT = 2,
+       ORC_LV_OFF = 3 };
+enum { ORC_FOG_ADD = 0, ORC_FOG_SUB = 1, ORC_FOG_OVERWRITE = 2 };
+enum { ORC_LIGHT_AMBIENT = 0, ORC_LIGHT_POINT = 1, ORC_LIGHT_DIRECTIONAL = 2, ORC_LIGHT_VOLUME = 3 };
+
+/* ---- scene description (flat, borrowed pointers) --------------------------- */
+
+/* Node local TRS (node.go:406, 572-608).  rotation is a row-major Matrix4. */
+typedef struct {
+    float   position[3];
+    float   scale[3];
+    float   rotation[16];
+    int32_t parent;              /* index into orc_scene.nodes, -1 = none */
+} orc_node;
+
+/* Material fields the geometry stage reads (material.go:66-131). */
+typedef struct {
+    int32_t present;             /* MeshPart.Material != nil */
+    float   color[4];
+    int32_t backface_culling;
+    int32_t triangle_sort_mode;
+    int32_t shadeless;
+    int32_t lighting_mode;
+    int32_t light_volume_shading_mode;
+    int32_t billboard_enabled, billboard_lock_x, billboard_lock_y, billboard_lock_z;
+    int32_t billboard_up_direction;
+    int32_t billboarded_depth_mode;
+    int32_t transparency_mode;
+    int32_t blend_source_over;   /* mat.Blend == ebiten.BlendSourceOver */
+    int32_t visible;
+    int32_t render_order;
+    int32_t use_texture;         /* UseTexture && Texture != nil */
+    float   tex_w, tex_h;        /* Texture.Bounds().Dx/Dy */
+} orc_material;
+
+/* MeshPart (mesh.go:2183-2190); triangle_end is INCLUSIVE as in the reference. */
+typedef struct {
+    int32_t vertex_index_start, vertex_index_end;
+    int32_t triangle_start, triangle_end;
+    orc_material material;
+} orc_part;
+
+/* Mesh SoA arrays (mesh.go:260-302). */
+typedef struct {
+    int32_t n_verts;
+    const float*    positions;      /* 3*n */
+    const float*    normals;        /* 3*n */
+    const float*    uvs;            /* 2*n */
+    const float*    colors;         /* 4*n: the ACTIVE channel, or NULL */
+    int32_t         active_color_channel; /* Mesh.VertexActiveColorChannel (<0: none) */
+    const float*    weights;        /* 4*n or NULL (mesh.VertexWeights, padded to 4) */
+    const uint16_t* bones;          /* 4*n or NULL (mesh.VertexBones, padded to 4)   */
+    const uint8_t*  n_influences;   /* n or NULL: len(VertexWeights[v])              */
+    int32_t n_tris;
+    const uint32_t* indices;        /* 3*t: Triangle.VertexIndexA/B/C */
+    int32_t n_parts;
+    const orc_part* parts;
+    int32_t n_shape_keys;           /* mesh.go:796-822 */
+    const float* key_positions;     /* k*n*3 */
+    const float* key_normals;       /* k*n*3 */
+    const float* key_weights;       /* k */
+} orc_mesh;
+
+/* Model (model.go:20-61). */
+typedef struct {
+    int32_t node;
+    int32_t mesh;
+    float   color[4];
+    int32_t shadeless;
+    int32_t visible;
+    int32_t frustum_culling;
+    int32_t skinned;
+    int32_t n_bones;
+    const float* bone_influences;   /* n_bones*16: Node.boneInfluence (node.go:592-594) per skin joint */
+    int32_t light_group;            /* index into light_groups, -1 = nil */
+    int32_t batch_owner;            /* Model.DynamicBatchOwner: model index, -1 = nil */
+    int32_t batch_owner_part;       /* the owner's MeshPart key in DynamicBatchModels */
+} orc_model;
+
+/* ILight (light.go:12-30): ambient/point/directional/volume. */
+typedef struct {
+    int32_t type;
+    int32_t node;
+    float   color[3];
+    float   energy;
+    int32_t visible;
+    float   range;                  /* PointLight.lightRange */
+    int32_t volume;                 /* index into volumes for ORC_LIGHT_VOLUME */
+} orc_light;
+
+typedef struct {
+    int32_t n_lights;
+    const int32_t* lights;          /* indices into orc_scene.lights */
+    int32_t active;
+} orc_light_group;
+
+/* LightVolume lookup data (light.go:376-396, 583-663, 717-728, 1267-1272). */
+typedef struct {
+    float dim_min[3], dim_max[3];
+    float cell_size[3];
+    int32_t cell_count[3];
+    float offset[3];
+    float light_bias[3];
+    const float* cell_colors;       /* 3 * cx*cy*cz, index x + y*cx + z*cx*cy */
+} orc_light_volume;
+
+/* Camera (camera.go:259-332). */
+typedef struct {
+    int32_t node;
+    int32_t width, height;
+    float   field_of_view;
+    float   near_plane, far_plane;
+    int32_t perspective;
+    float   ortho_scale;
+    float   depth_margin;
+    float   vertex_snapping;
+    int32_t render_depth;
+    int32_t render_normals;
+    int32_t perspective_corrected_texture_mapping;
+} orc_camera;
+
+/* World (world.go:25-42). */
+typedef struct {
+    int32_t present;
+    int32_t lighting_on;
+    int32_t fog_on;
+    int32_t fog_mode;
+    float   fog_color[4];
+    float   fog_range[2];
+    float   ambient_color[3];
+    float   ambient_energy;
+    int32_t ambient_visible;
+} orc_world;
+
+typedef struct {
+    int32_t n_nodes;        const orc_node* nodes;
+    int32_t n_meshes;       const orc_mesh* meshes;
+    int32_t n_models;       const orc_model* models;        /* DFS order of RenderNodes (camera.go:1200-1210) */
+    int32_t n_lights;       const orc_light* lights;        /* scene lights, DFS order */
+    int32_t n_scene_lights; const int32_t* scene_lights;    /* the subset that is in the tree under root */
+    int32_t n_light_groups; const orc_light_group* light_groups;
+    int32_t n_volumes;      const orc_light_volume* volumes;
+    orc_camera camera;
+    orc_world  world;
+} orc_scene;
+
+/* ---- results ---------------------------------------------------------------- */
+
+/* ebiten.Vertex (github.com/hajimehoshi/ebiten/v2 v2.9.7, go.mod:6): 12 x float32. */
+typedef struct {
+    float DstX, DstY, SrcX, SrcY, ColorR, ColorG, ColorB, ColorA, Custom0, Custom1, Custom2, Custom3;
+} orc_vertex;
+
+/* One render(rp) call (camera.go:1507-1827). */
+typedef struct {
+    int32_t model, part;
+    int32_t flush;                 /* which flush() consumed it */
+    int64_t first_vertex;          /* into the concatenated lists */
+    int32_t vertex_count;          /* 3 * drawn triangles */
+    int32_t total_tris;            /* meshPart.TriangleCount() */
+    float   min_depth, max_depth;  /* model.go:710-711, 962-967 */
+} orc_render_rec;
+
+/* One flush(rp) call (camera.go:1829-2048). */
+typedef struct {
+    int32_t model, part;
+    int64_t first_vertex;
+    int32_t vertex_count;
+} orc_flush_rec;
+
+typedef struct {
+    int32_t n_renders;  orc_render_rec* renders;
+    int32_t n_flushes;  orc_flush_rec*  flushes;
+    int64_t n_vertices;
+    orc_vertex* color_list;
+    orc_vertex* depth_list;
+    orc_vertex* normal_list;
+    uint16_t*   index_list;
+    uint32_t*   tri_ids;           /* n_vertices/3: mesh triangle index of each emitted triangle */
+    /* optional capture of the per-vertex intermediates of every render() call, concatenated in render
+     * order over the part's vertex range [vertex_index_start, vertex_index_end): */
+    int64_t n_captured;
+    float*  cap_clip;              /* 4 per vertex: globalVertexTransforms  */
+    float*  cap_light;             /* 4 per vertex: mesh.vertexLights.colors */
+    /* DebugInfo counters (camera.go:51-57) */
+    int32_t total_parts, drawn_parts, batched_parts, total_tris, drawn_tris, light_count, active_light_count;
+    /* wall-clock split, seconds (camera.go:41-48 mirrors) */
+    double t_total, t_process, t_light, t_emit;
+} orc_result;
+
+enum { ORC_OK = 0, ORC_E_UNSUPPORTED = -3, ORC_E_INVALID = -1 };
+
+/* Runs Camera.RenderScene on the scene.  capture != 0 fills cap_clip/cap_light. */
+int  orc_render_scene(const orc_scene* scene, int capture, orc_result** out);
+void orc_free_result(orc_result* r);
+const char* orc_last_error(void);
+
+/* ---- math exposed for known-answer tests (matrix.go) ------------------------- */
+void  orc_mat4_identity(float* m);
+void  orc_mat4_mult(const float* a, const float* b, float* out);        /* matrix_amd64.s / matrix_none.go */
+void  orc_mat4_inverted(const float* m, float* out);                     /* matrix.go:255-307 */
+void  orc_mat4_transposed(const float* m, float* out);                   /* matrix.go:218-230 */
+void  orc_mat4_rotate(float x, float y, float z, float angle, float* out); /* matrix.go:100-128 */
+void  orc_mat4_translate(float x, float y, float z, float* out);
+void  orc_mat4_scale(float x, float y, float z, float* out);
+int   orc_mat4_equals(const float* a, const float* b);                   /* matrix.go:511-522 */
+void  orc_mat4_decompose(const float* m, float* pos3, float* scale3, float* rot16); /* matrix.go:181-196 */
+void  orc_mat4_lookat(const float* from3, const float* to3, const float* up3, float* out); /* matrix.go:788-815 */
+void  orc_mat4_perspective(float fovy, float near_plane, float far_plane, float w, float h, float* out); /* matrix.go:588-604 */
+void  orc_mat4_orthographic(float near_plane, float far_plane, float r, float l, float t, float b, float* out);
+void  orc_node_transform(const orc_node* nodes, int32_t idx, float* out16); /* node.go:572-608 */
+/* Triangle.RecalculateCenter (mesh.go:1972-1982) for every triangle of a mesh. */
+void  orc_triangle_centers(const float* positions, const uint32_t* indices, int32_t n_tris, float* centers3);
+/* The 512-bin assignment alone (sortingTriangles.go:38-64). */
+int   orc_bin_index(float depth, float min_depth, float max_depth, int sort_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,205 @@
+"""Small seeded scenes for parity tests (shared by the CPU-oracle tests and the GPU tests)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from tetra3d_b200 import workloads as W
+from tetra3d_b200.scenedesc import (LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_VOLUME, CameraDesc, LightDesc,
+                                    LightGroupDesc, MaterialDesc, MeshDesc, ModelDesc, NodeDesc, PartDesc, SceneDesc, VolumeDesc,
+                                    WorldDesc)
+
+F32 = np.float32
+
+
+def single_triangle(z=0.0, flip=False, backface=True) -> MeshDesc:
+    pos = np.array([[-1, -1, z], [1, -1, z], [0, 1, z]], F32)
+    idx = np.array([[0, 2, 1]] if flip else [[0, 1, 2]], np.uint32)
+    nrm = np.tile(np.array([[0, 0, 1]], F32), (3, 1))
+    uv = np.array([[0, 0], [1, 0], [0.5, 1]], F32)
+    return MeshDesc(pos, nrm, uv, idx, [PartDesc(0, 3, 0, 0, MaterialDesc(backface_culling=backface))])
+
+
+def random_soup(n_tris=500, seed=0, extent=6.0, material=None, colors=False, n_parts=1) -> MeshDesc:
+    """Random, partly shared-vertex triangle soup around the origin."""
+    rng = np.random.default_rng(seed)
+    n_verts = max(8, n_tris // 2 * 3 // 2)
+    n_verts = (n_verts + n_parts - 1) // n_parts * n_parts
+    pos = rng.uniform(-extent, extent, (n_verts, 3)).astype(F32)
+    nrm = rng.normal(size=(n_verts, 3)).astype(F32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    uv = rng.uniform(0, 1, (n_verts, 2)).astype(F32)
+    per_v = n_verts // n_parts
+    per_t = n_tris // n_parts
+    idx_l, parts = [], []
+    for p in range(n_parts):
+        lo = p * per_v
+        tri = lo + rng.integers(0, per_v, (per_t, 3))
+        # no repeated index inside a triangle (the reference double-lights such triangles)
+        bad = (tri[:, 0] == tri[:, 1]) | (tri[:, 1] == tri[:, 2]) | (tri[:, 0] == tri[:, 2])
+        tri[bad] = lo + np.array([0, 1, 2])
+        idx_l.append(tri)
+        mat = material if material is not None else MaterialDesc(backface_culling=bool(p % 2 == 0), triangle_sort_mode=p % 3)
+        parts.append(PartDesc(lo, lo + per_v, p * per_t, (p + 1) * per_t - 1, mat))
+    idx = np.concatenate(idx_l).astype(np.uint32)
+    col = rng.uniform(0, 1, (n_verts, 4)).astype(F32) if colors else None
+    return MeshDesc(pos, nrm.astype(F32), uv, idx, parts, colors=col, active_color_channel=0 if colors else -1)
+
+
+def random_rotation(rng) -> np.ndarray:
+    return W.rotation_matrix(rng.normal(size=3), float(rng.uniform(0, 2 * np.pi)))
+
+
+def lights_mixed(rng, ranged=False) -> list:
+    ls = [LightDesc(LIGHT_POINT, NodeDesc(position=tuple(float(x) for x in rng.uniform(-8, 8, 3))), color=tuple(float(x) for x in rng.uniform(0.2, 1, 3)),
+                    energy=float(rng.uniform(1, 6)), range=float(rng.uniform(4, 12)) if ranged and i % 2 == 0 else 0.0, name="p%d" % i) for i in range(3)]
+    ls.append(LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=random_rotation(rng)), color=(1.0, 0.9, 0.8), energy=0.8, name="sun"))
+    ls.append(LightDesc(LIGHT_AMBIENT, NodeDesc(), color=(0.2, 0.3, 0.4), energy=0.5, name="amb"))
+    return ls
+
+
+def soup_scene(seed=0, n_models=4, n_tris=600, lit=True, ranged=False, cam: CameraDesc = None, world: WorldDesc = None, colors=False,
+               n_parts=3, material=None, scale_range=(0.5, 1.5), parent=False) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    mesh = random_soup(n_tris, seed + 100, colors=colors, n_parts=n_parts, material=material)
+    models = []
+    group = NodeDesc(position=(1.0, -0.5, 0.25), rotation=random_rotation(rng), scale=(1.0, 1.0, 1.0), name="group") if parent else None
+    for i in range(n_models):
+        s = rng.uniform(*scale_range, 3)
+        nd = NodeDesc(position=tuple(float(x) for x in rng.uniform(-5, 5, 3)), scale=tuple(float(x) for x in s), rotation=random_rotation(rng),
+                      parent=group if (parent and i % 2 == 0) else None)
+        models.append(ModelDesc(mesh, nd, color=tuple(float(x) for x in rng.uniform(0.5, 1, 4)) if i % 2 else (1, 1, 1, 1),
+                                frustum_culling=bool(i % 3), name="m%d" % i))
+    if parent:   # keep description order == depth-first order: children of the group node first
+        models = [m for m in models if m.node.parent is not None] + [m for m in models if m.node.parent is None]
+    lights = lights_mixed(rng, ranged) if lit else []
+    cam = cam if cam is not None else CameraDesc(node=NodeDesc(position=(0.5, 1.0, 14.0), rotation=W.rotation_matrix((0, 1, 0), 0.05)))
+    return SceneDesc(models, lights, cam, world if world is not None else WorldDesc(ambient_energy=0.1), name="soup%d" % seed)
+
+
+def skinned_scene(seed=0, n=6) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=5)
+    # make some weights exactly 0 / 1 and vary the influence count to reach every branch of skinVertex
+    w = mesh.weights.copy(); n_inf = mesh.n_influences.copy()
+    w[::7, 0] = 1.0; w[::7, 1] = 0.0
+    w[3::11, 0] = 0.0; w[3::11, 1] = 1.0
+    n_inf[5::13] = 1
+    extra = rng.uniform(0, 0.2, len(w)).astype(F32)
+    w[1::5, 2] = extra[1::5]; n_inf[1::5] = 3
+    mesh.bones[1::5, 2] = (mesh.bones[1::5, 0] + 1) % 5
+    mesh.weights = w; mesh.n_influences = n_inf
+    models = []
+    ls = [LightDesc(LIGHT_POINT, NodeDesc(position=(2.0, 3.0, 4.0)), color=(1, 0.8, 0.6), energy=4.0, range=30.0, in_scene=False),
+          LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=W.rotation_matrix((1, 0, 0), 0.7)), color=(0.5, 0.6, 1.0), energy=1.0, in_scene=False)]
+    group = LightGroupDesc(ls)
+    for i in range(n):
+        bi = W.chain_bone_influences(bone_y, (2.0 * (i - n / 2), -1.0, 0.0), float(rng.uniform(0, 6)), 0.3)
+        models.append(ModelDesc(mesh, NodeDesc(), bone_influences=bi, light_group=group if i % 2 == 0 else None, frustum_culling=False, name="char%d" % i))
+    lights = [LightDesc(LIGHT_POINT, NodeDesc(position=(-3.0, 2.0, 5.0)), color=(0.9, 0.9, 0.5), energy=3.0, name="scene_point")]
+    return SceneDesc(models, lights, CameraDesc(node=NodeDesc(position=(0.0, 1.0, 9.0))), WorldDesc(ambient_energy=0.15), name="skinned")
+
+
+def shape_key_scene(seed=0) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    mesh = random_soup(200, seed, n_parts=1, material=MaterialDesc(backface_culling=False))
+    k = 2
+    mesh.key_positions = rng.normal(0, 0.3, (k, mesh.n_verts, 3)).astype(F32)
+    mesh.key_normals = rng.normal(0, 0.1, (k, mesh.n_verts, 3)).astype(F32)
+    mesh.key_weights = np.array([0.35, 0.8], F32)
+    return SceneDesc([ModelDesc(mesh, NodeDesc(position=(0.0, 0.0, -2.0)))], lights_mixed(rng), CameraDesc(), WorldDesc(), name="shapekeys")
+
+
+def billboard_scene(seed=0, locks=(False, False, False), camera_up=False, unbillboarded=False) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    mat = MaterialDesc(billboard_enabled=True, billboard_lock_x=locks[0], billboard_lock_y=locks[1], billboard_lock_z=locks[2],
+                       billboard_up_direction=1 if camera_up else 0, billboarded_depth_mode=1 if unbillboarded else 0, backface_culling=False,
+                       shadeless=True)
+    colors = rng.uniform(0.1, 1, (4, 4)).astype(F32)
+    mesh = W.plane_mesh(2, 2, material=mat, colors=colors)
+    models = [ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-6, 6, 3)), scale=(float(rng.uniform(0.3, 1.5)),) * 3,
+                                       rotation=random_rotation(rng)), name="bb%d" % i) for i in range(12)]
+    cam = CameraDesc(node=NodeDesc(position=(1.0, 2.0, 12.0), rotation=W.rotation_matrix((1, 0, 0), -0.15)))
+    return SceneDesc(models, [], cam, WorldDesc(), name="billboards")
+
+
+def batch_scene(seed=0, n_children=40, transparent=True) -> SceneDesc:
+    """A dynamic batch owner with particle-like children (camera.go:1398-1453, 2075-2100)."""
+    rng = np.random.default_rng(seed)
+    child_mat = MaterialDesc(billboard_enabled=True, transparency_mode=3 if transparent else 0, shadeless=True, backface_culling=False)
+    colors = rng.uniform(0.1, 1, (4, 4)).astype(F32)
+    child_mesh = W.plane_mesh(1, 1, material=child_mat, colors=colors)
+    owner_mesh = W.plane_mesh(1, 1, material=MaterialDesc(transparency_mode=3 if transparent else 0, shadeless=True))
+    owner = ModelDesc(owner_mesh, NodeDesc(position=(0.0, 0.0, -3.0)), frustum_culling=False, name="owner")
+    models = [owner]
+    for i in range(n_children):
+        models.append(ModelDesc(child_mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-5, 5, 3)), scale=(float(rng.uniform(0.2, 1)),) * 3),
+                                color=(1.0, float(rng.uniform(0, 1)), 0.5, 0.7), batch_owner=owner, frustum_culling=bool(i % 2), name="c%d" % i))
+    solid = ModelDesc(W.cube_mesh(1, 1, 1), NodeDesc(position=(2.0, 0.0, 0.0)), name="solid")
+    models.append(solid)
+    return SceneDesc(models, [], CameraDesc(), WorldDesc(), name="batch")
+
+
+def volume_scene(seed=0, mode=0) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    cx, cy, cz = 5, 4, 6
+    vol = VolumeDesc(dim_min=(-6, -5, -6), dim_max=(6, 5, 6), cell_size=(2.4, 2.5, 2.0), cell_count=(cx, cy, cz),
+                     colors=rng.uniform(0, 1, (cx * cy * cz, 3)).astype(F32), offset=(0.1, -0.2, 0.05), light_bias=(0.0, 0.1, 0.0))
+    mat = MaterialDesc(light_volume_shading_mode=mode, backface_culling=False)
+    mesh = random_soup(300, seed, extent=3.0, n_parts=1, material=mat)
+    models = [ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-2, 2, 3)), rotation=random_rotation(rng)), name="v%d" % i) for i in range(3)]
+    lights = [LightDesc(LIGHT_VOLUME, NodeDesc(), color=(1.0, 0.9, 0.7), energy=1.5, volume=vol, name="volume"),
+              LightDesc(LIGHT_POINT, NodeDesc(position=(0.0, 4.0, 3.0)), energy=2.0)]
+    return SceneDesc(models, lights, CameraDesc(), WorldDesc(), name="volume")
+
+
+def transparent_scene(seed=0) -> SceneDesc:
+    rng = np.random.default_rng(seed)
+    models = []
+    for i in range(8):
+        mat = MaterialDesc(transparency_mode=3 if i % 2 else 0, render_order=int(rng.integers(0, 3)), backface_culling=False,
+                           color=(1, 1, 1, 0.5 if i % 3 == 0 else 1.0), triangle_sort_mode=i % 3)
+        mesh = W.cube_mesh(1, 1.5, 1, material=mat)
+        models.append(ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-4, 4, 3)), rotation=random_rotation(rng)),
+                                color=(1, 1, 1, 1.0 if i % 4 else 0.6), name="t%d" % i))
+    # fully transparent model: ProcessVertices early-out (model.go:604)
+    models.append(ModelDesc(W.cube_mesh(1, 1, 1, material=MaterialDesc(transparency_mode=0)), NodeDesc(), color=(1, 1, 1, 0.0), name="ghost"))
+    # invisible model and invisible material
+    models.append(ModelDesc(W.cube_mesh(), NodeDesc(position=(1.0, 1.0, 1.0)), visible=False, name="hidden"))
+    models.append(ModelDesc(W.cube_mesh(material=MaterialDesc(visible=False)), NodeDesc(position=(-1.0, 1.0, 1.0)), name="hiddenmat"))
+    # no material at all
+    nomat = W.cube_mesh(); nomat.parts[0].material = None
+    models.append(ModelDesc(nomat, NodeDesc(position=(0.0, -2.0, 0.0)), name="nomat"))
+    return SceneDesc(models, lights_mixed(rng), CameraDesc(), WorldDesc(), name="transparent")
+
+
+ALL_SMALL = {
+    "soup_lit": lambda: soup_scene(1),
+    "soup_unlit_colors": lambda: soup_scene(2, lit=False, colors=True),
+    "soup_ranged": lambda: soup_scene(3, ranged=True),
+    "soup_parent": lambda: soup_scene(4, parent=True),
+    "soup_ortho": lambda: soup_scene(5, cam=CameraDesc(perspective=False, ortho_scale=16.0)),
+    "soup_snap_pctm_normals": lambda: soup_scene(6, cam=CameraDesc(vertex_snapping=8.0, perspective_corrected_texture_mapping=True, render_normals=True),
+                                                 material=MaterialDesc(use_texture=True, tex_w=64, tex_h=32)),
+    "soup_fog_add": lambda: soup_scene(7, cam=CameraDesc(render_depth=False), world=WorldDesc(fog_mode=0, fog_color=(0.3, 0.2, 0.1, 1), fog_range=(0.1, 0.9))),
+    "soup_fog_sub": lambda: soup_scene(8, cam=CameraDesc(render_depth=False), world=WorldDesc(fog_mode=1, fog_color=(0.9, 0.8, 0.7, 1))),
+    "soup_fixed_normals": lambda: soup_scene(9, material=MaterialDesc(lighting_mode=1, backface_culling=False)),
+    "soup_double_sided": lambda: soup_scene(10, material=MaterialDesc(lighting_mode=2, backface_culling=False, triangle_sort_mode=1)),
+    "soup_lighting_off": lambda: soup_scene(11, world=WorldDesc(lighting_on=False)),
+    "soup_no_world": lambda: soup_scene(12, world=WorldDesc(present=False)),
+    "skinned": lambda: skinned_scene(1),
+    "shape_keys": lambda: shape_key_scene(1),
+    "billboard": lambda: billboard_scene(1),
+    "billboard_locks": lambda: billboard_scene(2, locks=(True, False, True), camera_up=True),
+    "billboard_lock_y_unbill": lambda: billboard_scene(3, locks=(False, True, False), unbillboarded=True),
+    "batch_transparent": lambda: batch_scene(1),
+    "batch_solid": lambda: batch_scene(2, transparent=False),
+    "volume_mode0": lambda: volume_scene(1, 0),
+    "volume_mode1": lambda: volume_scene(2, 1),
+    "volume_mode2": lambda: volume_scene(3, 2),
+    "volume_off": lambda: volume_scene(4, 3),
+    "transparent": lambda: transparent_scene(1),
+    "stress_small": lambda: SceneDesc([ModelDesc(W.cube_mesh(2, 2, 2, copies=20, material=MaterialDesc(shadeless=True, use_texture=True, tex_w=16, tex_h=16)),
+                                                  NodeDesc(position=(4.0 * x, 0.0, 0.0)), name="m%d" % x) for x in range(6)], [], CameraDesc(), WorldDesc()),
+}

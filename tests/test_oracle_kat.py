@@ -1,0 +1,116 @@
+"""Pins the oracle's math against the only assertion-bearing test of the reference (matrix_test.go:36-55)
+and against an independent numpy float32 evaluation of the cited formulas."""
+import numpy as np
+import pytest
+
+from oracle import binding as O
+
+F32 = np.float32
+
+
+def np_mult(a, b):
+    """matrix_none.go:6-32 / matrix_amd64.s: ((a0*b0 + a1*b1) + a2*b2) + a3*b3 in float32, no fusion."""
+    a = a.astype(F32); b = b.astype(F32)
+    out = np.zeros((4, 4), F32)
+    for i in range(4):
+        for j in range(4):
+            acc = F32(a[i, 0] * b[0, j])
+            for k in range(1, 4):
+                acc = F32(acc + F32(a[i, k] * b[k, j]))
+            out[i, j] = acc
+    return out
+
+
+def test_matrix_inversion_known_answer():
+    """TestMatrixInversion (matrix_test.go:36-55): M * M.Inverted() must be IsIdentity() for the four matrices.
+    The fourth has a zero Z scale: its inverse is non-finite and Matrix4.Equals (matrix.go:511-522) lets NaN
+    differences through, which is how the reference's own test passes; the oracle reproduces that."""
+    mats = [
+        O.mat4_rotate(0, 1, 0, 0.1),
+        O.mat4_translate(-10, 0.1, 3232.1976),
+        O.mat4_scale(10, 0.1, -0.45),
+        O.mat4_mult(O.mat4_mult(O.mat4_translate(-1, -1, -1), O.mat4_rotate(1, 0, 0.1, 0.334)), O.mat4_scale(10, 1, 0)),
+    ]
+    ident = O.mat4_identity()
+    for i, m in enumerate(mats):
+        prod = O.mat4_mult(m, O.mat4_inverted(m))
+        assert O.mat4_equals(prod, ident), "matrix #%d: M * M.Inverted() is not identity" % i
+    # the first three are genuinely invertible: check against float64
+    for m in mats[:3]:
+        inv = O.mat4_inverted(m)
+        assert np.allclose(inv.astype(np.float64), np.linalg.inv(m.astype(np.float64)), rtol=1e-5, atol=1e-6)
+    assert not np.isfinite(O.mat4_inverted(mats[3])).all()
+
+
+def test_mult_matches_float32_evaluation_order():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        a = rng.normal(size=(4, 4)).astype(F32) * F32(10)
+        b = rng.normal(size=(4, 4)).astype(F32)
+        got = O.mat4_mult(a, b)
+        assert np.array_equal(got.view(np.uint32), np_mult(a, b).view(np.uint32))
+
+
+def test_transposed_and_translate_scale_builders():
+    m = np.arange(16, dtype=F32).reshape(4, 4)
+    assert np.array_equal(O.mat4_transposed(m), m.T)
+    t = O.mat4_translate(1, 2, 3)
+    assert np.array_equal(t[3], np.array([1, 2, 3, 1], F32)) and np.array_equal(t[:3, :3], np.eye(3, dtype=F32))   # matrix.go:81-87
+    s = O.mat4_scale(2, 3, 4)
+    assert np.array_equal(np.diag(s), np.array([2, 3, 4, 1], F32))
+
+
+def test_rotate_is_counter_clockwise_about_axis():
+    # matrix.go:100-128: rotating +X about +Y by 90 degrees; vectors are rows (v * M)
+    r = O.mat4_rotate(0, 1, 0, np.pi / 2)
+    v = np.array([1, 0, 0, 0], F32) @ r
+    assert np.allclose(v[:3], [0, 0, -1], atol=1e-6)
+
+
+def test_decompose_roundtrip():
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        s = rng.uniform(0.5, 2, 3).astype(F32)
+        r = O.mat4_rotate(*rng.normal(size=3), float(rng.uniform(0, 6)))
+        p = rng.uniform(-5, 5, 3).astype(F32)
+        m = O.mat4_mult(O.mat4_mult(O.mat4_scale(*s), r), O.mat4_translate(*p))        # node.go:581-583
+        pos, sc, rot = O.mat4_decompose(m)
+        assert np.array_equal(pos, p)
+        assert np.allclose(sc, s, rtol=1e-5)
+        assert np.allclose(rot, r, atol=1e-5)
+
+
+def test_perspective_matrix_layout():
+    # matrix.go:588-604, row-vector convention: clip.W = -z_view * (2 f n)/(f-n) ... row 2 column 3
+    m = O.mat4_perspective(60, 0.1, 100, 640, 360)
+    t = np.tan(np.float32(60) * np.float32(np.pi) / 360)
+    assert np.isclose(m[1, 1], 0.1 / t, rtol=1e-6)
+    assert np.isclose(m[0, 0], 0.1 / (t * 640 / 360), rtol=1e-6)
+    assert np.isclose(m[2, 2], -(100.1) / (99.9), rtol=1e-6) and np.isclose(m[2, 3], -(2 * 100 * 0.1) / 99.9, rtol=1e-6)
+    assert m[3, 2] == -1 and m[3, 3] == 0
+
+
+def test_lookat_degenerate_cases():
+    assert np.array_equal(O.mat4_lookat((1, 2, 3), (1, 2, 3), (0, 1, 0)), np.eye(4, dtype=F32))      # matrix.go:791-793
+    m = O.mat4_lookat((0, 0, 0), (0, 5, 0), (0, 1, 0))                                              # z == up -> WorldRight
+    assert np.allclose(m[2, :3], [0, 1, 0]) and np.isfinite(m).all()
+
+
+def test_triangle_centers_formula():
+    pos = np.array([[0, 0, 0], [3, 0, 0], [0, 3, 3], [1, 1, 1]], F32)
+    idx = np.array([[0, 1, 2], [3, 2, 1]], np.uint32)
+    c = O.triangle_centers(pos, idx)
+    exp = np.array([[(F32(0) + F32(3) + F32(0)) / F32(3), 1, 1], [(F32(1) + F32(0) + F32(3)) / F32(3), (F32(1) + F32(3) + F32(0)) / F32(3), (F32(1) + F32(3) + F32(0)) / F32(3)]], F32)
+    assert np.array_equal(c, exp)                                                                    # mesh.go:1980-1982
+
+
+@pytest.mark.parametrize("depth,mn,mx,mode,expected", [
+    (5.0, 5.0, 5.0, 0, 0),          # rangeDiff == 0 -> +0.001 (sortingTriangles.go:43-46): (0/0.001)*512 = 0
+    (0.0, 0.0, 10.0, 0, 0),
+    (10.0, 0.0, 10.0, 0, 511),      # clamp to binCount-1 (sortingTriangles.go:54)
+    (5.0, 0.0, 10.0, 0, 256),
+    (9.99, 0.0, 10.0, 1, 511),
+    (5.0, 0.0, 10.0, 2, 0),         # TriangleSortModeNone -> bin 0 (sortingTriangles.go:52)
+])
+def test_bin_index(depth, mn, mx, mode, expected):
+    assert O.bin_index(depth, mn, mx, mode) == expected

@@ -1,0 +1,713 @@
+// t3d_api.cu -- the C ABI of include/t3dgeo.h: context, mesh residency, per-frame arenas, pipeline.
+//
+// Per frame: the host resolves every submitted draw into a DrawRec (device pointers + arena offsets),
+// uploads the records with the light lists and bone matrices in a few async copies from pinned
+// staging, then enqueues  prep -> vertex -> cull -> keys -> radix sort -> emit  on one stream.
+// Results stay on the device until t3d_frame_results (pinned D2H) or are handed out as device
+// pointers by t3d_frame_results_device.
+#include "../../include/t3dgeo.h"
+#include "t3d_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace t3d;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = std::max(bytes, cap + cap / 2);
+        want = (want + 255) & ~(size_t)255;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// growable pinned host array that keeps its contents
+template <class T> struct PinVec {
+    T* p = nullptr; size_t n = 0, cap = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        size_t nc = std::max(want, cap * 2 + 16);
+        T* q = nullptr;
+        cudaError_t e = cudaHostAlloc((void**)&q, nc * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (p) { memcpy(q, p, n * sizeof(T)); cudaFreeHost(p); }
+        p = q; cap = nc;
+        return cudaSuccess;
+    }
+    cudaError_t resize(size_t want) { cudaError_t e = reserve(want); if (e == cudaSuccess) n = want; return e; }
+    cudaError_t push(const T& v) { cudaError_t e = reserve(n + 1); if (e == cudaSuccess) p[n++] = v; return e; }
+    void clear() { n = 0; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+};
+
+struct PartInfo { uint32_t triStart, triEnd, a0, nv; };
+
+struct Mesh {
+    uint32_t generation = 0;
+    uint32_t nVerts = 0, nVertsPad = 0, nTris = 0, nKeys = 0;
+    uint32_t maxJoint = 0;
+    float maxSpan = 0;
+    float *pos = nullptr, *nrm = nullptr, *uv = nullptr, *col = nullptr, *wgt = nullptr, *ctr = nullptr;
+    float *keyPos = nullptr, *keyNrm = nullptr, *keyW = nullptr;
+    uint16_t* jnt = nullptr; uint8_t* ninf = nullptr; uint32_t* idx = nullptr;
+    std::vector<PartInfo> parts;
+    void release() {
+        void* ptrs[] = {pos, nrm, uv, col, wgt, ctr, keyPos, keyNrm, keyW, jnt, ninf, idx};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        *this = Mesh();
+    }
+};
+
+struct LightList { uint32_t off, count; };
+
+}  // namespace
+
+struct t3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::unordered_map<uint64_t, Mesh> meshes;
+    std::unordered_map<uint32_t, uint32_t> volumeIndex;     // id -> slot in volumes
+    std::vector<VolumeU> volumes;
+    std::vector<float*> volumeCells;
+    DevBuf dVolumes; bool volumesDirty = true;
+
+    // frame staging (pinned)
+    bool inFrame = false, executed = false, haveResults = false;
+    FrameConst fc;
+    PinVec<DrawRec> hDraws;
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hTileT;
+    PinVec<t3d_light> hLights;
+    PinVec<float> hBones;
+    std::vector<LightList> lightLists;
+    std::vector<uint32_t> drawTotalTris;
+    std::vector<uint8_t> drawContinue;
+    uint32_t vAcc = 0, tAcc = 0, luAcc = 0;
+    bool anyLit = false, anySkinned = false, anyUnbill = false;
+
+    // device arenas
+    DevBuf dDraws, dVbase, dTbase, dTileV, dTileT, dLightsIn, dLightsU, dBones, dStats;
+    DevBuf dClip, dLight, dWpos, dUnbill, dTnrm;
+    DevBuf dTdepth, dTdraw, dKeys0, dKeysA, dKeysB, dValsA, dValsB, dSortScratch, dCount;
+    DevBuf dColor, dDepth, dNormal, dTriIds;
+    const uint32_t* sortedKeys = nullptr; const uint32_t* sortedVals = nullptr;
+
+    // results (pinned)
+    PinVec<DrawStat> hStats;
+    PinVec<uint32_t> hCount;
+    PinVec<t3d_draw_result> hResults;
+    PinVec<t3d_vertex> hColor, hDepth, hNormal;
+    PinVec<uint32_t> hTriIds;
+    PinVec<uint16_t> hIndex;
+    uint64_t nVerticesOut = 0;
+
+    cudaEvent_t ev[10] = {};
+    uint64_t h2dBytes = 0, d2hBytes = 0;
+    int launches = 0;
+    uint64_t vertexKernelBytes = 0;
+    float downloadMs = 0;
+};
+
+static thread_local std::string g_createErr;
+
+static int fail(t3d_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_createErr = msg;
+    return code;
+}
+static int cuda_fail(t3d_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, e == cudaErrorMemoryAllocation ? T3D_E_NOMEM : T3D_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+template <class T>
+static cudaError_t upload_padded(T** dst, const T* src, size_t nElems, size_t nPadded, cudaStream_t s) {
+    *dst = nullptr;
+    cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(nPadded, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (nPadded > nElems) { e = cudaMemsetAsync(*dst + nElems, 0, (nPadded - nElems) * sizeof(T), s); if (e != cudaSuccess) return e; }
+    if (nElems) e = cudaMemcpyAsync(*dst, src, nElems * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
+
+extern "C" {
+
+int t3d_abi_version(void) { return T3D_ABI_VERSION; }
+
+const char* t3d_last_error(t3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+int t3d_create(t3d_ctx** out, int device_id) {
+    if (!out) return fail(nullptr, T3D_E_INVALID, "t3d_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, T3D_E_CUDA, std::string("t3d_create: no CUDA device (") + cudaGetErrorString(e) + "); libt3dgeo has no CPU fallback");
+    if (device_id < 0 || device_id >= n) return fail(nullptr, T3D_E_INVALID, "t3d_create: device_id out of range");
+    e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    t3d_ctx* ctx = new t3d_ctx();
+    ctx->device = device_id;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return T3D_OK;
+}
+
+void t3d_destroy(t3d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->meshes) kv.second.release();
+    for (float* c : ctx->volumeCells) if (c) cudaFree(c);
+    DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dDraws, &ctx->dVbase, &ctx->dTbase, &ctx->dTileV, &ctx->dTileT, &ctx->dLightsIn,
+                      &ctx->dLightsU, &ctx->dBones, &ctx->dStats, &ctx->dClip, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
+                      &ctx->dTnrm, &ctx->dTdepth, &ctx->dTdraw, &ctx->dKeys0, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
+                      &ctx->dValsB, &ctx->dSortScratch, &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
+    for (DevBuf* b : bufs) b->release();
+    ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hTileT.release();
+    ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
+    ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ---- residency -------------------------------------------------------------------------------------
+
+int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t3d_mesh_desc* d) {
+    if (!ctx || !d) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    if (!d->positions || !d->normals || !d->uvs || (d->n_tris && (!d->indices || !d->centers)) || (d->n_parts && !d->parts))
+        return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: positions, normals, uvs, indices, centers and parts are required");
+    if ((d->weights == nullptr) != (d->bones == nullptr))
+        return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: weights and bones must be given together");
+    if (d->n_shape_keys && (!d->key_positions || !d->key_normals))
+        return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: shape key arrays missing");
+    for (uint32_t t = 0; t < 3 * d->n_tris; t++)
+        if (d->indices[t] >= d->n_verts) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: triangle index out of range");
+
+    auto it = ctx->meshes.find(mesh_id);
+    if (it != ctx->meshes.end()) {
+        if (it->second.generation == generation) return T3D_OK;      // already resident
+        CU(cudaStreamSynchronize(ctx->stream));
+        it->second.release();
+    }
+    Mesh m;
+    m.generation = generation;
+    m.nVerts = d->n_verts; m.nVertsPad = (d->n_verts + 3u) & ~3u; m.nTris = d->n_tris; m.nKeys = d->n_shape_keys;
+    m.maxSpan = d->max_span;
+    const size_t nv = m.nVerts, np = m.nVertsPad;
+    cudaStream_t s = ctx->stream;
+    CU(upload_padded(&m.pos, d->positions, nv * 3, np * 3, s));
+    CU(upload_padded(&m.nrm, d->normals, nv * 3, np * 3, s));
+    CU(upload_padded(&m.uv, d->uvs, nv * 2, np * 2, s));
+    if (d->colors) CU(upload_padded(&m.col, d->colors, nv * 4, np * 4, s));
+    if (d->weights) {
+        CU(upload_padded(&m.wgt, d->weights, nv * 4, np * 4, s));
+        CU(upload_padded(&m.jnt, d->bones, nv * 4, np * 4, s));
+        if (d->n_influences) {
+            for (size_t i = 0; i < nv; i++) if (d->n_influences[i] > 4) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: more than 4 influences per vertex");
+            CU(upload_padded(&m.ninf, d->n_influences, nv, np, s));
+        }
+        for (size_t i = 0; i < nv * 4; i++) m.maxJoint = std::max<uint32_t>(m.maxJoint, d->bones[i]);
+    }
+    CU(upload_padded(&m.idx, d->indices, (size_t)m.nTris * 3, (size_t)m.nTris * 3, s));
+    CU(upload_padded(&m.ctr, d->centers, (size_t)m.nTris * 3, (size_t)m.nTris * 3, s));
+    if (m.nKeys) {
+        // keys are stored with the padded vertex stride so 4-vertex groups stay 16B-aligned
+        CU(cudaMalloc((void**)&m.keyPos, (size_t)m.nKeys * np * 3 * sizeof(float)));
+        CU(cudaMalloc((void**)&m.keyNrm, (size_t)m.nKeys * np * 3 * sizeof(float)));
+        CU(cudaMalloc((void**)&m.keyW, (size_t)m.nKeys * sizeof(float)));
+        CU(cudaMemsetAsync(m.keyPos, 0, (size_t)m.nKeys * np * 3 * sizeof(float), s));
+        CU(cudaMemsetAsync(m.keyNrm, 0, (size_t)m.nKeys * np * 3 * sizeof(float), s));
+        CU(cudaMemsetAsync(m.keyW, 0, (size_t)m.nKeys * sizeof(float), s));
+        for (uint32_t k = 0; k < m.nKeys; k++) {
+            CU(cudaMemcpyAsync(m.keyPos + (size_t)k * np * 3, d->key_positions + (size_t)k * nv * 3, nv * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(m.keyNrm + (size_t)k * np * 3, d->key_normals + (size_t)k * nv * 3, nv * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+    }
+    m.parts.resize(d->n_parts);
+    for (uint32_t p = 0; p < d->n_parts; p++) {
+        const t3d_part_range& pr = d->parts[p];
+        if (pr.tri_start > pr.tri_end || pr.tri_end > d->n_tris) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: part triangle range out of bounds"); }
+        PartInfo pi; pi.triStart = pr.tri_start; pi.triEnd = pr.tri_end; pi.a0 = 0; pi.nv = 0;
+        if (pr.tri_end > pr.tri_start) {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0;
+            for (size_t t = (size_t)pr.tri_start * 3; t < (size_t)pr.tri_end * 3; t++) { lo = std::min(lo, d->indices[t]); hi = std::max(hi, d->indices[t]); }
+            pi.a0 = lo & ~3u;
+            pi.nv = ((hi + 4u) & ~3u) - pi.a0;
+        }
+        m.parts[p] = pi;
+    }
+    // the source arrays are borrowed only for this call
+    CU(cudaStreamSynchronize(s));
+    ctx->meshes[mesh_id] = std::move(m);
+    return T3D_OK;
+}
+
+int t3d_mesh_set_shape_key_weights(t3d_ctx* ctx, uint64_t mesh_id, const float* weights, uint32_t k) {
+    if (!ctx || !weights) return fail(ctx, T3D_E_INVALID, "t3d_mesh_set_shape_key_weights: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    auto it = ctx->meshes.find(mesh_id);
+    if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_mesh_set_shape_key_weights: unknown mesh");
+    if (it->second.nKeys != k) return fail(ctx, T3D_E_INVALID, "t3d_mesh_set_shape_key_weights: key count mismatch");
+    if (k == 0) return T3D_OK;
+    CU(cudaMemcpyAsync(it->second.keyW, weights, k * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return T3D_OK;
+}
+
+int t3d_mesh_release(t3d_ctx* ctx, uint64_t mesh_id) {
+    if (!ctx) return T3D_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    auto it = ctx->meshes.find(mesh_id);
+    if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_mesh_release: unknown mesh");
+    CU(cudaStreamSynchronize(ctx->stream));
+    it->second.release();
+    ctx->meshes.erase(it);
+    return T3D_OK;
+}
+
+int t3d_volume_upload(t3d_ctx* ctx, uint32_t volume_id, const t3d_volume_desc* d) {
+    if (!ctx || !d || !d->cell_colors) return fail(ctx, T3D_E_INVALID, "t3d_volume_upload: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t cells = (size_t)d->cell_count[0] * d->cell_count[1] * d->cell_count[2];
+    if (cells == 0) return fail(ctx, T3D_E_INVALID, "t3d_volume_upload: empty grid");
+    uint32_t slot;
+    auto it = ctx->volumeIndex.find(volume_id);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (it == ctx->volumeIndex.end()) {
+        slot = (uint32_t)ctx->volumes.size();
+        ctx->volumes.push_back(VolumeU());
+        ctx->volumeCells.push_back(nullptr);
+        ctx->volumeIndex[volume_id] = slot;
+    } else {
+        slot = it->second;
+        if (ctx->volumeCells[slot]) { cudaFree(ctx->volumeCells[slot]); ctx->volumeCells[slot] = nullptr; }
+    }
+    float* dc = nullptr;
+    CU(cudaMalloc((void**)&dc, cells * 3 * sizeof(float)));
+    CU(cudaMemcpy(dc, d->cell_colors, cells * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    VolumeU V;
+    for (int i = 0; i < 3; i++) {
+        V.dimMin[i] = d->dim_min[i]; V.dimMax[i] = d->dim_max[i]; V.cellSize[i] = d->cell_size[i];
+        V.cellCount[i] = (int32_t)d->cell_count[i]; V.offset[i] = d->offset[i]; V.bias[i] = d->light_bias[i];
+    }
+    V.cells = dc;
+    ctx->volumes[slot] = V;
+    ctx->volumeCells[slot] = dc;
+    ctx->volumesDirty = true;
+    return T3D_OK;
+}
+
+int t3d_volume_release(t3d_ctx* ctx, uint32_t volume_id) {
+    if (!ctx) return T3D_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    auto it = ctx->volumeIndex.find(volume_id);
+    if (it == ctx->volumeIndex.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_volume_release: unknown volume");
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t slot = it->second;
+    if (ctx->volumeCells[slot]) { cudaFree(ctx->volumeCells[slot]); ctx->volumeCells[slot] = nullptr; }
+    ctx->volumes[slot].cells = nullptr;
+    ctx->volumeIndex.erase(it);
+    ctx->volumesDirty = true;
+    return T3D_OK;
+}
+
+// ---- per frame -------------------------------------------------------------------------------------
+
+int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world) {
+    if (!ctx || !cam) return fail(ctx, T3D_E_INVALID, "t3d_frame_begin: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    if (cam->width <= 0 || cam->height <= 0) return fail(ctx, T3D_E_INVALID, "t3d_frame_begin: camera size must be positive");
+    // the previous frame's outputs die here
+    CU(cudaStreamSynchronize(ctx->stream));
+    FrameConst& fc = ctx->fc;
+    memset(&fc, 0, sizeof fc);
+    memcpy(fc.vp, cam->vp, 64);
+    memcpy(fc.view, cam->view, 64);
+    memcpy(fc.camPos, cam->position, 12);
+    memcpy(fc.camUp, cam->up, 12);
+    fc.nearP = cam->near_plane; fc.farP = cam->far_plane;
+    fc.camW = (float)cam->width; fc.camH = (float)cam->height;
+    fc.halfW = (float)cam->width / 2; fc.halfH = (float)cam->height / 2;          // camera.go:1603
+    fc.depthMargin = (cam->far_plane - cam->near_plane) * cam->depth_margin;       // camera.go:1339
+    fc.camSpread = cam->far_plane - cam->near_plane + (fc.depthMargin * 2);        // camera.go:1341
+    fc.snapping = cam->vertex_snapping;
+    fc.camFlags = cam->flags;
+    if (world) {
+        fc.worldPresent = world->present; fc.fogOn = world->fog_on; fc.fogMode = world->fog_mode;
+        memcpy(fc.fogColor, world->fog_color, 12);
+        memcpy(fc.fogRange, world->fog_range, 8);
+    }
+    ctx->hDraws.clear(); ctx->hVbase.clear(); ctx->hTbase.clear(); ctx->hLights.clear(); ctx->hBones.clear();
+    ctx->lightLists.clear();
+    ctx->lightLists.push_back(LightList{0, 0});     // list 0: empty
+    ctx->drawTotalTris.clear(); ctx->drawContinue.clear();
+    ctx->vAcc = ctx->tAcc = ctx->luAcc = 0;
+    ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
+    ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
+    ctx->nVerticesOut = 0;
+    return T3D_OK;
+}
+
+int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id) {
+    if (!ctx || !list_id || (n && !lights)) return fail(ctx, T3D_E_INVALID, "t3d_submit_lights: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_lights: not between frame_begin and frame_execute");
+    const uint32_t off = (uint32_t)ctx->hLights.n;
+    CU(ctx->hLights.reserve(off + n));
+    for (uint32_t i = 0; i < n; i++) {
+        t3d_light L = lights[i];
+        if (L.type > T3D_LIGHT_VOLUME) return fail(ctx, T3D_E_INVALID, "t3d_submit_lights: unknown light type");
+        if (L.type == T3D_LIGHT_VOLUME) {
+            auto it = ctx->volumeIndex.find(L.volume);
+            if (it == ctx->volumeIndex.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_lights: unknown light volume");
+            L.volume = it->second;
+        }
+        ctx->hLights.p[off + i] = L;
+    }
+    ctx->hLights.n = off + n;
+    *list_id = (uint32_t)ctx->lightLists.size();
+    ctx->lightLists.push_back(LightList{off, n});
+    return T3D_OK;
+}
+
+int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset) {
+    if (!ctx || !offset || (n && !matrices16)) return fail(ctx, T3D_E_INVALID, "t3d_submit_bones: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_bones: not between frame_begin and frame_execute");
+    const size_t off = ctx->hBones.n;
+    CU(ctx->hBones.reserve(off + (size_t)n * 16));
+    memcpy(ctx->hBones.p + off, matrices16, (size_t)n * 64);
+    ctx->hBones.n = off + (size_t)n * 16;
+    *offset = (uint32_t)(off / 16);
+    return T3D_OK;
+}
+
+int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
+    if (!ctx || (n && !draws)) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_draws: not between frame_begin and frame_execute");
+    if (ctx->hDraws.n + n >= (1u << (32 - BIN_BITS))) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: too many draws in one frame");
+    CU(ctx->hDraws.reserve(ctx->hDraws.n + n));
+    CU(ctx->hVbase.reserve(ctx->hDraws.n + n + 1));
+    CU(ctx->hTbase.reserve(ctx->hDraws.n + n + 1));
+    for (uint32_t i = 0; i < n; i++) {
+        const t3d_draw& in = draws[i];
+        auto it = ctx->meshes.find(in.mesh_id);
+        if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_draws: unknown mesh");
+        const Mesh& m = it->second;
+        if (in.part >= m.parts.size()) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: part index out of range");
+        if (in.light_list >= ctx->lightLists.size()) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: unknown light list");
+        if (in.sort_mode > T3D_SORT_NONE || in.lighting_mode > T3D_LIGHTING_DOUBLE_SIDED || in.light_volume_mode > T3D_LV_OFF)
+            return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: enum out of range");
+        const PartInfo& pi = m.parts[in.part];
+        uint32_t flags = in.flags;
+        if (flags & T3D_DRAW_SKINNED) {
+            if (!m.wgt) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: skinned draw of a mesh without weights");
+            if (in.bone_count <= m.maxJoint || (size_t)in.bone_offset + in.bone_count > ctx->hBones.n / 16)
+                return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: bone span does not cover the mesh's joints");
+            flags &= ~(uint32_t)T3D_DRAW_DEPTH_UNBILLBOARDED;   // the reference never writes it for skinned models (model.go:800)
+        }
+        if ((uint64_t)ctx->vAcc + pi.nv > 0xFFFFFFF0ull || (uint64_t)ctx->tAcc + (pi.triEnd - pi.triStart) > 0x55555550ull)
+            return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: frame exceeds 32-bit arena indexing");
+        DrawRec R;
+        memset(&R, 0, sizeof R);
+        R.pos = m.pos; R.nrm = m.nrm; R.uv = m.uv; R.col = m.col; R.wgt = m.wgt; R.jnt = m.jnt; R.ninf = m.ninf;
+        R.idx = m.idx; R.ctr = m.ctr; R.keyPos = m.keyPos; R.keyNrm = m.keyNrm; R.keyW = m.keyW;
+        R.a0 = pi.a0; R.nv = pi.nv; R.vbase = ctx->vAcc;
+        R.t0 = pi.triStart; R.nt = pi.triEnd - pi.triStart; R.tbase = ctx->tAcc;
+        R.flags = flags; R.nKeys = m.nKeys; R.keyStride = m.nVertsPad;
+        R.boneOffset = in.bone_offset;
+        const LightList& ll = ctx->lightLists[in.light_list];
+        R.lightIn = ll.off; R.lightCount = ll.count; R.lightU = ctx->luAcc;
+        R.sortMode = (flags & T3D_DRAW_HAS_MATERIAL) ? in.sort_mode : (uint8_t)T3D_SORT_BACK_TO_FRONT;   // camera.go:1540-1543
+        R.lightingMode = in.lighting_mode; R.lvMode = in.light_volume_mode;
+        memcpy(R.transform, in.transform, 64);
+        memcpy(R.worldRot, in.world_rotation, 64);
+        memcpy(R.color, in.color, 16);
+        R.srcW = in.src_w; R.srcH = in.src_h; R.maxSpan = m.maxSpan;
+        if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.count; ctx->anyLit = true; }
+        if (flags & T3D_DRAW_SKINNED) ctx->anySkinned = true;
+        if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) ctx->anyUnbill = true;
+        ctx->hVbase.p[ctx->hDraws.n] = ctx->vAcc;
+        ctx->hTbase.p[ctx->hDraws.n] = ctx->tAcc;
+        ctx->vAcc += pi.nv; ctx->tAcc += R.nt;
+        ctx->hDraws.p[ctx->hDraws.n++] = R;
+        ctx->drawTotalTris.push_back(R.nt);
+        ctx->drawContinue.push_back((flags & T3D_DRAW_CONTINUE_FLUSH) ? 1 : 0);
+    }
+    return T3D_OK;
+}
+
+// tileFirst[b] = largest d with base[d] <= b*tile (b = 0..nTiles)
+static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, uint32_t tile, uint32_t* out) {
+    uint32_t d = 0;
+    for (uint32_t b = 0; b <= nTiles; b++) {
+        const uint64_t slot = (uint64_t)b * tile;
+        while (d + 1 < nDraws && base[d + 1] <= slot) d++;
+        out[b] = d;
+    }
+}
+
+int t3d_frame_execute(t3d_ctx* ctx) {
+    if (!ctx) return T3D_E_INVALID;
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_execute: no open frame");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t nDraws = (uint32_t)ctx->hDraws.n;
+    const uint32_t totalV = ctx->vAcc, totalT = ctx->tAcc;
+    ctx->launches = 0;
+    ctx->executed = true;
+    CU(cudaEventRecord(ctx->ev[0], s));
+    if (nDraws == 0 || totalT == 0) {
+        for (int i = 1; i < 7; i++) CU(cudaEventRecord(ctx->ev[i], s));
+        ctx->h2dBytes = 0;
+        return T3D_OK;
+    }
+    const uint32_t totalGroups = totalV / 4;
+    const uint32_t nTilesV = (totalGroups + 255) / 256, nTilesT = (totalT + 255) / 256;
+    ctx->hVbase.p[nDraws] = totalV; ctx->hVbase.n = nDraws + 1;
+    ctx->hTbase.p[nDraws] = totalT; ctx->hTbase.n = nDraws + 1;
+    CU(ctx->hTileV.resize(nTilesV + 1));
+    CU(ctx->hTileT.resize(nTilesT + 1));
+    build_tiles(ctx->hVbase.p, nDraws, nTilesV, 1024, ctx->hTileV.p);
+    build_tiles(ctx->hTbase.p, nDraws, nTilesT, 256, ctx->hTileT.p);
+
+    const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
+    const SortPlan plan = sort_plan(totalT, nDraws);
+
+    // arenas
+    CU(ctx->dDraws.ensure(sizeof(DrawRec) * nDraws));
+    CU(ctx->dVbase.ensure(4ull * (nDraws + 1)));
+    CU(ctx->dTbase.ensure(4ull * (nDraws + 1)));
+    CU(ctx->dTileV.ensure(4ull * (nTilesV + 1)));
+    CU(ctx->dTileT.ensure(4ull * (nTilesT + 1)));
+    CU(ctx->dLightsIn.ensure(sizeof(t3d_light) * std::max<size_t>(ctx->hLights.n, 1)));
+    CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
+    CU(ctx->dBones.ensure(4ull * std::max<size_t>(ctx->hBones.n, 16)));
+    CU(ctx->dStats.ensure(sizeof(DrawStat) * nDraws));
+    CU(ctx->dClip.ensure(16ull * std::max(totalV, 4u)));
+    CU(ctx->dLight.ensure(16ull * std::max(ctx->anyLit ? totalV : 4u, 4u)));
+    CU(ctx->dWpos.ensure(16ull * std::max(ctx->anySkinned ? totalV : 4u, 4u)));
+    CU(ctx->dUnbill.ensure(4ull * std::max(ctx->anyUnbill ? totalV : 4u, 4u)));
+    CU(ctx->dTnrm.ensure(16ull * std::max(normals ? totalV : 4u, 4u)));
+    CU(ctx->dTdepth.ensure(4ull * totalT));
+    CU(ctx->dTdraw.ensure(4ull * totalT));
+    CU(ctx->dKeys0.ensure(4ull * totalT));
+    CU(ctx->dKeysA.ensure(4ull * totalT)); CU(ctx->dKeysB.ensure(4ull * totalT));
+    CU(ctx->dValsA.ensure(4ull * totalT)); CU(ctx->dValsB.ensure(4ull * totalT));
+    CU(ctx->dSortScratch.ensure(sort_scratch_bytes(plan)));
+    CU(ctx->dCount.ensure(256));
+    CU(ctx->dColor.ensure(144ull * totalT));
+    CU(ctx->dDepth.ensure(144ull * totalT));
+    CU(ctx->dNormal.ensure(normals ? 144ull * totalT : 16));
+    CU(ctx->dTriIds.ensure(4ull * totalT));
+    if (ctx->volumesDirty) {
+        CU(ctx->dVolumes.ensure(sizeof(VolumeU) * std::max<size_t>(ctx->volumes.size(), 1)));
+        if (!ctx->volumes.empty())
+            CU(cudaMemcpyAsync(ctx->dVolumes.p, ctx->volumes.data(), sizeof(VolumeU) * ctx->volumes.size(), cudaMemcpyHostToDevice, s));
+        ctx->volumesDirty = false;
+    }
+
+    // uniforms up
+    CU(cudaMemcpyAsync(ctx->dDraws.p, ctx->hDraws.p, sizeof(DrawRec) * nDraws, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->dVbase.p, ctx->hVbase.p, 4ull * (nDraws + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->dTbase.p, ctx->hTbase.p, 4ull * (nDraws + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->dTileV.p, ctx->hTileV.p, 4ull * (nTilesV + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->dTileT.p, ctx->hTileT.p, 4ull * (nTilesT + 1), cudaMemcpyHostToDevice, s));
+    if (ctx->hLights.n) CU(cudaMemcpyAsync(ctx->dLightsIn.p, ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, cudaMemcpyHostToDevice, s));
+    if (ctx->hBones.n) CU(cudaMemcpyAsync(ctx->dBones.p, ctx->hBones.p, 4ull * ctx->hBones.n, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(ctx->ev[1], s));
+
+    // K0 + K1
+    launch_prep_draws(s, ctx->dDraws.as<DrawRec>(), nDraws, ctx->fc, ctx->dLightsIn.as<t3d_light>(), ctx->dLightsU.as<LightU>(), ctx->dStats.as<DrawStat>());
+    CU(cudaEventRecord(ctx->ev[2], s));
+    launch_vertex(s, ctx->dDraws.as<DrawRec>(), ctx->dVbase.as<uint32_t>(), ctx->dTileV.as<uint32_t>(), totalGroups, ctx->fc,
+                  ctx->dLightsU.as<LightU>(), ctx->dBones.as<float>(), ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
+                  ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
+    ctx->launches += 2;
+    CU(cudaEventRecord(ctx->ev[3], s));
+    // K2
+    launch_cull(s, ctx->dDraws.as<DrawRec>(), ctx->dTbase.as<uint32_t>(), ctx->dTileT.as<uint32_t>(), totalT, ctx->fc,
+                ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), ctx->dStats.as<DrawStat>());
+    ctx->launches += 1;
+    CU(cudaEventRecord(ctx->ev[4], s));
+    // K3 + sort
+    launch_keys(s, ctx->dDraws.as<DrawRec>(), ctx->dStats.as<DrawStat>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), totalT, ctx->dKeys0.as<uint32_t>());
+    ctx->launches += 1;
+    ctx->launches += sort_pairs(s, plan, ctx->dKeys0.as<uint32_t>(), ctx->dKeysA.as<uint32_t>(), ctx->dValsA.as<uint32_t>(),
+                                ctx->dKeysB.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dSortScratch.p, ctx->dCount.as<uint32_t>(),
+                                &ctx->sortedKeys, &ctx->sortedVals);
+    CU(cudaEventRecord(ctx->ev[5], s));
+    // K4
+    launch_emit(s, ctx->dDraws.as<DrawRec>(), ctx->sortedKeys, ctx->sortedVals, ctx->dCount.as<uint32_t>(), totalT, ctx->fc,
+                ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+                ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
+    ctx->launches += 1;
+    CU(cudaEventRecord(ctx->ev[6], s));
+    CU(cudaGetLastError());
+    ctx->h2dBytes = sizeof(DrawRec) * (uint64_t)nDraws + 8ull * (nDraws + 1) + 4ull * (nTilesV + 1) + 4ull * (nTilesT + 1) +
+                    sizeof(t3d_light) * (uint64_t)ctx->hLights.n + 4ull * ctx->hBones.n;
+
+    // algorithmic bytes of the fused vertex kernel: pos 12 [+ normal 12] -> clip 16 [+ light 16],
+    // skinned adds weights 16 + joints 8 + world position 16.
+    uint64_t bytes = 0;
+    for (uint32_t i = 0; i < nDraws; i++) {
+        const DrawRec& R = ctx->hDraws.p[i];
+        uint64_t per = 12 + 16;
+        if (R.flags & T3D_DRAW_LIT) per += 12 + 16;
+        if (R.flags & T3D_DRAW_SKINNED) per += ((R.flags & T3D_DRAW_LIT) ? 0 : 12) + 16 + 8 + 16;
+        bytes += per * R.nv;
+    }
+    ctx->vertexKernelBytes = bytes;
+    return T3D_OK;
+}
+
+static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_timings* tm) {
+    if (!ctx || !out) return fail(ctx, T3D_E_INVALID, "t3d_frame_results: NULL argument");
+    if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_results: frame not executed");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t nDraws = (uint32_t)ctx->hDraws.n;
+    const uint32_t totalT = ctx->tAcc;
+    const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
+    memset(out, 0, sizeof *out);
+    out->n_draws = nDraws;
+    CU(ctx->hResults.resize(nDraws));
+    ctx->downloadMs = 0;
+    ctx->d2hBytes = 0;
+    uint64_t nVerts = 0;
+    if (nDraws && totalT) {
+        CU(ctx->hStats.resize(nDraws));
+        CU(ctx->hCount.resize(1));
+        CU(cudaMemcpyAsync(ctx->hStats.p, ctx->dStats.p, sizeof(DrawStat) * nDraws, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(ctx->hCount.p, ctx->dCount.p, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        ctx->d2hBytes += sizeof(DrawStat) * (uint64_t)nDraws + 4;
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < nDraws; i++) {
+            const DrawStat& st = ctx->hStats.p[i];
+            t3d_draw_result& r = ctx->hResults.p[i];
+            r.first_vertex = 3 * acc;
+            r.vertex_count = 3 * st.survivors;
+            r.total_tris = ctx->drawTotalTris[i];
+            if (st.survivors) { memcpy(&r.min_depth, &st.minBits, 4); memcpy(&r.max_depth, &st.maxBits, 4); }
+            else { r.min_depth = FLT_MAX; r.max_depth = -FLT_MAX; }
+            acc += st.survivors;
+        }
+        if (acc != ctx->hCount.p[0]) return fail(ctx, T3D_E_CUDA, "internal: survivor count mismatch between cull and sort");
+        nVerts = 3 * acc;
+    } else {
+        CU(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < nDraws; i++) {
+            t3d_draw_result& r = ctx->hResults.p[i];
+            r.first_vertex = 0; r.vertex_count = 0; r.total_tris = ctx->drawTotalTris[i]; r.min_depth = FLT_MAX; r.max_depth = -FLT_MAX;
+        }
+    }
+    ctx->nVerticesOut = nVerts;
+    out->n_vertices = nVerts;
+    out->draws = ctx->hResults.p;
+
+    // identity index table (camera.go:1816), sized for the largest flush
+    uint64_t maxFlush = 0, cur = 0;
+    for (uint32_t i = 0; i < nDraws; i++) {
+        if (!ctx->drawContinue[i]) cur = 0;
+        cur += ctx->hResults.p[i].vertex_count;
+        maxFlush = std::max(maxFlush, cur);
+    }
+    if (ctx->hIndex.n < maxFlush || ctx->hIndex.n == 0) {
+        size_t old = ctx->hIndex.n;
+        size_t want = std::max<size_t>(std::max<uint64_t>(maxFlush, 65536), old);
+        CU(ctx->hIndex.resize(want));
+        for (size_t i = old; i < want; i++) ctx->hIndex.p[i] = (uint16_t)i;
+    }
+    out->index_list = ctx->hIndex.p;
+
+    if (download) {
+        if (nVerts) {
+            cudaEvent_t e0 = ctx->ev[7], e1 = ctx->ev[8];
+            CU(ctx->hColor.resize(nVerts)); CU(ctx->hDepth.resize(nVerts)); CU(ctx->hTriIds.resize(nVerts / 3));
+            if (normals) CU(ctx->hNormal.resize(nVerts));
+            CU(cudaEventRecord(e0, s));
+            CU(cudaMemcpyAsync(ctx->hColor.p, ctx->dColor.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(ctx->hDepth.p, ctx->dDepth.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            if (normals) CU(cudaMemcpyAsync(ctx->hNormal.p, ctx->dNormal.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(ctx->hTriIds.p, ctx->dTriIds.p, (nVerts / 3) * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(e1, s));
+            CU(cudaStreamSynchronize(s));
+            cudaEventElapsedTime(&ctx->downloadMs, e0, e1);
+            ctx->d2hBytes += nVerts * sizeof(t3d_vertex) * (normals ? 3 : 2) + (nVerts / 3) * 4;
+        }
+        out->color_list = ctx->hColor.p; out->depth_list = ctx->hDepth.p;
+        out->normal_list = normals ? ctx->hNormal.p : nullptr;
+        out->tri_ids = ctx->hTriIds.p;
+    } else {
+        out->color_list = ctx->dColor.as<t3d_vertex>(); out->depth_list = ctx->dDepth.as<t3d_vertex>();
+        out->normal_list = normals ? ctx->dNormal.as<t3d_vertex>() : nullptr;
+        out->tri_ids = ctx->dTriIds.as<uint32_t>();
+    }
+    if (tm) {
+        memset(tm, 0, sizeof *tm);
+        cudaEventElapsedTime(&tm->upload_ms, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&tm->prep_ms, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&tm->vertex_ms, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&tm->cull_ms, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&tm->sort_ms, ctx->ev[4], ctx->ev[5]);
+        cudaEventElapsedTime(&tm->emit_ms, ctx->ev[5], ctx->ev[6]);
+        cudaEventElapsedTime(&tm->total_ms, ctx->ev[1], ctx->ev[6]);
+        tm->download_ms = ctx->downloadMs;
+    }
+    ctx->haveResults = true;
+    return T3D_OK;
+}
+
+int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, true, out, timings); }
+int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, false, out, timings); }
+
+// ---- introspection ---------------------------------------------------------------------------------
+
+int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end, float* clip4, float* light4) {
+    if (!ctx) return T3D_E_INVALID;
+    if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_debug_read_draw_vertices: frame not executed");
+    if (draw >= ctx->hDraws.n) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: draw out of range");
+    CU(cudaSetDevice(ctx->device));
+    const DrawRec& R = ctx->hDraws.p[draw];
+    if (vtx_start > vtx_end) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: bad range");
+    const size_t n = vtx_end - vtx_start;
+    if (n == 0) return T3D_OK;
+    if (vtx_start < R.a0 || vtx_end > R.a0 + R.nv) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: range outside the part's vertices");
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t slot = R.vbase + (vtx_start - R.a0);
+    if (clip4) CU(cudaMemcpy(clip4, ctx->dClip.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
+    if (light4) {
+        if (R.flags & T3D_DRAW_LIT) CU(cudaMemcpy(light4, ctx->dLight.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
+        else memset(light4, 0, n * 16);
+    }
+    return T3D_OK;
+}
+
+int t3d_debug_last_launch_count(t3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* t3d_debug_stream(t3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t t3d_debug_vertex_kernel_bytes(t3d_ctx* ctx) { return ctx ? ctx->vertexKernelBytes : 0; }
+int t3d_debug_frame_bytes(t3d_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+    if (!ctx) return T3D_E_INVALID;
+    if (h2d) *h2d = ctx->h2dBytes;
+    if (d2h) *d2h = ctx->d2hBytes;
+    return T3D_OK;
+}
+
+}  // extern "C"

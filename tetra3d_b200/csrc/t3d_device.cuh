@@ -1,0 +1,120 @@
+// t3d_device.cuh -- device-side records and float32 math for the geometry stage.
+//
+// Everything that feeds a cull decision, a depth key or a bin index is computed in float32 with
+// separate multiply and add (the translation units are built with -fmad=false and IEEE div/sqrt),
+// in the operand order of the reference, so the draw lists come out bit-identical to the Go path:
+// matrix_amd64.s:4-81 uses MULPS+ADDPS, Go/amd64 (GOAMD64=v1) never fuses.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "t3d_math.h"
+#include <stddef.h>
+
+namespace t3d {
+
+// ---- records ----------------------------------------------------------------------------------
+
+// Frame constants (camera.go:1329-1341, 1603; world fog camera.go:1784-1812).
+struct FrameConst {
+    float vp[16];
+    float view[16];
+    float camPos[3];
+    float camUp[3];
+    float nearP, farP;
+    float camW, camH, halfW, halfH;
+    float depthMargin;      // (far - near) * DepthMargin          camera.go:1339
+    float camSpread;        // far - near + 2*margin               camera.go:1341
+    float snapping;
+    uint32_t camFlags;      // T3D_CAM_*
+    int32_t worldPresent, fogOn, fogMode;
+    float fogColor[3];
+    float fogRange[2];
+};
+
+// Resolved light as seen by one draw: light.beginRender/beginModel products (light.go:110-112,
+// 175-189, 322-330) plus the per-draw range skip of camera.go:1625-1629.
+struct LightU {
+    uint32_t type;          // T3D_LIGHT_*, or LIGHT_SKIP
+    float color[3];
+    float energy;
+    float wpos[3];          // PointLight.workingPosition
+    float range, range2;    // lightRange, lightRangeSquared
+    float fwd[3];           // DirectionalLight.workingForward
+    uint32_t volume;        // index into the context's volume table
+    uint32_t pad[2];
+};
+static const uint32_t LIGHT_SKIP = 0xFFu;
+
+// LightVolume on the device.
+struct VolumeU {
+    float dimMin[3], dimMax[3];
+    float cellSize[3];
+    int32_t cellCount[3];
+    float offset[3];
+    float bias[3];
+    const float* cells;
+};
+
+// One render(rp): host-resolved inputs first, then the fields k_prep_draws derives.
+struct __align__(16) DrawRec {
+    // ---- resolved by the host at submit ----
+    const float*    pos;        // packed float3, 16B-aligned, padded to a multiple of 4 vertices
+    const float*    nrm;
+    const float*    uv;         // float2
+    const float*    col;        // float4 or nullptr
+    const float*    wgt;        // float4 or nullptr
+    const uint16_t* jnt;        // ushort4 or nullptr
+    const uint8_t*  ninf;       // or nullptr
+    const uint32_t* idx;        // 3 per triangle
+    const float*    ctr;        // 3 per triangle
+    const float*    keyPos;     // k * nMeshVertsPadded * 3
+    const float*    keyNrm;
+    const float*    keyW;       // k
+    uint32_t a0;                // first mesh vertex of the aligned range (multiple of 4)
+    uint32_t nv;                // aligned vertex count (multiple of 4)
+    uint32_t vbase;             // first slot in the per-frame vertex arenas (multiple of 4)
+    uint32_t t0;                // first mesh triangle
+    uint32_t nt;                // triangle count
+    uint32_t tbase;             // first slot in the per-frame triangle arenas
+    uint32_t flags;             // T3D_DRAW_*
+    uint32_t nKeys;
+    uint32_t keyStride;         // padded mesh vertex count (floats3 per key)
+    uint32_t boneOffset;
+    uint32_t lightIn;           // first t3d_light of the draw's list
+    uint32_t lightCount;
+    uint32_t lightU;            // first LightU slot of this draw
+    uint8_t  sortMode, lightingMode, lvMode, pad0;
+    uint32_t padA[2];           // keeps the float4-loaded arrays below 16B-aligned
+    float transform[16];
+    float worldRot[16];
+    float color[4];
+    float srcW, srcH;
+    float maxSpan;
+    float pad1;
+    // ---- derived on the device (model.go:616-708) ----
+    float mvp[16];              // base * vp (static); skinned draws use FrameConst.vp
+    float unbill[4];            // column 2 of modelTransform * vp       model.go:702, 801
+    float nrmRot[12];           // mvJustRForNormals columns 0..2, rows 0..3   model.go:707, 815-817
+    float invCam[3];            // invertedCamPos                        model.go:629-630
+    float pad2;
+};
+
+static_assert(offsetof(DrawRec, transform) % 16 == 0 && offsetof(DrawRec, worldRot) % 16 == 0 &&
+              offsetof(DrawRec, color) % 16 == 0 && offsetof(DrawRec, mvp) % 16 == 0 &&
+              offsetof(DrawRec, unbill) % 16 == 0 && offsetof(DrawRec, nrmRot) % 16 == 0 &&
+              sizeof(DrawRec) % 16 == 0, "DrawRec arrays are read with 128-bit loads");
+static_assert(sizeof(LightU) == 64, "LightU is read as four float4");
+
+// Per-draw reduction state written by the cull kernel.
+struct DrawStat {
+    uint32_t minBits;           // float bits of minDepth (depth >= 0, so uint order == float order)
+    uint32_t maxBits;
+    uint32_t survivors;
+    uint32_t pad;
+};
+
+static const uint32_t KEY_CULLED = 0xFFFFFFFFu;
+static const int BIN_BITS = 9;      // 512 bins, sortingTriangles.go:166-168
+static const int BIN_COUNT = 512;
+
+}  // namespace t3d

@@ -1,0 +1,639 @@
+// tetra3d.cpp -- host-side mirror of the Tetra3D API (see tetra3d.hpp).  Build with -ffp-contract=off.
+#include <functional>
+#include <stdexcept>
+#include "tetra3d.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+namespace tetra3d {
+
+using namespace t3d;
+
+static uint64_t g_nextMeshId = 1;
+
+// ---- math32 wrappers (math32/math32.go): float64 libm rounded to float32 ----------------------------
+static inline float m32_tan(float x) { return (float)std::tan((double)x); }
+static inline float m32_cos(float x) { return (float)std::cos((double)x); }
+static inline float m32_sin(float x) { return (float)std::sin((double)x); }
+static inline float m32_atan(float x) { return (float)std::atan((double)x); }
+static const float M32_PI = (float)3.14159265358979323846;
+
+Matrix4 NewMatrix4() { return m4_identity(); }
+Matrix4 NewMatrix4Translate(float x, float y, float z) { Matrix4 r = m4_identity(); r.m[3][0] = x; r.m[3][1] = y; r.m[3][2] = z; return r; }
+Matrix4 NewMatrix4Scale(float x, float y, float z) { return m4_scale(x, y, z); }
+Matrix4 NewMatrix4Rotate(float x, float y, float z, float angle) {       // matrix.go:100-128
+    if (x == 0 && y == 0 && z == 0) y = 1;
+    Matrix4 mat = m4_identity();
+    Vector3 v = v3_unit(v3(x, y, z));
+    float s = m32_sin(angle), c = m32_cos(angle), m = 1 - c;
+    mat.m[0][0] = m * v.X * v.X + c;
+    mat.m[0][1] = m * v.X * v.Y + v.Z * s;
+    mat.m[0][2] = m * v.Z * v.X - v.Y * s;
+    mat.m[1][0] = m * v.X * v.Y - v.Z * s;
+    mat.m[1][1] = m * v.Y * v.Y + c;
+    mat.m[1][2] = m * v.Y * v.Z + v.X * s;
+    mat.m[2][0] = m * v.Z * v.X + v.Y * s;
+    mat.m[2][1] = m * v.Y * v.Z - v.X * s;
+    mat.m[2][2] = m * v.Z * v.Z + c;
+    return mat;
+}
+Matrix4 NewProjectionMatrix4Perspective(float fovy, float near_, float far_, float viewWidth, float viewHeight) {   // matrix.go:588-604
+    float aspect = viewWidth / viewHeight;
+    float t = m32_tan(fovy * M32_PI / 360);
+    float b = -t;
+    float r = t * aspect;
+    float l = -r;
+    Matrix4 m; std::memset(&m, 0, sizeof m);
+    m.m[0][0] = (2 * near_) / (r - l); m.m[0][2] = (r + l) / (r - l);
+    m.m[1][1] = (2 * near_) / (t - b); m.m[1][2] = (t + b) / (t - b);
+    m.m[2][2] = -((far_ + near_) / (far_ - near_)); m.m[2][3] = -((2 * far_ * near_) / (far_ - near_));
+    m.m[3][2] = -1;
+    return m;
+}
+Matrix4 NewProjectionMatrix4Orthographic(float near_, float far_, float right, float left, float top, float bottom) {   // matrix.go:609-616
+    Matrix4 m; std::memset(&m, 0, sizeof m);
+    m.m[0][0] = 2 / (right - left);
+    m.m[1][1] = 2 / (top - bottom);
+    m.m[2][2] = -2 / (far_ - near_);
+    m.m[3][3] = 1;
+    return m;
+}
+bool Matrix4Equals(const Matrix4& a, const Matrix4& b) {                  // matrix.go:511-522
+    const float eps = 0.0001f;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) if (std::fabs(a.m[i][j] - b.m[i][j]) > eps) return false;
+    return true;
+}
+static bool isIdentity(const Matrix4& a) { return Matrix4Equals(a, m4_identity()); }
+
+// ---- Dimensions / Mesh ------------------------------------------------------------------------------
+float Dimensions::MaxSpan() const { return v3_magnitude(v3_sub(Max, Min)); }
+Vector3 Dimensions::Center() const { return v3((Max.X + Min.X) / 2, (Max.Y + Min.Y) / 2, (Max.Z + Min.Z) / 2); }
+
+std::shared_ptr<Material> NewMaterial(const std::string& name) { auto m = std::make_shared<Material>(); m->name = name; return m; }
+
+std::shared_ptr<Mesh> NewMesh(const std::string& name) { auto m = std::make_shared<Mesh>(); m->Name = name; m->id = g_nextMeshId++; return m; }
+
+std::shared_ptr<MeshPart> Mesh::AddMeshPart(std::shared_ptr<Material> mat, int vs, int ve, int ts, int te) {
+    auto p = std::make_shared<MeshPart>();
+    p->mesh = this; p->material = std::move(mat);
+    p->VertexIndexStart = vs; p->VertexIndexEnd = ve; p->TriangleStart = ts; p->TriangleEnd = te;
+    MeshParts.push_back(p);
+    return p;
+}
+void Mesh::UpdateDimensions() {                                           // mesh.go:719-751
+    dimensions.Min = v3(FLT_MAX, FLT_MAX, FLT_MAX);
+    dimensions.Max = v3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int i = 0; i < VertexCount(); i++) {
+        float x = VertexPositions[3 * i], y = VertexPositions[3 * i + 1], z = VertexPositions[3 * i + 2];
+        if (dimensions.Min.X > x) dimensions.Min.X = x;
+        if (dimensions.Min.Y > y) dimensions.Min.Y = y;
+        if (dimensions.Min.Z > z) dimensions.Min.Z = z;
+        if (dimensions.Max.X < x) dimensions.Max.X = x;
+        if (dimensions.Max.Y < y) dimensions.Max.Y = y;
+        if (dimensions.Max.Z < z) dimensions.Max.Z = z;
+    }
+}
+void Mesh::RecalculateCenters() {                                         // mesh.go:1980-1982
+    const int nt = TriangleTotal();
+    TriangleCenters.resize((size_t)nt * 3);
+    for (int t = 0; t < nt; t++) {
+        const float* a = &VertexPositions[3 * (size_t)TriangleIndices[3 * t]];
+        const float* b = &VertexPositions[3 * (size_t)TriangleIndices[3 * t + 1]];
+        const float* c = &VertexPositions[3 * (size_t)TriangleIndices[3 * t + 2]];
+        TriangleCenters[3 * t + 0] = (a[0] + b[0] + c[0]) / 3;
+        TriangleCenters[3 * t + 1] = (a[1] + b[1] + c[1]) / 3;
+        TriangleCenters[3 * t + 2] = (a[2] + b[2] + c[2]) / 3;
+    }
+}
+// calculateNormal (vector.go) + Mesh.AutoNormal (mesh.go:755-764)
+void Mesh::AutoNormal() {
+    const int nt = TriangleTotal();
+    for (int t = 0; t < nt; t++) {
+        uint32_t ia = TriangleIndices[3 * t], ib = TriangleIndices[3 * t + 1], ic = TriangleIndices[3 * t + 2];
+        Vector3 p1 = v3(VertexPositions[3 * ia], VertexPositions[3 * ia + 1], VertexPositions[3 * ia + 2]);
+        Vector3 p2 = v3(VertexPositions[3 * ib], VertexPositions[3 * ib + 1], VertexPositions[3 * ib + 2]);
+        Vector3 p3 = v3(VertexPositions[3 * ic], VertexPositions[3 * ic + 1], VertexPositions[3 * ic + 2]);
+        Vector3 n = v3_unit(v3_cross(v3_sub(p2, p1), v3_sub(p3, p2)));
+        for (uint32_t v : {ia, ib, ic}) { VertexNormals[3 * v] = n.X; VertexNormals[3 * v + 1] = n.Y; VertexNormals[3 * v + 2] = n.Z; }
+    }
+}
+void Mesh::SetShapeKeyWeights(const std::vector<float>& w) {
+    if (w.size() != ShapeKeyWeights.size()) throw T3DError(T3D_E_INVALID, "SetShapeKeyWeights: key count mismatch");
+    ShapeKeyWeights = w; shapeKeyWeightGeneration++;
+}
+
+// mesh.go:1251-1342: vertex and index tables of the unit cube
+std::shared_ptr<Mesh> NewCubeMesh(float w, float h, float d) {
+    w /= 2; h /= 2; d /= 2;
+    auto mesh = NewMesh("Cube");
+    const float V[24][5] = {
+        {-w, h, -d, 0, 0}, {w, h, d, 1, 1}, {w, h, -d, 1, 0}, {-w, h, d, 0, 1},           // top
+        {w, -h, -d, 1, 0}, {w, -h, d, 1, 1}, {-w, -h, -d, 0, 0}, {-w, -h, d, 0, 1},       // bottom
+        {-w, h, d, 0, 0}, {w, -h, d, 1, 1}, {w, h, d, 1, 0}, {-w, -h, d, 0, 1},           // front
+        {w, h, -d, 1, 0}, {w, -h, -d, 1, 1}, {-w, h, -d, 0, 0}, {-w, -h, -d, 0, 1},       // back
+        {w, h, -d, 1, 0}, {w, h, d, 1, 1}, {w, -h, -d, 0, 0}, {w, -h, d, 0, 1},           // right
+        {-w, -h, -d, 0, 0}, {-w, h, d, 1, 1}, {-w, h, -d, 1, 0}, {-w, -h, d, 0, 1},       // left
+    };
+    const uint32_t I[36] = {0, 1, 2, 3, 1, 0, 4, 5, 6, 6, 5, 7, 8, 9, 10, 11, 9, 8,
+                            12, 13, 14, 14, 13, 15, 16, 17, 18, 18, 17, 19, 20, 21, 22, 23, 21, 20};
+    for (auto& v : V) {
+        mesh->VertexPositions.insert(mesh->VertexPositions.end(), {v[0], v[1], v[2]});
+        mesh->VertexNormals.insert(mesh->VertexNormals.end(), {0.f, 0.f, 0.f});
+        mesh->VertexUVs.insert(mesh->VertexUVs.end(), {v[3], v[4]});
+    }
+    mesh->TriangleIndices.assign(I, I + 36);
+    mesh->AddMeshPart(NewMaterial("Cube"), 0, 24, 0, 11);
+    mesh->RecalculateCenters();
+    mesh->UpdateDimensions();
+    mesh->AutoNormal();
+    return mesh;
+}
+
+// ---- Node ---------------------------------------------------------------------------------------------
+Node::Node(const std::string& n) : name(n) { rotation = m4_identity(); cachedTransform = m4_identity(); }
+
+Matrix4 Node::Transform() {                                               // node.go:572-608
+    if (!isTransformDirty) return cachedTransform;
+    Matrix4 transform = NewMatrix4Scale(scale.X, scale.Y, scale.Z);
+    transform = m4_mult(transform, rotation);
+    transform = m4_mult(transform, NewMatrix4Translate(position.X, position.Y, position.Z));
+    if (parent) transform = m4_mult(transform, parent->Transform());
+    cachedTransform = transform;
+    isTransformDirty = false;
+    onTransformUpdate();
+    for (auto& c : children) c->Transform();
+    return transform;
+}
+void Node::dirtyTransform() { for (auto& c : children) c->dirtyTransform(); isTransformDirty = true; }
+Vector3 Node::WorldPosition() { Matrix4 t = Transform(); return v3(t.m[3][0], t.m[3][1], t.m[3][2]); }
+Matrix4 Node::WorldRotation() {                                           // node.go:916-938
+    bool need = false;
+    for (Node* p = parent; p; p = p->parent) if (!isIdentity(p->rotation)) { need = true; break; }
+    if (need) return m4_decompose_rotation(Transform());
+    return rotation;
+}
+void Node::SetLocalPosition(float x, float y, float z) { position = v3(x, y, z); dirtyTransform(); }
+void Node::SetLocalScale(float x, float y, float z) { scale = v3(x, y, z); dirtyTransform(); }
+void Node::SetLocalRotation(const Matrix4& r) { rotation = r; dirtyTransform(); }
+void Node::AddChildren(const std::vector<std::shared_ptr<Node>>& kids) {
+    for (auto& k : kids) { k->parent = this; children.push_back(k); k->dirtyTransform(); }
+}
+void Node::SetVisible(bool v, bool recursive) { if (recursive) for (auto& c : children) c->SetVisible(v, true); visible = v; }
+void Node::ForEachChild(const std::function<void(Node*)>& f) { for (auto& c : children) { f(c.get()); c->ForEachChild(f); } }
+
+// ---- Model --------------------------------------------------------------------------------------------
+Model::Model(const std::string& n, std::shared_ptr<Mesh> m) : Node(n), mesh(std::move(m)) {
+    if (mesh) sphereRadius = mesh->dimensions.MaxSpan() / 2;            // model.go:83-87
+}
+void Model::onTransformUpdate() {                                         // model.go:142-182
+    if (!mesh) return;
+    Vector3 pos, sc; Matrix4 rot;
+    m4_decompose(cachedTransform, pos, sc, rot);
+    Vector3 center = v3(0, 0, 0);
+    if (!skinned) center = mesh->dimensions.Center();
+    center = m4_multvec(rot, center);
+    pos.X += center.X * sc.X;
+    pos.Y += center.Y * sc.Y;
+    pos.Z += center.Z * sc.Z;
+    spherePosition = pos;
+    Dimensions dim = mesh->dimensions;
+    dim.Min.X *= sc.X; dim.Min.Y *= sc.Y; dim.Min.Z *= sc.Z;
+    dim.Max.X *= sc.X; dim.Max.Y *= sc.Y; dim.Max.Z *= sc.Z;
+    sphereRadius = dim.MaxSpan() / 2;
+}
+bool Model::isTransparent(const MeshPart& part) const {                   // model.go:1274-1282
+    const Material* mat = part.material.get();
+    if (mat) {
+        bool matT = mat->TransparencyMode == TransparencyModeTransparent || !mat->BlendSourceOver ||
+                    (mat->TransparencyMode == TransparencyModeAuto && mat->Color.A < 0.999f);
+        bool modelT = mat->TransparencyMode != TransparencyModeOpaque && Color.A < 0.999f;
+        return matT || modelT;
+    }
+    return Color.A < 0.999f;
+}
+void Model::DynamicBatchAdd(int meshPartIndex, const std::vector<std::shared_ptr<Model>>& models) {   // model.go:217-247
+    for (auto& other : models) {
+        if (other.get() == this) continue;
+        auto& slice = DynamicBatchModels[meshPartIndex];
+        if (std::find(slice.begin(), slice.end(), other) != slice.end()) continue;
+        slice.push_back(other);
+        other->DynamicBatchOwner = this;
+    }
+}
+
+Scene::Scene(const std::string& n) : Name(n), Root(std::make_shared<Node>("Root")), world(std::make_shared<World>()) {}
+
+// ---- GeometryDevice -----------------------------------------------------------------------------------
+static void check(t3d_ctx* ctx, int rc, const char* what) {
+    if (rc != T3D_OK) throw T3DError(rc, std::string(what) + ": " + t3d_last_error(ctx));
+}
+
+GeometryDevice::GeometryDevice(int device) : deviceId(device) {
+    int rc = t3d_create(&ctx, device);
+    if (rc != T3D_OK) throw T3DError(rc, std::string("t3d_create: ") + t3d_last_error(nullptr));
+}
+GeometryDevice::~GeometryDevice() { if (ctx) t3d_destroy(ctx); }
+
+void GeometryDevice::ensureMesh(Mesh& m) {
+    std::vector<t3d_part_range> parts(m.MeshParts.size());
+    for (size_t i = 0; i < parts.size(); i++) {
+        const MeshPart& p = *m.MeshParts[i];
+        parts[i].vtx_start = (uint32_t)p.VertexIndexStart; parts[i].vtx_end = (uint32_t)p.VertexIndexEnd;
+        parts[i].tri_start = (uint32_t)p.TriangleStart; parts[i].tri_end = (uint32_t)(p.TriangleEnd + 1);
+    }
+    t3d_mesh_desc d; std::memset(&d, 0, sizeof d);
+    d.n_verts = (uint32_t)m.VertexCount();
+    d.positions = m.VertexPositions.data(); d.normals = m.VertexNormals.data(); d.uvs = m.VertexUVs.data();
+    d.colors = (m.VertexActiveColorChannel >= 0 && !m.VertexColors.empty()) ? m.VertexColors.data() : nullptr;
+    if (!m.VertexWeights.empty()) {
+        d.weights = m.VertexWeights.data(); d.bones = m.VertexBones.data();
+        d.n_influences = m.VertexInfluences.empty() ? nullptr : m.VertexInfluences.data();
+    }
+    d.n_tris = (uint32_t)m.TriangleTotal();
+    d.indices = m.TriangleIndices.data(); d.centers = m.TriangleCenters.data();
+    d.n_parts = (uint32_t)parts.size(); d.parts = parts.data();
+    d.max_span = m.dimensions.MaxSpan();
+    d.n_shape_keys = (uint32_t)m.ShapeKeyWeights.size();
+    d.key_positions = m.ShapeKeyPositions.data(); d.key_normals = m.ShapeKeyNormals.data();
+    // t3d_mesh_upload is a no-op when (id, generation) is already resident
+    check(ctx, t3d_mesh_upload(ctx, m.id, m.generation + (m.shapeKeyWeightGeneration << 20), &d), "t3d_mesh_upload");
+    if (d.n_shape_keys) check(ctx, t3d_mesh_set_shape_key_weights(ctx, m.id, m.ShapeKeyWeights.data(), d.n_shape_keys), "t3d_mesh_set_shape_key_weights");
+}
+
+void GeometryDevice::ensureVolume(LightVolume& v) {
+    if (v.hasUseLights) throw T3DError(T3D_E_UNSUPPORTED, "LightVolumeCell.useLights (light.go:652) cannot run on the device");
+    if (v.volumeId == 0) v.volumeId = nextVolumeId++;
+    if (v.uploadedGeneration == v.generation) return;
+    t3d_volume_desc d; std::memset(&d, 0, sizeof d);
+    d.dim_min[0] = v.dimensions.Min.X; d.dim_min[1] = v.dimensions.Min.Y; d.dim_min[2] = v.dimensions.Min.Z;
+    d.dim_max[0] = v.dimensions.Max.X; d.dim_max[1] = v.dimensions.Max.Y; d.dim_max[2] = v.dimensions.Max.Z;
+    for (int i = 0; i < 3; i++) { d.cell_size[i] = v.cellSize[i]; d.cell_count[i] = (uint32_t)v.cellCount[i]; }
+    d.offset[0] = v.offset.X; d.offset[1] = v.offset.Y; d.offset[2] = v.offset.Z;
+    d.light_bias[0] = v.lightBias.X; d.light_bias[1] = v.lightBias.Y; d.light_bias[2] = v.lightBias.Z;
+    d.cell_colors = v.cellColors.data();
+    check(ctx, t3d_volume_upload(ctx, v.volumeId, &d), "t3d_volume_upload");
+    v.uploadedGeneration = v.generation;
+}
+
+// ---- Camera -------------------------------------------------------------------------------------------
+Camera::Camera(const std::string& n, int w, int h) : Node(n), width(w), height(h) {}
+
+Matrix4 Camera::ViewMatrix() {                                            // camera.go:638-648
+    Vector3 camPos = v3_invert(WorldPosition());
+    Matrix4 transform = NewMatrix4Translate(camPos.X, camPos.Y, camPos.Z);
+    return m4_mult(transform, m4_transposed(WorldRotation()));
+}
+Matrix4 Camera::Projection() {                                            // camera.go:651-679
+    float angle = fieldOfView * 3.1415f / 360;                            // the reference's literal (camera.go:660)
+    sphereFactorTang = m32_tan(angle);
+    sphereFactorY = 1.0f / m32_cos(angle);
+    sphereFactorX = 1.0f / m32_cos(m32_atan(sphereFactorTang * AspectRatio()));
+    if (perspective) return NewProjectionMatrix4Perspective(fieldOfView, near_, far_, (float)width, (float)height);
+    float asr = (float)height / (float)width;
+    return NewProjectionMatrix4Orthographic(near_, far_, 1 * orthoScale, -1 * orthoScale, asr * orthoScale, -asr * orthoScale);
+}
+bool Camera::SphereInFrustum(Vector3 position, float radius) {            // camera.go:933-983
+    Vector3 diff = v3_sub(position, WorldPosition());
+    float pcZ = v3_dot(diff, v3_invert(cameraForward));
+    if (pcZ > far_ + radius || pcZ < near_ - radius) return false;
+    if (perspective) {
+        float d = sphereFactorY * radius;
+        pcZ *= sphereFactorTang;
+        float pcY = v3_dot(diff, cameraUp);
+        if (pcY > pcZ + d || pcY < -pcZ - d) return false;
+        pcZ *= AspectRatio();
+        d = sphereFactorX * radius;
+        float pcX = v3_dot(diff, cameraRight);
+        if (pcX > pcZ + d || pcX < -pcZ - d) return false;
+    } else {
+        float w = orthoScale;
+        float h = w / AspectRatio();
+        float pcY = v3_dot(diff, cameraUp);
+        if (-h / 2 - radius > pcY || pcY > h / 2 + radius) return false;
+        float pcX = v3_dot(diff, cameraRight);
+        if (-w / 2 - radius > pcX || pcX > w / 2 + radius) return false;
+    }
+    return true;
+}
+bool Camera::ModelInFrustum(Model& m) {                                   // camera.go:986-989
+    m.Transform();                  // make sure the transform (and the culling sphere with it) is up to date
+    return SphereInFrustum(m.spherePosition, m.sphereRadius);
+}
+void Camera::Clear() {                                                    // camera.go:1018-1090
+    debugInfo = DebugInfo();
+    Matrix4 rot = WorldRotation();
+    cameraForward = v3_unit(v3(rot.m[2][0], rot.m[2][1], rot.m[2][2]));
+    cameraRight = v3_unit(v3(rot.m[0][0], rot.m[0][1], rot.m[0][2]));
+    cameraUp = v3_unit(v3(rot.m[1][0], rot.m[1][1], rot.m[1][2]));
+}
+void Camera::RenderScene(Scene& scene) { RenderNodes(scene, *scene.Root); }   // camera.go:1095
+
+void Camera::RenderNodes(Scene& scene, Node& root) {                      // camera.go:1105-1216
+    std::vector<Model*> meshes; std::vector<ILight*> lights;
+    root.ForEachChild([&](Node* n) {
+        switch (n->Type()) {
+        case NodeType::Model: { Model* m = static_cast<Model*>(n); if (!m->DynamicBatchOwner) meshes.push_back(m); break; }
+        case NodeType::AmbientLight: case NodeType::PointLight: case NodeType::DirectionalLight: case NodeType::LightVolume:
+            lights.push_back(static_cast<ILight*>(n)); break;
+        default: break;
+        }
+    });
+    Render(scene, lights, meshes);
+}
+
+namespace {
+struct renderPair { Model* model; int part; float depth; int order; };   // camera.go:1249-1254
+
+template <class T, class Less> void stableSort(std::vector<T>& v, Less less) { std::stable_sort(v.begin(), v.end(), less); }
+
+t3d_light toLight(GeometryDevice& dev, ILight* l) {
+    t3d_light L; std::memset(&L, 0, sizeof L);
+    L.color[0] = l->color.R; L.color[1] = l->color.G; L.color[2] = l->color.B; L.energy = l->energy;
+    switch (l->Type()) {
+    case NodeType::AmbientLight: L.type = T3D_LIGHT_AMBIENT; break;
+    case NodeType::PointLight: {
+        L.type = T3D_LIGHT_POINT;
+        Vector3 p = l->WorldPosition();
+        L.position[0] = p.X; L.position[1] = p.Y; L.position[2] = p.Z;
+        L.range = static_cast<PointLight*>(l)->lightRange;
+        break;
+    }
+    case NodeType::DirectionalLight: {
+        L.type = T3D_LIGHT_DIRECTIONAL;
+        Matrix4 r = l->WorldRotation();                                   // light.go:322-324
+        Vector3 f = v3_unit(v3(r.m[2][0], r.m[2][1], r.m[2][2]));
+        L.forward[0] = f.X; L.forward[1] = f.Y; L.forward[2] = f.Z;
+        break;
+    }
+    case NodeType::LightVolume: {
+        LightVolume* v = static_cast<LightVolume*>(l);
+        dev.ensureVolume(*v);
+        L.type = T3D_LIGHT_VOLUME; L.volume = v->volumeId;
+        break;
+    }
+    default: throw T3DError(T3D_E_INVALID, "node is not a light");
+    }
+    return L;
+}
+}  // namespace
+
+void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std::vector<Model*>& models) {   // camera.go:1269-2114
+    if (!device) throw T3DError(T3D_E_STATE, "Camera has no GeometryDevice: the geometry stage has no CPU path");
+    t3d_ctx* ctx = device->ctx;
+    World* world = scene.world.get();
+
+    // sceneLights (camera.go:1275-1303)
+    std::vector<ILight*> sceneLights;
+    if (world) {
+        debugInfo.lightCount++;
+        if (world->LightingOn && world->ambientLight->IsVisible()) sceneLights.push_back(world->ambientLight.get());
+    }
+    for (ILight* l : lights) {
+        debugInfo.lightCount++;
+        if ((!world || world->LightingOn) && l->IsVisible()) sceneLights.push_back(l);
+    }
+    for (ILight* l : sceneLights) if (world && world->LightingOn && l->IsVisible()) debugInfo.activeLightCount++;   // camera.go:1499-1505
+
+    Matrix4 proj = Projection();
+    Matrix4 view = ViewMatrix();
+    Matrix4 vpMatrix = m4_mult(view, proj);                                // camera.go:1329
+    Vector3 cameraPos = WorldPosition();
+
+    std::vector<renderPair> solids, transparents;
+    for (Model* model : models) {                                          // camera.go:1343-1457
+        if (!model->visible || model->DynamicBatchOwner) continue;
+        if (!model->DynamicBatcher()) {
+            if (model->mesh) debugInfo.totalParts += (int)model->mesh->MeshParts.size();
+            if (model->FrustumCulling && !ModelInFrustum(*model)) continue;
+            if (!model->mesh) continue;
+            for (size_t pi = 0; pi < model->mesh->MeshParts.size(); pi++) {
+                MeshPart& mp = *model->mesh->MeshParts[pi];
+                if (!mp.isVisible()) continue;
+                renderPair rp{model, (int)pi, v3_dist2(cameraPos, model->WorldPosition()), 0};
+                if (mp.material) rp.order = mp.material->RenderOrder;
+                if (model->isTransparent(mp)) transparents.push_back(rp); else solids.push_back(rp);
+            }
+        } else {
+            bool transparent = false;
+            // Go ranges over a map here (random order); the contract is ascending MeshPart index.
+            for (auto& kv : model->DynamicBatchModels) {
+                if (!model->mesh || kv.first >= (int)model->mesh->MeshParts.size()) continue;
+                MeshPart& meshPart = *model->mesh->MeshParts[kv.first];
+                if (!meshPart.isVisible()) continue;
+                for (auto& child : kv.second) {
+                    if (!child->visible) continue;
+                    if (!transparent)
+                        for (auto& mp : child->mesh->MeshParts)
+                            if (mp->isVisible() && child->isTransparent(*mp)) { transparent = true; break; }
+                }
+                renderPair rp{model, kv.first, 0, 0};
+                if (transparent || !RenderDepth) rp.depth = v3_dist2(cameraPos, model->WorldPosition());
+                if (meshPart.material) rp.order = meshPart.material->RenderOrder;
+                if (transparent) transparents.push_back(rp); else solids.push_back(rp);
+                debugInfo.totalParts += (int)kv.second.size();
+            }
+        }
+    }
+    if (!RenderDepth)                                                      // camera.go:1460-1469
+        stableSort(solids, [](const renderPair& i, const renderPair& j) { if (i.order < j.order) return true; return i.depth > j.depth; });
+    stableSort(transparents, [](const renderPair& i, const renderPair& j) {   // camera.go:2050-2055
+        if (i.order == j.order) return i.depth > j.depth;
+        return i.order < j.order;
+    });
+
+    // ---- walk the passes and collect every render(rp) call, grouped by flush (camera.go:2057-2109) ----
+    struct PendingDraw { Model* model; int part; int flush; bool first; };
+    std::vector<PendingDraw> pending;
+    std::vector<std::pair<Model*, int>> flushOwners;
+    for (auto* pass : {&solids, &transparents}) {
+        for (renderPair& pair : *pass) {
+            if (!pair.model->visible) continue;
+            const int flushId = (int)flushOwners.size();
+            bool first = true;
+            if (pair.model->DynamicBatcher()) {
+                auto& modelSlice = pair.model->DynamicBatchModels[pair.part];
+                // sort.Slice far -> near (camera.go:2078-2080); ties keep insertion order (contract)
+                std::stable_sort(modelSlice.begin(), modelSlice.end(), [&](const std::shared_ptr<Model>& a, const std::shared_ptr<Model>& b) {
+                    return v3_dist2(cameraPos, a->WorldPosition()) > v3_dist2(cameraPos, b->WorldPosition());
+                });
+                for (auto& merged : modelSlice) {
+                    if (!merged->visible) continue;
+                    if (merged->FrustumCulling && !ModelInFrustum(*merged)) continue;
+                    if (!merged->mesh) continue;
+                    for (size_t cp = 0; cp < merged->mesh->MeshParts.size(); cp++) { pending.push_back({merged.get(), (int)cp, flushId, first}); first = false; }
+                }
+            } else {
+                if (!pair.model->mesh) continue;
+                pending.push_back({pair.model, pair.part, flushId, true});
+            }
+            flushOwners.push_back({pair.model, pair.part});
+        }
+    }
+
+    // ---- object-wise sharding: whole flushes, largest first onto the least-loaded rank ----
+    const int nFlush = (int)flushOwners.size();
+    flushOwnerRank.assign(nFlush, 0);
+    if (shardCount > 1) {
+        std::vector<uint64_t> flushTris(nFlush, 0);
+        for (auto& pd : pending) flushTris[pd.flush] += (uint64_t)pd.model->mesh->MeshParts[pd.part]->TriangleCount();
+        std::vector<int> order(nFlush);
+        for (int i = 0; i < nFlush; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return flushTris[a] > flushTris[b]; });
+        std::vector<uint64_t> load(shardCount, 0);
+        for (int f : order) {
+            int best = 0;
+            for (int r = 1; r < shardCount; r++) if (load[r] < load[best]) best = r;
+            flushOwnerRank[f] = best; load[best] += flushTris[f];
+        }
+    }
+
+    // ---- frame ----
+    t3d_camera cam; std::memset(&cam, 0, sizeof cam);
+    m4_store(vpMatrix, cam.vp); m4_store(view, cam.view);
+    cam.position[0] = cameraPos.X; cam.position[1] = cameraPos.Y; cam.position[2] = cameraPos.Z;
+    cam.up[0] = cameraUp.X; cam.up[1] = cameraUp.Y; cam.up[2] = cameraUp.Z;
+    cam.near_plane = near_; cam.far_plane = far_; cam.width = width; cam.height = height;
+    cam.depth_margin = DepthMargin; cam.vertex_snapping = VertexSnapping;
+    cam.flags = (perspective ? T3D_CAM_PERSPECTIVE : 0) | (RenderDepth ? T3D_CAM_RENDER_DEPTH : 0) |
+                (RenderNormals ? T3D_CAM_RENDER_NORMALS : 0) | (PerspectiveCorrectedTextureMapping ? T3D_CAM_PERSP_CORRECT_UV : 0);
+    t3d_world tw; std::memset(&tw, 0, sizeof tw);
+    if (world) {
+        tw.present = 1; tw.fog_on = world->FogOn; tw.fog_mode = world->FogMode;
+        tw.fog_color[0] = world->FogColor.R; tw.fog_color[1] = world->FogColor.G; tw.fog_color[2] = world->FogColor.B;
+        tw.fog_range[0] = world->FogRange[0]; tw.fog_range[1] = world->FogRange[1];
+    }
+    check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
+
+    // light lists: the scene list once, each active LightGroup once (camera.go:1576-1581)
+    uint32_t sceneList = 0; bool sceneListMade = false;
+    std::unordered_map<LightGroup*, uint32_t> groupLists;
+    auto makeList = [&](const std::vector<ILight*>& ls) {
+        std::vector<t3d_light> recs; recs.reserve(ls.size());
+        for (ILight* l : ls) recs.push_back(toLight(*device, l));
+        uint32_t id = 0;
+        check(ctx, t3d_submit_lights(ctx, recs.data(), (uint32_t)recs.size(), &id), "t3d_submit_lights");
+        return id;
+    };
+    std::unordered_map<Model*, uint32_t> boneOffsets;
+
+    renders.clear(); flushes.clear(); localFlushIds.clear();
+    std::vector<t3d_draw> draws; draws.reserve(pending.size());
+    std::vector<const PendingDraw*> submitted;
+    for (auto& pd : pending) {
+        if (flushOwnerRank[pd.flush] != shardRank) continue;
+        Model* model = pd.model;
+        Mesh& mesh = *model->mesh;
+        MeshPart& meshPart = *mesh.MeshParts[pd.part];
+        Material* mat = meshPart.material.get();
+        if (model->HasVertexTransformFunction || model->HasVertexClipFunction || (mat && mat->HasCustomDepthFunction))
+            throw T3DError(T3D_E_UNSUPPORTED, "host callbacks (VertexTransformFunction / VertexClipFunction / CustomDepthFunction) cannot run on the device");
+        if (model->DynamicBatchOwner) debugInfo.batchedParts++;            // camera.go:1534-1536
+        // ProcessVertices early-out (model.go:604): nothing is transformed or emitted
+        const bool skip = (model->Color.A == 0 && model->isTransparent(meshPart)) || !model->visible;
+
+        device->ensureMesh(mesh);
+        bool lighting = false;                                             // camera.go:1521-1528
+        if (world) lighting = world->LightingOn && !(mat && mat->Shadeless) && !model->Shadeless;
+
+        t3d_draw d; std::memset(&d, 0, sizeof d);
+        d.mesh_id = mesh.id; d.part = (uint32_t)pd.part;
+        uint32_t f = 0;
+        if (mat) {
+            f |= T3D_DRAW_HAS_MATERIAL;
+            if (mat->BackfaceCulling) f |= T3D_DRAW_BACKFACE_CULLING;
+            if (mat->BillboardEnabled) f |= T3D_DRAW_BILLBOARD;
+            if (mat->BillboardLockX) f |= T3D_DRAW_BILLBOARD_LOCK_X;
+            if (mat->BillboardLockY) f |= T3D_DRAW_BILLBOARD_LOCK_Y;
+            if (mat->BillboardLockZ) f |= T3D_DRAW_BILLBOARD_LOCK_Z;
+            if (mat->BillboardUpDirection == BillboardYUpCameraY) f |= T3D_DRAW_BILLBOARD_CAMERA_UP;
+            if (mat->BillboardedDepthMode == DepthModeUnbillboarded) f |= T3D_DRAW_DEPTH_UNBILLBOARDED;
+            d.sort_mode = (uint8_t)mat->TriangleSortMode; d.lighting_mode = (uint8_t)mat->LightingMode;
+            d.light_volume_mode = (uint8_t)mat->LightVolumeShadingMode;
+        }
+        if (lighting) f |= T3D_DRAW_LIT;
+        if (model->skinned) f |= T3D_DRAW_SKINNED;
+        if (!pd.first) f |= T3D_DRAW_CONTINUE_FLUSH;
+        d.flags = f;
+        m4_store(model->Transform(), d.transform);
+        m4_store(model->WorldRotation(), d.world_rotation);
+        Color4 mp = model->Color;                                          // camera.go:1597-1601
+        if (mat) { mp.R *= mat->Color.R; mp.G *= mat->Color.G; mp.B *= mat->Color.B; mp.A *= mat->Color.A; }
+        d.color[0] = mp.R; d.color[1] = mp.G; d.color[2] = mp.B; d.color[3] = mp.A;
+        if (mat && mat->UseTexture && mat->TextureWidth > 0) { d.src_w = (float)mat->TextureWidth; d.src_h = (float)mat->TextureHeight; }   // camera.go:1560-1566
+        if (lighting) {
+            if (model->lightGroup && model->lightGroup->Active) {
+                auto it = groupLists.find(model->lightGroup.get());
+                if (it == groupLists.end()) {
+                    std::vector<ILight*> ls; for (auto& l : model->lightGroup->Lights) ls.push_back(l.get());
+                    it = groupLists.emplace(model->lightGroup.get(), makeList(ls)).first;
+                }
+                d.light_list = it->second;
+            } else {
+                if (!sceneListMade) { sceneList = makeList(sceneLights); sceneListMade = true; }
+                d.light_list = sceneList;
+            }
+        }
+        if (model->skinned) {
+            auto it = boneOffsets.find(model);
+            if (it == boneOffsets.end()) {
+                uint32_t off = 0;
+                check(ctx, t3d_submit_bones(ctx, model->boneInfluences.data(), (uint32_t)(model->boneInfluences.size() / 16), &off), "t3d_submit_bones");
+                it = boneOffsets.emplace(model, off).first;
+            }
+            d.bone_offset = it->second; d.bone_count = (uint32_t)(model->boneInfluences.size() / 16);
+        }
+        debugInfo.totalTris += meshPart.TriangleCount();                   // camera.go:1532
+        if (skip) {
+            // keep the flush structure, submit nothing for this render(): record an empty render
+            renders.push_back({model, pd.part, pd.flush, 0, 0, (uint32_t)meshPart.TriangleCount(), FLT_MAX, -FLT_MAX, -1});
+            submitted.push_back(nullptr);
+            continue;
+        }
+        draws.push_back(d);
+        submitted.push_back(&pd);
+        renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)draws.size() - 1});
+    }
+    if (!draws.empty()) check(ctx, t3d_submit_draws(ctx, draws.data(), (uint32_t)draws.size()), "t3d_submit_draws");
+    check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
+    if (downloadResults) check(ctx, t3d_frame_results(ctx, &output, &timings), "t3d_frame_results");
+    else check(ctx, t3d_frame_results_device(ctx, &output, &timings), "t3d_frame_results_device");
+    launchCount = t3d_debug_last_launch_count(ctx);
+
+    // per-render and per-flush records (what flush() would slice: camera.go:1829-2048)
+    size_t di = 0;
+    uint64_t lastEnd = 0;
+    for (size_t i = 0; i < renders.size(); i++) {
+        RenderRecord& r = renders[i];
+        if (submitted[i]) {
+            const t3d_draw_result& dr = output.draws[di++];
+            r.firstVertex = dr.first_vertex; r.vertexCount = dr.vertex_count; r.totalTris = dr.total_tris;
+            r.minDepth = dr.min_depth; r.maxDepth = dr.max_depth;
+            lastEnd = dr.first_vertex + dr.vertex_count;
+        } else {
+            r.firstVertex = lastEnd;
+        }
+    }
+    {
+        size_t ri = 0;
+        for (int fId = 0; fId < nFlush; fId++) {
+            if (flushOwnerRank[fId] != shardRank) continue;
+            FlushRecord fr{flushOwners[fId].first, flushOwners[fId].second, 0, 0};
+            bool any = false;
+            while (ri < renders.size() && renders[ri].flush == fId) {
+                if (!any) { fr.firstVertex = renders[ri].firstVertex; any = true; }
+                fr.vertexCount += renders[ri].vertexCount;
+                ri++;
+            }
+            if (!any) fr.firstVertex = lastEnd;
+            if (fr.vertexCount) { debugInfo.drawnTris += (int)(fr.vertexCount / 3); debugInfo.drawnParts++; }   // camera.go:2041-2044
+            flushes.push_back(fr);
+            localFlushIds.push_back(fId);
+        }
+    }
+}
+
+}  // namespace tetra3d

@@ -1,0 +1,197 @@
+"""Neutral, pure-data description of a Tetra3D scene (numpy arrays + dataclasses).
+
+One description can be materialised twice: as host-mirror objects driving the GPU path
+(`tetra3d_b200.build.build_scene`) and, in tests / bench baselines only, as the flat structs the CPU
+oracle reads (`oracle.binding`).  Field names follow the reference (material.go:66-131,
+model.go:20-61, mesh.go:260-302, camera.go:259-332, world.go:25-42, light.go).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+F32 = np.float32
+
+
+def identity4() -> np.ndarray:
+    return np.eye(4, dtype=F32)
+
+
+@dataclass
+class MaterialDesc:
+    color: Sequence[float] = (1.0, 1.0, 1.0, 1.0)
+    backface_culling: bool = True
+    triangle_sort_mode: int = 0
+    shadeless: bool = False
+    lighting_mode: int = 0
+    light_volume_shading_mode: int = 0
+    billboard_enabled: bool = False
+    billboard_lock_x: bool = False
+    billboard_lock_y: bool = False
+    billboard_lock_z: bool = False
+    billboard_up_direction: int = 0
+    billboarded_depth_mode: int = 0
+    transparency_mode: int = 0
+    blend_source_over: bool = True
+    visible: bool = True
+    render_order: int = 0
+    use_texture: bool = False
+    tex_w: int = 0
+    tex_h: int = 0
+
+
+@dataclass
+class PartDesc:
+    vertex_start: int
+    vertex_end: int
+    tri_start: int
+    tri_end: int                       # inclusive, as MeshPart.TriangleEnd (mesh.go:2189)
+    material: Optional[MaterialDesc] = field(default_factory=MaterialDesc)
+
+
+@dataclass
+class MeshDesc:
+    positions: np.ndarray              # (n, 3) float32
+    normals: np.ndarray                # (n, 3)
+    uvs: np.ndarray                    # (n, 2)
+    indices: np.ndarray                # (t, 3) uint32
+    parts: List[PartDesc]
+    colors: Optional[np.ndarray] = None          # (n, 4): the active colour channel
+    active_color_channel: int = -1
+    weights: Optional[np.ndarray] = None         # (n, 4)
+    bones: Optional[np.ndarray] = None           # (n, 4) uint16
+    n_influences: Optional[np.ndarray] = None    # (n,) uint8
+    key_positions: Optional[np.ndarray] = None   # (k, n, 3)
+    key_normals: Optional[np.ndarray] = None     # (k, n, 3)
+    key_weights: Optional[np.ndarray] = None     # (k,)
+    name: str = "mesh"
+
+    def __post_init__(self):
+        self.positions = np.ascontiguousarray(self.positions, dtype=F32).reshape(-1, 3)
+        self.normals = np.ascontiguousarray(self.normals, dtype=F32).reshape(-1, 3)
+        self.uvs = np.ascontiguousarray(self.uvs, dtype=F32).reshape(-1, 2)
+        self.indices = np.ascontiguousarray(self.indices, dtype=np.uint32).reshape(-1, 3)
+        if self.colors is not None:
+            self.colors = np.ascontiguousarray(self.colors, dtype=F32).reshape(-1, 4)
+        if self.weights is not None:
+            self.weights = np.ascontiguousarray(self.weights, dtype=F32).reshape(-1, 4)
+            self.bones = np.ascontiguousarray(self.bones, dtype=np.uint16).reshape(-1, 4)
+            if self.n_influences is None:
+                self.n_influences = np.full(len(self.positions), 4, dtype=np.uint8)
+            self.n_influences = np.ascontiguousarray(self.n_influences, dtype=np.uint8)
+        if self.key_weights is not None:
+            self.key_positions = np.ascontiguousarray(self.key_positions, dtype=F32)
+            self.key_normals = np.ascontiguousarray(self.key_normals, dtype=F32)
+            self.key_weights = np.ascontiguousarray(self.key_weights, dtype=F32)
+
+    @property
+    def n_verts(self) -> int:
+        return len(self.positions)
+
+    @property
+    def n_tris(self) -> int:
+        return len(self.indices)
+
+
+@dataclass(eq=False)
+class NodeDesc:
+    position: Sequence[float] = (0.0, 0.0, 0.0)
+    scale: Sequence[float] = (1.0, 1.0, 1.0)
+    rotation: np.ndarray = field(default_factory=identity4)     # row-major Matrix4
+    parent: Optional["NodeDesc"] = None
+    name: str = "node"
+
+
+@dataclass
+class VolumeDesc:
+    dim_min: Sequence[float]
+    dim_max: Sequence[float]
+    cell_size: Sequence[float]
+    cell_count: Sequence[int]
+    colors: np.ndarray                 # (cx*cy*cz, 3), index x + y*cx + z*cx*cy
+    offset: Sequence[float] = (0.0, 0.0, 0.0)
+    light_bias: Sequence[float] = (0.0, 0.0, 0.0)
+
+
+LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL, LIGHT_VOLUME = 0, 1, 2, 3
+
+
+@dataclass(eq=False)
+class LightDesc:
+    type: int
+    node: NodeDesc = field(default_factory=NodeDesc)
+    color: Sequence[float] = (1.0, 1.0, 1.0)
+    energy: float = 1.0
+    visible: bool = True
+    range: float = 0.0
+    volume: Optional[VolumeDesc] = None
+    in_scene: bool = True              # under scene.Root (a LightGroup may hold lights that are not)
+    name: str = "light"
+
+
+@dataclass(eq=False)
+class LightGroupDesc:
+    lights: List[LightDesc]
+    active: bool = True
+
+
+@dataclass(eq=False)
+class ModelDesc:
+    mesh: MeshDesc
+    node: NodeDesc = field(default_factory=NodeDesc)
+    color: Sequence[float] = (1.0, 1.0, 1.0, 1.0)
+    shadeless: bool = False
+    visible: bool = True
+    frustum_culling: bool = True
+    bone_influences: Optional[np.ndarray] = None     # (n_bones, 16): makes the model skinned
+    light_group: Optional[LightGroupDesc] = None
+    batch_owner: Optional["ModelDesc"] = None        # Model.DynamicBatchOwner
+    batch_owner_part: int = 0
+    name: str = "model"
+
+
+@dataclass
+class CameraDesc:
+    node: NodeDesc = field(default_factory=lambda: NodeDesc(position=(0.0, 0.0, 10.0)))
+    width: int = 640
+    height: int = 360
+    field_of_view: float = 60.0
+    near: float = 0.1
+    far: float = 100.0
+    perspective: bool = True
+    ortho_scale: float = 20.0
+    depth_margin: float = 0.04
+    vertex_snapping: float = 0.0
+    render_depth: bool = True
+    render_normals: bool = False
+    perspective_corrected_texture_mapping: bool = False
+
+
+@dataclass
+class WorldDesc:
+    present: bool = True
+    lighting_on: bool = True
+    fog_on: bool = True
+    fog_mode: int = 0
+    fog_color: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+    fog_range: Sequence[float] = (0.0, 1.0)
+    ambient_color: Sequence[float] = (1.0, 1.0, 1.0)
+    ambient_energy: float = 0.0
+    ambient_visible: bool = True
+
+
+@dataclass
+class SceneDesc:
+    models: List[ModelDesc]            # in the depth-first order RenderNodes visits them
+    lights: List[LightDesc] = field(default_factory=list)
+    camera: CameraDesc = field(default_factory=CameraDesc)
+    world: WorldDesc = field(default_factory=WorldDesc)
+    name: str = "scene"
+
+    def total_triangles(self) -> int:
+        return sum(m.mesh.n_tris for m in self.models if m.visible)
+
+    def total_vertices(self) -> int:
+        return sum(m.mesh.n_verts for m in self.models if m.visible)
