@@ -100,7 +100,10 @@ struct t3d_ctx {
     bool anyLit = false, anySkinned = false, anyUnbill = false;
 
     // device arenas
-    DevBuf dDraws, dVbase, dTbase, dTileV, dTileT, dLightsIn, dLightsU, dBones, dStats;
+    DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
+    PinVec<uint8_t> hFrame;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pTileT = nullptr;
+    t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dLight, dWpos, dUnbill, dTnrm;
     DevBuf dTdepth, dTdraw, dKeys0, dKeysA, dKeysB, dValsA, dValsB, dSortScratch, dCount;
     DevBuf dColor, dDepth, dNormal, dTriIds;
@@ -174,12 +177,12 @@ void t3d_destroy(t3d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->meshes) kv.second.release();
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
-    DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dDraws, &ctx->dVbase, &ctx->dTbase, &ctx->dTileV, &ctx->dTileT, &ctx->dLightsIn,
-                      &ctx->dLightsU, &ctx->dBones, &ctx->dStats, &ctx->dClip, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
+    DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame,
+                      &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dTdraw, &ctx->dKeys0, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
                       &ctx->dValsB, &ctx->dSortScratch, &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
-    ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hTileT.release();
+    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hTileT.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -198,12 +201,11 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
         return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: weights and bones must be given together");
     if (d->n_shape_keys && (!d->key_positions || !d->key_normals))
         return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: shape key arrays missing");
-    for (uint32_t t = 0; t < 3 * d->n_tris; t++)
-        if (d->indices[t] >= d->n_verts) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: triangle index out of range");
-
     auto it = ctx->meshes.find(mesh_id);
+    if (it != ctx->meshes.end() && it->second.generation == generation) return T3D_OK;      // already resident
+    for (size_t t = 0; t < 3 * (size_t)d->n_tris; t++)
+        if (d->indices[t] >= d->n_verts) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: triangle index out of range");
     if (it != ctx->meshes.end()) {
-        if (it->second.generation == generation) return T3D_OK;      // already resident
         CU(cudaStreamSynchronize(ctx->stream));
         it->second.release();
     }
@@ -491,14 +493,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     const SortPlan plan = sort_plan(totalT, nDraws);
 
     // arenas
-    CU(ctx->dDraws.ensure(sizeof(DrawRec) * nDraws));
-    CU(ctx->dVbase.ensure(4ull * (nDraws + 1)));
-    CU(ctx->dTbase.ensure(4ull * (nDraws + 1)));
-    CU(ctx->dTileV.ensure(4ull * (nTilesV + 1)));
-    CU(ctx->dTileT.ensure(4ull * (nTilesT + 1)));
-    CU(ctx->dLightsIn.ensure(sizeof(t3d_light) * std::max<size_t>(ctx->hLights.n, 1)));
     CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
-    CU(ctx->dBones.ensure(4ull * std::max<size_t>(ctx->hBones.n, 16)));
     CU(ctx->dStats.ensure(sizeof(DrawStat) * nDraws));
     CU(ctx->dClip.ensure(16ull * std::max(totalV, 4u)));
     CU(ctx->dLight.ensure(16ull * std::max(ctx->anyLit ? totalV : 4u, 4u)));
@@ -523,38 +518,53 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->volumesDirty = false;
     }
 
-    // uniforms up
-    CU(cudaMemcpyAsync(ctx->dDraws.p, ctx->hDraws.p, sizeof(DrawRec) * nDraws, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->dVbase.p, ctx->hVbase.p, 4ull * (nDraws + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->dTbase.p, ctx->hTbase.p, 4ull * (nDraws + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->dTileV.p, ctx->hTileV.p, 4ull * (nTilesV + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->dTileT.p, ctx->hTileT.p, 4ull * (nTilesT + 1), cudaMemcpyHostToDevice, s));
-    if (ctx->hLights.n) CU(cudaMemcpyAsync(ctx->dLightsIn.p, ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, cudaMemcpyHostToDevice, s));
-    if (ctx->hBones.n) CU(cudaMemcpyAsync(ctx->dBones.p, ctx->hBones.p, 4ull * ctx->hBones.n, cudaMemcpyHostToDevice, s));
+    // uniforms up: pack every per-frame array into one pinned block -> one async copy
+    {
+        struct Seg { const void* src; size_t bytes; size_t off; };
+        Seg segs[7] = {
+            {ctx->hDraws.p, sizeof(DrawRec) * (size_t)nDraws, 0}, {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
+            {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTileT.p, 4ull * (nTilesT + 1), 0},
+            {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0}};
+        size_t total = 0;
+        for (Seg& g : segs) { g.off = total; total += (g.bytes + 255) & ~(size_t)255; }
+        total = std::max<size_t>(total, 256);
+        CU(ctx->hFrame.resize(total));
+        CU(ctx->dFrame.ensure(total));
+        for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
+        CU(cudaMemcpyAsync(ctx->dFrame.p, ctx->hFrame.p, total, cudaMemcpyHostToDevice, s));
+        uint8_t* base = ctx->dFrame.as<uint8_t>();
+        ctx->pDraws = reinterpret_cast<DrawRec*>(base + segs[0].off);
+        ctx->pVbase = reinterpret_cast<uint32_t*>(base + segs[1].off);
+        ctx->pTbase = reinterpret_cast<uint32_t*>(base + segs[2].off);
+        ctx->pTileV = reinterpret_cast<uint32_t*>(base + segs[3].off);
+        ctx->pTileT = reinterpret_cast<uint32_t*>(base + segs[4].off);
+        ctx->pLightsIn = reinterpret_cast<t3d_light*>(base + segs[5].off);
+        ctx->pBones = reinterpret_cast<float*>(base + segs[6].off);
+    }
     CU(cudaEventRecord(ctx->ev[1], s));
 
     // K0 + K1
-    launch_prep_draws(s, ctx->dDraws.as<DrawRec>(), nDraws, ctx->fc, ctx->dLightsIn.as<t3d_light>(), ctx->dLightsU.as<LightU>(), ctx->dStats.as<DrawStat>());
+    launch_prep_draws(s, ctx->pDraws, nDraws, ctx->fc, ctx->pLightsIn, ctx->dLightsU.as<LightU>(), ctx->dStats.as<DrawStat>());
     CU(cudaEventRecord(ctx->ev[2], s));
-    launch_vertex(s, ctx->dDraws.as<DrawRec>(), ctx->dVbase.as<uint32_t>(), ctx->dTileV.as<uint32_t>(), totalGroups, ctx->fc,
-                  ctx->dLightsU.as<LightU>(), ctx->dBones.as<float>(), ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
+    launch_vertex(s, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalGroups, ctx->fc,
+                  ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->ev[3], s));
     // K2
-    launch_cull(s, ctx->dDraws.as<DrawRec>(), ctx->dTbase.as<uint32_t>(), ctx->dTileT.as<uint32_t>(), totalT, ctx->fc,
+    launch_cull(s, ctx->pDraws, ctx->pTbase, ctx->pTileT, totalT, ctx->fc,
                 ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), ctx->dStats.as<DrawStat>());
     ctx->launches += 1;
     CU(cudaEventRecord(ctx->ev[4], s));
     // K3 + sort
-    launch_keys(s, ctx->dDraws.as<DrawRec>(), ctx->dStats.as<DrawStat>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), totalT, ctx->dKeys0.as<uint32_t>());
+    launch_keys(s, ctx->pDraws, ctx->dStats.as<DrawStat>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), totalT, ctx->dKeys0.as<uint32_t>());
     ctx->launches += 1;
     ctx->launches += sort_pairs(s, plan, ctx->dKeys0.as<uint32_t>(), ctx->dKeysA.as<uint32_t>(), ctx->dValsA.as<uint32_t>(),
                                 ctx->dKeysB.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dSortScratch.p, ctx->dCount.as<uint32_t>(),
                                 &ctx->sortedKeys, &ctx->sortedVals);
     CU(cudaEventRecord(ctx->ev[5], s));
     // K4
-    launch_emit(s, ctx->dDraws.as<DrawRec>(), ctx->sortedKeys, ctx->sortedVals, ctx->dCount.as<uint32_t>(), totalT, ctx->fc,
+    launch_emit(s, ctx->pDraws, ctx->sortedKeys, ctx->sortedVals, ctx->dCount.as<uint32_t>(), totalT, ctx->fc,
                 ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                 ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
     ctx->launches += 1;
@@ -563,14 +573,16 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     ctx->h2dBytes = sizeof(DrawRec) * (uint64_t)nDraws + 8ull * (nDraws + 1) + 4ull * (nTilesV + 1) + 4ull * (nTilesT + 1) +
                     sizeof(t3d_light) * (uint64_t)ctx->hLights.n + 4ull * ctx->hBones.n;
 
-    // algorithmic bytes of the fused vertex kernel: pos 12 [+ normal 12] -> clip 16 [+ light 16],
-    // skinned adds weights 16 + joints 8 + world position 16.
+    // algorithmic bytes of the fused vertex kernel (SURVEY.md 8d / DESIGN.md): static unlit 28 B/vertex
+    // (pos 12 -> clip 16), static lit 52 (+ normal 12, light rgb 12), skinned lit 88 (+ weights 16, joints 8,
+    // world position 12), skinned unlit 76 (normals are still skinned).
     uint64_t bytes = 0;
     for (uint32_t i = 0; i < nDraws; i++) {
         const DrawRec& R = ctx->hDraws.p[i];
+        const bool lit = R.flags & T3D_DRAW_LIT, sk = R.flags & T3D_DRAW_SKINNED;
         uint64_t per = 12 + 16;
-        if (R.flags & T3D_DRAW_LIT) per += 12 + 16;
-        if (R.flags & T3D_DRAW_SKINNED) per += ((R.flags & T3D_DRAW_LIT) ? 0 : 12) + 16 + 8 + 16;
+        if (lit) per += 12 + 12;
+        if (sk) per += (lit ? 0 : 12) + 16 + 8 + 12;
         bytes += per * R.nv;
     }
     ctx->vertexKernelBytes = bytes;

@@ -239,6 +239,9 @@ GeometryDevice::GeometryDevice(int device) : deviceId(device) {
 GeometryDevice::~GeometryDevice() { if (ctx) t3d_destroy(ctx); }
 
 void GeometryDevice::ensureMesh(Mesh& m) {
+    const uint64_t genKey = ((uint64_t)m.generation << 32) | m.shapeKeyWeightGeneration;
+    auto res = residentMeshes.find(m.id);
+    if (res != residentMeshes.end() && res->second == genKey) return;
     std::vector<t3d_part_range> parts(m.MeshParts.size());
     for (size_t i = 0; i < parts.size(); i++) {
         const MeshPart& p = *m.MeshParts[i];
@@ -260,8 +263,9 @@ void GeometryDevice::ensureMesh(Mesh& m) {
     d.n_shape_keys = (uint32_t)m.ShapeKeyWeights.size();
     d.key_positions = m.ShapeKeyPositions.data(); d.key_normals = m.ShapeKeyNormals.data();
     // t3d_mesh_upload is a no-op when (id, generation) is already resident
-    check(ctx, t3d_mesh_upload(ctx, m.id, m.generation + (m.shapeKeyWeightGeneration << 20), &d), "t3d_mesh_upload");
+    check(ctx, t3d_mesh_upload(ctx, m.id, m.generation, &d), "t3d_mesh_upload");
     if (d.n_shape_keys) check(ctx, t3d_mesh_set_shape_key_weights(ctx, m.id, m.ShapeKeyWeights.data(), d.n_shape_keys), "t3d_mesh_set_shape_key_weights");
+    residentMeshes[m.id] = genKey;
 }
 
 void GeometryDevice::ensureVolume(LightVolume& v) {

@@ -218,6 +218,7 @@ struct GeometryDevice {
     t3d_ctx* ctx = nullptr;
     int deviceId = 0;
     uint32_t nextVolumeId = 1;
+    std::map<uint64_t, uint64_t> residentMeshes;   // mesh id -> generation key last uploaded
     explicit GeometryDevice(int device);
     ~GeometryDevice();
     void ensureMesh(Mesh& m);
