@@ -320,5 +320,6 @@ PYBIND11_MODULE(_host, m) {
             return d;
         })
         .def("LaunchCount", [](Camera& c) { return c.launchCount; });
+    m.def("AssignFlushesToRanks", &AssignFlushesToRanks, py::arg("flush_triangles"), py::arg("rank_count"));
     m.def("NewCamera", [](const std::string& n, int w, int h) { return std::make_shared<Camera>(n, w, h); });
 }

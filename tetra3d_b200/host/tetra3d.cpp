@@ -283,6 +283,22 @@ void GeometryDevice::ensureVolume(LightVolume& v) {
     v.uploadedGeneration = v.generation;
 }
 
+std::vector<int> AssignFlushesToRanks(const std::vector<uint64_t>& flushTris, int rankCount) {
+    const int n = (int)flushTris.size();
+    std::vector<int> owner(n, 0);
+    if (rankCount <= 1) return owner;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return flushTris[a] > flushTris[b]; });
+    std::vector<uint64_t> load(rankCount, 0);
+    for (int f : order) {
+        int best = 0;
+        for (int r = 1; r < rankCount; r++) if (load[r] < load[best]) best = r;
+        owner[f] = best; load[best] += flushTris[f];
+    }
+    return owner;
+}
+
 // ---- Camera -------------------------------------------------------------------------------------------
 Camera::Camera(const std::string& n, int w, int h) : Node(n), width(w), height(h) {}
 
@@ -480,19 +496,10 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
 
     // ---- object-wise sharding: whole flushes, largest first onto the least-loaded rank ----
     const int nFlush = (int)flushOwners.size();
-    flushOwnerRank.assign(nFlush, 0);
-    if (shardCount > 1) {
+    {
         std::vector<uint64_t> flushTris(nFlush, 0);
         for (auto& pd : pending) flushTris[pd.flush] += (uint64_t)pd.model->mesh->MeshParts[pd.part]->TriangleCount();
-        std::vector<int> order(nFlush);
-        for (int i = 0; i < nFlush; i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return flushTris[a] > flushTris[b]; });
-        std::vector<uint64_t> load(shardCount, 0);
-        for (int f : order) {
-            int best = 0;
-            for (int r = 1; r < shardCount; r++) if (load[r] < load[best]) best = r;
-            flushOwnerRank[f] = best; load[best] += flushTris[f];
-        }
+        flushOwnerRank = AssignFlushesToRanks(flushTris, shardCount);
     }
 
     // ---- frame ----

@@ -271,6 +271,10 @@ struct Camera : Node {
     int launchCount = 0;
 };
 
+// Object-wise sharding: whole flushes, largest first onto the least-loaded rank (deterministic; every rank computes
+// the same assignment from the same scene).  Returns owner rank per flush.
+std::vector<int> AssignFlushesToRanks(const std::vector<uint64_t>& flushTriangles, int rankCount);
+
 struct T3DError : std::runtime_error { int code; T3DError(int c, const std::string& m) : std::runtime_error(m), code(c) {} };
 
 }  // namespace tetra3d
