@@ -108,7 +108,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -188,7 +188,9 @@ def run_ours(args):
             table = [(f["global_flush"], f["vertex_count"]) for f in cam.Flushes()]
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            out, _ = parallel.gather_lists([col, dep], table, dst=0, out=gather_out[0])
+            out, _ = parallel.gather_lists([col, dep], table, dst=0, out=gather_out[0], n_flushes_total=len(cam.FlushOwnerRanks()))
+            if out is not None:
+                gather_out[0] = out
             e1.record(); torch.cuda.synchronize()
             tm = dict(tm); tm["gather_ms"] = e0.elapsed_time(e1)
             ms += tm["gather_ms"]
@@ -213,7 +215,6 @@ def run_ours(args):
             stage_sum[k] = stage_sum.get(k, 0.0) + v
     barrier()
     wall1 = time.perf_counter()
-    clocks = sampler.stop()
     launches_per_step = cam.LaunchCount()
     n_vertices_out = cam.VertexCount()
     vbytes = device.VertexKernelBytes()
@@ -237,6 +238,7 @@ def run_ours(args):
         h2d, d2h = device.FrameBytes()
     barrier()
     e2e_s = time.perf_counter() - e0
+    clocks = sampler.stop()      # sampled every 20 ms across both timed loops (device-resident + e2e)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -109,3 +109,18 @@ def test_unsupported_host_callbacks_fail_loudly(device):
     cam.Clear()
     with pytest.raises(t3d.T3DError):
         cam.RenderScene(scene)
+
+
+def test_multi_gpu_sharded_gather_matches_oracle():
+    """Runs only on boxes with >= 2 GPUs: tests/run_multigpu_parity.py under torchrun."""
+    import os, subprocess, sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "run_multigpu_parity.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout

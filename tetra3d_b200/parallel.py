@@ -29,28 +29,39 @@ def device_lists(cam, device_index: int) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def gather_lists(local: List[torch.Tensor], flush_table: List[Tuple[int, int]], dst: int = 0, group=None,
-                 out: Optional[List[torch.Tensor]] = None):
+                 out: Optional[List[torch.Tensor]] = None, n_flushes_total: Optional[int] = None):
     """Gathers variable-size per-rank lists to `dst`.
 
-    local:        this rank's lists (same count and byte length on one rank, e.g. [colour, depth]), uint8
+    local:        this rank's lists (same byte length on one rank, e.g. [colour, depth]), uint8
     flush_table:  this rank's (global_flush_id, vertex_count) in local order
     Returns on dst: (lists, table) where lists[i] is the concatenation over ranks 0..W-1 of list i and table maps
     global_flush_id -> (first_vertex, vertex_count) in the concatenated lists.  Other ranks get (None, None).
+
+    The only metadata exchanged is one small all_reduce: a [W + F] int64 vector holding every rank's byte count
+    and every flush's (owner rank + 1, vertex count) packed as owner * 2^40 + count.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     nbytes = int(local[0].numel())
     dev = local[0].device
-    # sizes + flush tables (tiny, host-side objects)
-    meta = [None] * world
-    dist.all_gather_object(meta, (nbytes, list(flush_table)), group=group)
-    sizes = [m[0] for m in meta]
+    if n_flushes_total is None:
+        m = torch.tensor([max([f for f, _ in flush_table], default=-1) + 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        n_flushes_total = int(m.item())
+    meta = torch.zeros(world + n_flushes_total, dtype=torch.int64)
+    meta[rank] = nbytes
+    for fid, cnt in flush_table:
+        meta[world + fid] = ((rank + 1) << 40) + int(cnt)
+    meta = meta.to(dev)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
+    meta = meta.cpu().tolist()
+    sizes = meta[:world]
     offsets = [0]
-    for s in sizes:
-        offsets.append(offsets[-1] + s)
+    for sz in sizes:
+        offsets.append(offsets[-1] + sz)
     if rank == dst:
         total = offsets[-1]
-        if out is None:
+        if out is None or out[0].numel() < total:
             out = [torch.empty(total, dtype=torch.uint8, device=dev) for _ in local]
         ops = []
         for i, t in enumerate(local):
@@ -63,12 +74,15 @@ def gather_lists(local: List[torch.Tensor], flush_table: List[Tuple[int, int]], 
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         table: Dict[int, Tuple[int, int]] = {}
-        for r in range(world):
-            v = offsets[r] // 48
-            for fid, cnt in meta[r][1]:
-                table[int(fid)] = (v, int(cnt))
-                v += int(cnt)
-        return out, table
+        cursor = [offsets[r] // 48 for r in range(world)]
+        for fid in range(n_flushes_total):
+            v = meta[world + fid]
+            if v == 0:
+                continue
+            owner, cnt = (v >> 40) - 1, v & ((1 << 40) - 1)
+            table[fid] = (cursor[owner], int(cnt))      # a rank's flushes are stored in ascending global id
+            cursor[owner] += int(cnt)
+        return [o[:total] for o in out], table
     ops = [dist.P2POp(dist.isend, t, dst, group) for t in local if nbytes]
     if ops:
         for w in dist.batch_isend_irecv(ops):
