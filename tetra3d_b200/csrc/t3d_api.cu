@@ -1,8 +1,9 @@
 // t3d_api.cu -- the C ABI of include/t3dgeo.h: context, mesh residency, per-frame arenas, pipeline.
 //
 // Per frame: the host resolves every submitted draw into a DrawRec (device pointers + arena offsets),
-// uploads the records with the light lists and bone matrices in a few async copies from pinned
-// staging, then enqueues  prep -> vertex -> cull -> keys -> radix sort -> emit  on one stream.
+// cuts the triangle arena into tiles (t3d_device.cuh: TriTile), uploads everything in one async copy from
+// pinned staging, then enqueues  prep -> vertex -> cull (+ in-tile sort for small draws) -> bin histogram
+// -> scatter -> tile scan -> emit  on one stream.
 // Results stay on the device until t3d_frame_results (pinned D2H) or are handed out as device
 // pointers by t3d_frame_results_device.
 #include "../../include/t3dgeo.h"
@@ -58,7 +59,7 @@ struct PartInfo { uint32_t triStart, triEnd, a0, nv; };
 
 struct Mesh {
     uint32_t generation = 0;
-    uint32_t nVerts = 0, nVertsPad = 0, nTris = 0, nKeys = 0;
+    uint32_t nVerts = 0, nVertsPad = 0, nTris = 0, nTrisPad = 0, nKeys = 0;
     uint32_t maxJoint = 0;
     float maxSpan = 0;
     float *pos = nullptr, *nrm = nullptr, *uv = nullptr, *col = nullptr, *wgt = nullptr, *ctr = nullptr;
@@ -90,7 +91,8 @@ struct t3d_ctx {
     bool inFrame = false, executed = false, haveResults = false;
     FrameConst fc;
     PinVec<DrawRec> hDraws;
-    PinVec<uint32_t> hVbase, hTbase, hTileV, hTileT;
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked;
+    PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
     PinVec<float> hBones;
     std::vector<LightList> lightLists;
@@ -102,12 +104,12 @@ struct t3d_ctx {
     // device arenas
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
     PinVec<uint8_t> hFrame;
-    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pTileT = nullptr;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr;
+    TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dLight, dWpos, dUnbill, dTnrm;
-    DevBuf dTdepth, dTdraw, dKeys0, dKeysA, dKeysB, dValsA, dValsB, dSortScratch, dCount;
+    DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
     DevBuf dColor, dDepth, dNormal, dTriIds;
-    const uint32_t* sortedKeys = nullptr; const uint32_t* sortedVals = nullptr;
 
     // results (pinned)
     PinVec<DrawStat> hStats;
@@ -142,6 +144,18 @@ static cudaError_t upload_padded(T** dst, const T* src, size_t nElems, size_t nP
     if (nPadded > nElems) { e = cudaMemsetAsync(*dst + nElems, 0, (nPadded - nElems) * sizeof(T), s); if (e != cudaSuccess) return e; }
     if (nElems) e = cudaMemcpyAsync(*dst, src, nElems * sizeof(T), cudaMemcpyHostToDevice, s);
     return e;
+}
+
+// AoS [n][3] on the host -> SoA planes [3][nPad] on the device (zero padded).
+template <class T>
+static cudaError_t upload_planes3(T** dst, const T* src, size_t n, size_t nPad, std::vector<T>& tmp) {
+    *dst = nullptr;
+    nPad = std::max<size_t>(nPad, 4);
+    tmp.assign(3 * nPad, T(0));
+    for (size_t i = 0; i < n; i++) { tmp[i] = src[3 * i]; tmp[nPad + i] = src[3 * i + 1]; tmp[2 * nPad + i] = src[3 * i + 2]; }
+    cudaError_t e = cudaMalloc((void**)dst, 3 * nPad * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, tmp.data(), 3 * nPad * sizeof(T), cudaMemcpyHostToDevice);
 }
 
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
@@ -179,10 +193,10 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
-                      &ctx->dTnrm, &ctx->dTdepth, &ctx->dTdraw, &ctx->dKeys0, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
-                      &ctx->dValsB, &ctx->dSortScratch, &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
+                      &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
+                      &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
-    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hTileT.release();
+    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -211,12 +225,14 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
     }
     Mesh m;
     m.generation = generation;
-    m.nVerts = d->n_verts; m.nVertsPad = (d->n_verts + 3u) & ~3u; m.nTris = d->n_tris; m.nKeys = d->n_shape_keys;
+    m.nVerts = d->n_verts; m.nVertsPad = std::max((d->n_verts + 3u) & ~3u, 4u); m.nTris = d->n_tris; m.nKeys = d->n_shape_keys;
+    m.nTrisPad = std::max((d->n_tris + 3u) & ~3u, 4u);
     m.maxSpan = d->max_span;
     const size_t nv = m.nVerts, np = m.nVertsPad;
     cudaStream_t s = ctx->stream;
-    CU(upload_padded(&m.pos, d->positions, nv * 3, np * 3, s));
-    CU(upload_padded(&m.nrm, d->normals, nv * 3, np * 3, s));
+    std::vector<float> ftmp; std::vector<uint32_t> utmp;
+    CU(upload_planes3(&m.pos, d->positions, nv, np, ftmp));
+    CU(upload_planes3(&m.nrm, d->normals, nv, np, ftmp));
     CU(upload_padded(&m.uv, d->uvs, nv * 2, np * 2, s));
     if (d->colors) CU(upload_padded(&m.col, d->colors, nv * 4, np * 4, s));
     if (d->weights) {
@@ -228,20 +244,23 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
         }
         for (size_t i = 0; i < nv * 4; i++) m.maxJoint = std::max<uint32_t>(m.maxJoint, d->bones[i]);
     }
-    CU(upload_padded(&m.idx, d->indices, (size_t)m.nTris * 3, (size_t)m.nTris * 3, s));
-    CU(upload_padded(&m.ctr, d->centers, (size_t)m.nTris * 3, (size_t)m.nTris * 3, s));
+    CU(upload_planes3(&m.idx, d->indices, (size_t)m.nTris, (size_t)m.nTrisPad, utmp));
+    CU(upload_planes3(&m.ctr, d->centers, (size_t)m.nTris, (size_t)m.nTrisPad, ftmp));
     if (m.nKeys) {
-        // keys are stored with the padded vertex stride so 4-vertex groups stay 16B-aligned
-        CU(cudaMalloc((void**)&m.keyPos, (size_t)m.nKeys * np * 3 * sizeof(float)));
-        CU(cudaMalloc((void**)&m.keyNrm, (size_t)m.nKeys * np * 3 * sizeof(float)));
+        // key k: three planes of np floats at keyPos + k * 3 * np
+        std::vector<float> kp((size_t)m.nKeys * 3 * np, 0.0f), kn((size_t)m.nKeys * 3 * np, 0.0f);
+        for (uint32_t k = 0; k < m.nKeys; k++)
+            for (size_t i = 0; i < nv; i++)
+                for (int c = 0; c < 3; c++) {
+                    kp[((size_t)k * 3 + c) * np + i] = d->key_positions[((size_t)k * nv + i) * 3 + c];
+                    kn[((size_t)k * 3 + c) * np + i] = d->key_normals[((size_t)k * nv + i) * 3 + c];
+                }
+        CU(cudaMalloc((void**)&m.keyPos, kp.size() * sizeof(float)));
+        CU(cudaMalloc((void**)&m.keyNrm, kn.size() * sizeof(float)));
         CU(cudaMalloc((void**)&m.keyW, (size_t)m.nKeys * sizeof(float)));
-        CU(cudaMemsetAsync(m.keyPos, 0, (size_t)m.nKeys * np * 3 * sizeof(float), s));
-        CU(cudaMemsetAsync(m.keyNrm, 0, (size_t)m.nKeys * np * 3 * sizeof(float), s));
+        CU(cudaMemcpy(m.keyPos, kp.data(), kp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(m.keyNrm, kn.data(), kn.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(m.keyW, 0, (size_t)m.nKeys * sizeof(float), s));
-        for (uint32_t k = 0; k < m.nKeys; k++) {
-            CU(cudaMemcpyAsync(m.keyPos + (size_t)k * np * 3, d->key_positions + (size_t)k * nv * 3, nv * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-            CU(cudaMemcpyAsync(m.keyNrm + (size_t)k * np * 3, d->key_normals + (size_t)k * nv * 3, nv * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-        }
     }
     m.parts.resize(d->n_parts);
     for (uint32_t p = 0; p < d->n_parts; p++) {
@@ -432,7 +451,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         R.idx = m.idx; R.ctr = m.ctr; R.keyPos = m.keyPos; R.keyNrm = m.keyNrm; R.keyW = m.keyW;
         R.a0 = pi.a0; R.nv = pi.nv; R.vbase = ctx->vAcc;
         R.t0 = pi.triStart; R.nt = pi.triEnd - pi.triStart; R.tbase = ctx->tAcc;
-        R.flags = flags; R.nKeys = m.nKeys; R.keyStride = m.nVertsPad;
+        R.flags = flags; R.nKeys = m.nKeys; R.vstride = m.nVertsPad; R.tstride = m.nTrisPad;
         R.boneOffset = in.bone_offset;
         const LightList& ll = ctx->lightLists[in.light_list];
         R.lightIn = ll.off; R.lightCount = ll.count; R.lightU = ctx->luAcc;
@@ -465,6 +484,44 @@ static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, 
     }
 }
 
+// Cuts the triangle arena into tiles (t3d_device.cuh).  Draws with more than TILE_TRIS triangles get
+// exclusive tiles and go through k_cull_large + the segmented counting sort; smaller draws are packed whole
+// into tiles of at most TILE_TRIS triangles and TILE_TRIS draws and are culled and sorted by k_tile_packed.
+static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
+    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear();
+    const uint32_t* tb = ctx->hTbase.p;
+    TriTile cur; cur.start = 0; cur.count = 0; cur.dFirst = 0; cur.info = 0;
+    cudaError_t e = cudaSuccess;
+    auto close = [&]() -> cudaError_t {
+        if (cur.info == 0) return cudaSuccess;
+        if (cur.count) {        // a tile of empty draws has nothing to do
+            cudaError_t e2 = ctx->hPacked.push((uint32_t)ctx->hTiles.n);
+            if (e2 != cudaSuccess) return e2;
+            e2 = ctx->hTiles.push(cur);
+            if (e2 != cudaSuccess) return e2;
+        }
+        cur.count = 0; cur.info = 0;
+        return cudaSuccess;
+    };
+    for (uint32_t d = 0; d < nDraws; d++) {
+        const uint32_t nt = tb[d + 1] - tb[d];
+        if (nt > TILE_TRIS) {
+            if ((e = close()) != cudaSuccess) return e;
+            const uint32_t n = (nt + TILE_TRIS - 1) / TILE_TRIS;
+            for (uint32_t j = 0; j < n; j++) {
+                TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
+                if ((e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
+                if ((e = ctx->hTiles.push(t)) != cudaSuccess) return e;
+            }
+            continue;
+        }
+        if (cur.info && (cur.count + nt > TILE_TRIS || cur.info >= TILE_TRIS)) { if ((e = close()) != cudaSuccess) return e; }
+        if (cur.info == 0) { cur.start = tb[d]; cur.dFirst = d; }
+        cur.count += nt; cur.info++;
+    }
+    return close();
+}
+
 int t3d_frame_execute(t3d_ctx* ctx) {
     if (!ctx) return T3D_E_INVALID;
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_execute: no open frame");
@@ -480,17 +537,15 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->h2dBytes = 0;
         return T3D_OK;
     }
-    const uint32_t totalGroups = totalV / 4;
-    const uint32_t nTilesV = (totalGroups + 255) / 256, nTilesT = (totalT + 255) / 256;
+    const uint32_t nTilesV = (totalV + VERTEX_TILE - 1) / VERTEX_TILE;
     ctx->hVbase.p[nDraws] = totalV; ctx->hVbase.n = nDraws + 1;
     ctx->hTbase.p[nDraws] = totalT; ctx->hTbase.n = nDraws + 1;
     CU(ctx->hTileV.resize(nTilesV + 1));
-    CU(ctx->hTileT.resize(nTilesT + 1));
-    build_tiles(ctx->hVbase.p, nDraws, nTilesV, 1024, ctx->hTileV.p);
-    build_tiles(ctx->hTbase.p, nDraws, nTilesT, 256, ctx->hTileT.p);
+    build_tiles(ctx->hVbase.p, nDraws, nTilesV, VERTEX_TILE, ctx->hTileV.p);
+    CU(build_tri_tiles(ctx, nDraws));
+    const uint32_t nTiles = (uint32_t)ctx->hTiles.n, nLarge = (uint32_t)ctx->hLarge.n, nPacked = (uint32_t)ctx->hPacked.n;
 
     const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
-    const SortPlan plan = sort_plan(totalT, nDraws);
 
     // arenas
     CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
@@ -501,11 +556,10 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dUnbill.ensure(4ull * std::max(ctx->anyUnbill ? totalV : 4u, 4u)));
     CU(ctx->dTnrm.ensure(16ull * std::max(normals ? totalV : 4u, 4u)));
     CU(ctx->dTdepth.ensure(4ull * totalT));
-    CU(ctx->dTdraw.ensure(4ull * totalT));
-    CU(ctx->dKeys0.ensure(4ull * totalT));
-    CU(ctx->dKeysA.ensure(4ull * totalT)); CU(ctx->dKeysB.ensure(4ull * totalT));
-    CU(ctx->dValsA.ensure(4ull * totalT)); CU(ctx->dValsB.ensure(4ull * totalT));
-    CU(ctx->dSortScratch.ensure(sort_scratch_bytes(plan)));
+    CU(ctx->dSorted.ensure(4ull * totalT));
+    CU(ctx->dHist.ensure(4ull * BIN_COUNT * std::max(nLarge, 1u)));
+    CU(ctx->dTileSurv.ensure(4ull * std::max(nTiles, 1u)));
+    CU(ctx->dTileOut.ensure(4ull * (nTiles + 1)));
     CU(ctx->dCount.ensure(256));
     CU(ctx->dColor.ensure(144ull * totalT));
     CU(ctx->dDepth.ensure(144ull * totalT));
@@ -521,9 +575,10 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     // uniforms up: pack every per-frame array into one pinned block -> one async copy
     {
         struct Seg { const void* src; size_t bytes; size_t off; };
-        Seg segs[7] = {
+        Seg segs[9] = {
             {ctx->hDraws.p, sizeof(DrawRec) * (size_t)nDraws, 0}, {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
-            {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTileT.p, 4ull * (nTilesT + 1), 0},
+            {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
+            {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0}};
         size_t total = 0;
         for (Seg& g : segs) { g.off = total; total += (g.bytes + 255) & ~(size_t)255; }
@@ -537,41 +592,45 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pVbase = reinterpret_cast<uint32_t*>(base + segs[1].off);
         ctx->pTbase = reinterpret_cast<uint32_t*>(base + segs[2].off);
         ctx->pTileV = reinterpret_cast<uint32_t*>(base + segs[3].off);
-        ctx->pTileT = reinterpret_cast<uint32_t*>(base + segs[4].off);
-        ctx->pLightsIn = reinterpret_cast<t3d_light*>(base + segs[5].off);
-        ctx->pBones = reinterpret_cast<float*>(base + segs[6].off);
+        ctx->pTiles = reinterpret_cast<TriTile*>(base + segs[4].off);
+        ctx->pLarge = reinterpret_cast<uint32_t*>(base + segs[5].off);
+        ctx->pPacked = reinterpret_cast<uint32_t*>(base + segs[6].off);
+        ctx->pLightsIn = reinterpret_cast<t3d_light*>(base + segs[7].off);
+        ctx->pBones = reinterpret_cast<float*>(base + segs[8].off);
+        ctx->h2dBytes = 0;
+        for (Seg& g : segs) ctx->h2dBytes += g.bytes;
     }
     CU(cudaEventRecord(ctx->ev[1], s));
 
+    DrawStat* stats = ctx->dStats.as<DrawStat>();
     // K0 + K1
-    launch_prep_draws(s, ctx->pDraws, nDraws, ctx->fc, ctx->pLightsIn, ctx->dLightsU.as<LightU>(), ctx->dStats.as<DrawStat>());
+    launch_prep_draws(s, ctx->pDraws, nDraws, ctx->fc, ctx->pLightsIn, ctx->dLightsU.as<LightU>(), stats);
     CU(cudaEventRecord(ctx->ev[2], s));
-    launch_vertex(s, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalGroups, ctx->fc,
+    launch_vertex(s, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->ev[3], s));
-    // K2
-    launch_cull(s, ctx->pDraws, ctx->pTbase, ctx->pTileT, totalT, ctx->fc,
-                ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), ctx->dStats.as<DrawStat>());
-    ctx->launches += 1;
+    // K2: cull (small draws are also sorted here)
+    launch_cull_large(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
+                      ctx->dTdepth.as<uint32_t>(), stats);
+    launch_tile_packed(s, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
+                       ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats);
+    ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0);
     CU(cudaEventRecord(ctx->ev[4], s));
-    // K3 + sort
-    launch_keys(s, ctx->pDraws, ctx->dStats.as<DrawStat>(), ctx->dTdepth.as<uint32_t>(), ctx->dTdraw.as<uint32_t>(), totalT, ctx->dKeys0.as<uint32_t>());
-    ctx->launches += 1;
-    ctx->launches += sort_pairs(s, plan, ctx->dKeys0.as<uint32_t>(), ctx->dKeysA.as<uint32_t>(), ctx->dValsA.as<uint32_t>(),
-                                ctx->dKeysB.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dSortScratch.p, ctx->dCount.as<uint32_t>(),
-                                &ctx->sortedKeys, &ctx->sortedVals);
+    // K3: segmented 512-bin counting sort of the large draws, then where every tile starts in the lists
+    launch_bin_hist(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>());
+    launch_scatter(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
+    launch_tile_scan(s, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+    ctx->launches += (nLarge ? 2 : 0) + 1;
     CU(cudaEventRecord(ctx->ev[5], s));
     // K4
-    launch_emit(s, ctx->pDraws, ctx->sortedKeys, ctx->sortedVals, ctx->dCount.as<uint32_t>(), totalT, ctx->fc,
-                ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+    launch_emit(s, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
+                ctx->fc, ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                 ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
-    ctx->launches += 1;
+    ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[6], s));
     CU(cudaGetLastError());
-    ctx->h2dBytes = sizeof(DrawRec) * (uint64_t)nDraws + 8ull * (nDraws + 1) + 4ull * (nTilesV + 1) + 4ull * (nTilesT + 1) +
-                    sizeof(t3d_light) * (uint64_t)ctx->hLights.n + 4ull * ctx->hBones.n;
 
     // algorithmic bytes of the fused vertex kernel (SURVEY.md 8d / DESIGN.md): static unlit 28 B/vertex
     // (pos 12 -> clip 16), static lit 52 (+ normal 12, light rgb 12), skinned lit 88 (+ weights 16, joints 8,

@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include "t3d_math.h"
+#include "../../include/t3dgeo.h"
 #include <stddef.h>
 
 namespace t3d {
@@ -58,16 +59,16 @@ struct VolumeU {
 // One render(rp): host-resolved inputs first, then the fields k_prep_draws derives.
 struct __align__(16) DrawRec {
     // ---- resolved by the host at submit ----
-    const float*    pos;        // packed float3, 16B-aligned, padded to a multiple of 4 vertices
-    const float*    nrm;
+    const float*    pos;        // SoA planes x|y|z, plane stride = vstride floats (a multiple of 4 vertices)
+    const float*    nrm;        // same layout
     const float*    uv;         // float2
     const float*    col;        // float4 or nullptr
     const float*    wgt;        // float4 or nullptr
     const uint16_t* jnt;        // ushort4 or nullptr
     const uint8_t*  ninf;       // or nullptr
-    const uint32_t* idx;        // 3 per triangle
-    const float*    ctr;        // 3 per triangle
-    const float*    keyPos;     // k * nMeshVertsPadded * 3
+    const uint32_t* idx;        // SoA planes a|b|c (Triangle.VertexIndexA/B/C), plane stride = tstride
+    const float*    ctr;        // SoA planes x|y|z (Triangle.Center), plane stride = tstride
+    const float*    keyPos;     // k keys x 3 planes x vstride
     const float*    keyNrm;
     const float*    keyW;       // k
     uint32_t a0;                // first mesh vertex of the aligned range (multiple of 4)
@@ -78,13 +79,14 @@ struct __align__(16) DrawRec {
     uint32_t tbase;             // first slot in the per-frame triangle arenas
     uint32_t flags;             // T3D_DRAW_*
     uint32_t nKeys;
-    uint32_t keyStride;         // padded mesh vertex count (floats3 per key)
+    uint32_t vstride;           // padded mesh vertex count: plane stride of pos / nrm / shape keys
     uint32_t boneOffset;
     uint32_t lightIn;           // first t3d_light of the draw's list
     uint32_t lightCount;
     uint32_t lightU;            // first LightU slot of this draw
     uint8_t  sortMode, lightingMode, lvMode, pad0;
-    uint32_t padA[2];           // keeps the float4-loaded arrays below 16B-aligned
+    uint32_t tstride;           // padded mesh triangle count: plane stride of idx / ctr
+    uint32_t padA;              // keeps the float4-loaded arrays below 16B-aligned
     float transform[16];
     float worldRot[16];
     float color[4];
@@ -105,16 +107,47 @@ static_assert(offsetof(DrawRec, transform) % 16 == 0 && offsetof(DrawRec, worldR
               sizeof(DrawRec) % 16 == 0, "DrawRec arrays are read with 128-bit loads");
 static_assert(sizeof(LightU) == 64, "LightU is read as four float4");
 
-// Per-draw reduction state written by the cull kernel.
+// Per-draw reduction state written by the cull kernels.
 struct DrawStat {
     uint32_t minBits;           // float bits of minDepth (depth >= 0, so uint order == float order)
     uint32_t maxBits;
     uint32_t survivors;
-    uint32_t pad;
+    uint32_t done;              // tiles of this draw whose bin histogram is complete (k_bin_hist)
 };
+
+// Triangle tiles: the unit of work of the cull / sort / emit kernels.  A tile is a run of at most
+// TILE_TRIS consecutive slots of the frame's triangle arena that never cuts a small draw: a draw with
+// more than TILE_TRIS triangles owns ceil(nt / TILE_TRIS) exclusive tiles ("large"), smaller draws are
+// packed whole, several to a tile ("packed").
+struct __align__(16) TriTile {
+    uint32_t start;             // first triangle slot
+    uint32_t count;             // slots in the tile (<= TILE_TRIS)
+    uint32_t dFirst;            // first draw
+    uint32_t info;              // packed: number of draws (<= TILE_TRIS); large: TILE_LARGE | tile index in the draw
+};
+static const uint32_t TILE_TRIS = 1024;
+static const uint32_t TILE_LARGE = 0x80000000u;
 
 static const uint32_t KEY_CULLED = 0xFFFFFFFFu;
 static const int BIN_BITS = 9;      // 512 bins, sortingTriangles.go:166-168
 static const int BIN_COUNT = 512;
+
+#ifdef __CUDACC__
+// 512-bin key of one surviving triangle (sortingTriangles.go:38-64).  BackToFront visits bins 511..0
+// (sortingTriangles.go:101), so the key is the visiting rank of the bin: ascending key == draw order.
+__device__ __forceinline__ uint32_t bin_key(uint32_t depthBits, uint32_t minBits, uint32_t maxBits, uint32_t sortMode) {
+    const float minRange = __uint_as_float(minBits);
+    const float maxRange = __uint_as_float(maxBits);
+    float rangeDiff = maxRange - minRange;
+    if (rangeDiff == 0) rangeDiff += 0.001f;
+    uint32_t bin = 0;
+    if (sortMode != T3D_SORT_NONE) {
+        const float dd = (__uint_as_float(depthBits) - minRange) / rangeDiff * (float)BIN_COUNT;
+        const float tt = clampf(dd, 0.0f, (float)(BIN_COUNT - 1));
+        bin = (uint32_t)(int)tt;
+    }
+    return (sortMode == T3D_SORT_BACK_TO_FRONT) ? (BIN_COUNT - 1 - bin) : bin;
+}
+#endif
 
 }  // namespace t3d

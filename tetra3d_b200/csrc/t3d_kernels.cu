@@ -2,12 +2,15 @@
 //
 //   k_prep_draws  one thread per draw      per-draw uniforms of Model.ProcessVertices (model.go:616-708) and
 //                                           light.beginModel (light.go:175-189, 326-330)
-//   k_vertex      4 vertices per thread     fused skin + transform + light (model.go:559-596, 757-822;
+//   k_vertex      one vertex per thread     fused skin + transform + light (model.go:559-596, 757-822;
 //                                           light.go:116-120, 191-258, 332-360, 583-663)
-//   k_cull        one thread per triangle   near/far, side, backface cull + depth key + per-draw min/max
-//                                           (model.go:855-969)
-//   k_keys        one thread per triangle   512-bin key (sortingTriangles.go:38-64)
+//   k_cull_large  one tile per block        near/far, side, backface cull + depth key + per-draw min/max
+//                                           (model.go:855-969) for draws that own whole tiles
+//   k_tile_packed one tile per block        the same cull fused with the 512-bin sort
+//                                           (sortingTriangles.go:38-125) for draws that fit inside a tile
 //   k_emit        one thread per corner     colour/depth/normal vertex lists (camera.go:1646-1820)
+//
+// Mesh arrays are SoA planes (x|y|z, a|b|c) so one-element-per-thread loads are fully coalesced.
 //
 // Built with -fmad=false: no multiply-add contraction anywhere (see t3d_device.cuh).
 #include "t3d_device.cuh"
@@ -135,24 +138,13 @@ k_prep_draws(DrawRec* __restrict__ draws, uint32_t nDraws, const __grid_constant
         if (haveSun) m4_store(sunRot, R.worldRot);
     }
 
-    DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.pad = 0;   // model.go:710-711
+    DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
     stats[d] = st;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: fused skin + transform + light, 4 consecutive vertices per thread
+// K1: fused skin + transform + light, one vertex per thread
 // ------------------------------------------------------------------------------------------------
-
-struct Vtx4 { float x[4], y[4], z[4]; };
-
-// 4 packed float3 (48 B, 16B-aligned) -> SoA registers
-__device__ __forceinline__ void load_vec3x4(const float* p, Vtx4& o) {
-    float4 a = ldg4(p), b = ldg4(p + 4), c = ldg4(p + 8);
-    o.x[0] = a.x; o.y[0] = a.y; o.z[0] = a.z;
-    o.x[1] = a.w; o.y[1] = b.x; o.z[1] = b.y;
-    o.x[2] = b.z; o.y[2] = b.w; o.z[2] = c.x;
-    o.x[3] = c.y; o.y[3] = c.z; o.z[3] = c.w;
-}
 
 // LightVolume.VertexLight (light.go:583-663); rare, kept out of line.
 __device__ __noinline__ void light_volume(const DrawRec& R, const LightU& U, const VolumeU* __restrict__ vols,
@@ -197,93 +189,85 @@ __device__ __noinline__ void light_volume(const DrawRec& R, const LightU& U, con
 // Model.skinVertex (model.go:559-596) for one vertex.
 __device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4 w, ushort4 j, int n,
                                          Vec3 p, Vec3 nIn, Vec3& pOut, Vec3& nOut) {
-    float K[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) K[i] = 0.0f;
+    float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0, k3 = k0;
     const float ws[4] = {w.x, w.y, w.z, w.w};
     const uint16_t js[4] = {j.x, j.y, j.z, j.w};
 #pragma unroll
     for (int b = 0; b < 4; b++) {
         if (b >= n) break;
-        float weightPerc = ws[b];
+        const float weightPerc = ws[b];
         if (weightPerc == 0.0f) continue;
         const float4* B = reinterpret_cast<const float4*>(bones + 16 * (size_t)js[b]);
-        float4 r0 = __ldg(B), r1 = __ldg(B + 1), r2 = __ldg(B + 2), r3 = __ldg(B + 3);
-        const float I[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-        if (weightPerc == 1.0f) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) K[i] = I[i];
-            break;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) K[i] = K[i] + I[i] * weightPerc;      // Scale then Add (matrix.go:639-661)
+        const float4 r0 = __ldg(B), r1 = __ldg(B + 1), r2 = __ldg(B + 2), r3 = __ldg(B + 3);
+        if (weightPerc == 1.0f) { k0 = r0; k1 = r1; k2 = r2; k3 = r3; break; }
+        // Scale then Add (matrix.go:639-661)
+        k0.x = k0.x + r0.x * weightPerc; k0.y = k0.y + r0.y * weightPerc; k0.z = k0.z + r0.z * weightPerc; k0.w = k0.w + r0.w * weightPerc;
+        k1.x = k1.x + r1.x * weightPerc; k1.y = k1.y + r1.y * weightPerc; k1.z = k1.z + r1.z * weightPerc; k1.w = k1.w + r1.w * weightPerc;
+        k2.x = k2.x + r2.x * weightPerc; k2.y = k2.y + r2.y * weightPerc; k2.z = k2.z + r2.z * weightPerc; k2.w = k2.w + r2.w * weightPerc;
+        k3.x = k3.x + r3.x * weightPerc; k3.y = k3.y + r3.y * weightPerc; k3.z = k3.z + r3.z * weightPerc; k3.w = k3.w + r3.w * weightPerc;
     }
-    pOut.X = K[0] * p.X + K[4] * p.Y + K[8] * p.Z + K[12];                 // MultVec, matrix.go:619
-    pOut.Y = K[1] * p.X + K[5] * p.Y + K[9] * p.Z + K[13];
-    pOut.Z = K[2] * p.X + K[6] * p.Y + K[10] * p.Z + K[14];
+    pOut.X = k0.x * p.X + k1.x * p.Y + k2.x * p.Z + k3.x;                  // MultVec, matrix.go:619
+    pOut.Y = k0.y * p.X + k1.y * p.Y + k2.y * p.Z + k3.y;
+    pOut.Z = k0.z * p.X + k1.z * p.Y + k2.z * p.Z + k3.z;
     // skinMatrix[3] = {0,0,0,1} (model.go:587-590)
-    nOut.X = K[0] * nIn.X + K[4] * nIn.Y + K[8] * nIn.Z + 0.0f;
-    nOut.Y = K[1] * nIn.X + K[5] * nIn.Y + K[9] * nIn.Z + 0.0f;
-    nOut.Z = K[2] * nIn.X + K[6] * nIn.Y + K[10] * nIn.Z + 0.0f;
+    nOut.X = k0.x * nIn.X + k1.x * nIn.Y + k2.x * nIn.Z + 0.0f;
+    nOut.Y = k0.y * nIn.X + k1.y * nIn.Y + k2.y * nIn.Z + 0.0f;
+    nOut.Z = k0.z * nIn.X + k1.z * nIn.Y + k2.z * nIn.Z + 0.0f;
 }
 
-__global__ void __launch_bounds__(256)
+static const int VERTEX_BLOCK = 256;
+
+__global__ void __launch_bounds__(VERTEX_BLOCK)
 k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
-         uint32_t totalGroups, const __grid_constant__ FrameConst fc,
+         uint32_t totalV, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
-    if (g >= totalGroups) return;
-    const uint32_t slot = g * 4u;
+    const uint32_t slot = blockIdx.x * (uint32_t)VERTEX_BLOCK + threadIdx.x;
+    if (slot >= totalV) return;
     const uint32_t d = find_draw(vbase, __ldg(&tileFirst[blockIdx.x]), __ldg(&tileFirst[blockIdx.x + 1]), slot);
     const DrawRec& R = draws[d];
     const uint32_t flags = R.flags;
     const bool skinned = flags & T3D_DRAW_SKINNED;
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
-    const uint32_t mv = R.a0 + (slot - R.vbase);      // first of 4 mesh vertices
+    const uint32_t mv = R.a0 + (slot - R.vbase);
+    const uint32_t vs = R.vstride;
 
-    Vtx4 P, N;
-    load_vec3x4(R.pos + 3 * (size_t)mv, P);
+    Vec3 P, N = v3(0, 0, 0);
+    {
+        const float* pp = R.pos + mv;
+        P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs));
+    }
     const bool needN = lit || skinned;
-    if (needN) load_vec3x4(R.nrm + 3 * (size_t)mv, N);
-    else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) { N.x[k] = 0; N.y[k] = 0; N.z[k] = 0; }
+    if (needN) {
+        const float* np = R.nrm + mv;
+        N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
     }
 
     // shape keys (mesh.go:796-822)
     for (uint32_t k = 0; k < R.nKeys; k++) {
         const float w = __ldg(&R.keyW[k]);
-        Vtx4 KP; load_vec3x4(R.keyPos + ((size_t)k * R.keyStride + mv) * 3, KP);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { P.x[i] += KP.x[i] * w; P.y[i] += KP.y[i] * w; P.z[i] += KP.z[i] * w; }
+        const float* kp = R.keyPos + (size_t)k * 3 * vs + mv;
+        P.X += __ldg(kp) * w; P.Y += __ldg(kp + vs) * w; P.Z += __ldg(kp + 2 * (size_t)vs) * w;
         if (needN) {
-            Vtx4 KN; load_vec3x4(R.keyNrm + ((size_t)k * R.keyStride + mv) * 3, KN);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { N.x[i] += KN.x[i] * w; N.y[i] += KN.y[i] * w; N.z[i] += KN.z[i] * w; }
+            const float* kn = R.keyNrm + (size_t)k * 3 * vs + mv;
+            N.X += __ldg(kn) * w; N.Y += __ldg(kn + vs) * w; N.Z += __ldg(kn + 2 * (size_t)vs) * w;
         }
     }
 
     // skinning (model.go:760-775): positions and normals become world-space
     if (skinned) {
-        const uint32_t ninf4 = R.ninf ? __ldg(reinterpret_cast<const uint32_t*>(R.ninf + mv)) : 0x04040404u;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float4 w = ldg4(R.wgt + 4 * (size_t)(mv + i));
-            ushort4 j = __ldg(reinterpret_cast<const ushort4*>(R.jnt + 4 * (size_t)(mv + i)));
-            int n = (ninf4 >> (8 * i)) & 0xFF;
-            Vec3 po, no;
-            skin_one(bones + 16 * (size_t)R.boneOffset, w, j, n, v3(P.x[i], P.y[i], P.z[i]), v3(N.x[i], N.y[i], N.z[i]), po, no);
-            P.x[i] = po.X; P.y[i] = po.Y; P.z[i] = po.Z;
-            N.x[i] = no.X; N.y[i] = no.Y; N.z[i] = no.Z;
-            wposOut[slot + i] = make_float4(po.X, po.Y, po.Z, 0.0f);
-        }
+        const float4 w = ldg4(R.wgt + 4 * (size_t)mv);
+        const ushort4 j = __ldg(reinterpret_cast<const ushort4*>(R.jnt + 4 * (size_t)mv));
+        const int n = R.ninf ? (int)__ldg(R.ninf + mv) : 4;
+        Vec3 po, no;
+        skin_one(bones + 16 * (size_t)R.boneOffset, w, j, n, P, N, po, no);
+        P = po; N = no;
+        wposOut[slot] = make_float4(po.X, po.Y, po.Z, 0.0f);
     }
 
     // clip = [x y z 1] * M (model.go:772-775 / 795-798)
     {
-        const float* Mp = skinned ? fc.vp : R.mvp;
         float4 m0, m1, m2, m3;
         if (skinned) {
             m0 = make_float4(fc.vp[0], fc.vp[1], fc.vp[2], fc.vp[3]);
@@ -291,50 +275,39 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
             m2 = make_float4(fc.vp[8], fc.vp[9], fc.vp[10], fc.vp[11]);
             m3 = make_float4(fc.vp[12], fc.vp[13], fc.vp[14], fc.vp[15]);
         } else {
-            m0 = ldg4(Mp); m1 = ldg4(Mp + 4); m2 = ldg4(Mp + 8); m3 = ldg4(Mp + 12);
+            m0 = ldg4(R.mvp); m1 = ldg4(R.mvp + 4); m2 = ldg4(R.mvp + 8); m3 = ldg4(R.mvp + 12);
         }
         const float snap = fc.snapping;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float4 c;
-            c.x = m0.x * P.x[i] + m1.x * P.y[i] + m2.x * P.z[i] + m3.x;
-            c.y = m0.y * P.x[i] + m1.y * P.y[i] + m2.y * P.z[i] + m3.y;
-            c.z = m0.z * P.x[i] + m1.z * P.y[i] + m2.z * P.z[i] + m3.z;
-            c.w = m0.w * P.x[i] + m1.w * P.y[i] + m2.w * P.z[i] + m3.w;
-            if (snap > 0) {                                             // model.go:807-812
-                c.x = roundf(c.x * snap) / snap;
-                c.y = roundf(c.y * snap) / snap;
-                c.z = roundf(c.z * snap) / snap;
-            }
-            clipOut[slot + i] = c;
+        float4 c;
+        c.x = m0.x * P.X + m1.x * P.Y + m2.x * P.Z + m3.x;
+        c.y = m0.y * P.X + m1.y * P.Y + m2.y * P.Z + m3.y;
+        c.z = m0.z * P.X + m1.z * P.Y + m2.z * P.Z + m3.z;
+        c.w = m0.w * P.X + m1.w * P.Y + m2.w * P.Z + m3.w;
+        if (snap > 0) {                                                 // model.go:807-812
+            c.x = roundf(c.x * snap) / snap;
+            c.y = roundf(c.y * snap) / snap;
+            c.z = roundf(c.z * snap) / snap;
         }
+        clipOut[slot] = c;
         if (!skinned && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) {       // model.go:800-803
-            float4 u = ldg4(R.unbill);
-            float4 o;
-            o.x = u.x * P.x[0] + u.y * P.y[0] + u.z * P.z[0] + u.w;
-            o.y = u.x * P.x[1] + u.y * P.y[1] + u.z * P.z[1] + u.w;
-            o.z = u.x * P.x[2] + u.y * P.y[2] + u.z * P.z[2] + u.w;
-            o.w = u.x * P.x[3] + u.y * P.y[3] + u.z * P.z[3] + u.w;
-            *reinterpret_cast<float4*>(unbillOut + slot) = o;
+            const float4 u = ldg4(R.unbill);
+            unbillOut[slot] = u.x * P.X + u.y * P.Y + u.z * P.Z + u.w;
         }
         if (fc.camFlags & T3D_CAM_RENDER_NORMALS) {                     // model.go:814-818 (uses vert)
-            float4 c0 = ldg4(R.nrmRot), c1 = ldg4(R.nrmRot + 4), c2 = ldg4(R.nrmRot + 8);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float4 t;
-                t.x = c0.x * P.x[i] + c0.y * P.y[i] + c0.z * P.z[i] + c0.w;
-                t.y = c1.x * P.x[i] + c1.y * P.y[i] + c1.z * P.z[i] + c1.w;
-                t.z = c2.x * P.x[i] + c2.y * P.y[i] + c2.z * P.z[i] + c2.w;
-                t.w = 0.0f;
-                tnrmOut[slot + i] = t;
-            }
+            const float4 c0 = ldg4(R.nrmRot), c1 = ldg4(R.nrmRot + 4), c2 = ldg4(R.nrmRot + 8);
+            float4 t;
+            t.x = c0.x * P.X + c0.y * P.Y + c0.z * P.Z + c0.w;
+            t.y = c1.x * P.X + c1.y * P.Y + c1.z * P.Z + c1.w;
+            t.z = c2.x * P.X + c2.y * P.Y + c2.z * P.Z + c2.w;
+            t.w = 0.0f;
+            tnrmOut[slot] = t;
         }
     }
 
     if (!lit) return;
 
     // per-vertex lighting (camera.go:1610-1644): start at (0,0,0,1), add every light of the draw's list
-    float lr[4] = {0, 0, 0, 0}, lg[4] = {0, 0, 0, 0}, lb[4] = {0, 0, 0, 0};
+    float lr = 0, lg = 0, lb = 0;
     const uint8_t lightingMode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
     const uint32_t nL = R.lightCount;
     const float4* LUp = reinterpret_cast<const float4*>(lightsU + R.lightU);
@@ -343,208 +316,315 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
         const uint32_t type = __float_as_uint(q0.x);
         const float cR = q0.y, cG = q0.z, cB = q0.w, energy = q1.x;
         if (type == T3D_LIGHT_AMBIENT) {                                // light.go:110-120
-            const float ar = cR * energy, ag = cG * energy, ab = cB * energy;
-#pragma unroll
-            for (int i = 0; i < 4; i++) { lr[i] += ar; lg[i] += ag; lb[i] += ab; }
+            lr += cR * energy; lg += cG * energy; lb += cB * energy;
         } else if (type == T3D_LIGHT_POINT) {                           // light.go:191-258
             const Vec3 wp = v3(q1.y, q1.z, q1.w);
             const float range = q2.x, range2 = q2.y;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                Vec3 vertPos = v3(P.x[i], P.y[i], P.z[i]);
-                Vec3 vertNormal = v3(N.x[i], N.y[i], N.z[i]);
-                float distance = v3_dist2(wp, vertPos);
-                if (range > 0) { if (distance > range2) continue; }
-                else { if (1.0f / distance * energy < 0.001f) continue; }
-                Vec3 lightVec = v3_unit(v3_sub(wp, vertPos));
-                if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) vertNormal = lightVec;
-                float diffuse = v3_dot(vertNormal, lightVec);
-                if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuse = fabsf(diffuse);
-                if (diffuse > 0) {
-                    float diffuseFactor = diffuse * (1.0f / (1.0f + (0.1f * distance))) * 2.0f;
-                    if (range2 > 0) diffuseFactor *= clampf((range2 - distance) / distance, 0.0f, 1.0f);
-                    lr[i] += cR * diffuseFactor * energy;
-                    lg[i] += cG * diffuseFactor * energy;
-                    lb[i] += cB * diffuseFactor * energy;
-                }
+            Vec3 vertNormal = N;
+            const float distance = v3_dist2(wp, P);
+            if (range > 0) { if (distance > range2) continue; }
+            else { if (1.0f / distance * energy < 0.001f) continue; }
+            const Vec3 lightVec = v3_unit(v3_sub(wp, P));
+            if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) vertNormal = lightVec;
+            float diffuse = v3_dot(vertNormal, lightVec);
+            if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuse = fabsf(diffuse);
+            if (diffuse > 0) {
+                float diffuseFactor = diffuse * (1.0f / (1.0f + (0.1f * distance))) * 2.0f;
+                if (range2 > 0) diffuseFactor *= clampf((range2 - distance) / distance, 0.0f, 1.0f);
+                lr += cR * diffuseFactor * energy;
+                lg += cG * diffuseFactor * energy;
+                lb += cB * diffuseFactor * energy;
             }
         } else if (type == T3D_LIGHT_DIRECTIONAL) {                     // light.go:332-360
             const float4 q3 = __ldg(LUp + 4 * li + 3);
             const Vec3 fwd = v3(q2.z, q2.w, q3.x);
-            float4 s0, s1, s2, s3;
-            if (!skinned) { s0 = ldg4(R.worldRot); s1 = ldg4(R.worldRot + 4); s2 = ldg4(R.worldRot + 8); s3 = ldg4(R.worldRot + 12); }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                Vec3 normal;
-                if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) normal = fwd;
-                else if (skinned) normal = v3(N.x[i], N.y[i], N.z[i]);
-                else {
-                    normal.X = s0.x * N.x[i] + s1.x * N.y[i] + s2.x * N.z[i] + s3.x;
-                    normal.Y = s0.y * N.x[i] + s1.y * N.y[i] + s2.y * N.z[i] + s3.y;
-                    normal.Z = s0.z * N.x[i] + s1.z * N.y[i] + s2.z * N.z[i] + s3.z;
-                }
-                float diffuseFactor = v3_dot(normal, fwd);
-                if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuseFactor = fabsf(diffuseFactor);
-                if (diffuseFactor <= 0) continue;
-                lr[i] += cR * diffuseFactor * energy;
-                lg[i] += cG * diffuseFactor * energy;
-                lb[i] += cB * diffuseFactor * energy;
+            Vec3 normal;
+            if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) normal = fwd;
+            else if (skinned) normal = N;
+            else {
+                const float4 s0 = ldg4(R.worldRot), s1 = ldg4(R.worldRot + 4), s2 = ldg4(R.worldRot + 8), s3 = ldg4(R.worldRot + 12);
+                normal.X = s0.x * N.X + s1.x * N.Y + s2.x * N.Z + s3.x;
+                normal.Y = s0.y * N.X + s1.y * N.Y + s2.y * N.Z + s3.y;
+                normal.Z = s0.z * N.X + s1.z * N.Y + s2.z * N.Z + s3.z;
             }
+            float diffuseFactor = v3_dot(normal, fwd);
+            if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuseFactor = fabsf(diffuseFactor);
+            if (diffuseFactor <= 0) continue;
+            lr += cR * diffuseFactor * energy;
+            lg += cG * diffuseFactor * energy;
+            lb += cB * diffuseFactor * energy;
         } else if (type == T3D_LIGHT_VOLUME) {
             const LightU U = lightsU[R.lightU + li];
-#pragma unroll 1
-            for (int i = 0; i < 4; i++)
-                light_volume(R, U, vols, v3(P.x[i], P.y[i], P.z[i]), v3(N.x[i], N.y[i], N.z[i]), skinned, lr[i], lg[i], lb[i]);
+            light_volume(R, U, vols, P, N, skinned, lr, lg, lb);
         }
     }
+    lightOut[slot] = make_float4(lr, lg, lb, 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: cull + depth key (model.go:855-969)
+// ------------------------------------------------------------------------------------------------
+
+// The keep / drop decision of one triangle from its three clip-space corners (model.go:866-925).
+__device__ __forceinline__ bool cull_keep(const float4 c0, const float4 c1, const float4 c2, bool backface, float nearP, float farP) {
+    float w0 = c0.w, w1 = c1.w, w2 = c2.w;                              // model.go:866-875
+    if (w0 < 0) w0 = 0.000001f;
+    if (w1 < 0) w1 = 0.000001f;
+    if (w2 < 0) w2 = 0.000001f;
+    const float x0 = c0.x / w0, y0 = c0.y / w0;
+    const float x1 = c1.x / w1, y1 = c1.y / w1;
+    const float x2 = c2.x / w2, y2 = c2.y / w2;
+    bool keep = (c0.z + 1.0f >= nearP && c0.z < farP) || (c1.z + 1.0f >= nearP && c1.z < farP) ||
+                (c2.z + 1.0f >= nearP && c2.z < farP);                  // model.go:877-879
+    if (keep && ((x0 < -0.5f && x1 < -0.5f && x2 < -0.5f) || (x0 > 0.5f && x1 > 0.5f && x2 > 0.5f) ||
+                 (y0 < -0.5f && y1 < -0.5f && y2 < -0.5f) || (y0 > 0.5f && y1 > 0.5f && y2 > 0.5f)))
+        keep = false;                                                   // model.go:891-894
+    if (keep && backface) {                                             // model.go:902-925
+        const float n0x = x0 - x1, n0y = y0 - y1, n1x = x1 - x2, n1y = y1 - y2;
+        const float nor = (n0x * n1y) - (n1x * n0y);
+        if (nor < 0) keep = false;
+    }
+    return keep;
+}
+
+// Depth of a skinned triangle: distance from the camera to the mean of its skinned corners (model.go:840-864, 941-946).
+__device__ __forceinline__ float skinned_depth(const float4 p0, const float4 p1, const float4 p2, const float* camPos) {
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    sx += p0.x; sy += p0.y; sz += p0.z;
+    sx += p1.x; sy += p1.y; sz += p1.z;
+    sx += p2.x; sy += p2.y; sz += p2.z;
+    const float dx = camPos[0] - (sx / 3.0f), dy = camPos[1] - (sy / 3.0f), dz = camPos[2] - (sz / 3.0f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+static const int TILE_THREADS = 256;
+static const int TILE_ROUNDS = TILE_TRIS / TILE_THREADS;        // triangles per thread
+
+// Large draws: one exclusive tile per block, TILE_ROUNDS triangles per thread, all loads of a thread issued
+// before the first use.  Depth bits (or KEY_CULLED) go to tdepth; min / max / survivors are reduced per
+// block and merged into DrawStat with three atomics.
+__global__ void __launch_bounds__(TILE_THREADS)
+k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
+             const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float4* __restrict__ wpos,
+             uint32_t* __restrict__ tdepth, DrawStat* __restrict__ stats) {
+    __shared__ uint32_t sMin[TILE_THREADS / 32], sMax[TILE_THREADS / 32], sCnt[TILE_THREADS / 32];
+    const TriTile T = tiles[__ldg(&largeList[blockIdx.x])];
+    const DrawRec& R = draws[T.dFirst];
+    const uint32_t flags = R.flags;
+    const bool skinned = flags & T3D_DRAW_SKINNED;
+    const bool backface = (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING);
+    const uint32_t ts = R.tstride;
+    const uint32_t mt0 = R.t0 + (T.start - R.tbase);
+    const uint32_t vb = R.vbase - R.a0;
+    const uint32_t* ip = R.idx + mt0;
+    const float* cp = R.ctr + mt0;
+    const float icx = R.invCam[0], icy = R.invCam[1], icz = R.invCam[2];
+
+    uint32_t ia[TILE_ROUNDS], ib[TILE_ROUNDS], ic[TILE_ROUNDS];
+    float cx[TILE_ROUNDS], cy[TILE_ROUNDS], cz[TILE_ROUNDS];
 #pragma unroll
-    for (int i = 0; i < 4; i++) lightOut[slot + i] = make_float4(lr[i], lg[i], lb[i], 1.0f);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: cull + depth key + per-draw min/max (model.go:855-969)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_cull(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ tileFirst,
-       uint32_t totalTris, const __grid_constant__ FrameConst fc,
-       const float4* __restrict__ clip, const float4* __restrict__ wpos,
-       uint32_t* __restrict__ tdepth, uint32_t* __restrict__ tdraw, DrawStat* __restrict__ stats) {
-    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
-    const bool active = t < totalTris;
-    uint32_t d = 0;
-    bool keep = false;
-    float depth = 0.0f;
-    if (active) {
-        d = find_draw(tbase, __ldg(&tileFirst[blockIdx.x]), __ldg(&tileFirst[blockIdx.x + 1]), t);
-        const DrawRec& R = draws[d];
-        const uint32_t mt = R.t0 + (t - R.tbase);
-        const uint32_t i0 = __ldg(&R.idx[3 * (size_t)mt]), i1 = __ldg(&R.idx[3 * (size_t)mt + 1]), i2 = __ldg(&R.idx[3 * (size_t)mt + 2]);
-        const uint32_t vb = R.vbase - R.a0;
-        const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
-
-        float w0 = c0.w, w1 = c1.w, w2 = c2.w;                          // model.go:866-875
-        if (w0 < 0) w0 = 0.000001f;
-        if (w1 < 0) w1 = 0.000001f;
-        if (w2 < 0) w2 = 0.000001f;
-        const float x0 = c0.x / w0, y0 = c0.y / w0;
-        const float x1 = c1.x / w1, y1 = c1.y / w1;
-        const float x2 = c2.x / w2, y2 = c2.y / w2;
-        const float nearP = fc.nearP, farP = fc.farP;
-        const bool inRange = (c0.z + 1.0f >= nearP && c0.z < farP) || (c1.z + 1.0f >= nearP && c1.z < farP) ||
-                             (c2.z + 1.0f >= nearP && c2.z < farP);    // model.go:877-879
-        keep = inRange;
-        if (keep && ((x0 < -0.5f && x1 < -0.5f && x2 < -0.5f) || (x0 > 0.5f && x1 > 0.5f && x2 > 0.5f) ||
-                     (y0 < -0.5f && y1 < -0.5f && y2 < -0.5f) || (y0 > 0.5f && y1 > 0.5f && y2 > 0.5f)))
-            keep = false;                                               // model.go:891-894
-        if (keep && (R.flags & T3D_DRAW_HAS_MATERIAL) && (R.flags & T3D_DRAW_BACKFACE_CULLING)) {   // model.go:902-925
-            const float n0x = x0 - x1, n0y = y0 - y1, n1x = x1 - x2, n1y = y1 - y2;
-            const float nor = (n0x * n1y) - (n1x * n0y);
-            if (nor < 0) keep = false;
+    for (int r = 0; r < TILE_ROUNDS; r++) {
+        const uint32_t i = r * TILE_THREADS + threadIdx.x;
+        ia[r] = ib[r] = ic[r] = 0; cx[r] = cy[r] = cz[r] = 0.0f;
+        if (i < T.count) {
+            ia[r] = __ldg(ip + i); ib[r] = __ldg(ip + ts + i); ic[r] = __ldg(ip + 2 * (size_t)ts + i);
+            if (!skinned) { cx[r] = __ldg(cp + i); cy[r] = __ldg(cp + ts + i); cz[r] = __ldg(cp + 2 * (size_t)ts + i); }
         }
-        if (keep) {                                                     // model.go:933-955
-            if (R.flags & T3D_DRAW_SKINNED) {
-                const float4 p0 = __ldg(&wpos[vb + i0]), p1 = __ldg(&wpos[vb + i1]), p2 = __ldg(&wpos[vb + i2]);
-                float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-                sx += p0.x; sy += p0.y; sz += p0.z;
-                sx += p1.x; sy += p1.y; sz += p1.z;
-                sx += p2.x; sy += p2.y; sz += p2.z;
-                const float dx = fc.camPos[0] - (sx / 3.0f), dy = fc.camPos[1] - (sy / 3.0f), dz = fc.camPos[2] - (sz / 3.0f);
-                depth = dx * dx + dy * dy + dz * dz;
-            } else {
-                const float* C = R.ctr + 3 * (size_t)mt;
-                const float dx = R.invCam[0] - __ldg(C), dy = R.invCam[1] - __ldg(C + 1), dz = R.invCam[2] - __ldg(C + 2);
-                depth = dx * dx + dy * dy + dz * dz;
-            }
-            if (isnan(depth) || isinf(depth)) keep = false;            // model.go:957-960
-        }
-        tdepth[t] = keep ? __float_as_uint(depth) : KEY_CULLED;
-        tdraw[t] = d;
     }
-
-    // per-draw min / max / survivor count, aggregated per warp when the warp sits inside one draw
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u, cnt = 0u;
+#pragma unroll
+    for (int r = 0; r < TILE_ROUNDS; r++) {
+        const uint32_t i = r * TILE_THREADS + threadIdx.x;
+        if (i < T.count) {
+            const float4 c0 = __ldg(&clip[vb + ia[r]]), c1 = __ldg(&clip[vb + ib[r]]), c2 = __ldg(&clip[vb + ic[r]]);
+            bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+            float depth = 0.0f;
+            if (keep) {                                                 // model.go:933-955
+                if (skinned) depth = skinned_depth(__ldg(&wpos[vb + ia[r]]), __ldg(&wpos[vb + ib[r]]), __ldg(&wpos[vb + ic[r]]), fc.camPos);
+                else { const float dx = icx - cx[r], dy = icy - cy[r], dz = icz - cz[r]; depth = dx * dx + dy * dy + dz * dz; }
+                if (isnan(depth) || isinf(depth)) keep = false;        // model.go:957-960
+            }
+            const uint32_t bits = __float_as_uint(depth);
+            tdepth[T.start + i] = keep ? bits : KEY_CULLED;
+            if (keep) { mn = min(mn, bits); mx = max(mx, bits); cnt++; }
+        }
+    }
     const unsigned full = 0xFFFFFFFFu;
-    const uint32_t d0 = __shfl_sync(full, d, 0);
-    const bool uniform = __all_sync(full, (!active) || d == d0);
-    const uint32_t bits = __float_as_uint(depth);
-    if (uniform) {
-        const unsigned km = __ballot_sync(full, keep);
-        if (km) {
-            uint32_t mn = keep ? bits : 0xFFFFFFFFu, mx = keep ? bits : 0u;
-            mn = __reduce_min_sync(full, mn);
-            mx = __reduce_max_sync(full, mx);
-            if ((threadIdx.x & 31) == 0) {
-                atomicMin(&stats[d0].minBits, mn);
-                atomicMax(&stats[d0].maxBits, mx);
-                atomicAdd(&stats[d0].survivors, (uint32_t)__popc(km));
-            }
+    mn = __reduce_min_sync(full, mn); mx = __reduce_max_sync(full, mx); cnt = __reduce_add_sync(full, cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sMin[warp] = mn; sMax[warp] = mx; sCnt[warp] = cnt; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < TILE_THREADS / 32 ? sMin[lane] : 0xFFFFFFFFu;
+        mx = lane < TILE_THREADS / 32 ? sMax[lane] : 0u;
+        cnt = lane < TILE_THREADS / 32 ? sCnt[lane] : 0u;
+        mn = __reduce_min_sync(full, mn); mx = __reduce_max_sync(full, mx); cnt = __reduce_add_sync(full, cnt);
+        if (lane == 0 && cnt) {
+            atomicMin(&stats[T.dFirst].minBits, mn);
+            atomicMax(&stats[T.dFirst].maxBits, mx);
+            atomicAdd(&stats[T.dFirst].survivors, cnt);
         }
-    } else if (keep) {
-        atomicMin(&stats[d].minBits, bits);
-        atomicMax(&stats[d].maxBits, bits);
-        atomicAdd(&stats[d].survivors, 1u);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3: 512-bin key (sortingTriangles.go:38-64); BackToFront visits bins 511..0 (sortingTriangles.go:101)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_keys(const DrawRec* __restrict__ draws, const DrawStat* __restrict__ stats, const uint32_t* __restrict__ tdepth,
-       const uint32_t* __restrict__ tdraw, uint32_t totalTris, uint32_t* __restrict__ keys) {
-    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
-    if (t >= totalTris) return;
-    const uint32_t bits = tdepth[t];
-    uint32_t key = KEY_CULLED;
-    if (bits != KEY_CULLED) {
-        const uint32_t d = tdraw[t];
-        const uint32_t sortMode = draws[d].sortMode;
-        const float minRange = __uint_as_float(stats[d].minBits);
-        const float maxRange = __uint_as_float(stats[d].maxBits);
-        float rangeDiff = maxRange - minRange;
-        if (rangeDiff == 0) rangeDiff += 0.001f;
-        uint32_t bin = 0;
-        if (sortMode != T3D_SORT_NONE) {
-            float dd = (__uint_as_float(bits) - minRange) / rangeDiff * (float)BIN_COUNT;
-            float tt = clampf(dd, 0.0f, (float)(BIN_COUNT - 1));
-            bin = (uint32_t)(int)tt;
+// Packed tiles: every draw of the tile lies wholly inside it, so cull, per-draw min / max, binning and the
+// stable (draw, bin) ordering all happen in shared memory.  The order is a bitonic sort of the composite
+//   culled(1) | draw-in-tile(10) | bin rank(10) | slot-in-tile(10)
+// whose low bits make it stable; survivors come out first, in (draw, bin, arrival) order.
+static const uint32_t PK_CULLED = 1u << 30;
+__global__ void __launch_bounds__(TILE_THREADS)
+k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tbase, const TriTile* __restrict__ tiles,
+              const uint32_t* __restrict__ packedList, const __grid_constant__ FrameConst fc,
+              const float4* __restrict__ clip, const float4* __restrict__ wpos,
+              uint32_t* __restrict__ sorted, uint32_t* __restrict__ tileSurv, DrawStat* __restrict__ stats) {
+    __shared__ uint32_t sBase[TILE_TRIS + 1];       // tbase of the tile's draws
+    __shared__ uint32_t sKey[TILE_TRIS];            // depth bits, then composite keys
+    __shared__ uint32_t sMin[TILE_TRIS], sMax[TILE_TRIS];
+    __shared__ uint16_t sSeg[TILE_TRIS];
+    __shared__ uint32_t sCnt[TILE_TRIS];
+    __shared__ uint32_t sTotal;
+    const uint32_t tileId = __ldg(&packedList[blockIdx.x]);
+    const TriTile T = tiles[tileId];
+    const uint32_t nSeg = T.info;
+    const unsigned full = 0xFFFFFFFFu;
+
+    for (uint32_t s = threadIdx.x; s <= nSeg; s += TILE_THREADS) sBase[s] = __ldg(&tbase[T.dFirst + s]);
+    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) { sMin[s] = 0x7F7FFFFFu; sMax[s] = 0u; sCnt[s] = 0; }
+    if (threadIdx.x == 0) sTotal = 0;
+    __syncthreads();
+
+    // ---- cull + depth ----
+#pragma unroll 1
+    for (int r = 0; r < TILE_ROUNDS; r++) {
+        const uint32_t i = r * TILE_THREADS + threadIdx.x;
+        const bool active = i < T.count;
+        uint32_t seg = 0xFFFFu, bits = KEY_CULLED;
+        bool keep = false;
+        if (active) {
+            const uint32_t slot = T.start + i;
+            uint32_t lo = 0, hi = nSeg - 1;                            // largest seg with sBase[seg] <= slot
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (sBase[mid] <= slot) lo = mid; else hi = mid - 1; }
+            seg = lo;
+            const DrawRec& R = draws[T.dFirst + seg];
+            const uint32_t flags = R.flags;
+            const uint32_t ts = R.tstride;
+            const uint32_t mt = R.t0 + (slot - R.tbase);
+            const uint32_t vb = R.vbase - R.a0;
+            const uint32_t i0 = __ldg(R.idx + mt), i1 = __ldg(R.idx + ts + mt), i2 = __ldg(R.idx + 2 * (size_t)ts + mt);
+            const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
+            keep = cull_keep(c0, c1, c2, (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING), fc.nearP, fc.farP);
+            if (keep) {
+                float depth;
+                if (flags & T3D_DRAW_SKINNED) depth = skinned_depth(__ldg(&wpos[vb + i0]), __ldg(&wpos[vb + i1]), __ldg(&wpos[vb + i2]), fc.camPos);
+                else {
+                    const float dx = R.invCam[0] - __ldg(R.ctr + mt), dy = R.invCam[1] - __ldg(R.ctr + ts + mt), dz = R.invCam[2] - __ldg(R.ctr + 2 * (size_t)ts + mt);
+                    depth = dx * dx + dy * dy + dz * dz;
+                }
+                if (isnan(depth) || isinf(depth)) keep = false;
+                else bits = __float_as_uint(depth);
+            }
+            sSeg[i] = (uint16_t)seg;
         }
-        const uint32_t binKey = (sortMode == T3D_SORT_BACK_TO_FRONT) ? (BIN_COUNT - 1 - bin) : bin;
-        key = (d << BIN_BITS) | binKey;
+        sKey[i] = keep ? bits : KEY_CULLED;
+        // per-draw min / max / survivors: one set of shared atomics per warp when the warp sits in one draw
+        const uint32_t seg0 = __shfl_sync(full, seg, 0);
+        const bool uniform = __all_sync(full, (!active) || seg == seg0);
+        if (uniform) {
+            const unsigned km = __ballot_sync(full, keep);
+            if (km) {
+                const uint32_t mn = __reduce_min_sync(full, keep ? bits : 0xFFFFFFFFu);
+                const uint32_t mx = __reduce_max_sync(full, keep ? bits : 0u);
+                if ((threadIdx.x & 31) == 0) { atomicMin(&sMin[seg0], mn); atomicMax(&sMax[seg0], mx); atomicAdd(&sCnt[seg0], (uint32_t)__popc(km)); }
+            }
+        } else if (keep) {
+            atomicMin(&sMin[seg], bits); atomicMax(&sMax[seg], bits); atomicAdd(&sCnt[seg], 1u);
+        }
     }
-    keys[t] = key;
+    __syncthreads();
+
+    // ---- composite keys ----
+    uint32_t n2 = 32;
+    while (n2 < T.count) n2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += TILE_THREADS) {
+        uint32_t key = 0xFFFFFFFFu;                                     // padding sorts last
+        if (i < T.count) {
+            const uint32_t bits = sKey[i], seg = sSeg[i];
+            if (bits == KEY_CULLED) key = PK_CULLED | (seg << 20) | i;
+            else key = (seg << 20) | (bin_key(bits, sMin[seg], sMax[seg], draws[T.dFirst + seg].sortMode) << 10) | i;
+        }
+        sKey[i] = key;
+    }
+    __syncthreads();
+
+    // ---- bitonic sort, ascending ----
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += TILE_THREADS) {
+                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t hi = lo | j;
+                const uint32_t a = sKey[lo], b = sKey[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > b) == up) { sKey[lo] = b; sKey[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- survivors out: value = draw-in-tile << 20 | bin rank << 10 | slot-in-tile ----
+    uint32_t mine = 0;
+    for (uint32_t i = threadIdx.x; i < T.count; i += TILE_THREADS) {
+        const uint32_t key = sKey[i];
+        if (key < PK_CULLED) { sorted[T.start + i] = key; mine++; }
+    }
+    mine = __reduce_add_sync(full, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sTotal, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tileSurv[tileId] = sTotal;
+    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) {
+        DrawStat st; st.minBits = sMin[s]; st.maxBits = sMax[s]; st.survivors = sCnt[s]; st.done = 0;
+        stats[T.dFirst + s] = st;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4: emit (camera.go:1646-1820), one thread per output vertex
 // ------------------------------------------------------------------------------------------------
+// Blocks walk the tiles: block b covers output corners [q*256, q*256+256) of tile b / EMIT_PER_TILE.  The
+// i-th surviving triangle of a tile is sorted[tile.start + i]; its place in the lists is tileOut[tile] + i.
+static const int EMIT_PER_TILE = 3 * TILE_TRIS / 256;
 __global__ void __launch_bounds__(256)
-k_emit(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedTris,
-       const uint32_t* __restrict__ nSurvivors, const __grid_constant__ FrameConst fc,
+k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
+       const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const __grid_constant__ FrameConst fc,
        const float4* __restrict__ clip, const float4* __restrict__ light, const float* __restrict__ unbill,
        const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
        uint32_t* __restrict__ triIds) {
-    const uint32_t o = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t n = *nSurvivors;
-    if (o >= 3u * n) return;
-    const uint32_t k = o / 3u, c = o - 3u * k;
-    const uint32_t key = __ldg(&sortedKeys[k]);
-    const uint32_t t = __ldg(&sortedTris[k]);
-    const uint32_t d = key >> BIN_BITS;
+    const uint32_t tileId = blockIdx.x / EMIT_PER_TILE;
+    const uint32_t v = (blockIdx.x % EMIT_PER_TILE) * 256u + threadIdx.x;
+    const uint32_t nSurv = __ldg(&tileSurv[tileId]);
+    const uint32_t k = v / 3u, c = v - 3u * k;
+    if (k >= nSurv) return;
+    const TriTile T = tiles[tileId];
+    const uint32_t val = __ldg(&sorted[T.start + k]);
+    uint32_t d, tslot;
+    if (T.info & TILE_LARGE) { d = T.dFirst; tslot = val; }
+    else { d = T.dFirst + (val >> 20); tslot = T.start + (val & 1023u); }
+    const uint32_t outTri = __ldg(&tileOut[tileId]) + k;
+    const uint32_t o = 3u * outTri + c;
     const DrawRec& R = draws[d];
-    const uint32_t mt = R.t0 + (t - R.tbase);
-    const uint32_t vi = __ldg(&R.idx[3 * (size_t)mt + c]);
+    const uint32_t mt = R.t0 + (tslot - R.tbase);
+    const uint32_t vi = __ldg(R.idx + (size_t)c * R.tstride + mt);
     const uint32_t slot = R.vbase + (vi - R.a0);
-    const float4 T = __ldg(&clip[slot]);
-    if (c == 0) triIds[k] = mt;
+    const float4 Tc = __ldg(&clip[slot]);
+    if (c == 0) triIds[outTri] = mt;
 
     const bool persp = fc.camFlags & T3D_CAM_PERSPECTIVE;
     const bool pcuv = fc.camFlags & T3D_CAM_PERSP_CORRECT_UV;
-    float w = T.w;                                                      // camera.go:1655-1666
+    float w = Tc.w;                                                     // camera.go:1655-1666
     if (!persp) w = 1.0f;
     if (w < 0) w = 0.001f;
-    const float dx = (T.x / w) * fc.camW + fc.halfW;                    // camera.go:1674-1675
-    const float dy = (T.y / -w) * fc.camH + fc.halfH;
+    const float dx = (Tc.x / w) * fc.camW + fc.halfW;                   // camera.go:1674-1675
+    const float dy = (Tc.y / -w) * fc.camH + fc.halfH;
 
     const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
     float uvU, uvV, custom0 = 0.0f;
@@ -569,13 +649,13 @@ k_emit(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ sortedKey
 
     float4 dcol = make_float4(0, 0, 0, 0);
     if (fc.camFlags & T3D_CAM_RENDER_DEPTH) {                           // camera.go:1744-1782
-        float vertexDepth = T.z;
+        float vertexDepth = Tc.z;
         if ((R.flags & T3D_DRAW_HAS_MATERIAL) && (R.flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) vertexDepth = __ldg(&unbill[slot]);
         float depth = (vertexDepth + fc.depthMargin) / fc.camSpread;
         if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
         dcol = make_float4(depth, depth, depth, 1.0f);
     } else if (fc.worldPresent && fc.fogOn) {                           // camera.go:1784-1814
-        float depth = (T.z + fc.depthMargin) / fc.camSpread;
+        float depth = (Tc.z + fc.depthMargin) / fc.camSpread;
         if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
         depth = fc.fogRange[0] + ((fc.fogRange[1] - fc.fogRange[0]) * 1.0f - depth);
         if (fc.fogMode == T3D_FOG_ADD) {
@@ -612,33 +692,33 @@ void launch_prep_draws(cudaStream_t s, DrawRec* draws, uint32_t nDraws, const Fr
 }
 
 void launch_vertex(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
-                   uint32_t totalGroups, const FrameConst& fc, const LightU* lightsU, const float* bones,
+                   uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float4* light, float4* wpos, float* unbill, float4* tnrm) {
-    if (!totalGroups) return;
-    k_vertex<<<cdiv(totalGroups, 256), 256, 0, s>>>(draws, vbase, tileFirst, totalGroups, fc, lightsU, bones, vols,
-                                                    clip, light, wpos, unbill, tnrm);
+    if (!totalV) return;
+    k_vertex<<<cdiv(totalV, VERTEX_BLOCK), VERTEX_BLOCK, 0, s>>>(draws, vbase, tileFirst, totalV, fc, lightsU, bones, vols,
+                                                                 clip, light, wpos, unbill, tnrm);
 }
 
-void launch_cull(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, const uint32_t* tileFirst,
-                 uint32_t totalTris, const FrameConst& fc, const float4* clip, const float4* wpos,
-                 uint32_t* tdepth, uint32_t* tdraw, DrawStat* stats) {
-    if (!totalTris) return;
-    k_cull<<<cdiv(totalTris, 256), 256, 0, s>>>(draws, tbase, tileFirst, totalTris, fc, clip, wpos, tdepth, tdraw, stats);
+void launch_cull_large(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+                       const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats) {
+    if (!nLarge) return;
+    k_cull_large<<<nLarge, TILE_THREADS, 0, s>>>(draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
 }
 
-void launch_keys(cudaStream_t s, const DrawRec* draws, const DrawStat* stats, const uint32_t* tdepth,
-                 const uint32_t* tdraw, uint32_t totalTris, uint32_t* keys) {
-    if (!totalTris) return;
-    k_keys<<<cdiv(totalTris, 256), 256, 0, s>>>(draws, stats, tdepth, tdraw, totalTris, keys);
+void launch_tile_packed(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
+                        const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
+                        const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats) {
+    if (!nPacked) return;
+    k_tile_packed<<<nPacked, TILE_THREADS, 0, s>>>(draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
 }
 
-void launch_emit(cudaStream_t s, const DrawRec* draws, const uint32_t* sortedKeys, const uint32_t* sortedTris,
-                 const uint32_t* nSurvivors, uint32_t maxTris, const FrameConst& fc, const float4* clip,
+void launch_emit(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
+                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds) {
-    if (!maxTris) return;
-    k_emit<<<cdiv(3ull * maxTris, 256), 256, 0, s>>>(draws, sortedKeys, sortedTris, nSurvivors, fc, clip, light, unbill,
-                                                     tnrm, colorList, depthList, normalList, triIds);
+    if (!nTiles) return;
+    k_emit<<<nTiles * EMIT_PER_TILE, 256, 0, s>>>(draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm,
+                                                  colorList, depthList, normalList, triIds);
 }
 
 }  // namespace t3d

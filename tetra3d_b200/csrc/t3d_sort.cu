@@ -1,37 +1,29 @@
-// t3d_sort.cu -- stable LSD radix sort on quantised depth keys (sm_100a).
+// t3d_sort.cu -- the per-draw 512-bin depth sort for draws that span several tiles (sm_100a).
 //
-// The reference's sortingTriangleBucket (sortingTriangles.go:38-125) is a counting sort on a 9-bit
-// bin with arrival order preserved inside a bin, run once per MeshPart.  Here all draws of a frame are
-// sorted together: key = (draw ordinal << 9) | binKey, value = triangle slot.  Triangles enter in
-// (draw, triangle index) order, the sort is stable and pass 0 drops culled keys while keeping order
-// (order-preserving compaction), so inside every (draw, bin) group the reference's arrival order holds.
+// The reference's sortingTriangleBucket (sortingTriangles.go:38-125) is a counting sort on a 9-bit bin
+// with arrival order preserved inside a bin, run once per MeshPart.  Triangles of a frame already sit in
+// the arena draw after draw, so the frame-wide order is one *segmented* counting sort pass:
 //
-// One pass = k_hist (per-tile digit histogram) -> k_scan (exclusive scan over tiles per digit) ->
-// k_scatter (stable in-tile ranking with warp match + scatter).  Integer work only.
+//   k_bin_hist   per tile: bin every survivor (the draw's min / max are final after k_cull_large), count
+//                the tile's bins; the last tile of a draw to finish turns the draw's [tiles x 512] counts
+//                into offsets (bins in visiting order, tiles in arena order inside a bin).
+//   k_scatter    per tile: stable in-tile rank of every survivor inside its bin (warp match + per-warp
+//                counts), then sorted[tbase + offset + rank] = triangle slot.
+//   k_tile_scan  exclusive scan of the per-tile survivor counts: where each tile's triangles start in
+//                the output lists, and the frame's total.
+//
+// Draws that fit inside one tile never come here: k_tile_packed (t3d_kernels.cu) culls and sorts them in
+// shared memory.  Integer work only, apart from the bin expression itself.
 #include "t3d_internal.h"
+#include "../../include/t3dgeo.h"
 
 namespace t3d {
 
 static const int SORT_THREADS = 256;
-static const int SORT_ROUNDS = SORT_TILE / SORT_THREADS;
-static const int RADIX = 256;
+static const int SORT_ROUNDS = TILE_TRIS / SORT_THREADS;
+static const int BINS_PER_THREAD = BIN_COUNT / SORT_THREADS;
 
-SortPlan sort_plan(uint32_t maxItems, uint32_t nDraws) {
-    SortPlan p;
-    p.maxItems = maxItems;
-    p.nTiles = (maxItems + SORT_TILE - 1) / SORT_TILE;
-    uint32_t drawBits = 0;
-    while ((1ull << drawBits) < (uint64_t)nDraws) drawBits++;
-    p.keyBits = BIN_BITS + drawBits;
-    p.nPasses = (p.keyBits + 7) / 8;
-    return p;
-}
-
-size_t sort_scratch_bytes(const SortPlan& p) {
-    // hist[RADIX][nTiles] + binTotal[RADIX]
-    return ((size_t)RADIX * (p.nTiles ? p.nTiles : 1) + RADIX) * sizeof(uint32_t);
-}
-
+// Exclusive scan of one value per thread over a 256-thread block.
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* sWarp /*8*/, uint32_t* total) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,140 +48,182 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     return warpBase + inc - v;
 }
 
-template <bool FIRST>
+// hist row r belongs to large tile largeList[r]; the rows of one draw are consecutive.
 __global__ void __launch_bounds__(SORT_THREADS)
-k_hist(const uint32_t* __restrict__ keys, uint32_t nHost, const uint32_t* __restrict__ dCount, uint32_t shift,
-       uint32_t nTiles, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sHist[RADIX];
-    const uint32_t n = FIRST ? nHost : *dCount;
-    const uint32_t tile = blockIdx.x;
-    sHist[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t base = tile * SORT_TILE;
-    if (base < n) {
-#pragma unroll 4
-        for (int r = 0; r < SORT_ROUNDS; r++) {
-            const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
-            if (i < n) {
-                const uint32_t k = __ldg(&keys[i]);
-                if (!FIRST || k != KEY_CULLED) atomicAdd(&sHist[(k >> shift) & (RADIX - 1)], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    hist[(size_t)threadIdx.x * nTiles + tile] = sHist[threadIdx.x];
-}
-
-// One block per digit: exclusive scan of hist[digit][0..nTiles) in place; row total to binTotal[digit].
-__global__ void __launch_bounds__(SORT_THREADS)
-k_scan(uint32_t* __restrict__ hist, uint32_t nTiles, uint32_t* __restrict__ binTotal) {
+k_bin_hist(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
+           DrawStat* __restrict__ stats, uint32_t* __restrict__ tdepth, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sHist[BIN_COUNT];
     __shared__ uint32_t sWarp[8];
-    uint32_t* row = hist + (size_t)blockIdx.x * nTiles;
-    const uint32_t per = (nTiles + SORT_THREADS - 1) / SORT_THREADS;
-    const uint32_t lo = threadIdx.x * per;
-    const uint32_t hi = min(lo + per, nTiles);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += row[i];
-    uint32_t total;
-    uint32_t run = block_exclusive_scan_256(sum, sWarp, &total);
-    for (uint32_t i = lo; i < hi; i++) { uint32_t c = row[i]; row[i] = run; run += c; }
-    if (threadIdx.x == 0) binTotal[blockIdx.x] = total;
-}
-
-template <bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS)
-k_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, uint32_t nHost,
-          uint32_t* __restrict__ dCount, uint32_t shift, uint32_t nTiles, const uint32_t* __restrict__ hist,
-          const uint32_t* __restrict__ binTotal, uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut) {
-    __shared__ uint32_t sBase[RADIX];
-    __shared__ uint32_t sCnt[8][RADIX];
-    __shared__ uint32_t sOff[8][RADIX];
-    __shared__ uint32_t sWarp[8];
-    const unsigned full = 0xFFFFFFFFu;
-    const uint32_t tile = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // digit base = exclusive scan of the per-digit totals + this tile's offset inside the digit
-    uint32_t total;
-    const uint32_t bt = binTotal[threadIdx.x];
-    const uint32_t binBase = block_exclusive_scan_256(bt, sWarp, &total);
-    // n must be read before block 0 overwrites *dCount (FIRST pass defines it, later passes keep it)
-    const uint32_t n = FIRST ? nHost : *dCount;
-    if (FIRST && tile == 0 && threadIdx.x == 0) *dCount = total;
-    sBase[threadIdx.x] = binBase + hist[(size_t)threadIdx.x * nTiles + tile];
+    __shared__ uint32_t sLast;
+    const uint32_t row = blockIdx.x;
+    const TriTile T = tiles[__ldg(&largeList[row])];
+    const uint32_t d = T.dFirst;
+    const uint32_t sortMode = draws[d].sortMode;
+    const uint32_t nt = draws[d].nt;
+    const uint32_t minBits = stats[d].minBits, maxBits = stats[d].maxBits;
 #pragma unroll
-    for (int w = 0; w < 8; w++) sCnt[w][threadIdx.x] = 0;
+    for (int q = 0; q < BINS_PER_THREAD; q++) sHist[threadIdx.x + q * SORT_THREADS] = 0;
     __syncthreads();
-
-    const uint32_t base = tile * SORT_TILE;
-    if (base >= n) return;
-
+#pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
-        const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
-        uint32_t key = KEY_CULLED, val = 0;
-        bool valid = false;
-        if (i < n) {
-            key = __ldg(&keysIn[i]);
-            valid = !FIRST || key != KEY_CULLED;
-            val = FIRST ? i : __ldg(&valsIn[i]);
-        }
-        const uint32_t digit = valid ? ((key >> shift) & (RADIX - 1)) : 0xFFFFFFFFu;
-        const unsigned peers = __match_any_sync(full, digit);
-        const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rankInWarp == 0) sCnt[warp][digit] = __popc(peers);
-        __syncthreads();
-        {   // thread == digit: offsets of each warp's group, advance the running base, clear the counts
-            uint32_t run = sBase[threadIdx.x];
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                const uint32_t c = sCnt[w][threadIdx.x];
-                sOff[w][threadIdx.x] = run;
-                run += c;
-                sCnt[w][threadIdx.x] = 0;
+        const uint32_t i = r * SORT_THREADS + threadIdx.x;
+        if (i < T.count) {
+            const uint32_t bits = tdepth[T.start + i];
+            if (bits != KEY_CULLED) {
+                const uint32_t key = bin_key(bits, minBits, maxBits, sortMode);
+                atomicAdd(&sHist[key], 1u);
+                tdepth[T.start + i] = key;          // the depth is not needed again; k_scatter reads the bin rank
             }
-            sBase[threadIdx.x] = run;
         }
-        __syncthreads();
-        if (valid) {
-            const uint32_t pos = sOff[warp][digit] + rankInWarp;
-            keysOut[pos] = key;
-            valsOut[pos] = val;
+    }
+    __syncthreads();
+    uint32_t* myRow = hist + (size_t)row * BIN_COUNT;
+#pragma unroll
+    for (int q = 0; q < BINS_PER_THREAD; q++) myRow[threadIdx.x + q * SORT_THREADS] = sHist[threadIdx.x + q * SORT_THREADS];
+    __threadfence();
+    __syncthreads();
+    const uint32_t nTilesOfDraw = (nt + TILE_TRIS - 1) / TILE_TRIS;
+    if (threadIdx.x == 0) sLast = (atomicAdd(&stats[d].done, 1u) == nTilesOfDraw - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+
+    // Last tile of the draw: counts -> offsets.  offset(tile, bin) = sum of the draw's earlier bins over all
+    // tiles + the same bin in earlier tiles.
+    uint32_t* rows = hist + (size_t)(row - (T.info & ~TILE_LARGE)) * BIN_COUNT;
+    // thread owns bins [BINS_PER_THREAD * tid, +BINS_PER_THREAD) so that the block scan runs in bin order
+    uint32_t tot[BINS_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < BINS_PER_THREAD; q++) {
+        const uint32_t b = threadIdx.x * BINS_PER_THREAD + q;
+        uint32_t run = 0;
+        for (uint32_t t = 0; t < nTilesOfDraw; t++) {
+            uint32_t* p = rows + (size_t)t * BIN_COUNT + b;
+            const uint32_t c = __ldcg(p);
+            *p = run;
+            run += c;
         }
-        // sOff is rewritten only after the next round's first barrier; sCnt was cleared above.
+        tot[q] = run;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < BINS_PER_THREAD; q++) sum += tot[q];
+    uint32_t base = block_exclusive_scan_256(sum, sWarp, nullptr);
+#pragma unroll
+    for (int q = 0; q < BINS_PER_THREAD; q++) {
+        const uint32_t b = threadIdx.x * BINS_PER_THREAD + q;
+        if (base) for (uint32_t t = 0; t < nTilesOfDraw; t++) rows[(size_t)t * BIN_COUNT + b] += base;
+        base += tot[q];
     }
 }
 
-int sort_pairs(cudaStream_t s, const SortPlan& p, const uint32_t* keysIn, uint32_t* keysA, uint32_t* valsA,
-               uint32_t* keysB, uint32_t* valsB, void* scratch, uint32_t* dCount,
-               const uint32_t** outKeys, const uint32_t** outVals) {
-    int launches = 0;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(scratch);
-    uint32_t* binTotal = hist + (size_t)RADIX * (p.nTiles ? p.nTiles : 1);
-    if (p.maxItems == 0) {
-        cudaMemsetAsync(dCount, 0, sizeof(uint32_t), s);
-        *outKeys = keysA; *outVals = valsA;
-        return 0;
+__global__ void __launch_bounds__(SORT_THREADS)
+k_scatter(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
+          const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ hist, uint32_t* __restrict__ sorted) {
+    // sCnt[(round, warp)][bin]: how many of that warp's lanes hold the bin in that round, then (after the
+    // scan over (round, warp), which is arrival order) the in-tile rank of the group's first lane.
+    __shared__ uint16_t sCnt[SORT_ROUNDS * 8][BIN_COUNT];
+    __shared__ uint32_t sBase[BIN_COUNT];
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t row = blockIdx.x;
+    const TriTile T = tiles[__ldg(&largeList[row])];
+    const uint32_t tb = draws[T.dFirst].tbase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(&sCnt[0][0]);
+        for (uint32_t i = threadIdx.x; i < SORT_ROUNDS * 8 * BIN_COUNT / 2; i += SORT_THREADS) z[i] = 0;
+#pragma unroll
+        for (int q = 0; q < BINS_PER_THREAD; q++) sBase[threadIdx.x + q * SORT_THREADS] = hist[(size_t)row * BIN_COUNT + threadIdx.x + q * SORT_THREADS];
     }
-    const uint32_t* curK = keysIn;
-    const uint32_t* curV = nullptr;
-    uint32_t* dstK = keysA; uint32_t* dstV = valsA;
-    for (uint32_t pass = 0; pass < p.nPasses; pass++) {
-        const uint32_t shift = 8 * pass;
-        if (pass == 0) {
-            k_hist<true><<<p.nTiles, SORT_THREADS, 0, s>>>(curK, p.maxItems, dCount, shift, p.nTiles, hist);
-            k_scan<<<RADIX, SORT_THREADS, 0, s>>>(hist, p.nTiles, binTotal);
-            k_scatter<true><<<p.nTiles, SORT_THREADS, 0, s>>>(curK, curV, p.maxItems, dCount, shift, p.nTiles, hist, binTotal, dstK, dstV);
-        } else {
-            k_hist<false><<<p.nTiles, SORT_THREADS, 0, s>>>(curK, p.maxItems, dCount, shift, p.nTiles, hist);
-            k_scan<<<RADIX, SORT_THREADS, 0, s>>>(hist, p.nTiles, binTotal);
-            k_scatter<false><<<p.nTiles, SORT_THREADS, 0, s>>>(curK, curV, p.maxItems, dCount, shift, p.nTiles, hist, binTotal, dstK, dstV);
+    __syncthreads();
+    uint32_t key[SORT_ROUNDS], rank[SORT_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = r * SORT_THREADS + threadIdx.x;
+        key[r] = (i < T.count) ? __ldg(&tkeys[T.start + i]) : KEY_CULLED;
+        const unsigned peers = __match_any_sync(full, key[r]);
+        rank[r] = __popc(peers & ((1u << lane) - 1u));
+        if (key[r] != KEY_CULLED && rank[r] == 0) sCnt[r * 8 + warp][key[r]] = (uint16_t)__popc(peers);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BINS_PER_THREAD; q++) {
+        const uint32_t b = threadIdx.x + q * SORT_THREADS;
+        uint32_t run = 0;
+#pragma unroll 8
+        for (int e = 0; e < SORT_ROUNDS * 8; e++) { const uint32_t c = sCnt[e][b]; sCnt[e][b] = (uint16_t)run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        if (key[r] != KEY_CULLED) {
+            const uint32_t i = r * SORT_THREADS + threadIdx.x;
+            sorted[tb + sBase[key[r]] + sCnt[r * 8 + warp][key[r]] + rank[r]] = T.start + i;
         }
-        launches += 3;
-        curK = dstK; curV = dstV;
-        if (dstK == keysA) { dstK = keysB; dstV = valsB; } else { dstK = keysA; dstV = valsA; }
     }
-    *outKeys = curK; *outVals = curV;
-    return launches;
+}
+
+// One block.  Large tile j of a draw holds survivors [j * TILE_TRIS, ...) of the draw's sorted run; packed
+// tiles wrote their own counts.
+__global__ void __launch_bounds__(1024)
+k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* __restrict__ stats,
+            uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ dCount) {
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sCarry;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nTiles; base += 1024) {
+        const uint32_t t = base + threadIdx.x;
+        uint32_t c = 0;
+        if (t < nTiles) {
+            const TriTile T = tiles[t];
+            if (T.info & TILE_LARGE) {
+                const uint32_t surv = stats[T.dFirst].survivors, off = (T.info & ~TILE_LARGE) * TILE_TRIS;
+                c = surv > off ? min(surv - off, TILE_TRIS) : 0u;
+                tileSurv[t] = c;
+            } else {
+                c = tileSurv[t];
+            }
+        }
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, inc, o); if (lane >= o) inc += n; }
+        if (lane == 31) sWarp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sWarp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, wi, o); if (lane >= o) wi += n; }
+            sWarp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t carry = sCarry;
+        const uint32_t excl = carry + sWarp[warp] + inc - c;
+        if (t < nTiles) tileOut[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) sCarry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { tileOut[nTiles] = sCarry; *dCount = sCarry; }
+}
+
+void launch_bin_hist(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+                     DrawStat* stats, uint32_t* tdepth, uint32_t* hist) {
+    if (!nLarge) return;
+    k_bin_hist<<<nLarge, SORT_THREADS, 0, s>>>(draws, tiles, largeList, stats, tdepth, hist);
+}
+
+void launch_scatter(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+                    const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted) {
+    if (!nLarge) return;
+    k_scatter<<<nLarge, SORT_THREADS, 0, s>>>(draws, tiles, largeList, tkeys, hist, sorted);
+}
+
+void launch_tile_scan(cudaStream_t s, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
+                      uint32_t* tileOut, uint32_t* dCount) {
+    k_tile_scan<<<1, 1024, 0, s>>>(tiles, nTiles, stats, tileSurv, tileOut, dCount);
 }
 
 }  // namespace t3d
