@@ -189,16 +189,18 @@ typedef struct t3d_draw_result {
     float    min_depth, max_depth;  /* model.go:710-711, 962-967 (+-MaxFloat32 when nothing survived) */
 } t3d_draw_result;
 
-/* CUDA-event timings of the last executed frame, milliseconds (DebugInfo mirrors, camera.go:41-48). */
+/* CUDA-event timings of the last executed frame, milliseconds (DebugInfo mirrors, camera.go:41-48).
+ * total_ms is always measured; the per-stage fields only when t3d_set_stage_timings(ctx, 1) was in force
+ * for the frame (zero otherwise). */
 typedef struct t3d_timings {
-    float upload_ms;    /* H2D of the frame's uniforms */
-    float prep_ms;      /* K0 per-draw uniforms */
+    float upload_ms;    /* always ~0: the uniforms are fetched over PCIe by the first kernel (part of prep_ms) */
+    float prep_ms;      /* K0 fetch of the frame's uniforms + per-draw uniforms */
     float vertex_ms;    /* K1 fused skin/transform/light */
     float cull_ms;      /* K2 cull + depth + min/max */
     float sort_ms;      /* key + radix sort */
     float emit_ms;      /* K4 emit */
     float download_ms;  /* D2H of results (0 when results stayed on device) */
-    float total_ms;     /* first kernel to last kernel */
+    float total_ms;     /* first kernel to last kernel (the device time of the frame) */
 } t3d_timings;
 
 typedef struct t3d_frame_output {
@@ -252,6 +254,10 @@ int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings)
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
 
 /* ---- introspection (tests, profiling) ------------------------------------------------------------ */
+/* Stage timings put a CUDA event between the kernels of a frame, which serialises them; by default
+ * (enabled = 0) the kernels are chained with programmatic dependent launches and only total_ms is measured.
+ * Replaces: the per-phase timers of DebugInfo (camera.go:41-48). */
+int t3d_set_stage_timings(t3d_ctx* ctx, int enabled);
 /* Copies the per-vertex intermediates of draw `draw` (globalVertexTransforms tetra3d.go:30 and
  * mesh.vertexLights) for mesh vertices [vtx_start, vtx_end) of its part into clip4 / light4
  * (4 floats per vertex each; either may be NULL). */

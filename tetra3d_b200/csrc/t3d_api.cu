@@ -39,11 +39,12 @@ struct DevBuf {
 // growable pinned host array that keeps its contents
 template <class T> struct PinVec {
     T* p = nullptr; size_t n = 0, cap = 0;
+    bool mapped = false;        // also readable by kernels through UVA (cudaHostGetDevicePointer)
     cudaError_t reserve(size_t want) {
         if (want <= cap) return cudaSuccess;
         size_t nc = std::max(want, cap * 2 + 16);
         T* q = nullptr;
-        cudaError_t e = cudaHostAlloc((void**)&q, nc * sizeof(T), cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc((void**)&q, nc * sizeof(T), mapped ? (cudaHostAllocMapped | cudaHostAllocPortable) : cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
         if (p) { memcpy(q, p, n * sizeof(T)); cudaFreeHost(p); }
         p = q; cap = nc;
@@ -89,6 +90,7 @@ struct t3d_ctx {
 
     // frame staging (pinned)
     bool inFrame = false, executed = false, haveResults = false;
+    bool stageTimings = false, stagesTimed = false;
     FrameConst fc;
     PinVec<DrawRec> hDraws;
     PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked;
@@ -98,12 +100,13 @@ struct t3d_ctx {
     std::vector<LightList> lightLists;
     std::vector<uint32_t> drawTotalTris;
     std::vector<uint8_t> drawContinue;
-    uint32_t vAcc = 0, tAcc = 0, luAcc = 0;
+    uint32_t vAcc = 0, tAcc = 0, luAcc = 0, nHistRows = 0;
     bool anyLit = false, anySkinned = false, anyUnbill = false;
 
     // device arenas
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
     PinVec<uint8_t> hFrame;
+    void* hFrameDev = nullptr; size_t frameRestOff = 0, frameBytes = 0, frameLightsOff = 0;
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
@@ -490,8 +493,9 @@ static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, 
 static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
     ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear();
     const uint32_t* tb = ctx->hTbase.p;
-    TriTile cur; cur.start = 0; cur.count = 0; cur.dFirst = 0; cur.info = 0;
+    TriTile cur; memset(&cur, 0, sizeof cur);
     cudaError_t e = cudaSuccess;
+    ctx->nHistRows = 0;
     auto close = [&]() -> cudaError_t {
         if (cur.info == 0) return cudaSuccess;
         if (cur.count) {        // a tile of empty draws has nothing to do
@@ -510,9 +514,11 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
             const uint32_t n = (nt + TILE_TRIS - 1) / TILE_TRIS;
             for (uint32_t j = 0; j < n; j++) {
                 TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
+                t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws.p[d].sortMode; t.tbase = tb[d];
                 if ((e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
                 if ((e = ctx->hTiles.push(t)) != cudaSuccess) return e;
             }
+            ctx->nHistRows += n + 1;
             continue;
         }
         if (cur.info && (cur.count + nt > TILE_TRIS || cur.info >= TILE_TRIS)) { if ((e = close()) != cudaSuccess) return e; }
@@ -531,9 +537,9 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     const uint32_t totalV = ctx->vAcc, totalT = ctx->tAcc;
     ctx->launches = 0;
     ctx->executed = true;
-    CU(cudaEventRecord(ctx->ev[0], s));
+    ctx->stagesTimed = ctx->stageTimings;
     if (nDraws == 0 || totalT == 0) {
-        for (int i = 1; i < 7; i++) CU(cudaEventRecord(ctx->ev[i], s));
+        for (int i = 0; i < 7; i++) CU(cudaEventRecord(ctx->ev[i], s));
         ctx->h2dBytes = 0;
         return T3D_OK;
     }
@@ -557,7 +563,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dTnrm.ensure(16ull * std::max(normals ? totalV : 4u, 4u)));
     CU(ctx->dTdepth.ensure(4ull * totalT));
     CU(ctx->dSorted.ensure(4ull * totalT));
-    CU(ctx->dHist.ensure(4ull * BIN_COUNT * std::max(nLarge, 1u)));
+    CU(ctx->dHist.ensure(4ull * BIN_COUNT * std::max(ctx->nHistRows, 1u)));
     CU(ctx->dTileSurv.ensure(4ull * std::max(nTiles, 1u)));
     CU(ctx->dTileOut.ensure(4ull * (nTiles + 1)));
     CU(ctx->dCount.ensure(256));
@@ -583,10 +589,13 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         size_t total = 0;
         for (Seg& g : segs) { g.off = total; total += (g.bytes + 255) & ~(size_t)255; }
         total = std::max<size_t>(total, 256);
+        ctx->hFrame.mapped = true;
         CU(ctx->hFrame.resize(total));
         CU(ctx->dFrame.ensure(total));
         for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
-        CU(cudaMemcpyAsync(ctx->dFrame.p, ctx->hFrame.p, total, cudaMemcpyHostToDevice, s));
+        // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
+        CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
+        ctx->frameRestOff = segs[1].off; ctx->frameBytes = total; ctx->frameLightsOff = segs[7].off;
         uint8_t* base = ctx->dFrame.as<uint8_t>();
         ctx->pDraws = reinterpret_cast<DrawRec*>(base + segs[0].off);
         ctx->pVbase = reinterpret_cast<uint32_t*>(base + segs[1].off);
@@ -600,32 +609,41 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->h2dBytes = 0;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
     }
-    CU(cudaEventRecord(ctx->ev[1], s));
+    // Stage timings need an event between kernels, which also serialises them; the default path records only
+    // the frame's first and last event and chains the kernels with programmatic dependent launches.
+    const bool st = ctx->stageTimings;
+    const bool pdl = !st;
+    auto mark = [&](int i) -> cudaError_t { return st ? cudaEventRecord(ctx->ev[i], s) : cudaSuccess; };
+    CU(cudaEventRecord(ctx->ev[0], s));
+    CU(mark(1));
 
     DrawStat* stats = ctx->dStats.as<DrawStat>();
-    // K0 + K1
-    launch_prep_draws(s, ctx->pDraws, nDraws, ctx->fc, ctx->pLightsIn, ctx->dLightsU.as<LightU>(), stats);
-    CU(cudaEventRecord(ctx->ev[2], s));
-    launch_vertex(s, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalV, ctx->fc,
+    // K0 (fetches the uniforms over PCIe itself) + K1
+    launch_prep_draws(s, pdl, ctx->hFrameDev, ctx->dFrame.p, nDraws, ctx->frameRestOff, ctx->frameBytes, ctx->fc,
+                      reinterpret_cast<const t3d_light*>(static_cast<const uint8_t*>(ctx->hFrameDev) + ctx->frameLightsOff),
+                      (uint32_t)ctx->hLights.n, ctx->dLightsU.as<LightU>(), stats);
+    CU(mark(2));
+    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 2;
-    CU(cudaEventRecord(ctx->ev[3], s));
+    CU(mark(3));
     // K2: cull (small draws are also sorted here)
-    launch_cull_large(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
+    launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
                       ctx->dTdepth.as<uint32_t>(), stats);
-    launch_tile_packed(s, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
+    launch_tile_packed(s, pdl, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
                        ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats);
     ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0);
-    CU(cudaEventRecord(ctx->ev[4], s));
-    // K3: segmented 512-bin counting sort of the large draws, then where every tile starts in the lists
-    launch_bin_hist(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>());
-    launch_scatter(s, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
-    launch_tile_scan(s, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+    CU(mark(4));
+    // K3: where every tile starts in the lists (needs only the survivor counts), then the segmented 512-bin
+    // counting sort of the large draws
+    launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+    launch_bin_hist(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>());
+    launch_scatter(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
     ctx->launches += (nLarge ? 2 : 0) + 1;
-    CU(cudaEventRecord(ctx->ev[5], s));
+    CU(mark(5));
     // K4
-    launch_emit(s, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
+    launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                 ctx->fc, ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                 ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
     ctx->launches += nTiles ? 1 : 0;
@@ -733,13 +751,15 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     }
     if (tm) {
         memset(tm, 0, sizeof *tm);
-        cudaEventElapsedTime(&tm->upload_ms, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&tm->prep_ms, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&tm->vertex_ms, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&tm->cull_ms, ctx->ev[3], ctx->ev[4]);
-        cudaEventElapsedTime(&tm->sort_ms, ctx->ev[4], ctx->ev[5]);
-        cudaEventElapsedTime(&tm->emit_ms, ctx->ev[5], ctx->ev[6]);
-        cudaEventElapsedTime(&tm->total_ms, ctx->ev[1], ctx->ev[6]);
+        if (ctx->stagesTimed || !(nDraws && totalT)) {
+            cudaEventElapsedTime(&tm->upload_ms, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&tm->prep_ms, ctx->ev[1], ctx->ev[2]);
+            cudaEventElapsedTime(&tm->vertex_ms, ctx->ev[2], ctx->ev[3]);
+            cudaEventElapsedTime(&tm->cull_ms, ctx->ev[3], ctx->ev[4]);
+            cudaEventElapsedTime(&tm->sort_ms, ctx->ev[4], ctx->ev[5]);
+            cudaEventElapsedTime(&tm->emit_ms, ctx->ev[5], ctx->ev[6]);
+        }
+        cudaEventElapsedTime(&tm->total_ms, ctx->ev[0], ctx->ev[6]);
         tm->download_ms = ctx->downloadMs;
     }
     ctx->haveResults = true;
@@ -768,6 +788,12 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
         if (R.flags & T3D_DRAW_LIT) CU(cudaMemcpy(light4, ctx->dLight.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
         else memset(light4, 0, n * 16);
     }
+    return T3D_OK;
+}
+
+int t3d_set_stage_timings(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    ctx->stageTimings = enabled != 0;
     return T3D_OK;
 }
 

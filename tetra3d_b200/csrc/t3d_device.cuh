@@ -124,6 +124,12 @@ struct __align__(16) TriTile {
     uint32_t count;             // slots in the tile (<= TILE_TRIS)
     uint32_t dFirst;            // first draw
     uint32_t info;              // packed: number of draws (<= TILE_TRIS); large: TILE_LARGE | tile index in the draw
+    // large tiles only: where the draw's bin counts live (k_bin_hist / k_scatter)
+    uint32_t row0;              // first histogram row of the draw: rows row0 .. row0+nTilesOfDraw-1 are per-tile
+                                // offsets, row row0+nTilesOfDraw holds the draw's bin bases
+    uint32_t nTilesOfDraw;
+    uint32_t sortMode;          // T3D_SORT_* of the draw
+    uint32_t tbase;             // first arena slot of the draw
 };
 static const uint32_t TILE_TRIS = 1024;
 static const uint32_t TILE_LARGE = 0x80000000u;
@@ -133,6 +139,17 @@ static const int BIN_BITS = 9;      // 512 bins, sortingTriangles.go:166-168
 static const int BIN_COUNT = 512;
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL).  Every kernel of a frame after the first is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its blocks may start while the previous kernel's last
+// blocks are still running.  pdl_wait() blocks until the previous kernel has completed and its writes are
+// visible (a no-op for a plain launch); pdl_launch() lets the next kernel's blocks start once every block of
+// this grid has called it.  Every block calls pdl_launch() only AFTER pdl_wait(), so when kernel N+1's blocks
+// start, kernel N-1 and everything before it has completed: code placed before pdl_wait() may read what
+// kernels two or more launches back wrote (the frame tables, k_prep_draws' records) and static mesh data, but
+// nothing the immediately preceding kernel writes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 512-bin key of one surviving triangle (sortingTriangles.go:38-64).  BackToFront visits bins 511..0
 // (sortingTriangles.go:101), so the key is the visiting rank of the bin: ascending key == draw order.
 __device__ __forceinline__ uint32_t bin_key(uint32_t depthBits, uint32_t minBits, uint32_t maxBits, uint32_t sortMode) {

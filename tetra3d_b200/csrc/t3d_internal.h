@@ -7,29 +7,41 @@
 
 namespace t3d {
 
+// Launches with (pdl = true) or without the programmatic-dependent-launch attribute (t3d_device.cuh).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // t3d_kernels.cu
-void launch_prep_draws(cudaStream_t s, DrawRec* draws, uint32_t nDraws, const FrameConst& fc,
-                       const t3d_light* lightsIn, LightU* lightsU, DrawStat* stats);
-void launch_vertex(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
+void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* devFrame, uint32_t nDraws, size_t restOff, size_t totalBytes,
+                       const FrameConst& fc, const t3d_light* lightsHost, uint32_t nLightsIn, LightU* lightsU, DrawStat* stats);
+void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float4* light, float4* wpos, float* unbill, float4* tnrm);
-void launch_cull_large(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats);
-void launch_tile_packed(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
+void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
                         const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats);
-void launch_emit(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
+void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds);
 static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex block (tileFirst granularity)
 
 // t3d_sort.cu -- segmented 512-bin counting sort for draws that span several tiles
-void launch_bin_hist(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                      DrawStat* stats, uint32_t* tdepth, uint32_t* hist);
-void launch_scatter(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                     const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted);
-void launch_tile_scan(cudaStream_t s, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
+void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
                       uint32_t* tileOut, uint32_t* dCount);
 
 }  // namespace t3d

@@ -16,6 +16,7 @@
 #include "t3d_device.cuh"
 #include "t3d_internal.h"
 #include "../../include/t3dgeo.h"
+#include <algorithm>
 
 namespace t3d {
 
@@ -38,12 +39,63 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ------------------------------------------------------------------------------------------------
 // K0: per-draw uniforms
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_prep_draws(DrawRec* __restrict__ draws, uint32_t nDraws, const __grid_constant__ FrameConst fc,
-             const t3d_light* __restrict__ lightsIn, LightU* __restrict__ lightsU, DrawStat* __restrict__ stats) {
-    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= nDraws) return;
-    DrawRec& R = draws[d];
+// The frame's uniforms sit in one pinned host block (t3d_api.cu packs it: DrawRec[nDraws] first, then the
+// tables, light lists and bone matrices).  This kernel pulls the block over PCIe itself (UVA loads from the
+// mapped host allocation, all of a thread's loads in flight at once) instead of waiting for a DMA copy:
+// blocks < nPrepBlocks stage PREP_DRAWS records in shared memory, derive the per-draw uniforms there and
+// write the finished records to the device copy; the remaining blocks copy the rest of the block verbatim.
+static const int PREP_THREADS = 256;
+static const int PREP_DRAWS = 64;               // draws per block
+static const uint32_t PREP_SMEM_LIGHTS = 256;   // light lists up to this many entries are staged in shared memory
+static const int REC16 = sizeof(DrawRec) / 16;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prep_draws(const uint4* __restrict__ hostFrame, uint4* __restrict__ devFrame, uint32_t nDraws, uint32_t restOff16,
+             uint32_t total16, uint32_t nPrepBlocks, const __grid_constant__ FrameConst fc,
+             const t3d_light* __restrict__ lightsHost, uint32_t nLightsIn, LightU* __restrict__ lightsU,
+             DrawStat* __restrict__ stats) {
+    extern __shared__ uint4 prepSmem[];
+    pdl_launch();
+    if (blockIdx.x >= nPrepBlocks) {
+        const uint32_t nb = gridDim.x - nPrepBlocks;
+        const uint32_t stride = nb * PREP_THREADS;
+        uint32_t i = restOff16 + (blockIdx.x - nPrepBlocks) * PREP_THREADS + threadIdx.x;
+        for (; i + 7 * stride < total16; i += 8 * stride) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = hostFrame[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < 8; u++) devFrame[i + u * stride] = v[u];
+        }
+        for (; i < total16; i += stride) devFrame[i] = hostFrame[i];
+        return;
+    }
+    DrawRec* sR = reinterpret_cast<DrawRec*>(prepSmem);
+    t3d_light* sL = reinterpret_cast<t3d_light*>(prepSmem + PREP_DRAWS * REC16);
+    const uint32_t d0 = blockIdx.x * PREP_DRAWS;
+    const uint32_t n = min((uint32_t)PREP_DRAWS, nDraws - d0);
+    {
+        const uint4* src = hostFrame + (size_t)d0 * REC16;
+        const uint32_t n16 = n * REC16;
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) prepSmem[i] = v[u]; }
+        static_assert(8 * PREP_THREADS >= PREP_DRAWS * REC16, "staging covers a block's records in one sweep");
+    }
+    const bool lightsStaged = nLightsIn <= PREP_SMEM_LIGHTS;
+    if (lightsStaged) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(lightsHost);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sL);
+        const uint32_t nw = nLightsIn * (uint32_t)(sizeof(t3d_light) / 4);
+        for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) dst[i] = src[i];
+    }
+    const t3d_light* lightsIn = lightsStaged ? sL : lightsHost;
+    __syncthreads();
+    if (threadIdx.x < n) {
+    const uint32_t d = d0 + threadIdx.x;
+    DrawRec& R = sR[threadIdx.x];
 
     const uint32_t flags = R.flags;
     const bool skinned = flags & T3D_DRAW_SKINNED;
@@ -140,6 +192,13 @@ k_prep_draws(DrawRec* __restrict__ draws, uint32_t nDraws, const __grid_constant
 
     DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
     stats[d] = st;
+    }
+    __syncthreads();
+    {
+        uint4* dst = devFrame + (size_t)d0 * REC16;
+        const uint32_t n16 = n * REC16;
+        for (uint32_t i = threadIdx.x; i < n16; i += PREP_THREADS) dst[i] = prepSmem[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,8 +206,11 @@ k_prep_draws(DrawRec* __restrict__ draws, uint32_t nDraws, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 
 // LightVolume.VertexLight (light.go:583-663); rare, kept out of line.
-__device__ __noinline__ void light_volume(const DrawRec& R, const LightU& U, const VolumeU* __restrict__ vols,
-                                          Vec3 apos, Vec3 anrm, bool skinned, float& lr, float& lg, float& lb) {
+__device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, const LightU* __restrict__ Up, const VolumeU* __restrict__ vols,
+                                            float px, float py, float pz, float nx, float ny, float nz, bool skinned) {
+    const DrawRec& R = *Rp;
+    const LightU U = *Up;
+    const Vec3 apos = v3(px, py, pz), anrm = v3(nx, ny, nz);
     const VolumeU V = vols[U.volume];
     float cr = 0, cg = 0, cb = 0;
     const bool hasMat = R.flags & T3D_DRAW_HAS_MATERIAL;
@@ -170,7 +232,7 @@ __device__ __noinline__ void light_volume(const DrawRec& R, const LightU& U, con
         }
         // Dimensions.Contains on vertPos (mesh.go:82-84) -- zero in WithNormal mode, as in the reference
         if (!(vertPos.X >= V.dimMin[0] && vertPos.Y >= V.dimMin[1] && vertPos.Z >= V.dimMin[2] &&
-              vertPos.X <= V.dimMax[0] && vertPos.Y <= V.dimMax[1] && vertPos.Z <= V.dimMax[2])) return;
+              vertPos.X <= V.dimMax[0] && vertPos.Y <= V.dimMax[1] && vertPos.Z <= V.dimMax[2])) return make_float3(0.0f, 0.0f, 0.0f);
         lookup = (mode == T3D_LV_PER_VERTEX_WITH_NORMAL) ? vertPosWithNormal : vertPos;
     }
     // light.go:717-724, 1267-1272
@@ -181,31 +243,31 @@ __device__ __noinline__ void light_volume(const DrawRec& R, const LightU& U, con
         const float* c = V.cells + 3 * ((size_t)x + ((size_t)y * V.cellCount[0]) + ((size_t)z * V.cellCount[0] * V.cellCount[1]));
         cr = c[0]; cg = c[1]; cb = c[2];
     }
-    lr += U.color[0] * cr * U.energy;
-    lg += U.color[1] * cg * U.energy;
-    lb += U.color[2] * cb * U.energy;
+    return make_float3(U.color[0] * cr * U.energy, U.color[1] * cg * U.energy, U.color[2] * cb * U.energy);
 }
 
 // Model.skinVertex (model.go:559-596) for one vertex.
+struct SkinAcc { float4 k0, k1, k2, k3; bool done; };
+// One influence: skip weight 0, take the bone alone on weight 1 (and stop), else Scale then Add (matrix.go:639-661).
+__device__ __forceinline__ void skin_influence(SkinAcc& A, const float* __restrict__ bones, float weightPerc, uint32_t joint, bool present) {
+    if (A.done || !present || weightPerc == 0.0f) return;
+    const float4* B = reinterpret_cast<const float4*>(bones + 16 * (size_t)joint);
+    const float4 r0 = __ldg(B), r1 = __ldg(B + 1), r2 = __ldg(B + 2), r3 = __ldg(B + 3);
+    if (weightPerc == 1.0f) { A.k0 = r0; A.k1 = r1; A.k2 = r2; A.k3 = r3; A.done = true; return; }
+    A.k0.x = A.k0.x + r0.x * weightPerc; A.k0.y = A.k0.y + r0.y * weightPerc; A.k0.z = A.k0.z + r0.z * weightPerc; A.k0.w = A.k0.w + r0.w * weightPerc;
+    A.k1.x = A.k1.x + r1.x * weightPerc; A.k1.y = A.k1.y + r1.y * weightPerc; A.k1.z = A.k1.z + r1.z * weightPerc; A.k1.w = A.k1.w + r1.w * weightPerc;
+    A.k2.x = A.k2.x + r2.x * weightPerc; A.k2.y = A.k2.y + r2.y * weightPerc; A.k2.z = A.k2.z + r2.z * weightPerc; A.k2.w = A.k2.w + r2.w * weightPerc;
+    A.k3.x = A.k3.x + r3.x * weightPerc; A.k3.y = A.k3.y + r3.y * weightPerc; A.k3.z = A.k3.z + r3.z * weightPerc; A.k3.w = A.k3.w + r3.w * weightPerc;
+}
 __device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4 w, ushort4 j, int n,
                                          Vec3 p, Vec3 nIn, Vec3& pOut, Vec3& nOut) {
-    float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0, k3 = k0;
-    const float ws[4] = {w.x, w.y, w.z, w.w};
-    const uint16_t js[4] = {j.x, j.y, j.z, j.w};
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        if (b >= n) break;
-        const float weightPerc = ws[b];
-        if (weightPerc == 0.0f) continue;
-        const float4* B = reinterpret_cast<const float4*>(bones + 16 * (size_t)js[b]);
-        const float4 r0 = __ldg(B), r1 = __ldg(B + 1), r2 = __ldg(B + 2), r3 = __ldg(B + 3);
-        if (weightPerc == 1.0f) { k0 = r0; k1 = r1; k2 = r2; k3 = r3; break; }
-        // Scale then Add (matrix.go:639-661)
-        k0.x = k0.x + r0.x * weightPerc; k0.y = k0.y + r0.y * weightPerc; k0.z = k0.z + r0.z * weightPerc; k0.w = k0.w + r0.w * weightPerc;
-        k1.x = k1.x + r1.x * weightPerc; k1.y = k1.y + r1.y * weightPerc; k1.z = k1.z + r1.z * weightPerc; k1.w = k1.w + r1.w * weightPerc;
-        k2.x = k2.x + r2.x * weightPerc; k2.y = k2.y + r2.y * weightPerc; k2.z = k2.z + r2.z * weightPerc; k2.w = k2.w + r2.w * weightPerc;
-        k3.x = k3.x + r3.x * weightPerc; k3.y = k3.y + r3.y * weightPerc; k3.z = k3.z + r3.z * weightPerc; k3.w = k3.w + r3.w * weightPerc;
-    }
+    SkinAcc A;
+    A.k0 = make_float4(0, 0, 0, 0); A.k1 = A.k0; A.k2 = A.k0; A.k3 = A.k0; A.done = false;
+    skin_influence(A, bones, w.x, j.x, n > 0);
+    skin_influence(A, bones, w.y, j.y, n > 1);
+    skin_influence(A, bones, w.z, j.z, n > 2);
+    skin_influence(A, bones, w.w, j.w, n > 3);
+    const float4 k0 = A.k0, k1 = A.k1, k2 = A.k2, k3 = A.k3;
     pOut.X = k0.x * p.X + k1.x * p.Y + k2.x * p.Z + k3.x;                  // MultVec, matrix.go:619
     pOut.Y = k0.y * p.X + k1.y * p.Y + k2.y * p.Z + k3.y;
     pOut.Z = k0.z * p.X + k1.z * p.Y + k2.z * p.Z + k3.z;
@@ -215,34 +277,40 @@ __device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4
     nOut.Z = k0.z * nIn.X + k1.z * nIn.Y + k2.z * nIn.Z + 0.0f;
 }
 
+// Tunables (see profiles/README.md for the measurements behind the defaults).
+#ifndef T3D_K1_MINBLOCKS
+#define T3D_K1_MINBLOCKS 5      // resident blocks per SM the register allocation aims for
+#endif
 static const int VERTEX_BLOCK = 256;
+static const int VERTEX_SMEM_LIGHTS = 16;       // light lists up to this long are staged in shared memory
+static_assert(VERTEX_BLOCK == (int)VERTEX_TILE, "t3d_internal.h: VERTEX_TILE must be the slots one k_vertex block covers");
 
-__global__ void __launch_bounds__(VERTEX_BLOCK)
-k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
-         uint32_t totalV, const __grid_constant__ FrameConst fc,
-         const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
-         float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
-         float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    const uint32_t slot = blockIdx.x * (uint32_t)VERTEX_BLOCK + threadIdx.x;
-    if (slot >= totalV) return;
-    const uint32_t d = find_draw(vbase, __ldg(&tileFirst[blockIdx.x]), __ldg(&tileFirst[blockIdx.x + 1]), slot);
-    const DrawRec& R = draws[d];
-    const uint32_t flags = R.flags;
+// Everything one vertex needs from its draw: either the DrawRec / LightU records in global memory, or the
+// block's staged copy in shared memory (rows 0-3 mvp, 4-7 the sun's workingModelRotation, 8.. the LightU list).
+struct UniformsGlobal {
+    const float* mvpP; const float* sunP; const float4* lightP;
+    __device__ __forceinline__ float4 mvp(int i) const { return ldg4(mvpP + 4 * i); }
+    __device__ __forceinline__ float4 sun(int i) const { return ldg4(sunP + 4 * i); }
+    __device__ __forceinline__ float4 light(uint32_t i) const { return __ldg(lightP + i); }
+};
+struct UniformsShared {
+    const float4* s;
+    __device__ __forceinline__ float4 mvp(int i) const { return s[i]; }
+    __device__ __forceinline__ float4 sun(int i) const { return s[4 + i]; }
+    __device__ __forceinline__ float4 light(uint32_t i) const { return s[8 + i]; }
+};
+
+// One vertex: shape keys, skinning, clip transform, optional outputs, lighting.  P / N arrive loaded.
+template <class Uniforms>
+__device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const Uniforms U, const FrameConst& fc,
+                                             const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
+                                             const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
+                                             float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
+                                             float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     const bool skinned = flags & T3D_DRAW_SKINNED;
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
-    const uint32_t mv = R.a0 + (slot - R.vbase);
-    const uint32_t vs = R.vstride;
-
-    Vec3 P, N = v3(0, 0, 0);
-    {
-        const float* pp = R.pos + mv;
-        P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs));
-    }
     const bool needN = lit || skinned;
-    if (needN) {
-        const float* np = R.nrm + mv;
-        N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
-    }
+    const uint32_t vs = R.vstride;
 
     // shape keys (mesh.go:796-822)
     for (uint32_t k = 0; k < R.nKeys; k++) {
@@ -275,7 +343,7 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
             m2 = make_float4(fc.vp[8], fc.vp[9], fc.vp[10], fc.vp[11]);
             m3 = make_float4(fc.vp[12], fc.vp[13], fc.vp[14], fc.vp[15]);
         } else {
-            m0 = ldg4(R.mvp); m1 = ldg4(R.mvp + 4); m2 = ldg4(R.mvp + 8); m3 = ldg4(R.mvp + 12);
+            m0 = U.mvp(0); m1 = U.mvp(1); m2 = U.mvp(2); m3 = U.mvp(3);
         }
         const float snap = fc.snapping;
         float4 c;
@@ -310,14 +378,11 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
     float lr = 0, lg = 0, lb = 0;
     const uint8_t lightingMode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
     const uint32_t nL = R.lightCount;
-    const float4* LUp = reinterpret_cast<const float4*>(lightsU + R.lightU);
     for (uint32_t li = 0; li < nL; li++) {
-        const float4 q0 = __ldg(LUp + 4 * li), q1 = __ldg(LUp + 4 * li + 1), q2 = __ldg(LUp + 4 * li + 2);
+        const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
         const uint32_t type = __float_as_uint(q0.x);
         const float cR = q0.y, cG = q0.z, cB = q0.w, energy = q1.x;
-        if (type == T3D_LIGHT_AMBIENT) {                                // light.go:110-120
-            lr += cR * energy; lg += cG * energy; lb += cB * energy;
-        } else if (type == T3D_LIGHT_POINT) {                           // light.go:191-258
+        if (type == T3D_LIGHT_POINT) {                                  // light.go:191-258
             const Vec3 wp = v3(q1.y, q1.z, q1.w);
             const float range = q2.x, range2 = q2.y;
             Vec3 vertNormal = N;
@@ -336,13 +401,13 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
                 lb += cB * diffuseFactor * energy;
             }
         } else if (type == T3D_LIGHT_DIRECTIONAL) {                     // light.go:332-360
-            const float4 q3 = __ldg(LUp + 4 * li + 3);
+            const float4 q3 = U.light(4 * li + 3);
             const Vec3 fwd = v3(q2.z, q2.w, q3.x);
             Vec3 normal;
             if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) normal = fwd;
             else if (skinned) normal = N;
             else {
-                const float4 s0 = ldg4(R.worldRot), s1 = ldg4(R.worldRot + 4), s2 = ldg4(R.worldRot + 8), s3 = ldg4(R.worldRot + 12);
+                const float4 s0 = U.sun(0), s1 = U.sun(1), s2 = U.sun(2), s3 = U.sun(3);
                 normal.X = s0.x * N.X + s1.x * N.Y + s2.x * N.Z + s3.x;
                 normal.Y = s0.y * N.X + s1.y * N.Y + s2.y * N.Z + s3.y;
                 normal.Z = s0.z * N.X + s1.z * N.Y + s2.z * N.Z + s3.z;
@@ -353,12 +418,79 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
             lr += cR * diffuseFactor * energy;
             lg += cG * diffuseFactor * energy;
             lb += cB * diffuseFactor * energy;
+        } else if (type == T3D_LIGHT_AMBIENT) {                         // light.go:110-120
+            lr += cR * energy; lg += cG * energy; lb += cB * energy;
         } else if (type == T3D_LIGHT_VOLUME) {
-            const LightU U = lightsU[R.lightU + li];
-            light_volume(R, U, vols, P, N, skinned, lr, lg, lb);
+            // a vertex outside the volume adds nothing (x + 0 keeps x: the sums are never -0)
+            const float3 add = light_volume(&R, lightsU + R.lightU + li, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned);
+            lr += add.x; lg += add.y; lb += add.z;
         }
     }
     lightOut[slot] = make_float4(lr, lg, lb, 1.0f);
+}
+
+// One vertex per thread, VERTEX_BLOCK consecutive slots per block.  When the block lies inside one draw (any
+// draw of more than a few hundred vertices) the draw's matrices and light list are staged in shared memory
+// once; blocks that straddle draws look their draw up per vertex.
+__global__ void __launch_bounds__(VERTEX_BLOCK, T3D_K1_MINBLOCKS)
+k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
+         uint32_t totalV, const __grid_constant__ FrameConst fc,
+         const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
+         float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
+         float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
+    __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
+    pdl_wait();             // everything below reads what k_prep_draws wrote
+    pdl_launch();
+    const uint32_t base = blockIdx.x * (uint32_t)VERTEX_BLOCK;
+    const uint32_t slot = base + threadIdx.x;
+    const uint32_t dLo = __ldg(&tileFirst[blockIdx.x]), dHi = __ldg(&tileFirst[blockIdx.x + 1]);
+    const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
+    // dHi is the draw of the first slot of the NEXT block, so dLo == dHi covers this whole block; otherwise the
+    // block is still uniform when the next draw starts at or after its end
+    bool staged = dLo == dHi || __ldg(&vbase[dLo + 1]) >= end;
+    if (staged) {
+        const DrawRec& R = draws[dLo];
+        const uint32_t flags = R.flags;
+        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+        staged = nL <= (uint32_t)VERTEX_SMEM_LIGHTS;
+        if (staged) {
+            // the vertex's own loads go first so they overlap the staging
+            const uint32_t mv = R.a0 + (slot - R.vbase);
+            const uint32_t vs = R.vstride;
+            Vec3 P = v3(0, 0, 0), N = v3(0, 0, 0);
+            if (slot < end) {
+                const float* pp = R.pos + mv;
+                P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs));
+                if (flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) {
+                    const float* np = R.nrm + mv;
+                    N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
+                }
+            }
+            if (threadIdx.x < 4) sU[threadIdx.x] = ldg4(R.mvp + 4 * threadIdx.x);
+            else if (threadIdx.x < 8) sU[threadIdx.x] = ldg4(R.worldRot + 4 * (threadIdx.x - 4));
+            else if (threadIdx.x < 8 + 4 * nL) sU[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(lightsU + R.lightU) + (threadIdx.x - 8));
+            __syncthreads();
+            if (slot >= end) return;
+            UniformsShared U; U.s = sU;
+            shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, lightOut, wposOut, unbillOut, tnrmOut);
+            return;
+        }
+    }
+    if (slot >= end) return;
+    const uint32_t d = find_draw(vbase, dLo, dHi, slot);
+    const DrawRec& R = draws[d];
+    const uint32_t flags = R.flags;
+    const uint32_t mv = R.a0 + (slot - R.vbase);
+    const uint32_t vs = R.vstride;
+    const float* pp = R.pos + mv;
+    Vec3 P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs)), N = v3(0, 0, 0);
+    if (flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) {
+        const float* np = R.nrm + mv;
+        N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
+    }
+    UniformsGlobal U;
+    U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
+    shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, lightOut, wposOut, unbillOut, tnrmOut);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -431,6 +563,8 @@ k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tile
             if (!skinned) { cx[r] = __ldg(cp + i); cy[r] = __ldg(cp + ts + i); cz[r] = __ldg(cp + 2 * (size_t)ts + i); }
         }
     }
+    pdl_wait();             // the index / centre loads above only touch the mesh and k_prep_draws' output; clip is k_vertex's
+    pdl_launch();
     uint32_t mn = 0xFFFFFFFFu, mx = 0u, cnt = 0u;
 #pragma unroll
     for (int r = 0; r < TILE_ROUNDS; r++) {
@@ -491,6 +625,8 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
     for (uint32_t s = threadIdx.x; s <= nSeg; s += TILE_THREADS) sBase[s] = __ldg(&tbase[T.dFirst + s]);
     for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) { sMin[s] = 0x7F7FFFFFu; sMax[s] = 0u; sCnt[s] = 0; }
     if (threadIdx.x == 0) sTotal = 0;
+    pdl_wait();
+    pdl_launch();
     __syncthreads();
 
     // ---- cull + depth ----
@@ -587,97 +723,155 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: emit (camera.go:1646-1820), one thread per output vertex
+// K4: emit (camera.go:1646-1820)
 // ------------------------------------------------------------------------------------------------
-// Blocks walk the tiles: block b covers output corners [q*256, q*256+256) of tile b / EMIT_PER_TILE.  The
-// i-th surviving triangle of a tile is sorted[tile.start + i]; its place in the lists is tileOut[tile] + i.
-static const int EMIT_PER_TILE = 3 * TILE_TRIS / 256;
-__global__ void __launch_bounds__(256)
+// A block takes EMIT_TRIS consecutive sorted triangles of one tile: the i-th surviving triangle of a tile
+// is sorted[tile.start + i] and its place in the lists is tileOut[tile] + i.  Phase A (one thread per
+// triangle) resolves draw, mesh triangle and the three corner indices into shared memory; phase B (one
+// thread per corner, three rounds) builds the 48-byte ebiten.Vertex records of the colour / depth /
+// normal lists in shared memory, and one elected thread hands each finished 12 KB run to the TMA
+// (cp.async.bulk shared -> global), so every list is written as whole contiguous lines.
+static const int EMIT_TRIS = 256;
+static const int EMIT_PER_TILE = TILE_TRIS / EMIT_TRIS;
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool NORMALS>
+__global__ void __launch_bounds__(EMIT_TRIS)
 k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
        const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const __grid_constant__ FrameConst fc,
        const float4* __restrict__ clip, const float4* __restrict__ light, const float* __restrict__ unbill,
        const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
        uint32_t* __restrict__ triIds) {
-    const uint32_t tileId = blockIdx.x / EMIT_PER_TILE;
-    const uint32_t v = (blockIdx.x % EMIT_PER_TILE) * 256u + threadIdx.x;
-    const uint32_t nSurv = __ldg(&tileSurv[tileId]);
-    const uint32_t k = v / 3u, c = v - 3u * k;
-    if (k >= nSurv) return;
-    const TriTile T = tiles[tileId];
-    const uint32_t val = __ldg(&sorted[T.start + k]);
-    uint32_t d, tslot;
-    if (T.info & TILE_LARGE) { d = T.dFirst; tslot = val; }
-    else { d = T.dFirst + (val >> 20); tslot = T.start + (val & 1023u); }
-    const uint32_t outTri = __ldg(&tileOut[tileId]) + k;
-    const uint32_t o = 3u * outTri + c;
-    const DrawRec& R = draws[d];
-    const uint32_t mt = R.t0 + (tslot - R.tbase);
-    const uint32_t vi = __ldg(R.idx + (size_t)c * R.tstride + mt);
-    const uint32_t slot = R.vbase + (vi - R.a0);
-    const float4 Tc = __ldg(&clip[slot]);
-    if (c == 0) triIds[outTri] = mt;
+    extern __shared__ uint4 emitSmem[];
+    float4* sCol = reinterpret_cast<float4*>(emitSmem);             // [EMIT_TRIS][3]
+    float4* sDep = sCol + 3 * EMIT_TRIS;
+    float4* sNrm = sDep + 3 * EMIT_TRIS;                            // NORMALS only
+    uint32_t* sSlot = reinterpret_cast<uint32_t*>(sDep + (NORMALS ? 6 : 3) * EMIT_TRIS);   // [3 * EMIT_TRIS] arena slot of each corner
+    uint32_t* sVi = sSlot + 3 * EMIT_TRIS;                          // mesh vertex index of each corner
+    uint32_t* sDraw = sVi + 3 * EMIT_TRIS;                          // [EMIT_TRIS]
 
+    pdl_wait();
+    pdl_launch();
+    const uint32_t tileId = blockIdx.x / EMIT_PER_TILE;
+    const uint32_t k0 = (blockIdx.x % EMIT_PER_TILE) * EMIT_TRIS;
+    const uint32_t nSurv = __ldg(&tileSurv[tileId]);
+    if (k0 >= nSurv) return;
+    const uint32_t nTri = min((uint32_t)EMIT_TRIS, nSurv - k0);
+    const TriTile T = tiles[tileId];
+    const uint32_t outTri0 = __ldg(&tileOut[tileId]) + k0;
+
+    if (threadIdx.x < nTri) {
+        const uint32_t val = __ldg(&sorted[T.start + k0 + threadIdx.x]);
+        uint32_t d, tslot;
+        if (T.info & TILE_LARGE) { d = T.dFirst; tslot = val; }
+        else { d = T.dFirst + (val >> 20); tslot = T.start + (val & 1023u); }
+        const DrawRec& R = draws[d];
+        const uint32_t ts = R.tstride;
+        const uint32_t mt = R.t0 + (tslot - R.tbase);
+        const uint32_t vofs = R.vbase - R.a0;
+        const uint32_t i0 = __ldg(R.idx + mt), i1 = __ldg(R.idx + ts + mt), i2 = __ldg(R.idx + 2 * (size_t)ts + mt);
+        sVi[3 * threadIdx.x] = i0; sVi[3 * threadIdx.x + 1] = i1; sVi[3 * threadIdx.x + 2] = i2;
+        sSlot[3 * threadIdx.x] = vofs + i0; sSlot[3 * threadIdx.x + 1] = vofs + i1; sSlot[3 * threadIdx.x + 2] = vofs + i2;
+        sDraw[threadIdx.x] = d;
+        triIds[outTri0 + threadIdx.x] = mt;
+    }
+    __syncthreads();
+
+    const uint32_t nVert = 3 * nTri;
     const bool persp = fc.camFlags & T3D_CAM_PERSPECTIVE;
     const bool pcuv = fc.camFlags & T3D_CAM_PERSP_CORRECT_UV;
-    float w = Tc.w;                                                     // camera.go:1655-1666
-    if (!persp) w = 1.0f;
-    if (w < 0) w = 0.001f;
-    const float dx = (Tc.x / w) * fc.camW + fc.halfW;                   // camera.go:1674-1675
-    const float dy = (Tc.y / -w) * fc.camH + fc.halfH;
+#pragma unroll 1
+    for (uint32_t v0 = 0; v0 < nVert; v0 += EMIT_TRIS) {
+        if (v0) {                                                       // the TMA has read the previous round's records
+            if (threadIdx.x == 0) bulk_wait_read();
+            __syncthreads();
+        }
+        const uint32_t v = v0 + threadIdx.x;
+        if (v < nVert) {
+            const uint32_t kk = v / 3u;
+            const uint32_t vi = sVi[v], slot = sSlot[v];
+            const DrawRec& R = draws[sDraw[kk]];
+            const float4 Tc = __ldg(&clip[slot]);
+            float w = Tc.w;                                             // camera.go:1655-1666
+            if (!persp) w = 1.0f;
+            if (w < 0) w = 0.001f;
+            const float dx = (Tc.x / w) * fc.camW + fc.halfW;           // camera.go:1674-1675
+            const float dy = (Tc.y / -w) * fc.camH + fc.halfH;
 
-    const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
-    float uvU, uvV, custom0 = 0.0f;
-    if (pcuv) {                                                         // camera.go:1689-1705
-        uvU = (uv.x / w) * R.srcW;
-        uvV = ((1.0f - uv.y) / w) * R.srcH;
-        custom0 = 1.0f / w;
-    } else {
-        uvU = uv.x * R.srcW;
-        uvV = (1.0f - uv.y) * R.srcH;
-    }
+            const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
+            float uvU, uvV, custom0 = 0.0f;
+            if (pcuv) {                                                 // camera.go:1689-1705
+                uvU = (uv.x / w) * R.srcW;
+                uvV = ((1.0f - uv.y) / w) * R.srcH;
+                custom0 = 1.0f / w;
+            } else {
+                uvU = uv.x * R.srcW;
+                uvV = (1.0f - uv.y) * R.srcH;
+            }
 
-    float4 col = ldg4(R.color);                                         // camera.go:1726-1736
-    if (R.col) {
-        const float4 vc = ldg4(R.col + 4 * (size_t)vi);
-        col.x = vc.x * col.x; col.y = vc.y * col.y; col.z = vc.z * col.z; col.w = vc.w * col.w;
-    }
-    if (R.flags & T3D_DRAW_LIT) {                                       // camera.go:1738-1742
-        const float4 L = __ldg(&light[slot]);
-        col.x *= L.x; col.y *= L.y; col.z *= L.z;
-    }
+            float4 col = ldg4(R.color);                                 // camera.go:1726-1736
+            if (R.col) {
+                const float4 vc = ldg4(R.col + 4 * (size_t)vi);
+                col.x = vc.x * col.x; col.y = vc.y * col.y; col.z = vc.z * col.z; col.w = vc.w * col.w;
+            }
+            const uint32_t flags = R.flags;
+            if (flags & T3D_DRAW_LIT) {                                 // camera.go:1738-1742
+                const float4 L = __ldg(&light[slot]);
+                col.x *= L.x; col.y *= L.y; col.z *= L.z;
+            }
 
-    float4 dcol = make_float4(0, 0, 0, 0);
-    if (fc.camFlags & T3D_CAM_RENDER_DEPTH) {                           // camera.go:1744-1782
-        float vertexDepth = Tc.z;
-        if ((R.flags & T3D_DRAW_HAS_MATERIAL) && (R.flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) vertexDepth = __ldg(&unbill[slot]);
-        float depth = (vertexDepth + fc.depthMargin) / fc.camSpread;
-        if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
-        dcol = make_float4(depth, depth, depth, 1.0f);
-    } else if (fc.worldPresent && fc.fogOn) {                           // camera.go:1784-1814
-        float depth = (Tc.z + fc.depthMargin) / fc.camSpread;
-        if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
-        depth = fc.fogRange[0] + ((fc.fogRange[1] - fc.fogRange[0]) * 1.0f - depth);
-        if (fc.fogMode == T3D_FOG_ADD) {
-            col.x += fc.fogColor[0] * depth; col.y += fc.fogColor[1] * depth; col.z += fc.fogColor[2] * depth;
-        } else if (fc.fogMode == T3D_FOG_SUB) {
-            col.x *= fc.fogColor[0] * depth; col.y *= fc.fogColor[1] * depth; col.z *= fc.fogColor[2] * depth;
+            float4 dcol = make_float4(0, 0, 0, 0);
+            if (fc.camFlags & T3D_CAM_RENDER_DEPTH) {                   // camera.go:1744-1782
+                float vertexDepth = Tc.z;
+                if ((flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) vertexDepth = __ldg(&unbill[slot]);
+                float depth = (vertexDepth + fc.depthMargin) / fc.camSpread;
+                if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
+                dcol = make_float4(depth, depth, depth, 1.0f);
+            } else if (fc.worldPresent && fc.fogOn) {                   // camera.go:1784-1814
+                float depth = (Tc.z + fc.depthMargin) / fc.camSpread;
+                if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
+                depth = fc.fogRange[0] + ((fc.fogRange[1] - fc.fogRange[0]) * 1.0f - depth);
+                if (fc.fogMode == T3D_FOG_ADD) {
+                    col.x += fc.fogColor[0] * depth; col.y += fc.fogColor[1] * depth; col.z += fc.fogColor[2] * depth;
+                } else if (fc.fogMode == T3D_FOG_SUB) {
+                    col.x *= fc.fogColor[0] * depth; col.y *= fc.fogColor[1] * depth; col.z *= fc.fogColor[2] * depth;
+                }
+            }
+
+            const float4 a = make_float4(dx, dy, uvU, uvV);
+            const float4 cust = make_float4(custom0, 0.0f, 0.0f, 0.0f);
+            float4* C = sCol + 3 * threadIdx.x;
+            C[0] = a; C[1] = col; C[2] = cust;
+            float4* D = sDep + 3 * threadIdx.x;
+            D[0] = a; D[1] = dcol; D[2] = cust;
+            if (NORMALS) {                                              // camera.go:1710-1722
+                const float4 tn = __ldg(&tnrm[slot]);
+                float4* Nn = sNrm + 3 * threadIdx.x;
+                Nn[0] = a;
+                Nn[1] = make_float4(tn.x * 0.5f + 0.5f, tn.y * 0.5f + 0.5f, tn.z * 0.5f + 0.5f, 0.0f);
+                Nn[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        fence_async_smem();                                             // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t n = min((uint32_t)EMIT_TRIS, nVert - v0);
+            const size_t o = 3 * (size_t)outTri0 + v0;                  // first output vertex of this round
+            bulk_store(colorList + 3 * o, sCol, n * 48u);
+            bulk_store(depthList + 3 * o, sDep, n * 48u);
+            if (NORMALS) bulk_store(normalList + 3 * o, sNrm, n * 48u);
+            bulk_commit();
         }
     }
-
-    const float4 a = make_float4(dx, dy, uvU, uvV);
-    const float4 cust = make_float4(custom0, 0.0f, 0.0f, 0.0f);
-    float4* C = colorList + 3 * (size_t)o;
-    C[0] = a; C[1] = col; C[2] = cust;
-    float4* D = depthList + 3 * (size_t)o;
-    D[0] = a; D[1] = dcol; D[2] = cust;
-    if (fc.camFlags & T3D_CAM_RENDER_NORMALS) {                         // camera.go:1710-1722
-        const float4 tn = __ldg(&tnrm[slot]);
-        float4* Nn = normalList + 3 * (size_t)o;
-        Nn[0] = a;
-        Nn[1] = make_float4(tn.x * 0.5f + 0.5f, tn.y * 0.5f + 0.5f, tn.z * 0.5f + 0.5f, 0.0f);
-        Nn[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
+    if (threadIdx.x == 0) bulk_wait_read();                             // shared memory must outlive the TMA reads
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,40 +879,53 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
 // ------------------------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-void launch_prep_draws(cudaStream_t s, DrawRec* draws, uint32_t nDraws, const FrameConst& fc,
-                       const t3d_light* lightsIn, LightU* lightsU, DrawStat* stats) {
+void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* devFrame, uint32_t nDraws, size_t restOff, size_t totalBytes,
+                       const FrameConst& fc, const t3d_light* lightsHost, uint32_t nLightsIn, LightU* lightsU, DrawStat* stats) {
     if (!nDraws) return;
-    k_prep_draws<<<cdiv(nDraws, 128), 128, 0, s>>>(draws, nDraws, fc, lightsIn, lightsU, stats);
+    const uint32_t nPrep = cdiv(nDraws, PREP_DRAWS);
+    const uint32_t rest16 = (uint32_t)((totalBytes - restOff) / 16);
+    const uint32_t nCopy = rest16 ? std::min<uint32_t>(cdiv(rest16, PREP_THREADS * 8), 1184u) : 0u;
+    const size_t smem = (size_t)PREP_DRAWS * sizeof(DrawRec) + (size_t)PREP_SMEM_LIGHTS * sizeof(t3d_light);
+    // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
+    (void)pdl;
+    launch_kernel(k_prep_draws, nPrep + nCopy, PREP_THREADS, smem, s, false, reinterpret_cast<const uint4*>(hostFrame),
+                  reinterpret_cast<uint4*>(devFrame), nDraws, (uint32_t)(restOff / 16), (uint32_t)(totalBytes / 16), nPrep, fc, lightsHost,
+                  nLightsIn, lightsU, stats);
 }
 
-void launch_vertex(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
+void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float4* light, float4* wpos, float* unbill, float4* tnrm) {
     if (!totalV) return;
-    k_vertex<<<cdiv(totalV, VERTEX_BLOCK), VERTEX_BLOCK, 0, s>>>(draws, vbase, tileFirst, totalV, fc, lightsU, bones, vols,
-                                                                 clip, light, wpos, unbill, tnrm);
+    launch_kernel(k_vertex, cdiv(totalV, VERTEX_BLOCK), VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, totalV, fc, lightsU, bones, vols,
+                  clip, light, wpos, unbill, tnrm);
 }
 
-void launch_cull_large(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats) {
     if (!nLarge) return;
-    k_cull_large<<<nLarge, TILE_THREADS, 0, s>>>(draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
+    launch_kernel(k_cull_large, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
 }
 
-void launch_tile_packed(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
+void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
                         const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats) {
     if (!nPacked) return;
-    k_tile_packed<<<nPacked, TILE_THREADS, 0, s>>>(draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
+    launch_kernel(k_tile_packed, nPacked, TILE_THREADS, 0, s, pdl, draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
 }
 
-void launch_emit(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
+void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds) {
     if (!nTiles) return;
-    k_emit<<<nTiles * EMIT_PER_TILE, 256, 0, s>>>(draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm,
-                                                  colorList, depthList, normalList, triIds);
+    const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
+    if (normalList)
+        launch_kernel(k_emit<true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
+                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+    else
+        launch_kernel(k_emit<false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
+                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm, colorList, depthList, normalList, triIds);
 }
 
 }  // namespace t3d

@@ -48,118 +48,129 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     return warpBase + inc - v;
 }
 
-// hist row r belongs to large tile largeList[r]; the rows of one draw are consecutive.
+// Histogram rows: tile j of a large draw owns row T.row0 + j; row T.row0 + nTilesOfDraw receives the bin bases.
 __global__ void __launch_bounds__(SORT_THREADS)
-k_bin_hist(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
+k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
            DrawStat* __restrict__ stats, uint32_t* __restrict__ tdepth, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sHist[BIN_COUNT];
     __shared__ uint32_t sWarp[8];
     __shared__ uint32_t sLast;
-    const uint32_t row = blockIdx.x;
-    const TriTile T = tiles[__ldg(&largeList[row])];
+    const TriTile T = tiles[__ldg(&largeList[blockIdx.x])];
     const uint32_t d = T.dFirst;
-    const uint32_t sortMode = draws[d].sortMode;
-    const uint32_t nt = draws[d].nt;
-    const uint32_t minBits = stats[d].minBits, maxBits = stats[d].maxBits;
+    const uint32_t j = T.info & ~TILE_LARGE;
 #pragma unroll
     for (int q = 0; q < BINS_PER_THREAD; q++) sHist[threadIdx.x + q * SORT_THREADS] = 0;
-    __syncthreads();
+    pdl_wait();
+    pdl_launch();
+    uint32_t bits[SORT_ROUNDS];
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = r * SORT_THREADS + threadIdx.x;
-        if (i < T.count) {
-            const uint32_t bits = tdepth[T.start + i];
-            if (bits != KEY_CULLED) {
-                const uint32_t key = bin_key(bits, minBits, maxBits, sortMode);
-                atomicAdd(&sHist[key], 1u);
-                tdepth[T.start + i] = key;          // the depth is not needed again; k_scatter reads the bin rank
-            }
+        bits[r] = (i < T.count) ? tdepth[T.start + i] : KEY_CULLED;
+    }
+    const uint32_t minBits = stats[d].minBits, maxBits = stats[d].maxBits;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        if (bits[r] != KEY_CULLED) {
+            const uint32_t key = bin_key(bits[r], minBits, maxBits, T.sortMode);
+            atomicAdd(&sHist[key], 1u);
+            tdepth[T.start + r * SORT_THREADS + threadIdx.x] = key;   // the depth is not needed again; k_scatter reads the bin rank
         }
     }
     __syncthreads();
-    uint32_t* myRow = hist + (size_t)row * BIN_COUNT;
-#pragma unroll
-    for (int q = 0; q < BINS_PER_THREAD; q++) myRow[threadIdx.x + q * SORT_THREADS] = sHist[threadIdx.x + q * SORT_THREADS];
+    // thread owns bins 2*tid, 2*tid+1 from here on (block scans then run in bin order)
+    uint2* myRow = reinterpret_cast<uint2*>(hist + (size_t)(T.row0 + j) * BIN_COUNT);
+    myRow[threadIdx.x] = make_uint2(sHist[2 * threadIdx.x], sHist[2 * threadIdx.x + 1]);
     __threadfence();
     __syncthreads();
-    const uint32_t nTilesOfDraw = (nt + TILE_TRIS - 1) / TILE_TRIS;
-    if (threadIdx.x == 0) sLast = (atomicAdd(&stats[d].done, 1u) == nTilesOfDraw - 1) ? 1u : 0u;
+    if (threadIdx.x == 0) sLast = (atomicAdd(&stats[d].done, 1u) == T.nTilesOfDraw - 1) ? 1u : 0u;
     __syncthreads();
     if (!sLast) return;
     __threadfence();
 
-    // Last tile of the draw: counts -> offsets.  offset(tile, bin) = sum of the draw's earlier bins over all
-    // tiles + the same bin in earlier tiles.
-    uint32_t* rows = hist + (size_t)(row - (T.info & ~TILE_LARGE)) * BIN_COUNT;
-    // thread owns bins [BINS_PER_THREAD * tid, +BINS_PER_THREAD) so that the block scan runs in bin order
-    uint32_t tot[BINS_PER_THREAD];
+    // Last tile of the draw: per-tile counts -> exclusive prefix over the draw's tiles (arena order inside a bin),
+    // totals -> exclusive prefix over bins in visiting order (the base row).
+    uint2* rows = reinterpret_cast<uint2*>(hist + (size_t)T.row0 * BIN_COUNT);
+    uint2 run = make_uint2(0u, 0u);
+    const uint32_t nT = T.nTilesOfDraw;
+    for (uint32_t t0 = 0; t0 < nT; t0 += 8) {
+        uint2 c[8];
 #pragma unroll
-    for (int q = 0; q < BINS_PER_THREAD; q++) {
-        const uint32_t b = threadIdx.x * BINS_PER_THREAD + q;
-        uint32_t run = 0;
-        for (uint32_t t = 0; t < nTilesOfDraw; t++) {
-            uint32_t* p = rows + (size_t)t * BIN_COUNT + b;
-            const uint32_t c = __ldcg(p);
-            *p = run;
-            run += c;
+        for (int u = 0; u < 8; u++) c[u] = (t0 + u < nT) ? __ldcg(&rows[(size_t)(t0 + u) * (BIN_COUNT / 2) + threadIdx.x]) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (t0 + u < nT) rows[(size_t)(t0 + u) * (BIN_COUNT / 2) + threadIdx.x] = run;
+            run.x += c[u].x; run.y += c[u].y;
         }
-        tot[q] = run;
     }
-    uint32_t sum = 0;
-#pragma unroll
-    for (int q = 0; q < BINS_PER_THREAD; q++) sum += tot[q];
-    uint32_t base = block_exclusive_scan_256(sum, sWarp, nullptr);
-#pragma unroll
-    for (int q = 0; q < BINS_PER_THREAD; q++) {
-        const uint32_t b = threadIdx.x * BINS_PER_THREAD + q;
-        if (base) for (uint32_t t = 0; t < nTilesOfDraw; t++) rows[(size_t)t * BIN_COUNT + b] += base;
-        base += tot[q];
-    }
+    const uint32_t base = block_exclusive_scan_256(run.x + run.y, sWarp, nullptr);
+    rows[(size_t)nT * (BIN_COUNT / 2) + threadIdx.x] = make_uint2(base, base + run.x);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-k_scatter(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
+k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
           const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ hist, uint32_t* __restrict__ sorted) {
-    // sCnt[(round, warp)][bin]: how many of that warp's lanes hold the bin in that round, then (after the
-    // scan over (round, warp), which is arrival order) the in-tile rank of the group's first lane.
-    __shared__ uint16_t sCnt[SORT_ROUNDS * 8][BIN_COUNT];
+    // Warp w owns the tile's slots [w * 128, w * 128 + 128) and walks them in SORT_ROUNDS rounds of 32, so
+    // arrival order is (warp, round, lane).  sCnt[w][bin] accumulates the warp's count of a bin round by round
+    // (the value before a round's update is the rank base of that round's group), then becomes the exclusive
+    // prefix over warps.
+    __shared__ __align__(16) uint16_t sCnt[8][BIN_COUNT];
     __shared__ uint32_t sBase[BIN_COUNT];
     const unsigned full = 0xFFFFFFFFu;
-    const uint32_t row = blockIdx.x;
-    const TriTile T = tiles[__ldg(&largeList[row])];
-    const uint32_t tb = draws[T.dFirst].tbase;
+    const TriTile T = tiles[__ldg(&largeList[blockIdx.x])];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
-        uint32_t* z = reinterpret_cast<uint32_t*>(&sCnt[0][0]);
-        for (uint32_t i = threadIdx.x; i < SORT_ROUNDS * 8 * BIN_COUNT / 2; i += SORT_THREADS) z[i] = 0;
-#pragma unroll
-        for (int q = 0; q < BINS_PER_THREAD; q++) sBase[threadIdx.x + q * SORT_THREADS] = hist[(size_t)row * BIN_COUNT + threadIdx.x + q * SORT_THREADS];
+        uint4* z = reinterpret_cast<uint4*>(&sCnt[0][0]);
+        static_assert(sizeof(sCnt) == 2 * SORT_THREADS * sizeof(uint4), "two 128-bit stores per thread clear the counts");
+        z[threadIdx.x] = make_uint4(0, 0, 0, 0); z[threadIdx.x + SORT_THREADS] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
+    pdl_wait();             // bin ranks and offsets are k_bin_hist's
+    pdl_launch();
     uint32_t key[SORT_ROUNDS], rank[SORT_ROUNDS];
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
-        const uint32_t i = r * SORT_THREADS + threadIdx.x;
+        const uint32_t i = warp * (SORT_ROUNDS * 32) + r * 32 + lane;
         key[r] = (i < T.count) ? __ldg(&tkeys[T.start + i]) : KEY_CULLED;
-        const unsigned peers = __match_any_sync(full, key[r]);
-        rank[r] = __popc(peers & ((1u << lane) - 1u));
-        if (key[r] != KEY_CULLED && rank[r] == 0) sCnt[r * 8 + warp][key[r]] = (uint16_t)__popc(peers);
     }
-    __syncthreads();
+    {
+        const uint32_t* offRow = hist + (size_t)(T.row0 + (T.info & ~TILE_LARGE)) * BIN_COUNT;
+        const uint32_t* baseRow = hist + (size_t)(T.row0 + T.nTilesOfDraw) * BIN_COUNT;
 #pragma unroll
-    for (int q = 0; q < BINS_PER_THREAD; q++) {
-        const uint32_t b = threadIdx.x + q * SORT_THREADS;
-        uint32_t run = 0;
-#pragma unroll 8
-        for (int e = 0; e < SORT_ROUNDS * 8; e++) { const uint32_t c = sCnt[e][b]; sCnt[e][b] = (uint16_t)run; run += c; }
+        for (int q = 0; q < BINS_PER_THREAD; q++) {
+            const uint32_t b = threadIdx.x + q * SORT_THREADS;
+            sBase[b] = T.tbase + __ldg(&offRow[b]) + __ldg(&baseRow[b]);
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
-        if (key[r] != KEY_CULLED) {
-            const uint32_t i = r * SORT_THREADS + threadIdx.x;
-            sorted[tb + sBase[key[r]] + sCnt[r * 8 + warp][key[r]] + rank[r]] = T.start + i;
+        const unsigned peers = __match_any_sync(full, key[r]);
+        const uint32_t inGroup = __popc(peers & ((1u << lane) - 1u));
+        uint32_t before = 0;
+        if (key[r] != KEY_CULLED && inGroup == 0) {
+            before = sCnt[warp][key[r]];
+            sCnt[warp][key[r]] = (uint16_t)(before + __popc(peers));
         }
+        rank[r] = __shfl_sync(full, before, __ffs(peers) - 1) + inGroup;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive prefix over the 8 warps, two adjacent bins per thread packed in one 32-bit word (counts <= 1024)
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            uint32_t* word = reinterpret_cast<uint32_t*>(&sCnt[w][0]) + threadIdx.x;
+            const uint32_t c = *word;
+            *word = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        if (key[r] != KEY_CULLED)
+            sorted[sBase[key[r]] + sCnt[warp][key[r]] + rank[r]] = T.start + warp * (SORT_ROUNDS * 32) + r * 32 + lane;
     }
 }
 
@@ -173,6 +184,8 @@ k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* 
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sCarry = 0;
+    pdl_wait();
+    pdl_launch();
     __syncthreads();
     for (uint32_t base = 0; base < nTiles; base += 1024) {
         const uint32_t t = base + threadIdx.x;
@@ -209,21 +222,21 @@ k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* 
     if (threadIdx.x == 0) { tileOut[nTiles] = sCarry; *dCount = sCarry; }
 }
 
-void launch_bin_hist(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                      DrawStat* stats, uint32_t* tdepth, uint32_t* hist) {
     if (!nLarge) return;
-    k_bin_hist<<<nLarge, SORT_THREADS, 0, s>>>(draws, tiles, largeList, stats, tdepth, hist);
+    launch_kernel(k_bin_hist, nLarge, SORT_THREADS, 0, s, pdl, tiles, largeList, stats, tdepth, hist);
 }
 
-void launch_scatter(cudaStream_t s, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
+void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                     const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted) {
     if (!nLarge) return;
-    k_scatter<<<nLarge, SORT_THREADS, 0, s>>>(draws, tiles, largeList, tkeys, hist, sorted);
+    launch_kernel(k_scatter, nLarge, SORT_THREADS, 0, s, pdl, tiles, largeList, tkeys, hist, sorted);
 }
 
-void launch_tile_scan(cudaStream_t s, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
+void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
                       uint32_t* tileOut, uint32_t* dCount) {
-    k_tile_scan<<<1, 1024, 0, s>>>(tiles, nTiles, stats, tileSurv, tileOut, dCount);
+    launch_kernel(k_tile_scan, 1, 1024, 0, s, pdl, tiles, nTiles, stats, tileSurv, tileOut, dCount);
 }
 
 }  // namespace t3d

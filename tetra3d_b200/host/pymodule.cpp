@@ -235,6 +235,7 @@ PYBIND11_MODULE(_host, m) {
         .def(py::init<int>(), py::arg("device") = 0)
         .def_readonly("DeviceID", &GeometryDevice::deviceId)
         .def("Stream", [](GeometryDevice& d) { return (uintptr_t)t3d_debug_stream(d.ctx); })
+        .def("SetStageTimings", [](GeometryDevice& d, bool on) { t3d_set_stage_timings(d.ctx, on ? 1 : 0); })
         .def("VertexKernelBytes", [](GeometryDevice& d) { return t3d_debug_vertex_kernel_bytes(d.ctx); })
         .def("FrameBytes", [](GeometryDevice& d) { uint64_t a = 0, b = 0; t3d_debug_frame_bytes(d.ctx, &a, &b); return py::make_tuple(a, b); })
         .def("ReadDrawVertices", [](GeometryDevice& d, uint32_t draw, uint32_t v0, uint32_t v1) {
