@@ -110,7 +110,7 @@ struct t3d_ctx {
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
-    DevBuf dClip, dLight, dWpos, dUnbill, dTnrm;
+    DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
     DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
     DevBuf dColor, dDepth, dNormal, dTriIds;
 
@@ -195,7 +195,7 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (auto& kv : ctx->meshes) kv.second.release();
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame,
-                      &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
+                      &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
@@ -557,6 +557,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
     CU(ctx->dStats.ensure(sizeof(DrawStat) * nDraws));
     CU(ctx->dClip.ensure(16ull * std::max(totalV, 4u)));
+    CU(ctx->dClipXY.ensure(8ull * std::max(totalV, 4u)));
     CU(ctx->dLight.ensure(16ull * std::max(ctx->anyLit ? totalV : 4u, 4u)));
     CU(ctx->dWpos.ensure(16ull * std::max(ctx->anySkinned ? totalV : 4u, 4u)));
     CU(ctx->dUnbill.ensure(4ull * std::max(ctx->anyUnbill ? totalV : 4u, 4u)));
@@ -624,7 +625,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                       (uint32_t)ctx->hLights.n, ctx->dLightsU.as<LightU>(), stats);
     CU(mark(2));
     launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalV, ctx->fc,
-                  ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(),
+                  ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 2;
     CU(mark(3));
@@ -644,7 +645,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(mark(5));
     // K4
     launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
-                ctx->fc, ctx->dClip.as<float4>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+                ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                 ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[6], s));
@@ -783,7 +784,12 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
     if (vtx_start < R.a0 || vtx_end > R.a0 + R.nv) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: range outside the part's vertices");
     CU(cudaStreamSynchronize(ctx->stream));
     const size_t slot = R.vbase + (vtx_start - R.a0);
-    if (clip4) CU(cudaMemcpy(clip4, ctx->dClip.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
+    if (clip4) {        // the arenas hold {X/w, Y/w, Z, W} and {X, Y}: reassemble globalVertexTransforms' {X, Y, Z, W}
+        std::vector<float> xy(2 * n);
+        CU(cudaMemcpy(clip4, ctx->dClip.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(xy.data(), ctx->dClipXY.as<float2>() + slot, n * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) { clip4[4 * i] = xy[2 * i]; clip4[4 * i + 1] = xy[2 * i + 1]; }
+    }
     if (light4) {
         if (R.flags & T3D_DRAW_LIT) CU(cudaMemcpy(light4, ctx->dLight.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
         else memset(light4, 0, n * 16);

@@ -150,6 +150,31 @@ static const int BIN_COUNT = 512;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Exclusive scan of one value per thread over a 256-thread block.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* sWarp /*8*/, uint32_t* total) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(full, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    uint32_t wsum = (lane < 8) ? sWarp[lane] : 0;
+    uint32_t winc = wsum;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        uint32_t n = __shfl_up_sync(full, winc, o);
+        if (lane >= o) winc += n;
+    }
+    const uint32_t warpBase = __shfl_sync(full, winc - wsum, warp);
+    if (total) *total = __shfl_sync(full, winc, 7);
+    __syncthreads();
+    return warpBase + inc - v;
+}
+
 // 512-bin key of one surviving triangle (sortingTriangles.go:38-64).  BackToFront visits bins 511..0
 // (sortingTriangles.go:101), so the key is the visiting rank of the bin: ascending key == draw order.
 __device__ __forceinline__ uint32_t bin_key(uint32_t depthBits, uint32_t minBits, uint32_t maxBits, uint32_t sortMode) {

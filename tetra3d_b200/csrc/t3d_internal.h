@@ -24,14 +24,14 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* de
                        const FrameConst& fc, const t3d_light* lightsHost, uint32_t nLightsIn, LightU* lightsU, DrawStat* stats);
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
-                   const VolumeU* vols, float4* clip, float4* light, float4* wpos, float* unbill, float4* tnrm);
+                   const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats);
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
                         const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats);
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
-                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip,
+                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds);
 static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex block (tileFirst granularity)

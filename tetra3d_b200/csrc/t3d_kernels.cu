@@ -305,7 +305,7 @@ template <class Uniforms>
 __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const Uniforms U, const FrameConst& fc,
                                              const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
                                              const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
-                                             float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
+                                             float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
                                              float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     const bool skinned = flags & T3D_DRAW_SKINNED;
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
@@ -356,7 +356,13 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
             c.y = roundf(c.y * snap) / snap;
             c.z = roundf(c.z * snap) / snap;
         }
-        clipOut[slot] = c;
+        // The perspective divide of the cull (model.go:866-875) depends on the vertex alone, so it is done here once
+        // per vertex instead of once per triangle corner: {X/w, Y/w, Z, W} with the cull's clamp of a negative w.
+        // The emit loop divides by the same w unless w < 0 (camera.go:1655-1675), and then reads X, Y from clipXY.
+        float wc = c.w;
+        if (wc < 0) wc = 0.000001f;
+        clipOut[slot] = make_float4(c.x / wc, c.y / wc, c.z, c.w);
+        clipXY[slot] = make_float2(c.x, c.y);
         if (!skinned && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) {       // model.go:800-803
             const float4 u = ldg4(R.unbill);
             unbillOut[slot] = u.x * P.X + u.y * P.Y + u.z * P.Z + u.w;
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(VERTEX_BLOCK, T3D_K1_MINBLOCKS)
 k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
          uint32_t totalV, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
-         float4* __restrict__ clipOut, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
+         float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
     pdl_wait();             // everything below reads what k_prep_draws wrote
@@ -472,7 +478,7 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
             __syncthreads();
             if (slot >= end) return;
             UniformsShared U; U.s = sU;
-            shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, lightOut, wposOut, unbillOut, tnrmOut);
+            shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
             return;
         }
     }
@@ -490,22 +496,17 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
     }
     UniformsGlobal U;
     U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
-    shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, lightOut, wposOut, unbillOut, tnrmOut);
+    shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: cull + depth key (model.go:855-969)
 // ------------------------------------------------------------------------------------------------
 
-// The keep / drop decision of one triangle from its three clip-space corners (model.go:866-925).
+// The keep / drop decision of one triangle (model.go:866-925) from the three per-vertex records k_vertex left:
+// {X/w, Y/w, Z, W}, the divide already done with the cull's clamp of a negative w (model.go:866-875).
 __device__ __forceinline__ bool cull_keep(const float4 c0, const float4 c1, const float4 c2, bool backface, float nearP, float farP) {
-    float w0 = c0.w, w1 = c1.w, w2 = c2.w;                              // model.go:866-875
-    if (w0 < 0) w0 = 0.000001f;
-    if (w1 < 0) w1 = 0.000001f;
-    if (w2 < 0) w2 = 0.000001f;
-    const float x0 = c0.x / w0, y0 = c0.y / w0;
-    const float x1 = c1.x / w1, y1 = c1.y / w1;
-    const float x2 = c2.x / w2, y2 = c2.y / w2;
+    const float x0 = c0.x, y0 = c0.y, x1 = c1.x, y1 = c1.y, x2 = c2.x, y2 = c2.y;
     bool keep = (c0.z + 1.0f >= nearP && c0.z < farP) || (c1.z + 1.0f >= nearP && c1.z < farP) ||
                 (c2.z + 1.0f >= nearP && c2.z < farP);                  // model.go:877-879
     if (keep && ((x0 < -0.5f && x1 < -0.5f && x2 < -0.5f) || (x0 > 0.5f && x1 > 0.5f && x2 > 0.5f) ||
@@ -601,30 +602,110 @@ k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tile
     }
 }
 
+// One stable counting-sort pass over the block's (at most TILE_TRIS) keys in shared memory, on the NB-valued
+// digit (key >> SHIFT) & (NB - 1).  Warp w owns slots [w * 128, w * 128 + 128) and walks them in rounds of 32,
+// so arrival order is (warp, round, lane) == slot order.  Entries at or beyond n, and entries equal to
+// PK_INVALID, do not take part; the others land in out[0 .. valid) in (digit, arrival) order.
+static const uint32_t PK_INVALID = 0xFFFFFFFFu;
+template <int SHIFT, int NB>
+__device__ __forceinline__ void smem_radix_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                uint16_t* __restrict__ sCnt /*[8][NB]*/, uint32_t* __restrict__ sBucket /*[NB]*/,
+                                                uint32_t* __restrict__ sWarp /*[8]*/) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int WORDS = NB / 2;                       // 32-bit words per warp row (two 16-bit counts each)
+    constexpr int WPT = WORDS / TILE_THREADS;           // words per thread in the bucket scan
+    static_assert(WPT >= 1 && WORDS % TILE_THREADS == 0, "bucket scan layout");
+    {
+        uint4* z = reinterpret_cast<uint4*>(sCnt);
+        for (int i = threadIdx.x; i < 8 * NB * 2 / 16; i += TILE_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    uint32_t key[TILE_ROUNDS], rank[TILE_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < TILE_ROUNDS; r++) {
+        const uint32_t i = warp * (TILE_ROUNDS * 32) + r * 32 + lane;
+        key[r] = (i < n) ? in[i] : PK_INVALID;
+        const bool valid = key[r] != PK_INVALID;
+        const uint32_t digit = (key[r] >> SHIFT) & (NB - 1);
+        const unsigned peers = __match_any_sync(full, valid ? digit : 0xFFFFFFFFu);
+        const uint32_t inGroup = __popc(peers & ((1u << lane) - 1u));
+        uint32_t before = 0;
+        if (valid && inGroup == 0) {
+            before = sCnt[warp * NB + digit];
+            sCnt[warp * NB + digit] = (uint16_t)(before + __popc(peers));
+        }
+        rank[r] = __shfl_sync(full, before, __ffs(peers) - 1) + inGroup;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per bucket: exclusive prefix over the warps; then bucket bases = exclusive scan of the bucket totals
+        uint32_t* words = reinterpret_cast<uint32_t*>(sCnt);
+        uint32_t tot[WPT];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < WPT; q++) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t* p = words + w * WORDS + threadIdx.x * WPT + q;
+                const uint32_t c = *p;
+                *p = run;
+                run += c;                                   // two 16-bit lanes, each at most TILE_TRIS: no carry
+            }
+            tot[q] = run;
+            sum += (run & 0xFFFFu) + (run >> 16);
+        }
+        uint32_t base = block_exclusive_scan_256(sum, sWarp, nullptr);
+#pragma unroll
+        for (int q = 0; q < WPT; q++) {
+            const uint32_t b = 2 * (threadIdx.x * WPT + q);
+            sBucket[b] = base; base += tot[q] & 0xFFFFu;
+            sBucket[b + 1] = base; base += tot[q] >> 16;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TILE_ROUNDS; r++) {
+        if (key[r] != PK_INVALID) {
+            const uint32_t digit = (key[r] >> SHIFT) & (NB - 1);
+            out[sBucket[digit] + sCnt[warp * NB + digit] + rank[r]] = key[r];
+        }
+    }
+    __syncthreads();
+}
+
 // Packed tiles: every draw of the tile lies wholly inside it, so cull, per-draw min / max, binning and the
-// stable (draw, bin) ordering all happen in shared memory.  The order is a bitonic sort of the composite
-//   culled(1) | draw-in-tile(10) | bin rank(10) | slot-in-tile(10)
-// whose low bits make it stable; survivors come out first, in (draw, bin, arrival) order.
-static const uint32_t PK_CULLED = 1u << 30;
+// stable (draw, bin) ordering all happen in shared memory.  Survivors carry the composite
+//   draw-in-tile (10 bits) << 20 | bin rank (10) << 10 | slot-in-tile (10)
+// through two stable counting-sort passes (bin rank, then draw; the second is skipped for a one-draw tile) and
+// come out in (draw, bin, arrival) order -- the order sortingTriangleBucket.ForEach visits them in.
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tbase, const TriTile* __restrict__ tiles,
               const uint32_t* __restrict__ packedList, const __grid_constant__ FrameConst fc,
               const float4* __restrict__ clip, const float4* __restrict__ wpos,
               uint32_t* __restrict__ sorted, uint32_t* __restrict__ tileSurv, DrawStat* __restrict__ stats) {
-    __shared__ uint32_t sBase[TILE_TRIS + 1];       // tbase of the tile's draws
-    __shared__ uint32_t sKey[TILE_TRIS];            // depth bits, then composite keys
-    __shared__ uint32_t sMin[TILE_TRIS], sMax[TILE_TRIS];
+    // The per-draw tables of the cull phase and the counters of the sort phase share storage.
+    __shared__ __align__(16) uint8_t sRaw[16 * 1024 + 16];
+    __shared__ uint32_t sKeyA[TILE_TRIS];           // depth bits, then composite keys
+    __shared__ uint32_t sKeyB[TILE_TRIS];
+    __shared__ uint32_t sBucket[TILE_TRIS];
     __shared__ uint16_t sSeg[TILE_TRIS];
-    __shared__ uint32_t sCnt[TILE_TRIS];
-    __shared__ uint32_t sTotal;
+    __shared__ uint32_t sWarp[8];
+    uint32_t* sBase = reinterpret_cast<uint32_t*>(sRaw);            // [TILE_TRIS + 1] tbase of the tile's draws
+    uint32_t* sMin = sBucket;                                       // per-draw stats live in sBucket / sKeyB until the sort starts
+    uint32_t* sMax = sKeyB;
+    uint32_t* sCntSeg = sBase + TILE_TRIS + 4;                      // [TILE_TRIS] -- needs 8 KB + 16: see static_assert
+    static_assert(sizeof(sRaw) >= (2 * TILE_TRIS + 4) * sizeof(uint32_t) && sizeof(sRaw) >= 8 * 1024 * sizeof(uint16_t), "shared carve-up");
+    uint16_t* sCnt = reinterpret_cast<uint16_t*>(sRaw);             // [8][<=1024] sort phase
+
     const uint32_t tileId = __ldg(&packedList[blockIdx.x]);
     const TriTile T = tiles[tileId];
     const uint32_t nSeg = T.info;
     const unsigned full = 0xFFFFFFFFu;
 
     for (uint32_t s = threadIdx.x; s <= nSeg; s += TILE_THREADS) sBase[s] = __ldg(&tbase[T.dFirst + s]);
-    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) { sMin[s] = 0x7F7FFFFFu; sMax[s] = 0u; sCnt[s] = 0; }
-    if (threadIdx.x == 0) sTotal = 0;
+    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) { sMin[s] = 0x7F7FFFFFu; sMax[s] = 0u; sCntSeg[s] = 0; }
     pdl_wait();
     pdl_launch();
     __syncthreads();
@@ -661,7 +742,7 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
             }
             sSeg[i] = (uint16_t)seg;
         }
-        sKey[i] = keep ? bits : KEY_CULLED;
+        sKeyA[i] = keep ? bits : KEY_CULLED;
         // per-draw min / max / survivors: one set of shared atomics per warp when the warp sits in one draw
         const uint32_t seg0 = __shfl_sync(full, seg, 0);
         const bool uniform = __all_sync(full, (!active) || seg == seg0);
@@ -670,56 +751,48 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
             if (km) {
                 const uint32_t mn = __reduce_min_sync(full, keep ? bits : 0xFFFFFFFFu);
                 const uint32_t mx = __reduce_max_sync(full, keep ? bits : 0u);
-                if ((threadIdx.x & 31) == 0) { atomicMin(&sMin[seg0], mn); atomicMax(&sMax[seg0], mx); atomicAdd(&sCnt[seg0], (uint32_t)__popc(km)); }
+                if ((threadIdx.x & 31) == 0) { atomicMin(&sMin[seg0], mn); atomicMax(&sMax[seg0], mx); atomicAdd(&sCntSeg[seg0], (uint32_t)__popc(km)); }
             }
         } else if (keep) {
-            atomicMin(&sMin[seg], bits); atomicMax(&sMax[seg], bits); atomicAdd(&sCnt[seg], 1u);
+            atomicMin(&sMin[seg], bits); atomicMax(&sMax[seg], bits); atomicAdd(&sCntSeg[seg], 1u);
         }
     }
     __syncthreads();
 
-    // ---- composite keys ----
-    uint32_t n2 = 32;
-    while (n2 < T.count) n2 <<= 1;
-    for (uint32_t i = threadIdx.x; i < n2; i += TILE_THREADS) {
-        uint32_t key = 0xFFFFFFFFu;                                     // padding sorts last
-        if (i < T.count) {
-            const uint32_t bits = sKey[i], seg = sSeg[i];
-            if (bits == KEY_CULLED) key = PK_CULLED | (seg << 20) | i;
-            else key = (seg << 20) | (bin_key(bits, sMin[seg], sMax[seg], draws[T.dFirst + seg].sortMode) << 10) | i;
-        }
-        sKey[i] = key;
+    // ---- composite keys; per-draw results out (their storage is reused by the sort) ----
+    for (uint32_t i = threadIdx.x; i < T.count; i += TILE_THREADS) {
+        const uint32_t bits = sKeyA[i], seg = sSeg[i];
+        uint32_t key = PK_INVALID;
+        if (bits != KEY_CULLED) key = (seg << 20) | (bin_key(bits, sMin[seg], sMax[seg], draws[T.dFirst + seg].sortMode) << 10) | i;
+        sKeyA[i] = key;
+    }
+    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) {
+        DrawStat st; st.minBits = sMin[s]; st.maxBits = sMax[s]; st.survivors = sCntSeg[s]; st.done = 0;
+        stats[T.dFirst + s] = st;
     }
     __syncthreads();
 
-    // ---- bitonic sort, ascending ----
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += TILE_THREADS) {
-                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const uint32_t hi = lo | j;
-                const uint32_t a = sKey[lo], b = sKey[hi];
-                const bool up = (lo & k) == 0;
-                if ((a > b) == up) { sKey[lo] = b; sKey[hi] = a; }
-            }
-            __syncthreads();
-        }
+    // ---- stable order: by bin rank, then (tiles of several draws) by draw ----
+    uint32_t nSurv = 0;
+    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) nSurv += sCntSeg[s];
+    nSurv = __reduce_add_sync(full, nSurv);
+    __syncthreads();                                    // sCntSeg is about to be overwritten by the pass counters
+    if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = nSurv;
+    __syncthreads();
+    nSurv = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) nSurv += sWarp[w];
+    __syncthreads();
+    smem_radix_pass<10, 512>(sKeyA, sKeyB, T.count, sCnt, sBucket, sWarp);
+    const uint32_t* res = sKeyB;
+    if (nSeg > 1) {
+        smem_radix_pass<20, 1024>(sKeyB, sKeyA, nSurv, sCnt, sBucket, sWarp);
+        res = sKeyA;
     }
 
     // ---- survivors out: value = draw-in-tile << 20 | bin rank << 10 | slot-in-tile ----
-    uint32_t mine = 0;
-    for (uint32_t i = threadIdx.x; i < T.count; i += TILE_THREADS) {
-        const uint32_t key = sKey[i];
-        if (key < PK_CULLED) { sorted[T.start + i] = key; mine++; }
-    }
-    mine = __reduce_add_sync(full, mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sTotal, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) tileSurv[tileId] = sTotal;
-    for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) {
-        DrawStat st; st.minBits = sMin[s]; st.maxBits = sMax[s]; st.survivors = sCnt[s]; st.done = 0;
-        stats[T.dFirst + s] = st;
-    }
+    for (uint32_t i = threadIdx.x; i < nSurv; i += TILE_THREADS) sorted[T.start + i] = res[i];
+    if (threadIdx.x == 0) tileSurv[tileId] = nSurv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -746,8 +819,8 @@ template <bool NORMALS>
 __global__ void __launch_bounds__(EMIT_TRIS)
 k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
        const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const __grid_constant__ FrameConst fc,
-       const float4* __restrict__ clip, const float4* __restrict__ light, const float* __restrict__ unbill,
-       const float4* __restrict__ tnrm,
+       const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
+       const float* __restrict__ unbill, const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
        uint32_t* __restrict__ triIds) {
     extern __shared__ uint4 emitSmem[];
@@ -802,9 +875,17 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
             const float4 Tc = __ldg(&clip[slot]);
             float w = Tc.w;                                             // camera.go:1655-1666
             if (!persp) w = 1.0f;
-            if (w < 0) w = 0.001f;
-            const float dx = (Tc.x / w) * fc.camW + fc.halfW;           // camera.go:1674-1675
-            const float dy = (Tc.y / -w) * fc.camH + fc.halfH;
+            const bool behind = w < 0;
+            if (behind) w = 0.001f;
+            // X/w and Y/w are k_vertex's unless the emit loop's w differs from the cull's (w < 0, orthographic);
+            // Y / -w == -(Y / w) exactly
+            float qx = Tc.x, qy = -Tc.y;
+            if (behind || !persp) {
+                const float2 xy = __ldg(&clipXY[slot]);
+                qx = xy.x / w; qy = xy.y / -w;
+            }
+            const float dx = qx * fc.camW + fc.halfW;                   // camera.go:1674-1675
+            const float dy = qy * fc.camH + fc.halfH;
 
             const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
             float uvU, uvV, custom0 = 0.0f;
@@ -895,10 +976,10 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* de
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
-                   const VolumeU* vols, float4* clip, float4* light, float4* wpos, float* unbill, float4* tnrm) {
+                   const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
     if (!totalV) return;
     launch_kernel(k_vertex, cdiv(totalV, VERTEX_BLOCK), VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, totalV, fc, lightsU, bones, vols,
-                  clip, light, wpos, unbill, tnrm);
+                  clip, clipXY, light, wpos, unbill, tnrm);
 }
 
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
@@ -915,17 +996,17 @@ void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const ui
 }
 
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
-                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip,
+                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds) {
     if (!nTiles) return;
     const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
     if (normalList)
         launch_kernel(k_emit<true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
     else
         launch_kernel(k_emit<false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
 }
 
 }  // namespace t3d

@@ -23,31 +23,6 @@ static const int SORT_THREADS = 256;
 static const int SORT_ROUNDS = TILE_TRIS / SORT_THREADS;
 static const int BINS_PER_THREAD = BIN_COUNT / SORT_THREADS;
 
-// Exclusive scan of one value per thread over a 256-thread block.
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* sWarp /*8*/, uint32_t* total) {
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(full, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) sWarp[warp] = inc;
-    __syncthreads();
-    uint32_t wsum = (lane < 8) ? sWarp[lane] : 0;
-    uint32_t winc = wsum;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        uint32_t n = __shfl_up_sync(full, winc, o);
-        if (lane >= o) winc += n;
-    }
-    const uint32_t warpBase = __shfl_sync(full, winc - wsum, warp);
-    if (total) *total = __shfl_sync(full, winc, 7);
-    __syncthreads();
-    return warpBase + inc - v;
-}
-
 // Histogram rows: tile j of a large draw owns row T.row0 + j; row T.row0 + nTilesOfDraw receives the bin bases.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
@@ -175,51 +150,51 @@ k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeL
 }
 
 // One block.  Large tile j of a draw holds survivors [j * TILE_TRIS, ...) of the draw's sorted run; packed
-// tiles wrote their own counts.
+// tiles wrote their own counts.  Thread t owns the contiguous run of tiles [t * per, (t + 1) * per): one pass
+// to count, a block scan of the 1024 run totals, one pass to write the prefixes.
+__device__ __forceinline__ uint32_t tile_survivors(const TriTile* __restrict__ tiles, const DrawStat* __restrict__ stats,
+                                                   const uint32_t* __restrict__ tileSurv, uint32_t t) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(tiles + t));       // start, count, dFirst, info
+    if (a.w & TILE_LARGE) {
+        const uint32_t surv = stats[a.z].survivors, off = (a.w & ~TILE_LARGE) * TILE_TRIS;
+        return surv > off ? min(surv - off, TILE_TRIS) : 0u;
+    }
+    return tileSurv[t];
+}
+
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* __restrict__ stats,
             uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ dCount) {
     __shared__ uint32_t sWarp[32];
-    __shared__ uint32_t sCarry;
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) sCarry = 0;
+    const uint32_t per = (nTiles + 1023u) / 1024u;
+    const uint32_t t0 = min(threadIdx.x * per, nTiles), t1 = min(t0 + per, nTiles);
     pdl_wait();
     pdl_launch();
+    uint32_t sum = 0;
+    for (uint32_t t = t0; t < t1; t++) sum += tile_survivors(tiles, stats, tileSurv, t);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) sWarp[warp] = inc;
     __syncthreads();
-    for (uint32_t base = 0; base < nTiles; base += 1024) {
-        const uint32_t t = base + threadIdx.x;
-        uint32_t c = 0;
-        if (t < nTiles) {
-            const TriTile T = tiles[t];
-            if (T.info & TILE_LARGE) {
-                const uint32_t surv = stats[T.dFirst].survivors, off = (T.info & ~TILE_LARGE) * TILE_TRIS;
-                c = surv > off ? min(surv - off, TILE_TRIS) : 0u;
-                tileSurv[t] = c;
-            } else {
-                c = tileSurv[t];
-            }
-        }
-        uint32_t inc = c;
+    if (warp == 0) {
+        const uint32_t w = sWarp[lane];
+        uint32_t wi = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, inc, o); if (lane >= o) inc += n; }
-        if (lane == 31) sWarp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = sWarp[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, wi, o); if (lane >= o) wi += n; }
-            sWarp[lane] = wi - w;
-        }
-        __syncthreads();
-        const uint32_t carry = sCarry;
-        const uint32_t excl = carry + sWarp[warp] + inc - c;
-        if (t < nTiles) tileOut[t] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) sCarry = excl + c;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, wi, o); if (lane >= o) wi += n; }
+        sWarp[lane] = wi - w;
+        if (lane == 31) { tileOut[nTiles] = wi; *dCount = wi; }
     }
-    if (threadIdx.x == 0) { tileOut[nTiles] = sCarry; *dCount = sCarry; }
+    __syncthreads();
+    uint32_t run = sWarp[warp] + inc - sum;
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t c = tile_survivors(tiles, stats, tileSurv, t);
+        tileOut[t] = run;
+        tileSurv[t] = c;
+        run += c;
+    }
 }
 
 void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,

@@ -311,4 +311,9 @@ WORKLOADS = {
     "skinned_crowd": skinned_crowd_scene,
     "particles": particles_scene,
     "instanced": instanced_scene,
+    # reduced variants for exploration (not BASELINE configs): one GPU's share of configs[4] at 8 GPUs, and a
+    # tenth of configs[3]
+    "instanced_shard": lambda: instanced_scene(n=2442),
+    "particles_200k": lambda: particles_scene(n=200000),
+    "skinned_crowd_1k": lambda: skinned_crowd_scene(n=1000),
 }
