@@ -174,23 +174,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_out = [None]
+    shared = [None]
 
     def device_step(timed):
-        """One device-resident frame; returns (ms of this rank, stage timings)."""
+        """One device-resident frame; returns (ms of this rank, stage timings).  At N > 1 every rank's emit kernel
+        writes straight into rank 0's lists over NVLink (parallel.SharedLists), so the transfer is inside the
+        frame's own event pair; what remains is the all-reduce of the per-flush counts, timed as gather_ms."""
         flush_l2()
         cam.Clear()
         cam.RenderScene(scene)
         tm = cam.Timings()
         ms = tm["total_ms"]
         if world > 1:
-            col, dep = parallel.device_lists(cam, local)
             table = [(f["global_flush"], f["vertex_count"]) for f in cam.Flushes()]
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            out, _ = parallel.gather_lists([col, dep], table, dst=0, out=gather_out[0], n_flushes_total=len(cam.FlushOwnerRanks()))
-            if out is not None:
-                gather_out[0] = out
+            shared[0].collect(table, len(cam.FlushOwnerRanks()))
             e1.record(); torch.cuda.synchronize()
             tm = dict(tm); tm["gather_ms"] = e0.elapsed_time(e1)
             ms += tm["gather_ms"]
@@ -199,6 +198,9 @@ def run_ours(args):
     # ---- device-resident value: kernels chained with programmatic dependent launches, one event pair per frame ----
     cam.DownloadResults = False
     device.SetStageTimings(False)
+    if world > 1:
+        cam.Clear(); cam.RenderScene(scene)          # sizes the shared lists: 3 vertices per triangle this rank draws
+        shared[0] = parallel.SharedLists(device, local, 3 * sum(r["total_tris"] for r in cam.Renders()), dst=0)
     for _ in range(max(args.warmup, 3)):
         device_step(False)
     sampler = ClockSampler(local)
@@ -233,12 +235,19 @@ def run_ours(args):
     vbytes = device.VertexKernelBytes()
     h2d_dev, _ = device.FrameBytes()
     t = torch.tensor([ms_sum], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mine = torch.tensor([(ms_sum - gather_sum) / args.steps, gather_sum / args.steps], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"frame_ms": float(a[0]), "count_exchange_ms": float(a[1])} for a in allr]
     ms_per_step = float(t.item()) / args.steps
     value = tris_total / (ms_per_step * 1e-3)
 
     # ---- e2e through the public API with host buffers ----
+    if world > 1:
+        shared[0].release()
     cam.DownloadResults = True
     for _ in range(3):
         cam.Clear(); cam.RenderScene(scene)
@@ -311,9 +320,10 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "triangles_per_frame": tris_total, "vertices": desc.total_vertices(), "draws_rank0": n_draws,
                    "surviving_triangles_rank0": surv, "l2": "flushed between steps (512 MiB write)",
-                   "parallelism": "object-wise flush sharding x%d + NCCL gather to rank 0" % world if world > 1 else "1 GPU",
+                   "parallelism": "object-wise flush sharding x%d; every rank's emit kernel stores into rank 0's lists over NVLink (CUDA IPC peer memory), per-flush counts by NCCL all-reduce" % world if world > 1 else "1 GPU",
                    "timing": "CUDA events on the library's launch stream around the frame's kernels (the first one fetches the uniforms over PCIe), max over ranks; roofline.stages from a second loop with an event between kernels",
-                   "wall_ms_per_step_incl_flush_and_host": (wall1 - wall0) / args.steps * 1e3},
+                   "wall_ms_per_step_incl_flush_and_host": (wall1 - wall0) / args.steps * 1e3,
+                   **({"per_rank": per_rank} if per_rank is not None else {})},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "path": "Camera.RenderScene -> t3d_frame_begin/submit/execute/results (pinned H2D of uniforms, pinned D2H of colour+depth lists); meshes resident"},

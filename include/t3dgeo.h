@@ -253,6 +253,22 @@ int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings)
  * For device-resident consumers (NCCL gather, interop rasterisers). */
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
 
+/* ---- output placement ------------------------------------------------------------------------------ */
+/* Makes the emit kernel write colorVertexList / depthVertexList / normalVertexList (tetra3d.go:21-23) into
+ * caller-provided DEVICE memory instead of the library's own buffers: another GPU's memory mapped over
+ * NVLink (object-wise sharding: every rank emits straight into the lists of the rank that issues the draws,
+ * camera.go:1829-2048 consumes them there), or a buffer shared with the rasteriser.  `vertex_capacity` must
+ * cover the frame's worst case, 3 vertices per submitted triangle.  normal may be NULL unless RENDER_NORMALS.
+ * t3d_frame_results_device then returns these pointers; t3d_frame_results still copies to pinned host memory.
+ * Passing color = NULL restores the library's buffers. */
+int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity);
+/* Device memory that other processes of the same machine can map (CUDA IPC): the owning rank allocates, sends
+ * the handle over any channel, the other ranks open it and pass the pointer (plus their offset) to
+ * t3d_set_output_target.  Freed / unmapped by t3d_destroy. */
+typedef struct t3d_shared_handle { unsigned char bytes[64]; } t3d_shared_handle;
+int t3d_shared_alloc(t3d_ctx* ctx, uint64_t bytes, void** device_ptr, t3d_shared_handle* handle);
+int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device_ptr);
+
 /* ---- introspection (tests, profiling) ------------------------------------------------------------ */
 /* Stage timings put a CUDA event between the kernels of a frame, which serialises them; by default
  * (enabled = 0) the kernels are chained with programmatic dependent launches and only total_ms is measured.

@@ -25,8 +25,34 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = t3d.GeometryDevice(local)
     ok = True
-    for name, desc in (("soup_lit", scenes.soup_scene(1, n_models=9)), ("batch", scenes.batch_scene(1)),
-                       ("million_reduced", W.million_triangle_scene(nx=250, nz=125)), ("instanced", W.instanced_scene(n=24, subdivisions=2, box=(30.0, 10.0, 30.0)))):
+    scene_list = (("soup_lit", scenes.soup_scene(1, n_models=9)), ("batch", scenes.batch_scene(1)),
+                  ("million_reduced", W.million_triangle_scene(nx=250, nz=125)), ("instanced", W.instanced_scene(n=24, subdivisions=2, box=(30.0, 10.0, 30.0))))
+    # ---- peer-write path: every rank's emit kernel stores into rank 0's lists over NVLink (parallel.SharedLists) ----
+    shared = parallel.SharedLists(device, local, vertex_capacity=3 * max(d.total_triangles() for _, d in scene_list), dst=0)
+    for name, desc in scene_list:
+        scene, cam, objs = t3d.build_scene(desc, device)
+        cam.SetShard(rank, world)
+        cam.DownloadResults = False
+        for frame in range(2):      # twice: the regions are reused
+            cam.Clear(); cam.RenderScene(scene)
+            table = [(f["global_flush"], f["vertex_count"]) for f in cam.Flushes()]
+            out, tab = shared.collect(table, len(cam.FlushOwnerRanks()))
+        if rank == 0:
+            from oracle import binding as O
+            ref = O.render_scene(desc)
+            gcol = out[0].cpu().numpy().view(np.float32).reshape(-1, 12); gdep = out[1].cpu().numpy().view(np.float32).reshape(-1, 12)
+            good = len(tab) == len(ref.flushes)
+            for fid, f in enumerate(ref.flushes):
+                first, cnt = tab[fid]
+                good = good and cnt == f["vertex_count"]
+                good = good and np.array_equal(gcol[first:first + cnt].view(np.uint32), ref.color_list[f["first_vertex"]:f["first_vertex"] + cnt].view(np.uint32))
+                good = good and np.array_equal(gdep[first:first + cnt].view(np.uint32), ref.depth_list[f["first_vertex"]:f["first_vertex"] + cnt].view(np.uint32))
+            print("%-16s world=%d peer-write emit: flushes=%d -> %s" % (name, world, len(tab), "OK (bit-exact vs oracle)" if good else "MISMATCH"))
+            ok = ok and good
+        dist.barrier()
+    shared.release()
+    # ---- NCCL gather path ----
+    for name, desc in scene_list:
         scene, cam, objs = t3d.build_scene(desc, device)
         cam.SetShard(rank, world)
         cam.DownloadResults = False

@@ -78,6 +78,21 @@ def soup_scene(seed=0, n_models=4, n_tris=600, lit=True, ranged=False, cam: Came
     return SceneDesc(models, lights, cam, world if world is not None else WorldDesc(ambient_energy=0.1), name="soup%d" % seed)
 
 
+def tile_boundary_scene(seed=0, sizes=(1, 2, 1023, 1024, 1025, 7, 2048, 2049, 300, 300, 300, 300, 3000, 5, 1, 8200, 640)) -> SceneDesc:
+    """One model per entry of `sizes` (triangles in its single MeshPart): draws on both sides of the 1024-slot
+    triangle tile of the device pipeline, packed several to a tile, filling a tile exactly, and spanning several."""
+    rng = np.random.default_rng(seed)
+    models = []
+    for k, n in enumerate(sizes):
+        mat = MaterialDesc(backface_culling=bool(k % 2), triangle_sort_mode=k % 3)
+        mesh = random_soup(n, seed + 10 * k, material=mat, n_parts=1, colors=bool(k % 4 == 0))
+        nd = NodeDesc(position=tuple(float(x) for x in rng.uniform(-5, 5, 3)), scale=tuple(float(x) for x in rng.uniform(0.5, 1.5, 3)),
+                      rotation=random_rotation(rng))
+        models.append(ModelDesc(mesh, nd, frustum_culling=False, name="t%d_%d" % (k, n)))
+    cam = CameraDesc(node=NodeDesc(position=(0.5, 1.0, 14.0), rotation=W.rotation_matrix((0, 1, 0), 0.05)))
+    return SceneDesc(models, lights_mixed(rng, ranged=True), cam, WorldDesc(ambient_energy=0.1), name="tiles%d" % seed)
+
+
 def skinned_scene(seed=0, n=6) -> SceneDesc:
     rng = np.random.default_rng(seed)
     mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=5)

@@ -41,6 +41,19 @@ def test_instanced_reduced_parity(device):
     assert_parity(W.instanced_scene(n=12, subdivisions=2, box=(30.0, 10.0, 30.0)), device)
 
 
+def test_tile_boundaries_parity(device):
+    # draws of 1 .. 8200 triangles around the 1024-slot tile: packed tiles of several draws, exactly full tiles,
+    # one-draw tiles, draws spanning 2..9 tiles, all in one frame
+    assert_parity(scenes.tile_boundary_scene(31), device)
+    assert_parity(scenes.tile_boundary_scene(32, sizes=(1024,) * 3 + (1,) * 40 + (4097, 2, 2, 1030)), device, check_capture=False)
+
+
+def test_many_tiny_draws_parity(device):
+    # > 1024 draws of one or two triangles: packed tiles are cut by the draw-count limit, not by triangles
+    sc = scenes.tile_boundary_scene(33, sizes=(1, 2) * 700)
+    assert_parity(sc, device, check_capture=False)
+
+
 def test_everything_culled(device):
     sc = scenes.soup_scene(21)
     sc.camera.node.position = (0.0, 0.0, 500.0)      # everything beyond the far plane

@@ -113,6 +113,12 @@ struct t3d_ctx {
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
     DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
     DevBuf dColor, dDepth, dNormal, dTriIds;
+    // external output target (t3d_set_output_target): the emit kernel writes the lists there -- another GPU's
+    // memory over NVLink, or an interop buffer of the rasteriser -- instead of into dColor / dDepth / dNormal
+    t3d_vertex *xColor = nullptr, *xDepth = nullptr, *xNormal = nullptr;
+    t3d_vertex *oColor = nullptr, *oDepth = nullptr, *oNormal = nullptr;     // where the current frame's lists are
+    uint64_t xCapacity = 0;
+    std::vector<void*> sharedAllocs, sharedOpened;
 
     // results (pinned)
     PinVec<DrawStat> hStats;
@@ -202,6 +208,8 @@ void t3d_destroy(t3d_ctx* ctx) {
     ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
+    for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
+    for (void* q : ctx->sharedAllocs) cudaFree(q);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -568,9 +576,18 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dTileSurv.ensure(4ull * std::max(nTiles, 1u)));
     CU(ctx->dTileOut.ensure(4ull * (nTiles + 1)));
     CU(ctx->dCount.ensure(256));
-    CU(ctx->dColor.ensure(144ull * totalT));
-    CU(ctx->dDepth.ensure(144ull * totalT));
-    CU(ctx->dNormal.ensure(normals ? 144ull * totalT : 16));
+    const bool external = ctx->xColor != nullptr;
+    if (external) {
+        if (3ull * totalT > ctx->xCapacity) return fail(ctx, T3D_E_NOMEM, "t3d_frame_execute: the output target is smaller than the frame's worst case (3 vertices per submitted triangle)");
+        if (normals && !ctx->xNormal) return fail(ctx, T3D_E_INVALID, "t3d_frame_execute: RenderNormals needs a normal list in the output target");
+    } else {
+        CU(ctx->dColor.ensure(144ull * totalT));
+        CU(ctx->dDepth.ensure(144ull * totalT));
+        CU(ctx->dNormal.ensure(normals ? 144ull * totalT : 16));
+    }
+    ctx->oColor = external ? ctx->xColor : ctx->dColor.as<t3d_vertex>();
+    ctx->oDepth = external ? ctx->xDepth : ctx->dDepth.as<t3d_vertex>();
+    ctx->oNormal = external ? ctx->xNormal : ctx->dNormal.as<t3d_vertex>();
     CU(ctx->dTriIds.ensure(4ull * totalT));
     if (ctx->volumesDirty) {
         CU(ctx->dVolumes.ensure(sizeof(VolumeU) * std::max<size_t>(ctx->volumes.size(), 1)));
@@ -646,7 +663,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     // K4
     launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                 ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
-                ctx->dColor.as<float4>(), ctx->dDepth.as<float4>(), normals ? ctx->dNormal.as<float4>() : nullptr, ctx->dTriIds.as<uint32_t>());
+                reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
+                normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>());
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[6], s));
     CU(cudaGetLastError());
@@ -733,9 +751,9 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
             CU(ctx->hColor.resize(nVerts)); CU(ctx->hDepth.resize(nVerts)); CU(ctx->hTriIds.resize(nVerts / 3));
             if (normals) CU(ctx->hNormal.resize(nVerts));
             CU(cudaEventRecord(e0, s));
-            CU(cudaMemcpyAsync(ctx->hColor.p, ctx->dColor.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(ctx->hDepth.p, ctx->dDepth.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
-            if (normals) CU(cudaMemcpyAsync(ctx->hNormal.p, ctx->dNormal.p, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(ctx->hColor.p, ctx->oColor, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(ctx->hDepth.p, ctx->oDepth, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
+            if (normals) CU(cudaMemcpyAsync(ctx->hNormal.p, ctx->oNormal, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(ctx->hTriIds.p, ctx->dTriIds.p, (nVerts / 3) * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaEventRecord(e1, s));
             CU(cudaStreamSynchronize(s));
@@ -746,8 +764,8 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
         out->normal_list = normals ? ctx->hNormal.p : nullptr;
         out->tri_ids = ctx->hTriIds.p;
     } else {
-        out->color_list = ctx->dColor.as<t3d_vertex>(); out->depth_list = ctx->dDepth.as<t3d_vertex>();
-        out->normal_list = normals ? ctx->dNormal.as<t3d_vertex>() : nullptr;
+        out->color_list = ctx->oColor; out->depth_list = ctx->oDepth;
+        out->normal_list = normals ? ctx->oNormal : nullptr;
         out->tri_ids = ctx->dTriIds.as<uint32_t>();
     }
     if (tm) {
@@ -794,6 +812,44 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
         if (R.flags & T3D_DRAW_LIT) CU(cudaMemcpy(light4, ctx->dLight.as<float4>() + slot, n * 16, cudaMemcpyDeviceToHost));
         else memset(light4, 0, n * 16);
     }
+    return T3D_OK;
+}
+
+int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity) {
+    if (!ctx) return T3D_E_INVALID;
+    if (ctx->inFrame && ctx->executed && !ctx->haveResults) return fail(ctx, T3D_E_STATE, "t3d_set_output_target: a frame is in flight");
+    if ((color == nullptr) != (depth == nullptr)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: colour and depth lists go together");
+    if (color && (((uintptr_t)color | (uintptr_t)depth | (uintptr_t)normal) & 15)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: lists must be 16-byte aligned");
+    ctx->xColor = color; ctx->xDepth = depth; ctx->xNormal = color ? normal : nullptr;
+    ctx->xCapacity = color ? vertex_capacity : 0;
+    return T3D_OK;
+}
+
+int t3d_shared_alloc(t3d_ctx* ctx, uint64_t bytes, void** device_ptr, t3d_shared_handle* handle) {
+    if (!ctx || !device_ptr || !handle || bytes == 0) return fail(ctx, T3D_E_INVALID, "t3d_shared_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(t3d_shared_handle), "handle size");
+    CU(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(ctx, e, "cudaIpcGetMemHandle"); }
+    memset(handle, 0, sizeof *handle);
+    memcpy(handle->bytes, &h, sizeof h);
+    ctx->sharedAllocs.push_back(p);
+    *device_ptr = p;
+    return T3D_OK;
+}
+
+int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device_ptr) {
+    if (!ctx || !device_ptr || !handle) return fail(ctx, T3D_E_INVALID, "t3d_shared_open: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->sharedOpened.push_back(p);
+    *device_ptr = p;
     return T3D_OK;
 }
 

@@ -235,6 +235,26 @@ PYBIND11_MODULE(_host, m) {
         .def(py::init<int>(), py::arg("device") = 0)
         .def_readonly("DeviceID", &GeometryDevice::deviceId)
         .def("Stream", [](GeometryDevice& d) { return (uintptr_t)t3d_debug_stream(d.ctx); })
+        .def("SharedAlloc", [](GeometryDevice& d, uint64_t bytes) {
+            void* p = nullptr; t3d_shared_handle h;
+            const int rc = t3d_shared_alloc(d.ctx, bytes, &p, &h);
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+            return py::make_tuple((uintptr_t)p, py::bytes(reinterpret_cast<const char*>(h.bytes), sizeof h.bytes));
+        })
+        .def("SharedOpen", [](GeometryDevice& d, py::bytes handle) {
+            std::string b = handle; t3d_shared_handle h;
+            if (b.size() != sizeof h.bytes) throw std::invalid_argument("SharedOpen: handle must be 64 bytes");
+            memcpy(h.bytes, b.data(), sizeof h.bytes);
+            void* p = nullptr;
+            const int rc = t3d_shared_open(d.ctx, &h, &p);
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+            return (uintptr_t)p;
+        })
+        .def("SetOutputTarget", [](GeometryDevice& d, uintptr_t color, uintptr_t depth, uintptr_t normal, uint64_t capacity) {
+            const int rc = t3d_set_output_target(d.ctx, reinterpret_cast<t3d_vertex*>(color), reinterpret_cast<t3d_vertex*>(depth),
+                                                 reinterpret_cast<t3d_vertex*>(normal), capacity);
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+        })
         .def("SetStageTimings", [](GeometryDevice& d, bool on) { t3d_set_stage_timings(d.ctx, on ? 1 : 0); })
         .def("VertexKernelBytes", [](GeometryDevice& d) { return t3d_debug_vertex_kernel_bytes(d.ctx); })
         .def("FrameBytes", [](GeometryDevice& d) { uint64_t a = 0, b = 0; t3d_debug_frame_bytes(d.ctx, &a, &b); return py::make_tuple(a, b); })

@@ -1,6 +1,14 @@
 """Object-wise multi-GPU: every rank renders the flushes Camera.SetShard assigned to it; the emitted lists
-are gathered to the rank that issues the draws (no cross-GPU merge is needed: each MeshPart is sorted in
-isolation, model.go:602, 989).  torch.distributed is plumbing only (NCCL on GPUs, gloo in CPU tests)."""
+end up on the rank that issues the draws (no cross-GPU merge is needed: each MeshPart is sorted in isolation,
+model.go:602, 989).  Two ways to get them there:
+
+  SharedLists   the issuing rank's lists are mapped into every rank (CUDA IPC) and each rank's emit kernel
+                writes its records straight into its own region over NVLink -- the transfer is the kernel's
+                TMA stores, there is no separate copy; only a small per-flush count vector is all-reduced.
+  gather_lists  the lists stay local and are collected afterwards with NCCL send / recv (also what the gloo
+                CPU tests exercise).
+
+torch.distributed is plumbing only (NCCL on GPUs, gloo in CPU tests)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
@@ -88,3 +96,70 @@ def gather_lists(local: List[torch.Tensor], flush_table: List[Tuple[int, int]], 
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return None, None
+
+
+class SharedLists:
+    """Colour / depth lists of the issuing rank `dst`, one fixed-capacity region per rank, mapped into every rank.
+
+    After construction every rank's GeometryDevice emits into region `rank` (t3d_set_output_target).  `collect`
+    exchanges the per-flush vertex counts and, on `dst`, returns views of the complete lists plus the table
+    global_flush_id -> (first_vertex, vertex_count): region r starts at vertex r * capacity, a rank's flushes
+    sit there in ascending global id.
+    """
+
+    def __init__(self, device, device_index: int, vertex_capacity: int, dst: int = 0, group=None):
+        self.group, self.dst, self.device = group, dst, device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = torch.device("cuda", device_index)
+        cap = torch.tensor([int(vertex_capacity)], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        self.capacity = (int(cap.item()) + 255) // 256 * 256
+        nbytes = self.world * self.capacity * 48
+        payload = [None]
+        if self.rank == dst:
+            self.color_ptr, hc = device.SharedAlloc(nbytes)
+            self.depth_ptr, hd = device.SharedAlloc(nbytes)
+            payload = [(hc, hd)]
+        dist.broadcast_object_list(payload, src=dst, group=group)
+        if self.rank != dst:
+            hc, hd = payload[0]
+            self.color_ptr = device.SharedOpen(hc)
+            self.depth_ptr = device.SharedOpen(hd)
+        off = self.rank * self.capacity * 48
+        device.SetOutputTarget(self.color_ptr + off, self.depth_ptr + off, 0, self.capacity)
+        self.nbytes = nbytes
+        self._meta_host = None
+        self._meta_dev = None
+
+    def collect(self, flush_table: List[Tuple[int, int]], n_flushes_total: int):
+        """Call after the frame has completed on this rank (Camera.RenderScene with DownloadResults = False waits
+        for it).  The all-reduce doubles as the barrier: when it returns on `dst`, every rank's emit has finished."""
+        if self._meta_host is None or self._meta_host.numel() != n_flushes_total:
+            self._meta_host = torch.zeros(n_flushes_total, dtype=torch.int64).pin_memory()
+            self._meta_dev = torch.zeros(n_flushes_total, dtype=torch.int64, device=self.dev)
+        mh = self._meta_host.numpy()
+        mh[:] = 0
+        if flush_table:
+            import numpy as np
+            ft = np.asarray(flush_table, dtype=np.int64)
+            mh[ft[:, 0]] = ((self.rank + 1) << 40) + ft[:, 1]
+        self._meta_dev.copy_(self._meta_host, non_blocking=True)
+        dist.all_reduce(self._meta_dev, op=dist.ReduceOp.SUM, group=self.group)
+        if self.rank != self.dst:
+            return None, None
+        meta = self._meta_dev.cpu().tolist()
+        table: Dict[int, Tuple[int, int]] = {}
+        cursor = [r * self.capacity for r in range(self.world)]
+        for fid, v in enumerate(meta):
+            if v == 0:
+                continue
+            owner, cnt = (v >> 40) - 1, v & ((1 << 40) - 1)
+            table[fid] = (cursor[owner], int(cnt))
+            cursor[owner] += int(cnt)
+        lists = [torch.as_tensor(DeviceArray(self.color_ptr, self.nbytes), device=self.dev),
+                 torch.as_tensor(DeviceArray(self.depth_ptr, self.nbytes), device=self.dev)]
+        return lists, table
+
+    def release(self):
+        self.device.SetOutputTarget(0, 0, 0, 0)
