@@ -93,7 +93,7 @@ struct t3d_ctx {
     bool stageTimings = false, stagesTimed = false;
     FrameConst fc;
     PinVec<DrawRec> hDraws;
-    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked;
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium;
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
     PinVec<float> hBones;
@@ -107,7 +107,7 @@ struct t3d_ctx {
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
     PinVec<uint8_t> hFrame;
     void* hFrameDev = nullptr; size_t frameRestOff = 0, frameBytes = 0, frameLightsOff = 0;
-    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
@@ -205,7 +205,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
-    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hTiles.release();
+    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
@@ -499,7 +499,7 @@ static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, 
 // exclusive tiles and go through k_cull_large + the segmented counting sort; smaller draws are packed whole
 // into tiles of at most TILE_TRIS triangles and TILE_TRIS draws and are culled and sorted by k_tile_packed.
 static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
-    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear();
+    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear(); ctx->hMedium.clear();
     const uint32_t* tb = ctx->hTbase.p;
     TriTile cur; memset(&cur, 0, sizeof cur);
     cudaError_t e = cudaSuccess;
@@ -520,13 +520,15 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
         if (nt > TILE_TRIS) {
             if ((e = close()) != cudaSuccess) return e;
             const uint32_t n = (nt + TILE_TRIS - 1) / TILE_TRIS;
+            const bool medium = nt <= MEDIUM_TRIS;      // one block culls and sorts the whole draw (k_draw_medium)
+            if (medium && (e = ctx->hMedium.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
             for (uint32_t j = 0; j < n; j++) {
                 TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
                 t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws.p[d].sortMode; t.tbase = tb[d];
-                if ((e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
+                if (!medium && (e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
                 if ((e = ctx->hTiles.push(t)) != cudaSuccess) return e;
             }
-            ctx->nHistRows += n + 1;
+            if (!medium) ctx->nHistRows += n + 1;
             continue;
         }
         if (cur.info && (cur.count + nt > TILE_TRIS || cur.info >= TILE_TRIS)) { if ((e = close()) != cudaSuccess) return e; }
@@ -558,6 +560,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     build_tiles(ctx->hVbase.p, nDraws, nTilesV, VERTEX_TILE, ctx->hTileV.p);
     CU(build_tri_tiles(ctx, nDraws));
     const uint32_t nTiles = (uint32_t)ctx->hTiles.n, nLarge = (uint32_t)ctx->hLarge.n, nPacked = (uint32_t)ctx->hPacked.n;
+    const uint32_t nMedium = (uint32_t)ctx->hMedium.n;
 
     const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
 
@@ -575,7 +578,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dHist.ensure(4ull * BIN_COUNT * std::max(ctx->nHistRows, 1u)));
     CU(ctx->dTileSurv.ensure(4ull * std::max(nTiles, 1u)));
     CU(ctx->dTileOut.ensure(4ull * (nTiles + 1)));
-    CU(ctx->dCount.ensure(256));
+    CU(ctx->dCount.ensure(4ull * std::max<uint32_t>((nTiles + SCAN_CHUNK - 1) / SCAN_CHUNK, 64u)));     // per-chunk survivor totals of the tile scan
     const bool external = ctx->xColor != nullptr;
     if (external) {
         if (3ull * totalT > ctx->xCapacity) return fail(ctx, T3D_E_NOMEM, "t3d_frame_execute: the output target is smaller than the frame's worst case (3 vertices per submitted triangle)");
@@ -599,11 +602,12 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     // uniforms up: pack every per-frame array into one pinned block -> one async copy
     {
         struct Seg { const void* src; size_t bytes; size_t off; };
-        Seg segs[9] = {
+        Seg segs[10] = {
             {ctx->hDraws.p, sizeof(DrawRec) * (size_t)nDraws, 0}, {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
-            {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0}};
+            {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0},
+            {ctx->hMedium.p, 4ull * nMedium, 0}};
         size_t total = 0;
         for (Seg& g : segs) { g.off = total; total += (g.bytes + 255) & ~(size_t)255; }
         total = std::max<size_t>(total, 256);
@@ -624,6 +628,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pPacked = reinterpret_cast<uint32_t*>(base + segs[6].off);
         ctx->pLightsIn = reinterpret_cast<t3d_light*>(base + segs[7].off);
         ctx->pBones = reinterpret_cast<float*>(base + segs[8].off);
+        ctx->pMedium = reinterpret_cast<uint32_t*>(base + segs[9].off);
         ctx->h2dBytes = 0;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
     }
@@ -651,18 +656,30 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                       ctx->dTdepth.as<uint32_t>(), stats);
     launch_tile_packed(s, pdl, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
                        ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats);
-    ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0);
+    launch_draw_medium(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pMedium, nMedium, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
+                       ctx->dSorted.as<uint32_t>(), stats);
+    ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0) + (nMedium ? 1 : 0);
     CU(mark(4));
     // K3: where every tile starts in the lists (needs only the survivor counts), then the segmented 512-bin
     // counting sort of the large draws
-    launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
-    launch_bin_hist(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>());
-    launch_scatter(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
-    ctx->launches += (nLarge ? 2 : 0) + 1;
+    const bool scanRides = nLarge && nTiles <= SCAN_CHUNK;     // one chunk: the scan rides along as k_bin_hist's extra block
+    if (nLarge && !scanRides) {
+        launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+        ctx->launches += 1;
+    }
+    if (nLarge) {       // the tile scan rides along as k_bin_hist's extra block
+        launch_bin_hist(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, scanRides ? nTiles : 0xFFFFFFFFu, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(),
+                        ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+        launch_scatter(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
+        ctx->launches += 2;
+    } else {
+        launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+        ctx->launches += 1;
+    }
     CU(mark(5));
     // K4
     launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
-                ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+                ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                 reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
                 normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>());
     ctx->launches += nTiles ? 1 : 0;
@@ -701,9 +718,10 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     uint64_t nVerts = 0;
     if (nDraws && totalT) {
         CU(ctx->hStats.resize(nDraws));
-        CU(ctx->hCount.resize(1));
+        const uint32_t nChunks = ((uint32_t)ctx->hTiles.n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        CU(ctx->hCount.resize(std::max(nChunks, 1u)));
         CU(cudaMemcpyAsync(ctx->hStats.p, ctx->dStats.p, sizeof(DrawStat) * nDraws, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(ctx->hCount.p, ctx->dCount.p, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(ctx->hCount.p, ctx->dCount.p, 4ull * std::max(nChunks, 1u), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         ctx->d2hBytes += sizeof(DrawStat) * (uint64_t)nDraws + 4;
         uint64_t acc = 0;
@@ -717,7 +735,9 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
             else { r.min_depth = FLT_MAX; r.max_depth = -FLT_MAX; }
             acc += st.survivors;
         }
-        if (acc != ctx->hCount.p[0]) return fail(ctx, T3D_E_CUDA, "internal: survivor count mismatch between cull and sort");
+        uint64_t scanned = 0;
+        for (uint32_t c = 0; c < nChunks; c++) scanned += ctx->hCount.p[c];
+        if (acc != scanned) return fail(ctx, T3D_E_CUDA, "internal: survivor count mismatch between cull and tile scan");
         nVerts = 3 * acc;
     } else {
         CU(cudaStreamSynchronize(s));

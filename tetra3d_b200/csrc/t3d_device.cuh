@@ -118,7 +118,8 @@ struct DrawStat {
 // Triangle tiles: the unit of work of the cull / sort / emit kernels.  A tile is a run of at most
 // TILE_TRIS consecutive slots of the frame's triangle arena that never cuts a small draw: a draw with
 // more than TILE_TRIS triangles owns ceil(nt / TILE_TRIS) exclusive tiles ("large"), smaller draws are
-// packed whole, several to a tile ("packed").
+// packed whole, several to a tile ("packed").  Draws of up to MEDIUM_TRIS triangles keep their large tiles
+// for the tile scan and the emit but are culled and sorted by a single block (k_draw_medium).
 struct __align__(16) TriTile {
     uint32_t start;             // first triangle slot
     uint32_t count;             // slots in the tile (<= TILE_TRIS)
@@ -132,6 +133,8 @@ struct __align__(16) TriTile {
     uint32_t tbase;             // first arena slot of the draw
 };
 static const uint32_t TILE_TRIS = 1024;
+static const uint32_t SCAN_CHUNK = 4096;        // tiles per block of the tile scan (t3d_sort.cu)
+static const uint32_t MEDIUM_TRIS = 8192;       // draws of (TILE_TRIS, MEDIUM_TRIS] triangles are culled and sorted by one block
 static const uint32_t TILE_LARGE = 0x80000000u;
 
 static const uint32_t KEY_CULLED = 0xFFFFFFFFu;

@@ -30,18 +30,20 @@ void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const Tri
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
                         const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats);
+void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* mediumList, uint32_t nMedium,
+                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats);
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
-                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip, const float2* clipXY,
+                 const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds);
 static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex block (tileFirst granularity)
 
 // t3d_sort.cu -- segmented 512-bin counting sort for draws that span several tiles
-void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
-                     DrawStat* stats, uint32_t* tdepth, uint32_t* hist);
+void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge, uint32_t nTiles,
+                     DrawStat* stats, uint32_t* tdepth, uint32_t* hist, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum);
 void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                     const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted);
 void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
-                      uint32_t* tileOut, uint32_t* dCount);
+                      uint32_t* tileOut, uint32_t* chunkSum);
 
 }  // namespace t3d

@@ -536,7 +536,10 @@ static const int TILE_ROUNDS = TILE_TRIS / TILE_THREADS;        // triangles per
 // Large draws: one exclusive tile per block, TILE_ROUNDS triangles per thread, all loads of a thread issued
 // before the first use.  Depth bits (or KEY_CULLED) go to tdepth; min / max / survivors are reduced per
 // block and merged into DrawStat with three atomics.
-__global__ void __launch_bounds__(TILE_THREADS)
+#ifndef T3D_CULL_MINBLOCKS
+#define T3D_CULL_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, T3D_CULL_MINBLOCKS)
 k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
              const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float4* __restrict__ wpos,
              uint32_t* __restrict__ tdepth, DrawStat* __restrict__ stats) {
@@ -795,6 +798,133 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
     if (threadIdx.x == 0) tileSurv[tileId] = nSurv;
 }
 
+// Medium draws (more than one tile, at most MEDIUM_TRIS triangles): one block owns the whole draw, so the
+// depth keys never leave shared memory -- cull every triangle, reduce min / max in the block, bin, count the
+// 512 bins, then walk the draw's tiles in arena order ranking each survivor inside its bin (the same
+// warp-contiguous ranking as smem_radix_pass) and store sorted[tbase + bin start + rank] = arena slot.
+// No depth array, histogram rows or atomics in global memory.  The draw's tiles stay in the tile table as
+// "large" tiles for the tile scan and the emit.
+__global__ void __launch_bounds__(TILE_THREADS)
+k_draw_medium(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ mediumList,
+              const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float4* __restrict__ wpos,
+              uint32_t* __restrict__ sorted, DrawStat* __restrict__ stats) {
+    __shared__ uint32_t sKey[MEDIUM_TRIS];              // depth bits, then bin ranks (KEY_CULLED = dropped)
+    __shared__ uint32_t sHist[BIN_COUNT];               // bin counts, then the running start of each bin
+    __shared__ __align__(16) uint16_t sCnt[8 * BIN_COUNT];
+    __shared__ uint32_t sRed[3][TILE_THREADS / 32];
+    __shared__ uint32_t sWarp[8];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TriTile T = tiles[__ldg(&mediumList[blockIdx.x])];        // the draw's first tile
+    const uint32_t d = T.dFirst;
+    const DrawRec& R = draws[d];
+    const uint32_t flags = R.flags;
+    const bool skinned = flags & T3D_DRAW_SKINNED;
+    const bool backface = (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING);
+    const uint32_t ts = R.tstride, nt = R.nt, tb = R.tbase;
+    const uint32_t vb = R.vbase - R.a0;
+    const uint32_t* ip = R.idx + R.t0;
+    const float* cp = R.ctr + R.t0;
+    const float icx = R.invCam[0], icy = R.invCam[1], icz = R.invCam[2];
+    sHist[threadIdx.x] = 0; sHist[threadIdx.x + TILE_THREADS] = 0;
+    pdl_wait();
+    pdl_launch();
+
+    // ---- cull + depth ----
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u, cnt = 0u;
+    for (uint32_t i = threadIdx.x; i < nt; i += TILE_THREADS) {
+        const uint32_t i0 = __ldg(ip + i), i1 = __ldg(ip + ts + i), i2 = __ldg(ip + 2 * (size_t)ts + i);
+        const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
+        bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+        float depth = 0.0f;
+        if (keep) {                                                     // model.go:933-955
+            if (skinned) depth = skinned_depth(__ldg(&wpos[vb + i0]), __ldg(&wpos[vb + i1]), __ldg(&wpos[vb + i2]), fc.camPos);
+            else { const float dx = icx - __ldg(cp + i), dy = icy - __ldg(cp + ts + i), dz = icz - __ldg(cp + 2 * (size_t)ts + i); depth = dx * dx + dy * dy + dz * dz; }
+            if (isnan(depth) || isinf(depth)) keep = false;            // model.go:957-960
+        }
+        const uint32_t bits = __float_as_uint(depth);
+        sKey[i] = keep ? bits : KEY_CULLED;
+        if (keep) { mn = min(mn, bits); mx = max(mx, bits); cnt++; }
+    }
+    mn = __reduce_min_sync(full, mn); mx = __reduce_max_sync(full, mx); cnt = __reduce_add_sync(full, cnt);
+    if (lane == 0) { sRed[0][warp] = mn; sRed[1][warp] = mx; sRed[2][warp] = cnt; }
+    __syncthreads();
+    mn = 0xFFFFFFFFu; mx = 0u; cnt = 0u;
+#pragma unroll
+    for (int w = 0; w < TILE_THREADS / 32; w++) { mn = min(mn, sRed[0][w]); mx = max(mx, sRed[1][w]); cnt += sRed[2][w]; }
+    if (threadIdx.x == 0) {
+        DrawStat st; st.minBits = cnt ? mn : 0x7F7FFFFFu; st.maxBits = cnt ? mx : 0u; st.survivors = cnt; st.done = 0;
+        stats[d] = st;
+    }
+    if (cnt == 0) return;
+    mn = min(mn, 0x7F7FFFFFu);
+
+    // ---- bin rank + counts ----
+    const uint32_t sortMode = R.sortMode;
+    for (uint32_t i = threadIdx.x; i < nt; i += TILE_THREADS) {
+        const uint32_t bits = sKey[i];
+        if (bits != KEY_CULLED) {
+            const uint32_t key = bin_key(bits, mn, mx, sortMode);
+            sKey[i] = key;
+            atomicAdd(&sHist[key], 1u);
+        }
+    }
+    __syncthreads();
+    {   // counts -> start of every bin in the draw's sorted run (thread owns bins 2t, 2t+1)
+        const uint32_t c0 = sHist[2 * threadIdx.x], c1 = sHist[2 * threadIdx.x + 1];
+        const uint32_t base = block_exclusive_scan_256(c0 + c1, sWarp, nullptr);
+        sHist[2 * threadIdx.x] = base; sHist[2 * threadIdx.x + 1] = base + c0;
+    }
+    __syncthreads();
+
+    // ---- stable rank inside the bin, tile by tile in arena order ----
+    for (uint32_t t0 = 0; t0 < nt; t0 += TILE_TRIS) {
+        {
+            uint4* z = reinterpret_cast<uint4*>(sCnt);
+            z[threadIdx.x] = make_uint4(0, 0, 0, 0); z[threadIdx.x + TILE_THREADS] = make_uint4(0, 0, 0, 0);
+            static_assert(sizeof(sCnt) == 2 * TILE_THREADS * sizeof(uint4), "two 128-bit stores per thread clear the counts");
+        }
+        __syncthreads();
+        uint32_t key[TILE_ROUNDS], rank[TILE_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < TILE_ROUNDS; r++) {
+            const uint32_t i = t0 + warp * (TILE_ROUNDS * 32) + r * 32 + lane;
+            key[r] = (i < nt) ? sKey[i] : KEY_CULLED;
+            const unsigned peers = __match_any_sync(full, key[r]);
+            const uint32_t inGroup = __popc(peers & ((1u << lane) - 1u));
+            uint32_t before = 0;
+            if (key[r] != KEY_CULLED && inGroup == 0) {
+                before = sCnt[warp * BIN_COUNT + key[r]];
+                sCnt[warp * BIN_COUNT + key[r]] = (uint16_t)(before + __popc(peers));
+            }
+            rank[r] = __shfl_sync(full, before, __ffs(peers) - 1) + inGroup;
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t tot;
+        {   // exclusive prefix over the warps (two bins per thread, packed), tile totals kept for the bin starts
+            uint32_t* words = reinterpret_cast<uint32_t*>(sCnt);
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t* p = words + w * (BIN_COUNT / 2) + threadIdx.x;
+                const uint32_t c = *p;
+                *p = run;
+                run += c;
+            }
+            tot = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < TILE_ROUNDS; r++) {
+            if (key[r] != KEY_CULLED)
+                sorted[tb + sHist[key[r]] + sCnt[warp * BIN_COUNT + key[r]] + rank[r]] = tb + t0 + warp * (TILE_ROUNDS * 32) + r * 32 + lane;
+        }
+        __syncthreads();
+        sHist[2 * threadIdx.x] += tot & 0xFFFFu; sHist[2 * threadIdx.x + 1] += tot >> 16;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4: emit (camera.go:1646-1820)
 // ------------------------------------------------------------------------------------------------
@@ -818,8 +948,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool NORMALS>
 __global__ void __launch_bounds__(EMIT_TRIS)
 k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
-       const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const __grid_constant__ FrameConst fc,
-       const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
+       const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const uint32_t* __restrict__ chunkSum,
+       const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
        const float* __restrict__ unbill, const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
        uint32_t* __restrict__ triIds) {
@@ -839,7 +969,8 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
     if (k0 >= nSurv) return;
     const uint32_t nTri = min((uint32_t)EMIT_TRIS, nSurv - k0);
     const TriTile T = tiles[tileId];
-    const uint32_t outTri0 = __ldg(&tileOut[tileId]) + k0;
+    uint32_t outTri0 = __ldg(&tileOut[tileId]) + k0;
+    for (uint32_t c = 0; c < tileId / SCAN_CHUNK; c++) outTri0 += __ldg(&chunkSum[c]);     // earlier scan chunks (t3d_sort.cu)
 
     if (threadIdx.x < nTri) {
         const uint32_t val = __ldg(&sorted[T.start + k0 + threadIdx.x]);
@@ -995,18 +1126,24 @@ void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const ui
     launch_kernel(k_tile_packed, nPacked, TILE_THREADS, 0, s, pdl, draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
 }
 
+void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* mediumList, uint32_t nMedium,
+                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats) {
+    if (!nMedium) return;
+    launch_kernel(k_draw_medium, nMedium, TILE_THREADS, 0, s, pdl, draws, tiles, mediumList, fc, clip, wpos, sorted, stats);
+}
+
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
-                 const uint32_t* tileSurv, const uint32_t* tileOut, const FrameConst& fc, const float4* clip, const float2* clipXY,
+                 const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds) {
     if (!nTiles) return;
     const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
     if (normalList)
         launch_kernel(k_emit<true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
     else
         launch_kernel(k_emit<false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
 }
 
 }  // namespace t3d

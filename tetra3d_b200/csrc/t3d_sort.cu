@@ -23,13 +23,82 @@ static const int SORT_THREADS = 256;
 static const int SORT_ROUNDS = TILE_TRIS / SORT_THREADS;
 static const int BINS_PER_THREAD = BIN_COUNT / SORT_THREADS;
 
+// One block.  Large tile j of a draw holds survivors [j * TILE_TRIS, ...) of the draw's sorted run; packed
+// tiles wrote their own counts.  Thread t owns the contiguous run of tiles [t * per, (t + 1) * per): one pass
+// to count, a block scan of the 1024 run totals, one pass to write the prefixes.
+__device__ __forceinline__ uint32_t tile_survivors(const TriTile* __restrict__ tiles, const DrawStat* __restrict__ stats,
+                                                   const uint32_t* __restrict__ tileSurv, uint32_t t) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(tiles + t));       // start, count, dFirst, info
+    if (a.w & TILE_LARGE) {
+        const uint32_t surv = stats[a.z].survivors, off = (a.w & ~TILE_LARGE) * TILE_TRIS;
+        return surv > off ? min(surv - off, TILE_TRIS) : 0u;
+    }
+    return tileSurv[t];
+}
+
+// The tile scan works in chunks of SCAN_CHUNK tiles: tileOut[t] is the exclusive prefix of the survivor counts
+// inside t's chunk and chunkSum[c] the chunk's total, so the chunks are independent blocks and the emit adds
+// the (few) earlier chunk totals itself.  One block of NT threads per chunk: thread t owns a contiguous run
+// of tiles -- one pass to count, a block scan of the run totals, one pass to write the prefixes.
+template <int NT>
+__device__ __forceinline__ void tile_scan_chunk(const TriTile* __restrict__ tiles, uint32_t nTiles, uint32_t chunk,
+                                                const DrawStat* __restrict__ stats, uint32_t* __restrict__ tileSurv,
+                                                uint32_t* __restrict__ tileOut, uint32_t* __restrict__ chunkSum, uint32_t* sWarp /*[32]*/) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+    const uint32_t cBegin = chunk * SCAN_CHUNK, cEnd = min(cBegin + SCAN_CHUNK, nTiles);
+    const uint32_t per = (cEnd - cBegin + NT - 1) / NT;
+    const uint32_t t0 = min(cBegin + threadIdx.x * per, cEnd), t1 = min(t0 + per, cEnd);
+    uint32_t sum = 0;
+    for (uint32_t t = t0; t < t1; t++) sum += tile_survivors(tiles, stats, tileSurv, t);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < NW ? sWarp[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, wi, o); if (lane >= o) wi += n; }
+        if (lane < NW) sWarp[lane] = wi - w;
+        if (lane == 31) chunkSum[chunk] = wi;
+    }
+    __syncthreads();
+    uint32_t run = sWarp[warp] + inc - sum;
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t c = tile_survivors(tiles, stats, tileSurv, t);
+        tileOut[t] = run;
+        tileSurv[t] = c;
+        run += c;
+    }
+}
+
+// Stand-alone tile scan, one block per chunk (frames whose scan does not ride along in k_bin_hist's extra block).
+__global__ void __launch_bounds__(1024)
+k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* __restrict__ stats,
+            uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ chunkSum) {
+    __shared__ uint32_t sWarp[32];
+    pdl_wait();
+    pdl_launch();
+    tile_scan_chunk<1024>(tiles, nTiles, blockIdx.x, stats, tileSurv, tileOut, chunkSum, sWarp);
+}
+
 // Histogram rows: tile j of a large draw owns row T.row0 + j; row T.row0 + nTilesOfDraw receives the bin bases.
 __global__ void __launch_bounds__(SORT_THREADS)
-k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
-           DrawStat* __restrict__ stats, uint32_t* __restrict__ tdepth, uint32_t* __restrict__ hist) {
+k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList, uint32_t nLarge, uint32_t nTiles,
+           DrawStat* __restrict__ stats, uint32_t* __restrict__ tdepth, uint32_t* __restrict__ hist,
+           uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ chunkSum) {
     __shared__ uint32_t sHist[BIN_COUNT];
-    __shared__ uint32_t sWarp[8];
+    __shared__ uint32_t sWarp[32];
     __shared__ uint32_t sLast;
+    if (blockIdx.x == nLarge) {     // the extra block (launched only when nTiles is valid): where every tile starts in the lists (needs only the survivor counts)
+        pdl_wait();
+        pdl_launch();
+        tile_scan_chunk<SORT_THREADS>(tiles, nTiles, 0, stats, tileSurv, tileOut, chunkSum, sWarp);      // nTiles <= SCAN_CHUNK
+        return;
+    }
     const TriTile T = tiles[__ldg(&largeList[blockIdx.x])];
     const uint32_t d = T.dFirst;
     const uint32_t j = T.info & ~TILE_LARGE;
@@ -149,58 +218,10 @@ k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeL
     }
 }
 
-// One block.  Large tile j of a draw holds survivors [j * TILE_TRIS, ...) of the draw's sorted run; packed
-// tiles wrote their own counts.  Thread t owns the contiguous run of tiles [t * per, (t + 1) * per): one pass
-// to count, a block scan of the 1024 run totals, one pass to write the prefixes.
-__device__ __forceinline__ uint32_t tile_survivors(const TriTile* __restrict__ tiles, const DrawStat* __restrict__ stats,
-                                                   const uint32_t* __restrict__ tileSurv, uint32_t t) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(tiles + t));       // start, count, dFirst, info
-    if (a.w & TILE_LARGE) {
-        const uint32_t surv = stats[a.z].survivors, off = (a.w & ~TILE_LARGE) * TILE_TRIS;
-        return surv > off ? min(surv - off, TILE_TRIS) : 0u;
-    }
-    return tileSurv[t];
-}
-
-__global__ void __launch_bounds__(1024)
-k_tile_scan(const TriTile* __restrict__ tiles, uint32_t nTiles, const DrawStat* __restrict__ stats,
-            uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ dCount) {
-    __shared__ uint32_t sWarp[32];
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t per = (nTiles + 1023u) / 1024u;
-    const uint32_t t0 = min(threadIdx.x * per, nTiles), t1 = min(t0 + per, nTiles);
-    pdl_wait();
-    pdl_launch();
-    uint32_t sum = 0;
-    for (uint32_t t = t0; t < t1; t++) sum += tile_survivors(tiles, stats, tileSurv, t);
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, inc, o); if (lane >= o) inc += n; }
-    if (lane == 31) sWarp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = sWarp[lane];
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(full, wi, o); if (lane >= o) wi += n; }
-        sWarp[lane] = wi - w;
-        if (lane == 31) { tileOut[nTiles] = wi; *dCount = wi; }
-    }
-    __syncthreads();
-    uint32_t run = sWarp[warp] + inc - sum;
-    for (uint32_t t = t0; t < t1; t++) {
-        const uint32_t c = tile_survivors(tiles, stats, tileSurv, t);
-        tileOut[t] = run;
-        tileSurv[t] = c;
-        run += c;
-    }
-}
-
-void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
-                     DrawStat* stats, uint32_t* tdepth, uint32_t* hist) {
+void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge, uint32_t nTiles,
+                     DrawStat* stats, uint32_t* tdepth, uint32_t* hist, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum) {
     if (!nLarge) return;
-    launch_kernel(k_bin_hist, nLarge, SORT_THREADS, 0, s, pdl, tiles, largeList, stats, tdepth, hist);
+    launch_kernel(k_bin_hist, nLarge + (nTiles != 0xFFFFFFFFu ? 1 : 0), SORT_THREADS, 0, s, pdl, tiles, largeList, nLarge, nTiles, stats, tdepth, hist, tileSurv, tileOut, chunkSum);
 }
 
 void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
@@ -210,8 +231,8 @@ void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32
 }
 
 void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
-                      uint32_t* tileOut, uint32_t* dCount) {
-    launch_kernel(k_tile_scan, 1, 1024, 0, s, pdl, tiles, nTiles, stats, tileSurv, tileOut, dCount);
+                      uint32_t* tileOut, uint32_t* chunkSum) {
+    launch_kernel(k_tile_scan, (nTiles + SCAN_CHUNK - 1) / SCAN_CHUNK, 1024, 0, s, pdl, tiles, nTiles, stats, tileSurv, tileOut, chunkSum);
 }
 
 }  // namespace t3d
