@@ -92,7 +92,10 @@ struct t3d_ctx {
     bool inFrame = false, executed = false, haveResults = false;
     bool stageTimings = false, stagesTimed = false;
     FrameConst fc;
-    PinVec<DrawRec> hDraws;
+    PinVec<DrawRec> hDraws;             // full records, host side only (the device rebuilds them from hSlim + hTmpl)
+    PinVec<DrawSlim> hSlim;
+    PinVec<DrawRec> hTmpl;
+    PinVec<float> hRot;
     PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium;
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
@@ -106,7 +109,8 @@ struct t3d_ctx {
     // device arenas
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
     PinVec<uint8_t> hFrame;
-    void* hFrameDev = nullptr; size_t frameRestOff = 0, frameBytes = 0, frameLightsOff = 0;
+    void* hFrameDev = nullptr; void* pDevRest = nullptr;
+    size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0;
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
@@ -205,6 +209,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
+    ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
     ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
@@ -387,6 +392,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
         memcpy(fc.fogColor, world->fog_color, 12);
         memcpy(fc.fogRange, world->fog_range, 8);
     }
+    ctx->hSlim.clear(); ctx->hTmpl.clear(); ctx->hRot.clear();
     ctx->hDraws.clear(); ctx->hVbase.clear(); ctx->hTbase.clear(); ctx->hLights.clear(); ctx->hBones.clear();
     ctx->lightLists.clear();
     ctx->lightLists.push_back(LightList{0, 0});     // list 0: empty
@@ -478,6 +484,45 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         ctx->hVbase.p[ctx->hDraws.n] = ctx->vAcc;
         ctx->hTbase.p[ctx->hDraws.n] = ctx->tAcc;
         ctx->vAcc += pi.nv; ctx->tAcc += R.nt;
+        {   // what goes over PCIe: a 112-byte placement record, plus a template whenever anything else changes
+            // reuse one of the most recent templates when everything but the placement matches (instances of one
+            // MeshPart; models cycling through a handful of LightGroups or MeshParts)
+            uint32_t tmplIndex = 0xFFFFFFFFu;
+            const size_t nT = ctx->hTmpl.n;
+            for (size_t back = 1; back <= 16 && back <= nT; back++) {
+                const DrawRec& T = ctx->hTmpl.p[nT - back];
+                if (T.pos == R.pos && T.idx == R.idx && T.a0 == R.a0 && T.nv == R.nv && T.t0 == R.t0 && T.nt == R.nt && T.flags == R.flags &&
+                    T.lightIn == R.lightIn && T.lightCount == R.lightCount && T.sortMode == R.sortMode && T.lightingMode == R.lightingMode &&
+                    T.lvMode == R.lvMode && T.srcW == R.srcW && T.srcH == R.srcH && T.col == R.col && T.uv == R.uv && T.nrm == R.nrm) {
+                    tmplIndex = (uint32_t)(nT - back);
+                    break;
+                }
+            }
+            if (tmplIndex == 0xFFFFFFFFu) {
+                DrawRec T = R;      // every mesh-, material- and light-list-derived field; the per-draw ones are patched on the device
+                T.vbase = T.tbase = T.boneOffset = T.lightU = 0;
+                memset(T.transform, 0, sizeof T.transform); memset(T.worldRot, 0, sizeof T.worldRot); memset(T.color, 0, sizeof T.color);
+                CU(ctx->hTmpl.push(T));
+                tmplIndex = (uint32_t)ctx->hTmpl.n - 1;
+            }
+            DrawSlim S;
+            memset(&S, 0, sizeof S);
+            S.tmpl = tmplIndex; S.vbase = R.vbase; S.tbase = R.tbase; S.boneOffset = R.boneOffset; S.lightU = R.lightU;
+            memcpy(S.transform, R.transform, 64); memcpy(S.color, R.color, 16);
+            // the world rotation only feeds a directional light's workingModelRotation of an unskinned, lit draw (light.go:326-330)
+            S.rot = NO_ROTATION;
+            if ((flags & T3D_DRAW_LIT) && !(flags & T3D_DRAW_SKINNED) && ll.count) {
+                bool sun = false;
+                for (uint32_t k = 0; k < ll.count && !sun; k++) sun = ctx->hLights.p[ll.off + k].type == T3D_LIGHT_DIRECTIONAL;
+                if (sun) {
+                    S.rot = (uint32_t)(ctx->hRot.n / 16);
+                    CU(ctx->hRot.reserve(ctx->hRot.n + 16));
+                    memcpy(ctx->hRot.p + ctx->hRot.n, R.worldRot, 64);
+                    ctx->hRot.n += 16;
+                }
+            }
+            CU(ctx->hSlim.push(S));
+        }
         ctx->hDraws.p[ctx->hDraws.n++] = R;
         ctx->drawTotalTris.push_back(R.nt);
         ctx->drawContinue.push_back((flags & T3D_DRAW_CONTINUE_FLUSH) ? 1 : 0);
@@ -601,35 +646,44 @@ int t3d_frame_execute(t3d_ctx* ctx) {
 
     // uniforms up: pack every per-frame array into one pinned block -> one async copy
     {
+        // host block: [DrawSlim[D] | templates | rotations | tables ... ]; device block: [DrawRec[D] | tables ...]
         struct Seg { const void* src; size_t bytes; size_t off; };
-        Seg segs[10] = {
-            {ctx->hDraws.p, sizeof(DrawRec) * (size_t)nDraws, 0}, {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
+        Seg head[3] = {{ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
+                       {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
+        Seg segs[9] = {
+            {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0},
             {ctx->hMedium.p, 4ull * nMedium, 0}};
-        size_t total = 0;
-        for (Seg& g : segs) { g.off = total; total += (g.bytes + 255) & ~(size_t)255; }
-        total = std::max<size_t>(total, 256);
+        size_t headBytes = 0, restBytes = 0;
+        for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
+        for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
+        const size_t devDrawBytes = (sizeof(DrawRec) * (size_t)nDraws + 255) & ~(size_t)255;
         ctx->hFrame.mapped = true;
-        CU(ctx->hFrame.resize(total));
-        CU(ctx->dFrame.ensure(total));
-        for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
+        CU(ctx->hFrame.resize(headBytes + restBytes));
+        CU(ctx->dFrame.ensure(devDrawBytes + restBytes));
+        for (Seg& g : head) if (g.bytes) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
+        for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + headBytes + g.off, g.src, g.bytes);
         // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
         CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
-        ctx->frameRestOff = segs[1].off; ctx->frameBytes = total; ctx->frameLightsOff = segs[7].off;
+        ctx->frameHeadBytes = headBytes; ctx->frameRestBytes = restBytes; ctx->frameTmplOff = head[1].off; ctx->frameRotOff = head[2].off;
+        ctx->frameLightsOff = headBytes + segs[6].off;
         uint8_t* base = ctx->dFrame.as<uint8_t>();
-        ctx->pDraws = reinterpret_cast<DrawRec*>(base + segs[0].off);
-        ctx->pVbase = reinterpret_cast<uint32_t*>(base + segs[1].off);
-        ctx->pTbase = reinterpret_cast<uint32_t*>(base + segs[2].off);
-        ctx->pTileV = reinterpret_cast<uint32_t*>(base + segs[3].off);
-        ctx->pTiles = reinterpret_cast<TriTile*>(base + segs[4].off);
-        ctx->pLarge = reinterpret_cast<uint32_t*>(base + segs[5].off);
-        ctx->pPacked = reinterpret_cast<uint32_t*>(base + segs[6].off);
-        ctx->pLightsIn = reinterpret_cast<t3d_light*>(base + segs[7].off);
-        ctx->pBones = reinterpret_cast<float*>(base + segs[8].off);
-        ctx->pMedium = reinterpret_cast<uint32_t*>(base + segs[9].off);
+        uint8_t* rest = base + devDrawBytes;
+        ctx->pDevRest = rest;
+        ctx->pDraws = reinterpret_cast<DrawRec*>(base);
+        ctx->pVbase = reinterpret_cast<uint32_t*>(rest + segs[0].off);
+        ctx->pTbase = reinterpret_cast<uint32_t*>(rest + segs[1].off);
+        ctx->pTileV = reinterpret_cast<uint32_t*>(rest + segs[2].off);
+        ctx->pTiles = reinterpret_cast<TriTile*>(rest + segs[3].off);
+        ctx->pLarge = reinterpret_cast<uint32_t*>(rest + segs[4].off);
+        ctx->pPacked = reinterpret_cast<uint32_t*>(rest + segs[5].off);
+        ctx->pLightsIn = reinterpret_cast<t3d_light*>(rest + segs[6].off);
+        ctx->pBones = reinterpret_cast<float*>(rest + segs[7].off);
+        ctx->pMedium = reinterpret_cast<uint32_t*>(rest + segs[8].off);
         ctx->h2dBytes = 0;
+        for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
     }
     // Stage timings need an event between kernels, which also serialises them; the default path records only
@@ -642,9 +696,25 @@ int t3d_frame_execute(t3d_ctx* ctx) {
 
     DrawStat* stats = ctx->dStats.as<DrawStat>();
     // K0 (fetches the uniforms over PCIe itself) + K1
-    launch_prep_draws(s, pdl, ctx->hFrameDev, ctx->dFrame.p, nDraws, ctx->frameRestOff, ctx->frameBytes, ctx->fc,
-                      reinterpret_cast<const t3d_light*>(static_cast<const uint8_t*>(ctx->hFrameDev) + ctx->frameLightsOff),
-                      (uint32_t)ctx->hLights.n, ctx->dLightsU.as<LightU>(), stats);
+    {
+        // template / rotation index windows of the first blocks of k_prep_draws (64 draws each)
+        uint32_t win[PREP_WINDOW_BLOCKS][4];
+        for (int b = 0; b < PREP_WINDOW_BLOCKS; b++) {
+            uint32_t tmin = 0xFFFFFFFFu, tmax = 0, rmin = NO_ROTATION, rmax = 0;
+            const uint32_t lo = (uint32_t)b * PREP_WINDOW_DRAWS, hi = std::min(lo + PREP_WINDOW_DRAWS, nDraws);
+            for (uint32_t d = lo; d < hi; d++) {
+                const DrawSlim& S = ctx->hSlim.p[d];
+                tmin = std::min(tmin, S.tmpl); tmax = std::max(tmax, S.tmpl);
+                if (S.rot != NO_ROTATION) { rmin = std::min(rmin, S.rot); rmax = std::max(rmax, S.rot); }
+            }
+            win[b][0] = lo < hi ? tmin : 0; win[b][1] = lo < hi ? tmax - tmin + 1 : 0;
+            win[b][2] = rmin; win[b][3] = rmin != NO_ROTATION ? rmax - rmin + 1 : 0;
+        }
+        const uint8_t* hf = static_cast<const uint8_t*>(ctx->hFrameDev);
+        launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
+                          reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
+                          (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win);
+    }
     CU(mark(2));
     launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),

@@ -101,6 +101,22 @@ struct __align__(16) DrawRec {
     float pad2;
 };
 
+// What crosses PCIe per draw.  Consecutive draws that differ only in placement (instances of one MeshPart:
+// particles, crowds, instanced scenery) share one DrawRec *template*; k_prep_draws rebuilds the full record on
+// the device from the template and this 112-byte record (a quarter of the bytes of a DrawRec).
+struct __align__(16) DrawSlim {
+    uint32_t tmpl;              // template index (one of the 16 most recent templates at submit time, or a new one)
+    uint32_t vbase, tbase;      // arena slots
+    uint32_t boneOffset;
+    uint32_t lightU;            // first LightU slot of this draw
+    uint32_t rot;               // index of the draw's world rotation in the rotation array, or NO_ROTATION
+    uint32_t pad[2];
+    float transform[16];
+    float color[4];
+};
+static const uint32_t NO_ROTATION = 0xFFFFFFFFu;
+static_assert(sizeof(DrawSlim) == 112, "DrawSlim is staged as seven uint4");
+
 static_assert(offsetof(DrawRec, transform) % 16 == 0 && offsetof(DrawRec, worldRot) % 16 == 0 &&
               offsetof(DrawRec, color) % 16 == 0 && offsetof(DrawRec, mvp) % 16 == 0 &&
               offsetof(DrawRec, unbill) % 16 == 0 && offsetof(DrawRec, nrmRot) % 16 == 0 &&

@@ -20,8 +20,10 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 }
 
 // t3d_kernels.cu
-void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* devFrame, uint32_t nDraws, size_t restOff, size_t totalBytes,
-                       const FrameConst& fc, const t3d_light* lightsHost, uint32_t nLightsIn, LightU* lightsU, DrawStat* stats);
+void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const void* hostTmpl, const void* hostRot, const void* hostRest,
+                       const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
+                       const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4]);
+static const int PREP_WINDOW_BLOCKS = 16, PREP_WINDOW_DRAWS = 64;     // k_prep_draws: blocks whose template windows travel as kernel parameters
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);

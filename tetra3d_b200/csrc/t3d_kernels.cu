@@ -17,6 +17,7 @@
 #include "t3d_internal.h"
 #include "../../include/t3dgeo.h"
 #include <algorithm>
+#include <cstring>
 
 namespace t3d {
 
@@ -39,63 +40,141 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ------------------------------------------------------------------------------------------------
 // K0: per-draw uniforms
 // ------------------------------------------------------------------------------------------------
-// The frame's uniforms sit in one pinned host block (t3d_api.cu packs it: DrawRec[nDraws] first, then the
-// tables, light lists and bone matrices).  This kernel pulls the block over PCIe itself (UVA loads from the
-// mapped host allocation, all of a thread's loads in flight at once) instead of waiting for a DMA copy:
-// blocks < nPrepBlocks stage PREP_DRAWS records in shared memory, derive the per-draw uniforms there and
-// write the finished records to the device copy; the remaining blocks copy the rest of the block verbatim.
+// The frame's uniforms sit in one pinned host block (t3d_api.cu packs it: DrawSlim[nDraws], the DrawRec templates,
+// the world rotations, then the tables, light lists and bone matrices).  This kernel pulls the block over PCIe
+// itself (UVA loads from the mapped host allocation, all of a thread's loads in flight at once) instead of
+// waiting for a DMA copy: blocks < nPrepBlocks stage PREP_DRAWS slim records plus the templates and rotations
+// they name in shared memory, rebuild the full records there, derive the per-draw uniforms and write the
+// finished records to the device; the remaining blocks copy the rest of the block verbatim.
 static const int PREP_THREADS = 256;
 static const int PREP_DRAWS = 64;               // draws per block
+static const int PREP_TEMPLATES = 80;           // templates staged per block: the index window [tmin, tmin + 80) of its draws
 static const uint32_t PREP_SMEM_LIGHTS = 256;   // light lists up to this many entries are staged in shared memory
+static const int PREP_PARAM_BLOCKS = PREP_WINDOW_BLOCKS;
+static_assert(PREP_DRAWS == PREP_WINDOW_DRAWS, "t3d_internal.h: the host computes the windows per PREP_DRAWS draws");
 static const int REC16 = sizeof(DrawRec) / 16;
+static const int SLIM16 = sizeof(DrawSlim) / 16;
+static const size_t PREP_SMEM_BYTES = (size_t)PREP_DRAWS * sizeof(DrawRec) + (size_t)PREP_DRAWS * sizeof(DrawSlim) +
+                                      (size_t)PREP_TEMPLATES * sizeof(DrawRec) + (size_t)PREP_DRAWS * 64 +
+                                      (size_t)PREP_SMEM_LIGHTS * sizeof(t3d_light);
+
+struct PrepFrame {
+    const uint4* hostSlim;      // DrawSlim[nDraws]          (pinned host, UVA)
+    const uint4* hostTmpl;      // DrawRec[nTemplates]
+    const uint4* hostRot;       // float[16][nRotations]
+    const uint4* hostRest;      // tables, lights, bones ...
+    const t3d_light* hostLights;
+    uint4* devDraws;            // DrawRec[nDraws]           (device)
+    uint4* devRest;
+    uint32_t nDraws, rest16, nPrepBlocks, nLightsIn;
+    // template / rotation windows {tmin, templates, rmin, rotations} of the first blocks, known to the host: those
+    // blocks (all of a small frame) fetch slim records, templates and rotations in ONE round trip over PCIe
+    uint32_t win[PREP_PARAM_BLOCKS][4];
+};
 
 __global__ void __launch_bounds__(PREP_THREADS)
-k_prep_draws(const uint4* __restrict__ hostFrame, uint4* __restrict__ devFrame, uint32_t nDraws, uint32_t restOff16,
-             uint32_t total16, uint32_t nPrepBlocks, const __grid_constant__ FrameConst fc,
-             const t3d_light* __restrict__ lightsHost, uint32_t nLightsIn, LightU* __restrict__ lightsU,
-             DrawStat* __restrict__ stats) {
+k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ FrameConst fc,
+             LightU* __restrict__ lightsU, DrawStat* __restrict__ stats) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
-    if (blockIdx.x >= nPrepBlocks) {
-        const uint32_t nb = gridDim.x - nPrepBlocks;
+    if (blockIdx.x >= pf.nPrepBlocks) {
+        const uint32_t nb = gridDim.x - pf.nPrepBlocks;
         const uint32_t stride = nb * PREP_THREADS;
-        uint32_t i = restOff16 + (blockIdx.x - nPrepBlocks) * PREP_THREADS + threadIdx.x;
-        for (; i + 7 * stride < total16; i += 8 * stride) {
+        const uint4* __restrict__ src = pf.hostRest;
+        uint4* __restrict__ dst = pf.devRest;
+        uint32_t i = (blockIdx.x - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x;
+        for (; i + 7 * stride < pf.rest16; i += 8 * stride) {
             uint4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = hostFrame[i + u * stride];
+            for (int u = 0; u < 8; u++) v[u] = src[i + u * stride];
 #pragma unroll
-            for (int u = 0; u < 8; u++) devFrame[i + u * stride] = v[u];
+            for (int u = 0; u < 8; u++) dst[i + u * stride] = v[u];
         }
-        for (; i < total16; i += stride) devFrame[i] = hostFrame[i];
+        for (; i < pf.rest16; i += stride) dst[i] = src[i];
         return;
     }
     DrawRec* sR = reinterpret_cast<DrawRec*>(prepSmem);
-    t3d_light* sL = reinterpret_cast<t3d_light*>(prepSmem + PREP_DRAWS * REC16);
+    DrawSlim* sS = reinterpret_cast<DrawSlim*>(prepSmem + PREP_DRAWS * REC16);
+    uint4* sT = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
+    uint4* sRot = sT + PREP_TEMPLATES * REC16;
+    t3d_light* sL = reinterpret_cast<t3d_light*>(sRot + PREP_DRAWS * 4);
     const uint32_t d0 = blockIdx.x * PREP_DRAWS;
-    const uint32_t n = min((uint32_t)PREP_DRAWS, nDraws - d0);
-    {
-        const uint4* src = hostFrame + (size_t)d0 * REC16;
-        const uint32_t n16 = n * REC16;
-        uint4 v[8];
+    const uint32_t n = min((uint32_t)PREP_DRAWS, pf.nDraws - d0);
+    constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
+    const bool known = blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
+    uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
+    {   // slim records (7 uint4 each), and for the first blocks the templates and rotations in the same round trip
+        const uint4* src = pf.hostSlim + (size_t)d0 * SLIM16;
+        uint4* dst = reinterpret_cast<uint4*>(sS);
+        const uint32_t n16 = n * SLIM16;
+        uint4 v[2], tv[T_SWEEPS], rv;
 #pragma unroll
-        for (int u = 0; u < 8; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
+        for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
+        const uint32_t t16 = known ? pf.win[blockIdx.x][1] * REC16 : 0u, r16 = known ? pf.win[blockIdx.x][3] * 4 : 0u;
+        const uint4* tsrc = pf.hostTmpl + (size_t)tmin * REC16;
 #pragma unroll
-        for (int u = 0; u < 8; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) prepSmem[i] = v[u]; }
-        static_assert(8 * PREP_THREADS >= PREP_DRAWS * REC16, "staging covers a block's records in one sweep");
+        for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) tv[u] = tsrc[i]; }
+        if (threadIdx.x < r16) rv = pf.hostRot[(size_t)rmin * 4 + threadIdx.x];
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) dst[i] = v[u]; }
+#pragma unroll
+        for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) sT[i] = tv[u]; }
+        if (threadIdx.x < r16) sRot[threadIdx.x] = rv;
+        static_assert(2 * PREP_THREADS >= PREP_DRAWS * SLIM16, "staging covers a block's slim records in one sweep");
     }
-    const bool lightsStaged = nLightsIn <= PREP_SMEM_LIGHTS;
+    const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
     if (lightsStaged) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(lightsHost);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(pf.hostLights);
         uint32_t* dst = reinterpret_cast<uint32_t*>(sL);
-        const uint32_t nw = nLightsIn * (uint32_t)(sizeof(t3d_light) / 4);
+        const uint32_t nw = pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4);
         for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) dst[i] = src[i];
     }
-    const t3d_light* lightsIn = lightsStaged ? sL : lightsHost;
+    const t3d_light* lightsIn = lightsStaged ? sL : pf.hostLights;
     __syncthreads();
+    if (!known) {
+        // later blocks find their windows in the slim records: a window of template indices (the host reuses one of
+        // its most recent templates when it can, so the window is small) and an ascending run of rotation indices
+        uint32_t tmax = 0u, rmax = 0u;
+        tmin = 0xFFFFFFFFu;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t t = sS[k].tmpl, r = sS[k].rot;
+            tmin = min(tmin, t); tmax = max(tmax, t);
+            if (r != NO_ROTATION) { rmin = min(rmin, r); rmax = max(rmax, r); }
+        }
+        const uint32_t n16 = min(tmax - tmin + 1, (uint32_t)PREP_TEMPLATES) * REC16;
+        const uint4* src = pf.hostTmpl + (size_t)tmin * REC16;
+        uint4 v[T_SWEEPS];
+#pragma unroll
+        for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
+#pragma unroll
+        for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) sT[i] = v[u]; }
+        if (rmin != NO_ROTATION) {
+            const uint32_t r16 = (rmax - rmin + 1) * 4;      // at most one rotation per draw
+            if (threadIdx.x < r16) sRot[threadIdx.x] = pf.hostRot[(size_t)rmin * 4 + threadIdx.x];
+        }
+        __syncthreads();
+    }
     if (threadIdx.x < n) {
     const uint32_t d = d0 + threadIdx.x;
     DrawRec& R = sR[threadIdx.x];
+    {   // full record = template + this draw's placement
+        const DrawSlim& S = sS[threadIdx.x];
+        uint4* dst = reinterpret_cast<uint4*>(&R);
+        const uint32_t ti = S.tmpl - tmin;
+        const uint4* src = ti < (uint32_t)PREP_TEMPLATES ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
+#pragma unroll
+        for (int i = 0; i < REC16; i++) dst[i] = src[i];
+        R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
+#pragma unroll
+        for (int i = 0; i < 16; i++) R.transform[i] = S.transform[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) R.color[i] = S.color[i];
+        if (S.rot != NO_ROTATION) {
+            const float* rs = reinterpret_cast<const float*>(sRot + (size_t)(S.rot - rmin) * 4);
+#pragma unroll
+            for (int i = 0; i < 16; i++) R.worldRot[i] = rs[i];
+        }
+    }
 
     const uint32_t flags = R.flags;
     const bool skinned = flags & T3D_DRAW_SKINNED;
@@ -195,7 +274,7 @@ k_prep_draws(const uint4* __restrict__ hostFrame, uint4* __restrict__ devFrame, 
     }
     __syncthreads();
     {
-        uint4* dst = devFrame + (size_t)d0 * REC16;
+        uint4* dst = pf.devDraws + (size_t)d0 * REC16;
         const uint32_t n16 = n * REC16;
         for (uint32_t i = threadIdx.x; i < n16; i += PREP_THREADS) dst[i] = prepSmem[i];
     }
@@ -1091,18 +1170,22 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
 // ------------------------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostFrame, void* devFrame, uint32_t nDraws, size_t restOff, size_t totalBytes,
-                       const FrameConst& fc, const t3d_light* lightsHost, uint32_t nLightsIn, LightU* lightsU, DrawStat* stats) {
+void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const void* hostTmpl, const void* hostRot, const void* hostRest,
+                       const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
+                       const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4]) {
     if (!nDraws) return;
-    const uint32_t nPrep = cdiv(nDraws, PREP_DRAWS);
-    const uint32_t rest16 = (uint32_t)((totalBytes - restOff) / 16);
-    const uint32_t nCopy = rest16 ? std::min<uint32_t>(cdiv(rest16, PREP_THREADS * 8), 1184u) : 0u;
-    const size_t smem = (size_t)PREP_DRAWS * sizeof(DrawRec) + (size_t)PREP_SMEM_LIGHTS * sizeof(t3d_light);
+    cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_BYTES);     // per device; cheap
+    PrepFrame pf;
+    pf.hostSlim = reinterpret_cast<const uint4*>(hostSlim); pf.hostTmpl = reinterpret_cast<const uint4*>(hostTmpl);
+    pf.hostRot = reinterpret_cast<const uint4*>(hostRot); pf.hostRest = reinterpret_cast<const uint4*>(hostRest);
+    pf.hostLights = hostLights;
+    pf.devDraws = reinterpret_cast<uint4*>(devDraws); pf.devRest = reinterpret_cast<uint4*>(devRest);
+    pf.nDraws = nDraws; pf.rest16 = (uint32_t)(restBytes / 16); pf.nPrepBlocks = cdiv(nDraws, PREP_DRAWS); pf.nLightsIn = nLightsIn;
+    memcpy(pf.win, win, sizeof pf.win);
+    const uint32_t nCopy = pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u;
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
-    launch_kernel(k_prep_draws, nPrep + nCopy, PREP_THREADS, smem, s, false, reinterpret_cast<const uint4*>(hostFrame),
-                  reinterpret_cast<uint4*>(devFrame), nDraws, (uint32_t)(restOff / 16), (uint32_t)(totalBytes / 16), nPrep, fc, lightsHost,
-                  nLightsIn, lightsU, stats);
+    launch_kernel(k_prep_draws, pf.nPrepBlocks + nCopy, PREP_THREADS, PREP_SMEM_BYTES, s, false, pf, fc, lightsU, stats);
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
