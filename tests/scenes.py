@@ -93,6 +93,45 @@ def tile_boundary_scene(seed=0, sizes=(1, 2, 1023, 1024, 1025, 7, 2048, 2049, 30
     return SceneDesc(models, lights_mixed(rng, ranged=True), cam, WorldDesc(ambient_energy=0.1), name="tiles%d" % seed)
 
 
+def fuzz_scene(seed: int) -> SceneDesc:
+    """A random frame: random camera / world switches, and a random mix of static soups of random sizes (packed,
+    medium and large draws), skinned characters, billboards, a dynamic batch and transparent parts."""
+    rng = np.random.default_rng(1000 + seed)
+    models = []
+    n_static = int(rng.integers(1, 7))
+    for k in range(n_static):
+        n_tris = int(rng.choice([1, 3, 40, 700, 1024, 1500, 2300, 5000, 9000]))
+        n_parts = int(rng.choice([1, 1, 2, 3])) if n_tris >= 40 else 1
+        mat = None if rng.random() < 0.6 else MaterialDesc(backface_culling=bool(rng.integers(0, 2)), triangle_sort_mode=int(rng.integers(0, 3)),
+                                                           lighting_mode=int(rng.integers(0, 3)), shadeless=bool(rng.random() < 0.2),
+                                                           transparency_mode=int(rng.choice([0, 0, 3])), use_texture=bool(rng.integers(0, 2)), tex_w=32, tex_h=16)
+        mesh = random_soup(n_tris, seed * 100 + k, material=mat, n_parts=n_parts, colors=bool(rng.integers(0, 2)), extent=float(rng.uniform(2, 8)))
+        for inst in range(int(rng.integers(1, 4))):
+            nd = NodeDesc(position=tuple(float(x) for x in rng.uniform(-6, 6, 3)), scale=tuple(float(x) for x in rng.uniform(0.4, 1.6, 3)),
+                          rotation=random_rotation(rng))
+            models.append(ModelDesc(mesh, nd, color=tuple(float(x) for x in rng.uniform(0.3, 1, 4)), frustum_culling=bool(rng.integers(0, 2)),
+                                    shadeless=bool(rng.random() < 0.1), name="f%d_%d" % (k, inst)))
+    if rng.random() < 0.5:
+        sk = skinned_scene(seed, n=int(rng.integers(1, 5)))
+        models.extend(sk.models)
+    if rng.random() < 0.5:
+        bb = billboard_scene(seed, locks=tuple(bool(x) for x in rng.integers(0, 2, 3)), camera_up=bool(rng.integers(0, 2)), unbillboarded=bool(rng.integers(0, 2)))
+        models.extend(bb.models[: int(rng.integers(1, 12))])
+    if rng.random() < 0.4:
+        bs = batch_scene(seed, n_children=int(rng.integers(1, 60)), transparent=bool(rng.integers(0, 2)))
+        models.extend(bs.models)
+    lights = lights_mixed(rng, ranged=bool(rng.integers(0, 2))) if rng.random() < 0.85 else []
+    persp = bool(rng.random() < 0.8)
+    cam = CameraDesc(node=NodeDesc(position=(float(rng.uniform(-2, 2)), float(rng.uniform(-1, 3)), float(rng.uniform(6, 16))),
+                                   rotation=W.rotation_matrix((0, 1, 0), float(rng.uniform(-0.2, 0.2)))),
+                     perspective=persp, ortho_scale=float(rng.uniform(8, 24)), far=float(rng.choice([20.0, 100.0])),
+                     vertex_snapping=float(rng.choice([0.0, 0.0, 8.0])), render_depth=bool(rng.random() < 0.7),
+                     render_normals=bool(rng.random() < 0.3), perspective_corrected_texture_mapping=bool(rng.random() < 0.3))
+    world = WorldDesc(present=bool(rng.random() < 0.9), lighting_on=bool(rng.random() < 0.9), fog_on=bool(rng.integers(0, 2)),
+                      fog_mode=int(rng.integers(0, 2)), fog_color=(0.3, 0.5, 0.7, 1.0), fog_range=(0.1, 0.9), ambient_energy=float(rng.uniform(0, 0.4)))
+    return SceneDesc(models, lights, cam, world, name="fuzz%d" % seed)
+
+
 def skinned_scene(seed=0, n=6) -> SceneDesc:
     rng = np.random.default_rng(seed)
     mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=5)

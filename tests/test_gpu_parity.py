@@ -54,6 +54,59 @@ def test_many_tiny_draws_parity(device):
     assert_parity(sc, device, check_capture=False)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_parity(device, seed):
+    assert_parity(scenes.fuzz_scene(seed), device, check_capture=False)
+
+
+def test_stage_timing_mode_gives_the_same_lists(device):
+    """t3d_set_stage_timings(1) serialises the kernels with events instead of chaining them with programmatic
+    dependent launches: same lists, and per-stage times that add up to no more than the frame."""
+    sc = scenes.tile_boundary_scene(34)
+    scene, cam, objs = render_gpu(sc, device)
+    col0 = cam.ColorVertexList().copy(); dep0 = cam.DepthVertexList().copy(); tri0 = cam.TriangleIDs().copy()
+    t0 = cam.Timings()
+    assert t0["total_ms"] > 0 and t0["vertex_ms"] == 0
+    device.SetStageTimings(True)
+    try:
+        cam.Clear(); cam.RenderScene(scene)
+        t1 = cam.Timings()
+        assert np.array_equal(bits(col0), bits(cam.ColorVertexList())) and np.array_equal(bits(dep0), bits(cam.DepthVertexList()))
+        assert np.array_equal(tri0, cam.TriangleIDs())
+        stages = t1["prep_ms"] + t1["vertex_ms"] + t1["cull_ms"] + t1["sort_ms"] + t1["emit_ms"]
+        assert t1["vertex_ms"] > 0 and t1["emit_ms"] > 0 and stages <= t1["total_ms"] * 1.001
+    finally:
+        device.SetStageTimings(False)
+
+
+def test_external_output_target(device):
+    """t3d_set_output_target: the emit kernel writes the lists into caller-provided device memory (what the
+    multi-GPU path maps from another rank); the host copy made from there is bit-identical."""
+    sc = scenes.soup_scene(41)
+    scene, cam, objs = render_gpu(sc, device)
+    col0 = cam.ColorVertexList().copy(); dep0 = cam.DepthVertexList().copy()
+    cap = 3 * sc.total_triangles()
+    pc, _ = device.SharedAlloc(cap * 48)
+    pd, _ = device.SharedAlloc(cap * 48)
+    device.SetOutputTarget(pc, pd, 0, cap)
+    try:
+        cam.DownloadResults = False
+        cam.Clear(); cam.RenderScene(scene)
+        assert cam.DevicePointers()["color"] == pc and cam.DevicePointers()["depth"] == pd
+        cam.DownloadResults = True
+        cam.Clear(); cam.RenderScene(scene)
+        assert np.array_equal(bits(col0), bits(cam.ColorVertexList())) and np.array_equal(bits(dep0), bits(cam.DepthVertexList()))
+        device.SetOutputTarget(pc, pd, 0, 3)         # too small for the frame: refused, not overrun
+        cam.Clear()
+        import tetra3d_b200 as t3d
+        with pytest.raises(t3d.T3DError):
+            cam.RenderScene(scene)
+    finally:
+        device.SetOutputTarget(0, 0, 0, 0)
+    cam.Clear(); cam.RenderScene(scene)
+    assert np.array_equal(bits(col0), bits(cam.ColorVertexList()))
+
+
 def test_everything_culled(device):
     sc = scenes.soup_scene(21)
     sc.camera.node.position = (0.0, 0.0, 500.0)      # everything beyond the far plane

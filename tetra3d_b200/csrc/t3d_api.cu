@@ -907,7 +907,8 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
 
 int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity) {
     if (!ctx) return T3D_E_INVALID;
-    if (ctx->inFrame && ctx->executed && !ctx->haveResults) return fail(ctx, T3D_E_STATE, "t3d_set_output_target: a frame is in flight");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));       // a frame still in flight keeps writing to the old target
     if ((color == nullptr) != (depth == nullptr)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: colour and depth lists go together");
     if (color && (((uintptr_t)color | (uintptr_t)depth | (uintptr_t)normal) & 15)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: lists must be 16-byte aligned");
     ctx->xColor = color; ctx->xDepth = depth; ctx->xNormal = color ? normal : nullptr;
