@@ -103,6 +103,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
     const bool known = blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
     uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
+    const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
     {   // slim records (7 uint4 each), and for the first blocks the templates and rotations in the same round trip
         const uint4* src = pf.hostSlim + (size_t)d0 * SLIM16;
         uint4* dst = reinterpret_cast<uint4*>(sS);
@@ -115,19 +116,22 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) tv[u] = tsrc[i]; }
         if (threadIdx.x < r16) rv = pf.hostRot[(size_t)rmin * 4 + threadIdx.x];
+        // the light table rides in the same round trip (its first 512 words; longer tables finish below)
+        const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(pf.hostLights);
+        uint32_t* ldst = reinterpret_cast<uint32_t*>(sL);
+        const uint32_t nw = lightsStaged ? pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4) : 0u;
+        uint32_t lv[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < nw) lv[u] = lsrc[i]; }
 #pragma unroll
         for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) dst[i] = v[u]; }
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) sT[i] = tv[u]; }
         if (threadIdx.x < r16) sRot[threadIdx.x] = rv;
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < nw) ldst[i] = lv[u]; }
+        for (uint32_t i = 2 * PREP_THREADS + threadIdx.x; i < nw; i += PREP_THREADS) ldst[i] = lsrc[i];
         static_assert(2 * PREP_THREADS >= PREP_DRAWS * SLIM16, "staging covers a block's slim records in one sweep");
-    }
-    const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
-    if (lightsStaged) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(pf.hostLights);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sL);
-        const uint32_t nw = pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4);
-        for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) dst[i] = src[i];
     }
     const t3d_light* lightsIn = lightsStaged ? sL : pf.hostLights;
     __syncthreads();
@@ -154,123 +158,154 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         }
         __syncthreads();
     }
-    if (threadIdx.x < n) {
-    const uint32_t d = d0 + threadIdx.x;
-    DrawRec& R = sR[threadIdx.x];
-    {   // full record = template + this draw's placement
-        const DrawSlim& S = sS[threadIdx.x];
-        uint4* dst = reinterpret_cast<uint4*>(&R);
+    // Four threads per draw (role = warp pair, so the roles run on different schedulers): the serial chain of one
+    // draw's uniform derivation is cut into independent pieces, each evaluated exactly as before.
+    const uint32_t role = threadIdx.x / PREP_DRAWS, k = threadIdx.x % PREP_DRAWS;
+    static_assert(PREP_THREADS == 4 * PREP_DRAWS, "four roles per draw");
+    const bool mine = k < n;
+    if (mine) {   // full record = template + this draw's placement, assembled by the draw's four threads
+        const DrawSlim& S = sS[k];
+        uint4* dst = reinterpret_cast<uint4*>(&sR[k]);
         const uint32_t ti = S.tmpl - tmin;
         const uint4* src = ti < (uint32_t)PREP_TEMPLATES ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
-#pragma unroll
-        for (int i = 0; i < REC16; i++) dst[i] = src[i];
-        R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
-#pragma unroll
-        for (int i = 0; i < 16; i++) R.transform[i] = S.transform[i];
-#pragma unroll
-        for (int i = 0; i < 4; i++) R.color[i] = S.color[i];
-        if (S.rot != NO_ROTATION) {
-            const float* rs = reinterpret_cast<const float*>(sRot + (size_t)(S.rot - rmin) * 4);
-#pragma unroll
-            for (int i = 0; i < 16; i++) R.worldRot[i] = rs[i];
+        const uint4* sl = reinterpret_cast<const uint4*>(&S);
+        const uint4* rs = S.rot != NO_ROTATION ? sRot + (size_t)(S.rot - rmin) * 4 : nullptr;
+        constexpr int TR16 = offsetof(DrawRec, transform) / 16, WR16 = offsetof(DrawRec, worldRot) / 16, CO16 = offsetof(DrawRec, color) / 16;
+        constexpr int STR16 = offsetof(DrawSlim, transform) / 16, SCO16 = offsetof(DrawSlim, color) / 16;
+        for (int i = role; i < REC16; i += 4) {
+            uint4 v = src[i];
+            if (i >= TR16 && i < TR16 + 4) v = sl[STR16 + (i - TR16)];
+            else if (i == CO16) v = sl[SCO16];
+            else if (rs && i >= WR16 && i < WR16 + 4) v = rs[i - WR16];
+            dst[i] = v;
         }
     }
-
+    __syncthreads();
+    if (mine && role == 0) {      // the scalar placement fields
+        const DrawSlim& S = sS[k];
+        DrawRec& R = sR[k];
+        R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
+    }
+    __syncthreads();
+    float* sInv = reinterpret_cast<float*>(sS);          // the slim records are consumed: 16 floats per draw {r rows 0-2, invPS}
+    static_assert(sizeof(DrawSlim) >= 16 * sizeof(float), "scratch per draw");
+    if (mine) {
+    DrawRec& R = sR[k];
     const uint32_t flags = R.flags;
     const bool skinned = flags & T3D_DRAW_SKINNED;
-    Mat4 modelT = m4_load(R.transform);
-    Mat4 vp = m4_load(fc.vp);
-    Vec3 camPos = v3(fc.camPos[0], fc.camPos[1], fc.camPos[2]);
-
-    // model.go:629-630
-    Vec3 p, s; Mat4 r;
-    { Mat4 inv = m4_inverted(modelT); m4_decompose(inv, p, s, r); }
-    Vec3 invPS = v3_mult(p, v3(1.0f / s.X, 1.0f / s.Y, 1.0f / s.Z));
-    Vec3 invCam = v3_add(m4_multvec(r, camPos), invPS);
-    R.invCam[0] = invCam.X; R.invCam[1] = invCam.Y; R.invCam[2] = invCam.Z;
-
-    Mat4 base = modelT;
-    if (flags & T3D_DRAW_BILLBOARD) {                                   // model.go:634-693
-        Vec3 up = v3(0, 1, 0);
-        if (flags & T3D_DRAW_BILLBOARD_CAMERA_UP) up = v3(fc.camUp[0], fc.camUp[1], fc.camUp[2]);
-        Mat4 lookat = m4_lookat(v3(modelT.m[3][0], modelT.m[3][1], modelT.m[3][2]), camPos, up);
-        if (flags & T3D_DRAW_BILLBOARD_LOCK_X) {
-            lookat.m[0][0] = 1; lookat.m[0][1] = 0; lookat.m[0][2] = 0; lookat.m[0][3] = 0;
-            lookat.m[1][0] = 0; m4_unit_row(lookat, 1);
-            lookat.m[2][0] = 0; m4_unit_row(lookat, 2);
-        }
-        if (flags & T3D_DRAW_BILLBOARD_LOCK_Y) {
-            lookat.m[1][0] = 0; lookat.m[1][1] = 1; lookat.m[1][2] = 0; lookat.m[1][3] = 0;
-            lookat.m[0][1] = 0; m4_unit_row(lookat, 0);
-            lookat.m[2][1] = 0; m4_unit_row(lookat, 2);
-        }
-        if (flags & T3D_DRAW_BILLBOARD_LOCK_Z) {
-            lookat.m[2][0] = 0; lookat.m[2][1] = 0; lookat.m[2][2] = 1; lookat.m[2][3] = 0;
-            lookat.m[0][2] = 0; m4_unit_row(lookat, 0);
-            lookat.m[1][2] = 0; m4_unit_row(lookat, 1);
-        }
-        Vec3 bp, bs; Mat4 br;
-        m4_decompose(base, bp, bs, br);
-        base = m4_mult(m4_mult(br, m4_scale(bs.X, bs.Y, bs.Z)), lookat);
-        base.m[3][0] = bp.X; base.m[3][1] = bp.Y; base.m[3][2] = bp.Z; base.m[3][3] = 1;
-    }
-    Mat4 mvp = m4_mult(base, vp);                                       // model.go:695
-    m4_store(mvp, R.mvp);
-
-    if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) {                         // model.go:700-703
-        Mat4 u = m4_mult(modelT, vp);
-        R.unbill[0] = u.m[0][2]; R.unbill[1] = u.m[1][2]; R.unbill[2] = u.m[2][2]; R.unbill[3] = u.m[3][2];
-    }
-    if (fc.camFlags & T3D_CAM_RENDER_NORMALS) {                         // model.go:705-708
-        Mat4 mv = m4_mult(modelT, m4_load(fc.view));
-        Mat4 rot = m4_decompose_rotation(mv);
+    const Mat4 modelT = m4_load(R.transform);
+    const Vec3 camPos = v3(fc.camPos[0], fc.camPos[1], fc.camPos[2]);
+    if (role == 0) {
+        // model.go:629-630
+        Vec3 p, sc; Mat4 r;
+        { Mat4 inv = m4_inverted(modelT); m4_decompose(inv, p, sc, r); }
+        const Vec3 invPS = v3_mult(p, v3(1.0f / sc.X, 1.0f / sc.Y, 1.0f / sc.Z));
+        const Vec3 invCam = v3_add(m4_multvec(r, camPos), invPS);
+        R.invCam[0] = invCam.X; R.invCam[1] = invCam.Y; R.invCam[2] = invCam.Z;
+        float* o = sInv + (sizeof(DrawSlim) / 4) * k;
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) R.nrmRot[c * 4 + rr] = rot.m[rr][c];
-    }
-
-    // Lights: beginModel products + per-draw skip (camera.go:1625-1629, light.go:671-673).
-    const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
-    if (nL) {
-        Mat4 sunRot = m4_identity();
-        bool haveSun = false;
-        Vec3 modelPos = v3(modelT.m[3][0], modelT.m[3][1], modelT.m[3][2]);
-        const float maxSpan = R.maxSpan;
-        for (uint32_t i = 0; i < nL; i++) {
-            const t3d_light L = lightsIn[R.lightIn + i];
-            LightU U;
-            U.type = L.type;
-            U.color[0] = L.color[0]; U.color[1] = L.color[1]; U.color[2] = L.color[2];
-            U.energy = L.energy;
-            U.wpos[0] = U.wpos[1] = U.wpos[2] = 0;
-            U.range = L.range; U.range2 = L.range * L.range;             // light.go:277-280
-            U.fwd[0] = L.forward[0]; U.fwd[1] = L.forward[1]; U.fwd[2] = L.forward[2];
-            U.volume = L.volume; U.pad[0] = U.pad[1] = 0;
-            if (L.type == T3D_LIGHT_POINT) {
-                Vec3 lp = v3(L.position[0], L.position[1], L.position[2]);
-                if (L.range > 0) {                                       // camera.go:1625-1629
-                    float dist = maxSpan + L.range;
-                    if (v3_dist2(modelPos, lp) > dist * dist) U.type = LIGHT_SKIP;
-                }
-                Vec3 wp = skinned ? lp : v3_add(m4_multvec(r, lp), invPS);   // light.go:183-187
-                U.wpos[0] = wp.X; U.wpos[1] = wp.Y; U.wpos[2] = wp.Z;
-            } else if (L.type == T3D_LIGHT_DIRECTIONAL) {
-                if (!skinned && !haveSun) {                              // light.go:326-330
-                    sunRot = m4_transposed(m4_inverted(m4_load(R.worldRot)));
-                    haveSun = true;
-                }
-            } else if (L.type == T3D_LIGHT_VOLUME) {
-                if ((flags & T3D_DRAW_HAS_MATERIAL) && R.lvMode == T3D_LV_OFF) U.type = LIGHT_SKIP;   // light.go:671-673
+            for (int j = 0; j < 3; j++) o[i * 3 + j] = r.m[i][j];       // rows 0-3, columns 0-2: all m4_multvec reads
+        o[12] = invPS.X; o[13] = invPS.Y; o[14] = invPS.Z;
+        DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
+        stats[d0 + k] = st;
+    } else if (role == 1) {
+        const Mat4 vp = m4_load(fc.vp);
+        Mat4 base = modelT;
+        if (flags & T3D_DRAW_BILLBOARD) {                               // model.go:634-693
+            Vec3 up = v3(0, 1, 0);
+            if (flags & T3D_DRAW_BILLBOARD_CAMERA_UP) up = v3(fc.camUp[0], fc.camUp[1], fc.camUp[2]);
+            Mat4 lookat = m4_lookat(v3(modelT.m[3][0], modelT.m[3][1], modelT.m[3][2]), camPos, up);
+            if (flags & T3D_DRAW_BILLBOARD_LOCK_X) {
+                lookat.m[0][0] = 1; lookat.m[0][1] = 0; lookat.m[0][2] = 0; lookat.m[0][3] = 0;
+                lookat.m[1][0] = 0; m4_unit_row(lookat, 1);
+                lookat.m[2][0] = 0; m4_unit_row(lookat, 2);
             }
-            lightsU[R.lightU + i] = U;
+            if (flags & T3D_DRAW_BILLBOARD_LOCK_Y) {
+                lookat.m[1][0] = 0; lookat.m[1][1] = 1; lookat.m[1][2] = 0; lookat.m[1][3] = 0;
+                lookat.m[0][1] = 0; m4_unit_row(lookat, 0);
+                lookat.m[2][1] = 0; m4_unit_row(lookat, 2);
+            }
+            if (flags & T3D_DRAW_BILLBOARD_LOCK_Z) {
+                lookat.m[2][0] = 0; lookat.m[2][1] = 0; lookat.m[2][2] = 1; lookat.m[2][3] = 0;
+                lookat.m[0][2] = 0; m4_unit_row(lookat, 0);
+                lookat.m[1][2] = 0; m4_unit_row(lookat, 1);
+            }
+            Vec3 bp, bs; Mat4 br;
+            m4_decompose(base, bp, bs, br);
+            base = m4_mult(m4_mult(br, m4_scale(bs.X, bs.Y, bs.Z)), lookat);
+            base.m[3][0] = bp.X; base.m[3][1] = bp.Y; base.m[3][2] = bp.Z; base.m[3][3] = 1;
         }
-        // The sun's workingModelRotation is per model; park it in worldRot (in place).
-        if (haveSun) m4_store(sunRot, R.worldRot);
+        const Mat4 mvp = m4_mult(base, vp);                             // model.go:695
+        m4_store(mvp, R.mvp);
+    } else if (role == 2) {
+        if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) {                     // model.go:700-703
+            const Mat4 u = m4_mult(modelT, m4_load(fc.vp));
+            R.unbill[0] = u.m[0][2]; R.unbill[1] = u.m[1][2]; R.unbill[2] = u.m[2][2]; R.unbill[3] = u.m[3][2];
+        }
+        if (fc.camFlags & T3D_CAM_RENDER_NORMALS) {                     // model.go:705-708
+            const Mat4 mv = m4_mult(modelT, m4_load(fc.view));
+            const Mat4 rot = m4_decompose_rotation(mv);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) R.nrmRot[c * 4 + rr] = rot.m[rr][c];
+        }
+    } else {
+        // The sun's workingModelRotation (light.go:326-330) is per model: parked in worldRot, in place, when the
+        // draw's list holds a directional light.
+        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+        bool haveSun = false;
+        for (uint32_t i = 0; i < nL && !haveSun; i++) haveSun = lightsIn[R.lightIn + i].type == T3D_LIGHT_DIRECTIONAL;
+        if (haveSun && !skinned) {
+            const Mat4 sunRot = m4_transposed(m4_inverted(m4_load(R.worldRot)));
+            m4_store(sunRot, R.worldRot);
+        }
     }
-
-    DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
-    stats[d] = st;
+    }
+    __syncthreads();
+    if (mine) {
+        // Lights: beginModel products + per-draw skip (camera.go:1625-1629, light.go:671-673), the draw's four
+        // threads taking every fourth light.
+        const DrawRec& R = sR[k];
+        const uint32_t flags = R.flags;
+        const bool skinned = flags & T3D_DRAW_SKINNED;
+        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+        if (role < nL) {
+            const float* o = sInv + (sizeof(DrawSlim) / 4) * k;
+            Mat4 r = m4_identity();
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) r.m[i][j] = o[i * 3 + j];
+            const Vec3 invPS = v3(o[12], o[13], o[14]);
+            const Vec3 modelPos = v3(R.transform[12], R.transform[13], R.transform[14]);
+            const float maxSpan = R.maxSpan;
+            for (uint32_t i = role; i < nL; i += 4) {
+                const t3d_light L = lightsIn[R.lightIn + i];
+                LightU U;
+                U.type = L.type;
+                U.color[0] = L.color[0]; U.color[1] = L.color[1]; U.color[2] = L.color[2];
+                U.energy = L.energy;
+                U.wpos[0] = U.wpos[1] = U.wpos[2] = 0;
+                U.range = L.range; U.range2 = L.range * L.range;         // light.go:277-280
+                U.fwd[0] = L.forward[0]; U.fwd[1] = L.forward[1]; U.fwd[2] = L.forward[2];
+                U.volume = L.volume; U.pad[0] = U.pad[1] = 0;
+                if (L.type == T3D_LIGHT_POINT) {
+                    const Vec3 lp = v3(L.position[0], L.position[1], L.position[2]);
+                    if (L.range > 0) {                                   // camera.go:1625-1629
+                        const float dist = maxSpan + L.range;
+                        if (v3_dist2(modelPos, lp) > dist * dist) U.type = LIGHT_SKIP;
+                    }
+                    const Vec3 wp = skinned ? lp : v3_add(m4_multvec(r, lp), invPS);   // light.go:183-187
+                    U.wpos[0] = wp.X; U.wpos[1] = wp.Y; U.wpos[2] = wp.Z;
+                } else if (L.type == T3D_LIGHT_VOLUME) {
+                    if ((flags & T3D_DRAW_HAS_MATERIAL) && R.lvMode == T3D_LV_OFF) U.type = LIGHT_SKIP;   // light.go:671-673
+                }
+                lightsU[R.lightU + i] = U;
+            }
+        }
     }
     __syncthreads();
     {
