@@ -92,7 +92,9 @@ struct t3d_ctx {
     bool inFrame = false, executed = false, haveResults = false;
     bool stageTimings = false, stagesTimed = false;
     FrameConst fc;
-    PinVec<DrawRec> hDraws;             // full records, host side only (the device rebuilds them from hSlim + hTmpl)
+    // what the host itself needs to remember about a submitted draw (the device rebuilds the full DrawRec from hSlim + hTmpl)
+    struct HostDraw { uint32_t a0, nv, vbase, nt, flags; uint8_t sortMode; };
+    std::vector<HostDraw> hDraws;
     PinVec<DrawSlim> hSlim;
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
@@ -210,7 +212,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
-    ctx->hFrame.release(); ctx->hDraws.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hTiles.release();
+    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
@@ -439,15 +441,21 @@ int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
     if (!ctx || (n && !draws)) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: NULL argument");
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_draws: not between frame_begin and frame_execute");
-    if (ctx->hDraws.n + n >= (1u << (32 - BIN_BITS))) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: too many draws in one frame");
-    CU(ctx->hDraws.reserve(ctx->hDraws.n + n));
-    CU(ctx->hVbase.reserve(ctx->hDraws.n + n + 1));
-    CU(ctx->hTbase.reserve(ctx->hDraws.n + n + 1));
+    if (ctx->hDraws.size() + n >= 0xFFFFFFF0ull) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: too many draws in one frame");
+    ctx->hDraws.reserve(ctx->hDraws.size() + n);
+    CU(ctx->hVbase.reserve(ctx->hDraws.size() + n + 1));
+    CU(ctx->hTbase.reserve(ctx->hDraws.size() + n + 1));
+    CU(ctx->hSlim.reserve(ctx->hSlim.n + n));
+    ctx->drawTotalTris.reserve(ctx->drawTotalTris.size() + n); ctx->drawContinue.reserve(ctx->drawContinue.size() + n);
+    const Mesh* lastMesh = nullptr; uint64_t lastMeshId = 0;
     for (uint32_t i = 0; i < n; i++) {
         const t3d_draw& in = draws[i];
-        auto it = ctx->meshes.find(in.mesh_id);
-        if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_draws: unknown mesh");
-        const Mesh& m = it->second;
+        if (!lastMesh || in.mesh_id != lastMeshId) {        // runs of instances share a mesh: one lookup per run
+            auto it = ctx->meshes.find(in.mesh_id);
+            if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_draws: unknown mesh");
+            lastMesh = &it->second; lastMeshId = in.mesh_id;
+        }
+        const Mesh& m = *lastMesh;
         if (in.part >= m.parts.size()) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: part index out of range");
         if (in.light_list >= ctx->lightLists.size()) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: unknown light list");
         if (in.sort_mode > T3D_SORT_NONE || in.lighting_mode > T3D_LIGHTING_DOUBLE_SIDED || in.light_volume_mode > T3D_LV_OFF)
@@ -481,8 +489,8 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.count; ctx->anyLit = true; }
         if (flags & T3D_DRAW_SKINNED) ctx->anySkinned = true;
         if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) ctx->anyUnbill = true;
-        ctx->hVbase.p[ctx->hDraws.n] = ctx->vAcc;
-        ctx->hTbase.p[ctx->hDraws.n] = ctx->tAcc;
+        ctx->hVbase.p[ctx->hDraws.size()] = ctx->vAcc;
+        ctx->hTbase.p[ctx->hDraws.size()] = ctx->tAcc;
         ctx->vAcc += pi.nv; ctx->tAcc += R.nt;
         {   // what goes over PCIe: a 112-byte placement record, plus a template whenever anything else changes
             // reuse one of the most recent templates when everything but the placement matches (instances of one
@@ -523,7 +531,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             }
             CU(ctx->hSlim.push(S));
         }
-        ctx->hDraws.p[ctx->hDraws.n++] = R;
+        ctx->hDraws.push_back(t3d_ctx::HostDraw{R.a0, R.nv, R.vbase, R.nt, R.flags, R.sortMode});
         ctx->drawTotalTris.push_back(R.nt);
         ctx->drawContinue.push_back((flags & T3D_DRAW_CONTINUE_FLUSH) ? 1 : 0);
     }
@@ -569,7 +577,7 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
             if (medium && (e = ctx->hMedium.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
             for (uint32_t j = 0; j < n; j++) {
                 TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
-                t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws.p[d].sortMode; t.tbase = tb[d];
+                t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws[d].sortMode; t.tbase = tb[d];
                 if (!medium && (e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
                 if ((e = ctx->hTiles.push(t)) != cudaSuccess) return e;
             }
@@ -588,7 +596,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_execute: no open frame");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint32_t nDraws = (uint32_t)ctx->hDraws.n;
+    const uint32_t nDraws = (uint32_t)ctx->hDraws.size();
     const uint32_t totalV = ctx->vAcc, totalT = ctx->tAcc;
     ctx->launches = 0;
     ctx->executed = true;
@@ -761,7 +769,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     // world position 12), skinned unlit 76 (normals are still skinned).
     uint64_t bytes = 0;
     for (uint32_t i = 0; i < nDraws; i++) {
-        const DrawRec& R = ctx->hDraws.p[i];
+        const t3d_ctx::HostDraw& R = ctx->hDraws[i];
         const bool lit = R.flags & T3D_DRAW_LIT, sk = R.flags & T3D_DRAW_SKINNED;
         uint64_t per = 12 + 16;
         if (lit) per += 12 + 12;
@@ -777,7 +785,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_results: frame not executed");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint32_t nDraws = (uint32_t)ctx->hDraws.n;
+    const uint32_t nDraws = (uint32_t)ctx->hDraws.size();
     const uint32_t totalT = ctx->tAcc;
     const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
     memset(out, 0, sizeof *out);
@@ -883,9 +891,9 @@ int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* t
 int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end, float* clip4, float* light4) {
     if (!ctx) return T3D_E_INVALID;
     if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_debug_read_draw_vertices: frame not executed");
-    if (draw >= ctx->hDraws.n) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: draw out of range");
+    if (draw >= ctx->hDraws.size()) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: draw out of range");
     CU(cudaSetDevice(ctx->device));
-    const DrawRec& R = ctx->hDraws.p[draw];
+    const t3d_ctx::HostDraw& R = ctx->hDraws[draw];
     if (vtx_start > vtx_end) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_draw_vertices: bad range");
     const size_t n = vtx_end - vtx_start;
     if (n == 0) return T3D_OK;

@@ -2,6 +2,9 @@
 #include <functional>
 #include <stdexcept>
 #include "tetra3d.hpp"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cfloat>
@@ -403,6 +406,14 @@ t3d_light toLight(GeometryDevice& dev, ILight* l) {
 
 void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std::vector<Model*>& models) {   // camera.go:1269-2114
     if (!device) throw T3DError(T3D_E_STATE, "Camera has no GeometryDevice: the geometry stage has no CPU path");
+    static const bool prof = getenv("T3D_HOST_PROFILE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!prof) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[host] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     t3d_ctx* ctx = device->ctx;
     World* world = scene.world.get();
 
@@ -465,6 +476,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         return i.order < j.order;
     });
 
+    lap("pairs + sorts");
     // ---- walk the passes and collect every render(rp) call, grouped by flush (camera.go:2057-2109) ----
     struct PendingDraw { Model* model; int part; int flush; bool first; };
     std::vector<PendingDraw> pending;
@@ -477,9 +489,15 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             if (pair.model->DynamicBatcher()) {
                 auto& modelSlice = pair.model->DynamicBatchModels[pair.part];
                 // sort.Slice far -> near (camera.go:2078-2080); ties keep insertion order (contract)
-                std::stable_sort(modelSlice.begin(), modelSlice.end(), [&](const std::shared_ptr<Model>& a, const std::shared_ptr<Model>& b) {
-                    return v3_dist2(cameraPos, a->WorldPosition()) > v3_dist2(cameraPos, b->WorldPosition());
-                });
+                // (the distance of every child is evaluated once, not once per comparison: same keys, same order)
+                {
+                    std::vector<std::pair<float, uint32_t>> keyed(modelSlice.size());
+                    for (size_t k = 0; k < modelSlice.size(); k++) keyed[k] = {v3_dist2(cameraPos, modelSlice[k]->WorldPosition()), (uint32_t)k};
+                    std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<float, uint32_t>& a, const std::pair<float, uint32_t>& b) { return a.first > b.first; });
+                    std::vector<std::shared_ptr<Model>> sorted(modelSlice.size());
+                    for (size_t k = 0; k < keyed.size(); k++) sorted[k] = std::move(modelSlice[keyed[k].second]);
+                    modelSlice.swap(sorted);
+                }
                 for (auto& merged : modelSlice) {
                     if (!merged->visible) continue;
                     if (merged->FrustumCulling && !ModelInFrustum(*merged)) continue;
@@ -494,6 +512,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         }
     }
 
+    lap("pending (batch order)");
     // ---- object-wise sharding: whole flushes, largest first onto the least-loaded rank ----
     const int nFlush = (int)flushOwners.size();
     {
@@ -534,6 +553,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     renders.clear(); flushes.clear(); localFlushIds.clear();
     std::vector<t3d_draw> draws; draws.reserve(pending.size());
     std::vector<const PendingDraw*> submitted;
+    submitted.reserve(pending.size()); renders.reserve(pending.size());
+    const Mesh* lastEnsured = nullptr;
     for (auto& pd : pending) {
         if (flushOwnerRank[pd.flush] != shardRank) continue;
         Model* model = pd.model;
@@ -546,7 +567,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         // ProcessVertices early-out (model.go:604): nothing is transformed or emitted
         const bool skip = (model->Color.A == 0 && model->isTransparent(meshPart)) || !model->visible;
 
-        device->ensureMesh(mesh);
+        if (&mesh != lastEnsured) { device->ensureMesh(mesh); lastEnsured = &mesh; }     // runs of instances share a mesh
         bool lighting = false;                                             // camera.go:1521-1528
         if (world) lighting = world->LightingOn && !(mat && mat->Shadeless) && !model->Shadeless;
 
@@ -570,7 +591,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         if (!pd.first) f |= T3D_DRAW_CONTINUE_FLUSH;
         d.flags = f;
         m4_store(model->Transform(), d.transform);
-        m4_store(model->WorldRotation(), d.world_rotation);
+        if (lighting) m4_store(model->WorldRotation(), d.world_rotation);    // only a directional light's beginModel reads it (light.go:326-330)
         Color4 mp = model->Color;                                          // camera.go:1597-1601
         if (mat) { mp.R *= mat->Color.R; mp.G *= mat->Color.G; mp.B *= mat->Color.B; mp.A *= mat->Color.A; }
         d.color[0] = mp.R; d.color[1] = mp.G; d.color[2] = mp.B; d.color[3] = mp.A;
@@ -608,11 +629,15 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         submitted.push_back(&pd);
         renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)draws.size() - 1});
     }
+    lap("build t3d_draw records");
     if (!draws.empty()) check(ctx, t3d_submit_draws(ctx, draws.data(), (uint32_t)draws.size()), "t3d_submit_draws");
+    lap("t3d_submit_draws");
     check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
+    lap("t3d_frame_execute");
     if (downloadResults) check(ctx, t3d_frame_results(ctx, &output, &timings), "t3d_frame_results");
     else check(ctx, t3d_frame_results_device(ctx, &output, &timings), "t3d_frame_results_device");
     launchCount = t3d_debug_last_launch_count(ctx);
+    lap("t3d_frame_results");
 
     // per-render and per-flush records (what flush() would slice: camera.go:1829-2048)
     size_t di = 0;
@@ -645,6 +670,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             localFlushIds.push_back(fId);
         }
     }
+    lap("render/flush records");
 }
 
 }  // namespace tetra3d
