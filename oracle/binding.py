@@ -78,7 +78,8 @@ class orc_camera(C.Structure):
                 ("near_plane", C.c_float), ("far_plane", C.c_float), ("perspective", C.c_int32),
                 ("ortho_scale", C.c_float), ("depth_margin", C.c_float), ("vertex_snapping", C.c_float),
                 ("render_depth", C.c_int32), ("render_normals", C.c_int32),
-                ("perspective_corrected_texture_mapping", C.c_int32)]
+                ("perspective_corrected_texture_mapping", C.c_int32), ("max_light_count", C.c_int32),
+                ("max_light_focus_node", C.c_int32)]
 
 
 class orc_world(C.Structure):
@@ -377,6 +378,7 @@ class _Marshalled:
         self.keep.append(c_models)
 
         cam_node = node_of(desc.camera.node)
+        focus_node = node_of(desc.camera.max_light_focus) if desc.camera.max_light_focus is not None else -1
 
         c_nodes = (orc_node * max(len(nodes), 1))()
         for i, (nd, parent) in enumerate(nodes):
@@ -401,6 +403,8 @@ class _Marshalled:
         sc.camera.depth_margin = float(cd.depth_margin); sc.camera.vertex_snapping = float(cd.vertex_snapping)
         sc.camera.render_depth = int(cd.render_depth); sc.camera.render_normals = int(cd.render_normals)
         sc.camera.perspective_corrected_texture_mapping = int(cd.perspective_corrected_texture_mapping)
+        sc.camera.max_light_count = int(cd.max_light_count)
+        sc.camera.max_light_focus_node = focus_node
         w = desc.world
         sc.world.present = int(w.present); sc.world.lighting_on = int(w.lighting_on); sc.world.fog_on = int(w.fog_on)
         sc.world.fog_mode = int(w.fog_mode); sc.world.fog_color[:] = [float(x) for x in w.fog_color]

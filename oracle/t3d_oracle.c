@@ -1183,6 +1183,93 @@ static int less_transparents(const render_pair_t* i, const render_pair_t* j) {
 
 typedef struct { int model; float dist; } child_t;
 
+/* ---- sort.SliceStable as the Go standard library implements it ---------------------------------------------
+ * The Go toolchain (and with it the standard library source) is absent from this image; this restates the
+ * algorithm of package sort (zsortfunc.go: stable_func, insertionSort_func, symMerge_func, rotate_func,
+ * swapRange_func; unchanged since Go 1.6 apart from renames): insertion sort on blocks of 20, then bottom-up
+ * SymMerge.  Needed because the reference feeds it an inconsistent comparator (camera.go:1484-1495), so only
+ * the exact sequence of Less / Swap calls defines the result. */
+typedef int (*gs_less_fn)(void*, int, int);
+typedef void (*gs_swap_fn)(void*, int, int);
+static void gs_insertion(int a, int b, gs_less_fn less, gs_swap_fn swap, void* c) {
+    for (int i = a + 1; i < b; i++)
+        for (int j = i; j > a && less(c, j, j - 1); j--) swap(c, j, j - 1);
+}
+static void gs_swap_range(int a, int b, int n, gs_swap_fn swap, void* c) { for (int i = 0; i < n; i++) swap(c, a + i, b + i); }
+static void gs_rotate(int a, int m, int b, gs_swap_fn swap, void* c) {
+    int i = m - a, j = b - m;
+    while (i != j) {
+        if (i > j) { gs_swap_range(m - i, m, j, swap, c); i -= j; }
+        else { gs_swap_range(m - i, m + j - i, i, swap, c); j -= i; }
+    }
+    gs_swap_range(m - i, m, i, swap, c);
+}
+static void gs_sym_merge(int a, int m, int b, gs_less_fn less, gs_swap_fn swap, void* c) {
+    if (m - a == 1) {
+        int i = m, j = b;
+        while (i < j) { int h = (int)(((unsigned)i + (unsigned)j) >> 1); if (less(c, h, a)) i = h + 1; else j = h; }
+        for (int k = a; k < i - 1; k++) swap(c, k, k + 1);
+        return;
+    }
+    if (b - m == 1) {
+        int i = a, j = m;
+        while (i < j) { int h = (int)(((unsigned)i + (unsigned)j) >> 1); if (!less(c, m, h)) i = h + 1; else j = h; }
+        for (int k = m; k > i; k--) swap(c, k, k - 1);
+        return;
+    }
+    int mid = (int)(((unsigned)a + (unsigned)b) >> 1);
+    int n = mid + m;
+    int start, r;
+    if (m > mid) { start = n - b; r = mid; } else { start = a; r = m; }
+    int p = n - 1;
+    while (start < r) {
+        int cc = (int)(((unsigned)start + (unsigned)r) >> 1);
+        if (!less(c, p - cc, cc)) start = cc + 1; else r = cc;
+    }
+    int end = n - start;
+    if (start < m && m < end) gs_rotate(start, m, end, swap, c);
+    if (a < start && start < mid) gs_sym_merge(a, start, mid, less, swap, c);
+    if (mid < end && end < b) gs_sym_merge(mid, end, b, less, swap, c);
+}
+static void go_stable_sort(int n, gs_less_fn less, gs_swap_fn swap, void* c) {
+    int blockSize = 20;
+    int a = 0, b = blockSize;
+    while (b <= n) { gs_insertion(a, b, less, swap, c); a = b; b += blockSize; }
+    gs_insertion(a, n, less, swap, c);
+    while (blockSize < n) {
+        a = 0; b = 2 * blockSize;
+        while (b <= n) { gs_sym_merge(a, a + blockSize, b, less, swap, c); a = b; b += 2 * blockSize; }
+        int m = a + blockSize;
+        if (m < n) gs_sym_merge(a, m, n, less, swap, c);
+        blockSize *= 2;
+    }
+}
+/* test hook: stable argsort of float keys with go_stable_sort (a consistent comparator, so the answer is unique) */
+typedef struct { const float* keys; int* perm; } gst_ctx;
+static int gst_less(void* cv, int i, int j) { gst_ctx* c = (gst_ctx*)cv; return c->keys[c->perm[i]] < c->keys[c->perm[j]]; }
+static void gst_swap(void* cv, int i, int j) { gst_ctx* c = (gst_ctx*)cv; int t = c->perm[i]; c->perm[i] = c->perm[j]; c->perm[j] = t; }
+void orc_test_go_stable_sort(int n, const float* keys, int* perm) {
+    gst_ctx c; c.keys = keys; c.perm = perm;
+    for (int i = 0; i < n; i++) perm[i] = i;
+    go_stable_sort(n, gst_less, gst_swap, &c);
+}
+
+/* the comparator of camera.go:1484-1495 over the sceneLights index list */
+typedef struct { rstate* S; int* ids; vec3 pos; } mls_ctx;
+static int mls_less(void* cv, int i, int j) {
+    mls_ctx* c = (mls_ctx*)cv;
+    const orc_light* li = &c->S->sc->lights[c->ids[i]];
+    const orc_light* lj = &c->S->sc->lights[c->ids[j]];
+    if (li->type == ORC_LIGHT_AMBIENT) return 1;
+    else if (lj->type == ORC_LIGHT_AMBIENT) return 0;
+    else if (li->type == ORC_LIGHT_DIRECTIONAL) return 1;
+    else if (lj->type == ORC_LIGHT_DIRECTIONAL) return 0;
+    vec3 pi = li->node >= 0 ? S_world_position(c->S, li->node) : v3(0, 0, 0);
+    vec3 pj = lj->node >= 0 ? S_world_position(c->S, lj->node) : v3(0, 0, 0);
+    return v3_dist2(c->pos, pi) < v3_dist2(c->pos, pj);
+}
+static void mls_swap(void* cv, int i, int j) { mls_ctx* c = (mls_ctx*)cv; int t = c->ids[i]; c->ids[i] = c->ids[j]; c->ids[j] = t; }
+
 int orc_render_scene(const orc_scene* sc, int capture, orc_result** out) {
     g_err[0] = 0;
     rstate S; memset(&S, 0, sizeof S);
@@ -1265,6 +1352,16 @@ int orc_render_scene(const orc_scene* sc, int capture, orc_result** out) {
             light_begin_render(&S, li);
             sceneLights[nSceneLights++] = li;
         }
+    }
+    /* Camera.MaxLightCount (camera.go:1474-1497): sort.SliceStable with the reference's comparator, then truncate.
+     * The comparator is not a strict weak ordering (two ambient lights each sort before the other), so the result is
+     * whatever Go's algorithm leaves: go_stable_sort restates it. */
+    if (sc->camera.max_light_count > 0) {
+        mls_ctx mc;
+        mc.S = &S; mc.ids = sceneLights;
+        mc.pos = sc->camera.max_light_focus_node >= 0 ? S_world_position(&S, sc->camera.max_light_focus_node) : S_world_position(&S, sc->camera.node);
+        go_stable_sort(nSceneLights, mls_less, mls_swap, &mc);
+        if (sc->camera.max_light_count < nSceneLights) nSceneLights = sc->camera.max_light_count;
     }
     S.sceneLights = sceneLights; S.nSceneLights = nSceneLights;
     for (int i = 0; i < nSceneLights; i++)                     /* camera.go:1499-1505 */

@@ -154,6 +154,8 @@ typedef struct {
     int32_t render_depth;
     int32_t render_normals;
     int32_t perspective_corrected_texture_mapping;
+    int32_t max_light_count;        /* Camera.MaxLightCount (camera.go:1474); 0 = unlimited */
+    int32_t max_light_focus_node;   /* Camera.MaxLightCountFocusPoint as a node index, or -1 = the camera (camera.go:1476-1481) */
 } orc_camera;
 
 /* World (world.go:25-42). */
@@ -254,4 +256,7 @@ int   orc_bin_index(float depth, float min_depth, float max_depth, int sort_mode
 #ifdef __cplusplus
 }
 #endif
+/* Test hook: perm = stable argsort of keys, computed with the restated sort.SliceStable (go_stable_sort). */
+void orc_test_go_stable_sort(int n, const float* keys, int* perm);
+
 #endif

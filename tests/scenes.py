@@ -228,8 +228,30 @@ def transparent_scene(seed=0) -> SceneDesc:
     return SceneDesc(models, lights_mixed(rng), CameraDesc(), WorldDesc(), name="transparent")
 
 
+def max_light_count_scene(seed=0, n_lights=7, max_count=3, focus=False) -> SceneDesc:
+    """Camera.MaxLightCount (camera.go:1474-1497): more visible lights than the cap, two ambient lights (the world's
+    and one in the tree: the comparator is inconsistent for them), a sun, point lights at scattered distances."""
+    rng = np.random.default_rng(seed)
+    sc = soup_scene(seed, n_models=3, n_tris=300)
+    ls = []
+    for i in range(n_lights):
+        kind = LIGHT_POINT if i % 5 not in (1, 3) else (LIGHT_AMBIENT if i % 5 == 1 else LIGHT_DIRECTIONAL)
+        ls.append(LightDesc(kind, NodeDesc(position=tuple(float(x) for x in rng.uniform(-12, 12, 3)), rotation=random_rotation(rng)),
+                            color=tuple(float(x) for x in rng.uniform(0.2, 1, 3)), energy=float(rng.uniform(1, 5)),
+                            range=float(rng.uniform(6, 20)) if i % 2 else 0.0, name="ml%d" % i))
+    sc.lights = ls
+    sc.camera.max_light_count = max_count
+    if focus:
+        sc.camera.max_light_focus = NodeDesc(position=(4.0, 1.0, -3.0), name="focus")
+    sc.name = "maxlights%d" % seed
+    return sc
+
+
 ALL_SMALL = {
     "soup_lit": lambda: soup_scene(1),
+    "max_light_count": lambda: max_light_count_scene(51),
+    "max_light_count_focus": lambda: max_light_count_scene(52, n_lights=9, max_count=4, focus=True),
+    "max_light_count_many": lambda: max_light_count_scene(53, n_lights=47, max_count=6),
     "soup_unlit_colors": lambda: soup_scene(2, lit=False, colors=True),
     "soup_ranged": lambda: soup_scene(3, ranged=True),
     "soup_parent": lambda: soup_scene(4, parent=True),

@@ -114,3 +114,22 @@ def test_triangle_centers_formula():
 ])
 def test_bin_index(depth, mn, mx, mode, expected):
     assert O.bin_index(depth, mn, mx, mode) == expected
+
+
+def test_go_stable_sort_restatement_is_a_stable_sort():
+    """Camera.MaxLightCount sorts with sort.SliceStable and an inconsistent comparator (camera.go:1484-1495), so the
+    oracle restates Go's algorithm (insertion sort on blocks of 20 + SymMerge).  With a consistent comparator the
+    answer is unique: it must equal numpy's stable argsort for every size around the block boundaries."""
+    import ctypes
+    import numpy as np
+    from oracle import binding as O
+    lib = O.lib()
+    lib.orc_test_go_stable_sort.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
+    lib.orc_test_go_stable_sort.restype = None
+    rng = np.random.default_rng(7)
+    for n in list(range(0, 70)) + [79, 80, 81, 159, 160, 161, 500, 1000]:
+        for distinct in (3, 10, 10 ** 6):          # many ties -> stability matters
+            keys = rng.integers(0, distinct, n).astype(np.float32)
+            perm = np.zeros(max(n, 1), np.int32)
+            lib.orc_test_go_stable_sort(n, keys.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+            assert np.array_equal(perm[:n], np.argsort(keys, kind="stable")), (n, distinct)

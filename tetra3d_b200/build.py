@@ -158,7 +158,12 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
     cam.RenderDepth = bool(cam_d.render_depth)
     cam.RenderNormals = bool(cam_d.render_normals)
     cam.PerspectiveCorrectedTextureMapping = bool(cam_d.perspective_corrected_texture_mapping)
+    cam.MaxLightCount = int(cam_d.max_light_count)
     attach(cam, cam_d.node)
+    if cam_d.max_light_focus is not None:
+        focus = t3d.Node("max light count focus")
+        attach(focus, cam_d.max_light_focus)
+        cam.MaxLightCountFocusPoint = focus
     if device is not None:
         cam.Device = device
 

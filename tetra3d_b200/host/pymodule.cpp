@@ -274,6 +274,8 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("DepthMargin", &Camera::DepthMargin)
         .def_readwrite("Device", &Camera::device)
         .def_readwrite("DownloadResults", &Camera::downloadResults)
+        .def_readwrite("MaxLightCount", &Camera::MaxLightCount)
+        .def_readwrite("MaxLightCountFocusPoint", &Camera::MaxLightCountFocusPoint)
         .def("SetFieldOfView", [](Camera& c, float f) { c.fieldOfView = f; })
         .def("SetNear", [](Camera& c, float v) { c.near_ = v; })
         .def("SetFar", [](Camera& c, float v) { c.far_ = v; })

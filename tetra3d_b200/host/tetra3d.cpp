@@ -371,6 +371,63 @@ void Camera::RenderNodes(Scene& scene, Node& root) {                      // cam
 namespace {
 struct renderPair { Model* model; int part; float depth; int order; };   // camera.go:1249-1254
 
+// sort.SliceStable as Go's package sort implements it (zsortfunc.go: stable_func, insertionSort_func, symMerge_func,
+// rotate_func, swapRange_func): insertion sort on blocks of 20, then bottom-up SymMerge.  The exact sequence of
+// less / swap calls matters when the comparator is inconsistent (Camera.MaxLightCount, camera.go:1484-1495).
+template <class Less, class Swap> void goInsertionSort(int a, int b, Less& less, Swap& swap) {
+    for (int i = a + 1; i < b; i++)
+        for (int j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
+}
+template <class Swap> void goSwapRange(int a, int b, int n, Swap& swap) { for (int i = 0; i < n; i++) swap(a + i, b + i); }
+template <class Swap> void goRotate(int a, int m, int b, Swap& swap) {
+    int i = m - a, j = b - m;
+    while (i != j) {
+        if (i > j) { goSwapRange(m - i, m, j, swap); i -= j; }
+        else { goSwapRange(m - i, m + j - i, i, swap); j -= i; }
+    }
+    goSwapRange(m - i, m, i, swap);
+}
+template <class Less, class Swap> void goSymMerge(int a, int m, int b, Less& less, Swap& swap) {
+    if (m - a == 1) {
+        int i = m, j = b;
+        while (i < j) { const int h = (int)(((unsigned)i + (unsigned)j) >> 1); if (less(h, a)) i = h + 1; else j = h; }
+        for (int k = a; k < i - 1; k++) swap(k, k + 1);
+        return;
+    }
+    if (b - m == 1) {
+        int i = a, j = m;
+        while (i < j) { const int h = (int)(((unsigned)i + (unsigned)j) >> 1); if (!less(m, h)) i = h + 1; else j = h; }
+        for (int k = m; k > i; k--) swap(k, k - 1);
+        return;
+    }
+    const int mid = (int)(((unsigned)a + (unsigned)b) >> 1);
+    const int n = mid + m;
+    int start, r;
+    if (m > mid) { start = n - b; r = mid; } else { start = a; r = m; }
+    const int p = n - 1;
+    while (start < r) {
+        const int c = (int)(((unsigned)start + (unsigned)r) >> 1);
+        if (!less(p - c, c)) start = c + 1; else r = c;
+    }
+    const int end = n - start;
+    if (start < m && m < end) goRotate(start, m, end, swap);
+    if (a < start && start < mid) goSymMerge(a, start, mid, less, swap);
+    if (mid < end && end < b) goSymMerge(mid, end, b, less, swap);
+}
+template <class Less, class Swap> void goStableSort(int n, Less less, Swap swap) {
+    int blockSize = 20;
+    int a = 0, b = blockSize;
+    while (b <= n) { goInsertionSort(a, b, less, swap); a = b; b += blockSize; }
+    goInsertionSort(a, n, less, swap);
+    while (blockSize < n) {
+        a = 0; b = 2 * blockSize;
+        while (b <= n) { goSymMerge(a, a + blockSize, b, less, swap); a = b; b += 2 * blockSize; }
+        const int m = a + blockSize;
+        if (m < n) goSymMerge(a, m, n, less, swap);
+        blockSize *= 2;
+    }
+}
+
 template <class T, class Less> void stableSort(std::vector<T>& v, Less less) { std::stable_sort(v.begin(), v.end(), less); }
 
 t3d_light toLight(GeometryDevice& dev, ILight* l) {
@@ -426,6 +483,22 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     for (ILight* l : lights) {
         debugInfo.lightCount++;
         if ((!world || world->LightingOn) && l->IsVisible()) sceneLights.push_back(l);
+    }
+    if (MaxLightCount > 0) {                                               // camera.go:1474-1497
+        const Vector3 pos = MaxLightCountFocusPoint ? MaxLightCountFocusPoint->WorldPosition() : WorldPosition();
+        // The reference's comparator is not a strict weak ordering (every ambient light sorts before every other one,
+        // itself included), so std::stable_sort may not be used: goStableSort replays Go's sort.SliceStable.
+        goStableSort((int)sceneLights.size(),
+                     [&](int i, int j) {
+                         const NodeType ti = sceneLights[i]->Type(), tj = sceneLights[j]->Type();
+                         if (ti == NodeType::AmbientLight) return true;
+                         else if (tj == NodeType::AmbientLight) return false;
+                         else if (ti == NodeType::DirectionalLight) return true;
+                         else if (tj == NodeType::DirectionalLight) return false;
+                         return v3_dist2(pos, sceneLights[i]->WorldPosition()) < v3_dist2(pos, sceneLights[j]->WorldPosition());
+                     },
+                     [&](int i, int j) { std::swap(sceneLights[i], sceneLights[j]); });
+        if ((size_t)MaxLightCount < sceneLights.size()) sceneLights.resize((size_t)MaxLightCount);
     }
     for (ILight* l : sceneLights) if (world && world->LightingOn && l->IsVisible()) debugInfo.activeLightCount++;   // camera.go:1499-1505
 

@@ -235,6 +235,8 @@ struct FlushRecord { Model* model; int part; uint64_t firstVertex; uint32_t vert
 
 struct Camera : Node {
     bool RenderDepth = true, RenderNormals = false, PerspectiveCorrectedTextureMapping = false;
+    int MaxLightCount = 0;                              // camera.go:223: 0 = every light
+    std::shared_ptr<Node> MaxLightCountFocusPoint;      // camera.go:226: nullptr = the camera
     float VertexSnapping = 0, DepthMargin = 0.04f;
     float near_ = 0.1f, far_ = 100, fieldOfView = 60, orthoScale = 20;
     bool perspective = true;

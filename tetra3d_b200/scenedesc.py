@@ -167,6 +167,8 @@ class CameraDesc:
     render_depth: bool = True
     render_normals: bool = False
     perspective_corrected_texture_mapping: bool = False
+    max_light_count: int = 0                        # Camera.MaxLightCount (camera.go:1474); 0 = unlimited
+    max_light_focus: Optional["NodeDesc"] = None    # Camera.MaxLightCountFocusPoint; None = the camera itself
 
 
 @dataclass
