@@ -6,6 +6,7 @@ import scenes
 from compare import assert_parity, render_gpu, bits
 from oracle import binding as O
 from tetra3d_b200 import workloads as W
+from tetra3d_b200.scenedesc import CameraDesc, ModelDesc, NodeDesc, SceneDesc, WorldDesc
 
 pytestmark = pytest.mark.gpu
 
@@ -46,6 +47,17 @@ def test_tile_boundaries_parity(device):
     # one-draw tiles, draws spanning 2..9 tiles, all in one frame
     assert_parity(scenes.tile_boundary_scene(31), device)
     assert_parity(scenes.tile_boundary_scene(32, sizes=(1024,) * 3 + (1,) * 40 + (4097, 2, 2, 1030)), device, check_capture=False)
+
+
+def test_more_than_one_scan_chunk_parity(device):
+    """More than 4096 triangle tiles in a frame with large (> 8192-triangle) draws: the tile scan runs as its own
+    multi-block kernel and the emit adds the earlier chunks' totals.  480 instances of a 9000-triangle soup."""
+    rng = np.random.default_rng(61)
+    mesh = scenes.random_soup(9000, 61, n_parts=1, extent=3.0)
+    models = [ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-10, 10, 3)), rotation=scenes.random_rotation(rng)),
+                        frustum_culling=False, name="big%d" % i) for i in range(480)]
+    sc = SceneDesc(models, scenes.lights_mixed(rng), CameraDesc(node=NodeDesc(position=(0.0, 2.0, 30.0))), WorldDesc(), name="chunks")
+    assert_parity(sc, device, check_capture=False)
 
 
 def test_many_tiny_draws_parity(device):
