@@ -393,7 +393,7 @@ __device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4
 
 // Tunables (see profiles/README.md for the measurements behind the defaults).
 #ifndef T3D_K1_MINBLOCKS
-#define T3D_K1_MINBLOCKS 5      // resident blocks per SM the register allocation aims for
+#define T3D_K1_MINBLOCKS 4      // resident blocks per SM the generic kernel's register allocation aims for
 #endif
 static const int VERTEX_BLOCK = 256;
 static const int VERTEX_SMEM_LIGHTS = 16;       // light lists up to this long are staged in shared memory
@@ -415,19 +415,22 @@ struct UniformsShared {
 };
 
 // One vertex: shape keys, skinning, clip transform, optional outputs, lighting.  P / N arrive loaded.
-template <class Uniforms>
+// FAST: the draw is static, has no shape keys, no unbillboarded depth and no volume light, and the frame has no
+// vertex snapping and no normal pass -- the rare paths are compiled out, which frees a quarter of the registers
+// (k_vertex<true> runs 6 blocks per SM without spilling where the generic kernel runs 5 and spills).
+template <bool FAST, class Uniforms>
 __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const Uniforms U, const FrameConst& fc,
                                              const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
                                              const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
                                              float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    const bool skinned = flags & T3D_DRAW_SKINNED;
+    const bool skinned = !FAST && (flags & T3D_DRAW_SKINNED);
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
     const bool needN = lit || skinned;
     const uint32_t vs = R.vstride;
 
     // shape keys (mesh.go:796-822)
-    for (uint32_t k = 0; k < R.nKeys; k++) {
+    for (uint32_t k = 0; !FAST && k < R.nKeys; k++) {
         const float w = __ldg(&R.keyW[k]);
         const float* kp = R.keyPos + (size_t)k * 3 * vs + mv;
         P.X += __ldg(kp) * w; P.Y += __ldg(kp + vs) * w; P.Z += __ldg(kp + 2 * (size_t)vs) * w;
@@ -438,7 +441,7 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
     }
 
     // skinning (model.go:760-775): positions and normals become world-space
-    if (skinned) {
+    if (!FAST && skinned) {
         const float4 w = ldg4(R.wgt + 4 * (size_t)mv);
         const ushort4 j = __ldg(reinterpret_cast<const ushort4*>(R.jnt + 4 * (size_t)mv));
         const int n = R.ninf ? (int)__ldg(R.ninf + mv) : 4;
@@ -465,7 +468,7 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
         c.y = m0.y * P.X + m1.y * P.Y + m2.y * P.Z + m3.y;
         c.z = m0.z * P.X + m1.z * P.Y + m2.z * P.Z + m3.z;
         c.w = m0.w * P.X + m1.w * P.Y + m2.w * P.Z + m3.w;
-        if (snap > 0) {                                                 // model.go:807-812
+        if (!FAST && snap > 0) {                                        // model.go:807-812
             c.x = roundf(c.x * snap) / snap;
             c.y = roundf(c.y * snap) / snap;
             c.z = roundf(c.z * snap) / snap;
@@ -477,11 +480,11 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
         if (wc < 0) wc = 0.000001f;
         clipOut[slot] = make_float4(c.x / wc, c.y / wc, c.z, c.w);
         clipXY[slot] = make_float2(c.x, c.y);
-        if (!skinned && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) {       // model.go:800-803
+        if (!FAST && !skinned && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) {   // model.go:800-803
             const float4 u = ldg4(R.unbill);
             unbillOut[slot] = u.x * P.X + u.y * P.Y + u.z * P.Z + u.w;
         }
-        if (fc.camFlags & T3D_CAM_RENDER_NORMALS) {                     // model.go:814-818 (uses vert)
+        if (!FAST && (fc.camFlags & T3D_CAM_RENDER_NORMALS)) {          // model.go:814-818 (uses vert)
             const float4 c0 = ldg4(R.nrmRot), c1 = ldg4(R.nrmRot + 4), c2 = ldg4(R.nrmRot + 8);
             float4 t;
             t.x = c0.x * P.X + c0.y * P.Y + c0.z * P.Z + c0.w;
@@ -540,7 +543,7 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
             lb += cB * diffuseFactor * energy;
         } else if (type == T3D_LIGHT_AMBIENT) {                         // light.go:110-120
             lr += cR * energy; lg += cG * energy; lb += cB * energy;
-        } else if (type == T3D_LIGHT_VOLUME) {
+        } else if (!FAST && type == T3D_LIGHT_VOLUME) {
             // a vertex outside the volume adds nothing (x + 0 keeps x: the sums are never -0)
             const float3 add = light_volume(&R, lightsU + R.lightU + li, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned);
             lr += add.x; lg += add.y; lb += add.z;
@@ -549,24 +552,27 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
     lightOut[slot] = make_float4(lr, lg, lb, 1.0f);
 }
 
-// One vertex per thread, VERTEX_BLOCK consecutive slots per block.  When the block lies inside one draw (any
-// draw of more than a few hundred vertices) the draw's matrices and light list are staged in shared memory
-// once; blocks that straddle draws look their draw up per vertex.
-__global__ void __launch_bounds__(VERTEX_BLOCK, T3D_K1_MINBLOCKS)
-k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
-         uint32_t totalV, const __grid_constant__ FrameConst fc,
+// One vertex per thread, VERTEX_BLOCK consecutive slots per block; blockIdx indexes a list of vertex tiles.  The
+// host sorts the frame's tiles into two lists: tiles whose draws are all FAST (see shade_vertex) go to
+// k_vertex<true>, everything else to k_vertex<false>.  When the block lies inside one draw (any draw of more than
+// a few hundred vertices) the draw's matrices and light list are staged in shared memory once; blocks that
+// straddle draws look their draw up per vertex.
+#ifndef T3D_K1_FAST_MINBLOCKS
+#define T3D_K1_FAST_MINBLOCKS 6
+#endif
+template <bool FAST>
+__device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
+         const uint32_t* __restrict__ tileFirst, const uint32_t* __restrict__ tileList, uint32_t totalV, const FrameConst& fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
-    pdl_wait();             // everything below reads what k_prep_draws wrote
-    pdl_launch();
-    const uint32_t base = blockIdx.x * (uint32_t)VERTEX_BLOCK;
+    const uint32_t tile = __ldg(&tileList[blockIdx.x]);
+    const uint32_t base = tile * (uint32_t)VERTEX_BLOCK;
     const uint32_t slot = base + threadIdx.x;
-    const uint32_t dLo = __ldg(&tileFirst[blockIdx.x]), dHi = __ldg(&tileFirst[blockIdx.x + 1]);
+    const uint32_t dLo = __ldg(&tileFirst[tile]), dHi = __ldg(&tileFirst[tile + 1]);
     const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
-    // dHi is the draw of the first slot of the NEXT block, so dLo == dHi covers this whole block; otherwise the
-    // block is still uniform when the next draw starts at or after its end
+    // dHi is the draw of the first slot of the NEXT tile, so dLo == dHi covers this whole tile; otherwise the
+    // tile is still uniform when the next draw starts at or after its end
     bool staged = dLo == dHi || __ldg(&vbase[dLo + 1]) >= end;
     if (staged) {
         const DrawRec& R = draws[dLo];
@@ -592,7 +598,7 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
             __syncthreads();
             if (slot >= end) return;
             UniformsShared U; U.s = sU;
-            shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+            shade_vertex<FAST>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
             return;
         }
     }
@@ -610,7 +616,25 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
     }
     UniformsGlobal U;
     U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
-    shade_vertex(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+    shade_vertex<FAST>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+}
+
+// `second`: this launch directly follows the other k_vertex launch of the frame.  The two are independent (disjoint
+// tiles) and both only need k_prep_draws, which has completed by the time a second launch's blocks can start (the
+// first launch's blocks call pdl_launch() after their own pdl_wait()).  So the second launch starts shading at
+// once and waits for the first one at its END, which keeps "this kernel complete => every earlier kernel complete".
+template <bool FAST>
+__global__ void __launch_bounds__(VERTEX_BLOCK, FAST ? T3D_K1_FAST_MINBLOCKS : T3D_K1_MINBLOCKS)
+k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
+         const uint32_t* __restrict__ tileList, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
+         const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
+         float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
+         float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
+    __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
+    if (!second) pdl_wait();        // everything below reads what k_prep_draws wrote
+    pdl_launch();
+    vertex_tile<FAST>(sU, draws, vbase, tileFirst, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+    if (second) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1224,11 +1248,17 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
+                   const uint32_t* fastTiles, uint32_t nFast, const uint32_t* genericTiles, uint32_t nGeneric,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
-    if (!totalV) return;
-    launch_kernel(k_vertex, cdiv(totalV, VERTEX_BLOCK), VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, totalV, fc, lightsU, bones, vols,
-                  clip, clipXY, light, wpos, unbill, tnrm);
+    // the two launches write disjoint slots; both wait for k_prep_draws (the second transitively, through the first)
+    // (`second` needs the dependent-launch chain; with stage events between kernels both launches wait at the top)
+    if (nFast)
+        launch_kernel(k_vertex<true>, nFast, VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, fastTiles, totalV, 0u, fc, lightsU, bones, vols,
+                      clip, clipXY, light, wpos, unbill, tnrm);
+    if (nGeneric)
+        launch_kernel(k_vertex<false>, nGeneric, VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, genericTiles, totalV, (nFast && pdl) ? 1u : 0u, fc,
+                      lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
 }
 
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
