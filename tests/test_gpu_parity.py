@@ -60,6 +60,12 @@ def test_more_than_one_scan_chunk_parity(device):
     assert_parity(sc, device, check_capture=False)
 
 
+def test_huge_draw_parity(device):
+    # one MeshPart of more than 64 tiles (66 000 triangles): its histogram scan runs in k_hist_scan_huge; next to it a
+    # large draw below that limit and a packed one
+    assert_parity(scenes.tile_boundary_scene(35, sizes=(66000, 9000, 300, 131073)), device, check_capture=False)
+
+
 def test_many_tiny_draws_parity(device):
     # > 1024 draws of one or two triangles: packed tiles are cut by the draw-count limit, not by triangles
     sc = scenes.tile_boundary_scene(33, sizes=(1, 2) * 700)

@@ -98,7 +98,7 @@ struct t3d_ctx {
     PinVec<DrawSlim> hSlim;
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
-    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVFast, hVGeneric;
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVFast, hVGeneric, hHuge;
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
     PinVec<float> hBones;
@@ -113,7 +113,7 @@ struct t3d_ctx {
     PinVec<uint8_t> hFrame;
     void* hFrameDev = nullptr; void* pDevRest = nullptr;
     size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0;
-    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVFast = nullptr, *pVGeneric = nullptr;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVFast = nullptr, *pVGeneric = nullptr, *pHuge = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
@@ -212,7 +212,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
-    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hVFast.release(); ctx->hVGeneric.release(); ctx->hTiles.release();
+    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hVFast.release(); ctx->hVGeneric.release(); ctx->hHuge.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
@@ -559,7 +559,7 @@ static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, 
 // exclusive tiles and go through k_cull_large + the segmented counting sort; smaller draws are packed whole
 // into tiles of at most TILE_TRIS triangles and TILE_TRIS draws and are culled and sorted by k_tile_packed.
 static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
-    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear(); ctx->hMedium.clear();
+    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear(); ctx->hMedium.clear(); ctx->hHuge.clear();
     const uint32_t* tb = ctx->hTbase.p;
     TriTile cur; memset(&cur, 0, sizeof cur);
     cudaError_t e = cudaSuccess;
@@ -582,6 +582,7 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
             const uint32_t n = (nt + TILE_TRIS - 1) / TILE_TRIS;
             const bool medium = nt <= MEDIUM_TRIS;      // one block culls and sorts the whole draw (k_draw_medium)
             if (medium && (e = ctx->hMedium.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
+            if (n > HUGE_TILES && (e = ctx->hHuge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
             for (uint32_t j = 0; j < n; j++) {
                 TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
                 t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws[d].sortMode; t.tbase = tb[d];
@@ -677,12 +678,13 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         struct Seg { const void* src; size_t bytes; size_t off; };
         Seg head[3] = {{ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
-        Seg segs[11] = {
+        Seg segs[12] = {
             {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0},
-            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVFast.p, 4ull * ctx->hVFast.n, 0}, {ctx->hVGeneric.p, 4ull * ctx->hVGeneric.n, 0}};
+            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVFast.p, 4ull * ctx->hVFast.n, 0}, {ctx->hVGeneric.p, 4ull * ctx->hVGeneric.n, 0},
+            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}};
         size_t headBytes = 0, restBytes = 0;
         for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
         for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
@@ -711,6 +713,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pMedium = reinterpret_cast<uint32_t*>(rest + segs[8].off);
         ctx->pVFast = reinterpret_cast<uint32_t*>(rest + segs[9].off);
         ctx->pVGeneric = reinterpret_cast<uint32_t*>(rest + segs[10].off);
+        ctx->pHuge = reinterpret_cast<uint32_t*>(rest + segs[11].off);
         ctx->h2dBytes = 0;
         for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
@@ -769,8 +772,9 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     if (nLarge) {       // the tile scan rides along as k_bin_hist's extra block
         launch_bin_hist(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, scanRides ? nTiles : 0xFFFFFFFFu, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(),
                         ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+        launch_hist_scan_huge(s, pdl, ctx->pTiles, ctx->pHuge, (uint32_t)ctx->hHuge.n, ctx->dHist.as<uint32_t>());
         launch_scatter(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
-        ctx->launches += 2;
+        ctx->launches += 2 + (ctx->hHuge.n ? 1 : 0);
     } else {
         launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
         ctx->launches += 1;

@@ -149,6 +149,7 @@ struct __align__(16) TriTile {
     uint32_t tbase;             // first arena slot of the draw
 };
 static const uint32_t TILE_TRIS = 1024;
+static const uint32_t HUGE_TILES = 64;          // draws of more tiles than this get their histogram scan from k_hist_scan_huge
 static const uint32_t SCAN_CHUNK = 4096;        // tiles per block of the tile scan (t3d_sort.cu)
 static const uint32_t MEDIUM_TRIS = 8192;       // draws of (TILE_TRIS, MEDIUM_TRIS] triangles are culled and sorted by one block
 static const uint32_t TILE_LARGE = 0x80000000u;

@@ -45,6 +45,7 @@ static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex blo
 // t3d_sort.cu -- segmented 512-bin counting sort for draws that span several tiles
 void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge, uint32_t nTiles,
                      DrawStat* stats, uint32_t* tdepth, uint32_t* hist, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum);
+void launch_hist_scan_huge(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* hugeList, uint32_t nHuge, uint32_t* hist);
 void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                     const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted);
 void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,

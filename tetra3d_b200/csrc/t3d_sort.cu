@@ -126,6 +126,7 @@ k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ large
     // thread owns bins 2*tid, 2*tid+1 from here on (block scans then run in bin order)
     uint2* myRow = reinterpret_cast<uint2*>(hist + (size_t)(T.row0 + j) * BIN_COUNT);
     myRow[threadIdx.x] = make_uint2(sHist[2 * threadIdx.x], sHist[2 * threadIdx.x + 1]);
+    if (T.nTilesOfDraw > HUGE_TILES) return;            // k_hist_scan_huge turns this draw's counts into offsets
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) sLast = (atomicAdd(&stats[d].done, 1u) == T.nTilesOfDraw - 1) ? 1u : 0u;
@@ -152,6 +153,59 @@ k_bin_hist(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ large
     rows[(size_t)nT * (BIN_COUNT / 2) + threadIdx.x] = make_uint2(base, base + run.x);
 }
 
+// Draws of more than HUGE_TILES tiles: sixteen blocks per draw, each owning 32 of the 512 bins (a 128-byte column of
+// the draw's [tiles x 512] counts), turn the counts into per-tile offsets.  Warp w owns a contiguous run of the
+// draw's tiles, lane l one bin: per-run sums, an exclusive scan of the 8 run sums per bin in shared memory, then a
+// second sweep writes offset(tile, bin) = earlier runs + earlier tiles of this run.  The base row receives the bin
+// TOTALS; k_scatter scans them itself (512 values).  (For a draw of 1 M triangles the last tile's serial scan in
+// k_bin_hist would be a 45 us tail.)
+static const int HUGE_GROUPS = BIN_COUNT / 32;
+__global__ void __launch_bounds__(SORT_THREADS)
+k_hist_scan_huge(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ hugeList, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sSeg[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    pdl_launch();
+    const TriTile T = tiles[__ldg(&hugeList[blockIdx.x / HUGE_GROUPS])];
+    const uint32_t nT = T.nTilesOfDraw;
+    uint32_t* col = hist + (size_t)T.row0 * BIN_COUNT + (blockIdx.x % HUGE_GROUPS) * 32 + lane;    // this lane's bin in row 0
+    const uint32_t per = (nT + 7) / 8;
+    const uint32_t t0 = min(warp * per, nT), t1 = min(t0 + per, nT);
+    uint32_t sum = 0;
+    {
+        uint32_t t = t0;
+        for (; t + 8 <= t1; t += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + (size_t)(t + u) * BIN_COUNT);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum += v[u];
+        }
+        for (; t < t1; t++) sum += __ldcg(col + (size_t)t * BIN_COUNT);
+    }
+    sSeg[warp][lane] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t c = sSeg[w][lane]; sSeg[w][lane] = run; run += c; }
+        col[(size_t)nT * BIN_COUNT] = run;              // base row: the bin total
+    }
+    __syncthreads();
+    uint32_t run = sSeg[warp][lane];
+    {
+        uint32_t t = t0;
+        for (; t + 8 <= t1; t += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + (size_t)(t + u) * BIN_COUNT);
+#pragma unroll
+            for (int u = 0; u < 8; u++) { col[(size_t)(t + u) * BIN_COUNT] = run; run += v[u]; }
+        }
+        for (; t < t1; t++) { const uint32_t v = __ldcg(col + (size_t)t * BIN_COUNT); col[(size_t)t * BIN_COUNT] = run; run += v; }
+    }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
           const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ hist, uint32_t* __restrict__ sorted) {
@@ -161,6 +215,7 @@ k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeL
     // prefix over warps.
     __shared__ __align__(16) uint16_t sCnt[8][BIN_COUNT];
     __shared__ uint32_t sBase[BIN_COUNT];
+    __shared__ uint32_t sWarp[8];
     const unsigned full = 0xFFFFFFFFu;
     const TriTile T = tiles[__ldg(&largeList[blockIdx.x])];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,10 +235,18 @@ k_scatter(const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeL
     {
         const uint32_t* offRow = hist + (size_t)(T.row0 + (T.info & ~TILE_LARGE)) * BIN_COUNT;
         const uint32_t* baseRow = hist + (size_t)(T.row0 + T.nTilesOfDraw) * BIN_COUNT;
+        if (T.nTilesOfDraw > HUGE_TILES) {              // the base row holds bin totals (k_hist_scan_huge): scan them here
+            const uint2 c = __ldg(reinterpret_cast<const uint2*>(baseRow) + threadIdx.x);
+            const uint2 o = __ldg(reinterpret_cast<const uint2*>(offRow) + threadIdx.x);
+            const uint32_t base = block_exclusive_scan_256(c.x + c.y, sWarp, nullptr);
+            sBase[2 * threadIdx.x] = T.tbase + o.x + base;
+            sBase[2 * threadIdx.x + 1] = T.tbase + o.y + base + c.x;
+        } else {
 #pragma unroll
-        for (int q = 0; q < BINS_PER_THREAD; q++) {
-            const uint32_t b = threadIdx.x + q * SORT_THREADS;
-            sBase[b] = T.tbase + __ldg(&offRow[b]) + __ldg(&baseRow[b]);
+            for (int q = 0; q < BINS_PER_THREAD; q++) {
+                const uint32_t b = threadIdx.x + q * SORT_THREADS;
+                sBase[b] = T.tbase + __ldg(&offRow[b]) + __ldg(&baseRow[b]);
+            }
         }
     }
     __syncthreads();
@@ -222,6 +285,11 @@ void launch_bin_hist(cudaStream_t s, bool pdl, const TriTile* tiles, const uint3
                      DrawStat* stats, uint32_t* tdepth, uint32_t* hist, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum) {
     if (!nLarge) return;
     launch_kernel(k_bin_hist, nLarge + (nTiles != 0xFFFFFFFFu ? 1 : 0), SORT_THREADS, 0, s, pdl, tiles, largeList, nLarge, nTiles, stats, tdepth, hist, tileSurv, tileOut, chunkSum);
+}
+
+void launch_hist_scan_huge(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* hugeList, uint32_t nHuge, uint32_t* hist) {
+    if (!nHuge) return;
+    launch_kernel(k_hist_scan_huge, nHuge * HUGE_GROUPS, SORT_THREADS, 0, s, pdl, tiles, hugeList, hist);
 }
 
 void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,

@@ -234,9 +234,9 @@ def stress_scene(lit: bool = False) -> SceneDesc:
     return SceneDesc(models, lights, cam, WorldDesc(), name="stress")
 
 
-def million_triangle_scene(nx: int = 1000, nz: int = 500) -> SceneDesc:
+def million_triangle_scene(nx: int = 1000, nz: int = 500, rows_per_part: int = 10) -> SceneDesc:
     """configs[1]: 1M-triangle static mesh in 50 MeshParts, 4 point lights + 1 directional, backface cull + depth sort."""
-    mesh = grid_mesh(nx, nz, rows_per_part=10, seed=1, material=MaterialDesc(backface_culling=True, triangle_sort_mode=0))
+    mesh = grid_mesh(nx, nz, rows_per_part=rows_per_part, seed=1, material=MaterialDesc(backface_culling=True, triangle_sort_mode=0))
     pitch = rotation_matrix((1, 0, 0), math.radians(-20))
     cam = CameraDesc(node=NodeDesc(position=(0.0, 15.0, 40.0), rotation=pitch), far=200.0)
     sx = 50.0 * nx / 1000.0; sz = 25.0 * nz / 500.0
@@ -313,6 +313,7 @@ WORKLOADS = {
     "instanced": instanced_scene,
     # reduced variants for exploration (not BASELINE configs): one GPU's share of configs[4] at 8 GPUs, and a
     # tenth of configs[3]
+    "million_one_part": lambda: million_triangle_scene(rows_per_part=500),      # the same mesh as ONE 1 M-triangle MeshPart
     "instanced_shard": lambda: instanced_scene(n=2442),
     "particles_200k": lambda: particles_scene(n=200000),
     "skinned_crowd_1k": lambda: skinned_crowd_scene(n=1000),
