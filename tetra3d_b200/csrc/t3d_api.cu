@@ -567,7 +567,15 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
     auto close = [&]() -> cudaError_t {
         if (cur.info == 0) return cudaSuccess;
         if (cur.count) {        // a tile of empty draws has nothing to do
-            cudaError_t e2 = ctx->hPacked.push((uint32_t)ctx->hTiles.n);
+            cudaError_t e2;
+            if (cur.info == 1) {
+                // a draw alone in its tile needs none of the packed kernel's per-slot draw lookup: k_draw_medium takes it
+                // (half the time per triangle), and the tile scan / emit see a one-tile "large" draw
+                cur.info = TILE_LARGE; cur.row0 = 0; cur.nTilesOfDraw = 1; cur.sortMode = ctx->hDraws[cur.dFirst].sortMode; cur.tbase = cur.start;
+                e2 = ctx->hMedium.push((uint32_t)ctx->hTiles.n);
+            } else {
+                e2 = ctx->hPacked.push((uint32_t)ctx->hTiles.n);
+            }
             if (e2 != cudaSuccess) return e2;
             e2 = ctx->hTiles.push(cur);
             if (e2 != cudaSuccess) return e2;
