@@ -93,12 +93,12 @@ struct t3d_ctx {
     bool stageTimings = false, stagesTimed = false;
     FrameConst fc;
     // what the host itself needs to remember about a submitted draw (the device rebuilds the full DrawRec from hSlim + hTmpl)
-    struct HostDraw { uint32_t a0, nv, vbase, nt, flags; uint8_t sortMode; uint8_t fast; /* eligible for k_vertex<true> */ };
+    struct HostDraw { uint32_t a0, nv, vbase, nt, flags; uint8_t sortMode; uint8_t vclass; /* k_vertex instantiation it is eligible for: 0 generic, 1 static fast, 2 skinned fast */ };
     std::vector<HostDraw> hDraws;
     PinVec<DrawSlim> hSlim;
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
-    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVFast, hVGeneric, hHuge;
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVClass[3], hHuge;       // hVClass: vertex tiles by class (0 generic, 1 static fast, 2 skinned fast)
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
     PinVec<float> hBones;
@@ -113,7 +113,7 @@ struct t3d_ctx {
     PinVec<uint8_t> hFrame;
     void* hFrameDev = nullptr; void* pDevRest = nullptr;
     size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0;
-    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVFast = nullptr, *pVGeneric = nullptr, *pHuge = nullptr;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVClass[3] = {nullptr, nullptr, nullptr}, *pHuge = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
@@ -212,7 +212,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
-    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); ctx->hVFast.release(); ctx->hVGeneric.release(); ctx->hHuge.release(); ctx->hTiles.release();
+    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
@@ -531,14 +531,14 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             }
             CU(ctx->hSlim.push(S));
         }
-        // k_vertex<true> (t3d_kernels.cu: shade_vertex<FAST>): static, no shape keys, no unbillboarded depth, a light list
-        // it can stage and that holds no volume light
-        bool fast = !(flags & (T3D_DRAW_SKINNED | T3D_DRAW_DEPTH_UNBILLBOARDED)) && m.nKeys == 0;
+        // k_vertex<K1_STATIC / K1_SKINNED> (t3d_kernels.cu: shade_vertex): no shape keys, no unbillboarded depth (ignored for
+        // skinned draws anyway), a light list the kernel can stage and that holds no volume light
+        bool fast = m.nKeys == 0 && ((flags & T3D_DRAW_SKINNED) || !(flags & T3D_DRAW_DEPTH_UNBILLBOARDED));
         if (fast && (flags & T3D_DRAW_LIT)) {
             fast = ll.count <= VERTEX_FAST_MAX_LIGHTS;
             for (uint32_t k = 0; k < ll.count && fast; k++) fast = ctx->hLights.p[ll.off + k].type != T3D_LIGHT_VOLUME;
         }
-        ctx->hDraws.push_back(t3d_ctx::HostDraw{R.a0, R.nv, R.vbase, R.nt, R.flags, R.sortMode, (uint8_t)fast});
+        ctx->hDraws.push_back(t3d_ctx::HostDraw{R.a0, R.nv, R.vbase, R.nt, R.flags, R.sortMode, (uint8_t)(!fast ? 0 : (flags & T3D_DRAW_SKINNED) ? 2 : 1)});
         ctx->drawTotalTris.push_back(R.nt);
         ctx->drawContinue.push_back((flags & T3D_DRAW_CONTINUE_FLUSH) ? 1 : 0);
     }
@@ -627,16 +627,19 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     ctx->hTbase.p[nDraws] = totalT; ctx->hTbase.n = nDraws + 1;
     CU(ctx->hTileV.resize(nTilesV + 1));
     build_tiles(ctx->hVbase.p, nDraws, nTilesV, VERTEX_TILE, ctx->hTileV.p);
-    {   // vertex tiles whose draws are all fast -> k_vertex<true>, the rest -> k_vertex<false>
+    {   // vertex tiles whose draws all belong to one fast class -> that k_vertex instantiation, the rest -> the generic one
         const bool frameFast = !(ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS) && !(ctx->fc.snapping > 0);
-        ctx->hVFast.clear(); ctx->hVGeneric.clear();
-        CU(ctx->hVFast.reserve(nTilesV)); CU(ctx->hVGeneric.reserve(nTilesV));
+        for (auto& v : ctx->hVClass) { v.clear(); CU(v.reserve(nTilesV)); }
         for (uint32_t b = 0; b < nTilesV; b++) {
             const uint64_t end = std::min<uint64_t>((uint64_t)(b + 1) * VERTEX_TILE, totalV);
-            bool fast = frameFast;
-            for (uint32_t d = ctx->hTileV.p[b]; fast && d < nDraws && ctx->hVbase.p[d] < end; d++) fast = ctx->hDraws[d].fast || ctx->hVbase.p[d + 1] == ctx->hVbase.p[d];
-            if (fast) ctx->hVFast.p[ctx->hVFast.n++] = b;
-            else ctx->hVGeneric.p[ctx->hVGeneric.n++] = b;
+            int cls = -1;       // -1: no draw seen yet
+            for (uint32_t d = ctx->hTileV.p[b]; cls != 0 && d < nDraws && ctx->hVbase.p[d] < end; d++) {
+                if (ctx->hVbase.p[d + 1] == ctx->hVbase.p[d]) continue;        // a draw without vertices
+                const int c = frameFast ? ctx->hDraws[d].vclass : 0;
+                cls = (cls == -1 || cls == c) ? c : 0;
+            }
+            auto& list = ctx->hVClass[cls < 0 ? 0 : cls];
+            list.p[list.n++] = b;
         }
     }
     CU(build_tri_tiles(ctx, nDraws));
@@ -686,13 +689,13 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         struct Seg { const void* src; size_t bytes; size_t off; };
         Seg head[3] = {{ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
-        Seg segs[12] = {
+        Seg segs[13] = {
             {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0},
-            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVFast.p, 4ull * ctx->hVFast.n, 0}, {ctx->hVGeneric.p, 4ull * ctx->hVGeneric.n, 0},
-            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}};
+            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVClass[0].p, 4ull * ctx->hVClass[0].n, 0}, {ctx->hVClass[1].p, 4ull * ctx->hVClass[1].n, 0},
+            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 4ull * ctx->hVClass[2].n, 0}};
         size_t headBytes = 0, restBytes = 0;
         for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
         for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
@@ -719,9 +722,10 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pLightsIn = reinterpret_cast<t3d_light*>(rest + segs[6].off);
         ctx->pBones = reinterpret_cast<float*>(rest + segs[7].off);
         ctx->pMedium = reinterpret_cast<uint32_t*>(rest + segs[8].off);
-        ctx->pVFast = reinterpret_cast<uint32_t*>(rest + segs[9].off);
-        ctx->pVGeneric = reinterpret_cast<uint32_t*>(rest + segs[10].off);
+        ctx->pVClass[0] = reinterpret_cast<uint32_t*>(rest + segs[9].off);
+        ctx->pVClass[1] = reinterpret_cast<uint32_t*>(rest + segs[10].off);
         ctx->pHuge = reinterpret_cast<uint32_t*>(rest + segs[11].off);
+        ctx->pVClass[2] = reinterpret_cast<uint32_t*>(rest + segs[12].off);
         ctx->h2dBytes = 0;
         for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
@@ -756,10 +760,11 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win);
     }
     CU(mark(2));
-    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, ctx->pVFast, (uint32_t)ctx->hVFast.n, ctx->pVGeneric, (uint32_t)ctx->hVGeneric.n, totalV, ctx->fc,
+    const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};
+    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, ctx->pVClass, nVClass, totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
-    ctx->launches += 1 + (ctx->hVFast.n ? 1 : 0) + (ctx->hVGeneric.n ? 1 : 0);
+    ctx->launches += 1 + (nVClass[0] ? 1 : 0) + (nVClass[1] ? 1 : 0) + (nVClass[2] ? 1 : 0);
     CU(mark(3));
     // K2: cull (small draws are also sorted here)
     launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),

@@ -415,16 +415,19 @@ struct UniformsShared {
 };
 
 // One vertex: shape keys, skinning, clip transform, optional outputs, lighting.  P / N arrive loaded.
-// FAST: the draw is static, has no shape keys, no unbillboarded depth and no volume light, and the frame has no
-// vertex snapping and no normal pass -- the rare paths are compiled out, which frees a quarter of the registers
-// (k_vertex<true> runs 6 blocks per SM without spilling where the generic kernel runs 5 and spills).
-template <bool FAST, class Uniforms>
+// MODE K1_STATIC: the draw is static, has no shape keys, no unbillboarded depth and no volume light, and the frame has
+// no vertex snapping and no normal pass -- the rare paths are compiled out, which frees a quarter of the registers
+// (k_vertex<K1_STATIC> runs 6 blocks per SM without spilling where the generic kernel runs 4).  MODE K1_SKINNED: the
+// same exclusions for a skinned draw.  MODE K1_GENERIC: everything.
+enum { K1_GENERIC = 0, K1_STATIC = 1, K1_SKINNED = 2 };
+template <int MODE, class Uniforms>
 __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const Uniforms U, const FrameConst& fc,
                                              const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
                                              const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
                                              float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    const bool skinned = !FAST && (flags & T3D_DRAW_SKINNED);
+    constexpr bool FAST = MODE != K1_GENERIC;       // shape keys, snapping, unbillboarded depth, normal pass, volume lights compiled out
+    const bool skinned = MODE == K1_SKINNED || (MODE == K1_GENERIC && (flags & T3D_DRAW_SKINNED));
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
     const bool needN = lit || skinned;
     const uint32_t vs = R.vstride;
@@ -441,7 +444,7 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
     }
 
     // skinning (model.go:760-775): positions and normals become world-space
-    if (!FAST && skinned) {
+    if (MODE != K1_STATIC && skinned) {
         const float4 w = ldg4(R.wgt + 4 * (size_t)mv);
         const ushort4 j = __ldg(reinterpret_cast<const ushort4*>(R.jnt + 4 * (size_t)mv));
         const int n = R.ninf ? (int)__ldg(R.ninf + mv) : 4;
@@ -553,14 +556,17 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
 }
 
 // One vertex per thread, VERTEX_BLOCK consecutive slots per block; blockIdx indexes a list of vertex tiles.  The
-// host sorts the frame's tiles into two lists: tiles whose draws are all FAST (see shade_vertex) go to
-// k_vertex<true>, everything else to k_vertex<false>.  When the block lies inside one draw (any draw of more than
+// host sorts the frame's tiles into three lists: tiles whose draws are all of one fast class (see shade_vertex) go to
+// k_vertex<K1_STATIC> or k_vertex<K1_SKINNED>, everything else to k_vertex<K1_GENERIC>.  When the block lies inside one draw (any draw of more than
 // a few hundred vertices) the draw's matrices and light list are staged in shared memory once; blocks that
 // straddle draws look their draw up per vertex.
 #ifndef T3D_K1_FAST_MINBLOCKS
 #define T3D_K1_FAST_MINBLOCKS 6
 #endif
-template <bool FAST>
+#ifndef T3D_K1_SKINNED_MINBLOCKS
+#define T3D_K1_SKINNED_MINBLOCKS 5
+#endif
+template <int MODE>
 __device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
          const uint32_t* __restrict__ tileFirst, const uint32_t* __restrict__ tileList, uint32_t totalV, const FrameConst& fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
@@ -598,7 +604,7 @@ __device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restric
             __syncthreads();
             if (slot >= end) return;
             UniformsShared U; U.s = sU;
-            shade_vertex<FAST>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+            shade_vertex<MODE>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
             return;
         }
     }
@@ -616,15 +622,15 @@ __device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restric
     }
     UniformsGlobal U;
     U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
-    shade_vertex<FAST>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+    shade_vertex<MODE>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
 }
 
-// `second`: this launch directly follows the other k_vertex launch of the frame.  The two are independent (disjoint
-// tiles) and both only need k_prep_draws, which has completed by the time a second launch's blocks can start (the
-// first launch's blocks call pdl_launch() after their own pdl_wait()).  So the second launch starts shading at
-// once and waits for the first one at its END, which keeps "this kernel complete => every earlier kernel complete".
-template <bool FAST>
-__global__ void __launch_bounds__(VERTEX_BLOCK, FAST ? T3D_K1_FAST_MINBLOCKS : T3D_K1_MINBLOCKS)
+// `second`: this launch directly follows another k_vertex launch of the frame.  They are independent (disjoint
+// tiles) and all only need k_prep_draws, which has completed by the time a later launch's blocks can start (the
+// first launch's blocks call pdl_launch() after their own pdl_wait()).  So a later launch starts shading at
+// once and waits for its predecessor at its END, which keeps "this kernel complete => every earlier kernel complete".
+template <int MODE>
+__global__ void __launch_bounds__(VERTEX_BLOCK, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
 k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
          const uint32_t* __restrict__ tileList, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
@@ -633,7 +639,7 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, 
     __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
     if (!second) pdl_wait();        // everything below reads what k_prep_draws wrote
     pdl_launch();
-    vertex_tile<FAST>(sU, draws, vbase, tileFirst, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+    vertex_tile<MODE>(sU, draws, vbase, tileFirst, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
     if (second) pdl_wait();
 }
 
@@ -1248,17 +1254,25 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
-                   const uint32_t* fastTiles, uint32_t nFast, const uint32_t* genericTiles, uint32_t nGeneric,
+                   const uint32_t* const tileLists[3], const uint32_t nTilesOf[3],
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
-    // the two launches write disjoint slots; both wait for k_prep_draws (the second transitively, through the first)
-    // (`second` needs the dependent-launch chain; with stage events between kernels both launches wait at the top)
-    if (nFast)
-        launch_kernel(k_vertex<true>, nFast, VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, fastTiles, totalV, 0u, fc, lightsU, bones, vols,
-                      clip, clipXY, light, wpos, unbill, tnrm);
-    if (nGeneric)
-        launch_kernel(k_vertex<false>, nGeneric, VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, genericTiles, totalV, (nFast && pdl) ? 1u : 0u, fc,
+    // the launches write disjoint slots; every one after the first overlaps its predecessor and waits for it at its end
+    // (`second`; needs the dependent-launch chain: with stage events between kernels they all wait at the top)
+    bool first = true;
+    if (nTilesOf[K1_STATIC]) {
+        launch_kernel(k_vertex<K1_STATIC>, nTilesOf[K1_STATIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_STATIC], totalV, 0u, fc,
                       lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+        first = false;
+    }
+    if (nTilesOf[K1_SKINNED]) {
+        launch_kernel(k_vertex<K1_SKINNED>, nTilesOf[K1_SKINNED], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_SKINNED], totalV,
+                      (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+        first = false;
+    }
+    if (nTilesOf[K1_GENERIC])
+        launch_kernel(k_vertex<K1_GENERIC>, nTilesOf[K1_GENERIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_GENERIC], totalV,
+                      (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
 }
 
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
