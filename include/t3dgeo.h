@@ -279,6 +279,9 @@ int t3d_set_stage_timings(t3d_ctx* ctx, int enabled);
  * (4 floats per vertex each; either may be NULL). */
 int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end,
                                  float* clip4, float* light4);
+/* Model transforms and bone matrices whose column 3 is exactly (0, 0, 0, 1) cross PCIe as 12 floats.  enabled = 1
+ * ships all 16 always (what happens by itself as soon as one matrix of a frame is not affine); for tests. */
+int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled);
 /* Number of kernels launched by the last t3d_frame_execute. */
 int t3d_debug_last_launch_count(t3d_ctx* ctx);
 /* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */

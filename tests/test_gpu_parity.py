@@ -66,6 +66,32 @@ def test_huge_draw_parity(device):
     assert_parity(scenes.tile_boundary_scene(35, sizes=(66000, 9000, 300, 131073)), device, check_capture=False)
 
 
+def test_non_affine_bone_matrices_parity(device):
+    # bone matrices normally travel as 12 floats (column 3 is exactly 0,0,0,1); one that is not switches the frame to
+    # the full 16-float upload
+    sc = scenes.skinned_scene(3)
+    bi = np.array(sc.models[1].bone_influences, np.float32).reshape(-1, 4, 4).copy()
+    bi[2, 1, 3] = 0.015625; bi[0, 3, 3] = 1.0009765625
+    sc.models[1].bone_influences = bi
+    assert_parity(sc, device)
+    sc2 = scenes.skinned_scene(3)
+    bi = np.array(sc2.models[0].bone_influences, np.float32).reshape(-1, 4, 4).copy()
+    bi[1, 0, 3] = -0.0                     # a negative zero must survive too
+    sc2.models[0].bone_influences = bi
+    assert_parity(sc2, device)
+
+
+def test_full_upload_paths_parity(device):
+    # the 16-float transform / bone upload paths (taken when a matrix of the frame is not affine), forced on
+    device.ForceFullUpload(True)
+    try:
+        assert_parity(scenes.skinned_scene(5), device)
+        assert_parity(scenes.tile_boundary_scene(36), device, check_capture=False)
+        assert_parity(W.particles_scene(n=600, batch_cap=256), device, check_capture=False)
+    finally:
+        device.ForceFullUpload(False)
+
+
 def test_many_tiny_draws_parity(device):
     # > 1024 draws of one or two triangles: packed tiles are cut by the draw-count limit, not by triangles
     sc = scenes.tile_boundary_scene(33, sizes=(1, 2) * 700)

@@ -10,6 +10,7 @@
 #include "t3d_internal.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -91,6 +92,7 @@ struct t3d_ctx {
     // frame staging (pinned)
     bool inFrame = false, executed = false, haveResults = false;
     bool stageTimings = false, stagesTimed = false;
+    bool forceFullUpload = false;       // t3d_debug_force_full_upload: never pack affine matrices (exercises the 16-float paths)
     FrameConst fc;
     // what the host itself needs to remember about a submitted draw (the device rebuilds the full DrawRec from hSlim + hTmpl)
     struct HostDraw { uint32_t a0, nv, vbase, nt, flags; uint8_t sortMode; uint8_t vclass; /* k_vertex instantiation it is eligible for: 0 generic, 1 static fast, 2 skinned fast */ };
@@ -106,13 +108,14 @@ struct t3d_ctx {
     std::vector<uint32_t> drawTotalTris;
     std::vector<uint8_t> drawContinue;
     uint32_t vAcc = 0, tAcc = 0, luAcc = 0, nHistRows = 0;
-    bool anyLit = false, anySkinned = false, anyUnbill = false;
+    bool anyLit = false, anySkinned = false, anyUnbill = false, bonesAffine = true, transformsAffine = true;
 
     // device arenas
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
     PinVec<uint8_t> hFrame;
     void* hFrameDev = nullptr; void* pDevRest = nullptr;
-    size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0;
+    size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0, frameBonesOff = 0;
+    uint32_t frameBoneCount = 0;
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVClass[3] = {nullptr, nullptr, nullptr}, *pHuge = nullptr;
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
@@ -401,6 +404,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->drawTotalTris.clear(); ctx->drawContinue.clear();
     ctx->vAcc = ctx->tAcc = ctx->luAcc = 0;
     ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
+    ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
     return T3D_OK;
@@ -434,6 +438,13 @@ int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t
     CU(ctx->hBones.reserve(off + (size_t)n * 16));
     memcpy(ctx->hBones.p + off, matrices16, (size_t)n * 64);
     ctx->hBones.n = off + (size_t)n * 16;
+    // boneInfluence = inverseBind x Transform (node.go:592-594) is affine in every ordinary scene: column 3 is exactly
+    // (0, 0, 0, 1), and then only 48 of the 64 bytes cross PCIe (k_prep_draws puts the column back)
+    for (uint32_t i = 0; i < n && ctx->bonesAffine; i++) {
+        const float* M = matrices16 + 16 * (size_t)i;
+        ctx->bonesAffine = M[3] == 0.0f && M[7] == 0.0f && M[11] == 0.0f && M[15] == 1.0f &&
+                           !std::signbit(M[3]) && !std::signbit(M[7]) && !std::signbit(M[11]);
+    }
     *offset = (uint32_t)(off / 16);
     return T3D_OK;
 }
@@ -517,6 +528,11 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             memset(&S, 0, sizeof S);
             S.tmpl = tmplIndex; S.vbase = R.vbase; S.tbase = R.tbase; S.boneOffset = R.boneOffset; S.lightU = R.lightU;
             memcpy(S.transform, R.transform, 64); memcpy(S.color, R.color, 16);
+            if (ctx->transformsAffine) {       // Node.Transform() of an ordinary scene graph: column 3 is exactly (0, 0, 0, 1)
+                const float* M = R.transform;
+                ctx->transformsAffine = M[3] == 0.0f && M[7] == 0.0f && M[11] == 0.0f && M[15] == 1.0f &&
+                                        !std::signbit(M[3]) && !std::signbit(M[7]) && !std::signbit(M[11]);
+            }
             // the world rotation only feeds a directional light's workingModelRotation of an unskinned, lit draw (light.go:326-330)
             S.rot = NO_ROTATION;
             if ((flags & T3D_DRAW_LIT) && !(flags & T3D_DRAW_SKINNED) && ll.count) {
@@ -687,24 +703,49 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     {
         // host block: [DrawSlim[D] | templates | rotations | tables ... ]; device block: [DrawRec[D] | tables ...]
         struct Seg { const void* src; size_t bytes; size_t off; };
-        Seg head[3] = {{ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
+        const size_t slimBytes = ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
+        Seg head[3] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
         Seg segs[13] = {
             {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
-            {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {ctx->hBones.p, 4ull * ctx->hBones.n, 0},
+            {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {nullptr, 0, 0} /* bones travel separately, below */,
             {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVClass[0].p, 4ull * ctx->hVClass[0].n, 0}, {ctx->hVClass[1].p, 4ull * ctx->hVClass[1].n, 0},
             {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 4ull * ctx->hVClass[2].n, 0}};
         size_t headBytes = 0, restBytes = 0;
         for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
         for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
         const size_t devDrawBytes = (sizeof(DrawRec) * (size_t)nDraws + 255) & ~(size_t)255;
+        // bone matrices: 12 floats each on the host side when all are affine, always 16 on the device
+        const size_t nBones = ctx->hBones.n / 16;
+        const size_t hostBoneBytes = ((ctx->bonesAffine ? 48 : 64) * nBones + 255) & ~(size_t)255;
+        const size_t devBoneBytes = (64 * nBones + 255) & ~(size_t)255;
         ctx->hFrame.mapped = true;
-        CU(ctx->hFrame.resize(headBytes + restBytes));
-        CU(ctx->dFrame.ensure(devDrawBytes + restBytes));
-        for (Seg& g : head) if (g.bytes) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
+        CU(ctx->hFrame.resize(headBytes + restBytes + hostBoneBytes));
+        CU(ctx->dFrame.ensure(devDrawBytes + restBytes + devBoneBytes));
+        for (Seg& g : head) if (g.bytes && g.src) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
         for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + headBytes + g.off, g.src, g.bytes);
+        if (!ctx->transformsAffine) memcpy(ctx->hFrame.p, ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws);
+        else for (uint32_t d = 0; d < nDraws; d++) {
+            const DrawSlim& S = ctx->hSlim.p[d];
+            uint8_t* o = ctx->hFrame.p + slimBytes * (size_t)d;
+            memcpy(o, &S, 32);                                          // header
+            float* t = reinterpret_cast<float*>(o + 32);
+            for (int r = 0; r < 4; r++) { t[3 * r] = S.transform[4 * r]; t[3 * r + 1] = S.transform[4 * r + 1]; t[3 * r + 2] = S.transform[4 * r + 2]; }
+            memcpy(o + 32 + 48, S.color, 16);
+        }
+        {
+            float* hb = reinterpret_cast<float*>(ctx->hFrame.p + headBytes + restBytes);
+            if (!ctx->bonesAffine) memcpy(hb, ctx->hBones.p, 64 * nBones);
+            else for (size_t i = 0; i < nBones; i++) {
+                const float* M = ctx->hBones.p + 16 * i;
+                float* o = hb + 12 * i;
+                o[0] = M[0]; o[1] = M[1]; o[2] = M[2]; o[3] = M[4]; o[4] = M[5]; o[5] = M[6];
+                o[6] = M[8]; o[7] = M[9]; o[8] = M[10]; o[9] = M[12]; o[10] = M[13]; o[11] = M[14];
+            }
+        }
+        ctx->frameBonesOff = headBytes + restBytes; ctx->frameBoneCount = (uint32_t)nBones;
         // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
         CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
         ctx->frameHeadBytes = headBytes; ctx->frameRestBytes = restBytes; ctx->frameTmplOff = head[1].off; ctx->frameRotOff = head[2].off;
@@ -720,7 +761,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pLarge = reinterpret_cast<uint32_t*>(rest + segs[4].off);
         ctx->pPacked = reinterpret_cast<uint32_t*>(rest + segs[5].off);
         ctx->pLightsIn = reinterpret_cast<t3d_light*>(rest + segs[6].off);
-        ctx->pBones = reinterpret_cast<float*>(rest + segs[7].off);
+        ctx->pBones = reinterpret_cast<float*>(rest + restBytes);
         ctx->pMedium = reinterpret_cast<uint32_t*>(rest + segs[8].off);
         ctx->pVClass[0] = reinterpret_cast<uint32_t*>(rest + segs[9].off);
         ctx->pVClass[1] = reinterpret_cast<uint32_t*>(rest + segs[10].off);
@@ -729,6 +770,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->h2dBytes = 0;
         for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
+        ctx->h2dBytes += (ctx->bonesAffine ? 48 : 64) * nBones;
     }
     // Stage timings need an event between kernels, which also serialises them; the default path records only
     // the frame's first and last event and chains the kernels with programmatic dependent launches.
@@ -757,7 +799,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         const uint8_t* hf = static_cast<const uint8_t*>(ctx->hFrameDev);
         launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
                           reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
-                          (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win);
+                          (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
+                          hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine);
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};
@@ -987,6 +1030,12 @@ int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->sharedOpened.push_back(p);
     *device_ptr = p;
+    return T3D_OK;
+}
+
+int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    ctx->forceFullUpload = enabled != 0;
     return T3D_OK;
 }
 

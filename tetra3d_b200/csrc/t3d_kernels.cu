@@ -70,6 +70,12 @@ struct PrepFrame {
     // template / rotation windows {tmin, templates, rmin, rotations} of the first blocks, known to the host: those
     // blocks (all of a small frame) fetch slim records, templates and rotations in ONE round trip over PCIe
     uint32_t win[PREP_PARAM_BLOCKS][4];
+    // bone matrices: 48 bytes each on the host when bonesPacked (rows 0-3, columns 0-2: column 3 is exactly 0,0,0,1),
+    // else 64; always 64 on the device
+    const uint4* hostBones; uint4* devBones; uint32_t nBones, bonesPacked;
+    // DrawSlim records: 7 uint4 each, or 6 when every model transform of the frame is affine (the transform travels as
+    // rows 0-3 x columns 0-2; column 3 is exactly 0,0,0,1)
+    uint32_t slim16;
 };
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -91,10 +97,28 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
             for (int u = 0; u < 8; u++) dst[i + u * stride] = v[u];
         }
         for (; i < pf.rest16; i += stride) dst[i] = src[i];
+        // bone matrices, one per thread: 3 (packed) or 4 uint4 in, 4 out
+        for (uint32_t b = (blockIdx.x - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x; b < pf.nBones; b += stride) {
+            uint4* o = pf.devBones + 4 * (size_t)b;
+            if (pf.bonesPacked) {
+                const uint4* p = pf.hostBones + 3 * (size_t)b;
+                const uint4 a = p[0], c = p[1], e = p[2];       // m00 m01 m02 m10 | m11 m12 m20 m21 | m22 m30 m31 m32
+                o[0] = make_uint4(a.x, a.y, a.z, 0u);
+                o[1] = make_uint4(a.w, c.x, c.y, 0u);
+                o[2] = make_uint4(c.z, c.w, e.x, 0u);
+                o[3] = make_uint4(e.y, e.z, e.w, 0x3F800000u);
+            } else {
+                const uint4* p = pf.hostBones + 4 * (size_t)b;
+                const uint4 a = p[0], c = p[1], e = p[2], f = p[3];
+                o[0] = a; o[1] = c; o[2] = e; o[3] = f;
+            }
+        }
         return;
     }
     DrawRec* sR = reinterpret_cast<DrawRec*>(prepSmem);
-    DrawSlim* sS = reinterpret_cast<DrawSlim*>(prepSmem + PREP_DRAWS * REC16);
+    uint4* sSraw = prepSmem + PREP_DRAWS * REC16;
+    const uint32_t s16 = pf.slim16;                      // record stride; the 32-byte header is the same in both layouts
+    auto slimOf = [&](uint32_t kk) -> const DrawSlim& { return *reinterpret_cast<const DrawSlim*>(sSraw + kk * s16); };
     uint4* sT = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
     uint4* sRot = sT + PREP_TEMPLATES * REC16;
     t3d_light* sL = reinterpret_cast<t3d_light*>(sRot + PREP_DRAWS * 4);
@@ -105,9 +129,9 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
     const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
     {   // slim records (7 uint4 each), and for the first blocks the templates and rotations in the same round trip
-        const uint4* src = pf.hostSlim + (size_t)d0 * SLIM16;
-        uint4* dst = reinterpret_cast<uint4*>(sS);
-        const uint32_t n16 = n * SLIM16;
+        const uint4* src = pf.hostSlim + (size_t)d0 * s16;
+        uint4* dst = sSraw;
+        const uint32_t n16 = n * s16;
         uint4 v[2], tv[T_SWEEPS], rv;
 #pragma unroll
         for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
@@ -141,7 +165,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         uint32_t tmax = 0u, rmax = 0u;
         tmin = 0xFFFFFFFFu;
         for (uint32_t k = 0; k < n; k++) {
-            const uint32_t t = sS[k].tmpl, r = sS[k].rot;
+            const uint32_t t = slimOf(k).tmpl, r = slimOf(k).rot;
             tmin = min(tmin, t); tmax = max(tmax, t);
             if (r != NO_ROTATION) { rmin = min(rmin, r); rmax = max(rmax, r); }
         }
@@ -164,31 +188,39 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     static_assert(PREP_THREADS == 4 * PREP_DRAWS, "four roles per draw");
     const bool mine = k < n;
     if (mine) {   // full record = template + this draw's placement, assembled by the draw's four threads
-        const DrawSlim& S = sS[k];
+        const DrawSlim& S = slimOf(k);
         uint4* dst = reinterpret_cast<uint4*>(&sR[k]);
         const uint32_t ti = S.tmpl - tmin;
         const uint4* src = ti < (uint32_t)PREP_TEMPLATES ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
         const uint4* sl = reinterpret_cast<const uint4*>(&S);
         const uint4* rs = S.rot != NO_ROTATION ? sRot + (size_t)(S.rot - rmin) * 4 : nullptr;
         constexpr int TR16 = offsetof(DrawRec, transform) / 16, WR16 = offsetof(DrawRec, worldRot) / 16, CO16 = offsetof(DrawRec, color) / 16;
-        constexpr int STR16 = offsetof(DrawSlim, transform) / 16, SCO16 = offsetof(DrawSlim, color) / 16;
+        constexpr int STR16 = offsetof(DrawSlim, transform) / 16;
+        const bool packed = s16 != (uint32_t)SLIM16;
         for (int i = role; i < REC16; i += 4) {
             uint4 v = src[i];
-            if (i >= TR16 && i < TR16 + 4) v = sl[STR16 + (i - TR16)];
-            else if (i == CO16) v = sl[SCO16];
+            if (i >= TR16 && i < TR16 + 4) {
+                if (!packed) v = sl[STR16 + (i - TR16)];
+                else {      // row r of the transform from the 12 packed floats
+                    const int r = i - TR16;
+                    const uint32_t* f = reinterpret_cast<const uint32_t*>(sl + STR16) + 3 * r;
+                    v = make_uint4(f[0], f[1], f[2], r == 3 ? 0x3F800000u : 0u);
+                }
+            }
+            else if (i == CO16) v = sl[STR16 + (packed ? 3 : 4)];
             else if (rs && i >= WR16 && i < WR16 + 4) v = rs[i - WR16];
             dst[i] = v;
         }
     }
     __syncthreads();
     if (mine && role == 0) {      // the scalar placement fields
-        const DrawSlim& S = sS[k];
+        const DrawSlim& S = slimOf(k);
         DrawRec& R = sR[k];
         R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
     }
     __syncthreads();
-    float* sInv = reinterpret_cast<float*>(sS);          // the slim records are consumed: 16 floats per draw {r rows 0-2, invPS}
-    static_assert(sizeof(DrawSlim) >= 16 * sizeof(float), "scratch per draw");
+    float* sInv = reinterpret_cast<float*>(sSraw);       // the slim records are consumed: 16 floats per draw {r rows 0-3, invPS}
+    const uint32_t invStride = s16 * 4;                  // floats; >= 24
     if (mine) {
     DrawRec& R = sR[k];
     const uint32_t flags = R.flags;
@@ -202,7 +234,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const Vec3 invPS = v3_mult(p, v3(1.0f / sc.X, 1.0f / sc.Y, 1.0f / sc.Z));
         const Vec3 invCam = v3_add(m4_multvec(r, camPos), invPS);
         R.invCam[0] = invCam.X; R.invCam[1] = invCam.Y; R.invCam[2] = invCam.Z;
-        float* o = sInv + (sizeof(DrawSlim) / 4) * k;
+        float* o = sInv + invStride * k;
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -273,7 +305,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const bool skinned = flags & T3D_DRAW_SKINNED;
         const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
         if (role < nL) {
-            const float* o = sInv + (sizeof(DrawSlim) / 4) * k;
+            const float* o = sInv + invStride * k;
             Mat4 r = m4_identity();
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -1237,7 +1269,8 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 
 void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const void* hostTmpl, const void* hostRot, const void* hostRest,
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
-                       const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4]) {
+                       const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
+                       const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_BYTES);     // per device; cheap
     PrepFrame pf;
@@ -1247,7 +1280,11 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.devDraws = reinterpret_cast<uint4*>(devDraws); pf.devRest = reinterpret_cast<uint4*>(devRest);
     pf.nDraws = nDraws; pf.rest16 = (uint32_t)(restBytes / 16); pf.nPrepBlocks = cdiv(nDraws, PREP_DRAWS); pf.nLightsIn = nLightsIn;
     memcpy(pf.win, win, sizeof pf.win);
-    const uint32_t nCopy = pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u;
+    pf.hostBones = reinterpret_cast<const uint4*>(hostBones); pf.devBones = reinterpret_cast<uint4*>(devBones);
+    pf.nBones = nBones; pf.bonesPacked = bonesPacked ? 1u : 0u;
+    pf.slim16 = slimPacked ? SLIM16 - 1 : SLIM16;
+    const uint32_t nCopy = std::max(pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u,
+                                    nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
     launch_kernel(k_prep_draws, pf.nPrepBlocks + nCopy, PREP_THREADS, PREP_SMEM_BYTES, s, false, pf, fc, lightsU, stats);

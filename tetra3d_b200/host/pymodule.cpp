@@ -255,6 +255,7 @@ PYBIND11_MODULE(_host, m) {
                                                  reinterpret_cast<t3d_vertex*>(normal), capacity);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
         })
+        .def("ForceFullUpload", [](GeometryDevice& d, bool on) { t3d_debug_force_full_upload(d.ctx, on ? 1 : 0); })
         .def("SetStageTimings", [](GeometryDevice& d, bool on) { t3d_set_stage_timings(d.ctx, on ? 1 : 0); })
         .def("VertexKernelBytes", [](GeometryDevice& d) { return t3d_debug_vertex_kernel_bytes(d.ctx); })
         .def("FrameBytes", [](GeometryDevice& d) { uint64_t a = 0, b = 0; t3d_debug_frame_bytes(d.ctx, &a, &b); return py::make_tuple(a, b); })
