@@ -1,0 +1,165 @@
+"""-m gpu: the C ABI of include/t3dgeo.h driven directly with ctypes, the way a cgo shim would:
+a minimal frame end to end, and the error behaviour (negative code + t3d_last_error text, nothing aborts)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+T3D_OK, T3D_E_INVALID, T3D_E_CUDA, T3D_E_UNSUPPORTED, T3D_E_NOMEM, T3D_E_STATE, T3D_E_NOTFOUND = 0, -1, -2, -3, -4, -5, -6
+f32p = C.POINTER(C.c_float)
+
+
+class PartRange(C.Structure):
+    _fields_ = [("vtx_start", C.c_uint32), ("vtx_end", C.c_uint32), ("tri_start", C.c_uint32), ("tri_end", C.c_uint32)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("n_verts", C.c_uint32), ("positions", f32p), ("normals", f32p), ("uvs", f32p), ("colors", f32p), ("weights", f32p),
+                ("bones", C.POINTER(C.c_uint16)), ("n_influences", C.POINTER(C.c_uint8)), ("n_tris", C.c_uint32),
+                ("indices", C.POINTER(C.c_uint32)), ("centers", f32p), ("n_parts", C.c_uint32), ("parts", C.POINTER(PartRange)),
+                ("max_span", C.c_float), ("n_shape_keys", C.c_uint32), ("key_positions", f32p), ("key_normals", f32p)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("vp", C.c_float * 16), ("view", C.c_float * 16), ("position", C.c_float * 3), ("up", C.c_float * 3),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("depth_margin", C.c_float), ("vertex_snapping", C.c_float), ("flags", C.c_uint32)]
+
+
+class World(C.Structure):
+    _fields_ = [("present", C.c_int32), ("fog_on", C.c_int32), ("fog_mode", C.c_int32), ("fog_color", C.c_float * 3), ("fog_range", C.c_float * 2)]
+
+
+class Draw(C.Structure):
+    _fields_ = [("mesh_id", C.c_uint64), ("part", C.c_uint32), ("flags", C.c_uint32), ("transform", C.c_float * 16),
+                ("world_rotation", C.c_float * 16), ("color", C.c_float * 4), ("src_w", C.c_float), ("src_h", C.c_float),
+                ("sort_mode", C.c_uint8), ("lighting_mode", C.c_uint8), ("light_volume_mode", C.c_uint8), ("reserved0", C.c_uint8),
+                ("bone_offset", C.c_uint32), ("bone_count", C.c_uint32), ("light_list", C.c_uint32), ("reserved1", C.c_uint32)]
+
+
+class DrawResult(C.Structure):
+    _fields_ = [("first_vertex", C.c_uint64), ("vertex_count", C.c_uint32), ("total_tris", C.c_uint32), ("min_depth", C.c_float), ("max_depth", C.c_float)]
+
+
+class FrameOutput(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint64), ("n_draws", C.c_uint32), ("color_list", f32p), ("depth_list", f32p), ("normal_list", f32p),
+                ("index_list", C.POINTER(C.c_uint16)), ("tri_ids", C.POINTER(C.c_uint32)), ("draws", C.POINTER(DrawResult))]
+
+
+@pytest.fixture(scope="module")
+def abi():
+    import tetra3d_b200
+    lib = C.CDLL(tetra3d_b200.LIB_PATH)
+    lib.t3d_last_error.restype = C.c_char_p
+    lib.t3d_last_error.argtypes = [C.c_void_p]
+    for name in ("t3d_mesh_upload", "t3d_frame_begin", "t3d_submit_draws", "t3d_frame_execute", "t3d_frame_results", "t3d_mesh_release",
+                 "t3d_submit_lights", "t3d_submit_bones", "t3d_create", "t3d_set_output_target"):
+        getattr(lib, name).restype = C.c_int
+    ctx = C.c_void_p()
+    assert lib.t3d_create(C.byref(ctx), 0) == T3D_OK, lib.t3d_last_error(None)
+    yield lib, ctx
+    lib.t3d_destroy.argtypes = [C.c_void_p]
+    lib.t3d_destroy(ctx)
+
+
+def _triangle_mesh():
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (3, 1))
+    uv = np.array([[0, 0], [1, 0], [0.5, 1]], np.float32)
+    idx = np.array([0, 1, 2], np.uint32)
+    ctr = pos.mean(axis=0).astype(np.float32)
+    parts = (PartRange * 1)(PartRange(0, 3, 0, 1))
+    d = MeshDesc()
+    d.n_verts = 3; d.positions = pos.ctypes.data_as(f32p); d.normals = nrm.ctypes.data_as(f32p); d.uvs = uv.ctypes.data_as(f32p)
+    d.n_tris = 1; d.indices = idx.ctypes.data_as(C.POINTER(C.c_uint32)); d.centers = ctr.ctypes.data_as(f32p)
+    d.n_parts = 1; d.parts = parts; d.max_span = 2.0
+    return d, (pos, nrm, uv, idx, ctr, parts)
+
+
+def _camera():
+    cam = Camera()
+    # view = translate(0, 0, -5); a projection whose row-vector form keeps the triangle in front of the camera
+    n, f = 0.1, 100.0
+    t = n * np.tan(np.radians(60.0) / 2); r = t * (640 / 360)
+    proj = np.array([[n / r, 0, 0, 0], [0, n / t, 0, 0], [0, 0, -(f + n) / (f - n), -2 * f * n / (f - n)], [0, 0, -1, 0]], np.float32)
+    view = np.eye(4, dtype=np.float32); view[3, 2] = -5.0
+    vp = (view @ proj.T).astype(np.float32)          # row vectors: v * view * projT (matrix.go:588-604 is applied row-wise)
+    cam.vp[:] = vp.reshape(-1).tolist(); cam.view[:] = view.reshape(-1).tolist()
+    cam.position[:] = [0, 0, 5]; cam.up[:] = [0, 1, 0]
+    cam.near_plane = n; cam.far_plane = f; cam.width = 640; cam.height = 360; cam.depth_margin = 0.04
+    cam.flags = 1 | 2       # perspective, render depth
+    return cam
+
+
+def _draw(mesh_id=7, part=0):
+    d = Draw()
+    d.mesh_id = mesh_id; d.part = part; d.flags = 0
+    d.transform[:] = np.eye(4, dtype=np.float32).reshape(-1).tolist()
+    d.world_rotation[:] = np.eye(4, dtype=np.float32).reshape(-1).tolist()
+    d.color[:] = [1, 0.5, 0.25, 1]
+    return d
+
+
+def test_minimal_frame_through_the_c_abi(abi):
+    lib, ctx = abi
+    md, keep = _triangle_mesh()
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(7), C.c_uint32(1), C.byref(md)) == T3D_OK, lib.t3d_last_error(ctx)
+    cam, world = _camera(), World()
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    dr = _draw()
+    assert lib.t3d_submit_draws(ctx, C.byref(dr), C.c_uint32(1)) == T3D_OK, lib.t3d_last_error(ctx)
+    assert lib.t3d_frame_execute(ctx) == T3D_OK, lib.t3d_last_error(ctx)
+    out = FrameOutput()
+    assert lib.t3d_frame_results(ctx, C.byref(out), None) == T3D_OK, lib.t3d_last_error(ctx)
+    assert out.n_draws == 1 and out.n_vertices == 3
+    r = out.draws[0]
+    assert (r.first_vertex, r.vertex_count, r.total_tris) == (0, 3, 1)
+    assert abs(r.min_depth - 25.111113) < 1e-3 and r.min_depth == r.max_depth       # |cam - centre|^2 = 25 + 1/9
+    v = np.ctypeslib.as_array(out.color_list, shape=(3, 12))
+    assert np.allclose(v[:, 4:8], [[1, 0.5, 0.25, 1]] * 3)                         # unlit: model colour
+    assert np.all((v[:, 0] > 0) & (v[:, 0] < 640) & (v[:, 1] > 0) & (v[:, 1] < 360))   # on screen
+    assert [out.index_list[i] for i in range(3)] == [0, 1, 2] and out.tri_ids[0] == 0
+    # re-upload with the same generation is a no-op; release works; the mesh is gone afterwards
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(7), C.c_uint32(1), C.byref(md)) == T3D_OK
+
+
+def test_error_codes_and_messages(abi):
+    lib, ctx = abi
+    cam, world = _camera(), World()
+    dr = _draw()
+    # call order
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    assert lib.t3d_frame_execute(ctx) == T3D_OK                                  # an empty frame is fine
+    assert lib.t3d_frame_execute(ctx) == T3D_E_STATE and b"no open frame" in lib.t3d_last_error(ctx)
+    assert lib.t3d_submit_draws(ctx, C.byref(dr), C.c_uint32(1)) == T3D_E_STATE
+    out = FrameOutput()
+    assert lib.t3d_frame_results(ctx, C.byref(out), None) == T3D_OK and out.n_vertices == 0
+    # arguments
+    assert lib.t3d_frame_begin(ctx, None, None) == T3D_E_INVALID
+    bad = _camera(); bad.width = 0
+    assert lib.t3d_frame_begin(ctx, C.byref(bad), C.byref(world)) == T3D_E_INVALID and b"camera size" in lib.t3d_last_error(ctx)
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    unknown = _draw(mesh_id=12345)
+    assert lib.t3d_submit_draws(ctx, C.byref(unknown), C.c_uint32(1)) == T3D_E_NOTFOUND and b"unknown mesh" in lib.t3d_last_error(ctx)
+    md, keep = _triangle_mesh()
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(8), C.c_uint32(1), C.byref(md)) == T3D_OK
+    badpart = _draw(mesh_id=8, part=3)
+    assert lib.t3d_submit_draws(ctx, C.byref(badpart), C.c_uint32(1)) == T3D_E_INVALID and b"part index" in lib.t3d_last_error(ctx)
+    badenum = _draw(mesh_id=8); badenum.sort_mode = 9
+    assert lib.t3d_submit_draws(ctx, C.byref(badenum), C.c_uint32(1)) == T3D_E_INVALID
+    skinned = _draw(mesh_id=8); skinned.flags = 1 << 3
+    assert lib.t3d_submit_draws(ctx, C.byref(skinned), C.c_uint32(1)) == T3D_E_INVALID and b"without weights" in lib.t3d_last_error(ctx)
+    nolist = _draw(mesh_id=8); nolist.light_list = 77
+    assert lib.t3d_submit_draws(ctx, C.byref(nolist), C.c_uint32(1)) == T3D_E_INVALID
+    # the frame is still usable after rejected submits
+    ok = _draw(mesh_id=8)
+    assert lib.t3d_submit_draws(ctx, C.byref(ok), C.c_uint32(1)) == T3D_OK
+    assert lib.t3d_frame_execute(ctx) == T3D_OK and lib.t3d_frame_results(ctx, C.byref(out), None) == T3D_OK and out.n_vertices == 3
+    # mesh upload validation
+    md2, keep2 = _triangle_mesh()
+    keep2[3][2] = 5                                                             # index out of range
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(9), C.c_uint32(1), C.byref(md2)) == T3D_E_INVALID and b"out of range" in lib.t3d_last_error(ctx)
+    assert lib.t3d_mesh_release(ctx, C.c_uint64(4242)) == T3D_E_NOTFOUND
+    assert lib.t3d_mesh_release(ctx, C.c_uint64(8)) == T3D_OK
