@@ -1,11 +1,16 @@
 // t3d_api.cu -- the C ABI of include/t3dgeo.h: context, mesh residency, per-frame arenas, pipeline.
 //
-// Per frame: the host resolves every submitted draw into a DrawRec (device pointers + arena offsets),
-// cuts the triangle arena into tiles (t3d_device.cuh: TriTile), uploads everything in one async copy from
-// pinned staging, then enqueues  prep -> vertex -> cull (+ in-tile sort for small draws) -> bin histogram
-// -> scatter -> tile scan -> emit  on one stream.
+// Per frame: the host resolves every submitted draw into a placement record (DrawSlim) plus, when anything else
+// changes, a DrawRec template; cuts the vertex and triangle arenas into tiles (t3d_device.cuh: TriTile) and sorts
+// them into per-kernel work lists; packs everything into one pinned, mapped block; then enqueues, chained with
+// programmatic dependent launches on one stream,
+//   k_prep_draws (pulls the block over PCIe, rebuilds DrawRec[D], per-draw uniforms)
+//   -> k_vertex<STATIC | SKINNED | GENERIC>
+//   -> k_cull_large | k_tile_packed | k_draw_medium          (by draw size; the last two also sort)
+//   -> k_bin_hist (+ tile scan) [-> k_hist_scan_huge] -> k_scatter    (draws of more than 8192 triangles)
+//   -> k_emit.
 // Results stay on the device until t3d_frame_results (pinned D2H) or are handed out as device
-// pointers by t3d_frame_results_device.
+// pointers by t3d_frame_results_device; t3d_set_output_target redirects the emit to caller-provided memory.
 #include "../../include/t3dgeo.h"
 #include "t3d_internal.h"
 
@@ -699,7 +704,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->volumesDirty = false;
     }
 
-    // uniforms up: pack every per-frame array into one pinned block -> one async copy
+    // uniforms: pack every per-frame array into one pinned, mapped block that k_prep_draws reads over PCIe
     {
         // host block: [DrawSlim[D] | templates | rotations | tables ... ]; device block: [DrawRec[D] | tables ...]
         struct Seg { const void* src; size_t bytes; size_t off; };

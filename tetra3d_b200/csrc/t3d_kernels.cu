@@ -1,14 +1,18 @@
 // t3d_kernels.cu -- sm_100a kernels of the Tetra3D geometry stage.
 //
-//   k_prep_draws  one thread per draw      per-draw uniforms of Model.ProcessVertices (model.go:616-708) and
-//                                           light.beginModel (light.go:175-189, 326-330)
-//   k_vertex      one vertex per thread     fused skin + transform + light (model.go:559-596, 757-822;
-//                                           light.go:116-120, 191-258, 332-360, 583-663)
+//   k_prep_draws  four threads per draw     pulls the frame's uniforms over PCIe; per-draw uniforms of
+//                                           Model.ProcessVertices (model.go:616-708) and light.beginModel
+//                                           (light.go:175-189, 326-330)
+//   k_vertex<M>   one vertex per thread     fused skin + transform + light (model.go:559-596, 757-822;
+//                                           light.go:116-120, 191-258, 332-360, 583-663); static-fast, skinned-fast
+//                                           and generic instantiations over host-built tile lists
 //   k_cull_large  one tile per block        near/far, side, backface cull + depth key + per-draw min/max
-//                                           (model.go:855-969) for draws that own whole tiles
-//   k_tile_packed one tile per block        the same cull fused with the 512-bin sort
-//                                           (sortingTriangles.go:38-125) for draws that fit inside a tile
-//   k_emit        one thread per corner     colour/depth/normal vertex lists (camera.go:1646-1820)
+//                                           (model.go:855-969) for draws of more than 8192 triangles
+//   k_draw_medium one draw per block        the same cull fused with the 512-bin sort (sortingTriangles.go:38-125)
+//                                           for draws of up to 8192 triangles and draws alone in their tile
+//   k_tile_packed one tile per block        the same for tiles packed with several small draws
+//   k_emit        one thread per corner     colour/depth/normal vertex lists (camera.go:1646-1820), written with
+//                                           TMA bulk stores
 //
 // Mesh arrays are SoA planes (x|y|z, a|b|c) so one-element-per-thread loads are fully coalesced.
 //
