@@ -712,7 +712,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         Seg head[3] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
         Seg segs[13] = {
-            {ctx->hVbase.p, 4ull * (nDraws + 1), 0}, {ctx->hTbase.p, 4ull * (nDraws + 1), 0},
+            {nullptr, 0, 0}, {nullptr, 0, 0} /* vbase / tbase: k_prep_draws writes the device tables from the placement records */,
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {nullptr, 0, 0} /* bones travel separately, below */,
@@ -726,9 +726,10 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         const size_t nBones = ctx->hBones.n / 16;
         const size_t hostBoneBytes = ((ctx->bonesAffine ? 48 : 64) * nBones + 255) & ~(size_t)255;
         const size_t devBoneBytes = (64 * nBones + 255) & ~(size_t)255;
+        const size_t devTableBytes = (4ull * (nDraws + 1) + 255) & ~(size_t)255;        // vbase, tbase
         ctx->hFrame.mapped = true;
         CU(ctx->hFrame.resize(headBytes + restBytes + hostBoneBytes));
-        CU(ctx->dFrame.ensure(devDrawBytes + restBytes + devBoneBytes));
+        CU(ctx->dFrame.ensure(devDrawBytes + restBytes + devBoneBytes + 2 * devTableBytes));
         for (Seg& g : head) if (g.bytes && g.src) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
         for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + headBytes + g.off, g.src, g.bytes);
         if (!ctx->transformsAffine) memcpy(ctx->hFrame.p, ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws);
@@ -759,8 +760,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         uint8_t* rest = base + devDrawBytes;
         ctx->pDevRest = rest;
         ctx->pDraws = reinterpret_cast<DrawRec*>(base);
-        ctx->pVbase = reinterpret_cast<uint32_t*>(rest + segs[0].off);
-        ctx->pTbase = reinterpret_cast<uint32_t*>(rest + segs[1].off);
+        ctx->pVbase = reinterpret_cast<uint32_t*>(rest + restBytes + devBoneBytes);
+        ctx->pTbase = reinterpret_cast<uint32_t*>(rest + restBytes + devBoneBytes + devTableBytes);
         ctx->pTileV = reinterpret_cast<uint32_t*>(rest + segs[2].off);
         ctx->pTiles = reinterpret_cast<TriTile*>(rest + segs[3].off);
         ctx->pLarge = reinterpret_cast<uint32_t*>(rest + segs[4].off);
@@ -805,7 +806,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
                           reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
-                          hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine);
+                          hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
+                          ctx->pVbase, ctx->pTbase);
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};

@@ -80,6 +80,7 @@ struct PrepFrame {
     // DrawSlim records: 7 uint4 each, or 6 when every model transform of the frame is affine (the transform travels as
     // rows 0-3 x columns 0-2; column 3 is exactly 0,0,0,1)
     uint32_t slim16;
+    uint32_t* devVbase; uint32_t* devTbase;     // [nDraws + 1] arena offsets per draw: written here from the records, not copied
 };
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -217,10 +218,12 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         }
     }
     __syncthreads();
-    if (mine && role == 0) {      // the scalar placement fields
+    if (mine && role == 0) {      // the scalar placement fields, and the frame's vbase / tbase tables
         const DrawSlim& S = slimOf(k);
         DrawRec& R = sR[k];
         R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
+        pf.devVbase[d0 + k] = S.vbase; pf.devTbase[d0 + k] = S.tbase;
+        if (d0 + k == pf.nDraws - 1) { pf.devVbase[pf.nDraws] = S.vbase + R.nv; pf.devTbase[pf.nDraws] = S.tbase + R.nt; }
     }
     __syncthreads();
     float* sInv = reinterpret_cast<float*>(sSraw);       // the slim records are consumed: 16 floats per draw {r rows 0-3, invPS}
@@ -1274,7 +1277,8 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const void* hostTmpl, const void* hostRot, const void* hostRest,
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
-                       const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked) {
+                       const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
+                       uint32_t* devVbase, uint32_t* devTbase) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_BYTES);     // per device; cheap
     PrepFrame pf;
@@ -1287,6 +1291,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.hostBones = reinterpret_cast<const uint4*>(hostBones); pf.devBones = reinterpret_cast<uint4*>(devBones);
     pf.nBones = nBones; pf.bonesPacked = bonesPacked ? 1u : 0u;
     pf.slim16 = slimPacked ? SLIM16 - 1 : SLIM16;
+    pf.devVbase = devVbase; pf.devTbase = devTbase;
     const uint32_t nCopy = std::max(pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u,
                                     nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
