@@ -103,6 +103,8 @@ struct t3d_ctx {
     struct HostDraw { uint32_t a0, nv, vbase, nt, flags; uint8_t sortMode; uint8_t vclass; /* k_vertex instantiation it is eligible for: 0 generic, 1 static fast, 2 skinned fast */ };
     std::vector<HostDraw> hDraws;
     PinVec<DrawSlim> hSlim;
+    std::vector<DrawRun> hRuns;          // run-length form of hSlim's headers, rebuilt every frame
+    std::vector<uint32_t> hBlockRun;
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
     PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVClass[3], hHuge;       // hVClass: vertex tiles by class (0 generic, 1 static fast, 2 skinned fast)
@@ -120,6 +122,7 @@ struct t3d_ctx {
     PinVec<uint8_t> hFrame;
     void* hFrameDev = nullptr; void* pDevRest = nullptr;
     size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0, frameBonesOff = 0;
+    size_t frameRunsOff = 0, frameBlockRunOff = 0; bool frameRunMode = false;
     uint32_t frameBoneCount = 0;
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVClass[3] = {nullptr, nullptr, nullptr}, *pHuge = nullptr;
     TriTile* pTiles = nullptr;
@@ -708,9 +711,55 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     {
         // host block: [DrawSlim[D] | templates | rotations | tables ... ]; device block: [DrawRec[D] | tables ...]
         struct Seg { const void* src; size_t bytes; size_t off; };
-        const size_t slimBytes = ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
-        Seg head[3] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
-                       {ctx->hRot.p, 4ull * ctx->hRot.n, 0}};
+        // Runs of consecutive draws whose headers progress regularly (instances of one MeshPart).  When they are long on
+        // average, the frame ships run records + 64-byte payloads instead of one 96-byte DrawSlim per draw.
+        ctx->hRuns.clear(); ctx->hBlockRun.clear();
+        bool runMode = false;
+        if (ctx->transformsAffine && nDraws >= 1024) {
+            const DrawSlim* S = ctx->hSlim.p;
+            for (uint32_t d = 0; d < nDraws; d++) {
+                bool extend = false;
+                if (!ctx->hRuns.empty()) {
+                    DrawRun& U = ctx->hRuns.back();
+                    const uint32_t i = d - U.first;
+                    if (S[d].tmpl == U.tmpl && ((S[d].rot != NO_ROTATION) == (U.rot != NO_ROTATION))) {
+                        if (U.count == 1) {      // the second draw of a run fixes the increments
+                            U.dV = S[d].vbase - U.vbase; U.dT = S[d].tbase - U.tbase; U.dBone = S[d].boneOffset - U.boneOffset;
+                            U.dLightU = S[d].lightU - U.lightU; U.dRot = U.rot != NO_ROTATION ? S[d].rot - U.rot : 0;
+                            extend = U.dRot <= 1 && (U.rot == NO_ROTATION || U.dRot == 1);
+                        } else {
+                            extend = S[d].vbase == U.vbase + i * U.dV && S[d].tbase == U.tbase + i * U.dT && S[d].boneOffset == U.boneOffset + i * U.dBone &&
+                                     S[d].lightU == U.lightU + i * U.dLightU && (U.rot == NO_ROTATION || S[d].rot == U.rot + i);
+                        }
+                    }
+                    if (extend) U.count++;
+                    else if (U.count == 1) { U.dV = U.dT = U.dBone = U.dLightU = U.dRot = 0; }
+                }
+                if (!extend) {
+                    DrawRun U; memset(&U, 0, sizeof U);
+                    U.first = d; U.count = 1; U.tmpl = S[d].tmpl; U.vbase = S[d].vbase; U.tbase = S[d].tbase; U.boneOffset = S[d].boneOffset;
+                    U.lightU = S[d].lightU; U.rot = S[d].rot;
+                    ctx->hRuns.push_back(U);
+                }
+            }
+            runMode = (uint64_t)ctx->hRuns.size() * RUN_MODE_MIN_AVG <= nDraws;
+            if (runMode) {      // hBlockRun[b] = run of draw b * 64 (k_prep_draws: 64 draws per block), one extra entry for the last draw
+                const uint32_t nBlocks = (nDraws + PREP_WINDOW_DRAWS - 1) / PREP_WINDOW_DRAWS;
+                ctx->hBlockRun.resize(nBlocks + 1);
+                uint32_t r = 0;
+                for (uint32_t b = 0; b <= nBlocks; b++) {
+                    const uint32_t d = std::min(b * (uint32_t)PREP_WINDOW_DRAWS, nDraws - 1);
+                    while (r + 1 < ctx->hRuns.size() && ctx->hRuns[r + 1].first <= d) r++;
+                    ctx->hBlockRun[b] = r;
+                }
+            }
+        }
+        ctx->frameRunMode = runMode;
+        const size_t slimBytes = runMode ? 64 : ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
+        Seg head[5] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
+                       {ctx->hRot.p, 4ull * ctx->hRot.n, 0},
+                       {ctx->hRuns.data(), runMode ? sizeof(DrawRun) * ctx->hRuns.size() : 0, 0},
+                       {ctx->hBlockRun.data(), runMode ? 4ull * ctx->hBlockRun.size() : 0, 0}};
         Seg segs[13] = {
             {nullptr, 0, 0}, {nullptr, 0, 0} /* vbase / tbase: k_prep_draws writes the device tables from the placement records */,
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
@@ -735,8 +784,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         if (!ctx->transformsAffine) memcpy(ctx->hFrame.p, ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws);
         else for (uint32_t d = 0; d < nDraws; d++) {
             const DrawSlim& S = ctx->hSlim.p[d];
-            uint8_t* o = ctx->hFrame.p + slimBytes * (size_t)d;
-            memcpy(o, &S, 32);                                          // header
+            uint8_t* o = ctx->hFrame.p + slimBytes * (size_t)d - (runMode ? 32 : 0);      // run mode: no header, payload only
+            if (!runMode) memcpy(o, &S, 32);                            // header
             float* t = reinterpret_cast<float*>(o + 32);
             for (int r = 0; r < 4; r++) { t[3 * r] = S.transform[4 * r]; t[3 * r + 1] = S.transform[4 * r + 1]; t[3 * r + 2] = S.transform[4 * r + 2]; }
             memcpy(o + 32 + 48, S.color, 16);
@@ -755,6 +804,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
         CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
         ctx->frameHeadBytes = headBytes; ctx->frameRestBytes = restBytes; ctx->frameTmplOff = head[1].off; ctx->frameRotOff = head[2].off;
+        ctx->frameRunsOff = head[3].off; ctx->frameBlockRunOff = head[4].off;
         ctx->frameLightsOff = headBytes + segs[6].off;
         uint8_t* base = ctx->dFrame.as<uint8_t>();
         uint8_t* rest = base + devDrawBytes;
@@ -807,7 +857,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                           reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
                           hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
-                          ctx->pVbase, ctx->pTbase);
+                          ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
+                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff));
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};

@@ -115,6 +115,19 @@ struct __align__(16) DrawSlim {
     float color[4];
 };
 static const uint32_t NO_ROTATION = 0xFFFFFFFFu;
+
+// Run-length form of the placement records, used for frames dominated by long runs of one template (particles,
+// instanced scenery): a run is a sequence of consecutive draws whose DrawSlim headers progress regularly, so the
+// header travels once per run and each draw ships only its transform rows and colour (64 bytes).
+struct __align__(16) DrawRun {
+    uint32_t first, count;      // draws [first, first + count)
+    uint32_t tmpl;
+    uint32_t vbase, tbase, boneOffset, lightU, rot;     // of the run's first draw
+    uint32_t dV, dT, dBone, dLightU, dRot;              // per-draw increments (dRot is 0 or 1; rot stays NO_ROTATION when 0)
+    uint32_t pad[3];
+};
+static_assert(sizeof(DrawRun) == 64, "DrawRun is staged as four uint4");
+static const uint32_t RUN_MODE_MIN_AVG = 8;     // average run length from which a frame is shipped in run-length form
 static_assert(sizeof(DrawSlim) == 112, "DrawSlim is staged as seven uint4");
 
 static_assert(offsetof(DrawRec, transform) % 16 == 0 && offsetof(DrawRec, worldRot) % 16 == 0 &&

@@ -81,6 +81,8 @@ struct PrepFrame {
     // rows 0-3 x columns 0-2; column 3 is exactly 0,0,0,1)
     uint32_t slim16;
     uint32_t* devVbase; uint32_t* devTbase;     // [nDraws + 1] arena offsets per draw: written here from the records, not copied
+    // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
+    const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
 };
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -130,9 +132,38 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     const uint32_t d0 = blockIdx.x * PREP_DRAWS;
     const uint32_t n = min((uint32_t)PREP_DRAWS, pf.nDraws - d0);
     constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
-    const bool known = blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
+    const bool known = !pf.runMode && blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
     uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
     const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
+    if (pf.runMode) {
+        // Round trip 1: this block's payloads (4 uint4 per draw: three of transform rows, one of colour) go straight into
+        // the packed record layout {header 2 | transform 3 | colour 1}; the runs covering the block; the light table.
+        const uint4* src = pf.hostSlim + (size_t)d0 * 4;
+        const uint32_t r0 = pf.hostBlockRun[blockIdx.x], r1 = pf.hostBlockRun[blockIdx.x + 1];
+        uint4 pv;
+        if (threadIdx.x < n * 4) pv = src[threadIdx.x];
+        const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(pf.hostLights);
+        uint32_t* ldst = reinterpret_cast<uint32_t*>(sL);
+        const uint32_t nw = lightsStaged ? pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4) : 0u;
+        for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) ldst[i] = lsrc[i];
+        if (threadIdx.x < n * 4) sSraw[(threadIdx.x >> 2) * s16 + 2 + (threadIdx.x & 3)] = pv;
+        // Round trip 2: the runs [r0, r1] (at most one per draw), parked where the templates will go
+        const uint32_t nR = min(r1 - r0 + 1, (uint32_t)PREP_DRAWS);       // a 65th run could only start at the next block's first draw
+        if (threadIdx.x < nR * 4) sT[threadIdx.x] = pf.hostRuns[(size_t)r0 * 4 + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x < n) {      // header of draw d from its run
+            const uint32_t d = d0 + threadIdx.x;
+            const DrawRun* runs = reinterpret_cast<const DrawRun*>(sT);
+            uint32_t r = 0;
+            while (r + 1 < nR && runs[r + 1].first <= d) r++;
+            const DrawRun& U = runs[r];
+            const uint32_t i = d - U.first;
+            uint32_t* h = reinterpret_cast<uint32_t*>(sSraw + threadIdx.x * s16);      // DrawSlim header: tmpl vbase tbase boneOffset | lightU rot pad pad
+            h[0] = U.tmpl; h[1] = U.vbase + i * U.dV; h[2] = U.tbase + i * U.dT; h[3] = U.boneOffset + i * U.dBone;
+            h[4] = U.lightU + i * U.dLightU; h[5] = U.dRot ? U.rot + i : U.rot; h[6] = 0; h[7] = 0;
+        }
+        __syncthreads();            // the runs are consumed: the template window may overwrite them
+    } else
     {   // slim records (7 uint4 each), and for the first blocks the templates and rotations in the same round trip
         const uint4* src = pf.hostSlim + (size_t)d0 * s16;
         uint4* dst = sSraw;
@@ -164,6 +195,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     }
     const t3d_light* lightsIn = lightsStaged ? sL : pf.hostLights;
     __syncthreads();
+    static_assert(PREP_THREADS >= PREP_DRAWS * 4, "one sweep stages a block's payloads and runs");
     if (!known) {
         // later blocks find their windows in the slim records: a window of template indices (the host reuses one of
         // its most recent templates when it can, so the window is small) and an ascending run of rotation indices
@@ -1278,7 +1310,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
-                       uint32_t* devVbase, uint32_t* devTbase) {
+                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_BYTES);     // per device; cheap
     PrepFrame pf;
@@ -1292,6 +1324,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.nBones = nBones; pf.bonesPacked = bonesPacked ? 1u : 0u;
     pf.slim16 = slimPacked ? SLIM16 - 1 : SLIM16;
     pf.devVbase = devVbase; pf.devTbase = devTbase;
+    pf.hostRuns = reinterpret_cast<const uint4*>(hostRuns); pf.hostBlockRun = hostBlockRun; pf.runMode = hostRuns ? 1u : 0u;
     const uint32_t nCopy = std::max(pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u,
                                     nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
