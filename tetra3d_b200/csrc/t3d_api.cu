@@ -123,6 +123,7 @@ struct t3d_ctx {
     void* hFrameDev = nullptr; void* pDevRest = nullptr;
     size_t frameHeadBytes = 0, frameRestBytes = 0, frameTmplOff = 0, frameRotOff = 0, frameLightsOff = 0, frameBonesOff = 0;
     size_t frameRunsOff = 0, frameBlockRunOff = 0; bool frameRunMode = false;
+    uint32_t blkTmin = 0, blkTmax = 0, tmplSpanMax = 1;     // widest template-index window of any 64-draw block (sizes k_prep_draws' staging)
     uint32_t frameBoneCount = 0;
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVClass[3] = {nullptr, nullptr, nullptr}, *pHuge = nullptr;
     TriTile* pTiles = nullptr;
@@ -413,6 +414,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->vAcc = ctx->tAcc = ctx->luAcc = 0;
     ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
+    ctx->tmplSpanMax = 1;
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
     return T3D_OK;
@@ -553,6 +555,9 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
                     ctx->hRot.n += 16;
                 }
             }
+            if (ctx->hSlim.n % PREP_WINDOW_DRAWS == 0) ctx->blkTmin = ctx->blkTmax = tmplIndex;
+            ctx->blkTmin = std::min(ctx->blkTmin, tmplIndex); ctx->blkTmax = std::max(ctx->blkTmax, tmplIndex);
+            ctx->tmplSpanMax = std::max(ctx->tmplSpanMax, ctx->blkTmax - ctx->blkTmin + 1);
             CU(ctx->hSlim.push(S));
         }
         // k_vertex<K1_STATIC / K1_SKINNED> (t3d_kernels.cu: shade_vertex): no shape keys, no unbillboarded depth (ignored for
@@ -858,7 +863,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
                           hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
                           ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
-                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff));
+                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax);
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};

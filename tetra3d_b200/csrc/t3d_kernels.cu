@@ -58,9 +58,11 @@ static const int PREP_PARAM_BLOCKS = PREP_WINDOW_BLOCKS;
 static_assert(PREP_DRAWS == PREP_WINDOW_DRAWS, "t3d_internal.h: the host computes the windows per PREP_DRAWS draws");
 static const int REC16 = sizeof(DrawRec) / 16;
 static const int SLIM16 = sizeof(DrawSlim) / 16;
-static const size_t PREP_SMEM_BYTES = (size_t)PREP_DRAWS * sizeof(DrawRec) + (size_t)PREP_DRAWS * sizeof(DrawSlim) +
-                                      (size_t)PREP_TEMPLATES * sizeof(DrawRec) + (size_t)PREP_DRAWS * 64 +
-                                      (size_t)PREP_SMEM_LIGHTS * sizeof(t3d_light);
+// shared memory: records | slim records | rotations (run mode parks the runs here first) | templates [tmplCap] | lights
+// [lightCap]; the last two are sized per frame, so frames with few templates and lights run more blocks per SM and keep
+// more PCIe reads in flight
+static const size_t PREP_SMEM_FIXED = (size_t)PREP_DRAWS * sizeof(DrawRec) + (size_t)PREP_DRAWS * sizeof(DrawSlim) + (size_t)PREP_DRAWS * 64;
+static const size_t PREP_SMEM_MAX = PREP_SMEM_FIXED + (size_t)PREP_TEMPLATES * sizeof(DrawRec) + (size_t)PREP_SMEM_LIGHTS * sizeof(t3d_light);
 
 struct PrepFrame {
     const uint4* hostSlim;      // DrawSlim[nDraws]          (pinned host, UVA)
@@ -83,9 +85,13 @@ struct PrepFrame {
     uint32_t* devVbase; uint32_t* devTbase;     // [nDraws + 1] arena offsets per draw: written here from the records, not copied
     // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
+    uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
 };
 
-__global__ void __launch_bounds__(PREP_THREADS)
+#ifndef T3D_PREP_MINBLOCKS
+#define T3D_PREP_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(PREP_THREADS, T3D_PREP_MINBLOCKS)
 k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ FrameConst fc,
              LightU* __restrict__ lightsU, DrawStat* __restrict__ stats) {
     extern __shared__ uint4 prepSmem[];
@@ -126,15 +132,15 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     uint4* sSraw = prepSmem + PREP_DRAWS * REC16;
     const uint32_t s16 = pf.slim16;                      // record stride; the 32-byte header is the same in both layouts
     auto slimOf = [&](uint32_t kk) -> const DrawSlim& { return *reinterpret_cast<const DrawSlim*>(sSraw + kk * s16); };
-    uint4* sT = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
-    uint4* sRot = sT + PREP_TEMPLATES * REC16;
-    t3d_light* sL = reinterpret_cast<t3d_light*>(sRot + PREP_DRAWS * 4);
+    uint4* sRot = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
+    uint4* sT = sRot + PREP_DRAWS * 4;
+    t3d_light* sL = reinterpret_cast<t3d_light*>(sT + pf.tmplCap * REC16);
     const uint32_t d0 = blockIdx.x * PREP_DRAWS;
     const uint32_t n = min((uint32_t)PREP_DRAWS, pf.nDraws - d0);
     constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
     const bool known = !pf.runMode && blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
     uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
-    const bool lightsStaged = pf.nLightsIn <= PREP_SMEM_LIGHTS;
+    const bool lightsStaged = pf.nLightsIn <= pf.lightCap;
     if (pf.runMode) {
         // Round trip 1: this block's payloads (4 uint4 per draw: three of transform rows, one of colour) go straight into
         // the packed record layout {header 2 | transform 3 | colour 1}; the runs covering the block; the light table.
@@ -147,13 +153,13 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const uint32_t nw = lightsStaged ? pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4) : 0u;
         for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) ldst[i] = lsrc[i];
         if (threadIdx.x < n * 4) sSraw[(threadIdx.x >> 2) * s16 + 2 + (threadIdx.x & 3)] = pv;
-        // Round trip 2: the runs [r0, r1] (at most one per draw), parked where the templates will go
+        // Round trip 2: the runs [r0, r1] (at most one per draw), parked where the rotations will go
         const uint32_t nR = min(r1 - r0 + 1, (uint32_t)PREP_DRAWS);       // a 65th run could only start at the next block's first draw
-        if (threadIdx.x < nR * 4) sT[threadIdx.x] = pf.hostRuns[(size_t)r0 * 4 + threadIdx.x];
+        if (threadIdx.x < nR * 4) sRot[threadIdx.x] = pf.hostRuns[(size_t)r0 * 4 + threadIdx.x];
         __syncthreads();
         if (threadIdx.x < n) {      // header of draw d from its run
             const uint32_t d = d0 + threadIdx.x;
-            const DrawRun* runs = reinterpret_cast<const DrawRun*>(sT);
+            const DrawRun* runs = reinterpret_cast<const DrawRun*>(sRot);
             uint32_t r = 0;
             while (r + 1 < nR && runs[r + 1].first <= d) r++;
             const DrawRun& U = runs[r];
@@ -162,7 +168,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
             h[0] = U.tmpl; h[1] = U.vbase + i * U.dV; h[2] = U.tbase + i * U.dT; h[3] = U.boneOffset + i * U.dBone;
             h[4] = U.lightU + i * U.dLightU; h[5] = U.dRot ? U.rot + i : U.rot; h[6] = 0; h[7] = 0;
         }
-        __syncthreads();            // the runs are consumed: the template window may overwrite them
+        __syncthreads();            // the runs are consumed: the rotation window may overwrite them
     } else
     {   // slim records (7 uint4 each), and for the first blocks the templates and rotations in the same round trip
         const uint4* src = pf.hostSlim + (size_t)d0 * s16;
@@ -171,7 +177,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         uint4 v[2], tv[T_SWEEPS], rv;
 #pragma unroll
         for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
-        const uint32_t t16 = known ? pf.win[blockIdx.x][1] * REC16 : 0u, r16 = known ? pf.win[blockIdx.x][3] * 4 : 0u;
+        const uint32_t t16 = known ? min(pf.win[blockIdx.x][1], pf.tmplCap) * REC16 : 0u, r16 = known ? pf.win[blockIdx.x][3] * 4 : 0u;
         const uint4* tsrc = pf.hostTmpl + (size_t)tmin * REC16;
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) tv[u] = tsrc[i]; }
@@ -206,7 +212,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
             tmin = min(tmin, t); tmax = max(tmax, t);
             if (r != NO_ROTATION) { rmin = min(rmin, r); rmax = max(rmax, r); }
         }
-        const uint32_t n16 = min(tmax - tmin + 1, (uint32_t)PREP_TEMPLATES) * REC16;
+        const uint32_t n16 = min(tmax - tmin + 1, pf.tmplCap) * REC16;
         const uint4* src = pf.hostTmpl + (size_t)tmin * REC16;
         uint4 v[T_SWEEPS];
 #pragma unroll
@@ -228,7 +234,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const DrawSlim& S = slimOf(k);
         uint4* dst = reinterpret_cast<uint4*>(&sR[k]);
         const uint32_t ti = S.tmpl - tmin;
-        const uint4* src = ti < (uint32_t)PREP_TEMPLATES ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
+        const uint4* src = ti < pf.tmplCap ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
         const uint4* sl = reinterpret_cast<const uint4*>(&S);
         const uint4* rs = S.rot != NO_ROTATION ? sRot + (size_t)(S.rot - rmin) * 4 : nullptr;
         constexpr int TR16 = offsetof(DrawRec, transform) / 16, WR16 = offsetof(DrawRec, worldRot) / 16, CO16 = offsetof(DrawRec, color) / 16;
@@ -1310,9 +1316,9 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
-                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun) {
+                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax) {
     if (!nDraws) return;
-    cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_BYTES);     // per device; cheap
+    cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
     PrepFrame pf;
     pf.hostSlim = reinterpret_cast<const uint4*>(hostSlim); pf.hostTmpl = reinterpret_cast<const uint4*>(hostTmpl);
     pf.hostRot = reinterpret_cast<const uint4*>(hostRot); pf.hostRest = reinterpret_cast<const uint4*>(hostRest);
@@ -1325,11 +1331,18 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.slim16 = slimPacked ? SLIM16 - 1 : SLIM16;
     pf.devVbase = devVbase; pf.devTbase = devTbase;
     pf.hostRuns = reinterpret_cast<const uint4*>(hostRuns); pf.hostBlockRun = hostBlockRun; pf.runMode = hostRuns ? 1u : 0u;
+    pf.tmplCap = std::min<uint32_t>(std::max(tmplSpanMax, 1u), PREP_TEMPLATES);
+    pf.lightCap = nLightsIn <= PREP_SMEM_LIGHTS ? nLightsIn : 0u;
+#ifdef T3D_PREP_SMEM_STATIC
+    const size_t smem = PREP_SMEM_MAX;
+#else
+    const size_t smem = PREP_SMEM_FIXED + (size_t)pf.tmplCap * sizeof(DrawRec) + (size_t)pf.lightCap * sizeof(t3d_light);
+#endif
     const uint32_t nCopy = std::max(pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u,
                                     nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
-    launch_kernel(k_prep_draws, pf.nPrepBlocks + nCopy, PREP_THREADS, PREP_SMEM_BYTES, s, false, pf, fc, lightsU, stats);
+    launch_kernel(k_prep_draws, pf.nPrepBlocks + nCopy, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats);
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
