@@ -132,9 +132,9 @@ def fuzz_scene(seed: int) -> SceneDesc:
     return SceneDesc(models, lights, cam, world, name="fuzz%d" % seed)
 
 
-def skinned_scene(seed=0, n=6) -> SceneDesc:
+def skinned_scene(seed=0, n=6, rings=9, sides=10) -> SceneDesc:
     rng = np.random.default_rng(seed)
-    mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=5)
+    mesh, bone_y = W.tube_character_mesh(rings=rings, sides=sides, n_bones=5)
     # make some weights exactly 0 / 1 and vary the influence count to reach every branch of skinVertex
     w = mesh.weights.copy(); n_inf = mesh.n_influences.copy()
     w[::7, 0] = 1.0; w[::7, 1] = 0.0

@@ -66,6 +66,22 @@ def test_huge_draw_parity(device):
     assert_parity(scenes.tile_boundary_scene(35, sizes=(66000, 9000, 300, 131073)), device, check_capture=False)
 
 
+def test_mid_size_draws_parity(device):
+    # draws of 9 .. 64 tiles (segmented sort, histogram scan by the draw's last block), a last tile of one triangle, the
+    # largest such draw (65 536) next to the smallest one whose scan runs in k_hist_scan_huge (65 537)
+    assert_parity(scenes.tile_boundary_scene(41, sizes=(8193, 9217, 15360, 16385, 20000, 700, 33000)), device, check_capture=False)
+    assert_parity(scenes.tile_boundary_scene(42, sizes=(65536, 65537, 12000, 8192, 40001)), device, check_capture=False)
+
+
+def test_mid_size_draws_skinned_and_culled_parity(device):
+    # a skinned draw above 8192 triangles (depth from the skinned positions) and a large draw with no survivors
+    sc = scenes.skinned_scene(7, n=2, rings=60, sides=80)
+    assert_parity(sc, device, check_capture=False)
+    sc = scenes.tile_boundary_scene(43, sizes=(10000, 9000))
+    sc.models[0].node.position = (0.0, 0.0, 500.0)        # behind the camera: everything culled
+    assert_parity(sc, device, check_capture=False)
+
+
 def test_non_affine_bone_matrices_parity(device):
     # bone matrices normally travel as 12 floats (column 3 is exactly 0,0,0,1); one that is not switches the frame to
     # the full 16-float upload
