@@ -215,6 +215,35 @@ typedef struct t3d_frame_output {
     const t3d_draw_result* draws;       /* n_draws, submit order */
 } t3d_frame_output;
 
+/* ---- bone poses evaluated on the device (the step before the path: SURVEY.md 8f N2) ---------------
+ * A skeleton is the joint list of a skin (gltf.go:1452-1511): per bone its parent inside the list, its
+ * Node.inverseBindMatrix and the local position / scale / rotation the bone's Node holds when no animation
+ * track overrides them.  An animation holds, per bone, the three AnimationTracks of the bone's
+ * AnimationChannel (animation.go:168-173): keyframe times and values.  With both resident, a frame ships one
+ * t3d_pose (playhead + the transform the root bones hang from) per armature instead of n_bones matrices. */
+enum { T3D_INTERPOLATION_LINEAR = 0, T3D_INTERPOLATION_CONSTANT = 1, T3D_INTERPOLATION_CUBIC = 2 /* evaluated as linear, animation.go:107 */ };
+typedef struct t3d_skeleton_desc {
+    uint32_t        n_bones;
+    const int32_t*  parent;         /* [n] parent bone, or -1: child of t3d_pose.root; a parent precedes its children */
+    const float*    inverse_bind;   /* [n][16] */
+    const float*    rest_position;  /* [n][3] */
+    const float*    rest_scale;     /* [n][3] */
+    const float*    rest_rotation;  /* [n][16] */
+} t3d_skeleton_desc;
+typedef struct t3d_track { uint32_t first_key, n_keys, interpolation; } t3d_track;   /* n_keys == 0: the bone has no such track */
+typedef struct t3d_animation_desc {
+    uint32_t         n_bones;       /* bones [0, n_bones) of the skeleton it is played on */
+    const t3d_track* tracks;        /* [n_bones][3]: TrackTypePosition, TrackTypeScale, TrackTypeRotation */
+    uint32_t         n_keys;        /* keyframes over all tracks */
+    const float*     key_times;     /* [n_keys] Keyframe.Time, non-decreasing inside a track */
+    const float*     key_values;    /* [n_keys][4] Keyframe.Data: x y z _ or quaternion x y z w */
+} t3d_animation_desc;
+typedef struct t3d_pose {
+    float root[16];                 /* Transform() of the node the skeleton's root bones are children of */
+    float playhead;                 /* AnimationPlayer playhead the tracks are sampled at (animation.go:686-712) */
+    float reserved[3];
+} t3d_pose;
+
 typedef struct t3d_ctx t3d_ctx;
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */
@@ -233,6 +262,12 @@ int t3d_mesh_release(t3d_ctx* ctx, uint64_t mesh_id);
 int t3d_volume_upload(t3d_ctx* ctx, uint32_t volume_id, const t3d_volume_desc* desc);
 int t3d_volume_release(t3d_ctx* ctx, uint32_t volume_id);
 
+/* Skeletons and animations for t3d_submit_poses; animation_id 0 is "no animation" (rest pose). */
+int t3d_skeleton_upload(t3d_ctx* ctx, uint64_t skeleton_id, const t3d_skeleton_desc* desc);
+int t3d_skeleton_release(t3d_ctx* ctx, uint64_t skeleton_id);
+int t3d_animation_upload(t3d_ctx* ctx, uint64_t animation_id, const t3d_animation_desc* desc);
+int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id);
+
 /* ---- per frame ---------------------------------------------------------------------------------- */
 /* Replaces: the prologue of Camera.Render that fixes vpMatrix / camera constants (camera.go:1329-1341). */
 int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world);
@@ -242,6 +277,13 @@ int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_
 /* Replaces: reading bone.boneInfluence per vertex (model.go:574-580, node.go:592-594).  Appends n
  * matrices to the frame's bone arena and returns the offset of the first in *offset. */
 int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset);
+/* Replaces: AnimationTrack.ValueAsVector / ValueAsQuaternion for every channel (animation.go:63-164, 674-722), the
+ * SetLocalPosition / Scale / Rotation calls of AnimationPlayer.forceUpdate without blending or relative motion
+ * (animation.go:961-980), Node.Transform of every bone and its boneInfluence (node.go:572-594) -- for n armatures
+ * playing `animation_id` on `skeleton_id`.  The device evaluates them at t3d_frame_execute; pose i's matrices are
+ * bones [*offset + i * n_bones, *offset + (i + 1) * n_bones) of the same arena t3d_submit_bones fills (the
+ * returned offset carries a tag bit: pass it through t3d_draw.bone_offset unchanged, adding i * n_bones). */
+int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset);
 /* Replaces: one render(rp) call (camera.go:1507-1827) per element, in render order. */
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
 /* Replaces: Model.ProcessVertices + the lighting and emit loops for all submitted draws.
@@ -281,6 +323,9 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
                                  float* clip4, float* light4);
 /* Model transforms and bone matrices whose column 3 is exactly (0, 0, 0, 1) cross PCIe as 12 floats.  enabled = 1
  * ships all 16 always (what happens by itself as soon as one matrix of a frame is not affine); for tests. */
+/* Reads n matrices of the executed frame's bone arena back; `offset` as it would be passed in t3d_draw.bone_offset
+ * (so offsets returned by t3d_submit_poses read the device-evaluated poses). */
+int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matrices16);
 int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled);
 /* Number of kernels launched by the last t3d_frame_execute. */
 int t3d_debug_last_launch_count(t3d_ctx* ctx);

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from tetra3d_b200.scenedesc import (LIGHT_VOLUME, MaterialDesc, MeshDesc, NodeDesc, SceneDesc)
+from tetra3d_b200.scenedesc import (LIGHT_VOLUME, AnimationDesc, MaterialDesc, MeshDesc, NodeDesc, SceneDesc, SkeletonDesc)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libt3doracle.so")
@@ -115,6 +115,19 @@ class orc_result(C.Structure):
                 ("t_process", C.c_double), ("t_light", C.c_double), ("t_emit", C.c_double)]
 
 
+class orc_track(C.Structure):
+    _fields_ = [("first_key", C.c_int32), ("n_keys", C.c_int32), ("interpolation", C.c_int32)]
+
+
+class orc_skeleton(C.Structure):
+    _fields_ = [("n_bones", C.c_int32), ("parent", i32p), ("inverse_bind", f32p), ("rest_position", f32p),
+                ("rest_scale", f32p), ("rest_rotation", f32p)]
+
+
+class orc_animation(C.Structure):
+    _fields_ = [("n_bones", C.c_int32), ("tracks", C.POINTER(orc_track)), ("key_times", f32p), ("key_values", f32p)]
+
+
 _lib = None
 
 
@@ -152,6 +165,11 @@ def lib():
         L.orc_bin_index.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
         L.orc_bin_index.restype = C.c_int
         L.orc_node_transform.argtypes = [C.POINTER(orc_node), C.c_int32, f32p]
+        L.orc_pose_bones.argtypes = [C.POINTER(orc_skeleton), C.POINTER(orc_animation), C.c_float, f32p, f32p]
+        L.orc_quat_slerp.argtypes = [f32p, f32p, C.c_float, f32p]
+        L.orc_quat_to_matrix.argtypes = [f32p, f32p]
+        L.orc_go_sin.argtypes = [C.c_double]; L.orc_go_sin.restype = C.c_double
+        L.orc_go_atan2.argtypes = [C.c_double, C.c_double]; L.orc_go_atan2.restype = C.c_double
         _lib = L
     return _lib
 
@@ -219,6 +237,81 @@ def triangle_centers(positions: np.ndarray, indices: np.ndarray) -> np.ndarray:
     p = np.ascontiguousarray(positions, np.float32); i = np.ascontiguousarray(indices, np.uint32)
     out = np.zeros((len(i.reshape(-1, 3)), 3), np.float32)
     lib().orc_triangle_centers(_fp(p), i.ctypes.data_as(u32p), len(out), _fp(out)); return out
+
+
+# ---- bone poses (animation.go, quaternion.go, node.go:572-594) -------------------------------------------
+def go_sin(x: float) -> float:
+    return float(lib().orc_go_sin(float(x)))
+
+
+def go_atan2(y: float, x: float) -> float:
+    return float(lib().orc_go_atan2(float(y), float(x)))
+
+
+def quat_slerp(a, b, percent: float) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32); out = np.zeros(4, np.float32)
+    lib().orc_quat_slerp(_fp(a), _fp(b), float(percent), _fp(out))
+    return out
+
+
+def quat_to_matrix(q) -> np.ndarray:
+    q = np.ascontiguousarray(q, np.float32); out = np.zeros(16, np.float32)
+    lib().orc_quat_to_matrix(_fp(q), _fp(out))
+    return out.reshape(4, 4)
+
+
+def node_world_transform(nd: NodeDesc) -> np.ndarray:
+    """Node.Transform() (node.go:572-608) of a NodeDesc with its chain of parents."""
+    chain = []
+    while nd is not None:
+        chain.append(nd); nd = nd.parent
+    arr = (orc_node * len(chain))()
+    for i, n in enumerate(chain):
+        arr[i].position[:] = [float(x) for x in n.position]; arr[i].scale[:] = [float(x) for x in n.scale]
+        arr[i].rotation[:] = [float(x) for x in np.asarray(n.rotation, np.float32).reshape(16)]
+        arr[i].parent = i + 1 if i + 1 < len(chain) else -1
+    out = np.zeros(16, np.float32)
+    lib().orc_node_transform(arr, 0, _fp(out))
+    return out
+
+
+def flatten_animation(anim: AnimationDesc, sk: SkeletonDesc):
+    """Per bone of `sk` the three tracks of the channel carrying the bone's name (assignChannels, animation.go:618-672)."""
+    n = len(sk.names)
+    tracks = np.zeros((n, 3, 3), np.int32)
+    times, values = [], []
+    k = 0
+    for b, name in enumerate(sk.names):
+        ch = anim.channels.get(name, {})
+        for t in range(3):
+            td = ch.get(t)
+            tracks[b, t, 0] = k
+            if td is None:
+                continue
+            tracks[b, t, 1] = len(td.times); tracks[b, t, 2] = int(td.interpolation)
+            times.append(td.times); values.append(td.values); k += len(td.times)
+    kt = np.concatenate(times).astype(np.float32) if times else np.zeros(1, np.float32)
+    kv = np.concatenate(values).astype(np.float32).reshape(-1, 4) if values else np.zeros((1, 4), np.float32)
+    return tracks, np.ascontiguousarray(kt), np.ascontiguousarray(kv)
+
+
+def pose_bones(sk: SkeletonDesc, anim: Optional[AnimationDesc], playhead: float, root16) -> np.ndarray:
+    """boneInfluence of every bone of an armature posed at `playhead`: (n_bones, 16)."""
+    L = lib()
+    cs = orc_skeleton()
+    cs.n_bones = len(sk.parent); cs.parent = sk.parent.ctypes.data_as(i32p); cs.inverse_bind = _fp(sk.inverse_bind)
+    cs.rest_position = _fp(sk.rest_position); cs.rest_scale = _fp(sk.rest_scale); cs.rest_rotation = _fp(sk.rest_rotation)
+    ca = None
+    if anim is not None:
+        tracks, kt, kv = flatten_animation(anim, sk)
+        ct = (orc_track * (3 * len(sk.parent)))()
+        for i, (f, n, ip) in enumerate(tracks.reshape(-1, 3)):
+            ct[i].first_key = int(f); ct[i].n_keys = int(n); ct[i].interpolation = int(ip)
+        ca = orc_animation(); ca.n_bones = len(sk.parent); ca.tracks = ct; ca.key_times = _fp(kt); ca.key_values = _fp(kv)
+    root = np.ascontiguousarray(root16, np.float32).reshape(16)
+    out = np.zeros((len(sk.parent), 16), np.float32)
+    L.orc_pose_bones(C.byref(cs), C.byref(ca) if ca is not None else None, float(playhead), _fp(root), _fp(out))
+    return out
 
 
 def bin_index(depth, mn, mx, sort_mode) -> int:
@@ -369,8 +462,11 @@ class _Marshalled:
             cm.node = node_of(md.node); cm.mesh = mesh_index[id(md.mesh)]
             cm.color[:] = [float(x) for x in md.color]
             cm.shadeless = int(md.shadeless); cm.visible = int(md.visible); cm.frustum_culling = int(md.frustum_culling)
-            if md.bone_influences is not None:
-                b = np.ascontiguousarray(md.bone_influences, np.float32).reshape(-1, 16); self.keep.append(b)
+            bi = md.bone_influences
+            if md.pose is not None:     # bones posed from a skeleton + animation: the oracle's own restatement of that step
+                bi = pose_bones(md.pose.skeleton, md.pose.animation, md.pose.playhead, node_world_transform(md.pose.root))
+            if bi is not None:
+                b = np.ascontiguousarray(bi, np.float32).reshape(-1, 16); self.keep.append(b)
                 cm.skinned = 1; cm.n_bones = len(b); cm.bone_influences = _fp(b)
             cm.light_group = group_index[id(md.light_group)] if md.light_group is not None else -1
             cm.batch_owner = model_index[id(md.batch_owner)] if md.batch_owner is not None else -1

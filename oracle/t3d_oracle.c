@@ -1492,3 +1492,224 @@ void orc_free_result(orc_result* r) {
     free(r->index_list); free(r->tri_ids); free(r->cap_clip); free(r->cap_light);
     free(r);
 }
+
+/* ================================================================================================
+ * Bone poses: animation.go, quaternion.go, node.go:572-594
+ * ================================================================================================ */
+
+/* Go's math.Sin for amd64 (pure Go, src/math/sin.go; Cephes sinl.c coefficients).  Arguments reach it from Slerp in
+ * [0, pi], far below the Payne-Hanek threshold (reduceThreshold = 1 << 29), which is therefore not restated: larger
+ * arguments fall back to libm.  The hexadecimal literals are the bit patterns Go's source lists next to each constant. */
+static const double GO_SIN[6] = {
+    1.58962301576546568060e-10,   /* 0x3de5d8fd1fd19ccd */
+    -2.50507477628578072866e-8,   /* 0xbe5ae5e5a9291f5d */
+    2.75573136213857245213e-6,    /* 0x3ec71de3567d48a1 */
+    -1.98412698295895385996e-4,   /* 0xbf2a01a019bfdf03 */
+    8.33333333332211858878e-3,    /* 0x3f8111111110f7d0 */
+    -1.66666666666666307295e-1,   /* 0xbfc5555555555548 */
+};
+static const double GO_COS[6] = {
+    -1.13585365213876817300e-11,  /* 0xbda8fa49a0861a9b */
+    2.08757008419747316778e-9,    /* 0x3e21ee9d7b4e3f05 */
+    -2.75573141792967388112e-7,   /* 0xbe927e4f7eac4bc6 */
+    2.48015872888517045348e-5,    /* 0x3efa01a019c844f5 */
+    -1.38888888888730564116e-3,   /* 0xbf56c16c16c14f91 */
+    4.16666666666665929218e-2,    /* 0x3fa555555555554b */
+};
+#define GO_PI 3.14159265358979323846264338327950288419716939937510582097494459
+double orc_go_sin(double x) {
+    const double PI4A = 7.85398125648498535156e-1;   /* 0x3fe921fb40000000 */
+    const double PI4B = 3.77489470793079817668e-8;   /* 0x3e64442d00000000 */
+    const double PI4C = 2.69515142907905952645e-15;  /* 0x3ce8469898cc5170 */
+    if (x == 0 || isnan(x)) return x;
+    if (isinf(x)) return NAN;
+    int sign = 0;
+    if (x < 0) { x = -x; sign = 1; }
+    if (x >= 536870912.0) return sign ? -sin(x) : sin(x);     /* reduceThreshold: trigReduce is not restated */
+    uint64_t j = (uint64_t)(x * (4 / GO_PI));        /* integer part of x / (Pi/4) */
+    double y = (double)j;
+    if (j & 1) { j++; y++; }                         /* map zeros to origin */
+    j &= 7;                                          /* octant modulo 2 Pi */
+    double z = ((x - y * PI4A) - y * PI4B) - y * PI4C;   /* extended precision modular arithmetic */
+    if (j > 3) { sign = !sign; j -= 4; }
+    const double zz = z * z;
+    if (j == 1 || j == 2)
+        y = 1.0 - 0.5 * zz + zz * zz * ((((((GO_COS[0] * zz) + GO_COS[1]) * zz + GO_COS[2]) * zz + GO_COS[3]) * zz + GO_COS[4]) * zz + GO_COS[5]);
+    else
+        y = z + z * zz * ((((((GO_SIN[0] * zz) + GO_SIN[1]) * zz + GO_SIN[2]) * zz + GO_SIN[3]) * zz + GO_SIN[4]) * zz + GO_SIN[5]);
+    return sign ? -y : y;
+}
+
+/* Go's math.Atan (src/math/atan.go: xatan / satan, Cephes atan.c). */
+static double go_xatan(double x) {
+    const double P0 = -8.750608600031904122785e-01, P1 = -1.615753718733365076637e+01, P2 = -7.500855792314704667340e+01,
+                 P3 = -1.228866684490136173410e+02, P4 = -6.485021904942025371773e+01;
+    const double Q0 = +2.485846490142306297962e+01, Q1 = +1.650270098316988542046e+02, Q2 = +4.328810604912902668951e+02,
+                 Q3 = +4.853903996359136964868e+02, Q4 = +1.945506571482613964425e+02;
+    double z = x * x;
+    z = z * ((((P0 * z + P1) * z + P2) * z + P3) * z + P4) / (((((z + Q0) * z + Q1) * z + Q2) * z + Q3) * z + Q4);
+    z = x * z + x;
+    return z;
+}
+static double go_satan(double x) {
+    const double Morebits = 6.123233995736765886130e-17;   /* pi/2 = PIO2 + Morebits */
+    const double Tan3pio8 = 2.41421356237309504880;        /* tan(3*pi/8) */
+    if (x <= 0.66) return go_xatan(x);
+    if (x > Tan3pio8) return GO_PI / 2 - go_xatan(1 / x) + Morebits;
+    return GO_PI / 4 + go_xatan((x - 1) / (x + 1)) + 0.5 * Morebits;
+}
+static double go_atan(double x) {
+    if (x == 0) return x;
+    if (x > 0) return go_satan(x);
+    return -go_satan(-x);
+}
+double orc_go_atan2(double y, double x) {              /* src/math/atan2.go */
+    if (isnan(y) || isnan(x)) return NAN;
+    if (y == 0) {
+        if (x >= 0 && !signbit(x)) return copysign(0, y);
+        return copysign(GO_PI, y);
+    }
+    if (x == 0) return copysign(GO_PI / 2, y);
+    if (isinf(x)) {
+        if (x > 0) return isinf(y) ? copysign(GO_PI / 4, y) : copysign(0, y);
+        return isinf(y) ? copysign(3 * GO_PI / 4, y) : copysign(GO_PI, y);
+    }
+    if (isinf(y)) return copysign(GO_PI / 2, y);
+    const double q = go_atan(y / x);
+    if (x < 0) return q <= 0 ? q + GO_PI : q - GO_PI;
+    return q;
+}
+
+typedef struct { float X, Y, Z, W; } quat;
+
+static quat quat_slerp(quat a, quat end, float percent) {          /* quaternion.go:26-59 */
+    float cosOmega = a.X * end.X + a.Y * end.Y + a.Z * end.Z + a.W * end.W;      /* Dot, quaternion.go:82-84 */
+    if (cosOmega < 0) { end.W *= -1; end.X *= -1; end.Y *= -1; end.Z *= -1; cosOmega *= -1; }
+    float k0, k1;
+    if (cosOmega > 0.9999f) { k0 = 1 - percent; k1 = percent; }
+    else {
+        const float sinOmega = m32_sqrt(1 - (cosOmega * cosOmega));
+        const float omega = (float)orc_go_atan2((double)sinOmega, (double)cosOmega);
+        const float oneOverSinOmega = 1 / sinOmega;
+        k0 = (float)orc_go_sin((double)((1 - percent) * omega)) * oneOverSinOmega;
+        k1 = (float)orc_go_sin((double)(percent * omega)) * oneOverSinOmega;
+    }
+    quat r;
+    r.W = a.W * k0 + end.W * k1;
+    r.X = a.X * k0 + end.X * k1;
+    r.Y = a.Y * k0 + end.Y * k1;
+    r.Z = a.Z * k0 + end.Z * k1;
+    return r;
+}
+
+static mat4 quat_to_matrix(quat q) {                               /* quaternion.go:132-178 */
+    mat4 m1 = m4_identity(), m2 = m4_identity();
+    m1.m[0][0] = q.W;  m1.m[0][1] = q.Z;  m1.m[0][2] = -q.Y; m1.m[0][3] = q.X;
+    m1.m[1][0] = -q.Z; m1.m[1][1] = q.W;  m1.m[1][2] = q.X;  m1.m[1][3] = q.Y;
+    m1.m[2][0] = q.Y;  m1.m[2][1] = -q.X; m1.m[2][2] = q.W;  m1.m[2][3] = q.Z;
+    m1.m[3][0] = -q.X; m1.m[3][1] = -q.Y; m1.m[3][2] = -q.Z; m1.m[3][3] = q.W;
+    m2.m[0][0] = q.W;  m2.m[0][1] = q.Z;  m2.m[0][2] = -q.Y; m2.m[0][3] = -q.X;
+    m2.m[1][0] = -q.Z; m2.m[1][1] = q.W;  m2.m[1][2] = q.X;  m2.m[1][3] = -q.Y;
+    m2.m[2][0] = q.Y;  m2.m[2][1] = -q.X; m2.m[2][2] = q.W;  m2.m[2][3] = -q.Z;
+    m2.m[3][0] = q.X;  m2.m[3][1] = q.Y;  m2.m[3][2] = q.Z;  m2.m[3][3] = q.W;
+    return m4_mult(m1, m2);
+}
+
+void orc_quat_slerp(const float* a4, const float* b4, float percent, float* out4) {
+    quat a = {a4[0], a4[1], a4[2], a4[3]}, b = {b4[0], b4[1], b4[2], b4[3]};
+    quat r = quat_slerp(a, b, percent);
+    out4[0] = r.X; out4[1] = r.Y; out4[2] = r.Z; out4[3] = r.W;
+}
+void orc_quat_to_matrix(const float* q4, float* out16) {
+    quat q = {q4[0], q4[1], q4[2], q4[3]};
+    mat4 m = quat_to_matrix(q);
+    m4_store(&m, out16);
+}
+
+/* The keyframe pair around `time` (animation.go:63-90, 116-141): returns 0 = no keyframes, 1 = a single value (*a),
+ * 2 = interpolate between *a and *b. */
+static int track_keys(const orc_animation* an, const orc_track* tr, float time, int* a, int* b) {
+    if (tr->n_keys == 0) return 0;
+    const float* T = an->key_times + tr->first_key;
+    if (time <= T[0]) { *a = tr->first_key; return 1; }
+    if (time >= T[tr->n_keys - 1]) { *a = tr->first_key + tr->n_keys - 1; return 1; }
+    int first = -1, last = -1;
+    for (int k = 0; k < tr->n_keys; k++) {
+        if (T[k] < time) first = k;
+        else { last = k; break; }
+    }
+    if (time == T[first]) { *a = tr->first_key + first; return 1; }
+    if (time == T[last]) { *a = tr->first_key + last; return 1; }
+    *a = tr->first_key + first; *b = tr->first_key + last;
+    if (tr->interpolation == 1) return 1;                           /* InterpolationConstant: the earlier keyframe */
+    return 2;
+}
+
+static int track_vector(const orc_animation* an, const orc_track* tr, float time, vec3* out) {      /* animation.go:63-112 */
+    int a = 0, b = 0;
+    const int k = track_keys(an, tr, time, &a, &b);
+    if (k == 0) return 0;
+    const float* fa = an->key_values + 4 * (size_t)a;
+    vec3 fd = v3(fa[0], fa[1], fa[2]);
+    if (k == 2) {
+        const float* fb = an->key_values + 4 * (size_t)b;
+        const float t = (time - an->key_times[a]) / (an->key_times[b] - an->key_times[a]);
+        fd.X = fd.X + ((fb[0] - fd.X) * t);                          /* Vector3.Lerp, vector.go:559-565 */
+        fd.Y = fd.Y + ((fb[1] - fd.Y) * t);
+        fd.Z = fd.Z + ((fb[2] - fd.Z) * t);
+    }
+    *out = fd;
+    return 1;
+}
+
+static int track_quaternion(const orc_animation* an, const orc_track* tr, float time, quat* out) {  /* animation.go:116-164 */
+    int a = 0, b = 0;
+    const int k = track_keys(an, tr, time, &a, &b);
+    if (k == 0) return 0;
+    const float* fa = an->key_values + 4 * (size_t)a;
+    quat fd = {fa[0], fa[1], fa[2], fa[3]};
+    if (k == 2) {
+        const float* fb = an->key_values + 4 * (size_t)b;
+        quat ld = {fb[0], fb[1], fb[2], fb[3]};
+        const float t = (time - an->key_times[a]) / (an->key_times[b] - an->key_times[a]);
+        fd = quat_slerp(fd, ld, t);
+    }
+    *out = fd;
+    return 1;
+}
+
+static int m4_is_zero(const mat4* a) {                              /* matrix.go:700-709 */
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) if (a->m[i][j] != 0) return 0;
+    return 1;
+}
+
+void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out) {
+    const int n = sk->n_bones;
+    mat4* world = (mat4*)malloc(sizeof(mat4) * (size_t)(n > 0 ? n : 1));
+    const mat4 root = m4_load(root16);
+    for (int b = 0; b < n; b++) {
+        /* AnimationPlayer.updateValues + forceUpdate (animation.go:674-722, 961-980): tracks that exist overwrite the
+         * node's local position / scale / rotation; SetLocalRotation ignores an all-zero matrix (node.go:906-912) */
+        vec3 pos = v3(sk->rest_position[3 * b], sk->rest_position[3 * b + 1], sk->rest_position[3 * b + 2]);
+        vec3 scl = v3(sk->rest_scale[3 * b], sk->rest_scale[3 * b + 1], sk->rest_scale[3 * b + 2]);
+        mat4 rot = m4_load(sk->rest_rotation + 16 * (size_t)b);
+        if (an && b < an->n_bones) {
+            vec3 v; quat q;
+            if (track_vector(an, &an->tracks[3 * b + 0], playhead, &v)) pos = v;
+            if (track_vector(an, &an->tracks[3 * b + 1], playhead, &v)) scl = v;
+            if (track_quaternion(an, &an->tracks[3 * b + 2], playhead, &q)) {
+                const mat4 r = quat_to_matrix(q);
+                if (!m4_is_zero(&r)) rot = r;
+            }
+        }
+        /* Node.Transform (node.go:572-594) */
+        mat4 t = m4_scale(scl.X, scl.Y, scl.Z);
+        t = m4_mult(t, rot);
+        t = m4_mult(t, m4_translate(pos.X, pos.Y, pos.Z));
+        t = m4_mult(t, sk->parent[b] >= 0 ? world[sk->parent[b]] : root);
+        world[b] = t;
+        const mat4 infl = m4_mult(m4_load(sk->inverse_bind + 16 * (size_t)b), t);
+        m4_store(&infl, out + 16 * (size_t)b);
+    }
+    free(world);
+}

@@ -253,6 +253,34 @@ void  orc_triangle_centers(const float* positions, const uint32_t* indices, int3
 /* The 512-bin assignment alone (sortingTriangles.go:38-64). */
 int   orc_bin_index(float depth, float min_depth, float max_depth, int sort_mode);
 
+/* ---- bone poses: the step before the path --------------------------------------------
+ * AnimationTrack.ValueAsVector / ValueAsQuaternion (animation.go:63-164), Quaternion.Slerp / ToMatrix4
+ * (quaternion.go:26-59, 132-178), AnimationPlayer.forceUpdate without blending or relative motion
+ * (animation.go:961-980), Node.Transform + boneInfluence (node.go:572-594).  Slerp goes through Go's float64
+ * math.Sin / math.Atan2 (math32/math32.go:137-139, 204-206), which are pure Go on amd64 (Cephes-derived,
+ * src/math/sin.go, atan.go, atan2.go of the Go standard library): restated below as orc_go_sin / orc_go_atan2. */
+typedef struct orc_track { int32_t first_key, n_keys, interpolation; } orc_track;    /* 0 linear, 1 constant, 2 cubic (evaluated as linear: animation.go:107) */
+typedef struct orc_skeleton {
+    int32_t n_bones;
+    const int32_t* parent;          /* [n] parent bone or -1 (child of the pose's root transform); parents come first */
+    const float* inverse_bind;      /* [n][16] Node.inverseBindMatrix */
+    const float* rest_position;     /* [n][3]  node.position / scale / rotation of bones the animation has no track for */
+    const float* rest_scale;        /* [n][3] */
+    const float* rest_rotation;     /* [n][16] */
+} orc_skeleton;
+typedef struct orc_animation {
+    int32_t n_bones;
+    const orc_track* tracks;        /* [n][3] position, scale, rotation */
+    const float* key_times;
+    const float* key_values;        /* [keys][4] */
+} orc_animation;
+/* boneInfluence of every bone, posed at `playhead`, with the skeleton's root bones parented to root16. */
+void   orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out);
+void   orc_quat_slerp(const float* a4, const float* b4, float percent, float* out4);      /* quaternion.go:26-59 */
+void   orc_quat_to_matrix(const float* q4, float* out16);                                 /* quaternion.go:132-178 */
+double orc_go_sin(double x);                                                              /* Go math.Sin (amd64: pure Go) */
+double orc_go_atan2(double y, double x);                                                  /* Go math.Atan2 */
+
 #ifdef __cplusplus
 }
 #endif

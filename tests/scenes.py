@@ -279,3 +279,78 @@ ALL_SMALL = {
     "stress_small": lambda: SceneDesc([ModelDesc(W.cube_mesh(2, 2, 2, copies=20, material=MaterialDesc(shadeless=True, use_texture=True, tex_w=16, tex_h=16)),
                                                   NodeDesc(position=(4.0 * x, 0.0, 0.0)), name="m%d" % x) for x in range(6)], [], CameraDesc(), WorldDesc()),
 }
+
+
+def random_skeleton(rng, n_bones: int, chain: bool = False) -> "SkeletonDesc":
+    """A random bone tree (parents first; several roots possible) with random rest transforms and inverse binds."""
+    from tetra3d_b200.scenedesc import SkeletonDesc
+    parent = np.full(n_bones, -1, np.int32)
+    for b in range(1, n_bones):
+        parent[b] = b - 1 if chain else int(rng.integers(-1, b)) if rng.random() < 0.9 else -1
+    inv = np.zeros((n_bones, 16), F32); rot = np.zeros((n_bones, 16), F32)
+    for b in range(n_bones):
+        m = random_rotation(rng).astype(np.float64).reshape(4, 4)
+        m[3, :3] = rng.uniform(-0.5, 0.5, 3)
+        inv[b] = m.astype(F32).reshape(16)
+        rot[b] = random_rotation(rng).reshape(16)
+    return SkeletonDesc(names=["b%d" % b for b in range(n_bones)], parent=parent, inverse_bind=inv,
+                        rest_position=rng.uniform(-0.3, 0.3, (n_bones, 3)).astype(F32), rest_scale=rng.uniform(0.8, 1.2, (n_bones, 3)).astype(F32),
+                        rest_rotation=rot)
+
+
+def random_animation(rng, sk, length: float = 3.0) -> "AnimationDesc":
+    """Random tracks: some bones without a channel, tracks of 1..12 keys, repeated key times, stepped tracks, opposite-hemisphere
+    and nearly equal quaternion pairs (both Slerp branches), one all-zero quaternion (SetLocalRotation ignores it)."""
+    from tetra3d_b200.scenedesc import AnimationDesc, TrackDesc
+    channels = {}
+    for b, name in enumerate(sk.names):
+        if rng.random() < 0.2:
+            continue
+        tracks = {}
+        for t in range(3):
+            if rng.random() < 0.25:
+                continue
+            k = int(rng.integers(1, 13))
+            times = np.sort(rng.uniform(0.0, length, k)).astype(F32)
+            if k > 3 and rng.random() < 0.3:
+                times[2] = times[1]
+            if t == 2:
+                v = rng.standard_normal((k, 4))
+                v /= np.linalg.norm(v, axis=1, keepdims=True)
+                for i in range(1, k):
+                    if rng.random() < 0.3:
+                        v[i] = v[i - 1] + 1e-4 * rng.standard_normal(4)      # cosOmega > 0.9999: the linear branch
+                if k > 2 and rng.random() < 0.15:
+                    v[1] = 0.0
+                v = v.astype(F32)
+            elif t == 1:
+                v = np.concatenate([rng.uniform(0.7, 1.3, (k, 3)), np.zeros((k, 1))], axis=1).astype(F32)
+            else:
+                v = np.concatenate([rng.uniform(-0.4, 0.4, (k, 3)), np.zeros((k, 1))], axis=1).astype(F32)
+            tracks[t] = TrackDesc(times, v, interpolation=int(rng.choice([0, 0, 1, 2])))
+        channels[name] = tracks
+    return AnimationDesc("random", length, channels)
+
+
+def posed_scene(seed=0, n_models=6, n_bones=5, chain=False, playheads=None) -> SceneDesc:
+    """Skinned characters whose bones come from a skeleton + animation sampled at a playhead (PoseDesc): two skeletons, two
+    animations and a rest-pose armature in one frame, next to a model with explicit bone matrices and a static one."""
+    from tetra3d_b200.scenedesc import PoseDesc
+    rng = np.random.default_rng(500 + seed)
+    mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=n_bones)
+    sks = [random_skeleton(rng, n_bones, chain=chain), W.chain_skeleton(bone_y)]
+    anims = [[random_animation(rng, sks[0]), random_animation(rng, sks[0], length=1.5)], [W.chain_animation(sks[1]), random_animation(rng, sks[1])]]
+    models = []
+    for i in range(n_models):
+        k = i % 2
+        anim = None if i == 3 else anims[k][(i // 2) % 2]
+        ph = float(playheads[i % len(playheads)]) if playheads is not None else float(rng.uniform(-0.2, 3.3))
+        root = NodeDesc(position=(1.5 * (i - n_models / 2), -1.0, 0.0), rotation=random_rotation(rng) if i % 3 == 0 else W.rotation_matrix((0, 1, 0), 0.0),
+                        scale=(1.0, 1.0 + 0.1 * (i % 2), 1.0))
+        models.append(ModelDesc(mesh, NodeDesc(), pose=PoseDesc(sks[k], anim, ph, root), frustum_culling=False, name="posed%d" % i))
+    bi = W.chain_bone_influences(bone_y, (0.0, 1.5, 0.0), 0.7, 0.3)
+    models.append(ModelDesc(mesh, NodeDesc(), bone_influences=bi, frustum_culling=False, name="explicit"))
+    models.append(ModelDesc(random_soup(300, seed, n_parts=1), NodeDesc(position=(0.0, 0.0, -2.0)), name="static"))
+    lights = [LightDesc(LIGHT_POINT, NodeDesc(position=(-3.0, 2.0, 5.0)), color=(0.9, 0.9, 0.5), energy=3.0, name="scene_point"),
+              LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=W.rotation_matrix((1, 0, 0), 0.7)), color=(0.5, 0.6, 1.0), energy=1.0, name="sun")]
+    return SceneDesc(models, lights, CameraDesc(node=NodeDesc(position=(0.0, 1.0, 9.0))), WorldDesc(ambient_energy=0.15), name="posed%d" % seed)

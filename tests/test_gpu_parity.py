@@ -227,7 +227,7 @@ def test_full_size_million_triangles_vs_oracle(device):
     assert_parity(W.million_triangle_scene(), device, check_capture=False)
 
 
-@pytest.mark.parametrize("name", ["skinned_crowd", "instanced_shard", "particles_200k", "stress_lit", "million_one_part"])
+@pytest.mark.parametrize("name", ["skinned_crowd", "skinned_crowd_animated", "instanced_shard", "particles_200k", "stress_lit", "million_one_part"])
 def test_full_size_workloads_vs_oracle(device, name):
     """The other BASELINE configs at (or near) full size, bit for bit against the oracle: configs[2] whole (10 000
     skinned characters, 7.68 M triangles), an eighth of configs[4] (the share of one of 8 GPUs: 12.5 M triangles),

@@ -130,6 +130,36 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
         return l
 
     groups: Dict[int, object] = {}
+    skeletons: Dict[int, object] = {}
+    animations: Dict[int, object] = {}
+
+    def build_skeleton(sd):
+        # a template armature: bone Nodes with the rest transforms, parented as the joint list says
+        joints = []
+        for b, name in enumerate(sd.names):
+            n = t3d.Node(name)
+            n.SetLocalPosition(*map(float, sd.rest_position[b]))
+            n.SetLocalScale(*map(float, sd.rest_scale[b]))
+            n.SetLocalRotation(np.asarray(sd.rest_rotation[b], np.float32).reshape(16))
+            joints.append(n)
+        for b, p in enumerate(sd.parent):
+            if p >= 0:
+                joints[int(p)].AddChildren(joints[b])
+        return t3d.NewSkeletonFromJoints(joints, np.asarray(sd.inverse_bind, np.float32).reshape(-1))
+
+    def build_animation(ad):
+        anim = t3d.NewAnimation(ad.name)
+        anim.SetLength(float(ad.length))
+        anim.SetLoopMode(int(ad.loop_mode))
+        for ch_name, tracks in ad.channels.items():
+            ch = anim.AddChannel(ch_name)
+            for ttype, td in tracks.items():
+                tr = ch.AddTrack(int(ttype))
+                tr.Interpolation = int(td.interpolation)
+                for t, v in zip(td.times, td.values):
+                    tr.AddKeyframe(float(t), [float(x) for x in (v if int(ttype) == 2 else v[:3])])
+        return anim
+
     models = []
     for md in desc.models:
         if id(md.mesh) not in meshes:
@@ -142,6 +172,21 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
         model.SetVisible(bool(md.visible))
         if md.bone_influences is not None:
             model.SetBoneInfluences(np.asarray(md.bone_influences, np.float32).reshape(-1))
+        if md.pose is not None:
+            pose = md.pose
+            if id(pose.skeleton) not in skeletons:
+                skeletons[id(pose.skeleton)] = build_skeleton(pose.skeleton)
+            armature = t3d.Node(md.name + " armature")
+            attach(armature, pose.root)
+            player = None
+            if pose.animation is not None:
+                if id(pose.animation) not in animations:
+                    animations[id(pose.animation)] = build_animation(pose.animation)
+                player = t3d.NewAnimationPlayer(armature)
+                player.Play(animations[id(pose.animation)])
+                player.SetPlayhead(float(pose.playhead))
+                objs[id(pose)] = player
+            model.SetSkeleton(skeletons[id(pose.skeleton)], armature, player)
         attach(model, md.node)
         objs[id(md)] = model
         models.append((md, model))

@@ -64,6 +64,20 @@ template <class T> struct PinVec {
 
 struct PartInfo { uint32_t triStart, triEnd, a0, nv; };
 
+// t3d_skeleton_upload / t3d_animation_upload: one device allocation each
+struct Skeleton {
+    uint32_t nBones = 0, maxDepth = 0;
+    void* block = nullptr;
+    int32_t* parent = nullptr; uint16_t* depth = nullptr; float *invBind = nullptr, *restPos = nullptr, *restScale = nullptr, *restRot = nullptr;
+};
+struct Animation {
+    uint32_t nBones = 0, nKeys = 0;
+    void* block = nullptr;
+    t3d_track* tracks = nullptr; float* keyTimes = nullptr; float4* keyValues = nullptr;
+};
+struct PoseCall { uint64_t skeleton, animation; uint32_t firstPose, nPoses, firstBone; };      // one t3d_submit_poses call of the frame
+
+
 struct Mesh {
     uint32_t generation = 0;
     uint32_t nVerts = 0, nVertsPad = 0, nTris = 0, nTrisPad = 0, nKeys = 0;
@@ -93,6 +107,10 @@ struct t3d_ctx {
     std::vector<VolumeU> volumes;
     std::vector<float*> volumeCells;
     DevBuf dVolumes; bool volumesDirty = true;
+    std::unordered_map<uint64_t, Skeleton> skeletons;
+    std::unordered_map<uint64_t, Animation> animations;
+    PinVec<t3d_pose> hPoses; std::vector<PoseCall> poseCalls; uint32_t posedBones = 0;     // this frame's t3d_submit_poses calls
+    size_t framePosesOff = 0;
 
     // frame staging (pinned)
     bool inFrame = false, executed = false, haveResults = false;
@@ -218,6 +236,9 @@ void t3d_destroy(t3d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->meshes) kv.second.release();
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
+    for (auto& kv : ctx->skeletons) if (kv.second.block) cudaFree(kv.second.block);
+    for (auto& kv : ctx->animations) if (kv.second.block) cudaFree(kv.second.block);
+    ctx->hPoses.release();
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
@@ -415,6 +436,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->tmplSpanMax = 1;
+    ctx->hPoses.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
     return T3D_OK;
@@ -438,6 +460,124 @@ int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_
     ctx->hLights.n = off + n;
     *list_id = (uint32_t)ctx->lightLists.size();
     ctx->lightLists.push_back(LightList{off, n});
+    return T3D_OK;
+}
+
+int t3d_skeleton_upload(t3d_ctx* ctx, uint64_t skeleton_id, const t3d_skeleton_desc* d) {
+    if (!ctx || !d || !d->parent || !d->inverse_bind || !d->rest_position || !d->rest_scale || !d->rest_rotation)
+        return fail(ctx, T3D_E_INVALID, "t3d_skeleton_upload: NULL argument");
+    if (d->n_bones == 0) return fail(ctx, T3D_E_INVALID, "t3d_skeleton_upload: no bones");
+    if (d->n_bones > POSE_MAX_BONES) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_skeleton_upload: more than 1024 bones (submit the matrices with t3d_submit_bones)");
+    const uint32_t n = d->n_bones;
+    std::vector<uint16_t> depth(n);
+    uint32_t maxDepth = 0;
+    for (uint32_t b = 0; b < n; b++) {
+        const int32_t par = d->parent[b];
+        if (par >= (int32_t)b) return fail(ctx, T3D_E_INVALID, "t3d_skeleton_upload: a parent must precede its children");
+        depth[b] = par < 0 ? 0 : (uint16_t)(depth[par] + 1);
+        maxDepth = std::max<uint32_t>(maxDepth, depth[b]);
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    Skeleton& S = ctx->skeletons[skeleton_id];
+    if (S.block) { cudaFree(S.block); S.block = nullptr; }
+    // [invBind 64n | restRot 64n | restPos 12n | restScale 12n | parent 4n | depth 2n]
+    const size_t bytes = (size_t)n * (64 + 64 + 12 + 12 + 4 + 2);
+    std::vector<uint8_t> h(bytes);
+    uint8_t* q = h.data();
+    memcpy(q, d->inverse_bind, 64ull * n); q += 64ull * n;
+    memcpy(q, d->rest_rotation, 64ull * n); q += 64ull * n;
+    memcpy(q, d->rest_position, 12ull * n); q += 12ull * n;
+    memcpy(q, d->rest_scale, 12ull * n); q += 12ull * n;
+    memcpy(q, d->parent, 4ull * n); q += 4ull * n;
+    memcpy(q, depth.data(), 2ull * n);
+    CU(cudaMalloc(&S.block, bytes));
+    CU(cudaMemcpy(S.block, h.data(), bytes, cudaMemcpyHostToDevice));
+    uint8_t* b = static_cast<uint8_t*>(S.block);
+    S.invBind = reinterpret_cast<float*>(b); b += 64ull * n;
+    S.restRot = reinterpret_cast<float*>(b); b += 64ull * n;
+    S.restPos = reinterpret_cast<float*>(b); b += 12ull * n;
+    S.restScale = reinterpret_cast<float*>(b); b += 12ull * n;
+    S.parent = reinterpret_cast<int32_t*>(b); b += 4ull * n;
+    S.depth = reinterpret_cast<uint16_t*>(b);
+    S.nBones = n; S.maxDepth = maxDepth;
+    return T3D_OK;
+}
+
+int t3d_skeleton_release(t3d_ctx* ctx, uint64_t skeleton_id) {
+    if (!ctx) return T3D_E_INVALID;
+    auto it = ctx->skeletons.find(skeleton_id);
+    if (it == ctx->skeletons.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_skeleton_release: unknown skeleton");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (it->second.block) cudaFree(it->second.block);
+    ctx->skeletons.erase(it);
+    return T3D_OK;
+}
+
+int t3d_animation_upload(t3d_ctx* ctx, uint64_t animation_id, const t3d_animation_desc* d) {
+    if (!ctx || !d || !d->tracks || (d->n_keys && (!d->key_times || !d->key_values)))
+        return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: NULL argument");
+    if (animation_id == 0) return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: id 0 is the rest pose");
+    if (d->n_bones == 0 || d->n_bones > POSE_MAX_BONES) return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: bone count out of range");
+    for (uint32_t t = 0; t < 3 * d->n_bones; t++) {
+        const t3d_track& tr = d->tracks[t];
+        if ((uint64_t)tr.first_key + tr.n_keys > d->n_keys) return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: track outside the keyframe arrays");
+        if (tr.interpolation > T3D_INTERPOLATION_CUBIC) return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: unknown interpolation");
+        for (uint32_t k = 1; k < tr.n_keys; k++)
+            if (!(d->key_times[tr.first_key + k] >= d->key_times[tr.first_key + k - 1]))
+                return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: keyframe times must be non-decreasing inside a track");
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    Animation& A = ctx->animations[animation_id];
+    if (A.block) { cudaFree(A.block); A.block = nullptr; }
+    // [keyValues 16k | tracks 36n | keyTimes 4k]
+    const size_t nk = d->n_keys, nt = 3ull * d->n_bones;
+    const size_t bytes = 16 * std::max<size_t>(nk, 1) + sizeof(t3d_track) * nt + 4 * std::max<size_t>(nk, 1);
+    std::vector<uint8_t> h(bytes, 0);
+    memcpy(h.data(), d->key_values, 16 * nk);
+    memcpy(h.data() + 16 * std::max<size_t>(nk, 1), d->tracks, sizeof(t3d_track) * nt);
+    memcpy(h.data() + 16 * std::max<size_t>(nk, 1) + sizeof(t3d_track) * nt, d->key_times, 4 * nk);
+    CU(cudaMalloc(&A.block, bytes));
+    CU(cudaMemcpy(A.block, h.data(), bytes, cudaMemcpyHostToDevice));
+    uint8_t* b = static_cast<uint8_t*>(A.block);
+    A.keyValues = reinterpret_cast<float4*>(b);
+    A.tracks = reinterpret_cast<t3d_track*>(b + 16 * std::max<size_t>(nk, 1));
+    A.keyTimes = reinterpret_cast<float*>(b + 16 * std::max<size_t>(nk, 1) + sizeof(t3d_track) * nt);
+    A.nBones = d->n_bones; A.nKeys = d->n_keys;
+    return T3D_OK;
+}
+
+int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id) {
+    if (!ctx) return T3D_E_INVALID;
+    auto it = ctx->animations.find(animation_id);
+    if (it == ctx->animations.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_animation_release: unknown animation");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (it->second.block) cudaFree(it->second.block);
+    ctx->animations.erase(it);
+    return T3D_OK;
+}
+
+int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset) {
+    if (!ctx || !offset || (n && !poses)) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_poses: not between frame_begin and frame_execute");
+    auto sk = ctx->skeletons.find(skeleton_id);
+    if (sk == ctx->skeletons.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_poses: unknown skeleton");
+    if (animation_id) {
+        auto an = ctx->animations.find(animation_id);
+        if (an == ctx->animations.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_poses: unknown animation");
+        if (an->second.nBones > sk->second.nBones) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: the animation has more bones than the skeleton");
+    }
+    if ((uint64_t)ctx->posedBones + (uint64_t)n * sk->second.nBones >= POSE_TAG) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: too many posed bones in one frame");
+    PoseCall c; c.skeleton = skeleton_id; c.animation = animation_id; c.firstPose = (uint32_t)ctx->hPoses.n; c.nPoses = n; c.firstBone = ctx->posedBones;
+    CU(ctx->hPoses.reserve(ctx->hPoses.n + n));
+    memcpy(ctx->hPoses.p + ctx->hPoses.n, poses, sizeof(t3d_pose) * (size_t)n);
+    ctx->hPoses.n += n;
+    ctx->poseCalls.push_back(c);
+    *offset = POSE_TAG | ctx->posedBones;
+    ctx->posedBones += n * sk->second.nBones;
     return T3D_OK;
 }
 
@@ -485,7 +625,8 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         uint32_t flags = in.flags;
         if (flags & T3D_DRAW_SKINNED) {
             if (!m.wgt) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: skinned draw of a mesh without weights");
-            if (in.bone_count <= m.maxJoint || (size_t)in.bone_offset + in.bone_count > ctx->hBones.n / 16)
+            const bool posed = in.bone_offset & POSE_TAG;
+            if (in.bone_count <= m.maxJoint || (size_t)(in.bone_offset & ~POSE_TAG) + in.bone_count > (posed ? (size_t)ctx->posedBones : ctx->hBones.n / 16))
                 return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: bone span does not cover the mesh's joints");
             flags &= ~(uint32_t)T3D_DRAW_DEPTH_UNBILLBOARDED;   // the reference never writes it for skinned models (model.go:800)
         }
@@ -761,10 +902,11 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         }
         ctx->frameRunMode = runMode;
         const size_t slimBytes = runMode ? 64 : ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
-        Seg head[5] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
+        Seg head[6] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0},
                        {ctx->hRuns.data(), runMode ? sizeof(DrawRun) * ctx->hRuns.size() : 0, 0},
-                       {ctx->hBlockRun.data(), runMode ? 4ull * ctx->hBlockRun.size() : 0, 0}};
+                       {ctx->hBlockRun.data(), runMode ? 4ull * ctx->hBlockRun.size() : 0, 0},
+                       {ctx->hPoses.p, sizeof(t3d_pose) * ctx->hPoses.n, 0}};       // read by k_pose_bones
         Seg segs[13] = {
             {nullptr, 0, 0}, {nullptr, 0, 0} /* vbase / tbase: k_prep_draws writes the device tables from the placement records */,
             {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
@@ -779,7 +921,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         // bone matrices: 12 floats each on the host side when all are affine, always 16 on the device
         const size_t nBones = ctx->hBones.n / 16;
         const size_t hostBoneBytes = ((ctx->bonesAffine ? 48 : 64) * nBones + 255) & ~(size_t)255;
-        const size_t devBoneBytes = (64 * nBones + 255) & ~(size_t)255;
+        const size_t devBoneBytes = (64 * (nBones + ctx->posedBones) + 255) & ~(size_t)255;      // submitted matrices, then the device-evaluated poses
         const size_t devTableBytes = (4ull * (nDraws + 1) + 255) & ~(size_t)255;        // vbase, tbase
         ctx->hFrame.mapped = true;
         CU(ctx->hFrame.resize(headBytes + restBytes + hostBoneBytes));
@@ -809,7 +951,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
         CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
         ctx->frameHeadBytes = headBytes; ctx->frameRestBytes = restBytes; ctx->frameTmplOff = head[1].off; ctx->frameRotOff = head[2].off;
-        ctx->frameRunsOff = head[3].off; ctx->frameBlockRunOff = head[4].off;
+        ctx->frameRunsOff = head[3].off; ctx->frameBlockRunOff = head[4].off; ctx->framePosesOff = head[5].off;
         ctx->frameLightsOff = headBytes + segs[6].off;
         uint8_t* base = ctx->dFrame.as<uint8_t>();
         uint8_t* rest = base + devDrawBytes;
@@ -858,6 +1000,21 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             win[b][2] = rmin; win[b][3] = rmin != NO_ROTATION ? rmax - rmin + 1 : 0;
         }
         const uint8_t* hf = static_cast<const uint8_t*>(ctx->hFrameDev);
+        // bone poses evaluated on the device: one launch per t3d_submit_poses call, into the arena behind the submitted matrices
+        for (const PoseCall& c : ctx->poseCalls) {
+            const Skeleton& S = ctx->skeletons.at(c.skeleton);
+            PoseBatch pb; memset(&pb, 0, sizeof pb);
+            pb.nBones = S.nBones; pb.maxDepth = S.maxDepth; pb.nPoses = c.nPoses;
+            pb.parent = S.parent; pb.depth = S.depth; pb.invBind = S.invBind; pb.restPos = S.restPos; pb.restScale = S.restScale; pb.restRot = S.restRot;
+            if (c.animation) {
+                const Animation& A = ctx->animations.at(c.animation);
+                pb.animBones = A.nBones; pb.tracks = A.tracks; pb.keyTimes = A.keyTimes; pb.keyValues = A.keyValues;
+            }
+            pb.poses = reinterpret_cast<const t3d_pose*>(hf + ctx->framePosesOff) + c.firstPose;
+            pb.out = ctx->pBones + 16 * ((size_t)ctx->frameBoneCount + c.firstBone);
+            CU(launch_pose_bones(s, pb));
+            ctx->launches += 1;
+        }
         launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
                           reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
@@ -1093,6 +1250,17 @@ int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->sharedOpened.push_back(p);
     *device_ptr = p;
+    return T3D_OK;
+}
+
+int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matrices16) {
+    if (!ctx || (n && !matrices16)) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_bones: NULL argument");
+    if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_debug_read_bones: frame not executed");
+    const size_t first = (offset & POSE_TAG) ? (size_t)ctx->frameBoneCount + (offset & ~POSE_TAG) : offset;
+    if (first + n > (size_t)ctx->frameBoneCount + ctx->posedBones) return fail(ctx, T3D_E_INVALID, "t3d_debug_read_bones: range outside the bone arena");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n) CU(cudaMemcpy(matrices16, ctx->pBones + 16 * first, 64ull * n, cudaMemcpyDeviceToHost));
     return T3D_OK;
 }
 

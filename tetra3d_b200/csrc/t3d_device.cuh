@@ -225,4 +225,18 @@ __device__ __forceinline__ uint32_t bin_key(uint32_t depthBits, uint32_t minBits
 }
 #endif
 
+// ---- bone poses (t3d_pose.cu) -------------------------------------------------------------------------------
+// One t3d_submit_poses call: n armatures of one skeleton playing one animation.  Skeleton and animation tables are
+// resident device memory; the pose records are read from the pinned frame block.
+static const uint32_t POSE_MAX_BONES = 1024;        // bones per skeleton (the hierarchy walk keeps an armature's matrices in shared memory)
+static const uint32_t POSE_TAG = 0x80000000u;       // bone offsets of device-evaluated poses: index among the posed bones | tag
+struct PoseBatch {
+    uint32_t nBones, maxDepth, animBones, nPoses;
+    const int32_t* parent; const uint16_t* depth;       // [nBones]
+    const float* invBind; const float* restPos; const float* restScale; const float* restRot;
+    const t3d_track* tracks; const float* keyTimes; const float4* keyValues;   // animBones == 0: rest pose
+    const t3d_pose* poses;                              // [nPoses] pinned host memory (UVA)
+    float* out;                                         // first matrix of pose 0 in the frame's bone arena
+};
+
 }  // namespace t3d

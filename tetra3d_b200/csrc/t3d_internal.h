@@ -54,4 +54,7 @@ void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32
 void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
                       uint32_t* tileOut, uint32_t* chunkSum);
 
+// t3d_pose.cu -- bone poses evaluated on the device
+cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb);
+
 }  // namespace t3d

@@ -259,7 +259,9 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     if (mine && role == 0) {      // the scalar placement fields, and the frame's vbase / tbase tables
         const DrawSlim& S = slimOf(k);
         DrawRec& R = sR[k];
-        R.vbase = S.vbase; R.tbase = S.tbase; R.boneOffset = S.boneOffset; R.lightU = S.lightU;
+        R.vbase = S.vbase; R.tbase = S.tbase; R.lightU = S.lightU;
+        // device-evaluated poses (t3d_submit_poses) sit behind the submitted matrices in the bone arena
+        R.boneOffset = (S.boneOffset & POSE_TAG) ? pf.nBones + (S.boneOffset & ~POSE_TAG) : S.boneOffset;
         pf.devVbase[d0 + k] = S.vbase; pf.devTbase[d0 + k] = S.tbase;
         if (d0 + k == pf.nDraws - 1) { pf.devVbase[pf.nDraws] = S.vbase + R.nv; pf.devTbase[pf.nDraws] = S.tbase + R.nt; }
     }

@@ -199,6 +199,53 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("Active", &LightGroup::Active);
     m.def("NewLightGroup", [](py::args lights) { auto g = std::make_shared<LightGroup>(); for (auto l : lights) g->Lights.push_back(l.cast<std::shared_ptr<ILight>>()); return g; });
 
+    // ---- animation.go ----
+    py::class_<AnimationTrack, std::shared_ptr<AnimationTrack>>(m, "AnimationTrack")
+        .def_readwrite("Interpolation", &AnimationTrack::Interpolation)
+        .def("AddKeyframe", [](AnimationTrack& t, float time, const std::vector<float>& v) {
+            if (v.size() != 3 && v.size() != 4) throw std::invalid_argument("keyframe data: a Vector3 or a Quaternion");
+            t.AddKeyframe(time, v[0], v[1], v[2], v.size() == 4 ? v[3] : 0.0f);
+        })
+        .def("KeyframeCount", [](AnimationTrack& t) { return t.Keyframes.size(); });
+    py::class_<AnimationChannel, std::shared_ptr<AnimationChannel>>(m, "AnimationChannel")
+        .def_readonly("Name", &AnimationChannel::Name)
+        .def("AddTrack", &AnimationChannel::AddTrack);
+    py::class_<Animation, std::shared_ptr<Animation>>(m, "Animation")
+        .def(py::init<const std::string&>())
+        .def("AddChannel", &Animation::AddChannel)
+        .def("Name", [](Animation& a) { return a.name; })
+        .def("Length", [](Animation& a) { return a.length; })
+        .def("SetLength", [](Animation& a, float l) { a.length = l; })
+        .def("LoopMode", [](Animation& a) { return a.loopMode; })
+        .def("SetLoopMode", [](Animation& a, int m) { a.loopMode = m; })
+        .def("SetRelativeMotion", [](Animation& a, bool r) { a.relativeMotion = r; })
+        .def("MarkDirty", &Animation::MarkDirty);
+    m.def("NewAnimation", [](const std::string& n) { return std::make_shared<Animation>(n); });
+    m.attr("TrackTypePosition") = (int)TrackTypePosition; m.attr("TrackTypeScale") = (int)TrackTypeScale; m.attr("TrackTypeRotation") = (int)TrackTypeRotation;
+    m.attr("InterpolationLinear") = (int)InterpolationLinear; m.attr("InterpolationConstant") = (int)InterpolationConstant; m.attr("InterpolationCubic") = (int)InterpolationCubic;
+    m.attr("AnimationLoopModeLoop") = (int)AnimationLoopModeLoop; m.attr("AnimationLoopModePingPong") = (int)AnimationLoopModePingPong; m.attr("AnimationLoopModeOneshot") = (int)AnimationLoopModeOneshot;
+    py::class_<Skeleton, std::shared_ptr<Skeleton>>(m, "Skeleton")
+        .def("BoneCount", &Skeleton::BoneCount)
+        .def_readonly("boneNames", &Skeleton::boneNames);
+    m.def("NewSkeletonFromJoints", [](const std::vector<std::shared_ptr<Node>>& joints, const farr& inverseBind) {
+        return Skeleton::FromJoints(joints, vec_from<float>(inverseBind));
+    });
+    py::class_<AnimationPlayer, std::shared_ptr<AnimationPlayer>>(m, "AnimationPlayer")
+        .def(py::init<std::shared_ptr<Node>>())
+        .def_readwrite("PlaySpeed", &AnimationPlayer::PlaySpeed)
+        .def_readwrite("BlendTime", &AnimationPlayer::BlendTime)
+        .def("Play", &AnimationPlayer::Play)
+        .def("Update", &AnimationPlayer::Update)
+        .def("SetPlayhead", &AnimationPlayer::SetPlayhead)
+        .def("Playhead", &AnimationPlayer::Playhead)
+        .def("Finished", &AnimationPlayer::Finished)
+        .def("IsPlaying", &AnimationPlayer::IsPlaying)
+        .def("Pause", &AnimationPlayer::Pause)
+        .def("Resume", &AnimationPlayer::Resume)
+        .def("LoopCount", [](AnimationPlayer& a) { return a.loopCount; })
+        .def("SampledPlayhead", [](AnimationPlayer& a) { return a.sampledPlayhead; });
+    m.def("NewAnimationPlayer", [](std::shared_ptr<Node> n) { return std::make_shared<AnimationPlayer>(n); });
+
     py::class_<Model, Node, std::shared_ptr<Model>>(m, "Model")
         .def(py::init<const std::string&, std::shared_ptr<Mesh>>())
         .def("Mesh", [](Model& s) { return s.mesh; })
@@ -211,6 +258,8 @@ PYBIND11_MODULE(_host, m) {
         .def("Skinned", [](Model& s) { return s.skinned; })
         // the per-joint Node.boneInfluence matrices (node.go:592-594), n x 16
         .def("SetBoneInfluences", [](Model& s, const farr& mats) { if (mats.size() % 16) throw std::invalid_argument("need 16 floats per bone"); s.SetBoneInfluences(vec_from<float>(mats)); })
+        // bones posed on the device: skeleton, the node its root bones hang from (Model.SkinRoot), the armature's player (or None)
+        .def("SetSkeleton", &Model::SetSkeleton, py::arg("skeleton"), py::arg("skin_root"), py::arg("player") = nullptr)
         .def("DynamicBatchAdd", [](Model& s, int part, py::args models) { std::vector<std::shared_ptr<Model>> v; for (auto k : models) v.push_back(k.cast<std::shared_ptr<Model>>()); s.DynamicBatchAdd(part, v); })
         .def("DynamicBatcher", &Model::DynamicBatcher);
     m.def("NewModel", [](const std::string& n, std::shared_ptr<Mesh> mesh) { return std::make_shared<Model>(n, mesh); });
@@ -254,6 +303,12 @@ PYBIND11_MODULE(_host, m) {
             const int rc = t3d_set_output_target(d.ctx, reinterpret_cast<t3d_vertex*>(color), reinterpret_cast<t3d_vertex*>(depth),
                                                  reinterpret_cast<t3d_vertex*>(normal), capacity);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+        })
+        .def("ReadBones", [](GeometryDevice& d, uint32_t offset, uint32_t n) {
+            py::array_t<float> out({(py::ssize_t)n, (py::ssize_t)16});
+            int rc = t3d_debug_read_bones(d.ctx, offset, n, out.mutable_data());
+            if (rc != T3D_OK) throw std::runtime_error(t3d_last_error(d.ctx));
+            return out;
         })
         .def("ForceFullUpload", [](GeometryDevice& d, bool on) { t3d_debug_force_full_upload(d.ctx, on ? 1 : 0); })
         .def("SetStageTimings", [](GeometryDevice& d, bool on) { t3d_set_stage_timings(d.ctx, on ? 1 : 0); })
@@ -312,6 +367,7 @@ PYBIND11_MODULE(_host, m) {
             d["n_vertices"] = c.output.n_vertices; d["on_device"] = !c.downloadResults;
             return d;
         })
+        .def("BoneOffsets", [](Camera& c) { return c.lastBoneOffsets; })
         .def("Renders", [](Camera& c) {
             py::list out;
             for (auto& r : c.renders) {

@@ -286,6 +286,122 @@ void GeometryDevice::ensureVolume(LightVolume& v) {
     v.uploadedGeneration = v.generation;
 }
 
+void GeometryDevice::ensureSkeleton(Skeleton& s) {
+    if (s.uploadedGeneration == s.generation) return;
+    t3d_skeleton_desc d; std::memset(&d, 0, sizeof d);
+    d.n_bones = (uint32_t)s.BoneCount();
+    d.parent = s.parent.data(); d.inverse_bind = s.inverseBind.data();
+    d.rest_position = s.restPosition.data(); d.rest_scale = s.restScale.data(); d.rest_rotation = s.restRotation.data();
+    check(ctx, t3d_skeleton_upload(ctx, s.id, &d), "t3d_skeleton_upload");
+    s.uploadedGeneration = s.generation;
+}
+
+uint64_t GeometryDevice::ensureAnimation(Animation& a, Skeleton& s) {
+    const auto key = std::make_pair(a.id, s.id);
+    const uint64_t genKey = ((uint64_t)a.generation << 32) | s.generation;
+    auto it = residentAnimations.find(key);
+    if (it != residentAnimations.end() && it->second.second == genKey) return it->second.first;
+    // every bone gets the tracks of the channel carrying its name (assignChannels, animation.go:618-672)
+    const size_t nb = (size_t)s.BoneCount();
+    std::vector<t3d_track> tracks(3 * nb);
+    std::vector<float> times, values;
+    for (size_t b = 0; b < nb; b++) {
+        const AnimationChannel* ch = nullptr;
+        for (auto& c : a.channels) if (c->Name == s.boneNames[b]) { ch = c.get(); break; }
+        for (int t = 0; t < 3; t++) {
+            t3d_track& T = tracks[3 * b + t];
+            T.first_key = (uint32_t)times.size(); T.n_keys = 0; T.interpolation = T3D_INTERPOLATION_LINEAR;
+            const AnimationTrack* tr = ch ? ch->Tracks[t].get() : nullptr;
+            if (!tr) continue;
+            T.n_keys = (uint32_t)tr->Keyframes.size(); T.interpolation = (uint32_t)tr->Interpolation;
+            for (const Keyframe& k : tr->Keyframes) { times.push_back(k.Time); values.insert(values.end(), k.Data, k.Data + 4); }
+        }
+    }
+    t3d_animation_desc d; std::memset(&d, 0, sizeof d);
+    d.n_bones = (uint32_t)nb; d.tracks = tracks.data(); d.n_keys = (uint32_t)times.size(); d.key_times = times.data(); d.key_values = values.data();
+    const uint64_t devId = it != residentAnimations.end() ? it->second.first : nextAnimationId++;
+    check(ctx, t3d_animation_upload(ctx, devId, &d), "t3d_animation_upload");
+    residentAnimations[key] = {devId, genKey};
+    return devId;
+}
+
+// ---- animation.go -------------------------------------------------------------------------------------
+static uint64_t g_nextAnimationId = 1, g_nextSkeletonId = 1;
+Animation::Animation(const std::string& n) : name(n), id(g_nextAnimationId++) {}
+std::shared_ptr<AnimationChannel> Animation::AddChannel(const std::string& chName) {      // animation.go:238-242
+    auto c = std::make_shared<AnimationChannel>();
+    c->Name = chName;
+    for (auto& old : channels) if (old->Name == chName) { old = c; return c; }            // a map in Go: same name replaces
+    channels.push_back(c);
+    return c;
+}
+std::shared_ptr<AnimationTrack> AnimationChannel::AddTrack(int trackType) {                // animation.go:188-192
+    if (trackType < 0 || trackType > 2) throw T3DError(T3D_E_INVALID, "AddTrack: unknown track type");
+    Tracks[trackType] = std::make_shared<AnimationTrack>();
+    Tracks[trackType]->Type = trackType;
+    return Tracks[trackType];
+}
+
+Skeleton::Skeleton() : id(g_nextSkeletonId++) {}
+std::shared_ptr<Skeleton> Skeleton::FromJoints(const std::vector<std::shared_ptr<Node>>& joints, const std::vector<float>& inverseBind16) {
+    if (inverseBind16.size() != joints.size() * 16) throw T3DError(T3D_E_INVALID, "Skeleton: 16 inverse-bind floats per joint");
+    auto sk = std::make_shared<Skeleton>();
+    sk->inverseBind = inverseBind16;
+    for (size_t j = 0; j < joints.size(); j++) {
+        Node& n = *joints[j];
+        int32_t par = -1;
+        for (size_t k = 0; k < joints.size(); k++) if (joints[k].get() == n.parent) { par = (int32_t)k; break; }
+        if (par >= (int32_t)j) throw T3DError(T3D_E_INVALID, "Skeleton: a parent bone must precede its children in the joint list");
+        sk->parent.push_back(par);
+        sk->boneNames.push_back(n.name);
+        sk->restPosition.insert(sk->restPosition.end(), {n.position.X, n.position.Y, n.position.Z});
+        sk->restScale.insert(sk->restScale.end(), {n.scale.X, n.scale.Y, n.scale.Z});
+        float r[16]; m4_store(n.rotation, r);
+        sk->restRotation.insert(sk->restRotation.end(), r, r + 16);
+    }
+    return sk;
+}
+
+void AnimationPlayer::Play(std::shared_ptr<Animation> anim) {                               // animation.go:517-566
+    if (!anim) return;
+    if (animation == anim && playing) return;
+    animation = std::move(anim);
+    playing = true;
+    loopCount = 0;
+    playhead = PlaySpeed > 0 ? 0.0f : animation->length;
+}
+
+void AnimationPlayer::Update(float dt) {                                                    // animation.go:810-824
+    finished = false;
+    forceUpdate(dt);
+}
+
+void AnimationPlayer::forceUpdate(float dt) {                                               // animation.go:837 -> updateValues 674-806
+    if (!animation) return;
+    sampledPlayhead = playhead;             // the tracks are sampled here (animation.go:686-712): on the device, at the next Render
+    sampled = true;
+    playhead += dt * PlaySpeed;
+    float ph = playhead;
+    prevPlayhead = ph;
+    justLooped = false;
+    const float length = animation->length;
+    if (animation->loopMode == AnimationLoopModeLoop && (ph >= length || ph < 0)) {
+        if (ph >= length) playhead -= length;
+        if (ph < 0) playhead += length;
+        justLooped = true;
+        loopCount++;
+        finished = true;
+    } else if (animation->loopMode == AnimationLoopModePingPong && (ph >= length || ph < 0)) {
+        if (ph >= length) playhead -= playhead - length;
+        if (ph < 0) { playhead = -playhead; loopCount++; }
+        finished = true;
+        PlaySpeed *= -1;
+    } else if (animation->loopMode == AnimationLoopModeOneshot && ((ph >= length && PlaySpeed > 0) || (ph <= 0 && PlaySpeed < 0))) {
+        finished = true;
+        playing = false;
+    }
+}
+
 std::vector<int> AssignFlushesToRanks(const std::vector<uint64_t>& flushTris, int rankCount) {
     const int n = (int)flushTris.size();
     std::vector<int> owner(n, 0);
@@ -622,6 +738,40 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         return id;
     };
     std::unordered_map<Model*, uint32_t> boneOffsets;
+    {   // armatures posed on the device: one t3d_submit_poses call per (skeleton, animation), in first-use order
+        struct Group { Skeleton* sk; uint64_t anim; std::vector<t3d_pose> poses; std::vector<Model*> models; };
+        std::vector<Group> groups;
+        std::map<std::pair<uint64_t, uint64_t>, size_t> groupOf;
+        for (auto& pd : pending) {
+            if (flushOwnerRank[pd.flush] != shardRank) continue;
+            Model* model = pd.model;
+            if (!model->skinned || !model->skeleton || boneOffsets.count(model)) continue;
+            Skeleton& sk = *model->skeleton;
+            device->ensureSkeleton(sk);
+            uint64_t anim = 0;
+            t3d_pose P; std::memset(&P, 0, sizeof P);
+            if (AnimationPlayer* ap = model->posePlayer.get()) {
+                if (ap->animation && ap->sampled) {
+                    if (ap->BlendTime > 0 || ap->animation->relativeMotion)
+                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer blending / relative motion (animation.go:850-907, 962-984) is not evaluated on the device");
+                    anim = device->ensureAnimation(*ap->animation, sk);
+                    P.playhead = ap->sampledPlayhead;
+                }
+            }
+            m4_store(model->SkinRoot ? model->SkinRoot->Transform() : m4_identity(), P.root);
+            auto key = std::make_pair(sk.id, anim);
+            auto it = groupOf.find(key);
+            if (it == groupOf.end()) { it = groupOf.emplace(key, groups.size()).first; groups.push_back(Group{&sk, anim, {}, {}}); }
+            Group& g = groups[it->second];
+            g.poses.push_back(P); g.models.push_back(model);
+            boneOffsets.emplace(model, 0u);        // filled in below
+        }
+        for (Group& g : groups) {
+            uint32_t off = 0;
+            check(ctx, t3d_submit_poses(ctx, g.sk->id, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses");
+            for (size_t i = 0; i < g.models.size(); i++) boneOffsets[g.models[i]] = off + (uint32_t)(i * g.sk->BoneCount());
+        }
+    }
 
     renders.clear(); flushes.clear(); localFlushIds.clear();
     std::vector<t3d_draw> draws; draws.reserve(pending.size());
@@ -682,7 +832,9 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                 d.light_list = sceneList;
             }
         }
-        if (model->skinned) {
+        if (model->skinned && model->skeleton) {
+            d.bone_offset = boneOffsets.at(model); d.bone_count = (uint32_t)model->skeleton->BoneCount();
+        } else if (model->skinned) {
             auto it = boneOffsets.find(model);
             if (it == boneOffsets.end()) {
                 uint32_t off = 0;
@@ -702,6 +854,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         submitted.push_back(&pd);
         renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)draws.size() - 1});
     }
+    lastBoneOffsets.clear();
+    for (auto& kv : boneOffsets) lastBoneOffsets[kv.first->name] = kv.second;
     lap("build t3d_draw records");
     if (!draws.empty()) check(ctx, t3d_submit_draws(ctx, draws.data(), (uint32_t)draws.size()), "t3d_submit_draws");
     lap("t3d_submit_draws");

@@ -171,6 +171,72 @@ struct LightGroup {
     bool Active = true;
 };
 
+// ---- animation.go -------------------------------------------------------------------------------------
+enum { TrackTypePosition = 0, TrackTypeScale = 1, TrackTypeRotation = 2 };           // animation.go:10-14 (strings there)
+enum { InterpolationLinear = 0, InterpolationConstant = 1, InterpolationCubic = 2 }; // animation.go:17-21
+enum { AnimationLoopModeLoop = 0, AnimationLoopModePingPong = 1, AnimationLoopModeOneshot = 2 };
+struct Keyframe { float Time; float Data[4]; };                                       // animation.go:36-39
+struct AnimationTrack {                                                              // animation.go:49-54
+    int Type = TrackTypePosition, Interpolation = InterpolationLinear;
+    std::vector<Keyframe> Keyframes;
+    void AddKeyframe(float time, float x, float y, float z, float w) { Keyframes.push_back(Keyframe{time, {x, y, z, w}}); }
+};
+struct AnimationChannel {                                                            // animation.go:168-173
+    std::string Name;
+    std::shared_ptr<AnimationTrack> Tracks[3];
+    std::shared_ptr<AnimationTrack> AddTrack(int trackType);
+};
+struct Animation {                                                                   // animation.go:204-222
+    std::string name;
+    uint64_t id;
+    std::vector<std::shared_ptr<AnimationChannel>> channels;    // Go: map by channel name
+    float length = 0;
+    int loopMode = AnimationLoopModeLoop;
+    bool relativeMotion = false;
+    uint32_t generation = 1;                                    // bump (MarkDirty) after editing keyframes: the device copy is rebuilt
+    explicit Animation(const std::string& n);
+    std::shared_ptr<AnimationChannel> AddChannel(const std::string& name);
+    void MarkDirty() { generation++; }
+};
+
+// The joint list of a skin (gltf.go:1452-1511) as one shareable object: which bone hangs off which, the bones'
+// inverse bind matrices and the local transforms their Nodes hold when no track overrides them.  Every armature
+// cloned from one GLTF skin shares it.
+struct Skeleton {
+    uint64_t id;
+    std::vector<std::string> boneNames;
+    std::vector<int32_t> parent;                 // parent bone or -1; parents first
+    std::vector<float> inverseBind, restPosition, restScale, restRotation;   // 16, 3, 3, 16 floats per bone
+    uint32_t generation = 1, uploadedGeneration = 0;
+    Skeleton();
+    int BoneCount() const { return (int)parent.size(); }
+    // bone nodes in joint order; parents must come before children.  Bones whose parent is not in the list hang off the pose's root.
+    static std::shared_ptr<Skeleton> FromJoints(const std::vector<std::shared_ptr<Node>>& joints, const std::vector<float>& inverseBind16);
+};
+
+// AnimationPlayer (animation.go:437-480) for armatures whose bone poses are evaluated on the device: it keeps the
+// playhead logic of updateValues (animation.go:724-806) on the host and records the playhead the tracks were last
+// sampled at; the sampling itself, the bones' Transform() and boneInfluence run in k_pose_bones.  Blending
+// (BlendTime > 0), relative motion, markers and sequence callbacks need the host path and are refused.
+struct AnimationPlayer {
+    std::shared_ptr<Node> RootNode;
+    std::shared_ptr<Animation> animation;
+    float playhead = 0, prevPlayhead = 0, PlaySpeed = 1, BlendTime = 0;
+    bool playing = false, finished = false, justLooped = false, sampled = false;
+    int loopCount = 0;
+    float sampledPlayhead = 0;                  // the playhead updateValues evaluated the tracks at (animation.go:686-712)
+    explicit AnimationPlayer(std::shared_ptr<Node> root) : RootNode(std::move(root)) {}
+    void Play(std::shared_ptr<Animation> anim);         // animation.go:517-566
+    void Update(float dt);                              // animation.go:810-824
+    void SetPlayhead(float time) { playhead = time; forceUpdate(0); }    // animation.go:828-831
+    float Playhead() const { return playhead; }
+    bool Finished() const { return finished; }
+    bool IsPlaying() const { return playing; }
+    void Pause() { playing = false; }
+    void Resume() { playing = true; }
+    void forceUpdate(float dt);                         // animation.go:837 -> updateValues 674-806
+};
+
 // ---- model.go -----------------------------------------------------------------------------------------
 struct Model : Node {
     std::shared_ptr<Mesh> mesh;
@@ -194,6 +260,14 @@ struct Model : Node {
     bool DynamicBatcher() const { return !DynamicBatchModels.empty(); }
     void DynamicBatchAdd(int meshPartIndex, const std::vector<std::shared_ptr<Model>>& models);   // model.go:217
     void SetBoneInfluences(const std::vector<float>& m) { boneInfluences = m; skinned = !m.empty(); }
+    // Bones posed on the device: the skin's skeleton, the node its root bones are children of (Model.SkinRoot, model.go:33)
+    // and the player animating that armature (nullptr: rest pose).
+    std::shared_ptr<Skeleton> skeleton;
+    std::shared_ptr<Node> SkinRoot;
+    std::shared_ptr<AnimationPlayer> posePlayer;
+    void SetSkeleton(std::shared_ptr<Skeleton> sk, std::shared_ptr<Node> skinRoot, std::shared_ptr<AnimationPlayer> player) {
+        skeleton = std::move(sk); SkinRoot = std::move(skinRoot); posePlayer = std::move(player); skinned = skeleton != nullptr; boneInfluences.clear();
+    }
 };
 
 // ---- world.go / scene.go ----------------------------------------------------------------------------
@@ -223,6 +297,11 @@ struct GeometryDevice {
     ~GeometryDevice();
     void ensureMesh(Mesh& m);
     void ensureVolume(LightVolume& v);
+    void ensureSkeleton(Skeleton& s);
+    // animation tracks reordered to the skeleton's bones (channels find their bone by name, animation.go:618-672): device id
+    uint64_t ensureAnimation(Animation& a, Skeleton& s);
+    std::map<std::pair<uint64_t, uint64_t>, std::pair<uint64_t, uint64_t>> residentAnimations;   // (animation, skeleton) -> (device id, generation key)
+    uint64_t nextAnimationId = 1;
 };
 
 // ---- camera.go ------------------------------------------------------------------------------------------
@@ -258,6 +337,7 @@ struct Camera : Node {
     bool ModelInFrustum(Model& m);                  // camera.go:986
     void Clear();                                   // camera.go:1002 (DebugInfo reset + cached camera axes)
     void RenderScene(Scene& scene);                 // camera.go:1095
+    std::map<std::string, uint32_t> lastBoneOffsets;   // skinned model name -> t3d_draw.bone_offset of the last Render (tests read the bones back)
     void RenderNodes(Scene& scene, Node& root);     // camera.go:1105
     void Render(Scene& scene, const std::vector<ILight*>& lights, const std::vector<Model*>& models);   // camera.go:1269
     // when false the lists stay on the device (t3d_frame_results_device)

@@ -138,6 +138,62 @@ class LightGroupDesc:
 
 
 @dataclass(eq=False)
+class SkeletonDesc:
+    """The joint list of a skin (gltf.go:1452-1511): parents first; a parent of -1 hangs off the armature node."""
+    names: List[str]
+    parent: np.ndarray              # (n,) int32
+    inverse_bind: np.ndarray        # (n, 16)
+    rest_position: np.ndarray       # (n, 3)
+    rest_scale: np.ndarray          # (n, 3)
+    rest_rotation: np.ndarray       # (n, 16)
+
+    def __post_init__(self):
+        self.parent = np.ascontiguousarray(self.parent, np.int32).reshape(-1)
+        n = len(self.parent)
+        self.inverse_bind = np.ascontiguousarray(self.inverse_bind, np.float32).reshape(n, 16)
+        self.rest_position = np.ascontiguousarray(self.rest_position, np.float32).reshape(n, 3)
+        self.rest_scale = np.ascontiguousarray(self.rest_scale, np.float32).reshape(n, 3)
+        self.rest_rotation = np.ascontiguousarray(self.rest_rotation, np.float32).reshape(n, 16)
+
+
+TRACK_POSITION, TRACK_SCALE, TRACK_ROTATION = 0, 1, 2
+INTERPOLATION_LINEAR, INTERPOLATION_CONSTANT, INTERPOLATION_CUBIC = 0, 1, 2
+
+
+@dataclass(eq=False)
+class TrackDesc:
+    times: np.ndarray               # (k,)
+    values: np.ndarray              # (k, 4): x y z _ or a quaternion x y z w
+    interpolation: int = INTERPOLATION_LINEAR
+
+    def __post_init__(self):
+        self.times = np.ascontiguousarray(self.times, np.float32).reshape(-1)
+        v = np.asarray(self.values, np.float32).reshape(len(self.times), -1)
+        if v.shape[1] == 3:
+            v = np.concatenate([v, np.zeros((len(v), 1), np.float32)], axis=1)
+        self.values = np.ascontiguousarray(v, np.float32)
+
+
+@dataclass(eq=False)
+class AnimationDesc:
+    """animation.go:204-222: channel name (= bone name) -> {track type -> TrackDesc}."""
+    name: str
+    length: float
+    channels: dict
+    loop_mode: int = 0
+
+
+@dataclass(eq=False)
+class PoseDesc:
+    """An armature whose bones are posed from an animation at `playhead` (None: rest pose); `root` is the armature node
+    the skeleton's root bones are children of (Model.SkinRoot, model.go:33)."""
+    skeleton: SkeletonDesc
+    animation: Optional[AnimationDesc] = None
+    playhead: float = 0.0
+    root: NodeDesc = field(default_factory=NodeDesc)
+
+
+@dataclass(eq=False)
 class ModelDesc:
     mesh: MeshDesc
     node: NodeDesc = field(default_factory=NodeDesc)
@@ -146,6 +202,7 @@ class ModelDesc:
     visible: bool = True
     frustum_culling: bool = True
     bone_influences: Optional[np.ndarray] = None     # (n_bones, 16): makes the model skinned
+    pose: Optional[PoseDesc] = None                  # instead of bone_influences: bones posed from a skeleton + animation
     light_group: Optional[LightGroupDesc] = None
     batch_owner: Optional["ModelDesc"] = None        # Model.DynamicBatchOwner
     batch_owner_part: int = 0

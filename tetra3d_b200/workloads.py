@@ -10,8 +10,9 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .scenedesc import (LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_VOLUME, CameraDesc, LightDesc, LightGroupDesc,
-                        MaterialDesc, MeshDesc, ModelDesc, NodeDesc, PartDesc, SceneDesc, VolumeDesc, WorldDesc)
+from .scenedesc import (INTERPOLATION_CONSTANT, LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_VOLUME, TRACK_POSITION, TRACK_ROTATION,
+                        TRACK_SCALE, AnimationDesc, CameraDesc, LightDesc, LightGroupDesc, MaterialDesc, MeshDesc, ModelDesc, NodeDesc, PartDesc,
+                        PoseDesc, SceneDesc, SkeletonDesc, TrackDesc, VolumeDesc, WorldDesc)
 
 F32 = np.float32
 
@@ -203,6 +204,73 @@ def chain_bone_influences(bone_y: np.ndarray, base_pos, phase: float, t: float =
     return out
 
 
+def chain_skeleton(bone_y: np.ndarray) -> "SkeletonDesc":
+    """The bone chain of tube_character_mesh as a skin's joint list: bone b is a child of bone b - 1, sits at (0, bone_y[b], 0)
+    in the bind pose, inverseBind = Translate(0, -bone_y[b], 0)."""
+    n = len(bone_y)
+    inv = np.tile(np.eye(4, dtype=F32).reshape(1, 16), (n, 1))
+    inv[:, 13] = -bone_y
+    pos = np.zeros((n, 3), F32)
+    pos[:, 1] = np.diff(np.concatenate([[0.0], bone_y.astype(np.float64)])).astype(F32)
+    return SkeletonDesc(names=["bone%d" % b for b in range(n)], parent=np.arange(-1, n - 1, dtype=np.int32), inverse_bind=inv,
+                        rest_position=pos, rest_scale=np.ones((n, 3), F32), rest_rotation=np.tile(np.eye(4, dtype=F32).reshape(1, 16), (n, 1)))
+
+
+def chain_animation(skeleton: "SkeletonDesc", length: float = 2.0, n_keys: int = 9, amplitude: float = 0.4, seed: int = 11) -> "AnimationDesc":
+    """A swaying loop for chain_skeleton: every bone has a rotation track (quaternions about Z, slerped), the root bone also a
+    position track (bobbing), one bone a stepped scale track and one bone no channel at all (it keeps its rest transform)."""
+    rng = np.random.default_rng(seed)
+    times = np.linspace(0.0, length, n_keys).astype(F32)
+    channels = {}
+    n = len(skeleton.names)
+    for b, name in enumerate(skeleton.names):
+        if b == n - 2 and n > 3:
+            continue
+        ang = amplitude * np.sin(2 * np.pi * times.astype(np.float64) / length + 0.5 * b)
+        axis_tilt = 0.15 * rng.standard_normal(3)
+        axis = np.array([0.0, 0.0, 1.0]) + axis_tilt
+        axis /= np.linalg.norm(axis)
+        q = np.concatenate([axis[None, :] * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1).astype(F32)
+        tracks = {TRACK_ROTATION: TrackDesc(times, q)}
+        if b == 0:
+            p = np.zeros((n_keys, 3), F32)
+            p[:, 1] = (0.1 * np.sin(4 * np.pi * times.astype(np.float64) / length)).astype(F32)
+            tracks[TRACK_POSITION] = TrackDesc(times, p)
+        if b == 2:
+            sc = np.ones((3, 3), F32); sc[1] = (1.1, 0.95, 1.1)
+            tracks[TRACK_SCALE] = TrackDesc(np.array([0.0, length / 2, length], F32), sc, interpolation=INTERPOLATION_CONSTANT)
+        channels[name] = tracks
+    return AnimationDesc("sway", length, channels)
+
+
+def skinned_crowd_animated_scene(n: int = 10000, seed: int = 3) -> SceneDesc:
+    """configs[2] with the bones posed on the device: the same characters, one shared skeleton and animation, every character at
+    its own playhead -- a frame ships one 80-byte pose per character instead of 8 matrices."""
+    rng = np.random.default_rng(seed)
+    mesh, bone_y = tube_character_mesh()
+    sk = chain_skeleton(bone_y)
+    anim = chain_animation(sk)
+    side = int(math.ceil(math.sqrt(n)))
+    playheads = rng.uniform(0, anim.length, n).astype(F32)
+    groups = []
+    for g in range(8):
+        ls = []
+        for k in range(2):
+            p = rng.uniform((-side, 1.0, -side), (side, 4.0, side))
+            c = rng.uniform(0.3, 1.0, 3)
+            ls.append(LightDesc(LIGHT_POINT, NodeDesc(position=tuple(float(x) for x in p)), color=tuple(float(x) for x in c), energy=3.0,
+                                range=12.0 + side, in_scene=False, name="g%dp%d" % (g, k)))
+        groups.append(LightGroupDesc(ls))
+    models = []
+    for i in range(n):
+        gx, gz = i % side, i // side
+        root = NodeDesc(position=(2.0 * (gx - side / 2), 0.0, 2.0 * (gz - side / 2)))
+        models.append(ModelDesc(mesh, NodeDesc(), pose=PoseDesc(sk, anim, float(playheads[i]), root), light_group=groups[i % 8],
+                                frustum_culling=False, name="char%d" % i))
+    cam = CameraDesc(node=NodeDesc(position=(0.0, 12.0, float(side) + 20.0), rotation=rotation_matrix((1, 0, 0), math.radians(-25))), far=400.0)
+    return SceneDesc(models, [], cam, WorldDesc(ambient_energy=0.2), name="skinned_crowd_animated")
+
+
 # ---- lights ----------------------------------------------------------------------------------------------
 def standard_lights(seed: int = 2, box_min=(-50, 2, -25), box_max=(50, 6, 25), n_point: int = 4, point_range: float = 0.0,
                     energy: float = 2.0) -> List[LightDesc]:
@@ -317,4 +385,6 @@ WORKLOADS = {
     "instanced_shard": lambda: instanced_scene(n=2442),
     "particles_200k": lambda: particles_scene(n=200000),
     "skinned_crowd_1k": lambda: skinned_crowd_scene(n=1000),
+    "skinned_crowd_animated": skinned_crowd_animated_scene,
+    "skinned_crowd_animated_1k": lambda: skinned_crowd_animated_scene(n=1000),
 }
