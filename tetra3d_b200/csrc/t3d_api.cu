@@ -1001,6 +1001,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         }
         const uint8_t* hf = static_cast<const uint8_t*>(ctx->hFrameDev);
         // bone poses evaluated on the device: one launch per t3d_submit_poses call, into the arena behind the submitted matrices
+        PoseBatch fused[PREP_POSE_BATCHES]; uint32_t nFused = 0;
         for (const PoseCall& c : ctx->poseCalls) {
             const Skeleton& S = ctx->skeletons.at(c.skeleton);
             PoseBatch pb; memset(&pb, 0, sizeof pb);
@@ -1012,15 +1013,18 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             }
             pb.poses = reinterpret_cast<const t3d_pose*>(hf + ctx->framePosesOff) + c.firstPose;
             pb.out = ctx->pBones + 16 * ((size_t)ctx->frameBoneCount + c.firstBone);
-            CU(launch_pose_bones(s, pb));
-            ctx->launches += 1;
+            // small skeletons (every ordinary character) ride as extra blocks of k_prep_draws: no launch of their own, and
+            // their PCIe round trip and double-precision Slerp overlap the draw records' fetch
+            const size_t need = ((size_t)32 * (pb.nBones >= 256 ? 1 : 256 / pb.nBones) * pb.nBones + 20 * (pb.nBones >= 256 ? 1 : 256 / pb.nBones)) * 4;
+            if (nFused < PREP_POSE_BATCHES && need <= PREP_POSE_SMEM) fused[nFused++] = pb;
+            else { CU(launch_pose_bones(s, pb)); ctx->launches += 1; }
         }
         launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
                           reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
                           (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
                           hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
                           ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
-                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax);
+                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused);
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};

@@ -18,6 +18,7 @@
 //
 // Built with -fmad=false: no multiply-add contraction anywhere (see t3d_device.cuh).
 #include "t3d_device.cuh"
+#include "t3d_pose.cuh"
 #include "t3d_internal.h"
 #include "../../include/t3dgeo.h"
 #include <algorithm>
@@ -51,6 +52,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // they name in shared memory, rebuild the full records there, derive the per-draw uniforms and write the
 // finished records to the device; the remaining blocks copy the rest of the block verbatim.
 static const int PREP_THREADS = 256;
+static_assert(PREP_THREADS == POSE_THREADS, "pose blocks ride in k_prep_draws' grid");
 static const int PREP_DRAWS = 64;               // draws per block
 static const int PREP_TEMPLATES = 80;           // templates staged per block: the index window [tmin, tmin + 80) of its draws
 static const uint32_t PREP_SMEM_LIGHTS = 256;   // light lists up to this many entries are staged in shared memory
@@ -86,6 +88,8 @@ struct PrepFrame {
     // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
     uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
+    // bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i
+    PoseBatch pose[PREP_POSE_BATCHES]; uint32_t poseBlock[PREP_POSE_BATCHES + 1]; uint32_t nPoseBatches;
 };
 
 #ifndef T3D_PREP_MINBLOCKS
@@ -96,8 +100,14 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
              LightU* __restrict__ lightsU, DrawStat* __restrict__ stats) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
+    if (pf.nPoseBatches && blockIdx.x >= pf.poseBlock[0]) {      // the last blocks of the grid: bone poses (independent of the rest)
+        uint32_t i = 0;
+        while (i + 1 < pf.nPoseBatches && blockIdx.x >= pf.poseBlock[i + 1]) i++;
+        pose_block(pf.pose[i], blockIdx.x - pf.poseBlock[i], reinterpret_cast<float*>(prepSmem));
+        return;
+    }
     if (blockIdx.x >= pf.nPrepBlocks) {
-        const uint32_t nb = gridDim.x - pf.nPrepBlocks;
+        const uint32_t nb = (pf.nPoseBatches ? pf.poseBlock[0] : gridDim.x) - pf.nPrepBlocks;
         const uint32_t stride = nb * PREP_THREADS;
         const uint4* __restrict__ src = pf.hostRest;
         uint4* __restrict__ dst = pf.devRest;
@@ -1318,7 +1328,8 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
-                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax) {
+                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
+                       const PoseBatch* poses, uint32_t nPoseBatches) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
     PrepFrame pf;
@@ -1336,15 +1347,25 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.tmplCap = std::min<uint32_t>(std::max(tmplSpanMax, 1u), PREP_TEMPLATES);
     pf.lightCap = nLightsIn <= PREP_SMEM_LIGHTS ? nLightsIn : 0u;
 #ifdef T3D_PREP_SMEM_STATIC
-    const size_t smem = PREP_SMEM_MAX;
+    size_t smem = PREP_SMEM_MAX;
 #else
-    const size_t smem = PREP_SMEM_FIXED + (size_t)pf.tmplCap * sizeof(DrawRec) + (size_t)pf.lightCap * sizeof(t3d_light);
+    size_t smem = PREP_SMEM_FIXED + (size_t)pf.tmplCap * sizeof(DrawRec) + (size_t)pf.lightCap * sizeof(t3d_light);
 #endif
     const uint32_t nCopy = std::max(pf.rest16 ? std::min<uint32_t>(cdiv(pf.rest16, PREP_THREADS * 8), 1184u) : 0u,
                                     nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
-    launch_kernel(k_prep_draws, pf.nPrepBlocks + nCopy, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats);
+    // pose batches ride as extra blocks at the end of the grid (the caller only passes batches whose shared memory fits)
+    pf.nPoseBatches = std::min<uint32_t>(nPoseBatches, PREP_POSE_BATCHES);
+    uint32_t nBlocks = pf.nPrepBlocks + nCopy;
+    for (uint32_t i = 0; i < pf.nPoseBatches; i++) {
+        pf.pose[i] = poses[i];
+        pf.poseBlock[i] = nBlocks;
+        nBlocks += cdiv(poses[i].nPoses, pose_armatures_per_block(poses[i].nBones));
+        smem = std::max(smem, pose_smem_bytes(poses[i].nBones));
+    }
+    pf.poseBlock[pf.nPoseBatches] = nBlocks;
+    launch_kernel(k_prep_draws, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats);
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
