@@ -125,7 +125,8 @@ struct t3d_ctx {
     std::vector<uint32_t> hBlockRun;
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
-    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hVClass[3], hHuge;       // hVClass: vertex tiles by class (0 generic, 1 static fast, 2 skinned fast)
+    PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hHuge;
+    PinVec<uint4> hVClass[3];       // vertex tiles by class (0 generic, 1 static fast, 2 skinned fast): {tile, first draw, first draw of the next tile, end of the first draw's vertices}
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
     PinVec<float> hBones;
@@ -143,7 +144,7 @@ struct t3d_ctx {
     size_t frameRunsOff = 0, frameBlockRunOff = 0; bool frameRunMode = false;
     uint32_t blkTmin = 0, blkTmax = 0, tmplSpanMax = 1;     // widest template-index window of any 64-draw block (sizes k_prep_draws' staging)
     uint32_t frameBoneCount = 0;
-    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pTileV = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pVClass[3] = {nullptr, nullptr, nullptr}, *pHuge = nullptr;
+    DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pHuge = nullptr; uint4* pVClass[3] = {nullptr, nullptr, nullptr};
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
@@ -809,7 +810,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                 cls = (cls == -1 || cls == c) ? c : 0;
             }
             auto& list = ctx->hVClass[cls < 0 ? 0 : cls];
-            list.p[list.n++] = b;
+            const uint32_t dLo = ctx->hTileV.p[b];
+            list.p[list.n++] = make_uint4(b, dLo, ctx->hTileV.p[b + 1], ctx->hVbase.p[dLo + 1]);
         }
     }
     CU(build_tri_tiles(ctx, nDraws));
@@ -909,11 +911,11 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                        {ctx->hPoses.p, sizeof(t3d_pose) * ctx->hPoses.n, 0}};       // read by k_pose_bones
         Seg segs[13] = {
             {nullptr, 0, 0}, {nullptr, 0, 0} /* vbase / tbase: k_prep_draws writes the device tables from the placement records */,
-            {ctx->hTileV.p, 4ull * (nTilesV + 1), 0}, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
+            {nullptr, 0, 0} /* the vertex-tile table stays on the host: its entries travel inside the class lists */, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {nullptr, 0, 0} /* bones travel separately, below */,
-            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVClass[0].p, 4ull * ctx->hVClass[0].n, 0}, {ctx->hVClass[1].p, 4ull * ctx->hVClass[1].n, 0},
-            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 4ull * ctx->hVClass[2].n, 0}};
+            {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVClass[0].p, 16ull * ctx->hVClass[0].n, 0}, {ctx->hVClass[1].p, 16ull * ctx->hVClass[1].n, 0},
+            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 16ull * ctx->hVClass[2].n, 0}};
         size_t headBytes = 0, restBytes = 0;
         for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
         for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
@@ -959,17 +961,16 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pDraws = reinterpret_cast<DrawRec*>(base);
         ctx->pVbase = reinterpret_cast<uint32_t*>(rest + restBytes + devBoneBytes);
         ctx->pTbase = reinterpret_cast<uint32_t*>(rest + restBytes + devBoneBytes + devTableBytes);
-        ctx->pTileV = reinterpret_cast<uint32_t*>(rest + segs[2].off);
         ctx->pTiles = reinterpret_cast<TriTile*>(rest + segs[3].off);
         ctx->pLarge = reinterpret_cast<uint32_t*>(rest + segs[4].off);
         ctx->pPacked = reinterpret_cast<uint32_t*>(rest + segs[5].off);
         ctx->pLightsIn = reinterpret_cast<t3d_light*>(rest + segs[6].off);
         ctx->pBones = reinterpret_cast<float*>(rest + restBytes);
         ctx->pMedium = reinterpret_cast<uint32_t*>(rest + segs[8].off);
-        ctx->pVClass[0] = reinterpret_cast<uint32_t*>(rest + segs[9].off);
-        ctx->pVClass[1] = reinterpret_cast<uint32_t*>(rest + segs[10].off);
+        ctx->pVClass[0] = reinterpret_cast<uint4*>(rest + segs[9].off);
+        ctx->pVClass[1] = reinterpret_cast<uint4*>(rest + segs[10].off);
         ctx->pHuge = reinterpret_cast<uint32_t*>(rest + segs[11].off);
-        ctx->pVClass[2] = reinterpret_cast<uint32_t*>(rest + segs[12].off);
+        ctx->pVClass[2] = reinterpret_cast<uint4*>(rest + segs[12].off);
         ctx->h2dBytes = 0;
         for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
@@ -1028,7 +1029,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};
-    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pTileV, ctx->pVClass, nVClass, totalV, ctx->fc,
+    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pVClass, nVClass, totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 1 + (nVClass[0] ? 1 : 0) + (nVClass[1] ? 1 : 0) + (nVClass[2] ? 1 : 0);

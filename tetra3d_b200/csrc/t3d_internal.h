@@ -30,8 +30,8 @@ static const uint32_t PREP_POSE_BATCHES = 4;       // t3d_submit_poses calls tha
 static const size_t PREP_POSE_SMEM = 40 * 1024;
 static const int PREP_WINDOW_BLOCKS = 16, PREP_WINDOW_DRAWS = 64;     // k_prep_draws: blocks whose template windows travel as kernel parameters
 // tileLists / nTilesOf are indexed by vertex-tile class: 0 generic, 1 static fast, 2 skinned fast (t3d_kernels.cu: K1_*)
-void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
-                   const uint32_t* const tileLists[3], const uint32_t nTilesOf[3],
+void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
+                   const uint4* const tileLists[3], const uint32_t nTilesOf[3],
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel

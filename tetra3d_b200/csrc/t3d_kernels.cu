@@ -657,18 +657,20 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
 #endif
 template <int MODE>
 __device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
-         const uint32_t* __restrict__ tileFirst, const uint32_t* __restrict__ tileList, uint32_t totalV, const FrameConst& fc,
+         const uint4* __restrict__ tileList, uint32_t totalV, const FrameConst& fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    const uint32_t tile = __ldg(&tileList[blockIdx.x]);
-    const uint32_t base = tile * (uint32_t)VERTEX_BLOCK;
+    // one load tells the block everything about its tile: {tile, first draw, first draw of the next tile, end of the first
+    // draw's vertices} (the host builds the lists from its vertex-tile table)
+    const uint4 entry = __ldg(&tileList[blockIdx.x]);
+    const uint32_t base = entry.x * (uint32_t)VERTEX_BLOCK;
     const uint32_t slot = base + threadIdx.x;
-    const uint32_t dLo = __ldg(&tileFirst[tile]), dHi = __ldg(&tileFirst[tile + 1]);
+    const uint32_t dLo = entry.y, dHi = entry.z;
     const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
     // dHi is the draw of the first slot of the NEXT tile, so dLo == dHi covers this whole tile; otherwise the
     // tile is still uniform when the next draw starts at or after its end
-    bool staged = dLo == dHi || __ldg(&vbase[dLo + 1]) >= end;
+    bool staged = dLo == dHi || entry.w >= end;
     if (staged) {
         const DrawRec& R = draws[dLo];
         const uint32_t flags = R.flags;
@@ -720,15 +722,15 @@ __device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restric
 // once and waits for its predecessor at its END, which keeps "this kernel complete => every earlier kernel complete".
 template <int MODE>
 __global__ void __launch_bounds__(VERTEX_BLOCK, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
-k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ tileFirst,
-         const uint32_t* __restrict__ tileList, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
+k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
+         const uint4* __restrict__ tileList, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
     if (!second) pdl_wait();        // everything below reads what k_prep_draws wrote
     pdl_launch();
-    vertex_tile<MODE>(sU, draws, vbase, tileFirst, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+    vertex_tile<MODE>(sU, draws, vbase, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
     if (second) pdl_wait();
 }
 
@@ -1368,25 +1370,25 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     launch_kernel(k_prep_draws, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats);
 }
 
-void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint32_t* tileFirst,
-                   const uint32_t* const tileLists[3], const uint32_t nTilesOf[3],
+void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
+                   const uint4* const tileLists[3], const uint32_t nTilesOf[3],
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
     // the launches write disjoint slots; every one after the first overlaps its predecessor and waits for it at its end
     // (`second`; needs the dependent-launch chain: with stage events between kernels they all wait at the top)
     bool first = true;
     if (nTilesOf[K1_STATIC]) {
-        launch_kernel(k_vertex<K1_STATIC>, nTilesOf[K1_STATIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_STATIC], totalV, 0u, fc,
+        launch_kernel(k_vertex<K1_STATIC>, nTilesOf[K1_STATIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_STATIC], totalV, 0u, fc,
                       lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
         first = false;
     }
     if (nTilesOf[K1_SKINNED]) {
-        launch_kernel(k_vertex<K1_SKINNED>, nTilesOf[K1_SKINNED], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_SKINNED], totalV,
+        launch_kernel(k_vertex<K1_SKINNED>, nTilesOf[K1_SKINNED], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_SKINNED], totalV,
                       (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
         first = false;
     }
     if (nTilesOf[K1_GENERIC])
-        launch_kernel(k_vertex<K1_GENERIC>, nTilesOf[K1_GENERIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileFirst, tileLists[K1_GENERIC], totalV,
+        launch_kernel(k_vertex<K1_GENERIC>, nTilesOf[K1_GENERIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_GENERIC], totalV,
                       (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
 }
 
