@@ -1016,8 +1016,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             pb.out = ctx->pBones + 16 * ((size_t)ctx->frameBoneCount + c.firstBone);
             // small skeletons (every ordinary character) ride as extra blocks of k_prep_draws: no launch of their own, and
             // their PCIe round trip and double-precision Slerp overlap the draw records' fetch
-            const size_t need = ((size_t)32 * (pb.nBones >= 256 ? 1 : 256 / pb.nBones) * pb.nBones + 20 * (pb.nBones >= 256 ? 1 : 256 / pb.nBones)) * 4;
-            if (nFused < PREP_POSE_BATCHES && need <= PREP_POSE_SMEM) fused[nFused++] = pb;
+            if (nFused < PREP_POSE_BATCHES && pose_batch_smem(pb.nBones) <= PREP_POSE_SMEM) fused[nFused++] = pb;
             else { CU(launch_pose_bones(s, pb)); ctx->launches += 1; }
         }
         launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,

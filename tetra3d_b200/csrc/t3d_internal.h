@@ -59,5 +59,6 @@ void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t n
 
 // t3d_pose.cu -- bone poses evaluated on the device
 cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb);
+size_t pose_batch_smem(uint32_t nBones);        // shared memory a block needs for a skeleton of nBones
 
 }  // namespace t3d

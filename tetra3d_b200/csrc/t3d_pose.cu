@@ -25,6 +25,8 @@ k_pose_bones(const __grid_constant__ PoseBatch pb) {
     pose_block(pb, blockIdx.x, poseSmem);
 }
 
+size_t pose_batch_smem(uint32_t nBones) { return pose_smem_bytes(nBones); }
+
 cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb) {
     if (!pb.nPoses || !pb.nBones) return cudaSuccess;
     const uint32_t ipb = pose_armatures_per_block(pb.nBones);
