@@ -15,8 +15,8 @@
  *  - Outputs are library-owned buffers, valid until the next t3d_frame_begin on the same context.
  *  - Every function returns T3D_OK (0) or a negative T3D_E_* code; t3d_last_error gives the text.
  *    Nothing aborts.  Features that need host callbacks (Model.VertexTransformFunction model.go:47,
- *    Model.VertexClipFunction model.go:53, Material.CustomDepthFunction material.go:129, auto-subdivision
- *    model.go:729-739, LightVolumeCell.useLights light.go:652-654) cannot run on the device: the shim
+ *    Model.VertexClipFunction model.go:53, Material.CustomDepthFunction material.go:129) and auto-subdivision
+ *    (model.go:729-739) cannot run on the device: the shim
  *    must not submit such draws (it keeps the Go path for them) -- there is no CPU fallback in here.
  *  - One context per GPU, single caller at a time (the reference path is single-goroutine, non
  *    re-entrant: tetra3d.go:21-35, sortingTriangles.go:164).
@@ -160,6 +160,10 @@ typedef struct t3d_volume_desc {
     float    offset[3];
     float    light_bias[3];
     const float* cell_colors;          /* 3 * cx*cy*cz, index x + y*cx + z*cx*cy (light.go:1271) */
+    /* LightVolumeCell.useLights (light.go:1381, 1508-1514), optional: per cell a run of indices into the light array the
+     * frame passes to t3d_volume_use_lights, in SetUseLights order.  NULL: no cell uses lights. */
+    const uint32_t* cell_light_start;  /* [cells + 1] */
+    const uint32_t* cell_light_index;  /* [cell_light_start[cells]] */
 } t3d_volume_desc;
 
 /* One render(rp) call (camera.go:1507): Model x MeshPart, in render order. */
@@ -274,6 +278,11 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
 /* Replaces: building sceneLights / LightGroup.Lights (camera.go:1275-1303, 1576-1581).  Returns a
  * light-list handle in *list_id; list 0 is always the empty list. */
 int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id);
+/* Replaces: LightVolume.beginRender / beginModel over useLightsRenderSet (light.go:565-580) and the nested
+ * light.VertexLight calls of LightVolume.VertexLight (light.go:652-654).  `lights` are the lights the volume's cells
+ * refer to (cell_light_index), in world space like t3d_submit_lights; ambient, point and directional only.  Per frame,
+ * before the first t3d_submit_lights whose list holds the volume. */
+int t3d_volume_use_lights(t3d_ctx* ctx, uint32_t volume_id, const t3d_light* lights, uint32_t n);
 /* Replaces: reading bone.boneInfluence per vertex (model.go:574-580, node.go:592-594).  Appends n
  * matrices to the frame's bone arena and returns the offset of the first in *offset. */
 int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset);

@@ -70,7 +70,7 @@ class orc_light_group(C.Structure):
 class orc_light_volume(C.Structure):
     _fields_ = [("dim_min", C.c_float * 3), ("dim_max", C.c_float * 3), ("cell_size", C.c_float * 3),
                 ("cell_count", C.c_int32 * 3), ("offset", C.c_float * 3), ("light_bias", C.c_float * 3),
-                ("cell_colors", f32p)]
+                ("cell_colors", f32p), ("cell_light_start", i32p), ("cell_light_index", i32p)]
 
 
 class orc_camera(C.Structure):
@@ -419,6 +419,12 @@ class _Marshalled:
                 for l in m.light_group.lights:
                     if not any(l is x for x in all_lights):
                         all_lights.append(l)
+        for l in list(all_lights):          # lights that only LightVolume cells use (LightVolumeCell.SetUseLights)
+            if l.type == LIGHT_VOLUME and l.volume is not None and l.volume.cell_lights:
+                for key in sorted(l.volume.cell_lights):
+                    for nl in l.volume.cell_lights[key]:
+                        if not any(nl is x for x in all_lights):
+                            all_lights.append(nl)
         light_index = {id(l): i for i, l in enumerate(all_lights)}
         volumes = []
         c_lights = (orc_light * max(len(all_lights), 1))()
@@ -442,6 +448,16 @@ class _Marshalled:
             cv.offset[:] = [float(x) for x in v.offset]; cv.light_bias[:] = [float(x) for x in v.light_bias]
             cols = np.ascontiguousarray(v.colors, np.float32); self.keep.append(cols)
             cv.cell_colors = _fp(cols)
+            if v.cell_lights:
+                cx, cy, cz = (int(x) for x in v.cell_count)
+                start = np.zeros(cx * cy * cz + 1, np.int32); index = []
+                per_cell = {int(x) + int(y) * cx + int(z) * cx * cy: ls for (x, y, z), ls in v.cell_lights.items()}
+                for c in range(cx * cy * cz):
+                    index.extend(light_index[id(nl)] for nl in per_cell.get(c, []))
+                    start[c + 1] = len(index)
+                index = np.asarray(index if index else [0], np.int32)
+                self.keep.extend([start, index])
+                cv.cell_light_start = start.ctypes.data_as(i32p); cv.cell_light_index = index.ctypes.data_as(i32p)
         self.keep.append(c_volumes)
 
         groups = []

@@ -791,8 +791,17 @@ static void process_vertices(rstate* S, int mi, int pi, float* outMin, float* ou
 /* ------------------------------------------------------------------------------------------ */
 
 /* beginRender: light.go:110-112 (ambient), 173 (point), 322-324 (sun), 567-572 (volume) */
+static int lv_cell_count(const orc_light_volume* lv) { return lv->cell_count[0] * lv->cell_count[1] * lv->cell_count[2]; }
+
 static void light_begin_render(rstate* S, int li) {
     const orc_light* l = &S->sc->lights[li];
+    if (l->type == ORC_LIGHT_VOLUME) {                        /* light.go:565-570: every light some cell uses */
+        const orc_light_volume* lv = &S->sc->volumes[l->volume];
+        if (lv->cell_light_start)
+            for (int k = 0; k < lv->cell_light_start[lv_cell_count(lv)]; k++)
+                if (S->sc->lights[lv->cell_light_index[k]].type != ORC_LIGHT_VOLUME) light_begin_render(S, lv->cell_light_index[k]);
+        return;
+    }
     if (l->type == ORC_LIGHT_AMBIENT) {
         S->ambResult[li][0] = l->color[0] * l->energy;
         S->ambResult[li][1] = l->color[1] * l->energy;
@@ -807,6 +816,13 @@ static void light_begin_render(rstate* S, int li) {
 static void light_begin_model(rstate* S, int li, int mi) {
     const orc_light* l = &S->sc->lights[li];
     const orc_model* model = &S->sc->models[mi];
+    if (l->type == ORC_LIGHT_VOLUME) {                        /* light.go:574-580 */
+        const orc_light_volume* lv = &S->sc->volumes[l->volume];
+        if (lv->cell_light_start)
+            for (int k = 0; k < lv->cell_light_start[lv_cell_count(lv)]; k++)
+                if (S->sc->lights[lv->cell_light_index[k]].type != ORC_LIGHT_VOLUME) light_begin_model(S, lv->cell_light_index[k], mi);
+        return;
+    }
     if (l->type == ORC_LIGHT_POINT) {
         mat4 inv = m4_inverted(S_transform(S, model->node));
         vec3 pos, sca; mat4 rot;
@@ -917,8 +933,15 @@ static void vertex_light(rstate* S, int li, int index, int mi, const orc_materia
             if (objectShadingMode == ORC_LV_PER_VERTEX_WITH_NORMAL) lv_indices(lv, vertPosWithNormal, &x, &y, &z);
             else lv_indices(lv, vertPos, &x, &y, &z);
             const float* cell = lv_cell(lv, x, y, z);
-            if (cell) { cellColor[0] = cell[0]; cellColor[1] = cell[1]; cellColor[2] = cell[2]; }
-            /* cell.useLights nesting (light.go:652-654) is not modelled: scenes must not use it. */
+            if (cell) {
+                cellColor[0] = cell[0]; cellColor[1] = cell[1]; cellColor[2] = cell[2];
+                if (lv->cell_light_start) {                   /* light.go:652-654: the cell's own lights, before the cell colour */
+                    const size_t c = (size_t)(cell - lv->cell_colors) / 3;
+                    for (int k = lv->cell_light_start[c]; k < lv->cell_light_start[c + 1]; k++)
+                        if (S->sc->lights[lv->cell_light_index[k]].type != ORC_LIGHT_VOLUME)   /* a volume nested in a volume: not modelled */
+                            vertex_light(S, lv->cell_light_index[k], index, mi, mat);
+                }
+            }
         }
         target->X += l->color[0] * cellColor[0] * l->energy;
         target->Y += l->color[1] * cellColor[1] * l->energy;

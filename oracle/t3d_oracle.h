@@ -139,6 +139,10 @@ typedef struct {
     float offset[3];
     float light_bias[3];
     const float* cell_colors;       /* 3 * cx*cy*cz, index x + y*cx + z*cx*cy */
+    /* LightVolumeCell.useLights (light.go:1381, 1508-1514): per cell (same index as cell_colors) a run of scene light
+     * indices, in SetUseLights order; cell_light_start == NULL: no cell uses lights */
+    const int32_t* cell_light_start;    /* [cells + 1] */
+    const int32_t* cell_light_index;    /* indices into orc_scene.lights */
 } orc_light_volume;
 
 /* Camera (camera.go:259-332). */

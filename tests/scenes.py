@@ -208,6 +208,36 @@ def volume_scene(seed=0, mode=0) -> SceneDesc:
     return SceneDesc(models, lights, CameraDesc(), WorldDesc(), name="volume")
 
 
+def volume_cell_lights_scene(seed=0, mode=0, skinned=False) -> SceneDesc:
+    """LightVolumeCell.useLights (light.go:652-654, 1508-1514): a third of the cells carry their own lights -- ranged and
+    unranged point lights, a sun, an ambient light, one of them also in the scene list, some cells with several -- that
+    light a vertex before the cell colour does."""
+    sc = volume_scene(seed, mode)
+    rng = np.random.default_rng(900 + seed)
+    vol = sc.lights[0].volume
+    cx, cy, cz = vol.cell_count
+    pool = [LightDesc(LIGHT_POINT, NodeDesc(position=(2.0, 3.0, 1.0)), color=(1.0, 0.3, 0.2), energy=3.0, in_scene=False, name="cell_point"),
+            LightDesc(LIGHT_POINT, NodeDesc(position=(-2.5, -1.0, 2.0)), color=(0.2, 0.4, 1.0), energy=2.0, range=6.0, in_scene=False, name="cell_ranged"),
+            LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=W.rotation_matrix((1, 0, 0), 0.9)), color=(0.6, 0.9, 0.5), energy=0.8, in_scene=False, name="cell_sun"),
+            LightDesc(LIGHT_AMBIENT, NodeDesc(), color=(0.3, 0.1, 0.3), energy=0.5, in_scene=False, name="cell_ambient"),
+            sc.lights[1]]                           # the scene's own point light: it then lights such vertices twice, as in the reference
+    cell_lights = {}
+    for z in range(cz):
+        for y in range(cy):
+            for x in range(cx):
+                if rng.random() < 0.35:
+                    k = int(rng.integers(1, 4))
+                    cell_lights[(x, y, z)] = [pool[int(i)] for i in rng.choice(len(pool), size=k, replace=False)]
+    vol.cell_lights = cell_lights
+    if skinned:
+        sk = skinned_scene(seed, n=2)
+        for m in sk.models:
+            m.light_group = None
+        sc.models.extend(sk.models)
+    sc.name = "volume_cell_lights"
+    return sc
+
+
 def transparent_scene(seed=0) -> SceneDesc:
     rng = np.random.default_rng(seed)
     models = []
@@ -275,6 +305,9 @@ ALL_SMALL = {
     "volume_mode1": lambda: volume_scene(2, 1),
     "volume_mode2": lambda: volume_scene(3, 2),
     "volume_off": lambda: volume_scene(4, 3),
+    "volume_cell_lights": lambda: volume_cell_lights_scene(5, 0),
+    "volume_cell_lights_normal": lambda: volume_cell_lights_scene(6, 1, skinned=True),
+    "volume_cell_lights_object": lambda: volume_cell_lights_scene(7, 2),
     "transparent": lambda: transparent_scene(1),
     "stress_small": lambda: SceneDesc([ModelDesc(W.cube_mesh(2, 2, 2, copies=20, material=MaterialDesc(shadeless=True, use_texture=True, tex_w=16, tex_h=16)),
                                                   NodeDesc(position=(4.0 * x, 0.0, 0.0)), name="m%d" % x) for x in range(6)], [], CameraDesc(), WorldDesc()),

@@ -127,6 +127,9 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
             _apply_node(l, ld.node)
         lights[id(ld)] = l
         objs[id(ld)] = l
+        if ld.type == LIGHT_VOLUME and ld.volume.cell_lights:
+            for (x, y, z) in sorted(ld.volume.cell_lights):
+                l.CellSetUseLights(int(x), int(y), int(z), *[make_light(nl) for nl in ld.volume.cell_lights[(x, y, z)]])
         return l
 
     groups: Dict[int, object] = {}

@@ -94,7 +94,7 @@ struct Mesh {
     }
 };
 
-struct LightList { uint32_t off, count; };
+struct LightList { uint32_t off, count, total; };     // total: count + the lights the list's LightVolume cells use
 
 }  // namespace
 
@@ -106,6 +106,9 @@ struct t3d_ctx {
     std::unordered_map<uint32_t, uint32_t> volumeIndex;     // id -> slot in volumes
     std::vector<VolumeU> volumes;
     std::vector<float*> volumeCells;
+    // LightVolumeCell.useLights: per volume slot the CSR (one device block: start[cells + 1] | index[]), how many lights the
+    // cells refer to, and this frame's lights (t3d_volume_use_lights)
+    std::vector<uint32_t*> volumeCsr; std::vector<uint32_t> volumeUseCount; std::vector<std::vector<t3d_light>> volumeUse;
     DevBuf dVolumes; bool volumesDirty = true;
     std::unordered_map<uint64_t, Skeleton> skeletons;
     std::unordered_map<uint64_t, Animation> animations;
@@ -237,6 +240,7 @@ void t3d_destroy(t3d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->meshes) kv.second.release();
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
+    for (uint32_t* c : ctx->volumeCsr) if (c) cudaFree(c);
     for (auto& kv : ctx->skeletons) if (kv.second.block) cudaFree(kv.second.block);
     for (auto& kv : ctx->animations) if (kv.second.block) cudaFree(kv.second.block);
     ctx->hPoses.release();
@@ -368,10 +372,13 @@ int t3d_volume_upload(t3d_ctx* ctx, uint32_t volume_id, const t3d_volume_desc* d
         slot = (uint32_t)ctx->volumes.size();
         ctx->volumes.push_back(VolumeU());
         ctx->volumeCells.push_back(nullptr);
+        ctx->volumeCsr.push_back(nullptr); ctx->volumeUseCount.push_back(0); ctx->volumeUse.emplace_back();
         ctx->volumeIndex[volume_id] = slot;
     } else {
         slot = it->second;
         if (ctx->volumeCells[slot]) { cudaFree(ctx->volumeCells[slot]); ctx->volumeCells[slot] = nullptr; }
+        if (ctx->volumeCsr[slot]) { cudaFree(ctx->volumeCsr[slot]); ctx->volumeCsr[slot] = nullptr; }
+        ctx->volumeUseCount[slot] = 0;
     }
     float* dc = nullptr;
     CU(cudaMalloc((void**)&dc, cells * 3 * sizeof(float)));
@@ -382,6 +389,23 @@ int t3d_volume_upload(t3d_ctx* ctx, uint32_t volume_id, const t3d_volume_desc* d
         V.cellCount[i] = (int32_t)d->cell_count[i]; V.offset[i] = d->offset[i]; V.bias[i] = d->light_bias[i];
     }
     V.cells = dc;
+    V.cellLightStart = V.cellLightIndex = nullptr;
+    if (d->cell_light_start) {
+        const uint32_t nIdx = d->cell_light_start[cells];
+        if (nIdx && !d->cell_light_index) return fail(ctx, T3D_E_INVALID, "t3d_volume_upload: cell_light_index is NULL");
+        uint32_t useCount = 0;
+        for (size_t c = 0; c < cells; c++) if (d->cell_light_start[c] > d->cell_light_start[c + 1]) return fail(ctx, T3D_E_INVALID, "t3d_volume_upload: cell_light_start must be non-decreasing");
+        for (uint32_t k = 0; k < nIdx; k++) useCount = std::max(useCount, d->cell_light_index[k] + 1);
+        if (nIdx) {
+            uint32_t* csr = nullptr;
+            CU(cudaMalloc((void**)&csr, 4 * (cells + 1 + nIdx)));
+            CU(cudaMemcpy(csr, d->cell_light_start, 4 * (cells + 1), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(csr + cells + 1, d->cell_light_index, 4ull * nIdx, cudaMemcpyHostToDevice));
+            ctx->volumeCsr[slot] = csr;
+            ctx->volumeUseCount[slot] = useCount;
+            V.cellLightStart = csr; V.cellLightIndex = csr + cells + 1;
+        }
+    }
     ctx->volumes[slot] = V;
     ctx->volumeCells[slot] = dc;
     ctx->volumesDirty = true;
@@ -396,7 +420,9 @@ int t3d_volume_release(t3d_ctx* ctx, uint32_t volume_id) {
     CU(cudaStreamSynchronize(ctx->stream));
     uint32_t slot = it->second;
     if (ctx->volumeCells[slot]) { cudaFree(ctx->volumeCells[slot]); ctx->volumeCells[slot] = nullptr; }
-    ctx->volumes[slot].cells = nullptr;
+    if (ctx->volumeCsr[slot]) { cudaFree(ctx->volumeCsr[slot]); ctx->volumeCsr[slot] = nullptr; }
+    ctx->volumeUseCount[slot] = 0;
+    ctx->volumes[slot].cells = nullptr; ctx->volumes[slot].cellLightStart = ctx->volumes[slot].cellLightIndex = nullptr;
     ctx->volumeIndex.erase(it);
     ctx->volumesDirty = true;
     return T3D_OK;
@@ -431,13 +457,14 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->hSlim.clear(); ctx->hTmpl.clear(); ctx->hRot.clear();
     ctx->hDraws.clear(); ctx->hVbase.clear(); ctx->hTbase.clear(); ctx->hLights.clear(); ctx->hBones.clear();
     ctx->lightLists.clear();
-    ctx->lightLists.push_back(LightList{0, 0});     // list 0: empty
+    ctx->lightLists.push_back(LightList{0, 0, 0});     // list 0: empty
     ctx->drawTotalTris.clear(); ctx->drawContinue.clear();
     ctx->vAcc = ctx->tAcc = ctx->luAcc = 0;
     ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->tmplSpanMax = 1;
     ctx->hPoses.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
+    for (auto& u : ctx->volumeUse) u.clear();
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
     return T3D_OK;
@@ -448,19 +475,50 @@ int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_lights: not between frame_begin and frame_execute");
     const uint32_t off = (uint32_t)ctx->hLights.n;
     CU(ctx->hLights.reserve(off + n));
+    uint32_t total = n;
     for (uint32_t i = 0; i < n; i++) {
         t3d_light L = lights[i];
         if (L.type > T3D_LIGHT_VOLUME) return fail(ctx, T3D_E_INVALID, "t3d_submit_lights: unknown light type");
         if (L.type == T3D_LIGHT_VOLUME) {
             auto it = ctx->volumeIndex.find(L.volume);
             if (it == ctx->volumeIndex.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_lights: unknown light volume");
-            L.volume = it->second;
+            const uint32_t slot = it->second;
+            // the lights the volume's cells use follow the list's own lights; the volume entry remembers where (k_prep_draws
+            // derives a LightU for every one of them, k_vertex finds them through LightU.useFirst)
+            if (slot >= (1u << 12) || total >= (1u << 20)) return fail(ctx, T3D_E_INVALID, "t3d_submit_lights: too many volumes or lights");
+            L.volume = slot;
+            if (ctx->volumeUseCount[slot]) {
+                if (ctx->volumeUse[slot].size() < ctx->volumeUseCount[slot])
+                    return fail(ctx, T3D_E_STATE, "t3d_submit_lights: the volume's cells use lights: call t3d_volume_use_lights first");
+                L.volume = slot | (total << 12);
+                total += ctx->volumeUseCount[slot];
+            }
         }
         ctx->hLights.p[off + i] = L;
     }
-    ctx->hLights.n = off + n;
+    CU(ctx->hLights.reserve(off + total));
+    uint32_t at = off + n;
+    for (uint32_t i = 0; i < n; i++) {
+        const t3d_light& L = ctx->hLights.p[off + i];
+        if (L.type != T3D_LIGHT_VOLUME || !(L.volume >> 12)) continue;
+        const uint32_t slot = L.volume & 0xFFFu;
+        for (uint32_t k = 0; k < ctx->volumeUseCount[slot]; k++) ctx->hLights.p[at++] = ctx->volumeUse[slot][k];
+    }
+    ctx->hLights.n = off + total;
     *list_id = (uint32_t)ctx->lightLists.size();
-    ctx->lightLists.push_back(LightList{off, n});
+    ctx->lightLists.push_back(LightList{off, n, total});
+    return T3D_OK;
+}
+
+int t3d_volume_use_lights(t3d_ctx* ctx, uint32_t volume_id, const t3d_light* lights, uint32_t n) {
+    if (!ctx || (n && !lights)) return fail(ctx, T3D_E_INVALID, "t3d_volume_use_lights: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_volume_use_lights: not between frame_begin and frame_execute");
+    auto it = ctx->volumeIndex.find(volume_id);
+    if (it == ctx->volumeIndex.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_volume_use_lights: unknown light volume");
+    for (uint32_t i = 0; i < n; i++)
+        if (lights[i].type >= T3D_LIGHT_VOLUME) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_volume_use_lights: ambient, point and directional lights only");
+    if (n < ctx->volumeUseCount[it->second]) return fail(ctx, T3D_E_INVALID, "t3d_volume_use_lights: fewer lights than the volume's cells refer to");
+    ctx->volumeUse[it->second].assign(lights, lights + n);
     return T3D_OK;
 }
 
@@ -642,14 +700,14 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         R.flags = flags; R.nKeys = m.nKeys; R.vstride = m.nVertsPad; R.tstride = m.nTrisPad;
         R.boneOffset = in.bone_offset;
         const LightList& ll = ctx->lightLists[in.light_list];
-        R.lightIn = ll.off; R.lightCount = ll.count; R.lightU = ctx->luAcc;
+        R.lightIn = ll.off; R.lightCount = ll.count; R.lightTotal = ll.total; R.lightU = ctx->luAcc;
         R.sortMode = (flags & T3D_DRAW_HAS_MATERIAL) ? in.sort_mode : (uint8_t)T3D_SORT_BACK_TO_FRONT;   // camera.go:1540-1543
         R.lightingMode = in.lighting_mode; R.lvMode = in.light_volume_mode;
         memcpy(R.transform, in.transform, 64);
         memcpy(R.worldRot, in.world_rotation, 64);
         memcpy(R.color, in.color, 16);
         R.srcW = in.src_w; R.srcH = in.src_h; R.maxSpan = m.maxSpan;
-        if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.count; ctx->anyLit = true; }
+        if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.total; ctx->anyLit = true; }
         if (flags & T3D_DRAW_SKINNED) ctx->anySkinned = true;
         if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) ctx->anyUnbill = true;
         ctx->hVbase.p[ctx->hDraws.size()] = ctx->vAcc;
@@ -687,9 +745,9 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             }
             // the world rotation only feeds a directional light's workingModelRotation of an unskinned, lit draw (light.go:326-330)
             S.rot = NO_ROTATION;
-            if ((flags & T3D_DRAW_LIT) && !(flags & T3D_DRAW_SKINNED) && ll.count) {
+            if ((flags & T3D_DRAW_LIT) && !(flags & T3D_DRAW_SKINNED) && ll.total) {
                 bool sun = false;
-                for (uint32_t k = 0; k < ll.count && !sun; k++) sun = ctx->hLights.p[ll.off + k].type == T3D_LIGHT_DIRECTIONAL;
+                for (uint32_t k = 0; k < ll.total && !sun; k++) sun = ctx->hLights.p[ll.off + k].type == T3D_LIGHT_DIRECTIONAL;
                 if (sun) {
                     S.rot = (uint32_t)(ctx->hRot.n / 16);
                     CU(ctx->hRot.reserve(ctx->hRot.n + 16));

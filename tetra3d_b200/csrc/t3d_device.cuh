@@ -42,7 +42,8 @@ struct LightU {
     float range, range2;    // lightRange, lightRangeSquared
     float fwd[3];           // DirectionalLight.workingForward
     uint32_t volume;        // index into the context's volume table
-    uint32_t pad[2];
+    uint32_t useFirst;      // volume lights: where the LightU records of the lights its cells use start, relative to the draw's first
+    uint32_t pad;
 };
 static const uint32_t LIGHT_SKIP = 0xFFu;
 
@@ -54,6 +55,8 @@ struct VolumeU {
     float offset[3];
     float bias[3];
     const float* cells;
+    const uint32_t* cellLightStart;     // LightVolumeCell.useLights as CSR over the cells, or nullptr
+    const uint32_t* cellLightIndex;     // indices into the volume's use-light run of the draw's LightU list
 };
 
 // One render(rp): host-resolved inputs first, then the fields k_prep_draws derives.
@@ -86,7 +89,7 @@ struct __align__(16) DrawRec {
     uint32_t lightU;            // first LightU slot of this draw
     uint8_t  sortMode, lightingMode, lvMode, pad0;
     uint32_t tstride;           // padded mesh triangle count: plane stride of idx / ctr
-    uint32_t padA;              // keeps the float4-loaded arrays below 16B-aligned
+    uint32_t lightTotal;        // lightCount + the lights the list's LightVolume cells use (their LightU records follow the list's own)
     float transform[16];
     float worldRot[16];
     float color[4];

@@ -344,7 +344,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     } else {
         // The sun's workingModelRotation (light.go:326-330) is per model: parked in worldRot, in place, when the
         // draw's list holds a directional light.
-        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightTotal : 0;      // the lights LightVolume cells use included
         bool haveSun = false;
         for (uint32_t i = 0; i < nL && !haveSun; i++) haveSun = lightsIn[R.lightIn + i].type == T3D_LIGHT_DIRECTIONAL;
         if (haveSun && !skinned) {
@@ -360,7 +360,8 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const DrawRec& R = sR[k];
         const uint32_t flags = R.flags;
         const bool skinned = flags & T3D_DRAW_SKINNED;
-        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightTotal : 0;
+        const uint32_t nOwn = R.lightCount;         // entries beyond are lights that LightVolume cells use (light.go:652-654)
         if (role < nL) {
             const float* o = sInv + invStride * k;
             Mat4 r = m4_identity();
@@ -380,10 +381,10 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
                 U.wpos[0] = U.wpos[1] = U.wpos[2] = 0;
                 U.range = L.range; U.range2 = L.range * L.range;         // light.go:277-280
                 U.fwd[0] = L.forward[0]; U.fwd[1] = L.forward[1]; U.fwd[2] = L.forward[2];
-                U.volume = L.volume; U.pad[0] = U.pad[1] = 0;
+                U.volume = L.volume & 0xFFFu; U.useFirst = L.volume >> 12; U.pad = 0;
                 if (L.type == T3D_LIGHT_POINT) {
                     const Vec3 lp = v3(L.position[0], L.position[1], L.position[2]);
-                    if (L.range > 0) {                                   // camera.go:1625-1629
+                    if (L.range > 0 && i < nOwn) {                       // camera.go:1625-1629: only for the list's own lights
                         const float dist = maxSpan + L.range;
                         if (v3_dist2(modelPos, lp) > dist * dist) U.type = LIGHT_SKIP;
                     }
@@ -408,9 +409,61 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
 // K1: fused skin + transform + light, one vertex per thread
 // ------------------------------------------------------------------------------------------------
 
-// LightVolume.VertexLight (light.go:583-663); rare, kept out of line.
-__device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, const LightU* __restrict__ Up, const VolumeU* __restrict__ vols,
-                                            float px, float py, float pz, float nx, float ny, float nz, bool skinned) {
+// VertexLight of a light that a LightVolume cell uses (light.go:116-120, 191-258, 332-360): the arithmetic of shade_vertex's
+// light loop, from the LightU record k_prep_draws derived for this draw.  Rare, kept out of line.
+__device__ __noinline__ float3 nested_light(const DrawRec* __restrict__ Rp, const LightU* __restrict__ Up, float px, float py, float pz,
+                                            float nx, float ny, float nz, bool skinned, float3 acc) {
+    const DrawRec& R = *Rp;
+    const LightU U = *Up;
+    const uint8_t lightingMode = (R.flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
+    const Vec3 P = v3(px, py, pz), N = v3(nx, ny, nz);
+    const float cR = U.color[0], cG = U.color[1], cB = U.color[2], energy = U.energy;
+    if (U.type == T3D_LIGHT_POINT) {
+        const Vec3 wp = v3(U.wpos[0], U.wpos[1], U.wpos[2]);
+        const float range = U.range, range2 = U.range2;
+        Vec3 vertNormal = N;
+        const float distance = v3_dist2(wp, P);
+        if (range > 0) { if (distance > range2) return acc; }
+        else { if (1.0f / distance * energy < 0.001f) return acc; }
+        const Vec3 lightVec = v3_unit(v3_sub(wp, P));
+        if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) vertNormal = lightVec;
+        float diffuse = v3_dot(vertNormal, lightVec);
+        if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuse = fabsf(diffuse);
+        if (diffuse > 0) {
+            float diffuseFactor = diffuse * (1.0f / (1.0f + (0.1f * distance))) * 2.0f;
+            if (range2 > 0) diffuseFactor *= clampf((range2 - distance) / distance, 0.0f, 1.0f);
+            acc.x += cR * diffuseFactor * energy;
+            acc.y += cG * diffuseFactor * energy;
+            acc.z += cB * diffuseFactor * energy;
+        }
+    } else if (U.type == T3D_LIGHT_DIRECTIONAL) {
+        const Vec3 fwd = v3(U.fwd[0], U.fwd[1], U.fwd[2]);
+        Vec3 normal;
+        if (lightingMode == T3D_LIGHTING_FIXED_NORMALS) normal = fwd;
+        else if (skinned) normal = N;
+        else {                                                          // the draw's workingModelRotation, parked in worldRot by k_prep_draws
+            const float* s = R.worldRot;
+            normal.X = s[0] * N.X + s[4] * N.Y + s[8] * N.Z + s[12];
+            normal.Y = s[1] * N.X + s[5] * N.Y + s[9] * N.Z + s[13];
+            normal.Z = s[2] * N.X + s[6] * N.Y + s[10] * N.Z + s[14];
+        }
+        float diffuseFactor = v3_dot(normal, fwd);
+        if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuseFactor = fabsf(diffuseFactor);
+        if (diffuseFactor <= 0) return acc;
+        acc.x += cR * diffuseFactor * energy;
+        acc.y += cG * diffuseFactor * energy;
+        acc.z += cB * diffuseFactor * energy;
+    } else if (U.type == T3D_LIGHT_AMBIENT) {
+        acc.x += cR * energy; acc.y += cG * energy; acc.z += cB * energy;
+    }
+    return acc;
+}
+
+// LightVolume.VertexLight (light.go:583-663); rare, kept out of line.  `acc` is the vertex's running light sum: the lights the
+// cell uses are added first, then the cell colour.
+__device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, const LightU* __restrict__ Up, const LightU* __restrict__ drawLights,
+                                            const VolumeU* __restrict__ vols,
+                                            float px, float py, float pz, float nx, float ny, float nz, bool skinned, float3 acc) {
     const DrawRec& R = *Rp;
     const LightU U = *Up;
     const Vec3 apos = v3(px, py, pz), anrm = v3(nx, ny, nz);
@@ -435,7 +488,7 @@ __device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, cons
         }
         // Dimensions.Contains on vertPos (mesh.go:82-84) -- zero in WithNormal mode, as in the reference
         if (!(vertPos.X >= V.dimMin[0] && vertPos.Y >= V.dimMin[1] && vertPos.Z >= V.dimMin[2] &&
-              vertPos.X <= V.dimMax[0] && vertPos.Y <= V.dimMax[1] && vertPos.Z <= V.dimMax[2])) return make_float3(0.0f, 0.0f, 0.0f);
+              vertPos.X <= V.dimMax[0] && vertPos.Y <= V.dimMax[1] && vertPos.Z <= V.dimMax[2])) return acc;
         lookup = (mode == T3D_LV_PER_VERTEX_WITH_NORMAL) ? vertPosWithNormal : vertPos;
     }
     // light.go:717-724, 1267-1272
@@ -443,10 +496,18 @@ __device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, cons
     int y = (int)roundf(((lookup.Y - V.offset[1] - V.dimMin[1] - (V.cellSize[1] / 2)) / V.cellSize[1]));
     int z = (int)roundf(((lookup.Z - V.offset[2] - V.dimMin[2] - (V.cellSize[2] / 2)) / V.cellSize[2]));
     if (!(x < 0 || y < 0 || z < 0 || x >= V.cellCount[0] || y >= V.cellCount[1] || z >= V.cellCount[2])) {
-        const float* c = V.cells + 3 * ((size_t)x + ((size_t)y * V.cellCount[0]) + ((size_t)z * V.cellCount[0] * V.cellCount[1]));
+        const size_t cell = (size_t)x + ((size_t)y * V.cellCount[0]) + ((size_t)z * V.cellCount[0] * V.cellCount[1]);
+        const float* c = V.cells + 3 * cell;
         cr = c[0]; cg = c[1]; cb = c[2];
+        if (V.cellLightStart && !(hasMat && mode == T3D_LV_PER_OBJECT)) {      // light.go:652-654 (the per-object branch has no nested lights)
+            const uint32_t k1 = V.cellLightStart[cell + 1];
+            for (uint32_t k = V.cellLightStart[cell]; k < k1; k++)
+                acc = nested_light(Rp, drawLights + U.useFirst + V.cellLightIndex[k], px, py, pz, nx, ny, nz, skinned, acc);
+        }
     }
-    return make_float3(U.color[0] * cr * U.energy, U.color[1] * cg * U.energy, U.color[2] * cb * U.energy);
+    // a vertex outside the volume returned above and adds nothing; inside, x + 0 keeps x (the sums are never -0)
+    acc.x += U.color[0] * cr * U.energy; acc.y += U.color[1] * cg * U.energy; acc.z += U.color[2] * cb * U.energy;
+    return acc;
 }
 
 // Model.skinVertex (model.go:559-596) for one vertex.
@@ -636,9 +697,8 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
         } else if (type == T3D_LIGHT_AMBIENT) {                         // light.go:110-120
             lr += cR * energy; lg += cG * energy; lb += cB * energy;
         } else if (!FAST && type == T3D_LIGHT_VOLUME) {
-            // a vertex outside the volume adds nothing (x + 0 keeps x: the sums are never -0)
-            const float3 add = light_volume(&R, lightsU + R.lightU + li, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned);
-            lr += add.x; lg += add.y; lb += add.z;
+            const float3 acc = light_volume(&R, lightsU + R.lightU + li, lightsU + R.lightU, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned, make_float3(lr, lg, lb));
+            lr = acc.x; lg = acc.y; lb = acc.z;
         }
     }
     lightOut[slot] = make_float4(lr, lg, lb, 1.0f);

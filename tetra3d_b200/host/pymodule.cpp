@@ -188,7 +188,12 @@ PYBIND11_MODULE(_host, m) {
         })
         .def("LightVolumeSetOffset", [](LightVolume& v, float x, float y, float z) { v.offset = t3d::v3(x, y, z); v.generation++; })
         .def("LightVolumeSetLightBias", [](LightVolume& v, float x, float y, float z) { v.lightBias = t3d::v3(x, y, z); v.generation++; })
-        .def_readwrite("HasUseLights", &LightVolume::hasUseLights);
+        // LightVolumeCell.SetUseLights / ClearUseLights of the cell at (x, y, z) (light.go:1508-1518)
+        .def("CellSetUseLights", [](LightVolume& v, int x, int y, int z, py::args lights) {
+            std::vector<std::shared_ptr<ILight>> ls; for (auto l : lights) ls.push_back(l.cast<std::shared_ptr<ILight>>());
+            v.CellSetUseLights(x, y, z, ls);
+        })
+        .def("CellClearUseLights", &LightVolume::CellClearUseLights);
     m.def("NewAmbientLight", [](const std::string& n, float r, float g, float b, float e) { return std::make_shared<AmbientLight>(n, r, g, b, e); });
     m.def("NewPointLight", [](const std::string& n, float r, float g, float b, float e) { return std::make_shared<PointLight>(n, r, g, b, e); });
     m.def("NewDirectionalLight", [](const std::string& n, float r, float g, float b, float e) { return std::make_shared<DirectionalLight>(n, r, g, b, e); });

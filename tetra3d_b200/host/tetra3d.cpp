@@ -271,10 +271,33 @@ void GeometryDevice::ensureMesh(Mesh& m) {
     residentMeshes[m.id] = genKey;
 }
 
+void LightVolume::CellSetUseLights(int x, int y, int z, const std::vector<std::shared_ptr<ILight>>& lights) {   // light.go:1508-1514
+    if (x < 0 || y < 0 || z < 0 || x >= cellCount[0] || y >= cellCount[1] || z >= cellCount[2]) throw T3DError(T3D_E_INVALID, "light volume cell out of range");
+    auto& cell = cellUseLights[(size_t)x + (size_t)y * cellCount[0] + (size_t)z * cellCount[0] * cellCount[1]];
+    for (auto& l : lights) {
+        if (l->Type() == NodeType::LightVolume) throw T3DError(T3D_E_UNSUPPORTED, "a LightVolume used by a LightVolume cell is not evaluated on the device");
+        if (std::find(useLightsRenderSet.begin(), useLightsRenderSet.end(), l) == useLightsRenderSet.end()) useLightsRenderSet.push_back(l);
+        cell.push_back(l);
+    }
+    generation++;
+}
+void LightVolume::CellClearUseLights(int x, int y, int z) {                                                      // light.go:1516-1518
+    cellUseLights.erase((size_t)x + (size_t)y * cellCount[0] + (size_t)z * cellCount[0] * cellCount[1]);
+    generation++;
+}
+
+namespace { t3d_light toLight(GeometryDevice& dev, ILight* l); }
+
 void GeometryDevice::ensureVolume(LightVolume& v) {
-    if (v.hasUseLights) throw T3DError(T3D_E_UNSUPPORTED, "LightVolumeCell.useLights (light.go:652) cannot run on the device");
     if (v.volumeId == 0) v.volumeId = nextVolumeId++;
-    if (v.uploadedGeneration == v.generation) return;
+    if (!v.useLightsRenderSet.empty() && v.useLightsFrame != frameSerial) {
+        // LightVolume.beginRender / beginModel over the render set (light.go:565-580): this frame's world-space records
+        std::vector<t3d_light> recs;
+        for (auto& l : v.useLightsRenderSet) recs.push_back(toLight(*this, l.get()));
+        if (v.uploadedGeneration == v.generation)       // else: submitted below, after the upload
+            check(ctx, t3d_volume_use_lights(ctx, v.volumeId, recs.data(), (uint32_t)recs.size()), "t3d_volume_use_lights");
+    }
+    if (v.uploadedGeneration == v.generation) { v.useLightsFrame = frameSerial; return; }
     t3d_volume_desc d; std::memset(&d, 0, sizeof d);
     d.dim_min[0] = v.dimensions.Min.X; d.dim_min[1] = v.dimensions.Min.Y; d.dim_min[2] = v.dimensions.Min.Z;
     d.dim_max[0] = v.dimensions.Max.X; d.dim_max[1] = v.dimensions.Max.Y; d.dim_max[2] = v.dimensions.Max.Z;
@@ -282,8 +305,28 @@ void GeometryDevice::ensureVolume(LightVolume& v) {
     d.offset[0] = v.offset.X; d.offset[1] = v.offset.Y; d.offset[2] = v.offset.Z;
     d.light_bias[0] = v.lightBias.X; d.light_bias[1] = v.lightBias.Y; d.light_bias[2] = v.lightBias.Z;
     d.cell_colors = v.cellColors.data();
+    std::vector<uint32_t> start, index;
+    if (!v.cellUseLights.empty()) {
+        const size_t cells = (size_t)v.cellCount[0] * v.cellCount[1] * v.cellCount[2];
+        start.assign(cells + 1, 0);
+        for (size_t c = 0; c < cells; c++) {
+            auto it = v.cellUseLights.find(c);
+            if (it != v.cellUseLights.end())
+                for (auto& l : it->second)
+                    index.push_back((uint32_t)(std::find(v.useLightsRenderSet.begin(), v.useLightsRenderSet.end(), l) - v.useLightsRenderSet.begin()));
+            start[c + 1] = (uint32_t)index.size();
+        }
+        if (index.empty()) index.push_back(0);
+        d.cell_light_start = start.data(); d.cell_light_index = index.data();
+    }
     check(ctx, t3d_volume_upload(ctx, v.volumeId, &d), "t3d_volume_upload");
     v.uploadedGeneration = v.generation;
+    if (!v.useLightsRenderSet.empty()) {
+        std::vector<t3d_light> recs;
+        for (auto& l : v.useLightsRenderSet) recs.push_back(toLight(*this, l.get()));
+        check(ctx, t3d_volume_use_lights(ctx, v.volumeId, recs.data(), (uint32_t)recs.size()), "t3d_volume_use_lights");
+    }
+    v.useLightsFrame = frameSerial;
 }
 
 void GeometryDevice::ensureSkeleton(Skeleton& s) {
@@ -725,6 +768,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         tw.fog_color[0] = world->FogColor.R; tw.fog_color[1] = world->FogColor.G; tw.fog_color[2] = world->FogColor.B;
         tw.fog_range[0] = world->FogRange[0]; tw.fog_range[1] = world->FogRange[1];
     }
+    device->frameSerial++;
     check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
 
     // light lists: the scene list once, each active LightGroup once (camera.go:1576-1581)

@@ -163,7 +163,13 @@ struct LightVolume : ILight {
     Vector3 offset{0, 0, 0}, lightBias{0, 0, 0};
     std::vector<float> cellColors;      // 3 * cells
     uint32_t volumeId = 0; uint32_t generation = 1, uploadedGeneration = 0;
-    bool hasUseLights = false;          // LightVolumeCell.useLights (light.go:652): unsupported on the device
+    // LightVolumeCell.useLights (light.go:1381, 1508-1521), keyed by the cell's index x + y*cx + z*cx*cy, in SetUseLights
+    // order; useLightsRenderSet (light.go:392): every light some cell has used, first-added order
+    std::map<size_t, std::vector<std::shared_ptr<ILight>>> cellUseLights;
+    std::vector<std::shared_ptr<ILight>> useLightsRenderSet;
+    uint64_t useLightsFrame = 0;        // GeometryDevice frame the render set was last submitted for
+    void CellSetUseLights(int x, int y, int z, const std::vector<std::shared_ptr<ILight>>& lights);   // LightVolumeCell.SetUseLights
+    void CellClearUseLights(int x, int y, int z);                                                     // LightVolumeCell.ClearUseLights
     NodeType Type() const override { return NodeType::LightVolume; }
 };
 struct LightGroup {
@@ -297,6 +303,7 @@ struct GeometryDevice {
     ~GeometryDevice();
     void ensureMesh(Mesh& m);
     void ensureVolume(LightVolume& v);
+    uint64_t frameSerial = 0;       // bumped by Camera::Render before t3d_frame_begin
     void ensureSkeleton(Skeleton& s);
     // animation tracks reordered to the skeleton's bones (channels find their bone by name, animation.go:618-672): device id
     uint64_t ensureAnimation(Animation& a, Skeleton& s);

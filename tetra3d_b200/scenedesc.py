@@ -113,6 +113,7 @@ class VolumeDesc:
     colors: np.ndarray                 # (cx*cy*cz, 3), index x + y*cx + z*cx*cy
     offset: Sequence[float] = (0.0, 0.0, 0.0)
     light_bias: Sequence[float] = (0.0, 0.0, 0.0)
+    cell_lights: Optional[dict] = None  # (x, y, z) -> [LightDesc, ...]: LightVolumeCell.SetUseLights (light.go:1508-1514)
 
 
 LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL, LIGHT_VOLUME = 0, 1, 2, 3
