@@ -20,7 +20,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import scenes  # noqa: E402
 from oracle import binding as O  # noqa: E402
 
-SCENES = ["soup_lit", "soup_ortho", "skinned", "billboard_locks", "batch_transparent", "volume_mode1", "transparent"]
+SCENES = ["soup_lit", "soup_ortho", "skinned", "billboard_locks", "batch_transparent", "volume_mode1", "transparent",
+          "posed", "volume_cell_lights"]
 
 
 def digest(a: np.ndarray) -> str:
@@ -38,6 +39,6 @@ def record(name):
 
 
 if __name__ == "__main__":
-    for n in SCENES:
+    for n in (sys.argv[1:] or SCENES):
         np.savez_compressed(os.path.join(HERE, n + ".npz"), **record(n))
         print("wrote", n)

@@ -305,6 +305,8 @@ ALL_SMALL = {
     "volume_mode1": lambda: volume_scene(2, 1),
     "volume_mode2": lambda: volume_scene(3, 2),
     "volume_off": lambda: volume_scene(4, 3),
+    "posed": lambda: posed_scene(0),
+    "posed_chain": lambda: posed_scene(3, n_bones=8, chain=True),
     "volume_cell_lights": lambda: volume_cell_lights_scene(5, 0),
     "volume_cell_lights_normal": lambda: volume_cell_lights_scene(6, 1, skinned=True),
     "volume_cell_lights_object": lambda: volume_cell_lights_scene(7, 2),
