@@ -246,8 +246,23 @@ def run_ours(args):
     value = tris_total / (ms_per_step * 1e-3)
 
     # ---- e2e through the public API with host buffers ----
+    before_gather = None
     if world > 1:
+        # the same frames with every rank's lists staying in its own HBM: the geometry stage before the gather
+        # (SURVEY.md 8e asks for both figures; `value` above is the one after delivery to the issuing rank)
         shared[0].release()
+        for _ in range(3):
+            flush_l2(); cam.Clear(); cam.RenderScene(scene)
+        barrier()
+        loc = 0.0
+        for _ in range(args.steps):
+            flush_l2(); cam.Clear(); cam.RenderScene(scene)
+            loc += cam.Timings()["total_ms"]
+        tl = torch.tensor([loc], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        loc_ms = float(tl.item()) / args.steps
+        before_gather = {"value": tris_total / (loc_ms * 1e-3), "unit": UNIT, "ms_per_step": loc_ms,
+                         "note": "every rank's lists stay in its own HBM (no delivery to the issuing rank), max over ranks"}
     cam.DownloadResults = True
     for _ in range(3):
         cam.Clear(); cam.RenderScene(scene)
@@ -332,6 +347,8 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if before_gather is not None:
+        line["before_gather"] = before_gather
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
