@@ -82,6 +82,12 @@ def test_mid_size_draws_skinned_and_culled_parity(device):
     assert_parity(sc, device, check_capture=False)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_volume_cell_lights_fuzz(device, seed):
+    # LightVolumeCell.useLights: random cells with 1-3 lights each, the three shading modes, with and without skinned models
+    assert_parity(scenes.volume_cell_lights_scene(40 + seed, mode=seed % 3, skinned=bool(seed % 2)), device)
+
+
 def test_non_affine_bone_matrices_parity(device):
     # bone matrices normally travel as 12 floats (column 3 is exactly 0,0,0,1); one that is not switches the frame to
     # the full 16-float upload

@@ -36,6 +36,14 @@ def test_posed_scene_parity(device, seed):
     assert_parity(desc, device, check_capture=False)
 
 
+@pytest.mark.parametrize("seed", range(20, 36))
+def test_posed_fuzz(device, seed):
+    # many more random skeletons / animations / playheads: every bone matrix must equal the oracle's bit for bit
+    rng = np.random.default_rng(seed)
+    desc = scenes.posed_scene(seed, n_models=int(rng.integers(2, 12)), n_bones=int(rng.integers(2, 64)), chain=bool(rng.integers(0, 2)))
+    assert_bones_match(desc, device)
+
+
 def test_playheads_on_and_around_keyframes(device):
     # chain_animation has keys every 0.25 s over [0, 2]: on a key, before the first, after the last, between
     desc = scenes.posed_scene(7, n_models=8, n_bones=5, playheads=[0.0, 0.25, 2.0, 2.5, -1.0, 1.0, 0.3333, 1.9999])
