@@ -15,8 +15,7 @@
  *  - Outputs are library-owned buffers, valid until the next t3d_frame_begin on the same context.
  *  - Every function returns T3D_OK (0) or a negative T3D_E_* code; t3d_last_error gives the text.
  *    Nothing aborts.  Features that need host callbacks (Model.VertexTransformFunction model.go:47,
- *    Model.VertexClipFunction model.go:53, Material.CustomDepthFunction material.go:129) and auto-subdivision
- *    (model.go:729-739) cannot run on the device: the shim
+ *    Model.VertexClipFunction model.go:53, Material.CustomDepthFunction material.go:129) cannot run on the device: the shim
  *    must not submit such draws (it keeps the Go path for them) -- there is no CPU fallback in here.
  *  - One context per GPU, single caller at a time (the reference path is single-goroutine, non
  *    re-entrant: tetra3d.go:21-35, sortingTriangles.go:164).
@@ -33,7 +32,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 1
+#define T3D_ABI_VERSION 2      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew */
 
 enum {
     T3D_OK            =  0,
@@ -116,6 +115,16 @@ typedef struct t3d_mesh_desc {
     uint32_t        n_shape_keys;   /* mesh.shapeKeys (mesh.go:796-822)                              */
     const float*    key_positions;  /* k*n*3 */
     const float*    key_normals;    /* k*n*3 */
+    /* Auto-subdivision (Mesh.SetAutoSubdivide mesh.go:447-485, performSubdivision mesh.go:1758-1861), optional (all NULL:
+     * none).  `indices` / `centers` then hold every base triangle followed by its pre-built sub-triangles level by level,
+     * the order MeshPart.forEachTri(true, ...) visits them in (mesh.go:2238-2256); the new vertices sit in the vertex
+     * arrays like any other.  Which of {base, one level} is drawn is decided per draw on the device
+     * (Triangle.handleSubdivision, mesh.go:1877-1959) from the levels of t3d_frame_set_autosubdivision. */
+    const uint32_t* tri_sub_base;   /* t  index of the entry's base triangle (a base triangle names itself)           */
+    const int8_t*   tri_sub_level;  /* t  -1 base triangle, else the level (index into subdivisionLevels)             */
+    const uint8_t*  tri_n_levels;   /* t  len(subdivisionLevels) of a base triangle, 0 = never subdivided             */
+    const float*    tri_max_span;   /* t  Triangle.MaxSpan (mesh.go:2018-2022)                                        */
+    const float*    tri_normal;     /* 3*t Triangle.Normal (mesh.go:2030-2037), read for base triangles               */
 } t3d_mesh_desc;
 
 /* Per-frame camera uniforms (camera.go:1329-1341, 1471-1472, 1603). */
@@ -275,6 +284,10 @@ int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id);
 /* ---- per frame ---------------------------------------------------------------------------------- */
 /* Replaces: the prologue of Camera.Render that fixes vpMatrix / camera constants (camera.go:1329-1341). */
 int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world);
+/* Replaces: the autosubdivisionLevels argument of ProcessVertices (camera.go:1547-1553; scene.library.autosubdivisionLevels,
+ * library.go:206-209): n {DistanceSquared, MaximumTriangleSize} pairs, n <= 8.  Without it (or with n = 0) meshes uploaded
+ * with subdivision data draw their base triangles only. */
+int t3d_frame_set_autosubdivision(t3d_ctx* ctx, const float* levels2, uint32_t n);
 /* Replaces: building sceneLights / LightGroup.Lights (camera.go:1275-1303, 1576-1581).  Returns a
  * light-list handle in *list_id; list 0 is always the empty list. */
 int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id);

@@ -48,7 +48,9 @@ class orc_mesh(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("positions", f32p), ("normals", f32p), ("uvs", f32p), ("colors", f32p),
                 ("active_color_channel", C.c_int32), ("weights", f32p), ("bones", u16p), ("n_influences", u8p),
                 ("n_tris", C.c_int32), ("indices", u32p), ("n_parts", C.c_int32), ("parts", C.POINTER(orc_part)),
-                ("n_shape_keys", C.c_int32), ("key_positions", f32p), ("key_normals", f32p), ("key_weights", f32p)]
+                ("n_shape_keys", C.c_int32), ("key_positions", f32p), ("key_normals", f32p), ("key_weights", f32p),
+                ("auto_subdivide", C.c_int32), ("tri_centers", f32p), ("tri_sub_base", i32p), ("tri_sub_level", C.POINTER(C.c_int8)),
+                ("tri_n_levels", u8p), ("tri_max_span", f32p), ("tri_normal", f32p)]
 
 
 class orc_model(C.Structure):
@@ -93,6 +95,7 @@ class orc_scene(C.Structure):
                 ("n_models", C.c_int32), ("models", C.POINTER(orc_model)), ("n_lights", C.c_int32), ("lights", C.POINTER(orc_light)),
                 ("n_scene_lights", C.c_int32), ("scene_lights", i32p), ("n_light_groups", C.c_int32),
                 ("light_groups", C.POINTER(orc_light_group)), ("n_volumes", C.c_int32), ("volumes", C.POINTER(orc_light_volume)),
+                ("n_subdivision_levels", C.c_int32), ("subdivision_levels", f32p),
                 ("camera", orc_camera), ("world", orc_world)]
 
 
@@ -407,6 +410,11 @@ class _Marshalled:
                 _fill_material(parts[j].material, p.material)
             self.keep.append(parts)
             cm.n_parts = len(md.parts); cm.parts = parts
+            if md.auto_subdivide:
+                cm.auto_subdivide = 1
+                cm.tri_centers = _fp(md.tri_centers); cm.tri_sub_base = md.tri_sub_base.ctypes.data_as(i32p)
+                cm.tri_sub_level = md.tri_sub_level.ctypes.data_as(C.POINTER(C.c_int8)); cm.tri_n_levels = md.tri_n_levels.ctypes.data_as(u8p)
+                cm.tri_max_span = _fp(md.tri_max_span); cm.tri_normal = _fp(md.tri_normal)
             if md.key_weights is not None:
                 cm.n_shape_keys = len(md.key_weights)
                 cm.key_positions = _fp(md.key_positions); cm.key_normals = _fp(md.key_normals); cm.key_weights = _fp(md.key_weights)
@@ -508,6 +516,8 @@ class _Marshalled:
         sc.n_scene_lights = len(scene_light_ids); sc.scene_lights = scene_light_ids.ctypes.data_as(i32p)
         sc.n_light_groups = len(groups); sc.light_groups = c_groups
         sc.n_volumes = len(volumes); sc.volumes = c_volumes
+        lv = np.ascontiguousarray(np.asarray(list(desc.autosubdivision_levels), np.float32).reshape(-1, 2)); self.keep.append(lv)
+        sc.n_subdivision_levels = len(lv); sc.subdivision_levels = _fp(lv) if len(lv) else None
         cd = desc.camera
         sc.camera.node = cam_node; sc.camera.width = int(cd.width); sc.camera.height = int(cd.height)
         sc.camera.field_of_view = float(cd.field_of_view); sc.camera.near_plane = float(cd.near); sc.camera.far_plane = float(cd.far)

@@ -610,6 +610,66 @@ static void skin_vertex(const orc_mesh* mesh, const orc_model* model, int vertID
 }
 
 /* model.go:600-995; returns min/max depth through pointers. */
+/* colliderTriangles.go:177-182, 206-281: closestPointOnTri and its helpers */
+static vec3 plane_closest_point(vec3 normal, float distance, vec3 point) {
+    float dist = v3_dot(normal, point) - distance;
+    return v3_sub(point, v3(normal.X * dist, normal.Y * dist, normal.Z * dist));
+}
+static vec3 closest_point_on_line(vec3 point, vec3 start, vec3 end) {
+    vec3 diff = v3_sub(end, start);
+    float dotA = v3_dot(v3_sub(point, start), diff);
+    float dotB = v3_dot(diff, diff);
+    float d = dotA / dotB;
+    if (d > 1) d = 1; else if (d < 0) d = 0;
+    return v3_add(start, v3(diff.X * d, diff.Y * d, diff.Z * d));
+}
+static int point_inside_triangle(vec3 point, vec3 v0, vec3 v1, vec3 v2) {
+    vec3 ca = v3_sub(v2, v0), ba = v3_sub(v1, v0), pa = v3_sub(point, v0);
+    float dot00 = v3_dot(ca, ca), dot01 = v3_dot(ca, ba), dot02 = v3_dot(ca, pa), dot11 = v3_dot(ba, ba), dot12 = v3_dot(ba, pa);
+    float invDenom = 1.0f / ((dot00 * dot11) - (dot01 * dot01));
+    float u = ((dot11 * dot02) - (dot01 * dot12)) * invDenom;
+    float v = ((dot00 * dot12) - (dot01 * dot02)) * invDenom;
+    return (u >= 0) && (v >= 0) && (u + v < 1);
+}
+static vec3 closest_point_on_tri(vec3 point, vec3 v0, vec3 v1, vec3 v2, vec3 normal) {
+    float distance = v3_dot(normal, v0);
+    vec3 planePoint = plane_closest_point(normal, distance, point);
+    if (point_inside_triangle(planePoint, v0, v1, v2)) return planePoint;
+    vec3 ab = closest_point_on_line(point, v0, v1), bc = closest_point_on_line(point, v1, v2), ca = closest_point_on_line(point, v2, v0);
+    vec3 closest = ab;
+    float closestDist = v3_dist2(point, ab);
+    float bcDist = v3_dist2(point, bc), caDist = v3_dist2(point, ca);
+    if (bcDist < closestDist) { closest = bc; closestDist = bcDist; }
+    if (caDist < closestDist) closest = ca;
+    return closest;
+}
+
+/* Triangle.handleSubdivision (mesh.go:1877-1959) for base triangle `ti`: which of {the base, one of its levels} is visible.
+ * Returns -1 = the base triangle itself, else the index of the visible level. */
+static int subdivision_choice(const orc_scene* sc, const orc_mesh* mesh, int ti, vec3 cameraPos) {
+    const int nLevels = mesh->tri_n_levels[ti];
+    if (nLevels == 0) return -1;
+    const uint32_t* tri = mesh->indices + 3 * (size_t)ti;
+    const float* P = mesh->positions;
+    vec3 v0 = v3(P[3 * tri[0]], P[3 * tri[0] + 1], P[3 * tri[0] + 2]);
+    vec3 v1 = v3(P[3 * tri[1]], P[3 * tri[1] + 1], P[3 * tri[1] + 2]);
+    vec3 v2 = v3(P[3 * tri[2]], P[3 * tri[2] + 1], P[3 * tri[2] + 2]);
+    vec3 nrm = v3(mesh->tri_normal[3 * ti], mesh->tri_normal[3 * ti + 1], mesh->tri_normal[3 * ti + 2]);
+    float dist = v3_dist2(cameraPos, closest_point_on_tri(cameraPos, v0, v1, v2, nrm));
+    int active = -1;
+    float closestDistance = FLT_MAX;
+    for (int i = 0; i < sc->n_subdivision_levels; i++) {
+        float d2 = sc->subdivision_levels[2 * i];
+        if (dist < d2 && d2 < closestDistance) { closestDistance = d2; active = i; }
+    }
+    if (active == -1) return -1;
+    float ms = mesh->tri_max_span[ti];
+    int subIndex = -1;
+    while (ms > sc->subdivision_levels[2 * active + 1]) { ms /= 2; subIndex++; }
+    if (subIndex >= nLevels) subIndex = nLevels - 1;
+    return subIndex;
+}
+
 static void process_vertices(rstate* S, int mi, int pi, float* outMin, float* outMax) {
     const orc_scene* sc = S->sc;
     const orc_model* model = &sc->models[mi];
@@ -682,9 +742,19 @@ static void process_vertices(rstate* S, int mi, int pi, float* outMin, float* ou
     const int renderNormals = camera->render_normals;
     const float* centers = S->centers[model->mesh];
 
+    int subChoice = -1;                                      /* of the base triangle the loop is in (model.go:726-739) */
     for (int ti = part->triangle_start; ti <= part->triangle_end; ti++) {   /* forEachTri, mesh.go:2238-2256 */
         const uint32_t* tri = mesh->indices + 3 * (size_t)ti;
         vec3 vert, normal;
+
+        if (mesh->auto_subdivide) {
+            /* Triangle.visible as handleSubdivision leaves it (mesh.go:1877-1959).  Skinned models skip that block
+             * (model.go:726) and see whatever the last static draw of the mesh left: the contract is base triangles only,
+             * as with an empty level list (disableSubdivision). */
+            const int level = mesh->tri_sub_level[ti];
+            if (level < 0) subChoice = (!modelSkinned && sc->n_subdivision_levels > 0) ? subdivision_choice(sc, mesh, ti, invertedCamPos) : -1;
+            if (level != subChoice) continue;                /* model.go:753-755 */
+        }
 
         for (int vi = 0; vi < 3; vi++) {                     /* model.go:757-822 */
             int vertexIndex = (int)tri[vi];
@@ -1309,7 +1379,8 @@ int orc_render_scene(const orc_scene* sc, int capture, orc_result** out) {
         if (m->n_verts > maxVerts) maxVerts = m->n_verts;
         if (m->n_tris > maxTris) maxTris = m->n_tris;
         S.centers[i] = malloc((size_t)(m->n_tris > 0 ? m->n_tris : 1) * 12);
-        orc_triangle_centers(m->positions, m->indices, m->n_tris, S.centers[i]);
+        if (m->auto_subdivide && m->tri_centers) memcpy(S.centers[i], m->tri_centers, (size_t)m->n_tris * 12);
+        else orc_triangle_centers(m->positions, m->indices, m->n_tris, S.centers[i]);
         S.dims[i] = mesh_dimensions(m);
     }
     S.vertexTransforms = calloc((size_t)maxVerts, sizeof(vec4));

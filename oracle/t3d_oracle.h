@@ -96,6 +96,16 @@ typedef struct {
     const float* key_positions;     /* k*n*3 */
     const float* key_normals;       /* k*n*3 */
     const float* key_weights;       /* k */
+    /* Auto-subdivision (mesh.go:447-485, 1758-1959).  When auto_subdivide is set, `indices` hold every base triangle
+     * followed by its pre-built sub-triangles, level by level: the order MeshPart.forEachTri(true, ...) visits them in
+     * (mesh.go:2238-2256), and the arrays below describe every entry. */
+    int32_t auto_subdivide;
+    const float*   tri_centers;     /* 3*t Triangle.Center (sub-triangles: mesh.go:1828-1830), overrides RecalculateCenter */
+    const int32_t* tri_sub_base;    /* t: the base triangle's index (a base triangle names itself) */
+    const int8_t*  tri_sub_level;   /* t: -1 = base triangle, else its level in the base's subdivisionLevels */
+    const uint8_t* tri_n_levels;    /* t: len(subdivisionLevels) of a base triangle */
+    const float*   tri_max_span;    /* t: Triangle.MaxSpan */
+    const float*   tri_normal;      /* 3*t: Triangle.Normal (base triangles) */
 } orc_mesh;
 
 /* Model (model.go:20-61). */
@@ -183,6 +193,7 @@ typedef struct {
     int32_t n_scene_lights; const int32_t* scene_lights;    /* the subset that is in the tree under root */
     int32_t n_light_groups; const orc_light_group* light_groups;
     int32_t n_volumes;      const orc_light_volume* volumes;
+    int32_t n_subdivision_levels; const float* subdivision_levels;   /* scene.library.autosubdivisionLevels: {DistanceSquared, MaximumTriangleSize} pairs */
     orc_camera camera;
     orc_world  world;
 } orc_scene;

@@ -21,7 +21,7 @@ import scenes  # noqa: E402
 from oracle import binding as O  # noqa: E402
 
 SCENES = ["soup_lit", "soup_ortho", "skinned", "billboard_locks", "batch_transparent", "volume_mode1", "transparent",
-          "posed", "volume_cell_lights"]
+          "posed", "volume_cell_lights", "subdivision"]
 
 
 def digest(a: np.ndarray) -> str:

@@ -238,6 +238,28 @@ def volume_cell_lights_scene(seed=0, mode=0, skinned=False) -> SceneDesc:
     return sc
 
 
+def subdivision_scene(seed=0, with_levels=True) -> SceneDesc:
+    """Auto-subdivision (mesh.go:447-485, 1758-1959): meshes with pre-built subdivision levels at several distances from the
+    camera, so that base triangles, level 0, 1 and 2 are all chosen somewhere; sizes that land in the packed, the one-block and
+    the segmented cull paths; two MeshParts; vertex colours; next to an ordinary mesh."""
+    from tetra3d_b200.scenedesc import auto_subdivide
+    rng = np.random.default_rng(700 + seed)
+    levels = [(900.0, 2.5), (225.0, 1.2), (49.0, 0.5)]
+    cube = auto_subdivide(W.cube_mesh(2, 2, 2, material=MaterialDesc(backface_culling=True, triangle_sort_mode=seed % 3)), levels, 3)
+    soup = auto_subdivide(random_soup(60, seed, n_parts=2, colors=True, extent=4.0, material=MaterialDesc(backface_culling=False)), levels, 2)
+    grid = auto_subdivide(W.grid_mesh(24, 16, rows_per_part=8, seed=seed, material=MaterialDesc(backface_culling=True)), levels, 2)
+    models = []
+    for i, z in enumerate([6.0, 2.0, -4.0, -12.0, -30.0]):
+        models.append(ModelDesc(cube, NodeDesc(position=(float(rng.uniform(-3, 3)), float(rng.uniform(-1, 1)), z), rotation=random_rotation(rng)), name="cube%d" % i))
+    models.append(ModelDesc(soup, NodeDesc(position=(1.0, 0.5, 0.0), scale=(1.2, 0.8, 1.0), rotation=random_rotation(rng)), name="soup"))
+    models.append(ModelDesc(grid, NodeDesc(position=(0.0, -2.0, -5.0), scale=(0.6, 1.0, 0.6)), frustum_culling=False, name="grid"))
+    big = auto_subdivide(W.grid_mesh(24, 16, rows_per_part=16, seed=seed + 2, material=MaterialDesc(backface_culling=False, triangle_sort_mode=1)), levels, 2)
+    models.append(ModelDesc(big, NodeDesc(position=(0.0, 3.0, -8.0), scale=(0.5, 1.0, 0.5), rotation=W.rotation_matrix((1, 0, 0), 0.4)), frustum_culling=False, name="grid_big"))
+    models.append(ModelDesc(random_soup(200, seed + 1, n_parts=1), NodeDesc(position=(-2.0, 1.0, 1.0)), name="plain"))
+    return SceneDesc(models, lights_mixed(rng, ranged=True), CameraDesc(node=NodeDesc(position=(0.0, 1.0, 10.0))), WorldDesc(ambient_energy=0.2),
+                     name="subdivision", autosubdivision_levels=levels if with_levels else ())
+
+
 def transparent_scene(seed=0) -> SceneDesc:
     rng = np.random.default_rng(seed)
     models = []
@@ -305,6 +327,8 @@ ALL_SMALL = {
     "volume_mode1": lambda: volume_scene(2, 1),
     "volume_mode2": lambda: volume_scene(3, 2),
     "volume_off": lambda: volume_scene(4, 3),
+    "subdivision": lambda: subdivision_scene(0),
+    "subdivision_no_levels": lambda: subdivision_scene(1, with_levels=False),
     "posed": lambda: posed_scene(0),
     "posed_chain": lambda: posed_scene(3, n_bones=8, chain=True),
     "volume_cell_lights": lambda: volume_cell_lights_scene(5, 0),

@@ -19,7 +19,9 @@ class MeshDesc(C.Structure):
     _fields_ = [("n_verts", C.c_uint32), ("positions", f32p), ("normals", f32p), ("uvs", f32p), ("colors", f32p), ("weights", f32p),
                 ("bones", C.POINTER(C.c_uint16)), ("n_influences", C.POINTER(C.c_uint8)), ("n_tris", C.c_uint32),
                 ("indices", C.POINTER(C.c_uint32)), ("centers", f32p), ("n_parts", C.c_uint32), ("parts", C.POINTER(PartRange)),
-                ("max_span", C.c_float), ("n_shape_keys", C.c_uint32), ("key_positions", f32p), ("key_normals", f32p)]
+                ("max_span", C.c_float), ("n_shape_keys", C.c_uint32), ("key_positions", f32p), ("key_normals", f32p),
+                ("tri_sub_base", C.POINTER(C.c_uint32)), ("tri_sub_level", C.POINTER(C.c_int8)), ("tri_n_levels", C.POINTER(C.c_uint8)),
+                ("tri_max_span", f32p), ("tri_normal", f32p)]
 
 
 class Camera(C.Structure):

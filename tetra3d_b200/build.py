@@ -49,6 +49,8 @@ def build_mesh(md: MeshDesc):
     for p in md.parts:
         mesh.AddMeshPart(_material(p.material), int(p.vertex_start), int(p.vertex_end), int(p.tri_start), int(p.tri_end))
     mesh.UpdateDimensions()
+    if md.auto_subdivide:
+        mesh.SetAutoSubdivision(md.tri_centers, np.asarray(md.tri_sub_base, np.uint32), md.tri_sub_level, md.tri_n_levels, md.tri_max_span, md.tri_normal)
     return mesh
 
 
@@ -66,6 +68,8 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
     the order the description lists them.  A NodeDesc used as `parent` becomes a plain Node.
     """
     scene = t3d.NewScene(desc.name)
+    if len(desc.autosubdivision_levels):
+        scene.SetAutoSubdivisionLevels(np.asarray(list(desc.autosubdivision_levels), np.float32).reshape(-1))
     objs: Dict[int, object] = {}
     meshes: Dict[int, object] = {}
     group_nodes: Dict[int, object] = {}

@@ -86,9 +86,10 @@ struct Mesh {
     float *pos = nullptr, *nrm = nullptr, *uv = nullptr, *col = nullptr, *wgt = nullptr, *ctr = nullptr;
     float *keyPos = nullptr, *keyNrm = nullptr, *keyW = nullptr;
     uint16_t* jnt = nullptr; uint8_t* ninf = nullptr; uint32_t* idx = nullptr;
+    void* subdivBlock = nullptr; SubdivMesh* subdiv = nullptr;      // auto-subdivision arrays + the record DrawRec.subdiv points at
     std::vector<PartInfo> parts;
     void release() {
-        void* ptrs[] = {pos, nrm, uv, col, wgt, ctr, keyPos, keyNrm, keyW, jnt, ninf, idx};
+        void* ptrs[] = {pos, nrm, uv, col, wgt, ctr, keyPos, keyNrm, keyW, jnt, ninf, idx, subdivBlock};
         for (void* q : ptrs) if (q) cudaFree(q);
         *this = Mesh();
     }
@@ -137,7 +138,7 @@ struct t3d_ctx {
     std::vector<uint32_t> drawTotalTris;
     std::vector<uint8_t> drawContinue;
     uint32_t vAcc = 0, tAcc = 0, luAcc = 0, nHistRows = 0;
-    bool anyLit = false, anySkinned = false, anyUnbill = false, bonesAffine = true, transformsAffine = true;
+    bool anyLit = false, anySkinned = false, anyUnbill = false, anySubdiv = false, bonesAffine = true, transformsAffine = true;
 
     // device arenas
     DevBuf dFrame, dLightsU, dStats;            // dFrame: all per-frame uniforms, packed, uploaded with one copy
@@ -318,6 +319,31 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
         CU(cudaMemcpy(m.keyNrm, kn.data(), kn.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(m.keyW, 0, (size_t)m.nKeys * sizeof(float), s));
     }
+    if (d->tri_sub_base || d->tri_sub_level || d->tri_n_levels || d->tri_max_span || d->tri_normal) {
+        if (!(d->tri_sub_base && d->tri_sub_level && d->tri_n_levels && d->tri_max_span && d->tri_normal)) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: auto-subdivision needs all five tri_* arrays"); }
+        if (d->weights) { m.release(); return fail(ctx, T3D_E_UNSUPPORTED, "t3d_mesh_upload: auto-subdivision of a skinned mesh (model.go:726 skips it)"); }
+        const size_t t = d->n_tris;
+        for (size_t i = 0; i < t; i++)
+            if (d->tri_sub_base[i] >= t || d->tri_sub_level[i] < -1 || d->tri_sub_base[i] > i) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: tri_sub_base / tri_sub_level out of range"); }
+        // one block: [SubdivMesh | base 4t | span 4t | normal 12t | level t | nLevels t]
+        const size_t off0 = 64, bytes = off0 + t * (4 + 4 + 12 + 1 + 1);
+        std::vector<uint8_t> h(bytes, 0);
+        memcpy(h.data() + off0, d->tri_sub_base, 4 * t);
+        memcpy(h.data() + off0 + 4 * t, d->tri_max_span, 4 * t);
+        memcpy(h.data() + off0 + 8 * t, d->tri_normal, 12 * t);
+        memcpy(h.data() + off0 + 20 * t, d->tri_sub_level, t);
+        memcpy(h.data() + off0 + 21 * t, d->tri_n_levels, t);
+        CU(cudaMalloc(&m.subdivBlock, bytes));
+        uint8_t* b = static_cast<uint8_t*>(m.subdivBlock);
+        SubdivMesh sm;
+        sm.base = reinterpret_cast<const uint32_t*>(b + off0); sm.span = reinterpret_cast<const float*>(b + off0 + 4 * t);
+        sm.normal = reinterpret_cast<const float*>(b + off0 + 8 * t); sm.level = reinterpret_cast<const int8_t*>(b + off0 + 20 * t);
+        sm.nLevels = b + off0 + 21 * t;
+        memcpy(h.data(), &sm, sizeof sm);
+        static_assert(sizeof(SubdivMesh) <= 64, "SubdivMesh header");
+        CU(cudaMemcpy(m.subdivBlock, h.data(), bytes, cudaMemcpyHostToDevice));
+        m.subdiv = reinterpret_cast<SubdivMesh*>(m.subdivBlock);
+    }
     m.parts.resize(d->n_parts);
     for (uint32_t p = 0; p < d->n_parts; p++) {
         const t3d_part_range& pr = d->parts[p];
@@ -460,13 +486,24 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->lightLists.push_back(LightList{0, 0, 0});     // list 0: empty
     ctx->drawTotalTris.clear(); ctx->drawContinue.clear();
     ctx->vAcc = ctx->tAcc = ctx->luAcc = 0;
-    ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = false;
+    ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = ctx->anySubdiv = false;
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->tmplSpanMax = 1;
     ctx->hPoses.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
     for (auto& u : ctx->volumeUse) u.clear();
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
+    return T3D_OK;
+}
+
+int t3d_frame_set_autosubdivision(t3d_ctx* ctx, const float* levels2, uint32_t n) {
+    if (!ctx || (n && !levels2)) return fail(ctx, T3D_E_INVALID, "t3d_frame_set_autosubdivision: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_set_autosubdivision: not between frame_begin and frame_execute");
+    if (n > 8) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_set_autosubdivision: more than 8 levels");
+    for (uint32_t i = 0; i < n; i++)
+        if (!(levels2[2 * i + 1] > 0.0f)) return fail(ctx, T3D_E_INVALID, "t3d_frame_set_autosubdivision: MaximumTriangleSize must be positive");
+    ctx->fc.nSubLevels = n;
+    for (uint32_t i = 0; i < n; i++) { ctx->fc.subLevels[i][0] = levels2[2 * i]; ctx->fc.subLevels[i][1] = levels2[2 * i + 1]; }
     return T3D_OK;
 }
 
@@ -694,7 +731,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         DrawRec R;
         memset(&R, 0, sizeof R);
         R.pos = m.pos; R.nrm = m.nrm; R.uv = m.uv; R.col = m.col; R.wgt = m.wgt; R.jnt = m.jnt; R.ninf = m.ninf;
-        R.idx = m.idx; R.ctr = m.ctr; R.keyPos = m.keyPos; R.keyNrm = m.keyNrm; R.keyW = m.keyW;
+        R.idx = m.idx; R.ctr = m.ctr; R.keyPos = m.keyPos; R.keyNrm = m.keyNrm; R.keyW = m.keyW; R.subdiv = m.subdiv;
         R.a0 = pi.a0; R.nv = pi.nv; R.vbase = ctx->vAcc;
         R.t0 = pi.triStart; R.nt = pi.triEnd - pi.triStart; R.tbase = ctx->tAcc;
         R.flags = flags; R.nKeys = m.nKeys; R.vstride = m.nVertsPad; R.tstride = m.nTrisPad;
@@ -710,6 +747,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.total; ctx->anyLit = true; }
         if (flags & T3D_DRAW_SKINNED) ctx->anySkinned = true;
         if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) ctx->anyUnbill = true;
+        if (m.subdiv) ctx->anySubdiv = true;
         ctx->hVbase.p[ctx->hDraws.size()] = ctx->vAcc;
         ctx->hTbase.p[ctx->hDraws.size()] = ctx->tAcc;
         ctx->vAcc += pi.nv; ctx->tAcc += R.nt;
@@ -1093,11 +1131,11 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(mark(3));
     // K2: cull (small draws are also sorted here)
     launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
-                      ctx->dTdepth.as<uint32_t>(), stats);
+                      ctx->dTdepth.as<uint32_t>(), stats, ctx->anySubdiv);
     launch_tile_packed(s, pdl, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
-                       ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats);
+                       ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats, ctx->anySubdiv);
     launch_draw_medium(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pMedium, nMedium, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
-                       ctx->dSorted.as<uint32_t>(), stats);
+                       ctx->dSorted.as<uint32_t>(), stats, ctx->anySubdiv);
     ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0) + (nMedium ? 1 : 0);
     CU(mark(4));
     // K3: where every tile starts in the lists (needs only the survivor counts), then the segmented 512-bin

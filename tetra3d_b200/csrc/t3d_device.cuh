@@ -30,6 +30,9 @@ struct FrameConst {
     int32_t worldPresent, fogOn, fogMode;
     float fogColor[3];
     float fogRange[2];
+    // scene.library.autosubdivisionLevels (library.go:206-209): {DistanceSquared, MaximumTriangleSize}
+    uint32_t nSubLevels;
+    float subLevels[8][2];
 };
 
 // Resolved light as seen by one draw: light.beginRender/beginModel products (light.go:110-112,
@@ -59,6 +62,15 @@ struct VolumeU {
     const uint32_t* cellLightIndex;     // indices into the volume's use-light run of the draw's LightU list
 };
 
+// Auto-subdivision data of a mesh (t3d_mesh_desc.tri_*), one record per mesh in device memory.
+struct SubdivMesh {
+    const uint32_t* base;       // per triangle entry: its base triangle
+    const int8_t*   level;      // -1 base, else level
+    const uint8_t*  nLevels;    // base triangles: number of pre-built levels
+    const float*    span;       // Triangle.MaxSpan
+    const float*    normal;     // packed float3 Triangle.Normal
+};
+
 // One render(rp): host-resolved inputs first, then the fields k_prep_draws derives.
 struct __align__(16) DrawRec {
     // ---- resolved by the host at submit ----
@@ -74,6 +86,8 @@ struct __align__(16) DrawRec {
     const float*    keyPos;     // k keys x 3 planes x vstride
     const float*    keyNrm;
     const float*    keyW;       // k
+    const SubdivMesh* subdiv;   // auto-subdivision data of the mesh, or nullptr
+    uint64_t        padP;       // keeps the float4-loaded arrays below 16B-aligned
     uint32_t a0;                // first mesh vertex of the aligned range (multiple of 4)
     uint32_t nv;                // aligned vertex count (multiple of 4)
     uint32_t vbase;             // first slot in the per-frame vertex arenas (multiple of 4)

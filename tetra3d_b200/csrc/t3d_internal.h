@@ -36,12 +36,12 @@ void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
-                       const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats);
+                       const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats, bool subdiv);
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
-                        const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats);
+                        const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats, bool subdiv);
 void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* mediumList, uint32_t nMedium,
-                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats);
+                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats, bool subdiv);
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,

@@ -815,6 +815,72 @@ __device__ __forceinline__ bool cull_keep(const float4 c0, const float4 c1, cons
     return keep;
 }
 
+// ---- auto-subdivision (mesh.go:1877-1959): is triangle entry `mt` the one drawn for its base triangle? ----------------
+// closestPointOnTri and its helpers: colliderTriangles.go:177-182, 206-281
+__device__ __forceinline__ Vec3 closest_point_on_line(Vec3 point, Vec3 start, Vec3 end) {
+    const Vec3 diff = v3_sub(end, start);
+    const float dotA = v3_dot(v3_sub(point, start), diff);
+    const float dotB = v3_dot(diff, diff);
+    float d = dotA / dotB;
+    if (d > 1.0f) d = 1.0f; else if (d < 0.0f) d = 0.0f;
+    return v3_add(start, v3(diff.X * d, diff.Y * d, diff.Z * d));
+}
+__device__ __forceinline__ Vec3 closest_point_on_tri(Vec3 point, Vec3 v0, Vec3 v1, Vec3 v2, Vec3 normal) {
+    const float distance = v3_dot(normal, v0);
+    const float dist = v3_dot(normal, point) - distance;                       // collisionPlane.ClosestPoint
+    const Vec3 planePoint = v3_sub(point, v3(normal.X * dist, normal.Y * dist, normal.Z * dist));
+    {   // pointInsideTriangle
+        const Vec3 ca = v3_sub(v2, v0), ba = v3_sub(v1, v0), pa = v3_sub(planePoint, v0);
+        const float dot00 = v3_dot(ca, ca), dot01 = v3_dot(ca, ba), dot02 = v3_dot(ca, pa), dot11 = v3_dot(ba, ba), dot12 = v3_dot(ba, pa);
+        const float invDenom = 1.0f / ((dot00 * dot11) - (dot01 * dot01));
+        const float u = ((dot11 * dot02) - (dot01 * dot12)) * invDenom;
+        const float v = ((dot00 * dot12) - (dot01 * dot02)) * invDenom;
+        if ((u >= 0.0f) && (v >= 0.0f) && (u + v < 1.0f)) return planePoint;
+    }
+    const Vec3 ab = closest_point_on_line(point, v0, v1), bc = closest_point_on_line(point, v1, v2), ca = closest_point_on_line(point, v2, v0);
+    Vec3 closest = ab;
+    float closestDist = v3_dist2(point, ab);
+    const float bcDist = v3_dist2(point, bc), caDist = v3_dist2(point, ca);
+    if (bcDist < closestDist) { closest = bc; closestDist = bcDist; }
+    if (caDist < closestDist) closest = ca;
+    return closest;
+}
+// Triangle.handleSubdivision for the entry's base triangle, then Triangle.visible of the entry itself (model.go:753-755).
+// Skinned draws and frames without levels draw base triangles only.  Rare, kept out of line.
+__device__ __noinline__ bool subdiv_visible(const DrawRec* __restrict__ Rp, const FrameConst* __restrict__ fc, uint32_t mt) {
+    const DrawRec& R = *Rp;
+    const SubdivMesh S = *R.subdiv;
+    const int level = S.level[mt];
+    const uint32_t bt = S.base[mt];
+    const int nLevels = S.nLevels[bt];
+    int choice = -1;
+    if (!(R.flags & T3D_DRAW_SKINNED) && fc->nSubLevels > 0 && nLevels > 0) {
+        const uint32_t ts = R.tstride, vs = R.vstride;
+        const uint32_t a = R.idx[bt], b = R.idx[ts + bt], c = R.idx[2 * (size_t)ts + bt];
+        const Vec3 v0 = v3(R.pos[a], R.pos[vs + a], R.pos[2 * (size_t)vs + a]);
+        const Vec3 v1 = v3(R.pos[b], R.pos[vs + b], R.pos[2 * (size_t)vs + b]);
+        const Vec3 v2 = v3(R.pos[c], R.pos[vs + c], R.pos[2 * (size_t)vs + c]);
+        const Vec3 nrm = v3(S.normal[3 * (size_t)bt], S.normal[3 * (size_t)bt + 1], S.normal[3 * (size_t)bt + 2]);
+        const Vec3 cam = v3(R.invCam[0], R.invCam[1], R.invCam[2]);
+        const float dist = v3_dist2(cam, closest_point_on_tri(cam, v0, v1, v2, nrm));
+        int active = -1;
+        float closestDistance = FLT_MAX;
+        for (uint32_t i = 0; i < fc->nSubLevels; i++) {
+            const float d2 = fc->subLevels[i][0];
+            if (dist < d2 && d2 < closestDistance) { closestDistance = d2; active = (int)i; }
+        }
+        if (active >= 0) {
+            float ms = S.span[bt];
+            int subIndex = -1;
+            const float maxSize = fc->subLevels[active][1];
+            while (ms > maxSize) { ms /= 2.0f; subIndex++; }
+            if (subIndex >= nLevels) subIndex = nLevels - 1;
+            choice = subIndex;
+        }
+    }
+    return level == choice;
+}
+
 // Depth of a skinned triangle: distance from the camera to the mean of its skinned corners (model.go:840-864, 941-946).
 __device__ __forceinline__ float skinned_depth(const float4 p0, const float4 p1, const float4 p2, const float* camPos) {
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
@@ -834,6 +900,7 @@ static const int TILE_ROUNDS = TILE_TRIS / TILE_THREADS;        // triangles per
 #ifndef T3D_CULL_MINBLOCKS
 #define T3D_CULL_MINBLOCKS 5
 #endif
+template <bool SUBDIV>      // SUBDIV: the frame holds auto-subdivided meshes (mesh.go:1877-1959); the other instantiation carries none of it
 __global__ void __launch_bounds__(TILE_THREADS, T3D_CULL_MINBLOCKS)
 k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ largeList,
              const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float4* __restrict__ wpos,
@@ -871,6 +938,7 @@ k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tile
         if (i < T.count) {
             const float4 c0 = __ldg(&clip[vb + ia[r]]), c1 = __ldg(&clip[vb + ib[r]]), c2 = __ldg(&clip[vb + ic[r]]);
             bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+            if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt0 + i);       // model.go:753-755
             float depth = 0.0f;
             if (keep) {                                                 // model.go:933-955
                 if (skinned) depth = skinned_depth(__ldg(&wpos[vb + ia[r]]), __ldg(&wpos[vb + ib[r]]), __ldg(&wpos[vb + ic[r]]), fc.camPos);
@@ -978,6 +1046,7 @@ __device__ __forceinline__ void smem_radix_pass(const uint32_t* __restrict__ in,
 //   draw-in-tile (10 bits) << 20 | bin rank (10) << 10 | slot-in-tile (10)
 // through two stable counting-sort passes (bin rank, then draw; the second is skipped for a one-draw tile) and
 // come out in (draw, bin, arrival) order -- the order sortingTriangleBucket.ForEach visits them in.
+template <bool SUBDIV>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tbase, const TriTile* __restrict__ tiles,
               const uint32_t* __restrict__ packedList, const __grid_constant__ FrameConst fc,
@@ -1028,6 +1097,7 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
             const uint32_t i0 = __ldg(R.idx + mt), i1 = __ldg(R.idx + ts + mt), i2 = __ldg(R.idx + 2 * (size_t)ts + mt);
             const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
             keep = cull_keep(c0, c1, c2, (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING), fc.nearP, fc.farP);
+            if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt);
             if (keep) {
                 float depth;
                 if (flags & T3D_DRAW_SKINNED) depth = skinned_depth(__ldg(&wpos[vb + i0]), __ldg(&wpos[vb + i1]), __ldg(&wpos[vb + i2]), fc.camPos);
@@ -1099,6 +1169,7 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
 // warp-contiguous ranking as smem_radix_pass) and store sorted[tbase + bin start + rank] = arena slot.
 // No depth array, histogram rows or atomics in global memory.  The draw's tiles stay in the tile table as
 // "large" tiles for the tile scan and the emit.
+template <bool SUBDIV>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_draw_medium(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ mediumList,
               const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float4* __restrict__ wpos,
@@ -1131,6 +1202,7 @@ k_draw_medium(const DrawRec* __restrict__ draws, const TriTile* __restrict__ til
         const uint32_t i0 = __ldg(ip + i), i1 = __ldg(ip + ts + i), i2 = __ldg(ip + 2 * (size_t)ts + i);
         const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
         bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+        if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, R.t0 + i);
         float depth = 0.0f;
         if (keep) {                                                     // model.go:933-955
             if (skinned) depth = skinned_depth(__ldg(&wpos[vb + i0]), __ldg(&wpos[vb + i1]), __ldg(&wpos[vb + i2]), fc.camPos);
@@ -1453,22 +1525,25 @@ void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_
 }
 
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
-                       const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats) {
+                       const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats, bool subdiv) {
     if (!nLarge) return;
-    launch_kernel(k_cull_large, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
+    if (subdiv) launch_kernel(k_cull_large<true>, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
+    else launch_kernel(k_cull_large<false>, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
 }
 
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
-                        const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats) {
+                        const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats, bool subdiv) {
     if (!nPacked) return;
-    launch_kernel(k_tile_packed, nPacked, TILE_THREADS, 0, s, pdl, draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
+    if (subdiv) launch_kernel(k_tile_packed<true>, nPacked, TILE_THREADS, 0, s, pdl, draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
+    else launch_kernel(k_tile_packed<false>, nPacked, TILE_THREADS, 0, s, pdl, draws, tbase, tiles, packedList, fc, clip, wpos, sorted, tileSurv, stats);
 }
 
 void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* mediumList, uint32_t nMedium,
-                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats) {
+                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* sorted, DrawStat* stats, bool subdiv) {
     if (!nMedium) return;
-    launch_kernel(k_draw_medium, nMedium, TILE_THREADS, 0, s, pdl, draws, tiles, mediumList, fc, clip, wpos, sorted, stats);
+    if (subdiv) launch_kernel(k_draw_medium<true>, nMedium, TILE_THREADS, 0, s, pdl, draws, tiles, mediumList, fc, clip, wpos, sorted, stats);
+    else launch_kernel(k_draw_medium<false>, nMedium, TILE_THREADS, 0, s, pdl, draws, tiles, mediumList, fc, clip, wpos, sorted, stats);
 }
 
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,

@@ -132,6 +132,18 @@ PYBIND11_MODULE(_host, m) {
             for (uint32_t i : s.TriangleIndices) if (i >= s.VertexPositions.size() / 3) throw std::invalid_argument("SetTriangles: index out of range");
             s.RecalculateCenters(); s.MarkDirty();
         })
+        // the result of Mesh.SetAutoSubdivide(true) (mesh.go:447-485): the triangle arrays are already in the expanded order
+        .def("SetAutoSubdivision", [](Mesh& s, const farr& centers, const py::array_t<uint32_t, py::array::c_style | py::array::forcecast>& base,
+                                      const py::array_t<int8_t, py::array::c_style | py::array::forcecast>& level,
+                                      const py::array_t<uint8_t, py::array::c_style | py::array::forcecast>& nLevels, const farr& span, const farr& normals) {
+            const size_t t = (size_t)s.TriangleTotal();
+            if ((size_t)centers.size() != 3 * t || (size_t)base.size() != t || (size_t)level.size() != t || (size_t)nLevels.size() != t || (size_t)span.size() != t || (size_t)normals.size() != 3 * t)
+                throw std::invalid_argument("SetAutoSubdivision: arrays do not match the triangle count");
+            s.TriangleCenters = vec_from<float>(centers); s.TriangleSubBase = vec_from<uint32_t>(base); s.TriangleSubLevel = vec_from<int8_t>(level);
+            s.TriangleLevelCount = vec_from<uint8_t>(nLevels); s.TriangleMaxSpan = vec_from<float>(span); s.TriangleNormals = vec_from<float>(normals);
+            s.autoSubdivide = true; s.MarkDirty();
+        })
+        .def("AutoSubdivide", [](Mesh& s) { return s.autoSubdivide; })
         .def("AddMeshPart", &Mesh::AddMeshPart, py::arg("material"), py::arg("vertex_start"), py::arg("vertex_end"), py::arg("triangle_start"), py::arg("triangle_end"))
         .def("UpdateDimensions", &Mesh::UpdateDimensions)
         .def("AutoNormal", [](Mesh& s) { s.AutoNormal(); s.MarkDirty(); })
@@ -282,7 +294,8 @@ PYBIND11_MODULE(_host, m) {
     py::class_<Scene, std::shared_ptr<Scene>>(m, "Scene")
         .def(py::init<const std::string&>(), py::arg("name") = "scene")
         .def_readwrite("Root", &Scene::Root)
-        .def_readwrite("World", &Scene::world);
+        .def_readwrite("World", &Scene::world)
+        .def("SetAutoSubdivisionLevels", [](Scene& s, const farr& levels) { if (levels.size() % 2) throw std::invalid_argument("levels: (distance_squared, max_size) pairs"); s.autosubdivisionLevels = vec_from<float>(levels); });
     m.def("NewScene", [](const std::string& n) { return std::make_shared<Scene>(n); });
 
     py::class_<GeometryDevice, std::shared_ptr<GeometryDevice>>(m, "GeometryDevice")

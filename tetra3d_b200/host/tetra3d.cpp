@@ -265,6 +265,13 @@ void GeometryDevice::ensureMesh(Mesh& m) {
     d.max_span = m.dimensions.MaxSpan();
     d.n_shape_keys = (uint32_t)m.ShapeKeyWeights.size();
     d.key_positions = m.ShapeKeyPositions.data(); d.key_normals = m.ShapeKeyNormals.data();
+    if (m.autoSubdivide) {
+        const size_t t = (size_t)m.TriangleTotal();
+        if (m.TriangleSubBase.size() != t || m.TriangleSubLevel.size() != t || m.TriangleLevelCount.size() != t || m.TriangleMaxSpan.size() != t || m.TriangleNormals.size() != 3 * t)
+            throw T3DError(T3D_E_INVALID, "Mesh: auto-subdivision arrays do not match the triangle count");
+        d.tri_sub_base = m.TriangleSubBase.data(); d.tri_sub_level = m.TriangleSubLevel.data(); d.tri_n_levels = m.TriangleLevelCount.data();
+        d.tri_max_span = m.TriangleMaxSpan.data(); d.tri_normal = m.TriangleNormals.data();
+    }
     // t3d_mesh_upload is a no-op when (id, generation) is already resident
     check(ctx, t3d_mesh_upload(ctx, m.id, m.generation, &d), "t3d_mesh_upload");
     if (d.n_shape_keys) check(ctx, t3d_mesh_set_shape_key_weights(ctx, m.id, m.ShapeKeyWeights.data(), d.n_shape_keys), "t3d_mesh_set_shape_key_weights");
@@ -770,6 +777,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     }
     device->frameSerial++;
     check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
+    if (!scene.autosubdivisionLevels.empty())      // camera.go:1547-1553
+        check(ctx, t3d_frame_set_autosubdivision(ctx, scene.autosubdivisionLevels.data(), (uint32_t)(scene.autosubdivisionLevels.size() / 2)), "t3d_frame_set_autosubdivision");
 
     // light lists: the scene list once, each active LightGroup once (camera.go:1576-1581)
     uint32_t sceneList = 0; bool sceneListMade = false;

@@ -94,6 +94,12 @@ struct Mesh {
     std::vector<float> VertexWeights;  std::vector<uint16_t> VertexBones;  std::vector<uint8_t> VertexInfluences;  // 4n,4n,n
     std::vector<uint32_t> TriangleIndices;                          // 3t
     std::vector<float> TriangleCenters;                             // 3t  (Triangle.Center)
+    // Auto-subdivision (mesh.go:447-485, 1758-1861): TriangleIndices / TriangleCenters hold every base triangle followed by
+    // its pre-built sub-triangles level by level (the order forEachTri(true, ...) visits them in); per entry the base
+    // triangle, the level (-1: base), and for base triangles the number of levels, MaxSpan and Normal.
+    bool autoSubdivide = false;
+    std::vector<uint32_t> TriangleSubBase; std::vector<int8_t> TriangleSubLevel; std::vector<uint8_t> TriangleLevelCount;
+    std::vector<float> TriangleMaxSpan, TriangleNormals;
     std::vector<std::shared_ptr<MeshPart>> MeshParts;
     std::vector<float> ShapeKeyPositions, ShapeKeyNormals, ShapeKeyWeights;   // k*n*3, k*n*3, k
     uint32_t shapeKeyWeightGeneration = 0;
@@ -289,6 +295,7 @@ struct Scene {
     std::string Name;
     std::shared_ptr<Node> Root;
     std::shared_ptr<World> world;
+    std::vector<float> autosubdivisionLevels;      // scene.library.autosubdivisionLevels: {DistanceSquared, MaximumTriangleSize} pairs
     explicit Scene(const std::string& n);
 };
 

@@ -67,6 +67,15 @@ class MeshDesc:
     key_normals: Optional[np.ndarray] = None     # (k, n, 3)
     key_weights: Optional[np.ndarray] = None     # (k,)
     name: str = "mesh"
+    # Auto-subdivision (Mesh.SetAutoSubdivide, mesh.go:447-485): `indices` then hold every base triangle followed by its
+    # pre-built sub-triangles level by level -- the order MeshPart.forEachTri(true, ...) visits them in (mesh.go:2238-2256)
+    auto_subdivide: bool = False
+    tri_centers: Optional[np.ndarray] = None     # (t, 3) Triangle.Center of every entry (sub-triangles use their own formula)
+    tri_sub_base: Optional[np.ndarray] = None    # (t,) int32: index of the base triangle (a base triangle names itself)
+    tri_sub_level: Optional[np.ndarray] = None   # (t,) int8: -1 base triangle, else index into the base's subdivisionLevels
+    tri_n_levels: Optional[np.ndarray] = None    # (t,) uint8: len(subdivisionLevels) of a base triangle (0: never subdivided)
+    tri_max_span: Optional[np.ndarray] = None    # (t,) Triangle.MaxSpan
+    tri_normal: Optional[np.ndarray] = None      # (t, 3) Triangle.Normal (read for base triangles only)
 
     def __post_init__(self):
         self.positions = np.ascontiguousarray(self.positions, dtype=F32).reshape(-1, 3)
@@ -210,6 +219,74 @@ class ModelDesc:
     name: str = "model"
 
 
+def auto_subdivide(mesh: MeshDesc, levels, max_count: int = 3) -> MeshDesc:
+    """Mesh.SetAutoSubdivide(true) (mesh.go:447-485) + Triangle.performSubdivision (mesh.go:1758-1861) at load time: every
+    triangle whose MaxSpan exceeds the smallest MaximumTriangleSize of `levels` [(distance_squared, max_size), ...] gets up to
+    `max_count` pre-built levels of 4-way splits; the new vertices (edge midpoints: Lerp 0.5 of position, normal, uv, colour)
+    are appended to the vertex arrays.  Returns a new MeshDesc in the expanded layout described on MeshDesc."""
+    assert mesh.weights is None and mesh.key_weights is None, "auto-subdivision: static meshes only"
+    P = [np.asarray(v, F32) for v in mesh.positions]; N = [np.asarray(v, F32) for v in mesh.normals]; U = [np.asarray(v, F32) for v in mesh.uvs]
+    Cc = [np.asarray(v, F32) for v in mesh.colors] if mesh.colors is not None else None
+    half = F32(0.5)
+    lerp = lambda a, b: (a + ((b - a) * half)).astype(F32)                  # Vector3.Lerp, vector.go:559-565
+    third = F32(1.0 / 3.0)
+    smallest = min(F32(ms) for _, ms in levels)
+
+    def span(a, b, c):                                                      # Triangle.RecalculateCenter, mesh.go:2018-2022
+        mag = lambda v: F32(np.sqrt(np.float64(F32(F32(v[0] * v[0]) + F32(v[1] * v[1])) + F32(v[2] * v[2]))))
+        return max(mag(P[a] - P[b]), mag(P[b] - P[c]), mag(P[c] - P[a]))
+
+    def normal(a, b, c):                                                    # calculateNormal, mesh.go:2171-2181 (any unit normal will do: it is data)
+        n = np.cross((P[b] - P[a]).astype(np.float64), (P[c] - P[b]).astype(np.float64))
+        l = np.linalg.norm(n)
+        return (n / l).astype(F32) if l > 0 else N[a]
+
+    out_idx, out_ctr, out_base, out_lvl, out_nl, out_span, out_nrm = [], [], [], [], [], [], []
+    parts = []
+    for part in mesh.parts:
+        t_start = len(out_idx)
+        for ti in range(part.tri_start, part.tri_end + 1):
+            a, b, c = (int(x) for x in mesh.indices[ti])
+            base_slot = len(out_idx)
+            ms = span(a, b, c)
+            ctr = ((P[a] + P[b] + P[c]) / F32(3)).astype(F32)                # RecalculateCenter, mesh.go:1980-1982
+            subs = [[] for _ in range(max_count)]
+
+            def subdivide(level, ia, ib, ic, tspan):                        # performSubdivision
+                if level == max_count or tspan <= smallest:
+                    return
+                si = len(P)
+                P.extend([lerp(P[ia], P[ib]), lerp(P[ib], P[ic]), lerp(P[ic], P[ia])])
+                N.extend([lerp(N[ia], N[ib]), lerp(N[ib], N[ic]), lerp(N[ic], N[ia])])
+                U.extend([lerp(U[ia], U[ib]), lerp(U[ib], U[ic]), lerp(U[ic], U[ia])])
+                if Cc is not None:
+                    Cc.extend([lerp(Cc[ia], Cc[ib]), lerp(Cc[ib], Cc[ic]), lerp(Cc[ic], Cc[ia])])
+                kids = [(ia, si, si + 2), (si, ib, si + 1), (si + 1, ic, si + 2), (si, si + 1, si + 2)]
+                hs = F32(tspan / F32(2))
+                for k in kids:
+                    kc = (((P[k[0]] + P[k[1]]).astype(F32) + P[k[2]]).astype(F32) * third).astype(F32)
+                    subs[level].append((k, kc, hs))
+                for k in kids:
+                    subdivide(level + 1, k[0], k[1], k[2], hs)
+
+            n_levels = 0
+            if ms > smallest:
+                n_levels = max_count
+                subdivide(0, a, b, c, ms)
+            out_idx.append((a, b, c)); out_ctr.append(ctr); out_base.append(base_slot); out_lvl.append(-1)
+            out_nl.append(n_levels); out_span.append(ms); out_nrm.append(normal(a, b, c))
+            for lv in range(n_levels):
+                for k, kc, hs in subs[lv]:
+                    out_idx.append(k); out_ctr.append(kc); out_base.append(base_slot); out_lvl.append(lv)
+                    out_nl.append(0); out_span.append(hs); out_nrm.append(np.zeros(3, F32))
+        parts.append(PartDesc(part.vertex_start, part.vertex_end, t_start, len(out_idx) - 1, part.material))
+    return MeshDesc(np.asarray(P, F32), np.asarray(N, F32), np.asarray(U, F32), np.asarray(out_idx, np.uint32), parts,
+                    colors=np.asarray(Cc, F32) if Cc is not None else None, active_color_channel=mesh.active_color_channel,
+                    name=mesh.name + "_subdiv", auto_subdivide=True, tri_centers=np.asarray(out_ctr, F32),
+                    tri_sub_base=np.asarray(out_base, np.int32), tri_sub_level=np.asarray(out_lvl, np.int8),
+                    tri_n_levels=np.asarray(out_nl, np.uint8), tri_max_span=np.asarray(out_span, F32), tri_normal=np.asarray(out_nrm, F32))
+
+
 @dataclass
 class CameraDesc:
     node: NodeDesc = field(default_factory=lambda: NodeDesc(position=(0.0, 0.0, 10.0)))
@@ -249,6 +326,7 @@ class SceneDesc:
     camera: CameraDesc = field(default_factory=CameraDesc)
     world: WorldDesc = field(default_factory=WorldDesc)
     name: str = "scene"
+    autosubdivision_levels: Sequence = ()      # scene.library.autosubdivisionLevels (library.go:206-209): [(distance_squared, max_triangle_size), ...]
 
     def total_triangles(self) -> int:
         return sum(m.mesh.n_tris for m in self.models if m.visible)
