@@ -26,7 +26,10 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
                        uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
                        const PoseBatch* poses, uint32_t nPoseBatches);
-static const uint32_t PREP_POSE_BATCHES = 4;       // t3d_submit_poses calls that can ride in k_prep_draws' grid; PREP_POSE_SMEM: their shared-memory budget
+#ifndef T3D_PREP_POSE_BATCHES
+#define T3D_PREP_POSE_BATCHES 4
+#endif
+static const uint32_t PREP_POSE_BATCHES = T3D_PREP_POSE_BATCHES;       // t3d_submit_poses calls that can ride in k_prep_draws' grid; PREP_POSE_SMEM: their shared-memory budget
 static const size_t PREP_POSE_SMEM = 40 * 1024;
 static const int PREP_WINDOW_BLOCKS = 16, PREP_WINDOW_DRAWS = 64;     // k_prep_draws: blocks whose template windows travel as kernel parameters
 // tileLists / nTilesOf are indexed by vertex-tile class: 0 generic, 1 static fast, 2 skinned fast (t3d_kernels.cu: K1_*)

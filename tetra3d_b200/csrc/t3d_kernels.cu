@@ -88,26 +88,33 @@ struct PrepFrame {
     // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
     uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
-    // bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i
-    PoseBatch pose[PREP_POSE_BATCHES]; uint32_t poseBlock[PREP_POSE_BATCHES + 1]; uint32_t nPoseBatches;
+    uint32_t copyEnd;               // grid blocks [nPrepBlocks, copyEnd) copy; blocks beyond (k_prep_draws<true> only) evaluate bone poses
 };
+// Bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i.  Only frames
+// that pose armatures on the device launch the instantiation that carries this parameter and the pose code: on a frame of
+// 50 draws the longer kernel cost 4 us (parameters and instruction fetch) even when no block took the branch.
+template <bool POSES> struct PrepPoses { PoseBatch pose[PREP_POSE_BATCHES]; uint32_t poseBlock[PREP_POSE_BATCHES + 1]; uint32_t nPoseBatches; };
+template <> struct PrepPoses<false> { uint32_t nPoseBatches; };
 
 #ifndef T3D_PREP_MINBLOCKS
 #define T3D_PREP_MINBLOCKS 3
 #endif
+template <bool POSES>
 __global__ void __launch_bounds__(PREP_THREADS, T3D_PREP_MINBLOCKS)
 k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ FrameConst fc,
-             LightU* __restrict__ lightsU, DrawStat* __restrict__ stats) {
+             LightU* __restrict__ lightsU, DrawStat* __restrict__ stats, const __grid_constant__ PrepPoses<POSES> pp) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
-    if (pf.nPoseBatches && blockIdx.x >= pf.poseBlock[0]) {      // the last blocks of the grid: bone poses (independent of the rest)
-        uint32_t i = 0;
-        while (i + 1 < pf.nPoseBatches && blockIdx.x >= pf.poseBlock[i + 1]) i++;
-        pose_block(pf.pose[i], blockIdx.x - pf.poseBlock[i], reinterpret_cast<float*>(prepSmem));
-        return;
+    if constexpr (POSES) {
+        if (blockIdx.x >= pf.copyEnd) {      // the last blocks of the grid: bone poses (independent of the rest)
+            uint32_t i = 0;
+            while (i + 1 < pp.nPoseBatches && blockIdx.x >= pp.poseBlock[i + 1]) i++;
+            pose_block(pp.pose[i], blockIdx.x - pp.poseBlock[i], reinterpret_cast<float*>(prepSmem));
+            return;
+        }
     }
     if (blockIdx.x >= pf.nPrepBlocks) {
-        const uint32_t nb = (pf.nPoseBatches ? pf.poseBlock[0] : gridDim.x) - pf.nPrepBlocks;
+        const uint32_t nb = pf.copyEnd - pf.nPrepBlocks;
         const uint32_t stride = nb * PREP_THREADS;
         const uint4* __restrict__ src = pf.hostRest;
         uint4* __restrict__ dst = pf.devRest;
@@ -1465,7 +1472,8 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
                        const PoseBatch* poses, uint32_t nPoseBatches) {
     if (!nDraws) return;
-    cudaFuncSetAttribute(k_prep_draws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
+    cudaFuncSetAttribute(k_prep_draws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
+    cudaFuncSetAttribute(k_prep_draws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);
     PrepFrame pf;
     pf.hostSlim = reinterpret_cast<const uint4*>(hostSlim); pf.hostTmpl = reinterpret_cast<const uint4*>(hostTmpl);
     pf.hostRot = reinterpret_cast<const uint4*>(hostRot); pf.hostRest = reinterpret_cast<const uint4*>(hostRest);
@@ -1490,16 +1498,23 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
     // pose batches ride as extra blocks at the end of the grid (the caller only passes batches whose shared memory fits)
-    pf.nPoseBatches = std::min<uint32_t>(nPoseBatches, PREP_POSE_BATCHES);
     uint32_t nBlocks = pf.nPrepBlocks + nCopy;
-    for (uint32_t i = 0; i < pf.nPoseBatches; i++) {
-        pf.pose[i] = poses[i];
-        pf.poseBlock[i] = nBlocks;
-        nBlocks += cdiv(poses[i].nPoses, pose_armatures_per_block(poses[i].nBones));
-        smem = std::max(smem, pose_smem_bytes(poses[i].nBones));
+    pf.copyEnd = nBlocks;
+    if (nPoseBatches) {
+        PrepPoses<true> pp;
+        pp.nPoseBatches = std::min<uint32_t>(nPoseBatches, PREP_POSE_BATCHES);
+        for (uint32_t i = 0; i < pp.nPoseBatches; i++) {
+            pp.pose[i] = poses[i];
+            pp.poseBlock[i] = nBlocks;
+            nBlocks += cdiv(poses[i].nPoses, pose_armatures_per_block(poses[i].nBones));
+            smem = std::max(smem, pose_smem_bytes(poses[i].nBones));
+        }
+        pp.poseBlock[pp.nPoseBatches] = nBlocks;
+        launch_kernel(k_prep_draws<true>, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats, pp);
+    } else {
+        PrepPoses<false> pp; pp.nPoseBatches = 0;
+        launch_kernel(k_prep_draws<false>, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats, pp);
     }
-    pf.poseBlock[pf.nPoseBatches] = nBlocks;
-    launch_kernel(k_prep_draws, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats);
 }
 
 void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
