@@ -208,7 +208,7 @@ def volume_scene(seed=0, mode=0) -> SceneDesc:
     return SceneDesc(models, lights, CameraDesc(), WorldDesc(), name="volume")
 
 
-def volume_cell_lights_scene(seed=0, mode=0, skinned=False) -> SceneDesc:
+def volume_cell_lights_scene(seed=0, mode=0, skinned=False, n_extra=0) -> SceneDesc:
     """LightVolumeCell.useLights (light.go:652-654, 1508-1514): a third of the cells carry their own lights -- ranged and
     unranged point lights, a sun, an ambient light, one of them also in the scene list, some cells with several -- that
     light a vertex before the cell colour does."""
@@ -221,6 +221,9 @@ def volume_cell_lights_scene(seed=0, mode=0, skinned=False) -> SceneDesc:
             LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=W.rotation_matrix((1, 0, 0), 0.9)), color=(0.6, 0.9, 0.5), energy=0.8, in_scene=False, name="cell_sun"),
             LightDesc(LIGHT_AMBIENT, NodeDesc(), color=(0.3, 0.1, 0.3), energy=0.5, in_scene=False, name="cell_ambient"),
             sc.lights[1]]                           # the scene's own point light: it then lights such vertices twice, as in the reference
+    for k in range(n_extra):        # many more lights than a light list's first allocation holds
+        pool.append(LightDesc(LIGHT_POINT, NodeDesc(position=tuple(float(x) for x in rng.uniform(-5, 5, 3))), color=tuple(float(x) for x in rng.uniform(0.1, 1, 3)),
+                              energy=float(rng.uniform(0.5, 2.0)), range=float(rng.choice([0.0, 5.0])), in_scene=False, name="cell_extra%d" % k))
     cell_lights = {}
     for z in range(cz):
         for y in range(cy):

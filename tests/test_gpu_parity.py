@@ -88,6 +88,11 @@ def test_volume_cell_lights_fuzz(device, seed):
     assert_parity(scenes.volume_cell_lights_scene(40 + seed, mode=seed % 3, skinned=bool(seed % 2)), device)
 
 
+def test_volume_cell_lights_many(device):
+    # 40 lights behind one volume: the expanded light list outgrows its first allocation
+    assert_parity(scenes.volume_cell_lights_scene(60, mode=0, n_extra=40), device)
+
+
 def test_non_affine_bone_matrices_parity(device):
     # bone matrices normally travel as 12 floats (column 3 is exactly 0,0,0,1); one that is not switches the frame to
     # the full 16-float upload

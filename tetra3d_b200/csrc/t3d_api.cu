@@ -533,6 +533,7 @@ int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_
         }
         ctx->hLights.p[off + i] = L;
     }
+    ctx->hLights.n = off + n;          // reserve keeps the first n elements when it has to move the array
     CU(ctx->hLights.reserve(off + total));
     uint32_t at = off + n;
     for (uint32_t i = 0; i < n; i++) {
