@@ -665,7 +665,7 @@ static int subdivision_choice(const orc_scene* sc, const orc_mesh* mesh, int ti,
     if (active == -1) return -1;
     float ms = mesh->tri_max_span[ti];
     int subIndex = -1;
-    while (ms > sc->subdivision_levels[2 * active + 1]) { ms /= 2; subIndex++; }
+    while (ms > sc->subdivision_levels[2 * active + 1] && subIndex < 200) { ms /= 2; subIndex++; }   /* bounded: an infinite MaxSpan hangs the reference */
     if (subIndex >= nLevels) subIndex = nLevels - 1;
     return subIndex;
 }

@@ -880,7 +880,7 @@ __device__ __noinline__ bool subdiv_visible(const DrawRec* __restrict__ Rp, cons
             float ms = S.span[bt];
             int subIndex = -1;
             const float maxSize = fc->subLevels[active][1];
-            while (ms > maxSize) { ms /= 2.0f; subIndex++; }
+            while (ms > maxSize && subIndex < 200) { ms /= 2.0f; subIndex++; }      // (an infinite MaxSpan would spin forever in the reference)
             if (subIndex >= nLevels) subIndex = nLevels - 1;
             choice = subIndex;
         }
