@@ -92,7 +92,8 @@ struct PrepFrame {
 };
 // Bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i.  Only frames
 // that pose armatures on the device launch the instantiation that carries this parameter and the pose code: on a frame of
-// 50 draws the longer kernel cost 4 us (parameters and instruction fetch) even when no block took the branch.
+// 50 draws the combined kernel was 4 us slower even when no block took the branch (measured A/B; not explained by the
+// parameter bytes or the code length alone).
 template <bool POSES> struct PrepPoses { PoseBatch pose[PREP_POSE_BATCHES]; uint32_t poseBlock[PREP_POSE_BATCHES + 1]; uint32_t nPoseBatches; };
 template <> struct PrepPoses<false> { uint32_t nPoseBatches; };
 
