@@ -165,3 +165,62 @@ def test_error_codes_and_messages(abi):
     assert lib.t3d_mesh_upload(ctx, C.c_uint64(9), C.c_uint32(1), C.byref(md2)) == T3D_E_INVALID and b"out of range" in lib.t3d_last_error(ctx)
     assert lib.t3d_mesh_release(ctx, C.c_uint64(4242)) == T3D_E_NOTFOUND
     assert lib.t3d_mesh_release(ctx, C.c_uint64(8)) == T3D_OK
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("color", C.c_float * 3), ("energy", C.c_float), ("position", C.c_float * 3), ("range", C.c_float),
+                ("forward", C.c_float * 3), ("volume", C.c_uint32)]
+
+
+class VolumeDesc(C.Structure):
+    _fields_ = [("dim_min", C.c_float * 3), ("dim_max", C.c_float * 3), ("cell_size", C.c_float * 3), ("cell_count", C.c_uint32 * 3),
+                ("offset", C.c_float * 3), ("light_bias", C.c_float * 3), ("cell_colors", f32p),
+                ("cell_light_start", C.POINTER(C.c_uint32)), ("cell_light_index", C.POINTER(C.c_uint32))]
+
+
+def test_volume_cell_lights_and_subdivision_call_rules(abi):
+    """t3d_volume_use_lights / t3d_frame_set_autosubdivision: call order and argument checks (light.go:565-580, 1508-1514;
+    camera.go:1547-1553)."""
+    lib, ctx = abi
+    for name in ("t3d_volume_upload", "t3d_volume_use_lights", "t3d_volume_release", "t3d_frame_set_autosubdivision"):
+        getattr(lib, name).restype = C.c_int
+    cam, world = _camera(), World()
+    colors = np.ones(2 * 3, np.float32)
+    start = np.array([0, 1, 3], np.uint32); index = np.array([0, 1, 0], np.uint32)
+    vd = VolumeDesc()
+    vd.dim_min[:] = (-1, -1, -1); vd.dim_max[:] = (1, 1, 1); vd.cell_size[:] = (1, 2, 2); vd.cell_count[:] = (2, 1, 1)
+    vd.cell_colors = colors.ctypes.data_as(f32p)
+    vd.cell_light_start = start.ctypes.data_as(C.POINTER(C.c_uint32)); vd.cell_light_index = index.ctypes.data_as(C.POINTER(C.c_uint32))
+    assert lib.t3d_volume_upload(ctx, C.c_uint32(5), C.byref(vd)) == T3D_OK
+    bad_start = np.array([0, 2, 1], np.uint32)
+    vd2 = VolumeDesc(); C.memmove(C.byref(vd2), C.byref(vd), C.sizeof(vd)); vd2.cell_light_start = bad_start.ctypes.data_as(C.POINTER(C.c_uint32))
+    assert lib.t3d_volume_upload(ctx, C.c_uint32(6), C.byref(vd2)) == T3D_E_INVALID and b"non-decreasing" in lib.t3d_last_error(ctx)
+    point = Light(); point.type = 1; point.energy = 1.0
+    volume = Light(); volume.type = 3; volume.volume = 5; volume.energy = 1.0
+    lights2 = (Light * 2)(point, point)
+    lid = C.c_uint32()
+    levels = (C.c_float * 4)(100.0, 1.0, 25.0, 0.5)
+    # outside a frame
+    assert lib.t3d_volume_use_lights(ctx, C.c_uint32(5), lights2, C.c_uint32(2)) == T3D_E_STATE
+    assert lib.t3d_frame_set_autosubdivision(ctx, levels, C.c_uint32(2)) == T3D_E_STATE
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    # a list holding the volume before its cell lights were passed
+    assert lib.t3d_submit_lights(ctx, C.byref(volume), C.c_uint32(1), C.byref(lid)) == T3D_E_STATE and b"t3d_volume_use_lights" in lib.t3d_last_error(ctx)
+    assert lib.t3d_volume_use_lights(ctx, C.c_uint32(99), lights2, C.c_uint32(2)) == T3D_E_NOTFOUND
+    assert lib.t3d_volume_use_lights(ctx, C.c_uint32(5), lights2, C.c_uint32(1)) == T3D_E_INVALID and b"fewer lights" in lib.t3d_last_error(ctx)
+    nested = (Light * 2)(point, volume)
+    assert lib.t3d_volume_use_lights(ctx, C.c_uint32(5), nested, C.c_uint32(2)) == T3D_E_UNSUPPORTED
+    assert lib.t3d_volume_use_lights(ctx, C.c_uint32(5), lights2, C.c_uint32(2)) == T3D_OK
+    assert lib.t3d_submit_lights(ctx, C.byref(volume), C.c_uint32(1), C.byref(lid)) == T3D_OK and lid.value >= 1
+    # subdivision levels
+    assert lib.t3d_frame_set_autosubdivision(ctx, levels, C.c_uint32(2)) == T3D_OK
+    assert lib.t3d_frame_set_autosubdivision(ctx, levels, C.c_uint32(9)) == T3D_E_UNSUPPORTED
+    zero = (C.c_float * 2)(100.0, 0.0)
+    assert lib.t3d_frame_set_autosubdivision(ctx, zero, C.c_uint32(1)) == T3D_E_INVALID and b"positive" in lib.t3d_last_error(ctx)
+    assert lib.t3d_frame_execute(ctx) == T3D_OK
+    assert lib.t3d_volume_release(ctx, C.c_uint32(5)) == T3D_OK
+    # mesh upload: the five subdivision arrays come together
+    md, keep = _triangle_mesh()
+    base = np.zeros(1, np.uint32)
+    md.tri_sub_base = base.ctypes.data_as(C.POINTER(C.c_uint32))
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(21), C.c_uint32(1), C.byref(md)) == T3D_E_INVALID and b"all five" in lib.t3d_last_error(ctx)
