@@ -26,7 +26,9 @@ def main():
     device = t3d.GeometryDevice(local)
     ok = True
     scene_list = (("soup_lit", scenes.soup_scene(1, n_models=9)), ("batch", scenes.batch_scene(1)),
-                  ("million_reduced", W.million_triangle_scene(nx=250, nz=125)), ("instanced", W.instanced_scene(n=24, subdivisions=2, box=(30.0, 10.0, 30.0))))
+                  ("million_reduced", W.million_triangle_scene(nx=250, nz=125)), ("instanced", W.instanced_scene(n=24, subdivisions=2, box=(30.0, 10.0, 30.0))),
+                  ("posed", scenes.posed_scene(2, n_models=9, n_bones=6)), ("cell_lights", scenes.volume_cell_lights_scene(5, 0, skinned=True)),
+                  ("subdivision", scenes.subdivision_scene(0)), ("animated_crowd", W.skinned_crowd_animated_scene(n=64)))
     # ---- peer-write path: every rank's emit kernel stores into rank 0's lists over NVLink (parallel.SharedLists) ----
     shared = parallel.SharedLists(device, local, vertex_capacity=3 * max(d.total_triangles() for _, d in scene_list), dst=0)
     for name, desc in scene_list:
