@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     """ctypes mirrors of the ABI structs a cgo shim would declare: sizes must match the C compiler's."""
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world));return 0;}\n'
+    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world), sizeof(t3d_pose), sizeof(t3d_track));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
@@ -36,6 +36,7 @@ def test_struct_sizes_match_header():
     assert sizes[0] == 48           # ebiten.Vertex: 12 x float32
     assert sizes[1] == 52 and sizes[5] == 16 and sizes[4] == 24
     assert sizes[2] % 8 == 0
+    assert sizes[7] == 80 and sizes[8] == 12      # t3d_pose: root[16] + playhead + 3 reserved floats; t3d_track: 3 x uint32
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
