@@ -106,20 +106,25 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
              LightU* __restrict__ lightsU, DrawStat* __restrict__ stats, const __grid_constant__ PrepPoses<POSES> pp) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
+    // Pose blocks come FIRST in the grid (k_prep_draws<true>): they start at once and their float64 arithmetic overlaps the
+    // PCIe round trips of the prep blocks, instead of trailing them as a second wave.
+    uint32_t bid = blockIdx.x;
     if constexpr (POSES) {
-        if (blockIdx.x >= pf.copyEnd) {      // the last blocks of the grid: bone poses (independent of the rest)
+        const uint32_t nPoseBlocks = pp.poseBlock[pp.nPoseBatches];
+        if (bid < nPoseBlocks) {
             uint32_t i = 0;
-            while (i + 1 < pp.nPoseBatches && blockIdx.x >= pp.poseBlock[i + 1]) i++;
-            pose_block(pp.pose[i], blockIdx.x - pp.poseBlock[i], reinterpret_cast<float*>(prepSmem));
+            while (i + 1 < pp.nPoseBatches && bid >= pp.poseBlock[i + 1]) i++;
+            pose_block(pp.pose[i], bid - pp.poseBlock[i], reinterpret_cast<float*>(prepSmem));
             return;
         }
+        bid -= nPoseBlocks;
     }
-    if (blockIdx.x >= pf.nPrepBlocks) {
-        const uint32_t nb = pf.copyEnd - pf.nPrepBlocks;
+    if (bid >= pf.nPrepBlocks) {
+        const uint32_t nb = pf.copyEnd - pf.nPrepBlocks;      // copy blocks
         const uint32_t stride = nb * PREP_THREADS;
         const uint4* __restrict__ src = pf.hostRest;
         uint4* __restrict__ dst = pf.devRest;
-        uint32_t i = (blockIdx.x - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x;
+        uint32_t i = (bid - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x;
         for (; i + 7 * stride < pf.rest16; i += 8 * stride) {
             uint4 v[8];
 #pragma unroll
@@ -129,7 +134,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         }
         for (; i < pf.rest16; i += stride) dst[i] = src[i];
         // bone matrices, one per thread: 3 (packed) or 4 uint4 in, 4 out
-        for (uint32_t b = (blockIdx.x - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x; b < pf.nBones; b += stride) {
+        for (uint32_t b = (bid - pf.nPrepBlocks) * PREP_THREADS + threadIdx.x; b < pf.nBones; b += stride) {
             uint4* o = pf.devBones + 4 * (size_t)b;
             if (pf.bonesPacked) {
                 const uint4* p = pf.hostBones + 3 * (size_t)b;
@@ -153,17 +158,17 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     uint4* sRot = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
     uint4* sT = sRot + PREP_DRAWS * 4;
     t3d_light* sL = reinterpret_cast<t3d_light*>(sT + pf.tmplCap * REC16);
-    const uint32_t d0 = blockIdx.x * PREP_DRAWS;
+    const uint32_t d0 = bid * PREP_DRAWS;
     const uint32_t n = min((uint32_t)PREP_DRAWS, pf.nDraws - d0);
     constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
-    const bool known = !pf.runMode && blockIdx.x < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
-    uint32_t tmin = known ? pf.win[blockIdx.x][0] : 0u, rmin = known ? pf.win[blockIdx.x][2] : NO_ROTATION;
+    const bool known = !pf.runMode && bid < PREP_PARAM_BLOCKS;      // windows in the kernel parameters
+    uint32_t tmin = known ? pf.win[bid][0] : 0u, rmin = known ? pf.win[bid][2] : NO_ROTATION;
     const bool lightsStaged = pf.nLightsIn <= pf.lightCap;
     if (pf.runMode) {
         // Round trip 1: this block's payloads (4 uint4 per draw: three of transform rows, one of colour) go straight into
         // the packed record layout {header 2 | transform 3 | colour 1}; the runs covering the block; the light table.
         const uint4* src = pf.hostSlim + (size_t)d0 * 4;
-        const uint32_t r0 = pf.hostBlockRun[blockIdx.x], r1 = pf.hostBlockRun[blockIdx.x + 1];
+        const uint32_t r0 = pf.hostBlockRun[bid], r1 = pf.hostBlockRun[bid + 1];
         uint4 pv;
         if (threadIdx.x < n * 4) pv = src[threadIdx.x];
         const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(pf.hostLights);
@@ -195,7 +200,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         uint4 v[2], tv[T_SWEEPS], rv;
 #pragma unroll
         for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
-        const uint32_t t16 = known ? min(pf.win[blockIdx.x][1], pf.tmplCap) * REC16 : 0u, r16 = known ? pf.win[blockIdx.x][3] * 4 : 0u;
+        const uint32_t t16 = known ? min(pf.win[bid][1], pf.tmplCap) * REC16 : 0u, r16 = known ? pf.win[bid][3] * 4 : 0u;
         const uint4* tsrc = pf.hostTmpl + (size_t)tmin * REC16;
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) tv[u] = tsrc[i]; }
@@ -1498,20 +1503,22 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                                     nBones ? std::min<uint32_t>(cdiv(nBones, PREP_THREADS * 2), 1184u) : 0u);
     // the first kernel of a frame is never a dependent launch: it overwrites what the previous frame's kernels read
     (void)pdl;
-    // pose batches ride as extra blocks at the end of the grid (the caller only passes batches whose shared memory fits)
+    // pose batches ride as extra blocks at the START of the grid (the caller only passes batches whose shared memory fits);
+    // the kernel's other blocks then count from the first block behind them
     uint32_t nBlocks = pf.nPrepBlocks + nCopy;
     pf.copyEnd = nBlocks;
     if (nPoseBatches) {
         PrepPoses<true> pp;
         pp.nPoseBatches = std::min<uint32_t>(nPoseBatches, PREP_POSE_BATCHES);
+        uint32_t nPose = 0;
         for (uint32_t i = 0; i < pp.nPoseBatches; i++) {
             pp.pose[i] = poses[i];
-            pp.poseBlock[i] = nBlocks;
-            nBlocks += cdiv(poses[i].nPoses, pose_armatures_per_block(poses[i].nBones));
+            pp.poseBlock[i] = nPose;
+            nPose += cdiv(poses[i].nPoses, pose_armatures_per_block(poses[i].nBones));
             smem = std::max(smem, pose_smem_bytes(poses[i].nBones));
         }
-        pp.poseBlock[pp.nPoseBatches] = nBlocks;
-        launch_kernel(k_prep_draws<true>, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats, pp);
+        pp.poseBlock[pp.nPoseBatches] = nPose;
+        launch_kernel(k_prep_draws<true>, nBlocks + nPose, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats, pp);
     } else {
         PrepPoses<false> pp; pp.nPoseBatches = 0;
         launch_kernel(k_prep_draws<false>, nBlocks, PREP_THREADS, smem, s, false, pf, fc, lightsU, stats, pp);
