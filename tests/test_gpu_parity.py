@@ -93,6 +93,20 @@ def test_volume_cell_lights_many(device):
     assert_parity(scenes.volume_cell_lights_scene(60, mode=0, n_extra=40), device)
 
 
+def test_staged_and_chunked_uniform_upload_parity(monkeypatch):
+    # frames of a megabyte and more are copied to the device by DMA before k_prep_draws reads them, and very large ones in
+    # slices that overlap the kernel: both forced onto small frames here (run-length records, plain records, bones, poses)
+    import tetra3d_b200 as t3d
+    monkeypatch.setenv("T3D_DMA_THRESHOLD", "0")
+    monkeypatch.setenv("T3D_PREP_CHUNK_BLOCKS", "2")
+    dev = t3d.GeometryDevice(0)
+    assert_parity(W.particles_scene(n=3000, batch_cap=4096), dev, check_capture=False)      # run-length records, 47 blocks -> 24 slices
+    assert_parity(scenes.tile_boundary_scene(33, sizes=(1, 2) * 700), dev, check_capture=False)
+    assert_parity(W.skinned_crowd_scene(n=500), dev, check_capture=False)
+    assert_parity(W.skinned_crowd_animated_scene(n=500), dev, check_capture=False)
+    assert_parity(scenes.fuzz_scene(3), dev, check_capture=False)                            # a small frame: staged, one slice
+
+
 def test_non_affine_bone_matrices_parity(device):
     # bone matrices normally travel as 12 floats (column 3 is exactly 0,0,0,1); one that is not switches the frame to
     # the full 16-float upload

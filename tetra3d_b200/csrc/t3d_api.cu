@@ -151,6 +151,10 @@ struct t3d_ctx {
     DrawRec* pDraws = nullptr; uint32_t *pVbase = nullptr, *pTbase = nullptr, *pLarge = nullptr, *pPacked = nullptr, *pMedium = nullptr, *pHuge = nullptr; uint4* pVClass[3] = {nullptr, nullptr, nullptr};
     TriTile* pTiles = nullptr;
     t3d_light* pLightsIn = nullptr; float* pBones = nullptr;
+    DevBuf dStage;      // device copy of the pinned frame block, for frames large enough that a DMA copy beats k_prep_draws' own PCIe reads
+    size_t dmaThreshold = 1u << 20; bool frameStaged = false; size_t frameBlockBytes = 0, frameSlimBytes = 0;
+    uint32_t prepChunkBlocks = 0;       // 0: adaptive (see t3d_frame_execute); T3D_PREP_CHUNK_BLOCKS overrides
+    cudaStream_t copyStream = nullptr; cudaEvent_t evFork = nullptr; std::vector<cudaEvent_t> evChunk;     // chunked staging of very large frames
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
     DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
     DevBuf dColor, dDepth, dNormal, dTriIds;
@@ -231,6 +235,8 @@ int t3d_create(t3d_ctx** out, int device_id) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char* th = getenv("T3D_DMA_THRESHOLD")) ctx->dmaThreshold = (size_t)strtoull(th, nullptr, 10);      // diagnostics: bytes; 0 = always copy, huge = never
+    if (const char* cb = getenv("T3D_PREP_CHUNK_BLOCKS")) ctx->prepChunkBlocks = std::max(1u, (uint32_t)strtoul(cb, nullptr, 10));    // diagnostics / tests
     *out = ctx;
     return T3D_OK;
 }
@@ -242,10 +248,12 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (auto& kv : ctx->meshes) kv.second.release();
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
     for (uint32_t* c : ctx->volumeCsr) if (c) cudaFree(c);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); cudaEventDestroy(ctx->evFork); }
+    for (cudaEvent_t e : ctx->evChunk) cudaEventDestroy(e);
     for (auto& kv : ctx->skeletons) if (kv.second.block) cudaFree(kv.second.block);
     for (auto& kv : ctx->animations) if (kv.second.block) cudaFree(kv.second.block);
     ctx->hPoses.release();
-    DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame,
+    DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame, &ctx->dStage,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
                       &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
@@ -1049,6 +1057,11 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->frameBonesOff = headBytes + restBytes; ctx->frameBoneCount = (uint32_t)nBones;
         // no DMA copy: k_prep_draws reads the pinned block through UVA and writes the device copy
         CU(cudaHostGetDevicePointer(&ctx->hFrameDev, ctx->hFrame.p, 0));
+        // ... unless the block is large: zero-copy reads from the SMs top out at ~40 GB/s, the copy engine reaches ~55, so from
+        // about a megabyte on the block is copied into device memory first and k_prep_draws reads that copy instead
+        ctx->frameBlockBytes = headBytes + restBytes + hostBoneBytes; ctx->frameSlimBytes = slimBytes;
+        ctx->frameStaged = ctx->frameBlockBytes >= ctx->dmaThreshold;
+        if (ctx->frameStaged) CU(ctx->dStage.ensure(ctx->frameBlockBytes));
         ctx->frameHeadBytes = headBytes; ctx->frameRestBytes = restBytes; ctx->frameTmplOff = head[1].off; ctx->frameRotOff = head[2].off;
         ctx->frameRunsOff = head[3].off; ctx->frameBlockRunOff = head[4].off; ctx->framePosesOff = head[5].off;
         ctx->frameLightsOff = headBytes + segs[6].off;
@@ -1098,6 +1111,25 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             win[b][2] = rmin; win[b][3] = rmin != NO_ROTATION ? rmax - rmin + 1 : 0;
         }
         const uint8_t* hf = static_cast<const uint8_t*>(ctx->hFrameDev);
+        // Very large staged frames are prepared in chunks of PREP_CHUNK_BLOCKS blocks: the placement records are copied slice by
+        // slice on a second stream and every slice's k_prep_draws launch waits only for its own slice, so the copy engine runs
+        // back to back while the kernels work on what has arrived (2 M particles: 128 MB of records).
+        const uint32_t nPrepBlocks = (nDraws + PREP_WINDOW_DRAWS - 1) / PREP_WINDOW_DRAWS;
+        // slice size: an eighth of the frame, between 1024 and 4096 blocks (64 K .. 256 K draws) -- small enough to overlap, large
+        // enough that the per-slice launch and event cost stays invisible (measured on 200 K and 2 M particle frames)
+        const uint32_t PREP_CHUNK_BLOCKS = ctx->prepChunkBlocks ? ctx->prepChunkBlocks : std::min(4096u, std::max(1024u, nPrepBlocks / 8));
+        const bool chunked = ctx->frameStaged && nPrepBlocks >= 3 * PREP_CHUNK_BLOCKS;
+        if (ctx->frameStaged) {
+            hf = ctx->dStage.as<uint8_t>();
+            if (!chunked) CU(cudaMemcpyAsync(ctx->dStage.p, ctx->hFrame.p, ctx->frameBlockBytes, cudaMemcpyHostToDevice, s));
+            else {      // everything but the placement records (templates, rotations, runs, tables, lights, bones) goes first
+                const size_t off1 = ctx->frameTmplOff;
+                CU(cudaMemcpyAsync(ctx->dStage.as<uint8_t>() + off1, ctx->hFrame.p + off1, ctx->frameBlockBytes - off1, cudaMemcpyHostToDevice, s));
+                if (!ctx->copyStream) { CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)); }
+                CU(cudaEventRecord(ctx->evFork, s));
+                CU(cudaStreamWaitEvent(ctx->copyStream, ctx->evFork, 0));
+            }
+        }
         // bone poses evaluated on the device: one launch per t3d_submit_poses call, into the arena behind the submitted matrices
         PoseBatch fused[PREP_POSE_BATCHES]; uint32_t nFused = 0;
         for (const PoseCall& c : ctx->poseCalls) {
@@ -1116,12 +1148,25 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             if (nFused < PREP_POSE_BATCHES && pose_batch_smem(pb.nBones) <= PREP_POSE_SMEM) fused[nFused++] = pb;
             else { CU(launch_pose_bones(s, pb)); ctx->launches += 1; }
         }
-        launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
-                          reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
-                          (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
-                          hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
-                          ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
-                          reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused);
+        for (uint32_t b0 = 0, k = 0; b0 < nPrepBlocks; k++) {
+            const uint32_t b1 = chunked ? std::min(b0 + PREP_CHUNK_BLOCKS, nPrepBlocks) : nPrepBlocks;
+            if (chunked) {
+                const size_t lo = (size_t)b0 * PREP_WINDOW_DRAWS * ctx->frameSlimBytes;
+                const size_t hi = (size_t)std::min<uint64_t>((uint64_t)b1 * PREP_WINDOW_DRAWS, nDraws) * ctx->frameSlimBytes;
+                CU(cudaMemcpyAsync(ctx->dStage.as<uint8_t>() + lo, ctx->hFrame.p + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copyStream));
+                if (ctx->evChunk.size() <= k) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->evChunk.push_back(e); }
+                CU(cudaEventRecord(ctx->evChunk[k], ctx->copyStream));
+                CU(cudaStreamWaitEvent(s, ctx->evChunk[k], 0));
+            }
+            launch_prep_draws(s, pdl, hf, hf + ctx->frameTmplOff, hf + ctx->frameRotOff, hf + ctx->frameHeadBytes,
+                              reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
+                              (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
+                              hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
+                              ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
+                              reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused, b0, b1 - b0, b0 == 0);
+            if (b0) ctx->launches += 1;
+            b0 = b1;
+        }
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};

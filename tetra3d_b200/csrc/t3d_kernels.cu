@@ -88,7 +88,8 @@ struct PrepFrame {
     // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
     uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
-    uint32_t copyEnd;               // grid blocks [nPrepBlocks, copyEnd) copy; blocks beyond (k_prep_draws<true> only) evaluate bone poses
+    uint32_t copyEnd;               // this launch's blocks [nPrepBlocks, copyEnd) copy (behind the pose blocks of k_prep_draws<true>)
+    uint32_t blockBase;             // first 64-draw block of this launch: a large staged frame is prepared in chunks, each behind its slice's copy
 };
 // Bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i.  Only frames
 // that pose armatures on the device launch the instantiation that carries this parameter and the pose code: on a frame of
@@ -158,6 +159,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     uint4* sRot = prepSmem + PREP_DRAWS * (REC16 + SLIM16);
     uint4* sT = sRot + PREP_DRAWS * 4;
     t3d_light* sL = reinterpret_cast<t3d_light*>(sT + pf.tmplCap * REC16);
+    bid += pf.blockBase;
     const uint32_t d0 = bid * PREP_DRAWS;
     const uint32_t n = min((uint32_t)PREP_DRAWS, pf.nDraws - d0);
     constexpr int T_SWEEPS = (PREP_TEMPLATES * REC16 + PREP_THREADS - 1) / PREP_THREADS;
@@ -1476,7 +1478,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
                        uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
-                       const PoseBatch* poses, uint32_t nPoseBatches) {
+                       const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
     cudaFuncSetAttribute(k_prep_draws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);
@@ -1485,7 +1487,9 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.hostRot = reinterpret_cast<const uint4*>(hostRot); pf.hostRest = reinterpret_cast<const uint4*>(hostRest);
     pf.hostLights = hostLights;
     pf.devDraws = reinterpret_cast<uint4*>(devDraws); pf.devRest = reinterpret_cast<uint4*>(devRest);
-    pf.nDraws = nDraws; pf.rest16 = (uint32_t)(restBytes / 16); pf.nPrepBlocks = cdiv(nDraws, PREP_DRAWS); pf.nLightsIn = nLightsIn;
+    pf.nDraws = nDraws; pf.rest16 = firstChunk ? (uint32_t)(restBytes / 16) : 0u; pf.nPrepBlocks = nBlocksThis; pf.nLightsIn = nLightsIn;
+    pf.blockBase = blockBase;
+    if (!firstChunk) { nBones = 0; nPoseBatches = 0; }       // the copy and pose blocks ride with the first chunk only
     memcpy(pf.win, win, sizeof pf.win);
     pf.hostBones = reinterpret_cast<const uint4*>(hostBones); pf.devBones = reinterpret_cast<uint4*>(devBones);
     pf.nBones = nBones; pf.bonesPacked = bonesPacked ? 1u : 0u;
