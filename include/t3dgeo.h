@@ -326,6 +326,12 @@ int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* t
  * t3d_frame_results_device then returns these pointers; t3d_frame_results still copies to pinned host memory.
  * Passing color = NULL restores the library's buffers. */
 int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity);
+/* Sharded frames whose lists live on another GPU: the depth list differs from the colour list only in its colour,
+ * (d, d, d, 1) (camera.go:1760-1782).  With `depth_scalars` set (device memory, one float per vertex of the target's
+ * capacity) the emit writes d there instead of the target's depth list -- 52 instead of 96 bytes per vertex cross NVLink --
+ * and the owner of the lists rebuilds the records with t3d_expand_depth_list (synchronous).  NULL switches back. */
+int t3d_set_output_compact_depth(t3d_ctx* ctx, float* depth_scalars);
+int t3d_expand_depth_list(t3d_ctx* ctx, const t3d_vertex* color, const float* depth_scalars, t3d_vertex* depth, uint64_t n_vertices, int render_depth);
 /* Device memory that other processes of the same machine can map (CUDA IPC): the owning rank allocates, sends
  * the handle over any channel, the other ranks open it and pass the pointer (plus their offset) to
  * t3d_set_output_target.  Freed / unmapped by t3d_destroy. */

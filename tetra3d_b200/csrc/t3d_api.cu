@@ -161,6 +161,7 @@ struct t3d_ctx {
     // external output target (t3d_set_output_target): the emit kernel writes the lists there -- another GPU's
     // memory over NVLink, or an interop buffer of the rasteriser -- instead of into dColor / dDepth / dNormal
     t3d_vertex *xColor = nullptr, *xDepth = nullptr, *xNormal = nullptr;
+    float* xDepthScalar = nullptr;      // t3d_set_output_compact_depth: one depth value per vertex instead of the depth list
     t3d_vertex *oColor = nullptr, *oDepth = nullptr, *oNormal = nullptr;     // where the current frame's lists are
     uint64_t xCapacity = 0;
     std::vector<void*> sharedAllocs, sharedOpened;
@@ -1203,10 +1204,12 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     CU(mark(5));
     // K4
+    const bool compact = external && ctx->xDepthScalar != nullptr;
+    if (compact && normals) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_execute: compact depth output with RenderNormals");
     launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                 ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
-                reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
-                normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>());
+                reinterpret_cast<float4*>(ctx->oColor), compact ? reinterpret_cast<float4*>(ctx->xDepthScalar) : reinterpret_cast<float4*>(ctx->oDepth),
+                normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), compact);
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[6], s));
     CU(cudaGetLastError());
@@ -1368,6 +1371,25 @@ int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3
     if (color && (((uintptr_t)color | (uintptr_t)depth | (uintptr_t)normal) & 15)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: lists must be 16-byte aligned");
     ctx->xColor = color; ctx->xDepth = depth; ctx->xNormal = color ? normal : nullptr;
     ctx->xCapacity = color ? vertex_capacity : 0;
+    ctx->xDepthScalar = nullptr;
+    return T3D_OK;
+}
+
+int t3d_set_output_compact_depth(t3d_ctx* ctx, float* depth_scalars) {
+    if (!ctx) return T3D_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (depth_scalars && !ctx->xColor) return fail(ctx, T3D_E_STATE, "t3d_set_output_compact_depth: set an output target first");
+    ctx->xDepthScalar = depth_scalars;
+    return T3D_OK;
+}
+
+int t3d_expand_depth_list(t3d_ctx* ctx, const t3d_vertex* color, const float* depth_scalars, t3d_vertex* depth, uint64_t n_vertices, int render_depth) {
+    if (!ctx || (n_vertices && (!color || !depth_scalars || !depth))) return fail(ctx, T3D_E_INVALID, "t3d_expand_depth_list: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    launch_expand_depth(ctx->stream, reinterpret_cast<const float4*>(color), depth_scalars, reinterpret_cast<float4*>(depth), n_vertices, render_depth != 0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
     return T3D_OK;
 }
 

@@ -48,7 +48,8 @@ void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const Tr
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
-                 float4* depthList, float4* normalList, uint32_t* triIds);
+                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth);
+void launch_expand_depth(cudaStream_t s, const float4* color, const float* scalars, float4* depth, uint64_t nVerts, bool renderDepth);
 static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex block (tileFirst granularity)
 
 // t3d_sort.cu -- segmented 512-bin counting sort for draws that span several tiles

@@ -1327,7 +1327,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool NORMALS>
+// COMPACT (sharded frames whose lists live on another GPU): the depth list differs from the colour list only in its colour,
+// which is (d, d, d, 1) -- so only d crosses NVLink (4 bytes per vertex instead of 48, into depthList reinterpreted as
+// float[]) and the owner of the lists rebuilds the records with k_expand_depth.
+template <bool NORMALS, bool COMPACT>
 __global__ void __launch_bounds__(EMIT_TRIS)
 k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
        const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const uint32_t* __restrict__ chunkSum,
@@ -1444,8 +1447,11 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
             const float4 cust = make_float4(custom0, 0.0f, 0.0f, 0.0f);
             float4* C = sCol + 3 * threadIdx.x;
             C[0] = a; C[1] = col; C[2] = cust;
-            float4* D = sDep + 3 * threadIdx.x;
-            D[0] = a; D[1] = dcol; D[2] = cust;
+            if (COMPACT) reinterpret_cast<float*>(depthList)[3 * (size_t)outTri0 + v] = dcol.x;
+            else {
+                float4* D = sDep + 3 * threadIdx.x;
+                D[0] = a; D[1] = dcol; D[2] = cust;
+            }
             if (NORMALS) {                                              // camera.go:1710-1722
                 const float4 tn = __ldg(&tnrm[slot]);
                 float4* Nn = sNrm + 3 * threadIdx.x;
@@ -1460,7 +1466,7 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
             const uint32_t n = min((uint32_t)EMIT_TRIS, nVert - v0);
             const size_t o = 3 * (size_t)outTri0 + v0;                  // first output vertex of this round
             bulk_store(colorList + 3 * o, sCol, n * 48u);
-            bulk_store(depthList + 3 * o, sDep, n * 48u);
+            if (!COMPACT) bulk_store(depthList + 3 * o, sDep, n * 48u);
             if (NORMALS) bulk_store(normalList + 3 * o, sNrm, n * 48u);
             bulk_commit();
         }
@@ -1576,15 +1582,36 @@ void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const Tr
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
-                 float4* depthList, float4* normalList, uint32_t* triIds) {
+                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth) {
     if (!nTiles) return;
     const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
-    if (normalList)
-        launch_kernel(k_emit<true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
+    if (compactDepth)
+        launch_kernel(k_emit<false, true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+    else if (normalList)
+        launch_kernel(k_emit<true, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
                       draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
     else
-        launch_kernel(k_emit<false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
+        launch_kernel(k_emit<false, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
                       draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+}
+
+// The depth list from the colour list and one depth value per vertex (see k_emit<.., COMPACT>): record = {DstX DstY SrcX SrcY |
+// d d d 1 (or zeros without RenderDepth) | Custom0..3} (camera.go:1760-1782).
+__global__ void __launch_bounds__(256)
+k_expand_depth(const float4* __restrict__ color, const float* __restrict__ scalars, float4* __restrict__ depth, uint64_t nVerts, int renderDepth) {
+    const uint64_t v = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (v >= nVerts) return;
+    const float4 a = color[3 * v], c = color[3 * v + 2];
+    const float d = scalars[v];
+    depth[3 * v] = a;
+    depth[3 * v + 1] = renderDepth ? make_float4(d, d, d, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    depth[3 * v + 2] = c;
+}
+
+void launch_expand_depth(cudaStream_t s, const float4* color, const float* scalars, float4* depth, uint64_t nVerts, bool renderDepth) {
+    if (!nVerts) return;
+    launch_kernel(k_expand_depth, (uint32_t)((nVerts + 255) / 256), 256, 0, s, false, color, scalars, depth, nVerts, renderDepth ? 1 : 0);
 }
 
 }  // namespace t3d

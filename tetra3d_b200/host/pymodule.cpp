@@ -322,6 +322,15 @@ PYBIND11_MODULE(_host, m) {
                                                  reinterpret_cast<t3d_vertex*>(normal), capacity);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
         })
+        .def("SetOutputCompactDepth", [](GeometryDevice& d, uintptr_t scalars) {
+            const int rc = t3d_set_output_compact_depth(d.ctx, reinterpret_cast<float*>(scalars));
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+        })
+        .def("ExpandDepthList", [](GeometryDevice& d, uintptr_t color, uintptr_t scalars, uintptr_t depth, uint64_t nVertices, bool renderDepth) {
+            const int rc = t3d_expand_depth_list(d.ctx, reinterpret_cast<const t3d_vertex*>(color), reinterpret_cast<const float*>(scalars),
+                                                 reinterpret_cast<t3d_vertex*>(depth), nVertices, renderDepth ? 1 : 0);
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+        })
         .def("ReadBones", [](GeometryDevice& d, uint32_t offset, uint32_t n) {
             py::array_t<float> out({(py::ssize_t)n, (py::ssize_t)16});
             int rc = t3d_debug_read_bones(d.ctx, offset, n, out.mutable_data());

@@ -107,7 +107,8 @@ class SharedLists:
     sit there in ascending global id.
     """
 
-    def __init__(self, device, device_index: int, vertex_capacity: int, dst: int = 0, group=None):
+    def __init__(self, device, device_index: int, vertex_capacity: int, dst: int = 0, group=None, compact_depth: bool = True,
+                 render_depth: bool = True):
         self.group, self.dst, self.device = group, dst, device
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -128,6 +129,19 @@ class SharedLists:
             self.depth_ptr = device.SharedOpen(hd)
         off = self.rank * self.capacity * 48
         device.SetOutputTarget(self.color_ptr + off, self.depth_ptr + off, 0, self.capacity)
+        # compact depth: the depth list is the colour list with (d, d, d, 1) for a colour, so the other ranks ship one float per
+        # vertex instead of the second list (52 instead of 96 bytes per vertex into dst) and dst rebuilds the records
+        self.compact = bool(compact_depth) and self.world > 1
+        self.render_depth = bool(render_depth)
+        if self.compact:
+            payload = [None]
+            if self.rank == dst:
+                self.scalar_ptr, hs = device.SharedAlloc(self.world * self.capacity * 4)
+                payload = [hs]
+            dist.broadcast_object_list(payload, src=dst, group=group)
+            if self.rank != dst:
+                self.scalar_ptr = device.SharedOpen(payload[0])
+                device.SetOutputCompactDepth(self.scalar_ptr + self.rank * self.capacity * 4)
         self.nbytes = nbytes
         self._meta_host = None
         self._meta_dev = None
@@ -157,9 +171,15 @@ class SharedLists:
             owner, cnt = (v >> 40) - 1, v & ((1 << 40) - 1)
             table[fid] = (cursor[owner], int(cnt))
             cursor[owner] += int(cnt)
+        if self.compact:        # rebuild the other ranks' depth records from their colour records and depth values
+            for r in range(self.world):
+                n = cursor[r] - r * self.capacity
+                if r != self.dst and n:
+                    self.device.ExpandDepthList(self.color_ptr + r * self.capacity * 48, self.scalar_ptr + r * self.capacity * 4,
+                                                self.depth_ptr + r * self.capacity * 48, n, self.render_depth)
         lists = [torch.as_tensor(DeviceArray(self.color_ptr, self.nbytes), device=self.dev),
                  torch.as_tensor(DeviceArray(self.depth_ptr, self.nbytes), device=self.dev)]
         return lists, table
 
     def release(self):
-        self.device.SetOutputTarget(0, 0, 0, 0)
+        self.device.SetOutputTarget(0, 0, 0, 0)      # also drops the compact-depth redirection
