@@ -337,7 +337,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "triangles_per_frame": tris_total, "vertices": desc.total_vertices(), "draws_rank0": n_draws,
                    "surviving_triangles_rank0": surv, "l2": "flushed between steps (512 MiB write)",
-                   "parallelism": "object-wise flush sharding x%d; every rank's emit kernel stores into rank 0's lists over NVLink (CUDA IPC peer memory), per-flush counts by NCCL all-reduce" % world if world > 1 else "1 GPU",
+                   "parallelism": "object-wise flush sharding x%d; every rank's emit kernel stores its colour list and one depth value per vertex into rank 0's memory over NVLink (CUDA IPC peer memory), rank 0 rebuilds the depth records; per-flush counts by NCCL all-reduce" % world if world > 1 else "1 GPU",
                    "timing": "CUDA events on the library's launch stream around the frame's kernels (the first one fetches the uniforms over PCIe), max over ranks; roofline.stages from a second loop with an event between kernels",
                    "wall_ms_per_step_incl_flush_and_host": (wall1 - wall0) / args.steps * 1e3,
                    **({"per_rank": per_rank} if per_rank is not None else {})},
