@@ -1347,6 +1347,11 @@ void orc_test_go_stable_sort(int n, const float* keys, int* perm) {
     go_stable_sort(n, gst_less, gst_swap, &c);
 }
 
+/* camera.go:1460-1469 through sort.SliceStable */
+typedef struct { render_pair_t* a; } rp_ctx;
+static int rp_less_solids(void* cv, int i, int j) { rp_ctx* c = (rp_ctx*)cv; return less_solids(&c->a[i], &c->a[j]); }
+static void rp_swap(void* cv, int i, int j) { rp_ctx* c = (rp_ctx*)cv; render_pair_t t = c->a[i]; c->a[i] = c->a[j]; c->a[j] = t; }
+
 /* the comparator of camera.go:1484-1495 over the sceneLights index list */
 typedef struct { rstate* S; int* ids; vec3 pos; } mls_ctx;
 static int mls_less(void* cv, int i, int j) {
@@ -1526,7 +1531,9 @@ int orc_render_scene(const orc_scene* sc, int capture, orc_result** out) {
         }
     }
 
-    if (!sc->camera.render_depth) stable_sort_pairs(solids, nSolids, less_solids);     /* camera.go:1460-1469 */
+    /* camera.go:1460-1469: the comparator is not a strict weak ordering when RenderOrder values differ, so the result is
+     * defined by Go's sort.SliceStable alone: go_stable_sort restates it */
+    if (!sc->camera.render_depth) { rp_ctx rc; rc.a = solids; go_stable_sort(nSolids, rp_less_solids, rp_swap, &rc); }
     stable_sort_pairs(transparents, nTrans, less_transparents);                         /* camera.go:2050-2055 */
 
     child_t* kids = malloc((size_t)(sc->n_models + 1) * sizeof(child_t));

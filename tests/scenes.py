@@ -283,6 +283,19 @@ def transparent_scene(seed=0) -> SceneDesc:
     return SceneDesc(models, lights_mixed(rng), CameraDesc(), WorldDesc(), name="transparent")
 
 
+def render_order_scene(seed=0, n=45) -> SceneDesc:
+    """More than 20 solids with mixed RenderOrder under RenderDepth = false: the solids comparator of camera.go:1460-1469 is not
+    a strict weak ordering, so the draw order is defined by Go's sort.SliceStable alone (blocks of 20 + SymMerge)."""
+    rng = np.random.default_rng(seed)
+    models = []
+    for i in range(n):
+        mat = MaterialDesc(render_order=int(rng.integers(-2, 3)), backface_culling=bool(i % 2), triangle_sort_mode=i % 3)
+        mesh = W.cube_mesh(0.6, 0.8, 0.6, material=mat)
+        models.append(ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-7, 7, 3)), rotation=random_rotation(rng)), name="ro%d" % i))
+    sc = SceneDesc(models, lights_mixed(rng), CameraDesc(render_depth=False), WorldDesc(), name="render_order%d" % seed)
+    return sc
+
+
 def max_light_count_scene(seed=0, n_lights=7, max_count=3, focus=False) -> SceneDesc:
     """Camera.MaxLightCount (camera.go:1474-1497): more visible lights than the cap, two ambient lights (the world's
     and one in the tree: the comparator is inconsistent for them), a sun, point lights at scattered distances."""
@@ -338,6 +351,8 @@ ALL_SMALL = {
     "volume_cell_lights_normal": lambda: volume_cell_lights_scene(6, 1, skinned=True),
     "volume_cell_lights_object": lambda: volume_cell_lights_scene(7, 2),
     "transparent": lambda: transparent_scene(1),
+    "render_order": lambda: render_order_scene(1),
+    "render_order_many": lambda: render_order_scene(2, n=130),
     "stress_small": lambda: SceneDesc([ModelDesc(W.cube_mesh(2, 2, 2, copies=20, material=MaterialDesc(shadeless=True, use_texture=True, tex_w=16, tex_h=16)),
                                                   NodeDesc(position=(4.0 * x, 0.0, 0.0)), name="m%d" % x) for x in range(6)], [], CameraDesc(), WorldDesc()),
 }

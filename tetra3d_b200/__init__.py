@@ -10,13 +10,37 @@ import os as _os
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
 LIB_PATH = _os.path.join(_HERE, "lib", "libt3dgeo.so")
 
-try:
-    from . import _host  # noqa: F401
-    from ._host import *  # noqa: F401,F403
-except ImportError as _e:  # pragma: no cover - build missing
-    raise ImportError(
-        "tetra3d_b200: the native extension is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
-        "or `make -C tetra3d_b200/csrc && make -C tetra3d_b200/host`): %s" % (_e,)) from _e
+from . import scenedesc  # noqa: E402,F401   (pure Python: scene descriptions shared by tests and benches)
 
-from . import scenedesc  # noqa: E402,F401
-from .build import build_scene  # noqa: E402,F401
+
+def _load_host():
+    """The native extension is loaded on first use, not at import: `tetra3d_b200.scenedesc` / `.workloads` are plain
+    data modules that the CPU reference arm uses without touching the product's native code."""
+    import importlib
+    try:
+        return importlib.import_module("._host", __name__)
+    except ImportError as _e:  # pragma: no cover - build missing
+        raise ImportError(
+            "tetra3d_b200: the native extension is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C tetra3d_b200/csrc && make -C tetra3d_b200/host`): %s" % (_e,)) from _e
+
+
+def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    if name == "build_scene":
+        from .build import build_scene
+        globals()[name] = build_scene
+        return build_scene
+    if name in ("workloads", "parallel", "build", "glb"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    host = _load_host()
+    if name == "_host":
+        return host
+    try:
+        v = getattr(host, name)
+    except AttributeError:
+        raise AttributeError("module 'tetra3d_b200' has no attribute %r" % (name,)) from None
+    globals()[name] = v
+    return v

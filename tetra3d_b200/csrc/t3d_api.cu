@@ -285,11 +285,12 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
     if (it != ctx->meshes.end() && it->second.generation == generation) return T3D_OK;      // already resident
     for (size_t t = 0; t < 3 * (size_t)d->n_tris; t++)
         if (d->indices[t] >= d->n_verts) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: triangle index out of range");
-    if (it != ctx->meshes.end()) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        it->second.release();
-    }
+    if (ctx->inFrame && !ctx->executed && !ctx->hDraws.empty())
+        return fail(ctx, T3D_E_STATE, "t3d_mesh_upload: draws of the open frame hold pointers into resident meshes (upload before t3d_frame_begin or after t3d_frame_execute)");
+    // The replacement is built completely first; the resident mesh is only released once nothing can fail any more, and
+    // every early return below frees what `m` has allocated so far.
     Mesh m;
+    struct MeshGuard { Mesh* m; ~MeshGuard() { if (m) m->release(); } } guard{&m};
     m.generation = generation;
     m.nVerts = d->n_verts; m.nVertsPad = std::max((d->n_verts + 3u) & ~3u, 4u); m.nTris = d->n_tris; m.nKeys = d->n_shape_keys;
     m.nTrisPad = std::max((d->n_tris + 3u) & ~3u, 4u);
@@ -329,11 +330,11 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
         CU(cudaMemsetAsync(m.keyW, 0, (size_t)m.nKeys * sizeof(float), s));
     }
     if (d->tri_sub_base || d->tri_sub_level || d->tri_n_levels || d->tri_max_span || d->tri_normal) {
-        if (!(d->tri_sub_base && d->tri_sub_level && d->tri_n_levels && d->tri_max_span && d->tri_normal)) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: auto-subdivision needs all five tri_* arrays"); }
-        if (d->weights) { m.release(); return fail(ctx, T3D_E_UNSUPPORTED, "t3d_mesh_upload: auto-subdivision of a skinned mesh (model.go:726 skips it)"); }
+        if (!(d->tri_sub_base && d->tri_sub_level && d->tri_n_levels && d->tri_max_span && d->tri_normal)) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: auto-subdivision needs all five tri_* arrays");
+        if (d->weights) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_mesh_upload: auto-subdivision of a skinned mesh (model.go:726 skips it)");
         const size_t t = d->n_tris;
         for (size_t i = 0; i < t; i++)
-            if (d->tri_sub_base[i] >= t || d->tri_sub_level[i] < -1 || d->tri_sub_base[i] > i) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: tri_sub_base / tri_sub_level out of range"); }
+            if (d->tri_sub_base[i] >= t || d->tri_sub_level[i] < -1 || d->tri_sub_base[i] > i) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: tri_sub_base / tri_sub_level out of range");
         // one block: [SubdivMesh | base 4t | span 4t | normal 12t | level t | nLevels t]
         const size_t off0 = 64, bytes = off0 + t * (4 + 4 + 12 + 1 + 1);
         std::vector<uint8_t> h(bytes, 0);
@@ -356,7 +357,7 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
     m.parts.resize(d->n_parts);
     for (uint32_t p = 0; p < d->n_parts; p++) {
         const t3d_part_range& pr = d->parts[p];
-        if (pr.tri_start > pr.tri_end || pr.tri_end > d->n_tris) { m.release(); return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: part triangle range out of bounds"); }
+        if (pr.tri_start > pr.tri_end || pr.tri_end > d->n_tris) return fail(ctx, T3D_E_INVALID, "t3d_mesh_upload: part triangle range out of bounds");
         PartInfo pi; pi.triStart = pr.tri_start; pi.triEnd = pr.tri_end; pi.a0 = 0; pi.nv = 0;
         if (pr.tri_end > pr.tri_start) {
             uint32_t lo = 0xFFFFFFFFu, hi = 0;
@@ -366,9 +367,11 @@ int t3d_mesh_upload(t3d_ctx* ctx, uint64_t mesh_id, uint32_t generation, const t
         }
         m.parts[p] = pi;
     }
-    // the source arrays are borrowed only for this call
+    // the source arrays are borrowed only for this call; the sync also retires every kernel that reads the old mesh
     CU(cudaStreamSynchronize(s));
-    ctx->meshes[mesh_id] = std::move(m);
+    guard.m = nullptr;
+    if (it != ctx->meshes.end()) { it->second.release(); it->second = std::move(m); }
+    else ctx->meshes[mesh_id] = std::move(m);
     return T3D_OK;
 }
 
@@ -389,6 +392,8 @@ int t3d_mesh_release(t3d_ctx* ctx, uint64_t mesh_id) {
     CU(cudaSetDevice(ctx->device));
     auto it = ctx->meshes.find(mesh_id);
     if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_mesh_release: unknown mesh");
+    if (ctx->inFrame && !ctx->executed && !ctx->hDraws.empty())
+        return fail(ctx, T3D_E_STATE, "t3d_mesh_release: draws of the open frame hold pointers into resident meshes");
     CU(cudaStreamSynchronize(ctx->stream));
     it->second.release();
     ctx->meshes.erase(it);
@@ -583,6 +588,7 @@ int t3d_skeleton_upload(t3d_ctx* ctx, uint64_t skeleton_id, const t3d_skeleton_d
         depth[b] = par < 0 ? 0 : (uint16_t)(depth[par] + 1);
         maxDepth = std::max<uint32_t>(maxDepth, depth[b]);
     }
+    if (ctx->inFrame && !ctx->executed && !ctx->poseCalls.empty()) return fail(ctx, T3D_E_STATE, "t3d_skeleton_upload: poses of the open frame are pending");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     Skeleton& S = ctx->skeletons[skeleton_id];
@@ -614,6 +620,7 @@ int t3d_skeleton_release(t3d_ctx* ctx, uint64_t skeleton_id) {
     if (!ctx) return T3D_E_INVALID;
     auto it = ctx->skeletons.find(skeleton_id);
     if (it == ctx->skeletons.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_skeleton_release: unknown skeleton");
+    if (ctx->inFrame && !ctx->executed && !ctx->poseCalls.empty()) return fail(ctx, T3D_E_STATE, "t3d_skeleton_release: poses of the open frame are pending");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (it->second.block) cudaFree(it->second.block);
@@ -634,6 +641,7 @@ int t3d_animation_upload(t3d_ctx* ctx, uint64_t animation_id, const t3d_animatio
             if (!(d->key_times[tr.first_key + k] >= d->key_times[tr.first_key + k - 1]))
                 return fail(ctx, T3D_E_INVALID, "t3d_animation_upload: keyframe times must be non-decreasing inside a track");
     }
+    if (ctx->inFrame && !ctx->executed && !ctx->poseCalls.empty()) return fail(ctx, T3D_E_STATE, "t3d_animation_upload: poses of the open frame are pending");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     Animation& A = ctx->animations[animation_id];
@@ -659,6 +667,7 @@ int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id) {
     if (!ctx) return T3D_E_INVALID;
     auto it = ctx->animations.find(animation_id);
     if (it == ctx->animations.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_animation_release: unknown animation");
+    if (ctx->inFrame && !ctx->executed && !ctx->poseCalls.empty()) return fail(ctx, T3D_E_STATE, "t3d_animation_release: poses of the open frame are pending");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (it->second.block) cudaFree(it->second.block);
@@ -1293,6 +1302,11 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     }
     out->index_list = ctx->hIndex.p;
 
+    // compact-depth frames (t3d_set_output_compact_depth) never wrote a depth list: the owner of the lists rebuilds it with
+    // t3d_expand_depth_list from the colour list and the depth scalars
+    const bool compactDepth = ctx->xColor != nullptr && ctx->xDepthScalar != nullptr;
+    if (download && compactDepth)
+        return fail(ctx, T3D_E_STATE, "t3d_frame_results: the frame emitted compact depth into an external target; use t3d_frame_results_device and t3d_expand_depth_list");
     if (download) {
         if (nVerts) {
             cudaEvent_t e0 = ctx->ev[7], e1 = ctx->ev[8];
@@ -1312,7 +1326,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
         out->normal_list = normals ? ctx->hNormal.p : nullptr;
         out->tri_ids = ctx->hTriIds.p;
     } else {
-        out->color_list = ctx->oColor; out->depth_list = ctx->oDepth;
+        out->color_list = ctx->oColor; out->depth_list = compactDepth ? nullptr : ctx->oDepth;
         out->normal_list = normals ? ctx->oNormal : nullptr;
         out->tri_ids = ctx->dTriIds.as<uint32_t>();
     }

@@ -709,7 +709,11 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         }
     }
     if (!RenderDepth)                                                      // camera.go:1460-1469
-        stableSort(solids, [](const renderPair& i, const renderPair& j) { if (i.order < j.order) return true; return i.depth > j.depth; });
+        // not a strict weak ordering once RenderOrder values differ (less(i, j) and less(j, i) can both hold), so the outcome
+        // is whatever Go's sort.SliceStable leaves: goStableSort replays it (std::stable_sort would be undefined behaviour)
+        goStableSort((int)solids.size(),
+                     [&](int i, int j) { if (solids[i].order < solids[j].order) return true; return solids[i].depth > solids[j].depth; },
+                     [&](int i, int j) { std::swap(solids[i], solids[j]); });
     stableSort(transparents, [](const renderPair& i, const renderPair& j) {   // camera.go:2050-2055
         if (i.order == j.order) return i.depth > j.depth;
         return i.order < j.order;
