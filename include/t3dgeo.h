@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 2      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew */
+#define T3D_ABI_VERSION 3      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points */
 
 enum {
     T3D_OK            =  0,
@@ -338,6 +338,16 @@ int t3d_expand_depth_list(t3d_ctx* ctx, const t3d_vertex* color, const float* de
 typedef struct t3d_shared_handle { unsigned char bytes[64]; } t3d_shared_handle;
 int t3d_shared_alloc(t3d_ctx* ctx, uint64_t bytes, void** device_ptr, t3d_shared_handle* handle);
 int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device_ptr);
+
+/* ---- lighting precision ---------------------------------------------------------------------------- */
+/* Per-vertex lighting (light.go:191-258, 332-360) runs by default with single-instruction reciprocals and fused
+ * multiply-adds: lit colours match the reference within 1/255 (BASELINE.json north_star; measured maximum in
+ * profiles/README.md), everything else -- positions, the post-cull triangle set, depths, bins, order, depth colours --
+ * stays bit-exact, including the two cut-off DECISIONS of a point light (range, 1/d*energy < 0.001).  enabled = 1
+ * switches to the reference's arithmetic operation by operation (IEEE division and square root, no contraction):
+ * colours bit-exact, the fused vertex kernel about 2x slower.  Not callable while a frame is open (T3D_E_STATE).
+ * Replaces: nothing in the reference (it has one precision); this is the knob SURVEY.md A.8 allows. */
+int t3d_set_exact_lighting(t3d_ctx* ctx, int enabled);
 
 /* ---- introspection (tests, profiling) ------------------------------------------------------------ */
 /* Stage timings put a CUDA event between the kernels of a frame, which serialises them; by default

@@ -119,6 +119,7 @@ struct t3d_ctx {
     // frame staging (pinned)
     bool inFrame = false, executed = false, haveResults = false;
     bool stageTimings = false, stagesTimed = false;
+    bool exactLighting = false;         // t3d_set_exact_lighting: the reference's lighting arithmetic operation by operation (bit-exact colours)
     bool forceFullUpload = false;       // t3d_debug_force_full_upload: never pack affine matrices (exercises the 16-float paths)
     FrameConst fc;
     // what the host itself needs to remember about a submitted draw (the device rebuilds the full DrawRec from hSlim + hTmpl)
@@ -157,6 +158,7 @@ struct t3d_ctx {
     cudaStream_t copyStream = nullptr; cudaEvent_t evFork = nullptr; std::vector<cudaEvent_t> evChunk;     // chunked staging of very large frames
     DevBuf dClip, dClipXY, dLight, dWpos, dUnbill, dTnrm;     // dClip: {X/w, Y/w, Z, W} per vertex; dClipXY: {X, Y}
     DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
+    DevBuf dTileCtr;        // k_vertex's tile counters (one per vertex-tile class), zeroed by k_prep_draws every frame
     DevBuf dColor, dDepth, dNormal, dTriIds;
     // external output target (t3d_set_output_target): the emit kernel writes the lists there -- another GPU's
     // memory over NVLink, or an interop buffer of the rasteriser -- instead of into dColor / dDepth / dNormal
@@ -257,7 +259,7 @@ void t3d_destroy(t3d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame, &ctx->dStage,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
-                      &ctx->dCount, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
+                      &ctx->dCount, &ctx->dTileCtr, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
     ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release();
@@ -763,6 +765,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         memcpy(R.worldRot, in.world_rotation, 64);
         memcpy(R.color, in.color, 16);
         R.srcW = in.src_w; R.srcH = in.src_h; R.maxSpan = m.maxSpan;
+        R.nBones = (flags & T3D_DRAW_SKINNED) ? m.maxJoint + 1 : 0;
         if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.total; ctx->anyLit = true; }
         if (flags & T3D_DRAW_SKINNED) ctx->anySkinned = true;
         if (flags & T3D_DRAW_DEPTH_UNBILLBOARDED) ctx->anyUnbill = true;
@@ -938,6 +941,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     // arenas
     CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
     CU(ctx->dStats.ensure(sizeof(DrawStat) * nDraws));
+    CU(ctx->dTileCtr.ensure(64));
     CU(ctx->dClip.ensure(16ull * std::max(totalV, 4u)));
     CU(ctx->dClipXY.ensure(8ull * std::max(totalV, 4u)));
     CU(ctx->dLight.ensure(16ull * std::max(ctx->anyLit ? totalV : 4u, 4u)));
@@ -1173,14 +1177,14 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                               (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
                               hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
                               ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
-                              reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused, b0, b1 - b0, b0 == 0);
+                              reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused, b0, b1 - b0, b0 == 0, ctx->dTileCtr.as<uint32_t>());
             if (b0) ctx->launches += 1;
             b0 = b1;
         }
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};
-    launch_vertex(s, pdl, ctx->pDraws, ctx->pVbase, ctx->pVClass, nVClass, totalV, ctx->fc,
+    launch_vertex(s, pdl, ctx->exactLighting, ctx->pDraws, ctx->pVbase, ctx->pVClass, nVClass, ctx->dTileCtr.as<uint32_t>(), totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 1 + (nVClass[0] ? 1 : 0) + (nVClass[1] ? 1 : 0) + (nVClass[2] ? 1 : 0);
@@ -1449,6 +1453,13 @@ int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matri
 int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled) {
     if (!ctx) return T3D_E_INVALID;
     ctx->forceFullUpload = enabled != 0;
+    return T3D_OK;
+}
+
+int t3d_set_exact_lighting(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    if (ctx->inFrame && !ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_set_exact_lighting: a frame is open");
+    ctx->exactLighting = enabled != 0;
     return T3D_OK;
 }
 

@@ -109,7 +109,7 @@ struct __align__(16) DrawRec {
     float color[4];
     float srcW, srcH;
     float maxSpan;
-    float pad1;
+    uint32_t nBones;            // skinned draws: bones the mesh's joints reach (max joint + 1); k_vertex stages that many matrices
     // ---- derived on the device (model.go:616-708) ----
     float mvp[16];              // base * vp (static); skinned draws use FrameConst.vp
     float unbill[4];            // column 2 of modelTransform * vp       model.go:702, 801

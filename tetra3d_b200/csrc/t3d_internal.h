@@ -25,7 +25,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
                        uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
-                       const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk);
+                       const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk, uint32_t* tileCtr);
 #ifndef T3D_PREP_POSE_BATCHES
 #define T3D_PREP_POSE_BATCHES 4
 #endif
@@ -33,8 +33,8 @@ static const uint32_t PREP_POSE_BATCHES = T3D_PREP_POSE_BATCHES;       // t3d_su
 static const size_t PREP_POSE_SMEM = 40 * 1024;
 static const int PREP_WINDOW_BLOCKS = 16, PREP_WINDOW_DRAWS = 64;     // k_prep_draws: blocks whose template windows travel as kernel parameters
 // tileLists / nTilesOf are indexed by vertex-tile class: 0 generic, 1 static fast, 2 skinned fast (t3d_kernels.cu: K1_*)
-void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
-                   const uint4* const tileLists[3], const uint32_t nTilesOf[3],
+void launch_vertex(cudaStream_t s, bool pdl, bool exactLighting, const DrawRec* draws, const uint32_t* vbase,
+                   const uint4* const tileLists[3], const uint32_t nTilesOf[3], uint32_t* tileCtr /* [4] zeroed by k_prep_draws */,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel

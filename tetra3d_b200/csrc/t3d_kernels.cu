@@ -89,6 +89,7 @@ struct PrepFrame {
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
     uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
     uint32_t copyEnd;               // this launch's blocks [nPrepBlocks, copyEnd) copy (behind the pose blocks of k_prep_draws<true>)
+    uint32_t* tileCtr;              // first launch of the frame: k_vertex's tile counters, zeroed here
     uint32_t blockBase;             // first 64-draw block of this launch: a large staged frame is prepared in chunks, each behind its slice's copy
 };
 // Bone poses riding along (t3d_pose.cuh): blocks [poseBlock[i], poseBlock[i + 1]) of the grid evaluate batch i.  Only frames
@@ -107,6 +108,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
              LightU* __restrict__ lightsU, DrawStat* __restrict__ stats, const __grid_constant__ PrepPoses<POSES> pp) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
+    if (pf.tileCtr && blockIdx.x == 0 && threadIdx.x < 4) pf.tileCtr[threadIdx.x] = 0;      // k_vertex's tile counters (one per class)
     // Pose blocks come FIRST in the grid (k_prep_draws<true>): they start at once and their float64 arithmetic overlaps the
     // PCIe round trips of the prep blocks, instead of trailing them as a second wave.
     uint32_t bid = blockIdx.x;
@@ -405,8 +407,26 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
                     }
                     const Vec3 wp = skinned ? lp : v3_add(m4_multvec(r, lp), invPS);   // light.go:183-187
                     U.wpos[0] = wp.X; U.wpos[1] = wp.Y; U.wpos[2] = wp.Z;
+                    // default (approximate) lighting only: colour * energy * 2 premultiplied, and the distance beyond which
+                    // `1 / d * energy < 0.001` holds (light.go:205-210) -- fields a point light does not otherwise use
+                    U.fwd[0] = L.color[0] * L.energy * 2.0f; U.fwd[1] = L.color[1] * L.energy * 2.0f; U.fwd[2] = L.color[2] * L.energy * 2.0f;
+                    U.pad = __float_as_uint(L.energy * 1000.0f);
                 } else if (L.type == T3D_LIGHT_VOLUME) {
                     if ((flags & T3D_DRAW_HAS_MATERIAL) && R.lvMode == T3D_LV_OFF) U.type = LIGHT_SKIP;   // light.go:671-673
+                } else if (L.type == T3D_LIGHT_DIRECTIONAL) {
+                    // default lighting only: dot(n * workingModelRotation, forward) == dot(n, g) + c0 with g = rotation rows . forward,
+                    // folded per draw instead of per vertex (light.go:342-349); parked in wpos / range, which a sun does not use
+                    const uint8_t lm = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
+                    const float fx = L.forward[0], fy = L.forward[1], fz = L.forward[2];
+                    if (lm == T3D_LIGHTING_FIXED_NORMALS) { U.wpos[0] = U.wpos[1] = U.wpos[2] = 0; U.range = fx * fx + fy * fy + fz * fz; }
+                    else if (skinned) { U.wpos[0] = fx; U.wpos[1] = fy; U.wpos[2] = fz; U.range = 0; }
+                    else {
+                        const float* s = R.worldRot;        // the sun's workingModelRotation by now (role 3 above)
+                        U.wpos[0] = s[0] * fx + s[1] * fy + s[2] * fz; U.wpos[1] = s[4] * fx + s[5] * fy + s[6] * fz;
+                        U.wpos[2] = s[8] * fx + s[9] * fy + s[10] * fz; U.range = s[12] * fx + s[13] * fy + s[14] * fz;
+                    }
+                } else if (L.type == T3D_LIGHT_AMBIENT) {
+                    U.fwd[0] = L.color[0] * L.energy; U.fwd[1] = L.color[1] * L.energy; U.fwd[2] = L.color[2] * L.energy;
                 }
                 lightsU[R.lightU + i] = U;
             }
@@ -527,25 +547,28 @@ __device__ __noinline__ float3 light_volume(const DrawRec* __restrict__ Rp, cons
 
 // Model.skinVertex (model.go:559-596) for one vertex.
 struct SkinAcc { float4 k0, k1, k2, k3; bool done; };
-// One influence: skip weight 0, take the bone alone on weight 1 (and stop), else Scale then Add (matrix.go:639-661).
-__device__ __forceinline__ void skin_influence(SkinAcc& A, const float* __restrict__ bones, float weightPerc, uint32_t joint, bool present) {
+// One influence: skip weight 0, take the bone alone on weight 1 (and stop), else Scale then Add (matrix.go:639-661).  `U`
+// hands out the draw's bone matrices row by row: from the frame's bone arena, or from the copy the tile's producer staged in
+// shared memory.
+template <class Uniforms>
+__device__ __forceinline__ void skin_influence(SkinAcc& A, const Uniforms& U, float weightPerc, uint32_t joint, bool present) {
     if (A.done || !present || weightPerc == 0.0f) return;
-    const float4* B = reinterpret_cast<const float4*>(bones + 16 * (size_t)joint);
-    const float4 r0 = __ldg(B), r1 = __ldg(B + 1), r2 = __ldg(B + 2), r3 = __ldg(B + 3);
+    const float4 r0 = U.bone(joint, 0), r1 = U.bone(joint, 1), r2 = U.bone(joint, 2), r3 = U.bone(joint, 3);
     if (weightPerc == 1.0f) { A.k0 = r0; A.k1 = r1; A.k2 = r2; A.k3 = r3; A.done = true; return; }
     A.k0.x = A.k0.x + r0.x * weightPerc; A.k0.y = A.k0.y + r0.y * weightPerc; A.k0.z = A.k0.z + r0.z * weightPerc; A.k0.w = A.k0.w + r0.w * weightPerc;
     A.k1.x = A.k1.x + r1.x * weightPerc; A.k1.y = A.k1.y + r1.y * weightPerc; A.k1.z = A.k1.z + r1.z * weightPerc; A.k1.w = A.k1.w + r1.w * weightPerc;
     A.k2.x = A.k2.x + r2.x * weightPerc; A.k2.y = A.k2.y + r2.y * weightPerc; A.k2.z = A.k2.z + r2.z * weightPerc; A.k2.w = A.k2.w + r2.w * weightPerc;
     A.k3.x = A.k3.x + r3.x * weightPerc; A.k3.y = A.k3.y + r3.y * weightPerc; A.k3.z = A.k3.z + r3.z * weightPerc; A.k3.w = A.k3.w + r3.w * weightPerc;
 }
-__device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4 w, ushort4 j, int n,
+template <class Uniforms>
+__device__ __forceinline__ void skin_one(const Uniforms& U, float4 w, ushort4 j, int n,
                                          Vec3 p, Vec3 nIn, Vec3& pOut, Vec3& nOut) {
     SkinAcc A;
     A.k0 = make_float4(0, 0, 0, 0); A.k1 = A.k0; A.k2 = A.k0; A.k3 = A.k0; A.done = false;
-    skin_influence(A, bones, w.x, j.x, n > 0);
-    skin_influence(A, bones, w.y, j.y, n > 1);
-    skin_influence(A, bones, w.z, j.z, n > 2);
-    skin_influence(A, bones, w.w, j.w, n > 3);
+    skin_influence(A, U, w.x, j.x, n > 0);
+    skin_influence(A, U, w.y, j.y, n > 1);
+    skin_influence(A, U, w.z, j.z, n > 2);
+    skin_influence(A, U, w.w, j.w, n > 3);
     const float4 k0 = A.k0, k1 = A.k1, k2 = A.k2, k3 = A.k3;
     pOut.X = k0.x * p.X + k1.x * p.Y + k2.x * p.Z + k3.x;                  // MultVec, matrix.go:619
     pOut.Y = k0.y * p.X + k1.y * p.Y + k2.y * p.Z + k3.y;
@@ -558,37 +581,118 @@ __device__ __forceinline__ void skin_one(const float* __restrict__ bones, float4
 
 // Tunables (see profiles/README.md for the measurements behind the defaults).
 #ifndef T3D_K1_MINBLOCKS
-#define T3D_K1_MINBLOCKS 4      // resident blocks per SM the generic kernel's register allocation aims for
+#define T3D_K1_MINBLOCKS 3      // resident blocks per SM the generic kernel's register allocation aims for
 #endif
-static const int VERTEX_BLOCK = 256;
+static const int VERTEX_BLOCK = 256;                        // consumer threads of a k_vertex block == vertex slots per tile
+static const int VERTEX_THREADS = VERTEX_BLOCK + 32;        // + the producer warp
+#ifndef T3D_VERTEX_STAGES
+#define T3D_VERTEX_STAGES 2
+#endif
+static const int VERTEX_STAGES = T3D_VERTEX_STAGES;         // tiles in flight per block
 static const int VERTEX_SMEM_LIGHTS = 16;       // light lists up to this long are staged in shared memory
+static const int VERTEX_SMEM_BONES = 64;        // skinned tiles: armatures of up to this many bones are staged in shared memory
 static_assert(VERTEX_BLOCK == (int)VERTEX_TILE, "t3d_internal.h: VERTEX_TILE must be the slots one k_vertex block covers");
 
-// Everything one vertex needs from its draw: either the DrawRec / LightU records in global memory, or the
-// block's staged copy in shared memory (rows 0-3 mvp, 4-7 the sun's workingModelRotation, 8.. the LightU list).
+// Everything one vertex needs from its draw: either the DrawRec / LightU records and the mesh / bone arrays in global
+// memory, or the stage the block's producer warp filled in shared memory (mvp rows 0-3, the sun's workingModelRotation rows
+// 4-7, the LightU list from 8; weights / joints per tile slot; the draw's bone matrices).
 struct UniformsGlobal {
     const float* mvpP; const float* sunP; const float4* lightP;
+    const float* wgtP; const uint16_t* jntP; const float* bonesP; uint32_t mv;
     __device__ __forceinline__ float4 mvp(int i) const { return ldg4(mvpP + 4 * i); }
     __device__ __forceinline__ float4 sun(int i) const { return ldg4(sunP + 4 * i); }
     __device__ __forceinline__ float4 light(uint32_t i) const { return __ldg(lightP + i); }
+    __device__ __forceinline__ uint32_t lightType(uint32_t i) const { return __ldg(reinterpret_cast<const uint32_t*>(lightP + i)); }
+    __device__ __forceinline__ float4 weights() const { return ldg4(wgtP + 4 * (size_t)mv); }
+    __device__ __forceinline__ ushort4 joints() const { return __ldg(reinterpret_cast<const ushort4*>(jntP + 4 * (size_t)mv)); }
+    __device__ __forceinline__ float4 bone(uint32_t joint, int row) const { return __ldg(reinterpret_cast<const float4*>(bonesP + 16 * (size_t)joint) + row); }
 };
 struct UniformsShared {
-    const float4* s;
+    const float4* s; const float4* sWgt; const ushort4* sJnt; const float4* sBones; uint32_t ti;
     __device__ __forceinline__ float4 mvp(int i) const { return s[i]; }
     __device__ __forceinline__ float4 sun(int i) const { return s[4 + i]; }
     __device__ __forceinline__ float4 light(uint32_t i) const { return s[8 + i]; }
+    __device__ __forceinline__ uint32_t lightType(uint32_t i) const { return *reinterpret_cast<const uint32_t*>(s + 8 + i); }
+    __device__ __forceinline__ float4 weights() const { return sWgt[ti]; }
+    __device__ __forceinline__ ushort4 joints() const { return sJnt[ti]; }
+    __device__ __forceinline__ float4 bone(uint32_t joint, int row) const { return sBones[4 * joint + row]; }
 };
 
 // One vertex: shape keys, skinning, clip transform, optional outputs, lighting.  P / N arrive loaded.
 // MODE K1_STATIC: the draw is static, has no shape keys, no unbillboarded depth and no volume light, and the frame has
-// no vertex snapping and no normal pass -- the rare paths are compiled out, which frees a quarter of the registers
-// (k_vertex<K1_STATIC> runs 6 blocks per SM without spilling where the generic kernel runs 4).  MODE K1_SKINNED: the
-// same exclusions for a skinned draw.  MODE K1_GENERIC: everything.
+// no vertex snapping and no normal pass -- the rare paths are compiled out, which frees a quarter of the registers.
+// MODE K1_SKINNED: the same exclusions for a skinned draw.  MODE K1_GENERIC: everything.
 enum { K1_GENERIC = 0, K1_STATIC = 1, K1_SKINNED = 2 };
-template <int MODE, class Uniforms>
-__device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const Uniforms U, const FrameConst& fc,
+
+// Single-instruction reciprocal / reciprocal square root (MUFU.RCP / MUFU.RSQ, <= 2 ulp) for the lighting arithmetic of the
+// default build: lit colours only have to match within 1/255 (BASELINE.json north_star), whereas IEEE-exact
+// division and square root expand to ~12 instructions each plus a slow-path branch -- five divisions and a root per point
+// light (light.go:191-258) were two thirds of k_vertex's instructions.  Nothing that feeds a cull decision, a depth key, a bin
+// or a position uses these.
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// PointLight.VertexLight (light.go:191-258) with approximate reciprocals and fused multiply-adds; returns the factor the
+// light's premultiplied colour (colour * energy * 2, from k_prep_draws) is scaled by (0: no contribution).  The two cut-offs are
+// DECISIONS, not continuous quantities (a vertex on the wrong side of `1 / d * energy < 0.001` changes by up to 0.02), so they
+// are taken exactly as the reference takes them: the range test needs no division, and the energy test compares the (exact)
+// squared distance with energy * 1000 and falls back to the IEEE division inside a guard band of 4e-6 around it (practically
+// never).
+template <bool PLAIN>     // PLAIN: LightingModeDefault (the normal is the vertex normal, one-sided)
+__device__ __forceinline__ float point_light_factor_fast(float wx, float wy, float wz, float range, float range2, float cutoff, float energy,
+                                                         Vec3 P, Vec3 N, uint8_t lightingMode) {
+    const float dx = wx - P.X, dy = wy - P.Y, dz = wz - P.Z;
+    const float d2 = dx * dx + dy * dy + dz * dz;               // -fmad=false: the reference's distance, bit for bit
+    bool keep;
+    if (range > 0) keep = !(d2 > range2);
+    else {
+        keep = !(d2 > cutoff);
+        if (!(fabsf(d2 - cutoff) > cutoff * 4e-6f)) keep = !(1.0f / d2 * energy < 0.001f);      // also NaN
+    }
+    const float rl = rsqrt_fast(d2);
+    float ndl = __fmaf_rn(N.Z, dz, __fmaf_rn(N.Y, dy, N.X * dx));
+    if (!PLAIN && lightingMode == T3D_LIGHTING_FIXED_NORMALS) ndl = d2 * rl;
+    float diffuse = ndl * rl;
+    if (!PLAIN && lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuse = fabsf(diffuse);
+    float f = diffuse * rcp_fast(__fmaf_rn(0.1f, d2, 1.0f));
+    if (range2 > 0) f *= __saturatef((range2 - d2) * rcp_fast(d2));
+    // Unit (vector.go:258-266) leaves vectors shorter than 1e-8 as they are: their contribution is below 1e-7
+    if (!(keep && d2 >= 1e-16f && diffuse > 0)) f = 0.0f;
+    return f;
+}
+
+// The light loop of the fast classes with the default lighting arithmetic: per light one type word and the pre-folded fields
+// k_prep_draws left in the LightU record (premultiplied colours, the energy cut-off distance, the sun's forward in model space).
+template <bool PLAIN, class Uniforms>
+__device__ __forceinline__ float3 light_loop_fast(const Uniforms& U, uint32_t nL, Vec3 P, Vec3 N, uint8_t lightingMode) {
+    float lr = 0, lg = 0, lb = 0;
+    for (uint32_t li = 0; li < nL; li++) {
+        const uint32_t type = U.lightType(4 * li);
+        if (type == T3D_LIGHT_POINT) {                              // light.go:191-258
+            const float4 q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2), q3 = U.light(4 * li + 3);
+            const float f = point_light_factor_fast<PLAIN>(q1.y, q1.z, q1.w, q2.x, q2.y, q3.w, q1.x, P, N, lightingMode);
+            lr = __fmaf_rn(q2.z, f, lr); lg = __fmaf_rn(q2.w, f, lg); lb = __fmaf_rn(q3.x, f, lb);
+        } else if (type == T3D_LIGHT_DIRECTIONAL) {                 // light.go:332-360
+            const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
+            float f = __fmaf_rn(N.Z, q1.w, __fmaf_rn(N.Y, q1.z, __fmaf_rn(N.X, q1.y, q2.x)));
+            if (!PLAIN && lightingMode == T3D_LIGHTING_DOUBLE_SIDED) f = fabsf(f);
+            f = fmaxf(f, 0.0f) * q1.x;                              // diffuseFactor <= 0 contributes nothing
+            lr = __fmaf_rn(q0.y, f, lr); lg = __fmaf_rn(q0.z, f, lg); lb = __fmaf_rn(q0.w, f, lb);
+        } else if (type == T3D_LIGHT_AMBIENT) {                     // light.go:110-120
+            const float4 q2 = U.light(4 * li + 2), q3 = U.light(4 * li + 3);
+            lr += q2.z; lg += q2.w; lb += q3.x;
+        }
+    }
+    return make_float3(lr, lg, lb);
+}
+
+// APPROX: lighting with approximate reciprocals (colours within 1/255, the default); !APPROX: the reference's arithmetic
+// operation by operation (bit-exact colours; t3d_set_exact_lighting).  Positions, depths and everything the cull and the
+// sort read are exact in both.
+template <int MODE, bool APPROX, class Uniforms>
+__device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const uint32_t nL, const uint8_t lightingMode, const Uniforms U, const FrameConst& fc,
                                              const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
-                                             const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
+                                             const LightU* __restrict__ lightsU, const VolumeU* __restrict__ vols,
                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
                                              float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     constexpr bool FAST = MODE != K1_GENERIC;       // shape keys, snapping, unbillboarded depth, normal pass, volume lights compiled out
@@ -610,11 +714,11 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
 
     // skinning (model.go:760-775): positions and normals become world-space
     if (MODE != K1_STATIC && skinned) {
-        const float4 w = ldg4(R.wgt + 4 * (size_t)mv);
-        const ushort4 j = __ldg(reinterpret_cast<const ushort4*>(R.jnt + 4 * (size_t)mv));
+        const float4 w = U.weights();
+        const ushort4 j = U.joints();
         const int n = R.ninf ? (int)__ldg(R.ninf + mv) : 4;
         Vec3 po, no;
-        skin_one(bones + 16 * (size_t)R.boneOffset, w, j, n, P, N, po, no);
+        skin_one(U, w, j, n, P, N, po, no);
         P = po; N = no;
         wposOut[slot] = make_float4(po.X, po.Y, po.Z, 0.0f);
     }
@@ -667,13 +771,21 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
 
     // per-vertex lighting (camera.go:1610-1644): start at (0,0,0,1), add every light of the draw's list
     float lr = 0, lg = 0, lb = 0;
-    const uint8_t lightingMode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
-    const uint32_t nL = R.lightCount;
+    if constexpr (APPROX && FAST) {
+        // (the sun's folded forward assumes the mode k_prep_draws saw, which is this one)
+        const float3 acc = lightingMode == T3D_LIGHTING_DEFAULT ? light_loop_fast<true>(U, nL, P, N, lightingMode) : light_loop_fast<false>(U, nL, P, N, lightingMode);
+        lightOut[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        return;
+    }
     for (uint32_t li = 0; li < nL; li++) {
         const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
         const uint32_t type = __float_as_uint(q0.x);
         const float cR = q0.y, cG = q0.z, cB = q0.w, energy = q1.x;
-        if (type == T3D_LIGHT_POINT) {                                  // light.go:191-258
+        if (APPROX && type == T3D_LIGHT_POINT) {
+            const float4 q3 = U.light(4 * li + 3);
+            const float f = point_light_factor_fast<false>(q1.y, q1.z, q1.w, q2.x, q2.y, q3.w, energy, P, N, lightingMode);
+            lr = __fmaf_rn(q2.z, f, lr); lg = __fmaf_rn(q2.w, f, lg); lb = __fmaf_rn(q3.x, f, lb);
+        } else if (type == T3D_LIGHT_POINT) {                           // light.go:191-258
             const Vec3 wp = v3(q1.y, q1.z, q1.w);
             const float range = q2.x, range2 = q2.y;
             Vec3 vertNormal = N;
@@ -699,9 +811,22 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
             else if (skinned) normal = N;
             else {
                 const float4 s0 = U.sun(0), s1 = U.sun(1), s2 = U.sun(2), s3 = U.sun(3);
-                normal.X = s0.x * N.X + s1.x * N.Y + s2.x * N.Z + s3.x;
-                normal.Y = s0.y * N.X + s1.y * N.Y + s2.y * N.Z + s3.y;
-                normal.Z = s0.z * N.X + s1.z * N.Y + s2.z * N.Z + s3.z;
+                if (APPROX) {
+                    normal.X = __fmaf_rn(s2.x, N.Z, __fmaf_rn(s1.x, N.Y, __fmaf_rn(s0.x, N.X, s3.x)));
+                    normal.Y = __fmaf_rn(s2.y, N.Z, __fmaf_rn(s1.y, N.Y, __fmaf_rn(s0.y, N.X, s3.y)));
+                    normal.Z = __fmaf_rn(s2.z, N.Z, __fmaf_rn(s1.z, N.Y, __fmaf_rn(s0.z, N.X, s3.z)));
+                } else {
+                    normal.X = s0.x * N.X + s1.x * N.Y + s2.x * N.Z + s3.x;
+                    normal.Y = s0.y * N.X + s1.y * N.Y + s2.y * N.Z + s3.y;
+                    normal.Z = s0.z * N.X + s1.z * N.Y + s2.z * N.Z + s3.z;
+                }
+            }
+            if (APPROX) {
+                float f = __fmaf_rn(normal.Z, fwd.Z, __fmaf_rn(normal.Y, fwd.Y, normal.X * fwd.X));
+                if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) f = fabsf(f);
+                f = fmaxf(f, 0.0f) * energy;        // diffuseFactor <= 0 contributes nothing
+                lr = __fmaf_rn(cR, f, lr); lg = __fmaf_rn(cG, f, lg); lb = __fmaf_rn(cB, f, lb);
+                continue;
             }
             float diffuseFactor = v3_dot(normal, fwd);
             if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuseFactor = fabsf(diffuseFactor);
@@ -719,93 +844,209 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
     lightOut[slot] = make_float4(lr, lg, lb, 1.0f);
 }
 
-// One vertex per thread, VERTEX_BLOCK consecutive slots per block; blockIdx indexes a list of vertex tiles.  The
-// host sorts the frame's tiles into three lists: tiles whose draws are all of one fast class (see shade_vertex) go to
-// k_vertex<K1_STATIC> or k_vertex<K1_SKINNED>, everything else to k_vertex<K1_GENERIC>.  When the block lies inside one draw (any draw of more than
-// a few hundred vertices) the draw's matrices and light list are staged in shared memory once; blocks that
-// straddle draws look their draw up per vertex.
-#ifndef T3D_K1_FAST_MINBLOCKS
-#define T3D_K1_FAST_MINBLOCKS 6
-#endif
-#ifndef T3D_K1_SKINNED_MINBLOCKS
-#define T3D_K1_SKINNED_MINBLOCKS 5
-#endif
-template <int MODE>
-__device__ __forceinline__ void vertex_tile(float4* sU, const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
-         const uint4* __restrict__ tileList, uint32_t totalV, const FrameConst& fc,
-         const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
-         float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
-         float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    // one load tells the block everything about its tile: {tile, first draw, first draw of the next tile, end of the first
-    // draw's vertices} (the host builds the lists from its vertex-tile table)
-    const uint4 entry = __ldg(&tileList[blockIdx.x]);
-    const uint32_t base = entry.x * (uint32_t)VERTEX_BLOCK;
-    const uint32_t slot = base + threadIdx.x;
-    const uint32_t dLo = entry.y, dHi = entry.z;
-    const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
-    // dHi is the draw of the first slot of the NEXT tile, so dLo == dHi covers this whole tile; otherwise the
-    // tile is still uniform when the next draw starts at or after its end
-    bool staged = dLo == dHi || entry.w >= end;
-    if (staged) {
-        const DrawRec& R = draws[dLo];
-        const uint32_t flags = R.flags;
-        const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
-        staged = nL <= (uint32_t)VERTEX_SMEM_LIGHTS;
-        if (staged) {
-            // the vertex's own loads go first so they overlap the staging
-            const uint32_t mv = R.a0 + (slot - R.vbase);
-            const uint32_t vs = R.vstride;
-            Vec3 P = v3(0, 0, 0), N = v3(0, 0, 0);
-            if (slot < end) {
-                const float* pp = R.pos + mv;
-                P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs));
-                if (flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) {
-                    const float* np = R.nrm + mv;
-                    N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
-                }
-            }
-            if (threadIdx.x < 4) sU[threadIdx.x] = ldg4(R.mvp + 4 * threadIdx.x);
-            else if (threadIdx.x < 8) sU[threadIdx.x] = ldg4(R.worldRot + 4 * (threadIdx.x - 4));
-            else if (threadIdx.x < 8 + 4 * nL) sU[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(lightsU + R.lightU) + (threadIdx.x - 8));
-            __syncthreads();
-            if (slot >= end) return;
-            UniformsShared U; U.s = sU;
-            shade_vertex<MODE>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
-            return;
-        }
+// ---- mbarrier / bulk-copy plumbing of the k_vertex pipeline -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);        // a waiting warp must not eat the issue slots of the warps that shade
     }
-    if (slot >= end) return;
-    const uint32_t d = find_draw(vbase, dLo, dHi, slot);
-    const DrawRec& R = draws[d];
-    const uint32_t flags = R.flags;
-    const uint32_t mv = R.a0 + (slot - R.vbase);
-    const uint32_t vs = R.vstride;
-    const float* pp = R.pos + mv;
-    Vec3 P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs)), N = v3(0, 0, 0);
-    if (flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) {
-        const float* np = R.nrm + mv;
-        N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
-    }
-    UniformsGlobal U;
-    U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
-    shade_vertex<MODE>(R, flags, U, fc, slot, mv, P, N, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+}
+// global -> shared bulk copy by the copy engine of the SM (TMA, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// One stage of the pipeline: what the producer warp fetches for one tile.
+struct __align__(16) VStageDesc {
+    uint32_t base, end;         // slots [base, end) of the vertex arena
+    uint32_t dLo, dHi;          // draw of the first slot; draw of the first slot of the next tile
+    uint32_t staged;            // 1: the tile lies inside draw dLo and its inputs are in this stage; 0: consumers load for themselves
+    uint32_t mv0;               // mesh vertex of slot `base` (staged tiles)
+    uint32_t flags;             // staged tiles: the draw's flags, light count and lighting mode (what every vertex would otherwise
+    uint32_t nLmode;            //   fetch from the draw record): lightCount | lightingMode << 16; NO_TILE in `base`: the list is exhausted
+};
+static const uint32_t NO_TILE = 0xFFFFFFFFu;
+template <bool SKIN> struct __align__(128) VStage {
+    float4 U[8 + 4 * VERTEX_SMEM_LIGHTS];       // mvp | sun rotation | LightU list
+    float pos[3][VERTEX_BLOCK];
+    float nrm[3][VERTEX_BLOCK];
+    VStageDesc desc;
+};
+template <> struct __align__(128) VStage<true> {
+    float4 U[8 + 4 * VERTEX_SMEM_LIGHTS];
+    float pos[3][VERTEX_BLOCK];
+    float nrm[3][VERTEX_BLOCK];
+    float4 wgt[VERTEX_BLOCK];
+    ushort4 jnt[VERTEX_BLOCK];
+    float4 bones[4 * VERTEX_SMEM_BONES];
+    VStageDesc desc;
+};
+
+// k_vertex: persistent, warp-specialised, TMA-fed.  The host sorts the frame's vertex tiles (256 consecutive arena slots)
+// into three lists: tiles whose draws are all of one fast class (see shade_vertex) go to k_vertex<K1_STATIC> or
+// k_vertex<K1_SKINNED>, everything else to k_vertex<K1_GENERIC>.  A launch covers its list with ONE wave of blocks (at most
+// SMs x resident blocks) that take tiles off the list through an atomic counter until it is exhausted: no tail wave, and an SM
+// that falls behind (or starts late) simply takes fewer tiles.
+//   producer warp (one elected lane): per tile, reads the entry and the draw's record, and -- when the tile lies inside one
+//     draw with a stageable light list -- has the copy engine fetch the tile's position / normal plane runs (3 + 3 x 1 KB),
+//     skin weights / joints and the draw's bone matrices, mvp, sun rotation and LightU list into the stage (cp.async.bulk,
+//     completion counted on the stage's mbarrier); it runs up to VERTEX_STAGES tiles ahead of the consumers, so the
+//     entry -> record -> data dependency chain and the HBM latency are off the shading warps' critical path.
+//   consumer warps (8 x 32 threads, one vertex each): wait for the stage, shade from shared memory, release the stage.
+// Tiles that straddle draws (small meshes packed back to back) are flagged unstaged: the consumers look their draw up per
+// vertex and load for themselves, as before.
+#ifndef T3D_K1_FAST_MINBLOCKS
+#define T3D_K1_FAST_MINBLOCKS 5
+#endif
+#ifndef T3D_K1_SKINNED_MINBLOCKS
+#define T3D_K1_SKINNED_MINBLOCKS 4
+#endif
 // `second`: this launch directly follows another k_vertex launch of the frame.  They are independent (disjoint
 // tiles) and all only need k_prep_draws, which has completed by the time a later launch's blocks can start (the
 // first launch's blocks call pdl_launch() after their own pdl_wait()).  So a later launch starts shading at
 // once and waits for its predecessor at its END, which keeps "this kernel complete => every earlier kernel complete".
-template <int MODE>
-__global__ void __launch_bounds__(VERTEX_BLOCK, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
+template <int MODE, bool APPROX>
+__global__ void __launch_bounds__(VERTEX_THREADS, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
 k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
-         const uint4* __restrict__ tileList, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
+         const uint4* __restrict__ tileList, uint32_t nTiles, uint32_t* __restrict__ tileCtr, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
-    __shared__ float4 sU[8 + 4 * VERTEX_SMEM_LIGHTS];
+    constexpr bool SKIN = MODE != K1_STATIC;
+    __shared__ VStage<SKIN> stage[VERTEX_STAGES];
+    __shared__ __align__(8) uint64_t full[VERTEX_STAGES], empty[VERTEX_STAGES];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < VERTEX_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], VERTEX_BLOCK / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     if (!second) pdl_wait();        // everything below reads what k_prep_draws wrote
     pdl_launch();
-    vertex_tile<MODE>(sU, draws, vbase, tileList, totalV, fc, lightsU, bones, vols, clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+
+    if (warp == VERTEX_BLOCK / 32) {
+        // ---- producer ----
+        if (lane == 0) {
+            // tiles are handed out by an atomic counter (zeroed by k_prep_draws): SMs that run ahead take more tiles.  The
+            // counter is bumped one tile ahead, so its round trip to L2 overlaps the previous tile's record reads.
+            uint32_t tNext = blockIdx.x;            // the first tile needs no round trip; the counter hands out tiles gridDim.x, ...
+            for (uint32_t k = 0;; k++) {
+                const uint32_t sidx = k % VERTEX_STAGES, ph = (k / VERTEX_STAGES) & 1u;
+                VStage<SKIN>& S = stage[sidx];
+                const uint32_t t = tNext;
+                if (t >= nTiles) {          // tell the consumers that the list is exhausted
+                    mbar_wait(&empty[sidx], ph ^ 1u);
+                    S.desc.base = NO_TILE;
+                    mbar_arrive(&full[sidx]);
+                    break;
+                }
+                // {tile, first draw, first draw of the next tile, end of the first draw's vertices}
+                const uint4 entry = __ldg(&tileList[t]);
+                tNext = gridDim.x + atomicAdd(tileCtr, 1u);
+                const uint32_t base = entry.x * (uint32_t)VERTEX_BLOCK;
+                const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
+                const uint32_t dLo = entry.y, dHi = entry.z;
+                // dHi is the draw of the first slot of the NEXT tile, so dLo == dHi covers this whole tile; otherwise the
+                // tile is still uniform when the next draw starts at or after its end
+                bool staged = dLo == dHi || entry.w >= end;
+                const DrawRec& R = draws[dLo];
+                uint32_t flags = 0, nL = 0, mv0 = 0, lmode = T3D_LIGHTING_DEFAULT;
+                if (staged) {
+                    flags = R.flags;
+                    nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+                    lmode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
+                    staged = nL <= (uint32_t)VERTEX_SMEM_LIGHTS;
+                    if (SKIN && (flags & T3D_DRAW_SKINNED) && R.nBones > (uint32_t)VERTEX_SMEM_BONES) staged = false;
+                    mv0 = R.a0 + (base - R.vbase);
+                }
+                mbar_wait(&empty[sidx], ph ^ 1u);       // the consumers are done with the tile that used this stage before
+                VStageDesc D;
+                D.base = base; D.end = end; D.dLo = dLo; D.dHi = dHi; D.staged = staged ? 1u : 0u; D.mv0 = mv0; D.flags = flags; D.nLmode = nL | (lmode << 16);
+                S.desc = D;
+                if (!staged) { mbar_arrive(&full[sidx]); continue; }
+                const uint32_t cnt = end - base;            // a multiple of 4: every draw's vertex range is
+                const uint32_t vs = R.vstride;
+                const bool needN = flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED);
+                const bool skinned = SKIN && (flags & T3D_DRAW_SKINNED);
+                uint32_t bytes = 12u * cnt + 128u + 64u * nL;
+                if (needN) bytes += 12u * cnt;
+                if (skinned) bytes += 24u * cnt + 64u * R.nBones;
+                mbar_arrive_expect_tx(&full[sidx], bytes);
+                const float* pp = R.pos + mv0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) bulk_load(S.pos[c], pp + (size_t)c * vs, 4u * cnt, &full[sidx]);
+                if (needN) {
+                    const float* np = R.nrm + mv0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) bulk_load(S.nrm[c], np + (size_t)c * vs, 4u * cnt, &full[sidx]);
+                }
+                bulk_load(&S.U[0], R.mvp, 64u, &full[sidx]);
+                bulk_load(&S.U[4], R.worldRot, 64u, &full[sidx]);
+                if (nL) bulk_load(&S.U[8], lightsU + R.lightU, 64u * nL, &full[sidx]);
+                if constexpr (SKIN) {
+                    if (skinned) {
+                        bulk_load(S.wgt, R.wgt + 4 * (size_t)mv0, 16u * cnt, &full[sidx]);
+                        bulk_load(S.jnt, R.jnt + 4 * (size_t)mv0, 8u * cnt, &full[sidx]);
+                        bulk_load(S.bones, bones + 16 * (size_t)R.boneOffset, 64u * R.nBones, &full[sidx]);
+                    }
+                }
+            }
+        }
+        return;     // (the consumers keep the block alive; a `second` launch's wait at the end is theirs)
+    }
+
+    // ---- consumers ----
+    for (uint32_t k = 0;; k++) {
+        const uint32_t sidx = k % VERTEX_STAGES, ph = (k / VERTEX_STAGES) & 1u;
+        VStage<SKIN>& S = stage[sidx];
+        mbar_wait(&full[sidx], ph);
+        const VStageDesc D = S.desc;
+        if (D.base == NO_TILE) break;
+        const uint32_t slot = D.base + threadIdx.x;
+        if (slot < D.end) {
+            if (D.staged) {
+                const DrawRec& R = draws[D.dLo];
+                const uint32_t mv = D.mv0 + threadIdx.x;
+                const Vec3 P = v3(S.pos[0][threadIdx.x], S.pos[1][threadIdx.x], S.pos[2][threadIdx.x]);
+                Vec3 N = v3(0, 0, 0);
+                if (D.flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) N = v3(S.nrm[0][threadIdx.x], S.nrm[1][threadIdx.x], S.nrm[2][threadIdx.x]);
+                UniformsShared U; U.s = S.U; U.ti = threadIdx.x;
+                if constexpr (SKIN) { U.sWgt = S.wgt; U.sJnt = S.jnt; U.sBones = S.bones; }
+                else { U.sWgt = nullptr; U.sJnt = nullptr; U.sBones = nullptr; }
+                shade_vertex<MODE, APPROX>(R, D.flags, D.nLmode & 0xFFFFu, (uint8_t)(D.nLmode >> 16), U, fc, slot, mv, P, N, lightsU, vols,
+                                           clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+            } else {
+                const uint32_t d = find_draw(vbase, D.dLo, D.dHi, slot);
+                const DrawRec& R = draws[d];
+                const uint32_t flags = R.flags;
+                const uint32_t mv = R.a0 + (slot - R.vbase);
+                const uint32_t vs = R.vstride;
+                const float* pp = R.pos + mv;
+                Vec3 P = v3(__ldg(pp), __ldg(pp + vs), __ldg(pp + 2 * (size_t)vs)), N = v3(0, 0, 0);
+                if (flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) {
+                    const float* np = R.nrm + mv;
+                    N = v3(__ldg(np), __ldg(np + vs), __ldg(np + 2 * (size_t)vs));
+                }
+                UniformsGlobal U;
+                U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
+                U.wgtP = R.wgt; U.jntP = R.jnt; U.bonesP = bones + 16 * (size_t)R.boneOffset; U.mv = mv;
+                const uint8_t lightingMode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
+                shade_vertex<MODE, APPROX>(R, flags, R.lightCount, lightingMode, U, fc, slot, mv, P, N, lightsU, vols,
+                                           clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[sidx]);
+    }
     if (second) pdl_wait();
 }
 
@@ -1484,7 +1725,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
                        uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
-                       const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk) {
+                       const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk, uint32_t* tileCtr) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
     cudaFuncSetAttribute(k_prep_draws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);
@@ -1494,7 +1735,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.hostLights = hostLights;
     pf.devDraws = reinterpret_cast<uint4*>(devDraws); pf.devRest = reinterpret_cast<uint4*>(devRest);
     pf.nDraws = nDraws; pf.rest16 = firstChunk ? (uint32_t)(restBytes / 16) : 0u; pf.nPrepBlocks = nBlocksThis; pf.nLightsIn = nLightsIn;
-    pf.blockBase = blockBase;
+    pf.blockBase = blockBase; pf.tileCtr = firstChunk ? tileCtr : nullptr;
     if (!firstChunk) { nBones = 0; nPoseBatches = 0; }       // the copy and pose blocks ride with the first chunk only
     memcpy(pf.win, win, sizeof pf.win);
     pf.hostBones = reinterpret_cast<const uint4*>(hostBones); pf.devBones = reinterpret_cast<uint4*>(devBones);
@@ -1535,26 +1776,48 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     }
 }
 
-void launch_vertex(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
-                   const uint4* const tileLists[3], const uint32_t nTilesOf[3],
+// One wave of persistent blocks per class list: min(tiles, SMs x resident blocks) blocks pulling tiles off tileCtr[MODE].
+static int g_smCount = 0;
+template <int MODE, bool APPROX>
+static void launch_vertex_class(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, const uint4* tileList, uint32_t nTiles, uint32_t* tileCtr,
+                                uint32_t totalV, uint32_t second, const FrameConst& fc, const LightU* lightsU, const float* bones,
+                                const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
+    if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
+    constexpr uint32_t resident = MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS;
+    const uint32_t grid = std::min(nTiles, (uint32_t)g_smCount * resident);     // every block resident at once
+    launch_kernel(k_vertex<MODE, APPROX>, grid, VERTEX_THREADS, 0, s, pdl, draws, vbase, tileList, nTiles, tileCtr + MODE, totalV, second, fc,
+                  lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+}
+
+template <bool APPROX>
+static void launch_vertex_t(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase,
+                   const uint4* const tileLists[3], const uint32_t nTilesOf[3], uint32_t* tileCtr,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
     // the launches write disjoint slots; every one after the first overlaps its predecessor and waits for it at its end
     // (`second`; needs the dependent-launch chain: with stage events between kernels they all wait at the top)
     bool first = true;
     if (nTilesOf[K1_STATIC]) {
-        launch_kernel(k_vertex<K1_STATIC>, nTilesOf[K1_STATIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_STATIC], totalV, 0u, fc,
-                      lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+        launch_vertex_class<K1_STATIC, APPROX>(s, pdl, draws, vbase, tileLists[K1_STATIC], nTilesOf[K1_STATIC], tileCtr, totalV, 0u, fc,
+                                               lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
         first = false;
     }
     if (nTilesOf[K1_SKINNED]) {
-        launch_kernel(k_vertex<K1_SKINNED>, nTilesOf[K1_SKINNED], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_SKINNED], totalV,
-                      (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+        launch_vertex_class<K1_SKINNED, APPROX>(s, pdl, draws, vbase, tileLists[K1_SKINNED], nTilesOf[K1_SKINNED], tileCtr, totalV,
+                                                (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
         first = false;
     }
     if (nTilesOf[K1_GENERIC])
-        launch_kernel(k_vertex<K1_GENERIC>, nTilesOf[K1_GENERIC], VERTEX_BLOCK, 0, s, pdl, draws, vbase, tileLists[K1_GENERIC], totalV,
-                      (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+        launch_vertex_class<K1_GENERIC, APPROX>(s, pdl, draws, vbase, tileLists[K1_GENERIC], nTilesOf[K1_GENERIC], tileCtr, totalV,
+                                                (!first && pdl) ? 1u : 0u, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+}
+
+void launch_vertex(cudaStream_t s, bool pdl, bool exactLighting, const DrawRec* draws, const uint32_t* vbase,
+                   const uint4* const tileLists[3], const uint32_t nTilesOf[3], uint32_t* tileCtr,
+                   uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
+                   const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm) {
+    if (exactLighting) launch_vertex_t<false>(s, pdl, draws, vbase, tileLists, nTilesOf, tileCtr, totalV, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
+    else launch_vertex_t<true>(s, pdl, draws, vbase, tileLists, nTilesOf, tileCtr, totalV, fc, lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
 }
 
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,

@@ -339,6 +339,7 @@ PYBIND11_MODULE(_host, m) {
         })
         .def("ForceFullUpload", [](GeometryDevice& d, bool on) { t3d_debug_force_full_upload(d.ctx, on ? 1 : 0); })
         .def("SetStageTimings", [](GeometryDevice& d, bool on) { t3d_set_stage_timings(d.ctx, on ? 1 : 0); })
+        .def("SetExactLighting", [](GeometryDevice& d, bool on) { const int rc = t3d_set_exact_lighting(d.ctx, on ? 1 : 0); if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx)); })
         .def("VertexKernelBytes", [](GeometryDevice& d) { return t3d_debug_vertex_kernel_bytes(d.ctx); })
         .def("FrameBytes", [](GeometryDevice& d) { uint64_t a = 0, b = 0; t3d_debug_frame_bytes(d.ctx, &a, &b); return py::make_tuple(a, b); })
         .def("ReadDrawVertices", [](GeometryDevice& d, uint32_t draw, uint32_t v0, uint32_t v1) {
