@@ -260,6 +260,12 @@ def test_full_size_workloads_vs_oracle(device, name):
     assert_parity(W.WORKLOADS[name](), device, check_capture=False)
 
 
+def test_full_size_particles_vs_oracle(device):
+    """configs[3] at full size: 2 000 000 billboard particle draws (4 M triangles) in 184 dynamic batches, bit for bit against
+    the oracle (the scene is shadeless, so one lighting mode covers it; ~3 minutes, most of it building 2 M Python objects)."""
+    assert_parity(W.WORKLOADS["particles"](), device, check_capture=False, modes=("fast",))
+
+
 def test_unsupported_host_callbacks_fail_loudly(device):
     import tetra3d_b200 as t3d
     sc = scenes.soup_scene(23, n_models=1)
