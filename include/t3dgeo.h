@@ -213,6 +213,8 @@ typedef struct t3d_timings {
     float sort_ms;      /* key + radix sort */
     float emit_ms;      /* K4 emit */
     float download_ms;  /* D2H of results (0 when results stayed on device) */
+    float gather_ms;    /* t3d_gather_attach: end of the emit .. end of the delivery (shards: statistics + post; the issuing
+                         * rank: waiting for and rebuilding every shard's lists); part of total_ms */
     float total_ms;     /* first kernel to last kernel (the device time of the frame) */
 } t3d_timings;
 
@@ -326,18 +328,48 @@ int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* t
  * t3d_frame_results_device then returns these pointers; t3d_frame_results still copies to pinned host memory.
  * Passing color = NULL restores the library's buffers. */
 int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity);
-/* Sharded frames whose lists live on another GPU: the depth list differs from the colour list only in its colour,
- * (d, d, d, 1) (camera.go:1760-1782).  With `depth_scalars` set (device memory, one float per vertex of the target's
- * capacity) the emit writes d there instead of the target's depth list -- 52 instead of 96 bytes per vertex cross NVLink --
- * and the owner of the lists rebuilds the records with t3d_expand_depth_list (synchronous).  NULL switches back. */
-int t3d_set_output_compact_depth(t3d_ctx* ctx, float* depth_scalars);
-int t3d_expand_depth_list(t3d_ctx* ctx, const t3d_vertex* color, const float* depth_scalars, t3d_vertex* depth, uint64_t n_vertices, int render_depth);
 /* Device memory that other processes of the same machine can map (CUDA IPC): the owning rank allocates, sends
  * the handle over any channel, the other ranks open it and pass the pointer (plus their offset) to
  * t3d_set_output_target.  Freed / unmapped by t3d_destroy. */
 typedef struct t3d_shared_handle { unsigned char bytes[64]; } t3d_shared_handle;
 int t3d_shared_alloc(t3d_ctx* ctx, uint64_t bytes, void** device_ptr, t3d_shared_handle* handle);
 int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device_ptr);
+
+/* ---- delivery of sharded frames --------------------------------------------------------------------- */
+/* Object-wise sharding: every rank runs the geometry stage on the flushes it owns (each render(rp) is
+ * independent: own MVP, cull, min/max, bin sort -- model.go:602); the lists have to end up on the ONE rank that issues
+ * the DrawTriangles calls (camera.go:1829-2048).  These entry points do that delivery inside the frame, device to
+ * device over NVLink, with no host round trip and no collective:
+ *   - a shard's emit kernel stores a 36-byte compact form of every vertex ({DstX DstY SrcX SrcY | R G B A}, the depth
+ *     value, Custom0 under perspective-corrected texturing) straight into its inbox in the issuing rank's memory, ships its
+ *     per-draw statistics and posts {frame serial, vertex count} to its mailbox there;
+ *   - the issuing rank's frame ends with one kernel per shard that waits for that shard's post, rebuilds its part of
+ *     colorVertexList / depthVertexList (tetra3d.go:21-23) and acknowledges, which is what lets the shard overwrite its
+ *     inbox with the next frame.
+ * Every rank calls t3d_frame_execute once per frame, in lockstep (the serial is the frame count since attach).
+ *   t3d_gather_alloc   issuing rank: allocates the lists (world regions of vertex_capacity vertices), the inboxes and the
+ *                      mailboxes; returns three handles for the other ranks (send them over any channel).
+ *   t3d_gather_attach  every rank (the issuing rank passes handles = NULL): from the next frame on, frames are delivered.
+ *                      vertex_capacity >= 3 x the triangles any rank submits in a frame, draw_capacity >= its draws.
+ *   t3d_gather_results issuing rank, after t3d_frame_execute: waits for the frame; rank r's vertices are
+ *                      color_list / depth_list [r * vertex_capacity, r * vertex_capacity + n_vertices[r * n_vertices_stride]).
+ *   t3d_gather_rank_stats  issuing rank: rank r's per-draw {min depth bits, max depth bits, survivors} in r's submit order --
+ *                      with the (deterministic) assignment of flushes to ranks this gives every flush's slice.
+ * A shard that does not report within 10 s makes t3d_gather_results fail with T3D_E_CUDA instead of hanging the GPU.
+ * Replaces: nothing in the reference (it is single-process); SURVEY.md 8e's "NCCL gather of draw buffers". */
+typedef struct t3d_gather_output {
+    uint32_t world, n_vertices_stride;
+    uint64_t vertex_capacity;
+    const t3d_vertex* color_list;       /* DEVICE memory on the issuing rank */
+    const t3d_vertex* depth_list;
+    const uint32_t* n_vertices;         /* host memory: n_vertices[r * n_vertices_stride] */
+} t3d_gather_output;
+typedef struct t3d_draw_stat { uint32_t min_depth_bits, max_depth_bits, survivors, reserved; } t3d_draw_stat;
+int t3d_gather_alloc(t3d_ctx* ctx, uint32_t world, uint64_t vertex_capacity, uint32_t draw_capacity, t3d_shared_handle handles[3]);
+int t3d_gather_attach(t3d_ctx* ctx, uint32_t world, uint32_t rank, uint32_t dst, uint64_t vertex_capacity, uint32_t draw_capacity, const t3d_shared_handle handles[3]);
+int t3d_gather_detach(t3d_ctx* ctx);
+int t3d_gather_results(t3d_ctx* ctx, t3d_gather_output* out);
+int t3d_gather_rank_stats(t3d_ctx* ctx, uint32_t rank, uint32_t n_draws, t3d_draw_stat* out);
 
 /* ---- lighting precision ---------------------------------------------------------------------------- */
 /* Per-vertex lighting (light.go:191-258, 332-360) runs by default with single-instruction reciprocals and fused

@@ -69,3 +69,14 @@ def test_gather_lists_world_size_2(counts):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) is True
+
+
+def test_delivered_flush_table():
+    """The slicing of delivered lists by flush (parallel.delivered_flush_table) from the owners, every rank's draw -> flush map
+    and the survivor counts the shards ship."""
+    owners = [0, 1, 0, 1, 1, 0]
+    draw_flush = [[0, 0, 2, 5], [1, 3, 3, 3]]           # flush 4 (rank 1) submitted nothing
+    surv = [[2, 1, 0, 7], [4, 1, 0, 2]]
+    t = parallel.delivered_flush_table(owners, draw_flush, surv, capacity=1000)
+    assert t == {0: (0, 9), 2: (9, 0), 5: (9, 21), 1: (1000, 12), 3: (1012, 9), 4: (1021, 0)}
+    assert parallel.delivered_flush_table([], [[], []], [[], []], 256) == {}

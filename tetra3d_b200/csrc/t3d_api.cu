@@ -163,7 +163,25 @@ struct t3d_ctx {
     // external output target (t3d_set_output_target): the emit kernel writes the lists there -- another GPU's
     // memory over NVLink, or an interop buffer of the rasteriser -- instead of into dColor / dDepth / dNormal
     t3d_vertex *xColor = nullptr, *xDepth = nullptr, *xNormal = nullptr;
-    float* xDepthScalar = nullptr;      // t3d_set_output_compact_depth: one depth value per vertex instead of the depth list
+    // delivery of sharded frames to the rank that issues the draws (t3d_gather_*)
+    struct Gather {
+        bool active = false, allocated = false;
+        uint32_t world = 0, rank = 0, dst = 0, drawCap = 0, serial = 0;
+        uint64_t cap = 0;                       // vertices per rank region
+        uint8_t *color = nullptr, *depth = nullptr, *box = nullptr;     // the issuing rank's allocations (mapped over NVLink on the others)
+        size_t statsOff = 0, mailOff = 0, boxBytes = 0;
+        uint8_t* inbox(uint32_t r) const { return box + (size_t)r * cap * 40; }
+        uint8_t* stats(uint32_t r) const { return box + statsOff + (size_t)r * drawCap * sizeof(DrawStat); }
+        uint32_t* mail(uint32_t r) const { return reinterpret_cast<uint32_t*>(box + mailOff) + (size_t)r * GATHER_MAIL_WORDS; }
+        uint32_t* err() const { return reinterpret_cast<uint32_t*>(box + mailOff) + (size_t)world * GATHER_MAIL_WORDS; }
+        void layout() {
+            statsOff = ((size_t)world * cap * 40 + 255) & ~(size_t)255;
+            mailOff = (statsOff + (size_t)world * drawCap * sizeof(DrawStat) + 255) & ~(size_t)255;
+            boxBytes = mailOff + ((size_t)world + 1) * GATHER_MAIL_WORDS * 4;
+        }
+    } gather;
+    DevBuf dGatherErr;          // shards: the timeout flag of k_gather_wait_ack (the issuing rank keeps its own in the mailbox block)
+    PinVec<uint32_t> hMail; PinVec<DrawStat> hGatherStats;
     t3d_vertex *oColor = nullptr, *oDepth = nullptr, *oNormal = nullptr;     // where the current frame's lists are
     uint64_t xCapacity = 0;
     std::vector<void*> sharedAllocs, sharedOpened;
@@ -259,12 +277,12 @@ void t3d_destroy(t3d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame, &ctx->dStage,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
-                      &ctx->dCount, &ctx->dTileCtr, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
+                      &ctx->dCount, &ctx->dTileCtr, &ctx->dGatherErr, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
     ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
-    ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
+    ctx->hMail.release(); ctx->hGatherStats.release(); ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
     for (void* q : ctx->sharedAllocs) cudaFree(q);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -896,6 +914,29 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
     return close();
 }
 
+// Sharded delivery, enqueued behind the frame's emit.  A shard ships its per-draw statistics and reports the frame's serial
+// and vertex count to the issuing rank's mailbox; the issuing rank rebuilds every shard's part of the lists as it arrives.
+static int gather_enqueue(t3d_ctx* ctx, uint32_t nDraws, uint32_t nChunks) {
+    t3d_ctx::Gather& G = ctx->gather;
+    cudaStream_t s = ctx->stream;
+    if (G.rank != G.dst) {
+        launch_gather_post(s, G.mail(G.rank), ctx->dCount.as<uint32_t>(), nChunks, G.serial, ctx->dStats.p, G.stats(G.rank), nDraws);
+        ctx->launches += 1;
+    } else {
+        const bool renderDepth = ctx->fc.camFlags & T3D_CAM_RENDER_DEPTH, pcuv = ctx->fc.camFlags & T3D_CAM_PERSP_CORRECT_UV;
+        for (uint32_t r = 0; r < G.world; r++) {
+            if (r == G.dst) continue;
+            const uint8_t* in = G.inbox(r);
+            launch_gather_expand(s, in, reinterpret_cast<const float*>(in + G.cap * 32), reinterpret_cast<const float*>(in + G.cap * 36),
+                                 reinterpret_cast<t3d_vertex*>(G.color) + (size_t)r * G.cap, reinterpret_cast<t3d_vertex*>(G.depth) + (size_t)r * G.cap,
+                                 G.mail(r), G.serial, renderDepth, pcuv, G.err());
+            ctx->launches += 1;
+        }
+    }
+    CU(cudaGetLastError());
+    return T3D_OK;
+}
+
 int t3d_frame_execute(t3d_ctx* ctx) {
     if (!ctx) return T3D_E_INVALID;
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_execute: no open frame");
@@ -906,8 +947,17 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     ctx->launches = 0;
     ctx->executed = true;
     ctx->stagesTimed = ctx->stageTimings;
+    if (ctx->gather.active) {
+        t3d_ctx::Gather& G = ctx->gather;
+        G.serial++;
+        if (3ull * totalT > G.cap || nDraws > G.drawCap)
+            return fail(ctx, T3D_E_NOMEM, "t3d_frame_execute: the frame exceeds the capacity given to t3d_gather_attach (3 vertices per submitted triangle, one entry per draw)");
+    }
     if (nDraws == 0 || totalT == 0) {
-        for (int i = 0; i < 7; i++) CU(cudaEventRecord(ctx->ev[i], s));
+        for (int i = 0; i < 6; i++) CU(cudaEventRecord(ctx->ev[i], s));
+        CU(cudaEventRecord(ctx->ev[9], s));
+        if (ctx->gather.active) { const int rc = gather_enqueue(ctx, 0, 0); if (rc != T3D_OK) return rc; }     // an empty shard still reports in
+        CU(cudaEventRecord(ctx->ev[6], s));
         ctx->h2dBytes = 0;
         return T3D_OK;
     }
@@ -954,6 +1004,12 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dTileSurv.ensure(4ull * std::max(nTiles, 1u)));
     CU(ctx->dTileOut.ensure(4ull * (nTiles + 1)));
     CU(ctx->dCount.ensure(4ull * std::max<uint32_t>((nTiles + SCAN_CHUNK - 1) / SCAN_CHUNK, 64u)));     // per-chunk survivor totals of the tile scan
+    if (ctx->gather.active && ctx->gather.rank == ctx->gather.dst) {        // the issuing rank emits into its own region of the shared lists
+        t3d_ctx::Gather& G = ctx->gather;
+        ctx->xColor = reinterpret_cast<t3d_vertex*>(G.color) + (size_t)G.rank * G.cap;
+        ctx->xDepth = reinterpret_cast<t3d_vertex*>(G.depth) + (size_t)G.rank * G.cap;
+        ctx->xNormal = nullptr; ctx->xCapacity = G.cap;
+    }
     const bool external = ctx->xColor != nullptr;
     if (external) {
         if (3ull * totalT > ctx->xCapacity) return fail(ctx, T3D_E_NOMEM, "t3d_frame_execute: the output target is smaller than the frame's worst case (3 vertices per submitted triangle)");
@@ -1217,13 +1273,27 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     CU(mark(5));
     // K4
-    const bool compact = external && ctx->xDepthScalar != nullptr;
-    if (compact && normals) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_execute: compact depth output with RenderNormals");
-    launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
-                ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
-                reinterpret_cast<float4*>(ctx->oColor), compact ? reinterpret_cast<float4*>(ctx->xDepthScalar) : reinterpret_cast<float4*>(ctx->oDepth),
-                normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), compact);
+    t3d_ctx::Gather& G = ctx->gather;
+    const bool shard = G.active && G.rank != G.dst;        // this rank's lists live on the issuing rank: compact emit into its inbox there
+    if (G.active && normals) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_execute: sharded delivery with RenderNormals");
+    if (shard) {
+        CU(ctx->dGatherErr.ensure(64));
+        launch_gather_wait_ack(s, G.mail(G.rank) + 16, G.serial - 1, ctx->dGatherErr.as<uint32_t>());      // the previous frame has been expanded
+        uint8_t* in = G.inbox(G.rank);
+        launch_emit(s, false, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
+                    ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+                    reinterpret_cast<float4*>(in), reinterpret_cast<float4*>(in + G.cap * 32), nullptr, ctx->dTriIds.as<uint32_t>(), true,
+                    reinterpret_cast<float*>(in + G.cap * 36));
+        ctx->launches += 1;
+    } else {
+        launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
+                    ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
+                    reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
+                    normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), false, nullptr);
+    }
     ctx->launches += nTiles ? 1 : 0;
+    CU(cudaEventRecord(ctx->ev[9], s));
+    if (G.active) { const int rc = gather_enqueue(ctx, nDraws, ((uint32_t)ctx->hTiles.n + SCAN_CHUNK - 1) / SCAN_CHUNK); if (rc != T3D_OK) return rc; }
     CU(cudaEventRecord(ctx->ev[6], s));
     CU(cudaGetLastError());
 
@@ -1306,11 +1376,10 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     }
     out->index_list = ctx->hIndex.p;
 
-    // compact-depth frames (t3d_set_output_compact_depth) never wrote a depth list: the owner of the lists rebuilds it with
-    // t3d_expand_depth_list from the colour list and the depth scalars
-    const bool compactDepth = ctx->xColor != nullptr && ctx->xDepthScalar != nullptr;
+    // a shard's frame left no lists here: they were delivered in compact form to the issuing rank
+    const bool compactDepth = ctx->gather.active && ctx->gather.rank != ctx->gather.dst;
     if (download && compactDepth)
-        return fail(ctx, T3D_E_STATE, "t3d_frame_results: the frame emitted compact depth into an external target; use t3d_frame_results_device and t3d_expand_depth_list");
+        return fail(ctx, T3D_E_STATE, "t3d_frame_results: this rank's lists were delivered to the issuing rank (t3d_gather_attach); use t3d_frame_results_device here and t3d_gather_results there");
     if (download) {
         if (nVerts) {
             cudaEvent_t e0 = ctx->ev[7], e1 = ctx->ev[8];
@@ -1330,7 +1399,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
         out->normal_list = normals ? ctx->hNormal.p : nullptr;
         out->tri_ids = ctx->hTriIds.p;
     } else {
-        out->color_list = ctx->oColor; out->depth_list = compactDepth ? nullptr : ctx->oDepth;
+        out->color_list = compactDepth ? nullptr : ctx->oColor; out->depth_list = compactDepth ? nullptr : ctx->oDepth;
         out->normal_list = normals ? ctx->oNormal : nullptr;
         out->tri_ids = ctx->dTriIds.as<uint32_t>();
     }
@@ -1342,9 +1411,10 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
             cudaEventElapsedTime(&tm->vertex_ms, ctx->ev[2], ctx->ev[3]);
             cudaEventElapsedTime(&tm->cull_ms, ctx->ev[3], ctx->ev[4]);
             cudaEventElapsedTime(&tm->sort_ms, ctx->ev[4], ctx->ev[5]);
-            cudaEventElapsedTime(&tm->emit_ms, ctx->ev[5], ctx->ev[6]);
+            cudaEventElapsedTime(&tm->emit_ms, ctx->ev[5], ctx->ev[9]);
         }
         cudaEventElapsedTime(&tm->total_ms, ctx->ev[0], ctx->ev[6]);
+        cudaEventElapsedTime(&tm->gather_ms, ctx->ev[9], ctx->ev[6]);
         tm->download_ms = ctx->downloadMs;
     }
     ctx->haveResults = true;
@@ -1389,25 +1459,6 @@ int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3
     if (color && (((uintptr_t)color | (uintptr_t)depth | (uintptr_t)normal) & 15)) return fail(ctx, T3D_E_INVALID, "t3d_set_output_target: lists must be 16-byte aligned");
     ctx->xColor = color; ctx->xDepth = depth; ctx->xNormal = color ? normal : nullptr;
     ctx->xCapacity = color ? vertex_capacity : 0;
-    ctx->xDepthScalar = nullptr;
-    return T3D_OK;
-}
-
-int t3d_set_output_compact_depth(t3d_ctx* ctx, float* depth_scalars) {
-    if (!ctx) return T3D_E_INVALID;
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (depth_scalars && !ctx->xColor) return fail(ctx, T3D_E_STATE, "t3d_set_output_compact_depth: set an output target first");
-    ctx->xDepthScalar = depth_scalars;
-    return T3D_OK;
-}
-
-int t3d_expand_depth_list(t3d_ctx* ctx, const t3d_vertex* color, const float* depth_scalars, t3d_vertex* depth, uint64_t n_vertices, int render_depth) {
-    if (!ctx || (n_vertices && (!color || !depth_scalars || !depth))) return fail(ctx, T3D_E_INVALID, "t3d_expand_depth_list: NULL argument");
-    CU(cudaSetDevice(ctx->device));
-    launch_expand_depth(ctx->stream, reinterpret_cast<const float4*>(color), depth_scalars, reinterpret_cast<float4*>(depth), n_vertices, render_depth != 0);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
     return T3D_OK;
 }
 
@@ -1436,6 +1487,94 @@ int t3d_shared_open(t3d_ctx* ctx, const t3d_shared_handle* handle, void** device
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->sharedOpened.push_back(p);
     *device_ptr = p;
+    return T3D_OK;
+}
+
+int t3d_gather_alloc(t3d_ctx* ctx, uint32_t world, uint64_t vertex_capacity, uint32_t draw_capacity, t3d_shared_handle handles[3]) {
+    if (!ctx || !handles || world < 2 || vertex_capacity == 0) return fail(ctx, T3D_E_INVALID, "t3d_gather_alloc: bad argument");
+    if (ctx->gather.allocated || ctx->gather.active) return fail(ctx, T3D_E_STATE, "t3d_gather_alloc: already allocated");
+    t3d_ctx::Gather& G = ctx->gather;
+    G.world = world; G.cap = (vertex_capacity + 255) & ~(uint64_t)255; G.drawCap = std::max(draw_capacity, 1u);
+    G.layout();
+    void *c = nullptr, *d = nullptr, *b = nullptr;
+    int rc = t3d_shared_alloc(ctx, (uint64_t)world * G.cap * sizeof(t3d_vertex), &c, &handles[0]);
+    if (rc == T3D_OK) rc = t3d_shared_alloc(ctx, (uint64_t)world * G.cap * sizeof(t3d_vertex), &d, &handles[1]);
+    if (rc == T3D_OK) rc = t3d_shared_alloc(ctx, G.boxBytes, &b, &handles[2]);
+    if (rc != T3D_OK) return rc;
+    CU(cudaMemset(static_cast<uint8_t*>(b) + G.mailOff, 0, G.boxBytes - G.mailOff));
+    G.color = static_cast<uint8_t*>(c); G.depth = static_cast<uint8_t*>(d); G.box = static_cast<uint8_t*>(b);
+    G.allocated = true;
+    return T3D_OK;
+}
+
+int t3d_gather_attach(t3d_ctx* ctx, uint32_t world, uint32_t rank, uint32_t dst, uint64_t vertex_capacity, uint32_t draw_capacity, const t3d_shared_handle handles[3]) {
+    if (!ctx || world < 2 || rank >= world || dst >= world) return fail(ctx, T3D_E_INVALID, "t3d_gather_attach: bad argument");
+    if (ctx->inFrame && !ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_gather_attach: a frame is open");
+    t3d_ctx::Gather& G = ctx->gather;
+    if (G.active) return fail(ctx, T3D_E_STATE, "t3d_gather_attach: already attached");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (rank == dst) {
+        if (!G.allocated || G.world != world || G.cap != ((vertex_capacity + 255) & ~(uint64_t)255) || G.drawCap != std::max(draw_capacity, 1u))
+            return fail(ctx, T3D_E_STATE, "t3d_gather_attach: the issuing rank attaches what it allocated with t3d_gather_alloc");
+        // serials restart at 1 with every attach (all ranks detach and attach together, with a barrier of the caller's in between)
+        CU(cudaMemset(G.box + G.mailOff, 0, G.boxBytes - G.mailOff));
+    } else {
+        if (!handles) return fail(ctx, T3D_E_INVALID, "t3d_gather_attach: handles is NULL");
+        G.world = world; G.cap = (vertex_capacity + 255) & ~(uint64_t)255; G.drawCap = std::max(draw_capacity, 1u);
+        G.layout();
+        void *c = nullptr, *d = nullptr, *b = nullptr;
+        int rc = t3d_shared_open(ctx, &handles[0], &c);
+        if (rc == T3D_OK) rc = t3d_shared_open(ctx, &handles[1], &d);
+        if (rc == T3D_OK) rc = t3d_shared_open(ctx, &handles[2], &b);
+        if (rc != T3D_OK) return rc;
+        G.color = static_cast<uint8_t*>(c); G.depth = static_cast<uint8_t*>(d); G.box = static_cast<uint8_t*>(b);
+        CU(ctx->dGatherErr.ensure(64));
+        CU(cudaMemset(ctx->dGatherErr.p, 0, 64));
+    }
+    G.rank = rank; G.dst = dst; G.serial = 0; G.active = true;
+    return T3D_OK;
+}
+
+int t3d_gather_detach(t3d_ctx* ctx) {
+    if (!ctx) return T3D_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gather.active && ctx->gather.rank == ctx->gather.dst) { ctx->xColor = ctx->xDepth = ctx->xNormal = nullptr; ctx->xCapacity = 0; }
+    ctx->gather.active = false;      // the allocations stay mapped until t3d_destroy
+    return T3D_OK;
+}
+
+int t3d_gather_results(t3d_ctx* ctx, t3d_gather_output* out) {
+    if (!ctx || !out) return fail(ctx, T3D_E_INVALID, "t3d_gather_results: NULL argument");
+    t3d_ctx::Gather& G = ctx->gather;
+    if (!G.active || G.rank != G.dst) return fail(ctx, T3D_E_STATE, "t3d_gather_results: only on the issuing rank of an attached gather");
+    if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_gather_results: frame not executed");
+    CU(cudaSetDevice(ctx->device));
+    const size_t words = ((size_t)G.world + 1) * GATHER_MAIL_WORDS;
+    CU(ctx->hMail.resize(words));
+    CU(cudaMemcpyAsync(ctx->hMail.p, G.box + G.mailOff, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->hMail.p[(size_t)G.world * GATHER_MAIL_WORDS]) return fail(ctx, T3D_E_CUDA, "t3d_gather_results: timed out waiting for a shard's frame");
+    memset(out, 0, sizeof *out);
+    out->world = G.world; out->vertex_capacity = G.cap;
+    out->color_list = reinterpret_cast<const t3d_vertex*>(G.color); out->depth_list = reinterpret_cast<const t3d_vertex*>(G.depth);
+    out->n_vertices = ctx->hMail.p;        // stride GATHER_MAIL_WORDS; the issuing rank's own entry is patched below
+    ctx->hMail.p[(size_t)G.dst * GATHER_MAIL_WORDS + 1] = (uint32_t)ctx->nVerticesOut;
+    out->n_vertices_stride = GATHER_MAIL_WORDS; out->n_vertices += 1;
+    return T3D_OK;
+}
+
+int t3d_gather_rank_stats(t3d_ctx* ctx, uint32_t rank, uint32_t n_draws, t3d_draw_stat* out) {
+    if (!ctx || (n_draws && !out)) return fail(ctx, T3D_E_INVALID, "t3d_gather_rank_stats: NULL argument");
+    t3d_ctx::Gather& G = ctx->gather;
+    if (!G.active || G.rank != G.dst || rank >= G.world || n_draws > G.drawCap) return fail(ctx, T3D_E_STATE, "t3d_gather_rank_stats: only on the issuing rank, for a rank and draw count inside the attached capacity");
+    static_assert(sizeof(t3d_draw_stat) == sizeof(DrawStat), "t3d_draw_stat mirrors DrawStat");
+    CU(cudaSetDevice(ctx->device));
+    if (!n_draws) return T3D_OK;
+    const void* src = rank == G.dst ? ctx->dStats.p : (const void*)G.stats(rank);
+    CU(cudaMemcpyAsync(out, src, sizeof(DrawStat) * (size_t)n_draws, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return T3D_OK;
 }
 

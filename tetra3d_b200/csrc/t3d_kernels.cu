@@ -1568,9 +1568,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// COMPACT (sharded frames whose lists live on another GPU): the depth list differs from the colour list only in its colour,
-// which is (d, d, d, 1) -- so only d crosses NVLink (4 bytes per vertex instead of 48, into depthList reinterpreted as
-// float[]) and the owner of the lists rebuilds the records with k_expand_depth.
+// COMPACT (sharded frames whose lists live on another GPU): of the 96 bytes a vertex has in the two lists only 36 carry
+// information -- {DstX, DstY, SrcX, SrcY | R, G, B, A}, the depth value d of the depth list's colour (d, d, d, 1), and
+// Custom0 when texture mapping is perspective-corrected (Custom1-3 are zero, camera.go:1689-1705, 1760-1782).  So the emit
+// stores 32-byte records into colorList (reinterpreted), d into depthList (reinterpreted as float[]) and Custom0 into
+// custom0List, and the owner of the lists rebuilds both lists with k_gather_expand.
 template <bool NORMALS, bool COMPACT>
 __global__ void __launch_bounds__(EMIT_TRIS)
 k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
@@ -1578,7 +1580,7 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
        const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
        const float* __restrict__ unbill, const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
-       uint32_t* __restrict__ triIds) {
+       uint32_t* __restrict__ triIds, float* __restrict__ custom0List) {
     extern __shared__ uint4 emitSmem[];
     float4* sCol = reinterpret_cast<float4*>(emitSmem);             // [EMIT_TRIS][3]
     float4* sDep = sCol + 3 * EMIT_TRIS;
@@ -1686,10 +1688,14 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
 
             const float4 a = make_float4(dx, dy, uvU, uvV);
             const float4 cust = make_float4(custom0, 0.0f, 0.0f, 0.0f);
-            float4* C = sCol + 3 * threadIdx.x;
-            C[0] = a; C[1] = col; C[2] = cust;
-            if (COMPACT) reinterpret_cast<float*>(depthList)[3 * (size_t)outTri0 + v] = dcol.x;
-            else {
+            if (COMPACT) {
+                float4* C = sCol + 2 * threadIdx.x;
+                C[0] = a; C[1] = col;
+                reinterpret_cast<float*>(depthList)[3 * (size_t)outTri0 + v] = dcol.x;
+                if (pcuv) custom0List[3 * (size_t)outTri0 + v] = custom0;
+            } else {
+                float4* C = sCol + 3 * threadIdx.x;
+                C[0] = a; C[1] = col; C[2] = cust;
                 float4* D = sDep + 3 * threadIdx.x;
                 D[0] = a; D[1] = dcol; D[2] = cust;
             }
@@ -1706,8 +1712,8 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
         if (threadIdx.x == 0) {
             const uint32_t n = min((uint32_t)EMIT_TRIS, nVert - v0);
             const size_t o = 3 * (size_t)outTri0 + v0;                  // first output vertex of this round
-            bulk_store(colorList + 3 * o, sCol, n * 48u);
-            if (!COMPACT) bulk_store(depthList + 3 * o, sDep, n * 48u);
+            if (COMPACT) bulk_store(colorList + 2 * o, sCol, n * 32u);
+            else { bulk_store(colorList + 3 * o, sCol, n * 48u); bulk_store(depthList + 3 * o, sDep, n * 48u); }
             if (NORMALS) bulk_store(normalList + 3 * o, sNrm, n * 48u);
             bulk_commit();
         }
@@ -1845,36 +1851,108 @@ void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const Tr
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
-                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth) {
+                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth, float* custom0List) {
     if (!nTiles) return;
     const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
     if (compactDepth)
         launch_kernel(k_emit<false, true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
     else if (normalList)
         launch_kernel(k_emit<true, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
     else
         launch_kernel(k_emit<false, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
 }
 
-// The depth list from the colour list and one depth value per vertex (see k_emit<.., COMPACT>): record = {DstX DstY SrcX SrcY |
-// d d d 1 (or zeros without RenderDepth) | Custom0..3} (camera.go:1760-1782).
+// ---- delivery of sharded frames to the rank that issues the draws -----------------------------------------
+// Mailbox words live in the issuing rank's memory and are written / polled across NVLink: a peer's stores land in the owner's
+// L2, volatile loads bypass L1.  Serial numbers wrap: compare as signed differences.
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint64_t global_timer_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+static const uint64_t GATHER_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;       // a peer that never answers must not hang the GPU
+
+// Spins until *word has reached `serial`; returns false on timeout.
+__device__ __forceinline__ bool wait_serial(const uint32_t* word, uint32_t serial) {
+    const uint64_t t0 = global_timer_ns();
+    while ((int32_t)(ld_volatile_u32(word) - serial) < 0) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > GATHER_TIMEOUT_NS) return false;
+    }
+    return true;
+}
+
+// A shard's emit may overwrite its inbox on the issuing rank only after that rank has expanded the previous frame.
+__global__ void k_gather_wait_ack(const uint32_t* __restrict__ ackWord, uint32_t serial, uint32_t* __restrict__ errWord) {
+    if (!wait_serial(ackWord, serial)) *errWord = 1u;
+}
+
+// After the shard's emit (kernel boundary: its stores have been performed): the per-draw statistics, the frame's vertex count
+// and its serial go to the issuing rank -- statistics and count first, then a system-wide fence, then the serial the owner polls.
 __global__ void __launch_bounds__(256)
-k_expand_depth(const float4* __restrict__ color, const float* __restrict__ scalars, float4* __restrict__ depth, uint64_t nVerts, int renderDepth) {
-    const uint64_t v = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (v >= nVerts) return;
-    const float4 a = color[3 * v], c = color[3 * v + 2];
-    const float d = scalars[v];
-    depth[3 * v] = a;
-    depth[3 * v + 1] = renderDepth ? make_float4(d, d, d, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    depth[3 * v + 2] = c;
+k_gather_post(uint32_t* __restrict__ mail, const uint32_t* __restrict__ chunkSum, uint32_t nChunks, uint32_t serial,
+              const uint4* __restrict__ stats, uint4* __restrict__ statsOut, uint32_t nDraws) {
+    for (uint32_t i = threadIdx.x; i < nDraws; i += 256) statsOut[i] = stats[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t n = 0;
+        for (uint32_t c = 0; c < nChunks; c++) n += chunkSum[c];
+        mail[1] = 3u * n;
+        __threadfence_system();
+        mail[0] = serial;
+    }
 }
 
-void launch_expand_depth(cudaStream_t s, const float4* color, const float* scalars, float4* depth, uint64_t nVerts, bool renderDepth) {
-    if (!nVerts) return;
-    launch_kernel(k_expand_depth, (uint32_t)((nVerts + 255) / 256), 256, 0, s, false, color, scalars, depth, nVerts, renderDepth ? 1 : 0);
+// The issuing rank: waits for a shard's frame, rebuilds its part of colorVertexList / depthVertexList (tetra3d.go:21-23) from the
+// 36-byte compact form, and acknowledges (the last block to finish).  Persistent grid; one thread per 16-byte piece of the
+// 48-byte output records, so that every store instruction of a warp covers 512 contiguous bytes of each list.
+__global__ void __launch_bounds__(256)
+k_gather_expand(const float4* __restrict__ rec32, const float* __restrict__ dscal, const float* __restrict__ cust,
+                float4* __restrict__ color, float4* __restrict__ depth, uint32_t* __restrict__ mail /* {serial, nVerts} | +16: ack | +17: done counter */,
+                uint32_t serial, int renderDepth, int pcuv, uint32_t* __restrict__ errWord) {
+    __shared__ uint32_t sN;
+    if (threadIdx.x == 0) {
+        if (!wait_serial(mail, serial)) { *errWord = 1u; sN = 0; }
+        else sN = ld_volatile_u32(mail + 1);
+    }
+    __syncthreads();
+    const uint64_t n3 = 3ull * sN;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n3; i += (uint64_t)gridDim.x * 256) {
+        const uint32_t v = (uint32_t)(i / 3), part = (uint32_t)(i - 3ull * v);
+        float4 c, d;
+        if (part == 0) c = d = __ldcg(rec32 + 2 * (size_t)v);                       // DstX DstY SrcX SrcY
+        else if (part == 1) {
+            c = __ldcg(rec32 + 2 * (size_t)v + 1);                                  // R G B A
+            const float z = __ldcg(dscal + v);
+            d = renderDepth ? make_float4(z, z, z, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else c = d = make_float4(pcuv ? __ldcg(cust + v) : 0.0f, 0.0f, 0.0f, 0.0f);    // Custom0..3
+        __stcs(color + i, c);
+        __stcs(depth + i, d);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(mail + 17, 1u) == gridDim.x - 1) {
+            mail[17] = 0;
+            __threadfence_system();
+            mail[16] = serial;          // the shard may overwrite its inbox now
+        }
+    }
+}
+
+void launch_gather_wait_ack(cudaStream_t s, const uint32_t* ackWord, uint32_t serial, uint32_t* errWord) {
+    launch_kernel(k_gather_wait_ack, 1, 1, 0, s, false, ackWord, serial, errWord);
+}
+void launch_gather_post(cudaStream_t s, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
+                        const void* stats, void* statsOut, uint32_t nDraws) {
+    launch_kernel(k_gather_post, 1, 256, 0, s, false, mail, chunkSum, nChunks, serial, reinterpret_cast<const uint4*>(stats), reinterpret_cast<uint4*>(statsOut), nDraws);
+}
+void launch_gather_expand(cudaStream_t s, const void* rec32, const float* dscal, const float* cust, t3d_vertex* color, t3d_vertex* depth,
+                          uint32_t* mail, uint32_t serial, bool renderDepth, bool pcuv, uint32_t* errWord) {
+    if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
+    launch_kernel(k_gather_expand, (uint32_t)g_smCount * 8u, 256, 0, s, false, reinterpret_cast<const float4*>(rec32), dscal, cust,
+                  reinterpret_cast<float4*>(color), reinterpret_cast<float4*>(depth), mail, serial, renderDepth ? 1 : 0, pcuv ? 1 : 0, errWord);
 }
 
 }  // namespace t3d

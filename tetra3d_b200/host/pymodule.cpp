@@ -322,14 +322,39 @@ PYBIND11_MODULE(_host, m) {
                                                  reinterpret_cast<t3d_vertex*>(normal), capacity);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
         })
-        .def("SetOutputCompactDepth", [](GeometryDevice& d, uintptr_t scalars) {
-            const int rc = t3d_set_output_compact_depth(d.ctx, reinterpret_cast<float*>(scalars));
+        .def("GatherAlloc", [](GeometryDevice& d, uint32_t world, uint64_t vertexCapacity, uint32_t drawCapacity) {
+            t3d_shared_handle h[3];
+            const int rc = t3d_gather_alloc(d.ctx, world, vertexCapacity, drawCapacity, h);
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+            py::list out;
+            for (auto& x : h) out.append(py::bytes(reinterpret_cast<const char*>(x.bytes), sizeof x.bytes));
+            return out;
+        })
+        .def("GatherAttach", [](GeometryDevice& d, uint32_t world, uint32_t rank, uint32_t dst, uint64_t vertexCapacity, uint32_t drawCapacity, py::object handles) {
+            t3d_shared_handle h[3]; bool have = !handles.is_none();
+            if (have) {
+                py::list l = handles;
+                if (l.size() != 3) throw std::invalid_argument("GatherAttach: three handles");
+                for (int i = 0; i < 3; i++) { std::string b = py::bytes(l[i]); if (b.size() != sizeof h[i].bytes) throw std::invalid_argument("GatherAttach: handles are 64 bytes"); memcpy(h[i].bytes, b.data(), sizeof h[i].bytes); }
+            }
+            const int rc = t3d_gather_attach(d.ctx, world, rank, dst, vertexCapacity, drawCapacity, have ? h : nullptr);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
         })
-        .def("ExpandDepthList", [](GeometryDevice& d, uintptr_t color, uintptr_t scalars, uintptr_t depth, uint64_t nVertices, bool renderDepth) {
-            const int rc = t3d_expand_depth_list(d.ctx, reinterpret_cast<const t3d_vertex*>(color), reinterpret_cast<const float*>(scalars),
-                                                 reinterpret_cast<t3d_vertex*>(depth), nVertices, renderDepth ? 1 : 0);
+        .def("GatherDetach", [](GeometryDevice& d) { const int rc = t3d_gather_detach(d.ctx); if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx)); })
+        .def("GatherResults", [](GeometryDevice& d) {
+            t3d_gather_output o;
+            const int rc = t3d_gather_results(d.ctx, &o);
             if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+            py::dict r; r["color"] = (uintptr_t)o.color_list; r["depth"] = (uintptr_t)o.depth_list; r["capacity"] = o.vertex_capacity;
+            py::list n; for (uint32_t k = 0; k < o.world; k++) n.append(o.n_vertices[(size_t)k * o.n_vertices_stride]);
+            r["n_vertices"] = n;
+            return r;
+        })
+        .def("GatherRankStats", [](GeometryDevice& d, uint32_t rank, uint32_t nDraws) {
+            py::array_t<uint32_t> out({(py::ssize_t)nDraws, (py::ssize_t)4});
+            const int rc = t3d_gather_rank_stats(d.ctx, rank, nDraws, reinterpret_cast<t3d_draw_stat*>(out.mutable_data()));
+            if (rc != T3D_OK) throw T3DError(rc, t3d_last_error(d.ctx));
+            return out;
         })
         .def("ReadBones", [](GeometryDevice& d, uint32_t offset, uint32_t n) {
             py::array_t<float> out({(py::ssize_t)n, (py::ssize_t)16});
@@ -416,6 +441,7 @@ PYBIND11_MODULE(_host, m) {
             return out;
         })
         .def("FlushOwnerRanks", [](Camera& c) { return c.flushOwnerRank; })
+        .def("ShardDrawFlushes", [](Camera& c) { return c.shardDrawFlush; })
         .def("DebugInfo", [](Camera& c) {
             py::dict d; d["drawnParts"] = c.debugInfo.drawnParts; d["totalParts"] = c.debugInfo.totalParts; d["batchedParts"] = c.debugInfo.batchedParts;
             d["drawnTris"] = c.debugInfo.drawnTris; d["totalTris"] = c.debugInfo.totalTris; d["lightCount"] = c.debugInfo.lightCount;
@@ -424,7 +450,7 @@ PYBIND11_MODULE(_host, m) {
         })
         .def("Timings", [](Camera& c) {
             py::dict d; d["upload_ms"] = c.timings.upload_ms; d["prep_ms"] = c.timings.prep_ms; d["vertex_ms"] = c.timings.vertex_ms; d["cull_ms"] = c.timings.cull_ms;
-            d["sort_ms"] = c.timings.sort_ms; d["emit_ms"] = c.timings.emit_ms; d["download_ms"] = c.timings.download_ms; d["total_ms"] = c.timings.total_ms;
+            d["sort_ms"] = c.timings.sort_ms; d["emit_ms"] = c.timings.emit_ms; d["download_ms"] = c.timings.download_ms; d["total_ms"] = c.timings.total_ms; d["gather_ms"] = c.timings.gather_ms;
             return d;
         })
         .def("LaunchCount", [](Camera& c) { return c.launchCount; });

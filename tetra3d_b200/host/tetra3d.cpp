@@ -762,6 +762,13 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         std::vector<uint64_t> flushTris(nFlush, 0);
         for (auto& pd : pending) flushTris[pd.flush] += (uint64_t)pd.model->mesh->MeshParts[pd.part]->TriangleCount();
         flushOwnerRank = AssignFlushesToRanks(flushTris, shardCount);
+        shardDrawFlush.assign((size_t)shardCount, {});
+        if (shardCount > 1)
+            for (auto& pd : pending) {      // the same skip rule as below (ProcessVertices early-out, model.go:604)
+                MeshPart& mp = *pd.model->mesh->MeshParts[pd.part];
+                const bool skip = (pd.model->Color.A == 0 && pd.model->isTransparent(mp)) || !pd.model->visible;
+                if (!skip) shardDrawFlush[(size_t)flushOwnerRank[pd.flush]].push_back(pd.flush);
+            }
     }
 
     // ---- frame ----

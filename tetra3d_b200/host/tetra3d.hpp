@@ -363,6 +363,8 @@ struct Camera : Node {
     std::vector<RenderRecord> renders;
     std::vector<FlushRecord> flushes;
     std::vector<int> flushOwnerRank;        // for every flush of the frame (all ranks), the rank that ran it
+    std::vector<std::vector<int>> shardDrawFlush;   // per rank: the flush of every draw that rank submitted, in its submit order (what the
+                                                    // issuing rank needs to slice a shard's delivered lists by flush: t3d_gather_rank_stats)
     std::vector<int> localFlushIds;         // global flush ids of this rank's flushes, in order
     int launchCount = 0;
 };

@@ -2,11 +2,12 @@
 end up on the rank that issues the draws (no cross-GPU merge is needed: each MeshPart is sorted in isolation,
 model.go:602, 989).  Two ways to get them there:
 
-  SharedLists   the issuing rank's lists are mapped into every rank (CUDA IPC) and each rank's emit kernel
-                writes its records straight into its own region over NVLink -- the transfer is the kernel's
-                TMA stores, there is no separate copy; only a small per-flush count vector is all-reduced.
-  gather_lists  the lists stay local and are collected afterwards with NCCL send / recv (also what the gloo
-                CPU tests exercise).
+  DeliveredLists  the library delivers inside the frame (t3d_gather_*): each shard's emit kernel stores a 36-byte
+                  compact form of its vertices straight into the issuing rank's memory over NVLink (TMA bulk stores) and
+                  posts to a mailbox there; the issuing rank's frame ends with the kernels that rebuild the lists.  No
+                  collective, no host round trip per frame.
+  gather_lists    the lists stay local and are collected afterwards with NCCL send / recv (also what the gloo
+                  CPU tests exercise).
 
 torch.distributed is plumbing only (NCCL on GPUs, gloo in CPU tests)."""
 from __future__ import annotations
@@ -98,88 +99,74 @@ def gather_lists(local: List[torch.Tensor], flush_table: List[Tuple[int, int]], 
     return None, None
 
 
-class SharedLists:
-    """Colour / depth lists of the issuing rank `dst`, one fixed-capacity region per rank, mapped into every rank.
+def delivered_flush_table(owners: List[int], draw_flush: List[List[int]], survivors: List, capacity: int) -> Dict[int, Tuple[int, int]]:
+    """Where every flush's vertices are in the delivered lists (t3d_gather_*): global flush id -> (first_vertex, vertex_count).
 
-    After construction every rank's GeometryDevice emits into region `rank` (t3d_set_output_target).  `collect`
-    exchanges the per-flush vertex counts and, on `dst`, returns views of the complete lists plus the table
-    global_flush_id -> (first_vertex, vertex_count): region r starts at vertex r * capacity, a rank's flushes
-    sit there in ascending global id.
+    owners:      Camera.FlushOwnerRanks(): for every flush of the frame, the rank that ran it
+    draw_flush:  Camera.ShardDrawFlushes(): per rank, the flush of every draw it submitted, in submit order
+    survivors:   per rank, the surviving triangles of every submitted draw (t3d_gather_rank_stats, column 2)
+    capacity:    vertices per rank region: rank r's vertices start at r * capacity, its flushes follow each other in ascending id
+    """
+    import numpy as np
+    table: Dict[int, Tuple[int, int]] = {}
+    n_flush = len(owners)
+    for r in range(len(draw_flush)):
+        dfl = np.asarray(draw_flush[r], dtype=np.int64)
+        sv = np.asarray(survivors[r], dtype=np.int64).reshape(-1)
+        assert len(dfl) == len(sv), "one survivor count per submitted draw"
+        counts = np.bincount(dfl, weights=3 * sv, minlength=n_flush).astype(np.int64) if len(dfl) else np.zeros(n_flush, np.int64)
+        cursor = r * int(capacity)
+        for f in range(n_flush):
+            if owners[f] == r:
+                table[f] = (cursor, int(counts[f]))
+                cursor += int(counts[f])
+    return table
+
+
+class DeliveredLists:
+    """The draw lists of a sharded frame on the rank `dst` that issues the draws, delivered inside the frame by the library
+    (include/t3dgeo.h: t3d_gather_*): every shard's emit kernel stores a 36-byte compact form of its vertices straight into
+    dst's memory over NVLink and posts the frame to a mailbox there; dst's frame ends with the kernels that rebuild the 96-byte
+    colour / depth records.  No collective and no host round trip per frame: torch.distributed only carries the three CUDA IPC
+    handles at construction.  All ranks render the same number of frames, in lockstep.
     """
 
-    def __init__(self, device, device_index: int, vertex_capacity: int, dst: int = 0, group=None, compact_depth: bool = True,
-                 render_depth: bool = True):
+    def __init__(self, device, device_index: int, vertex_capacity: int, draw_capacity: int, dst: int = 0, group=None):
         self.group, self.dst, self.device = group, dst, device
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.dev = torch.device("cuda", device_index)
-        cap = torch.tensor([int(vertex_capacity)], dtype=torch.int64, device=self.dev)
+        cap = torch.tensor([int(vertex_capacity), int(draw_capacity)], dtype=torch.int64, device=self.dev)
         dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
-        self.capacity = (int(cap.item()) + 255) // 256 * 256
-        nbytes = self.world * self.capacity * 48
+        self.capacity = (int(cap[0].item()) + 255) // 256 * 256
+        self.draw_capacity = max(int(cap[1].item()), 1)
         payload = [None]
         if self.rank == dst:
-            self.color_ptr, hc = device.SharedAlloc(nbytes)
-            self.depth_ptr, hd = device.SharedAlloc(nbytes)
-            payload = [(hc, hd)]
+            payload = [device.GatherAlloc(self.world, self.capacity, self.draw_capacity)]
         dist.broadcast_object_list(payload, src=dst, group=group)
-        if self.rank != dst:
-            hc, hd = payload[0]
-            self.color_ptr = device.SharedOpen(hc)
-            self.depth_ptr = device.SharedOpen(hd)
-        off = self.rank * self.capacity * 48
-        device.SetOutputTarget(self.color_ptr + off, self.depth_ptr + off, 0, self.capacity)
-        # compact depth: the depth list is the colour list with (d, d, d, 1) for a colour, so the other ranks ship one float per
-        # vertex instead of the second list (52 instead of 96 bytes per vertex into dst) and dst rebuilds the records
-        self.compact = bool(compact_depth) and self.world > 1
-        self.render_depth = bool(render_depth)
-        if self.compact:
-            payload = [None]
-            if self.rank == dst:
-                self.scalar_ptr, hs = device.SharedAlloc(self.world * self.capacity * 4)
-                payload = [hs]
-            dist.broadcast_object_list(payload, src=dst, group=group)
-            if self.rank != dst:
-                self.scalar_ptr = device.SharedOpen(payload[0])
-                device.SetOutputCompactDepth(self.scalar_ptr + self.rank * self.capacity * 4)
-        self.nbytes = nbytes
-        self._meta_host = None
-        self._meta_dev = None
+        device.GatherAttach(self.world, self.rank, dst, self.capacity, self.draw_capacity, None if self.rank == dst else payload[0])
+        dist.barrier(group=group)
+        self.attached = True
 
-    def collect(self, flush_table: List[Tuple[int, int]], n_flushes_total: int):
-        """Call after the frame has completed on this rank (Camera.RenderScene with DownloadResults = False waits
-        for it).  The all-reduce doubles as the barrier: when it returns on `dst`, every rank's emit has finished."""
-        if self._meta_host is None or self._meta_host.numel() != n_flushes_total:
-            self._meta_host = torch.zeros(n_flushes_total, dtype=torch.int64).pin_memory()
-            self._meta_dev = torch.zeros(n_flushes_total, dtype=torch.int64, device=self.dev)
-        mh = self._meta_host.numpy()
-        mh[:] = 0
-        if flush_table:
-            import numpy as np
-            ft = np.asarray(flush_table, dtype=np.int64)
-            mh[ft[:, 0]] = ((self.rank + 1) << 40) + ft[:, 1]
-        self._meta_dev.copy_(self._meta_host, non_blocking=True)
-        dist.all_reduce(self._meta_dev, op=dist.ReduceOp.SUM, group=self.group)
+    def results(self, cam):
+        """On dst, after Camera.RenderScene: ([colour list, depth list] as uint8 CUDA tensors over the whole shared allocation,
+        {global flush id: (first_vertex, vertex_count)}).  Waits for every shard's frame.  Other ranks: (None, None)."""
         if self.rank != self.dst:
             return None, None
-        meta = self._meta_dev.cpu().tolist()
-        table: Dict[int, Tuple[int, int]] = {}
-        cursor = [r * self.capacity for r in range(self.world)]
-        for fid, v in enumerate(meta):
-            if v == 0:
-                continue
-            owner, cnt = (v >> 40) - 1, v & ((1 << 40) - 1)
-            table[fid] = (cursor[owner], int(cnt))
-            cursor[owner] += int(cnt)
-        if self.compact:        # rebuild the other ranks' depth records from their colour records and depth values
-            for r in range(self.world):
-                n = cursor[r] - r * self.capacity
-                if r != self.dst and n:
-                    self.device.ExpandDepthList(self.color_ptr + r * self.capacity * 48, self.scalar_ptr + r * self.capacity * 4,
-                                                self.depth_ptr + r * self.capacity * 48, n, self.render_depth)
-        lists = [torch.as_tensor(DeviceArray(self.color_ptr, self.nbytes), device=self.dev),
-                 torch.as_tensor(DeviceArray(self.depth_ptr, self.nbytes), device=self.dev)]
+        res = self.device.GatherResults()
+        draw_flush = cam.ShardDrawFlushes()
+        surv = [self.device.GatherRankStats(r, len(draw_flush[r]))[:, 2] for r in range(self.world)]
+        table = delivered_flush_table(cam.FlushOwnerRanks(), draw_flush, surv, res["capacity"])
+        for r in range(self.world):
+            n = sum(c for f, (_, c) in table.items() if cam.FlushOwnerRanks()[f] == r)
+            assert n == res["n_vertices"][r], ("rank %d delivered %d vertices, its statistics add up to %d" % (r, res["n_vertices"][r], n))
+        nbytes = self.world * res["capacity"] * 48
+        lists = [torch.as_tensor(DeviceArray(res["color"], nbytes), device=self.dev), torch.as_tensor(DeviceArray(res["depth"], nbytes), device=self.dev)]
         return lists, table
 
     def release(self):
-        self.device.SetOutputTarget(0, 0, 0, 0)      # also drops the compact-depth redirection
+        if self.attached:
+            dist.barrier(group=self.group)
+            self.device.GatherDetach()
+            dist.barrier(group=self.group)
+            self.attached = False

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 vs="$@"; [ -z "$vs" ] && vs=$(ls build/variants)
 for v in $vs; do
-  out=$(LD_LIBRARY_PATH=$PWD/build/variants/$v:$LD_LIBRARY_PATH timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline ${BENCH_ARGS} 2>&1 | tail -1)
+  out=$(LD_LIBRARY_PATH=$PWD/build/variants/$v:$LD_LIBRARY_PATH timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra ${BENCH_ARGS} 2>&1 | tail -1)
   python - "$v" "$out" <<'PY'
 import json, sys
 v, out = sys.argv[1], sys.argv[2]
