@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 3      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points */
+#define T3D_ABI_VERSION 4      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points; 4: t3d_submit_instances */
 
 enum {
     T3D_OK            =  0,
@@ -194,6 +194,15 @@ typedef struct t3d_draw {
     uint32_t reserved1;
 } t3d_draw;
 
+/* One of a run of Models that differ only in where they are and in their colour (particles and other DynamicBatch children,
+ * instanced scenery): the Model's own Node.position / Node.scale (node.go:19-21) and Model.Color.  40 bytes here; what crosses
+ * PCIe is 32 bytes per instance when every scale of the frame is uniform (x == y == z), 64 otherwise. */
+typedef struct t3d_instance {
+    float position[3];              /* node.position (local) */
+    float scale[3];                 /* node.scale (local) */
+    float color[4];                 /* model.Color */
+} t3d_instance;
+
 /* Per-draw result; `first_vertex` indexes the concatenated lists. */
 typedef struct t3d_draw_result {
     uint64_t first_vertex;
@@ -310,6 +319,17 @@ int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t
 int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset);
 /* Replaces: one render(rp) call (camera.go:1507-1827) per element, in render order. */
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
+/* Replaces: n render(rp) calls (camera.go:2083-2100: the children of a DynamicBatch owner; any run of Models sharing mesh,
+ * part, material and parent) TOGETHER WITH the Node.Transform() of each of those Models (node.go:572-583): the device builds
+ *     transform_i = Scale(scale_i) . rotation . Translate(position_i) [. parent]
+ * with the reference's Matrix4.Mult, operation for operation, instead of receiving 16 floats per Model.  Equivalent to
+ * t3d_submit_draws of n copies of *proto with that transform, color = instances[i].color x proto->color (component-wise: pass
+ * Material.Color, or ones without a material, in proto->color) and T3D_DRAW_CONTINUE_FLUSH set on every copy but the first
+ * (which keeps proto's flag).  proto->transform is ignored; proto->world_rotation is every instance's (they share rotation and
+ * parent).  rotation16: the Node.rotation the instances share, NULL = identity; parent16: parent.Transform(), NULL = the
+ * Models have no parent (node.go:581).  Both must be affine (column 3 = 0,0,0,1), as every Node.Transform() of a scene graph is. */
+int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16,
+                         const t3d_instance* instances, uint32_t n);
 /* Replaces: Model.ProcessVertices + the lighting and emit loops for all submitted draws.
  * Asynchronous: returns after enqueueing on the context's stream. */
 int t3d_frame_execute(t3d_ctx* ctx);
@@ -399,6 +419,9 @@ int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matri
 int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled);
 /* Number of kernels launched by the last t3d_frame_execute. */
 int t3d_debug_last_launch_count(t3d_ctx* ctx);
+/* Profiling builds (-DT3D_VERTEX_TRACE) only, T3D_E_UNSUPPORTED otherwise: 16 nanosecond time stamps per block of the last
+ * k_vertex launch (t3d_kernels.cu lists them), for the first n_blocks <= 1024 blocks. */
+int t3d_debug_vertex_trace(t3d_ctx* ctx, unsigned long long* out, uint32_t n_blocks);
 /* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
 void* t3d_debug_stream(t3d_ctx* ctx);
 /* Algorithmic bytes of the fused vertex kernel for the last frame (DESIGN.md roofline figure). */

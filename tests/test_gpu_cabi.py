@@ -224,3 +224,116 @@ def test_volume_cell_lights_and_subdivision_call_rules(abi):
     base = np.zeros(1, np.uint32)
     md.tri_sub_base = base.ctypes.data_as(C.POINTER(C.c_uint32))
     assert lib.t3d_mesh_upload(ctx, C.c_uint64(21), C.c_uint32(1), C.byref(md)) == T3D_E_INVALID and b"all five" in lib.t3d_last_error(ctx)
+
+
+# ---- t3d_submit_instances: the device builds Node.Transform (node.go:577-583) -------------------------------------------
+class Instance(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("scale", C.c_float * 3), ("color", C.c_float * 4)]
+
+
+def _go_mult(a, b):
+    """Matrix4.Mult (matrix_amd64.s:4-81 / matrix_none.go:6-32): row i = sum_k a[i][k] * b[k], k ascending, float32, multiply then add."""
+    out = np.zeros((4, 4), np.float32)
+    for i in range(4):
+        acc = np.float32(a[i, 0]) * b[0]
+        for k in range(1, 4):
+            acc = (acc + np.float32(a[i, k]) * b[k]).astype(np.float32)
+        out[i] = acc
+    return out
+
+
+def _node_transform(pos, scale, rot, parent):
+    m = _go_mult(np.diag(np.array([scale[0], scale[1], scale[2], 1], np.float32)), rot)
+    t = np.eye(4, dtype=np.float32); t[3, :3] = pos
+    m = _go_mult(m, t)
+    return _go_mult(m, parent) if parent is not None else m
+
+
+def _rot_y(a):
+    c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+    return np.array([[c, 0, -s, 0], [0, 1, 0, 0], [s, 0, c, 0], [0, 0, 0, 1]], np.float32)
+
+
+def _frame(lib, ctx, submit):
+    cam, world = _camera(), World()
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    submit()
+    assert lib.t3d_frame_execute(ctx) == T3D_OK, lib.t3d_last_error(ctx)
+    out = FrameOutput()
+    assert lib.t3d_frame_results(ctx, C.byref(out), None) == T3D_OK, lib.t3d_last_error(ctx)
+    n = int(out.n_vertices)
+    col = np.ctypeslib.as_array(out.color_list, shape=(max(n, 1), 12))[:n].copy()
+    dep = np.ctypeslib.as_array(out.depth_list, shape=(max(n, 1), 12))[:n].copy()
+    res = [(out.draws[i].first_vertex, out.draws[i].vertex_count, out.draws[i].min_depth, out.draws[i].max_depth) for i in range(out.n_draws)]
+    return col, dep, res
+
+
+@pytest.mark.parametrize("n,uniform,with_parent,with_rotation,mixed", [
+    (40, True, False, False, False),        # small frame: the host expands the instances (same operations)
+    (3000, True, False, False, False),      # a frame of nothing but uniformly scaled instances: 32-byte payloads
+    (3000, False, True, True, False),       # non-uniform scale, shared rotation, parent: 64-byte payloads
+    (2500, True, True, False, True),        # instances between ordinary draws
+])
+def test_instances_equal_draws_bit_for_bit(abi, n, uniform, with_parent, with_rotation, mixed):
+    lib, ctx = abi
+    lib.t3d_submit_instances.restype = C.c_int
+    md, keep = _triangle_mesh()
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(7), C.c_uint32(1), C.byref(md)) == T3D_OK, lib.t3d_last_error(ctx)
+    rng = np.random.default_rng(n)
+    pos = rng.uniform((-6, -3, -20), (6, 3, 2), (n, 3)).astype(np.float32)
+    scl = rng.uniform(0.2, 1.5, (n, 3)).astype(np.float32)
+    scl[::7, 0] *= -1          # mirrored instances: products with -0
+    if uniform:
+        scl[:] = scl[:, :1]
+    colr = rng.uniform(0.1, 1.0, (n, 4)).astype(np.float32)
+    rot = _rot_y(0.7) if with_rotation else np.eye(4, dtype=np.float32)
+    parent = _node_transform((0.5, -0.25, 1.0), (1.0, 2.0, 1.0), _rot_y(-0.3), None) if with_parent else None
+    mat_color = np.array([0.9, 0.8, 0.7, 1.0], np.float32)
+    extra = _draw(); extra.transform[12] = 1.5
+
+    def as_instances():
+        if mixed:
+            assert lib.t3d_submit_draws(ctx, C.byref(extra), C.c_uint32(1)) == T3D_OK
+        proto = _draw(); proto.color[:] = mat_color.tolist()
+        inst = (Instance * n)()
+        for i in range(n):
+            inst[i].position[:] = pos[i].tolist(); inst[i].scale[:] = scl[i].tolist(); inst[i].color[:] = colr[i].tolist()
+        r16 = (C.c_float * 16)(*rot.reshape(-1).tolist())
+        p16 = (C.c_float * 16)(*parent.reshape(-1).tolist()) if parent is not None else None
+        assert lib.t3d_submit_instances(ctx, C.byref(proto), r16 if with_rotation else None, p16, inst, C.c_uint32(n)) == T3D_OK, lib.t3d_last_error(ctx)
+        if mixed:
+            assert lib.t3d_submit_draws(ctx, C.byref(extra), C.c_uint32(1)) == T3D_OK
+
+    def as_draws():
+        if mixed:
+            assert lib.t3d_submit_draws(ctx, C.byref(extra), C.c_uint32(1)) == T3D_OK
+        arr = (Draw * n)()
+        for i in range(n):
+            d = _draw()
+            d.transform[:] = _node_transform(pos[i], scl[i], rot, parent).reshape(-1).tolist()
+            d.color[:] = (colr[i] * mat_color).astype(np.float32).tolist()
+            d.flags = 0 if i == 0 else (1 << 10)        # T3D_DRAW_CONTINUE_FLUSH
+            arr[i] = d
+        assert lib.t3d_submit_draws(ctx, arr, C.c_uint32(n)) == T3D_OK, lib.t3d_last_error(ctx)
+        if mixed:
+            assert lib.t3d_submit_draws(ctx, C.byref(extra), C.c_uint32(1)) == T3D_OK
+
+    ci, di, ri = _frame(lib, ctx, as_instances)
+    cd, dd, rd = _frame(lib, ctx, as_draws)
+    assert len(ci) == len(cd) and len(ci) > 0
+    assert np.array_equal(ci.view(np.uint32), cd.view(np.uint32)) and np.array_equal(di.view(np.uint32), dd.view(np.uint32))
+    assert ri == rd
+
+
+def test_instances_reject_what_they_cannot_express(abi):
+    lib, ctx = abi
+    lib.t3d_submit_instances.restype = C.c_int
+    cam, world = _camera(), World()
+    assert lib.t3d_frame_begin(ctx, C.byref(cam), C.byref(world)) == T3D_OK
+    proto = _draw(); inst = (Instance * 1)()
+    bad = np.eye(4, dtype=np.float32); bad[0, 3] = 0.5
+    b16 = (C.c_float * 16)(*bad.reshape(-1).tolist())
+    assert lib.t3d_submit_instances(ctx, C.byref(proto), b16, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED and b"affine" in lib.t3d_last_error(ctx)
+    proto.flags = 1 << 3     # T3D_DRAW_SKINNED
+    assert lib.t3d_submit_instances(ctx, C.byref(proto), None, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED
+    assert lib.t3d_frame_execute(ctx) == T3D_OK

@@ -138,6 +138,10 @@ struct t3d_ctx {
     std::vector<LightList> lightLists;
     std::vector<uint32_t> drawTotalTris;
     std::vector<uint8_t> drawContinue;
+    // t3d_submit_instances: what the instances of one call share.  rot / parent: where the two matrices sit in hRot
+    struct TrsGroup { uint32_t rot, parent; Mat4 rotation, parentT; bool hasParent; };
+    std::vector<TrsGroup> trsGroups;
+    uint32_t nTrsDraws = 0; bool trsUniform = true;       // draws submitted as instances; all of them with x == y == z scale
     uint32_t vAcc = 0, tAcc = 0, luAcc = 0, nHistRows = 0;
     bool anyLit = false, anySkinned = false, anyUnbill = false, anySubdiv = false, bonesAffine = true, transformsAffine = true;
 
@@ -231,6 +235,20 @@ static cudaError_t upload_planes3(T** dst, const T* src, size_t n, size_t nPad, 
     cudaError_t e = cudaMalloc((void**)dst, 3 * nPad * sizeof(T));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, tmp.data(), 3 * nPad * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// PointLight.VertexLight skips an unranged light when `1 / d * energy < 0.001` (light.go:205-210; d the squared distance).  The
+// left side -- two float32 roundings -- never increases with d, so the vertices that pass are exactly those with d <= T for one
+// float T: found here by bisection over the positive floats with the reference's own expression, it lets the default lighting
+// take the decision exactly with one comparison and no division (k_prep_draws hands it on in LightU.range).
+static float energy_cutoff(float energy) {
+    if (energy != energy) return INFINITY;          // NaN never compares below: every vertex passes
+    if (!(energy > 0)) return 0.0f;                 // the product is <= 0 (or NaN only where 1 / d overflows): nothing at a distance passes
+    auto passes = [&](uint32_t bits) { float d; memcpy(&d, &bits, 4); volatile float q = 1.0f / d; volatile float v = q * energy; return !(v < 0.001f); };
+    uint32_t lo = 1u, hi = 0x7F800000u;             // passes(lo) (1 / d overflows to +inf), !passes(+inf) (1 / d is 0)
+    while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (passes(mid)) lo = mid; else hi = mid; }
+    float T; memcpy(&T, &lo, 4);
+    return T;
 }
 
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
@@ -524,6 +542,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->tmplSpanMax = 1;
     ctx->hPoses.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
+    ctx->trsGroups.clear(); ctx->nTrsDraws = 0; ctx->trsUniform = true;
     for (auto& u : ctx->volumeUse) u.clear();
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
@@ -565,6 +584,7 @@ int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_
                 total += ctx->volumeUseCount[slot];
             }
         }
+        if (L.type == T3D_LIGHT_POINT) L.forward[0] = energy_cutoff(L.energy);      // (a point light has no forward)
         ctx->hLights.p[off + i] = L;
     }
     ctx->hLights.n = off + n;          // reserve keeps the first n elements when it has to move the array
@@ -734,9 +754,49 @@ int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t
     return T3D_OK;
 }
 
+// Node.Transform of an instance (node.go:577-583): Scale . rotation . Translate [. parent], each step the reference's Mult.
+// Host and device (k_prep_draws) run this same sequence of t3d_math.h operations.
+static Mat4 instance_transform(const float* pos3, const float* scale3, const Mat4& rotation, const Mat4* parent) {
+    Mat4 M = m4_mult(m4_scale(scale3[0], scale3[1], scale3[2]), rotation);
+    Mat4 T = m4_identity(); T.m[3][0] = pos3[0]; T.m[3][1] = pos3[1]; T.m[3][2] = pos3[2];
+    M = m4_mult(M, T);
+    if (parent) M = m4_mult(M, *parent);
+    return M;
+}
+static bool affine16(const float* M) {
+    return M[3] == 0.0f && M[7] == 0.0f && M[11] == 0.0f && M[15] == 1.0f && !std::signbit(M[3]) && !std::signbit(M[7]) && !std::signbit(M[11]);
+}
+
+// draws[0..n) -- or, with `inst`, n instances of draws[0] belonging to ctx->trsGroups[group] (t3d_submit_instances)
+static int submit_range(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n, const t3d_instance* inst, uint32_t group);
+
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
     if (!ctx || (n && !draws)) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: NULL argument");
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_draws: not between frame_begin and frame_execute");
+    return submit_range(ctx, draws, n, nullptr, 0);
+}
+
+int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16, const t3d_instance* instances, uint32_t n) {
+    if (!ctx || !proto || (n && !instances)) return fail(ctx, T3D_E_INVALID, "t3d_submit_instances: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_instances: not between frame_begin and frame_execute");
+    if (proto->flags & T3D_DRAW_SKINNED) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_submit_instances: skinned models carry their own bones: submit them with t3d_submit_draws");
+    if ((rotation16 && !affine16(rotation16)) || (parent16 && !affine16(parent16)))
+        return fail(ctx, T3D_E_UNSUPPORTED, "t3d_submit_instances: rotation and parent transform must be affine (column 3 = 0, 0, 0, 1)");
+    if (!n) return T3D_OK;
+    t3d_ctx::TrsGroup G;
+    G.rotation = rotation16 ? m4_load(rotation16) : m4_identity();
+    G.hasParent = parent16 != nullptr;
+    G.parentT = parent16 ? m4_load(parent16) : m4_identity();
+    CU(ctx->hRot.reserve(ctx->hRot.n + 32));
+    G.rot = (uint32_t)(ctx->hRot.n / 16);
+    m4_store(G.rotation, ctx->hRot.p + ctx->hRot.n); ctx->hRot.n += 16;
+    G.parent = NO_ROTATION;
+    if (G.hasParent) { G.parent = (uint32_t)(ctx->hRot.n / 16); m4_store(G.parentT, ctx->hRot.p + ctx->hRot.n); ctx->hRot.n += 16; }
+    ctx->trsGroups.push_back(G);
+    return submit_range(ctx, proto, n, instances, (uint32_t)ctx->trsGroups.size() - 1);
+}
+
+static int submit_range(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n, const t3d_instance* inst, uint32_t group) {
     if (ctx->hDraws.size() + n >= 0xFFFFFFF0ull) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: too many draws in one frame");
     ctx->hDraws.reserve(ctx->hDraws.size() + n);
     CU(ctx->hVbase.reserve(ctx->hDraws.size() + n + 1));
@@ -745,7 +805,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
     ctx->drawTotalTris.reserve(ctx->drawTotalTris.size() + n); ctx->drawContinue.reserve(ctx->drawContinue.size() + n);
     const Mesh* lastMesh = nullptr; uint64_t lastMeshId = 0;
     for (uint32_t i = 0; i < n; i++) {
-        const t3d_draw& in = draws[i];
+        const t3d_draw& in = inst ? draws[0] : draws[i];
         if (!lastMesh || in.mesh_id != lastMeshId) {        // runs of instances share a mesh: one lookup per run
             auto it = ctx->meshes.find(in.mesh_id);
             if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_draws: unknown mesh");
@@ -758,6 +818,7 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: enum out of range");
         const PartInfo& pi = m.parts[in.part];
         uint32_t flags = in.flags;
+        if (inst && i) flags |= T3D_DRAW_CONTINUE_FLUSH;
         if (flags & T3D_DRAW_SKINNED) {
             if (!m.wgt) return fail(ctx, T3D_E_INVALID, "t3d_submit_draws: skinned draw of a mesh without weights");
             const bool posed = in.bone_offset & POSE_TAG;
@@ -779,9 +840,9 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
         R.lightIn = ll.off; R.lightCount = ll.count; R.lightTotal = ll.total; R.lightU = ctx->luAcc;
         R.sortMode = (flags & T3D_DRAW_HAS_MATERIAL) ? in.sort_mode : (uint8_t)T3D_SORT_BACK_TO_FRONT;   // camera.go:1540-1543
         R.lightingMode = in.lighting_mode; R.lvMode = in.light_volume_mode;
-        memcpy(R.transform, in.transform, 64);
+        if (!inst) { memcpy(R.transform, in.transform, 64); memcpy(R.color, in.color, 16); }
+        else for (int c = 0; c < 4; c++) R.color[c] = inst[i].color[c] * in.color[c];     // mpColor = model.Color x Material.Color (camera.go:1597-1601)
         memcpy(R.worldRot, in.world_rotation, 64);
-        memcpy(R.color, in.color, 16);
         R.srcW = in.src_w; R.srcH = in.src_h; R.maxSpan = m.maxSpan;
         R.nBones = (flags & T3D_DRAW_SKINNED) ? m.maxJoint + 1 : 0;
         if (flags & T3D_DRAW_LIT) { ctx->luAcc += ll.total; ctx->anyLit = true; }
@@ -816,17 +877,21 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
             memset(&S, 0, sizeof S);
             S.tmpl = tmplIndex; S.vbase = R.vbase; S.tbase = R.tbase; S.boneOffset = R.boneOffset; S.lightU = R.lightU;
             memcpy(S.transform, R.transform, 64); memcpy(S.color, R.color, 16);
-            if (ctx->transformsAffine) {       // Node.Transform() of an ordinary scene graph: column 3 is exactly (0, 0, 0, 1)
-                const float* M = R.transform;
-                ctx->transformsAffine = M[3] == 0.0f && M[7] == 0.0f && M[11] == 0.0f && M[15] == 1.0f &&
-                                        !std::signbit(M[3]) && !std::signbit(M[7]) && !std::signbit(M[11]);
+            if (inst) {         // position and scale instead of a matrix: expanded on the device, or at execute time when the frame is not shipped as runs
+                memcpy(S.transform, inst[i].position, 12); memcpy(S.transform + 3, inst[i].scale, 12);
+                S.pad[0] = group + 1;
+                ctx->nTrsDraws++;
+                if (!(inst[i].scale[0] == inst[i].scale[1] && inst[i].scale[1] == inst[i].scale[2])) ctx->trsUniform = false;
+            } else if (ctx->transformsAffine) {       // Node.Transform() of an ordinary scene graph: column 3 is exactly (0, 0, 0, 1)
+                ctx->transformsAffine = affine16(R.transform);
             }
             // the world rotation only feeds a directional light's workingModelRotation of an unskinned, lit draw (light.go:326-330)
             S.rot = NO_ROTATION;
             if ((flags & T3D_DRAW_LIT) && !(flags & T3D_DRAW_SKINNED) && ll.total) {
                 bool sun = false;
                 for (uint32_t k = 0; k < ll.total && !sun; k++) sun = ctx->hLights.p[ll.off + k].type == T3D_LIGHT_DIRECTIONAL;
-                if (sun) {
+                if (sun && inst && i) S.rot = ctx->hSlim.p[ctx->hSlim.n - 1].rot;      // instances share their world rotation: shipped once
+                else if (sun) {
                     S.rot = (uint32_t)(ctx->hRot.n / 16);
                     CU(ctx->hRot.reserve(ctx->hRot.n + 16));
                     memcpy(ctx->hRot.p + ctx->hRot.n, R.worldRot, 64);
@@ -947,6 +1012,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     ctx->launches = 0;
     ctx->executed = true;
     ctx->stagesTimed = ctx->stageTimings;
+    ctx->fc.approxLighting = ctx->exactLighting ? 0u : 1u;
     if (ctx->gather.active) {
         t3d_ctx::Gather& G = ctx->gather;
         G.serial++;
@@ -1045,14 +1111,14 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                 if (!ctx->hRuns.empty()) {
                     DrawRun& U = ctx->hRuns.back();
                     const uint32_t i = d - U.first;
-                    if (S[d].tmpl == U.tmpl && ((S[d].rot != NO_ROTATION) == (U.rot != NO_ROTATION))) {
+                    if (S[d].tmpl == U.tmpl && ((S[d].rot != NO_ROTATION) == (U.rot != NO_ROTATION)) && S[d].pad[0] == U.pad[0]) {
                         if (U.count == 1) {      // the second draw of a run fixes the increments
                             U.dV = S[d].vbase - U.vbase; U.dT = S[d].tbase - U.tbase; U.dBone = S[d].boneOffset - U.boneOffset;
                             U.dLightU = S[d].lightU - U.lightU; U.dRot = U.rot != NO_ROTATION ? S[d].rot - U.rot : 0;
-                            extend = U.dRot <= 1 && (U.rot == NO_ROTATION || U.dRot == 1);
+                            extend = U.dRot <= 1;       // (0: instances sharing one world rotation)
                         } else {
                             extend = S[d].vbase == U.vbase + i * U.dV && S[d].tbase == U.tbase + i * U.dT && S[d].boneOffset == U.boneOffset + i * U.dBone &&
-                                     S[d].lightU == U.lightU + i * U.dLightU && (U.rot == NO_ROTATION || S[d].rot == U.rot + i);
+                                     S[d].lightU == U.lightU + i * U.dLightU && (U.rot == NO_ROTATION || S[d].rot == U.rot + i * U.dRot);
                         }
                     }
                     if (extend) U.count++;
@@ -1062,6 +1128,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                     DrawRun U; memset(&U, 0, sizeof U);
                     U.first = d; U.count = 1; U.tmpl = S[d].tmpl; U.vbase = S[d].vbase; U.tbase = S[d].tbase; U.boneOffset = S[d].boneOffset;
                     U.lightU = S[d].lightU; U.rot = S[d].rot;
+                    U.pad[0] = S[d].pad[0];         // t3d_submit_instances group + 1: k_prep_draws builds the run's transforms from position and scale
+                    if (U.pad[0]) { U.pad[1] = ctx->trsGroups[U.pad[0] - 1].rot; U.pad[2] = ctx->trsGroups[U.pad[0] - 1].parent; }
                     ctx->hRuns.push_back(U);
                 }
             }
@@ -1078,7 +1146,22 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             }
         }
         ctx->frameRunMode = runMode;
-        const size_t slimBytes = runMode ? 64 : ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
+        // Instances (t3d_submit_instances) travel as position + scale + colour when the frame is shipped as runs: 32 bytes each if
+        // the frame holds nothing else and every scale is uniform, else in the 64-byte payload slot of an ordinary draw.  A
+        // frame that is not shipped as runs gets their transforms from the host: the same sequence of operations (instance_transform).
+        const bool trsOnly = runMode && ctx->nTrsDraws == nDraws && ctx->trsUniform;
+        if (!runMode && ctx->nTrsDraws) {
+            for (uint32_t d = 0; d < nDraws; d++) {
+                DrawSlim& S = ctx->hSlim.p[d];
+                if (!S.pad[0]) continue;
+                const t3d_ctx::TrsGroup& G = ctx->trsGroups[S.pad[0] - 1];
+                float ps[6]; memcpy(ps, S.transform, 24);
+                m4_store(instance_transform(ps, ps + 3, G.rotation, G.hasParent ? &G.parentT : nullptr), S.transform);
+                S.pad[0] = 0;
+            }
+            ctx->nTrsDraws = 0;
+        }
+        const size_t slimBytes = runMode ? (trsOnly ? 32 : 64) : ctx->transformsAffine ? sizeof(DrawSlim) - 16 : sizeof(DrawSlim);    // affine transforms travel as 12 floats
         Seg head[6] = {{nullptr /* packed below */, slimBytes * (size_t)nDraws, 0}, {ctx->hTmpl.p, sizeof(DrawRec) * ctx->hTmpl.n, 0},
                        {ctx->hRot.p, 4ull * ctx->hRot.n, 0},
                        {ctx->hRuns.data(), runMode ? sizeof(DrawRun) * ctx->hRuns.size() : 0, 0},
@@ -1106,12 +1189,18 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         for (Seg& g : head) if (g.bytes && g.src) memcpy(ctx->hFrame.p + g.off, g.src, g.bytes);
         for (Seg& g : segs) if (g.bytes) memcpy(ctx->hFrame.p + headBytes + g.off, g.src, g.bytes);
         if (!ctx->transformsAffine) memcpy(ctx->hFrame.p, ctx->hSlim.p, sizeof(DrawSlim) * (size_t)nDraws);
+        else if (trsOnly) for (uint32_t d = 0; d < nDraws; d++) {       // {position, scale | colour}
+            const DrawSlim& S = ctx->hSlim.p[d];
+            uint8_t* o = ctx->hFrame.p + 32 * (size_t)d;
+            memcpy(o, S.transform, 16); memcpy(o + 16, S.color, 16);
+        }
         else for (uint32_t d = 0; d < nDraws; d++) {
             const DrawSlim& S = ctx->hSlim.p[d];
             uint8_t* o = ctx->hFrame.p + slimBytes * (size_t)d - (runMode ? 32 : 0);      // run mode: no header, payload only
             if (!runMode) memcpy(o, &S, 32);                            // header
             float* t = reinterpret_cast<float*>(o + 32);
-            for (int r = 0; r < 4; r++) { t[3 * r] = S.transform[4 * r]; t[3 * r + 1] = S.transform[4 * r + 1]; t[3 * r + 2] = S.transform[4 * r + 2]; }
+            if (S.pad[0]) { memcpy(t, S.transform, 24); memset(t + 6, 0, 24); }        // an instance: {position, scale x | scale y, z, - , - | - }
+            else for (int r = 0; r < 4; r++) { t[3 * r] = S.transform[4 * r]; t[3 * r + 1] = S.transform[4 * r + 1]; t[3 * r + 2] = S.transform[4 * r + 2]; }
             memcpy(o + 32 + 48, S.color, 16);
         }
         {
@@ -1232,7 +1321,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                               reinterpret_cast<const t3d_light*>(hf + ctx->frameLightsOff), ctx->pDraws, ctx->pDevRest, nDraws, ctx->frameRestBytes,
                               (uint32_t)ctx->hLights.n, ctx->fc, ctx->dLightsU.as<LightU>(), stats, win,
                               hf + ctx->frameBonesOff, ctx->pBones, ctx->frameBoneCount, ctx->bonesAffine, ctx->transformsAffine,
-                              ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr,
+                              ctx->pVbase, ctx->pTbase, ctx->frameRunMode ? hf + ctx->frameRunsOff : nullptr, (uint32_t)(ctx->frameSlimBytes / 16),
                               reinterpret_cast<const uint32_t*>(hf + ctx->frameBlockRunOff), ctx->tmplSpanMax, fused, nFused, b0, b1 - b0, b0 == 0, ctx->dTileCtr.as<uint32_t>());
             if (b0) ctx->launches += 1;
             b0 = b1;
@@ -1609,6 +1698,11 @@ int t3d_set_stage_timings(t3d_ctx* ctx, int enabled) {
 }
 
 int t3d_debug_last_launch_count(t3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int t3d_debug_vertex_trace(t3d_ctx* ctx, unsigned long long* out, uint32_t n_blocks) {
+    if (!ctx || !out) return T3D_E_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return T3D_E_CUDA;
+    return debug_vertex_trace(out, n_blocks) == 0 ? T3D_OK : fail(ctx, T3D_E_UNSUPPORTED, "t3d_debug_vertex_trace: the library was not built with -DT3D_VERTEX_TRACE");
+}
 void* t3d_debug_stream(t3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t t3d_debug_vertex_kernel_bytes(t3d_ctx* ctx) { return ctx ? ctx->vertexKernelBytes : 0; }
 int t3d_debug_frame_bytes(t3d_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {

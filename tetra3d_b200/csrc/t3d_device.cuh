@@ -33,15 +33,26 @@ struct FrameConst {
     // scene.library.autosubdivisionLevels (library.go:206-209): {DistanceSquared, MaximumTriangleSize}
     uint32_t nSubLevels;
     float subLevels[8][2];
+    // 1: default lighting (approximate reciprocals, colours within 1/255): k_prep_draws folds the per-light constants the fast
+    // light loops read and groups every draw's list by light type; 0: t3d_set_exact_lighting (lists stay in submit order)
+    uint32_t approxLighting;
 };
 
 // Resolved light as seen by one draw: light.beginRender/beginModel products (light.go:110-112,
 // 175-189, 322-330) plus the per-draw range skip of camera.go:1625-1629.
+//
+// Default (approximate) lighting re-purposes fields a light type does not otherwise read, for the list's own lights:
+//   point        range  = the squared distance beyond which the light is skipped: lightRangeSquared when range > 0, else the
+//                         largest d with !(1 / d * energy < 0.001) (light.go:205-210; found exactly by the host, t3d_submit_lights)
+//                range2 = lightRangeSquared when > 0, else +inf (the range falloff then multiplies by 1)
+//                fwd    = colour * energy * 2
+//   directional  wpos   = workingModelRotation rows . forward, range = its constant term (light.go:342-349 folded per draw)
+//   ambient      fwd    = colour * energy
 struct LightU {
     uint32_t type;          // T3D_LIGHT_*, or LIGHT_SKIP
     float color[3];
-    float energy;
     float wpos[3];          // PointLight.workingPosition
+    float energy;
     float range, range2;    // lightRange, lightRangeSquared
     float fwd[3];           // DirectionalLight.workingForward
     uint32_t volume;        // index into the context's volume table
@@ -87,7 +98,9 @@ struct __align__(16) DrawRec {
     const float*    keyNrm;
     const float*    keyW;       // k
     const SubdivMesh* subdiv;   // auto-subdivision data of the mesh, or nullptr
-    uint64_t        padP;       // keeps the float4-loaded arrays below 16B-aligned
+    // written by k_prep_draws under default lighting: the draw's LightU list is grouped [point | directional | ambient | skipped]
+    // (lightsSorted = 1) with these counts; 0: the list is in submit order and holds lightCount typed entries
+    uint16_t        nPoint, nSun, nAmbient, lightsSorted;
     uint32_t a0;                // first mesh vertex of the aligned range (multiple of 4)
     uint32_t nv;                // aligned vertex count (multiple of 4)
     uint32_t vbase;             // first slot in the per-frame vertex arenas (multiple of 4)

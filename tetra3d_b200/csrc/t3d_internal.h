@@ -24,7 +24,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
-                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
+                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, uint32_t runPayload16, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
                        const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk, uint32_t* tileCtr);
 #ifndef T3D_PREP_POSE_BATCHES
 #define T3D_PREP_POSE_BATCHES 4
@@ -37,6 +37,7 @@ void launch_vertex(cudaStream_t s, bool pdl, bool exactLighting, const DrawRec* 
                    const uint4* const tileLists[3], const uint32_t nTilesOf[3], uint32_t* tileCtr /* [4] zeroed by k_prep_draws */,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
+int debug_vertex_trace(unsigned long long* out, uint32_t nBlocks);      // -DT3D_VERTEX_TRACE builds only (else -1)
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats, bool subdiv);

@@ -56,6 +56,7 @@ static_assert(PREP_THREADS == POSE_THREADS, "pose blocks ride in k_prep_draws' g
 static const int PREP_DRAWS = 64;               // draws per block
 static const int PREP_TEMPLATES = 80;           // templates staged per block: the index window [tmin, tmin + 80) of its draws
 static const uint32_t PREP_SMEM_LIGHTS = 256;   // light lists up to this many entries are staged in shared memory
+static const uint32_t PREP_SORT_LIGHTS = 64;    // default lighting: draws with up to this many lights get their LightU list grouped by type
 static const int PREP_PARAM_BLOCKS = PREP_WINDOW_BLOCKS;
 static_assert(PREP_DRAWS == PREP_WINDOW_DRAWS, "t3d_internal.h: the host computes the windows per PREP_DRAWS draws");
 static const int REC16 = sizeof(DrawRec) / 16;
@@ -87,6 +88,7 @@ struct PrepFrame {
     uint32_t* devVbase; uint32_t* devTbase;     // [nDraws + 1] arena offsets per draw: written here from the records, not copied
     // run-length mode (t3d_device.cuh: DrawRun): hostSlim then holds 64-byte payloads {transform rows, colour}
     const uint4* hostRuns; const uint32_t* hostBlockRun; uint32_t runMode;
+    uint32_t pay16;                 // run mode: uint4 per payload -- 4, or 2 in a frame of nothing but uniformly scaled instances (t3d_submit_instances)
     uint32_t tmplCap, lightCap;     // templates / lights staged per block (<= PREP_TEMPLATES, PREP_SMEM_LIGHTS)
     uint32_t copyEnd;               // this launch's blocks [nPrepBlocks, copyEnd) copy (behind the pose blocks of k_prep_draws<true>)
     uint32_t* tileCtr;              // first launch of the frame: k_vertex's tile counters, zeroed here
@@ -171,15 +173,19 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
     if (pf.runMode) {
         // Round trip 1: this block's payloads (4 uint4 per draw: three of transform rows, one of colour) go straight into
         // the packed record layout {header 2 | transform 3 | colour 1}; the runs covering the block; the light table.
-        const uint4* src = pf.hostSlim + (size_t)d0 * 4;
+        const uint32_t pay16 = pf.pay16;
+        const uint4* src = pf.hostSlim + (size_t)d0 * pay16;
         const uint32_t r0 = pf.hostBlockRun[bid], r1 = pf.hostBlockRun[bid + 1];
         uint4 pv;
-        if (threadIdx.x < n * 4) pv = src[threadIdx.x];
+        if (threadIdx.x < n * pay16) pv = src[threadIdx.x];
         const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(pf.hostLights);
         uint32_t* ldst = reinterpret_cast<uint32_t*>(sL);
         const uint32_t nw = lightsStaged ? pf.nLightsIn * (uint32_t)(sizeof(t3d_light) / 4) : 0u;
         for (uint32_t i = threadIdx.x; i < nw; i += PREP_THREADS) ldst[i] = lsrc[i];
-        if (threadIdx.x < n * 4) sSraw[(threadIdx.x >> 2) * s16 + 2 + (threadIdx.x & 3)] = pv;
+        if (threadIdx.x < n * pay16) {      // 64-byte payloads fill slots 2-5; a 32-byte instance payload is {position, scale | colour}: slots 2 and 5
+            const uint32_t kk = pay16 == 4 ? threadIdx.x >> 2 : threadIdx.x >> 1, j = pay16 == 4 ? threadIdx.x & 3 : threadIdx.x & 1;
+            sSraw[kk * s16 + (pay16 == 4 ? 2 + j : j ? 5 : 2)] = pv;
+        }
         // Round trip 2: the runs [r0, r1] (at most one per draw), parked where the rotations will go
         const uint32_t nR = min(r1 - r0 + 1, (uint32_t)PREP_DRAWS);       // a 65th run could only start at the next block's first draw
         if (threadIdx.x < nR * 4) sRot[threadIdx.x] = pf.hostRuns[(size_t)r0 * 4 + threadIdx.x];
@@ -194,6 +200,30 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
             uint32_t* h = reinterpret_cast<uint32_t*>(sSraw + threadIdx.x * s16);      // DrawSlim header: tmpl vbase tbase boneOffset | lightU rot pad pad
             h[0] = U.tmpl; h[1] = U.vbase + i * U.dV; h[2] = U.tbase + i * U.dT; h[3] = U.boneOffset + i * U.dBone;
             h[4] = U.lightU + i * U.dLightU; h[5] = U.dRot ? U.rot + i : U.rot; h[6] = 0; h[7] = 0;
+            if (U.pad[0]) {
+                // An instance (t3d_submit_instances): Node.Transform (node.go:577-583) from its position and scale and the run's
+                // rotation and parent transform -- Scale . rotation . Translate [. parent], each step the reference's Mult --
+                // written where an ordinary draw's 12 transform floats arrive.
+                float* f = reinterpret_cast<float*>(sSraw + threadIdx.x * s16 + 2);
+                const float px = f[0], py = f[1], pz = f[2], sx = f[3];
+                const float sy = pay16 == 4 ? f[4] : sx, sz = pay16 == 4 ? f[5] : sx;
+                const float4* rp = reinterpret_cast<const float4*>(pf.hostRot) + (size_t)U.pad[1] * 4;
+                Mat4 rot;
+#pragma unroll
+                for (int r = 0; r < 4; r++) { const float4 v = rp[r]; rot.m[r][0] = v.x; rot.m[r][1] = v.y; rot.m[r][2] = v.z; rot.m[r][3] = v.w; }
+                Mat4 M = m4_mult(m4_scale(sx, sy, sz), rot);
+                Mat4 T = m4_identity(); T.m[3][0] = px; T.m[3][1] = py; T.m[3][2] = pz;
+                M = m4_mult(M, T);
+                if (U.pad[2] != NO_ROTATION) {
+                    const float4* pp = reinterpret_cast<const float4*>(pf.hostRot) + (size_t)U.pad[2] * 4;
+                    Mat4 par;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) { const float4 v = pp[r]; par.m[r][0] = v.x; par.m[r][1] = v.y; par.m[r][2] = v.z; par.m[r][3] = v.w; }
+                    M = m4_mult(M, par);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) { f[3 * r] = M.m[r][0]; f[3 * r + 1] = M.m[r][1]; f[3 * r + 2] = M.m[r][2]; }
+            }
         }
         __syncthreads();            // the runs are consumed: the rotation window may overwrite them
     } else
@@ -204,7 +234,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         uint4 v[2], tv[T_SWEEPS], rv;
 #pragma unroll
         for (int u = 0; u < 2; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) v[u] = src[i]; }
-        const uint32_t t16 = known ? min(pf.win[bid][1], pf.tmplCap) * REC16 : 0u, r16 = known ? pf.win[bid][3] * 4 : 0u;
+        const uint32_t t16 = known ? min(pf.win[bid][1], pf.tmplCap) * REC16 : 0u, r16 = known ? min(pf.win[bid][3], (uint32_t)PREP_DRAWS) * 4 : 0u;
         const uint4* tsrc = pf.hostTmpl + (size_t)tmin * REC16;
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < t16) tv[u] = tsrc[i]; }
@@ -247,7 +277,9 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
 #pragma unroll
         for (int u = 0; u < T_SWEEPS; u++) { const uint32_t i = u * PREP_THREADS + threadIdx.x; if (i < n16) sT[i] = v[u]; }
         if (rmin != NO_ROTATION) {
-            const uint32_t r16 = (rmax - rmin + 1) * 4;      // at most one rotation per draw
+            // one rotation per draw at most, but instances share theirs and their runs' matrices sit in between: the window holds
+            // PREP_DRAWS rotations, a draw beyond it reads its rotation from the frame block
+            const uint32_t r16 = min(rmax - rmin + 1, (uint32_t)PREP_DRAWS) * 4;
             if (threadIdx.x < r16) sRot[threadIdx.x] = pf.hostRot[(size_t)rmin * 4 + threadIdx.x];
         }
         __syncthreads();
@@ -263,7 +295,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const uint32_t ti = S.tmpl - tmin;
         const uint4* src = ti < pf.tmplCap ? sT + ti * REC16 : pf.hostTmpl + (size_t)S.tmpl * REC16;
         const uint4* sl = reinterpret_cast<const uint4*>(&S);
-        const uint4* rs = S.rot != NO_ROTATION ? sRot + (size_t)(S.rot - rmin) * 4 : nullptr;
+        const uint4* rs = S.rot == NO_ROTATION ? nullptr : S.rot - rmin < (uint32_t)PREP_DRAWS ? sRot + (size_t)(S.rot - rmin) * 4 : pf.hostRot + (size_t)S.rot * 4;
         constexpr int TR16 = offsetof(DrawRec, transform) / 16, WR16 = offsetof(DrawRec, worldRot) / 16, CO16 = offsetof(DrawRec, color) / 16;
         constexpr int STR16 = offsetof(DrawSlim, transform) / 16;
         const bool packed = s16 != (uint32_t)SLIM16;
@@ -379,6 +411,33 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const bool skinned = flags & T3D_DRAW_SKINNED;
         const uint32_t nL = (flags & T3D_DRAW_LIT) ? R.lightTotal : 0;
         const uint32_t nOwn = R.lightCount;         // entries beyond are lights that LightVolume cells use (light.go:652-654)
+        // Default lighting: the list goes out grouped by type [point | directional | ambient | skipped] so that k_vertex's fast
+        // light loops need no type dispatch (the sums then run in a different order: colours stay within the 1/255 tolerance;
+        // t3d_set_exact_lighting keeps submit order).  Every thread of the draw classifies the whole list itself -- two passes
+        // over at most PREP_SORT_LIGHTS staged records -- which needs no shared scratch and no barrier.
+        const Vec3 modelPos = v3(R.transform[12], R.transform[13], R.transform[14]);
+        const float maxSpan = R.maxSpan;
+        auto skipped = [&](const t3d_light& L, uint32_t i) -> bool {        // camera.go:1625-1629: only for the list's own lights
+            if (!(L.type == T3D_LIGHT_POINT && L.range > 0 && i < nOwn)) return false;
+            const float dist = maxSpan + L.range;
+            return v3_dist2(modelPos, v3(L.position[0], L.position[1], L.position[2])) > dist * dist;
+        };
+        const bool approx = fc.approxLighting != 0;
+        bool sortable = approx && lightsStaged && nL == nOwn && nL <= PREP_SORT_LIGHTS;
+        uint32_t nP = 0, nS = 0, nA = 0;
+        if (sortable) {
+            for (uint32_t i = 0; i < nL; i++) {
+                const t3d_light& L = lightsIn[R.lightIn + i];
+                if (L.type == T3D_LIGHT_VOLUME) { sortable = false; break; }
+                if (skipped(L, i)) continue;
+                nP += L.type == T3D_LIGHT_POINT; nS += L.type == T3D_LIGHT_DIRECTIONAL; nA += L.type == T3D_LIGHT_AMBIENT;
+            }
+        }
+        if (role == 0) {
+            DrawRec& W = sR[k];
+            W.nPoint = sortable ? (uint16_t)nP : 0; W.nSun = sortable ? (uint16_t)nS : 0; W.nAmbient = sortable ? (uint16_t)nA : 0;
+            W.lightsSorted = sortable ? 1 : 0;
+        }
         if (role < nL) {
             const float* o = sInv + invStride * k;
             Mat4 r = m4_identity();
@@ -387,8 +446,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
 #pragma unroll
                 for (int j = 0; j < 3; j++) r.m[i][j] = o[i * 3 + j];
             const Vec3 invPS = v3(o[12], o[13], o[14]);
-            const Vec3 modelPos = v3(R.transform[12], R.transform[13], R.transform[14]);
-            const float maxSpan = R.maxSpan;
+            uint32_t cP = 0, cS = 0, cA = 0, cX = 0, seen = 0;      // lights of each group before entry `seen`
             for (uint32_t i = role; i < nL; i += 4) {
                 const t3d_light L = lightsIn[R.lightIn + i];
                 LightU U;
@@ -399,36 +457,47 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
                 U.range = L.range; U.range2 = L.range * L.range;         // light.go:277-280
                 U.fwd[0] = L.forward[0]; U.fwd[1] = L.forward[1]; U.fwd[2] = L.forward[2];
                 U.volume = L.volume & 0xFFFu; U.useFirst = L.volume >> 12; U.pad = 0;
+                const bool own = i < nOwn;
                 if (L.type == T3D_LIGHT_POINT) {
                     const Vec3 lp = v3(L.position[0], L.position[1], L.position[2]);
-                    if (L.range > 0 && i < nOwn) {                       // camera.go:1625-1629: only for the list's own lights
-                        const float dist = maxSpan + L.range;
-                        if (v3_dist2(modelPos, lp) > dist * dist) U.type = LIGHT_SKIP;
-                    }
+                    if (skipped(L, i)) U.type = LIGHT_SKIP;
                     const Vec3 wp = skinned ? lp : v3_add(m4_multvec(r, lp), invPS);   // light.go:183-187
                     U.wpos[0] = wp.X; U.wpos[1] = wp.Y; U.wpos[2] = wp.Z;
-                    // default (approximate) lighting only: colour * energy * 2 premultiplied, and the distance beyond which
-                    // `1 / d * energy < 0.001` holds (light.go:205-210) -- fields a point light does not otherwise use
-                    U.fwd[0] = L.color[0] * L.energy * 2.0f; U.fwd[1] = L.color[1] * L.energy * 2.0f; U.fwd[2] = L.color[2] * L.energy * 2.0f;
-                    U.pad = __float_as_uint(L.energy * 1000.0f);
+                    U.fwd[0] = U.fwd[1] = U.fwd[2] = 0;
+                    if (approx && own) {        // see LightU: the skip distance (forward[0]: t3d_submit_lights), the falloff's range, colour * energy * 2
+                        U.range = L.range > 0 ? U.range2 : L.forward[0];
+                        U.range2 = U.range2 > 0 ? U.range2 : __int_as_float(0x7F800000);
+                        U.fwd[0] = L.color[0] * L.energy * 2.0f; U.fwd[1] = L.color[1] * L.energy * 2.0f; U.fwd[2] = L.color[2] * L.energy * 2.0f;
+                    }
                 } else if (L.type == T3D_LIGHT_VOLUME) {
                     if ((flags & T3D_DRAW_HAS_MATERIAL) && R.lvMode == T3D_LV_OFF) U.type = LIGHT_SKIP;   // light.go:671-673
                 } else if (L.type == T3D_LIGHT_DIRECTIONAL) {
-                    // default lighting only: dot(n * workingModelRotation, forward) == dot(n, g) + c0 with g = rotation rows . forward,
-                    // folded per draw instead of per vertex (light.go:342-349); parked in wpos / range, which a sun does not use
-                    const uint8_t lm = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
-                    const float fx = L.forward[0], fy = L.forward[1], fz = L.forward[2];
-                    if (lm == T3D_LIGHTING_FIXED_NORMALS) { U.wpos[0] = U.wpos[1] = U.wpos[2] = 0; U.range = fx * fx + fy * fy + fz * fz; }
-                    else if (skinned) { U.wpos[0] = fx; U.wpos[1] = fy; U.wpos[2] = fz; U.range = 0; }
-                    else {
-                        const float* s = R.worldRot;        // the sun's workingModelRotation by now (role 3 above)
-                        U.wpos[0] = s[0] * fx + s[1] * fy + s[2] * fz; U.wpos[1] = s[4] * fx + s[5] * fy + s[6] * fz;
-                        U.wpos[2] = s[8] * fx + s[9] * fy + s[10] * fz; U.range = s[12] * fx + s[13] * fy + s[14] * fz;
+                    if (approx && own) {
+                        // dot(n * workingModelRotation, forward) == dot(n, g) + c0 with g = rotation rows . forward, folded per
+                        // draw instead of per vertex (light.go:342-349)
+                        const uint8_t lm = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
+                        const float fx = L.forward[0], fy = L.forward[1], fz = L.forward[2];
+                        if (lm == T3D_LIGHTING_FIXED_NORMALS) { U.wpos[0] = U.wpos[1] = U.wpos[2] = 0; U.range = fx * fx + fy * fy + fz * fz; }
+                        else if (skinned) { U.wpos[0] = fx; U.wpos[1] = fy; U.wpos[2] = fz; U.range = 0; }
+                        else {
+                            const float* s = R.worldRot;        // the sun's workingModelRotation by now (role 3 above)
+                            U.wpos[0] = s[0] * fx + s[1] * fy + s[2] * fz; U.wpos[1] = s[4] * fx + s[5] * fy + s[6] * fz;
+                            U.wpos[2] = s[8] * fx + s[9] * fy + s[10] * fz; U.range = s[12] * fx + s[13] * fy + s[14] * fz;
+                        }
                     }
                 } else if (L.type == T3D_LIGHT_AMBIENT) {
-                    U.fwd[0] = L.color[0] * L.energy; U.fwd[1] = L.color[1] * L.energy; U.fwd[2] = L.color[2] * L.energy;
+                    if (approx && own) { U.fwd[0] = L.color[0] * L.energy; U.fwd[1] = L.color[1] * L.energy; U.fwd[2] = L.color[2] * L.energy; }
                 }
-                lightsU[R.lightU + i] = U;
+                uint32_t at = i;
+                if (sortable) {
+                    for (; seen < i; seen++) {          // group sizes among the entries before this one
+                        const t3d_light& Lj = lightsIn[R.lightIn + seen];
+                        if (skipped(Lj, seen)) cX++;
+                        else { cP += Lj.type == T3D_LIGHT_POINT; cS += Lj.type == T3D_LIGHT_DIRECTIONAL; cA += Lj.type == T3D_LIGHT_AMBIENT; }
+                    }
+                    at = U.type == T3D_LIGHT_POINT ? cP : U.type == T3D_LIGHT_DIRECTIONAL ? nP + cS : U.type == T3D_LIGHT_AMBIENT ? nP + nS + cA : nP + nS + nA + cX;
+                }
+                lightsU[R.lightU + at] = U;
             }
         }
     }
@@ -583,15 +652,29 @@ __device__ __forceinline__ void skin_one(const Uniforms& U, float4 w, ushort4 j,
 #ifndef T3D_K1_MINBLOCKS
 #define T3D_K1_MINBLOCKS 3      // resident blocks per SM the generic kernel's register allocation aims for
 #endif
-static const int VERTEX_BLOCK = 256;                        // consumer threads of a k_vertex block == vertex slots per tile
-static const int VERTEX_THREADS = VERTEX_BLOCK + 32;        // + the producer warp
+static const int VERTEX_BLOCK = 256;                        // vertex slots per tile
+// consumer threads of a k_vertex block: the static fast class shades two vertices per thread (slots t and t + 128 of the tile),
+// which halves everything a warp pays per tile and per light -- barrier polls, stage bookkeeping, the loads of the uniforms
+// and of every light record -- for a kernel that is bound by instruction issue; the other classes keep one vertex per thread
+#ifndef T3D_K1_STATIC_CONSUMERS
+#define T3D_K1_STATIC_CONSUMERS 128
+#endif
+template <int MODE> struct VertexShape { static const int CONSUMERS = VERTEX_BLOCK; static const int THREADS = VERTEX_BLOCK + 32; };
+template <> struct VertexShape<1 /* K1_STATIC */> { static const int CONSUMERS = T3D_K1_STATIC_CONSUMERS; static const int THREADS = T3D_K1_STATIC_CONSUMERS + 32; };
+// tiles in flight per block: the static class has the small stage (7 KB) and the short tiles, so its producer runs furthest ahead
+#ifndef T3D_VERTEX_STAGES_STATIC
+#define T3D_VERTEX_STAGES_STATIC 3
+#endif
 #ifndef T3D_VERTEX_STAGES
 #define T3D_VERTEX_STAGES 2
 #endif
-static const int VERTEX_STAGES = T3D_VERTEX_STAGES;         // tiles in flight per block
+#ifndef T3D_MBAR_SLEEP
+#define T3D_MBAR_SLEEP 64       // ns a waiting warp sleeps between polls of a stage barrier (0: poll back to back)
+#endif
 static const int VERTEX_SMEM_LIGHTS = 16;       // light lists up to this long are staged in shared memory
 static const int VERTEX_SMEM_BONES = 64;        // skinned tiles: armatures of up to this many bones are staged in shared memory
 static_assert(VERTEX_BLOCK == (int)VERTEX_TILE, "t3d_internal.h: VERTEX_TILE must be the slots one k_vertex block covers");
+static_assert(VERTEX_BLOCK % T3D_K1_STATIC_CONSUMERS == 0 && T3D_K1_STATIC_CONSUMERS % 32 == 0, "whole warps, whole passes over a tile");
 
 // Everything one vertex needs from its draw: either the DrawRec / LightU records and the mesh / bone arrays in global
 // memory, or the stage the block's producer warp filled in shared memory (mvp rows 0-3, the sun's workingModelRotation rows
@@ -602,7 +685,7 @@ struct UniformsGlobal {
     __device__ __forceinline__ float4 mvp(int i) const { return ldg4(mvpP + 4 * i); }
     __device__ __forceinline__ float4 sun(int i) const { return ldg4(sunP + 4 * i); }
     __device__ __forceinline__ float4 light(uint32_t i) const { return __ldg(lightP + i); }
-    __device__ __forceinline__ uint32_t lightType(uint32_t i) const { return __ldg(reinterpret_cast<const uint32_t*>(lightP + i)); }
+    __device__ __forceinline__ float lightWord(uint32_t i) const { return __ldg(reinterpret_cast<const float*>(lightP + i)); }     // first word of float4 i
     __device__ __forceinline__ float4 weights() const { return ldg4(wgtP + 4 * (size_t)mv); }
     __device__ __forceinline__ ushort4 joints() const { return __ldg(reinterpret_cast<const ushort4*>(jntP + 4 * (size_t)mv)); }
     __device__ __forceinline__ float4 bone(uint32_t joint, int row) const { return __ldg(reinterpret_cast<const float4*>(bonesP + 16 * (size_t)joint) + row); }
@@ -612,7 +695,7 @@ struct UniformsShared {
     __device__ __forceinline__ float4 mvp(int i) const { return s[i]; }
     __device__ __forceinline__ float4 sun(int i) const { return s[4 + i]; }
     __device__ __forceinline__ float4 light(uint32_t i) const { return s[8 + i]; }
-    __device__ __forceinline__ uint32_t lightType(uint32_t i) const { return *reinterpret_cast<const uint32_t*>(s + 8 + i); }
+    __device__ __forceinline__ float lightWord(uint32_t i) const { return *reinterpret_cast<const float*>(s + 8 + i); }
     __device__ __forceinline__ float4 weights() const { return sWgt[ti]; }
     __device__ __forceinline__ ushort4 joints() const { return sJnt[ti]; }
     __device__ __forceinline__ float4 bone(uint32_t joint, int row) const { return sBones[4 * joint + row]; }
@@ -632,55 +715,69 @@ enum { K1_GENERIC = 0, K1_STATIC = 1, K1_SKINNED = 2 };
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// PointLight.VertexLight (light.go:191-258) with approximate reciprocals and fused multiply-adds; returns the factor the
-// light's premultiplied colour (colour * energy * 2, from k_prep_draws) is scaled by (0: no contribution).  The two cut-offs are
-// DECISIONS, not continuous quantities (a vertex on the wrong side of `1 / d * energy < 0.001` changes by up to 0.02), so they
-// are taken exactly as the reference takes them: the range test needs no division, and the energy test compares the (exact)
-// squared distance with energy * 1000 and falls back to the IEEE division inside a guard band of 4e-6 around it (practically
-// never).
+// PointLight.VertexLight (light.go:191-258) with approximate reciprocals and fused multiply-adds, branch-free; returns the factor
+// the light's premultiplied colour (colour * energy * 2, from k_prep_draws) is scaled by (0: no contribution).  The two cut-offs
+// are DECISIONS, not continuous quantities (a vertex on the wrong side of `1 / d * energy < 0.001` changes by up to 0.02), so they
+// are taken exactly as the reference takes them, on the exact squared distance: `cut` is lightRangeSquared for a ranged light
+// and otherwise the largest d that passes the reference's energy test (t3d_submit_lights finds it by bisection over the floats,
+// with the reference's two roundings), so one comparison decides either.  `r2eff` is lightRangeSquared or +inf: the range
+// falloff (light.go:247-249) of an unranged light saturates to 1.
 template <bool PLAIN>     // PLAIN: LightingModeDefault (the normal is the vertex normal, one-sided)
-__device__ __forceinline__ float point_light_factor_fast(float wx, float wy, float wz, float range, float range2, float cutoff, float energy,
-                                                         Vec3 P, Vec3 N, uint8_t lightingMode) {
+__device__ __forceinline__ float point_light_factor_fast(float wx, float wy, float wz, float cut, float r2eff, Vec3 P, Vec3 N, uint8_t lightingMode) {
     const float dx = wx - P.X, dy = wy - P.Y, dz = wz - P.Z;
     const float d2 = dx * dx + dy * dy + dz * dz;               // -fmad=false: the reference's distance, bit for bit
-    bool keep;
-    if (range > 0) keep = !(d2 > range2);
-    else {
-        keep = !(d2 > cutoff);
-        if (!(fabsf(d2 - cutoff) > cutoff * 4e-6f)) keep = !(1.0f / d2 * energy < 0.001f);      // also NaN
-    }
     const float rl = rsqrt_fast(d2);
     float ndl = __fmaf_rn(N.Z, dz, __fmaf_rn(N.Y, dy, N.X * dx));
     if (!PLAIN && lightingMode == T3D_LIGHTING_FIXED_NORMALS) ndl = d2 * rl;
     float diffuse = ndl * rl;
     if (!PLAIN && lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuse = fabsf(diffuse);
-    float f = diffuse * rcp_fast(__fmaf_rn(0.1f, d2, 1.0f));
-    if (range2 > 0) f *= __saturatef((range2 - d2) * rcp_fast(d2));
+    float f = fmaxf(diffuse, 0.0f) * rcp_fast(__fmaf_rn(0.1f, d2, 1.0f));      // diffuse <= 0 contributes nothing
+    f *= __saturatef((r2eff - d2) * (rl * rl));
     // Unit (vector.go:258-266) leaves vectors shorter than 1e-8 as they are: their contribution is below 1e-7
-    if (!(keep && d2 >= 1e-16f && diffuse > 0)) f = 0.0f;
-    return f;
+    return (d2 <= cut && d2 >= 1e-16f) ? f : 0.0f;
 }
 
-// The light loop of the fast classes with the default lighting arithmetic: per light one type word and the pre-folded fields
-// k_prep_draws left in the LightU record (premultiplied colours, the energy cut-off distance, the sun's forward in model space).
+// The light loops of the fast classes with the default lighting arithmetic.  k_prep_draws grouped the draw's LightU list by type
+// ([point | directional | ambient], `sorted`) and left pre-folded fields in the records (t3d_device.cuh: LightU), so each group
+// is a tight loop without a type dispatch; a list it left in submit order (more than PREP_SORT_LIGHTS entries) is walked entry
+// by entry.  Summation order differs from the reference's either way this arithmetic is used: within the 1/255 tolerance.
 template <bool PLAIN, class Uniforms>
-__device__ __forceinline__ float3 light_loop_fast(const Uniforms& U, uint32_t nL, Vec3 P, Vec3 N, uint8_t lightingMode) {
+__device__ __forceinline__ float3 light_loop_fast(const Uniforms& U, uint32_t nL, uint32_t nPoint, uint32_t nSun, uint32_t nAmbient, bool sorted,
+                                                  Vec3 P, Vec3 N, uint8_t lightingMode) {
     float lr = 0, lg = 0, lb = 0;
-    for (uint32_t li = 0; li < nL; li++) {
-        const uint32_t type = U.lightType(4 * li);
-        if (type == T3D_LIGHT_POINT) {                              // light.go:191-258
-            const float4 q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2), q3 = U.light(4 * li + 3);
-            const float f = point_light_factor_fast<PLAIN>(q1.y, q1.z, q1.w, q2.x, q2.y, q3.w, q1.x, P, N, lightingMode);
-            lr = __fmaf_rn(q2.z, f, lr); lg = __fmaf_rn(q2.w, f, lg); lb = __fmaf_rn(q3.x, f, lb);
-        } else if (type == T3D_LIGHT_DIRECTIONAL) {                 // light.go:332-360
-            const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
-            float f = __fmaf_rn(N.Z, q1.w, __fmaf_rn(N.Y, q1.z, __fmaf_rn(N.X, q1.y, q2.x)));
-            if (!PLAIN && lightingMode == T3D_LIGHTING_DOUBLE_SIDED) f = fabsf(f);
-            f = fmaxf(f, 0.0f) * q1.x;                              // diffuseFactor <= 0 contributes nothing
-            lr = __fmaf_rn(q0.y, f, lr); lg = __fmaf_rn(q0.z, f, lg); lb = __fmaf_rn(q0.w, f, lb);
-        } else if (type == T3D_LIGHT_AMBIENT) {                     // light.go:110-120
-            const float4 q2 = U.light(4 * li + 2), q3 = U.light(4 * li + 3);
-            lr += q2.z; lg += q2.w; lb += q3.x;
+    auto point = [&](uint32_t li) {                                 // light.go:191-258
+        const float4 q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
+        const float pb = U.lightWord(4 * li + 3);
+        const float f = point_light_factor_fast<PLAIN>(q1.x, q1.y, q1.z, q2.x, q2.y, P, N, lightingMode);
+        lr = __fmaf_rn(q2.z, f, lr); lg = __fmaf_rn(q2.w, f, lg); lb = __fmaf_rn(pb, f, lb);
+    };
+    auto sun = [&](uint32_t li) {                                   // light.go:332-360
+        const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1);
+        const float c0 = U.lightWord(4 * li + 2);
+        float f = __fmaf_rn(N.Z, q1.z, __fmaf_rn(N.Y, q1.y, __fmaf_rn(N.X, q1.x, c0)));
+        if (!PLAIN && lightingMode == T3D_LIGHTING_DOUBLE_SIDED) f = fabsf(f);
+        f = fmaxf(f, 0.0f) * q1.w;                                  // diffuseFactor <= 0 contributes nothing
+        lr = __fmaf_rn(q0.y, f, lr); lg = __fmaf_rn(q0.z, f, lg); lb = __fmaf_rn(q0.w, f, lb);
+    };
+    auto ambient = [&](uint32_t li) {                               // light.go:110-120
+        const float4 q2 = U.light(4 * li + 2);
+        lr += q2.z; lg += q2.w; lb += U.lightWord(4 * li + 3);
+    };
+    if (sorted) {
+        uint32_t li = 0;
+#pragma unroll 2
+        for (; li < nPoint; li++) point(li);
+#pragma unroll 1
+        for (const uint32_t e = li + nSun; li < e; li++) sun(li);
+#pragma unroll 1
+        for (const uint32_t e = li + nAmbient; li < e; li++) ambient(li);
+    } else {
+#pragma unroll 1
+        for (uint32_t li = 0; li < nL; li++) {
+            const uint32_t type = __float_as_uint(U.lightWord(4 * li));
+            if (type == T3D_LIGHT_POINT) point(li);
+            else if (type == T3D_LIGHT_DIRECTIONAL) sun(li);
+            else if (type == T3D_LIGHT_AMBIENT) ambient(li);
         }
     }
     return make_float3(lr, lg, lb);
@@ -689,8 +786,9 @@ __device__ __forceinline__ float3 light_loop_fast(const Uniforms& U, uint32_t nL
 // APPROX: lighting with approximate reciprocals (colours within 1/255, the default); !APPROX: the reference's arithmetic
 // operation by operation (bit-exact colours; t3d_set_exact_lighting).  Positions, depths and everything the cull and the
 // sort read are exact in both.
+struct LightGroups { uint32_t nPoint, nSun, nAmbient; bool sorted; };     // DrawRec.nPoint ... lightsSorted
 template <int MODE, bool APPROX, class Uniforms>
-__device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const uint32_t nL, const uint8_t lightingMode, const Uniforms U, const FrameConst& fc,
+__device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t flags, const uint32_t nL, const LightGroups G, const uint8_t lightingMode, const Uniforms U, const FrameConst& fc,
                                              const uint32_t slot, const uint32_t mv, Vec3 P, Vec3 N,
                                              const LightU* __restrict__ lightsU, const VolumeU* __restrict__ vols,
                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
@@ -773,20 +871,21 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
     float lr = 0, lg = 0, lb = 0;
     if constexpr (APPROX && FAST) {
         // (the sun's folded forward assumes the mode k_prep_draws saw, which is this one)
-        const float3 acc = lightingMode == T3D_LIGHTING_DEFAULT ? light_loop_fast<true>(U, nL, P, N, lightingMode) : light_loop_fast<false>(U, nL, P, N, lightingMode);
+        const float3 acc = lightingMode == T3D_LIGHTING_DEFAULT ? light_loop_fast<true>(U, nL, G.nPoint, G.nSun, G.nAmbient, G.sorted, P, N, lightingMode)
+                                                                : light_loop_fast<false>(U, nL, G.nPoint, G.nSun, G.nAmbient, G.sorted, P, N, lightingMode);
         lightOut[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f);
         return;
     }
     for (uint32_t li = 0; li < nL; li++) {
         const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
         const uint32_t type = __float_as_uint(q0.x);
-        const float cR = q0.y, cG = q0.z, cB = q0.w, energy = q1.x;
+        const float cR = q0.y, cG = q0.z, cB = q0.w, energy = q1.w;
         if (APPROX && type == T3D_LIGHT_POINT) {
             const float4 q3 = U.light(4 * li + 3);
-            const float f = point_light_factor_fast<false>(q1.y, q1.z, q1.w, q2.x, q2.y, q3.w, energy, P, N, lightingMode);
+            const float f = point_light_factor_fast<false>(q1.x, q1.y, q1.z, q2.x, q2.y, P, N, lightingMode);
             lr = __fmaf_rn(q2.z, f, lr); lg = __fmaf_rn(q2.w, f, lg); lb = __fmaf_rn(q3.x, f, lb);
         } else if (type == T3D_LIGHT_POINT) {                           // light.go:191-258
-            const Vec3 wp = v3(q1.y, q1.z, q1.w);
+            const Vec3 wp = v3(q1.x, q1.y, q1.z);
             const float range = q2.x, range2 = q2.y;
             Vec3 vertNormal = N;
             const float distance = v3_dist2(wp, P);
@@ -855,7 +954,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(64);        // a waiting warp must not eat the issue slots of the warps that shade
+        if (T3D_MBAR_SLEEP) __nanosleep(T3D_MBAR_SLEEP);        // a waiting warp must not eat the issue slots of the warps that shade
     }
 }
 // global -> shared bulk copy by the copy engine of the SM (TMA, 1-D), completion counted in bytes on `bar`
@@ -872,6 +971,9 @@ struct __align__(16) VStageDesc {
     uint32_t mv0;               // mesh vertex of slot `base` (staged tiles)
     uint32_t flags;             // staged tiles: the draw's flags, light count and lighting mode (what every vertex would otherwise
     uint32_t nLmode;            //   fetch from the draw record): lightCount | lightingMode << 16; NO_TILE in `base`: the list is exhausted
+    uint32_t groups;            // staged tiles: nPoint | nSun << 16
+    uint32_t groups2;           //   nAmbient | lightsSorted << 16
+    uint32_t pad[2];
 };
 static const uint32_t NO_TILE = 0xFFFFFFFFu;
 template <bool SKIN> struct __align__(128) VStage {
@@ -890,6 +992,78 @@ template <> struct __align__(128) VStage<true> {
     VStageDesc desc;
 };
 
+// Two vertices of a staged tile of the static fast class under default lighting with a grouped light list (the hot case:
+// instanced scenery, terrain): slots `ta` and `tb` of the tile, shaded together so that the draw's mvp and every light record
+// are loaded from shared memory once per pair.  The arithmetic per vertex is shade_vertex<K1_STATIC, true>'s, operation for
+// operation (positions exact, lighting through light_loop_fast's formulas).  `hasB`: slot tb exists (a draw's last tile is short).
+__device__ __forceinline__ void shade2_static(const VStage<false>& S, const VStageDesc& D, const uint32_t ta, const uint32_t tb, const bool hasB,
+                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut) {
+    const bool lit = (D.flags & T3D_DRAW_LIT) != 0;
+    const Vec3 Pa = v3(S.pos[0][ta], S.pos[1][ta], S.pos[2][ta]), Pb = v3(S.pos[0][tb], S.pos[1][tb], S.pos[2][tb]);
+    {   // clip = [x y z 1] * mvp (model.go:795-798) and the cull's perspective divide (model.go:866-875), as in shade_vertex
+        const float4 m0 = S.U[0], m1 = S.U[1], m2 = S.U[2], m3 = S.U[3];
+        float4 ca, cb;
+        ca.x = m0.x * Pa.X + m1.x * Pa.Y + m2.x * Pa.Z + m3.x; cb.x = m0.x * Pb.X + m1.x * Pb.Y + m2.x * Pb.Z + m3.x;
+        ca.y = m0.y * Pa.X + m1.y * Pa.Y + m2.y * Pa.Z + m3.y; cb.y = m0.y * Pb.X + m1.y * Pb.Y + m2.y * Pb.Z + m3.y;
+        ca.z = m0.z * Pa.X + m1.z * Pa.Y + m2.z * Pa.Z + m3.z; cb.z = m0.z * Pb.X + m1.z * Pb.Y + m2.z * Pb.Z + m3.z;
+        ca.w = m0.w * Pa.X + m1.w * Pa.Y + m2.w * Pa.Z + m3.w; cb.w = m0.w * Pb.X + m1.w * Pb.Y + m2.w * Pb.Z + m3.w;
+        float wa = ca.w, wb = cb.w;
+        if (wa < 0) wa = 0.000001f;
+        if (wb < 0) wb = 0.000001f;
+        clipOut[D.base + ta] = make_float4(ca.x / wa, ca.y / wa, ca.z, ca.w);
+        clipXY[D.base + ta] = make_float2(ca.x, ca.y);
+        if (hasB) {
+            clipOut[D.base + tb] = make_float4(cb.x / wb, cb.y / wb, cb.z, cb.w);
+            clipXY[D.base + tb] = make_float2(cb.x, cb.y);
+        }
+    }
+    if (!lit) return;
+    const Vec3 Na = v3(S.nrm[0][ta], S.nrm[1][ta], S.nrm[2][ta]), Nb = v3(S.nrm[0][tb], S.nrm[1][tb], S.nrm[2][tb]);
+    const float4* L = S.U + 8;
+    const uint32_t nPoint = D.groups & 0xFFFFu, nSun = D.groups >> 16, nAmbient = D.groups2 & 0xFFFFu;
+    float ar = 0, ag = 0, ab = 0, br = 0, bg = 0, bb = 0;
+    uint32_t li = 0;
+#pragma unroll 2
+    for (; li < nPoint; li++) {                                     // light.go:191-258
+        const float4 q1 = L[4 * li + 1], q2 = L[4 * li + 2];
+        const float pb = L[4 * li + 3].x;
+        const float fa = point_light_factor_fast<true>(q1.x, q1.y, q1.z, q2.x, q2.y, Pa, Na, T3D_LIGHTING_DEFAULT);
+        const float fb = point_light_factor_fast<true>(q1.x, q1.y, q1.z, q2.x, q2.y, Pb, Nb, T3D_LIGHTING_DEFAULT);
+        ar = __fmaf_rn(q2.z, fa, ar); ag = __fmaf_rn(q2.w, fa, ag); ab = __fmaf_rn(pb, fa, ab);
+        br = __fmaf_rn(q2.z, fb, br); bg = __fmaf_rn(q2.w, fb, bg); bb = __fmaf_rn(pb, fb, bb);
+    }
+#pragma unroll 1
+    for (const uint32_t e = li + nSun; li < e; li++) {              // light.go:332-360
+        const float4 q0 = L[4 * li], q1 = L[4 * li + 1];
+        const float c0 = L[4 * li + 2].x;
+        const float fa = fmaxf(__fmaf_rn(Na.Z, q1.z, __fmaf_rn(Na.Y, q1.y, __fmaf_rn(Na.X, q1.x, c0))), 0.0f) * q1.w;
+        const float fb = fmaxf(__fmaf_rn(Nb.Z, q1.z, __fmaf_rn(Nb.Y, q1.y, __fmaf_rn(Nb.X, q1.x, c0))), 0.0f) * q1.w;
+        ar = __fmaf_rn(q0.y, fa, ar); ag = __fmaf_rn(q0.z, fa, ag); ab = __fmaf_rn(q0.w, fa, ab);
+        br = __fmaf_rn(q0.y, fb, br); bg = __fmaf_rn(q0.z, fb, bg); bb = __fmaf_rn(q0.w, fb, bb);
+    }
+#pragma unroll 1
+    for (const uint32_t e = li + nAmbient; li < e; li++) {          // light.go:110-120
+        const float4 q2 = L[4 * li + 2];
+        const float cb = L[4 * li + 3].x;
+        ar += q2.z; ag += q2.w; ab += cb; br += q2.z; bg += q2.w; bb += cb;
+    }
+    lightOut[D.base + ta] = make_float4(ar, ag, ab, 1.0f);
+    if (hasB) lightOut[D.base + tb] = make_float4(br, bg, bb, 1.0f);
+}
+
+// One-off timeline of k_vertex (build with -DT3D_VERTEX_TRACE; tools/vertex_trace.py prints it): %globaltimer stamps of the
+// first 1024 blocks -- [0] block start, [1] past the dependency wait, producer: [2] first entry + record read, [3] first tile's
+// copies issued, [4] last tile issued; consumer warp 0: [5] first tile arrived, [6] first tile shaded, [7] last tile shaded,
+// [8] tiles this block took.
+#ifdef T3D_VERTEX_TRACE
+__device__ unsigned long long g_vtrace[1024][16];
+__device__ __forceinline__ void vtrace(int i) { if (blockIdx.x < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_vtrace[blockIdx.x][i] = t; } }
+__device__ __forceinline__ void vtrace_set(int i, unsigned long long v) { if (blockIdx.x < 1024) g_vtrace[blockIdx.x][i] = v; }
+#else
+__device__ __forceinline__ void vtrace(int) {}
+__device__ __forceinline__ void vtrace_set(int, unsigned long long) {}
+#endif
+
 // k_vertex: persistent, warp-specialised, TMA-fed.  The host sorts the frame's vertex tiles (256 consecutive arena slots)
 // into three lists: tiles whose draws are all of one fast class (see shade_vertex) go to k_vertex<K1_STATIC> or
 // k_vertex<K1_SKINNED>, everything else to k_vertex<K1_GENERIC>.  A launch covers its list with ONE wave of blocks (at most
@@ -904,7 +1078,7 @@ template <> struct __align__(128) VStage<true> {
 // Tiles that straddle draws (small meshes packed back to back) are flagged unstaged: the consumers look their draw up per
 // vertex and load for themselves, as before.
 #ifndef T3D_K1_FAST_MINBLOCKS
-#define T3D_K1_FAST_MINBLOCKS 5
+#define T3D_K1_FAST_MINBLOCKS 7
 #endif
 #ifndef T3D_K1_SKINNED_MINBLOCKS
 #define T3D_K1_SKINNED_MINBLOCKS 4
@@ -914,44 +1088,51 @@ template <> struct __align__(128) VStage<true> {
 // first launch's blocks call pdl_launch() after their own pdl_wait()).  So a later launch starts shading at
 // once and waits for its predecessor at its END, which keeps "this kernel complete => every earlier kernel complete".
 template <int MODE, bool APPROX>
-__global__ void __launch_bounds__(VERTEX_THREADS, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
+__global__ void __launch_bounds__(VertexShape<MODE>::THREADS, MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS)
 k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
          const uint4* __restrict__ tileList, uint32_t nTiles, uint32_t* __restrict__ tileCtr, uint32_t totalV, uint32_t second, const __grid_constant__ FrameConst fc,
          const LightU* __restrict__ lightsU, const float* __restrict__ bones, const VolumeU* __restrict__ vols,
          float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
          float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     constexpr bool SKIN = MODE != K1_STATIC;
+    constexpr int VERTEX_STAGES = MODE == K1_STATIC ? T3D_VERTEX_STAGES_STATIC : T3D_VERTEX_STAGES;
+    constexpr uint32_t CONSUMERS = VertexShape<MODE>::CONSUMERS;
     __shared__ VStage<SKIN> stage[VERTEX_STAGES];
     __shared__ __align__(8) uint64_t full[VERTEX_STAGES], empty[VERTEX_STAGES];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        vtrace(0);
 #pragma unroll
-        for (int i = 0; i < VERTEX_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], VERTEX_BLOCK / 32); }
+        for (int i = 0; i < VERTEX_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (!second) pdl_wait();        // everything below reads what k_prep_draws wrote
     pdl_launch();
+    if (threadIdx.x == 0) vtrace(1);
 
-    if (warp == VERTEX_BLOCK / 32) {
+    if (warp == CONSUMERS / 32) {
         // ---- producer ----
         if (lane == 0) {
             // tiles are handed out by an atomic counter (zeroed by k_prep_draws): SMs that run ahead take more tiles.  The
-            // counter is bumped one tile ahead, so its round trip to L2 overlaps the previous tile's record reads.
-            uint32_t tNext = blockIdx.x;            // the first tile needs no round trip; the counter hands out tiles gridDim.x, ...
-            for (uint32_t k = 0;; k++) {
-                const uint32_t sidx = k % VERTEX_STAGES, ph = (k / VERTEX_STAGES) & 1u;
+            // producer claims a tile and fetches its list entry one iteration before it needs them, so neither the counter's
+            // round trip to L2 nor the entry's is on the path of a tile's bulk copies.
+            uint32_t t = blockIdx.x;                // the first tile needs no round trip; the counter hands out tiles gridDim.x, ...
+            uint4 entry = t < nTiles ? __ldg(&tileList[t]) : make_uint4(0u, 0u, 0u, 0u);
+            uint32_t tNext = gridDim.x + atomicAdd(tileCtr, 1u);
+            uint4 entryNext = entry; uint32_t tAfter = 0;
+            uint32_t sidx = 0, ph = 0;
+            for (;; t = tNext, entry = entryNext, tNext = tAfter, ph ^= (sidx + 1 == (uint32_t)VERTEX_STAGES) ? 1u : 0u, sidx = (sidx + 1 == (uint32_t)VERTEX_STAGES) ? 0u : sidx + 1) {
                 VStage<SKIN>& S = stage[sidx];
-                const uint32_t t = tNext;
                 if (t >= nTiles) {          // tell the consumers that the list is exhausted
                     mbar_wait(&empty[sidx], ph ^ 1u);
                     S.desc.base = NO_TILE;
                     mbar_arrive(&full[sidx]);
                     break;
                 }
-                // {tile, first draw, first draw of the next tile, end of the first draw's vertices}
-                const uint4 entry = __ldg(&tileList[t]);
-                tNext = gridDim.x + atomicAdd(tileCtr, 1u);
+                // {tile, first draw, first draw of the next tile, end of the first draw's vertices} of the tile after this one
+                entryNext = tNext < nTiles ? __ldg(&tileList[tNext]) : make_uint4(0u, 0u, 0u, 0u);
+                tAfter = gridDim.x + atomicAdd(tileCtr, 1u);
                 const uint32_t base = entry.x * (uint32_t)VERTEX_BLOCK;
                 const uint32_t end = min(base + (uint32_t)VERTEX_BLOCK, totalV);
                 const uint32_t dLo = entry.y, dHi = entry.z;
@@ -959,18 +1140,21 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
                 // tile is still uniform when the next draw starts at or after its end
                 bool staged = dLo == dHi || entry.w >= end;
                 const DrawRec& R = draws[dLo];
-                uint32_t flags = 0, nL = 0, mv0 = 0, lmode = T3D_LIGHTING_DEFAULT;
+                uint32_t flags = 0, nL = 0, mv0 = 0, lmode = T3D_LIGHTING_DEFAULT, groups = 0, groups2 = 0;
                 if (staged) {
                     flags = R.flags;
                     nL = (flags & T3D_DRAW_LIT) ? R.lightCount : 0;
+                    groups = (uint32_t)R.nPoint | ((uint32_t)R.nSun << 16); groups2 = (uint32_t)R.nAmbient | ((uint32_t)R.lightsSorted << 16);
                     lmode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
                     staged = nL <= (uint32_t)VERTEX_SMEM_LIGHTS;
                     if (SKIN && (flags & T3D_DRAW_SKINNED) && R.nBones > (uint32_t)VERTEX_SMEM_BONES) staged = false;
                     mv0 = R.a0 + (base - R.vbase);
                 }
+                if (t == blockIdx.x) { vtrace_set(15, flags); vtrace(2); }
                 mbar_wait(&empty[sidx], ph ^ 1u);       // the consumers are done with the tile that used this stage before
                 VStageDesc D;
                 D.base = base; D.end = end; D.dLo = dLo; D.dHi = dHi; D.staged = staged ? 1u : 0u; D.mv0 = mv0; D.flags = flags; D.nLmode = nL | (lmode << 16);
+                D.groups = groups; D.groups2 = groups2; D.pad[0] = D.pad[1] = 0;
                 S.desc = D;
                 if (!staged) { mbar_arrive(&full[sidx]); continue; }
                 const uint32_t cnt = end - base;            // a multiple of 4: every draw's vertex range is
@@ -999,30 +1183,49 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
                         bulk_load(S.bones, bones + 16 * (size_t)R.boneOffset, 64u * R.nBones, &full[sidx]);
                     }
                 }
+                if (t == blockIdx.x) vtrace(3);
+                vtrace(4);
             }
         }
         return;     // (the consumers keep the block alive; a `second` launch's wait at the end is theirs)
     }
 
     // ---- consumers ----
-    for (uint32_t k = 0;; k++) {
-        const uint32_t sidx = k % VERTEX_STAGES, ph = (k / VERTEX_STAGES) & 1u;
+    uint32_t sidx = 0, ph = 0;
+#ifdef T3D_VERTEX_TRACE
+    uint32_t nTaken = 0;
+#endif
+    for (;; ph ^= (sidx + 1 == (uint32_t)VERTEX_STAGES) ? 1u : 0u, sidx = (sidx + 1 == (uint32_t)VERTEX_STAGES) ? 0u : sidx + 1) {
         VStage<SKIN>& S = stage[sidx];
         mbar_wait(&full[sidx], ph);
-        const VStageDesc D = S.desc;
+        const VStageDesc& D = S.desc;       // (read from shared memory where needed: a register copy of all of it spills)
         if (D.base == NO_TILE) break;
-        const uint32_t slot = D.base + threadIdx.x;
-        if (slot < D.end) {
+#ifdef T3D_VERTEX_TRACE
+        if (threadIdx.x == 0 && nTaken == 0) vtrace(5);
+#endif
+        bool done = false;
+        if constexpr (MODE == K1_STATIC && APPROX && CONSUMERS * 2 == VERTEX_BLOCK) {
+            // the hot case, two vertices per thread: a staged tile, default lighting mode, light list grouped by type
+            if (D.staged && (D.nLmode >> 16) == T3D_LIGHTING_DEFAULT && ((D.groups2 >> 16) != 0 || !(D.flags & T3D_DRAW_LIT))) {
+                const uint32_t cnt = D.end - D.base;
+                const bool hasB = threadIdx.x + CONSUMERS < cnt;       // (a missing second vertex repeats the first: no stale shared memory is read)
+                if (threadIdx.x < cnt) shade2_static(S, D, threadIdx.x, hasB ? threadIdx.x + CONSUMERS : threadIdx.x, hasB, clipOut, clipXY, lightOut);
+                done = true;
+            }
+        }
+        for (uint32_t ti = threadIdx.x; !done && ti < D.end - D.base; ti += CONSUMERS) {
+            const uint32_t slot = D.base + ti;
             if (D.staged) {
                 const DrawRec& R = draws[D.dLo];
-                const uint32_t mv = D.mv0 + threadIdx.x;
-                const Vec3 P = v3(S.pos[0][threadIdx.x], S.pos[1][threadIdx.x], S.pos[2][threadIdx.x]);
+                const uint32_t mv = D.mv0 + ti;
+                const Vec3 P = v3(S.pos[0][ti], S.pos[1][ti], S.pos[2][ti]);
                 Vec3 N = v3(0, 0, 0);
-                if (D.flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) N = v3(S.nrm[0][threadIdx.x], S.nrm[1][threadIdx.x], S.nrm[2][threadIdx.x]);
-                UniformsShared U; U.s = S.U; U.ti = threadIdx.x;
+                if (D.flags & (T3D_DRAW_LIT | T3D_DRAW_SKINNED)) N = v3(S.nrm[0][ti], S.nrm[1][ti], S.nrm[2][ti]);
+                UniformsShared U; U.s = S.U; U.ti = ti;
                 if constexpr (SKIN) { U.sWgt = S.wgt; U.sJnt = S.jnt; U.sBones = S.bones; }
                 else { U.sWgt = nullptr; U.sJnt = nullptr; U.sBones = nullptr; }
-                shade_vertex<MODE, APPROX>(R, D.flags, D.nLmode & 0xFFFFu, (uint8_t)(D.nLmode >> 16), U, fc, slot, mv, P, N, lightsU, vols,
+                LightGroups G; G.nPoint = D.groups & 0xFFFFu; G.nSun = D.groups >> 16; G.nAmbient = D.groups2 & 0xFFFFu; G.sorted = (D.groups2 >> 16) != 0;
+                shade_vertex<MODE, APPROX>(R, D.flags, D.nLmode & 0xFFFFu, G, (uint8_t)(D.nLmode >> 16), U, fc, slot, mv, P, N, lightsU, vols,
                                            clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
             } else {
                 const uint32_t d = find_draw(vbase, D.dLo, D.dHi, slot);
@@ -1040,12 +1243,16 @@ k_vertex(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase,
                 U.mvpP = R.mvp; U.sunP = R.worldRot; U.lightP = reinterpret_cast<const float4*>(lightsU + R.lightU);
                 U.wgtP = R.wgt; U.jntP = R.jnt; U.bonesP = bones + 16 * (size_t)R.boneOffset; U.mv = mv;
                 const uint8_t lightingMode = (flags & T3D_DRAW_HAS_MATERIAL) ? R.lightingMode : (uint8_t)T3D_LIGHTING_DEFAULT;
-                shade_vertex<MODE, APPROX>(R, flags, R.lightCount, lightingMode, U, fc, slot, mv, P, N, lightsU, vols,
+                LightGroups G; G.nPoint = R.nPoint; G.nSun = R.nSun; G.nAmbient = R.nAmbient; G.sorted = R.lightsSorted != 0;
+                shade_vertex<MODE, APPROX>(R, flags, R.lightCount, G, lightingMode, U, fc, slot, mv, P, N, lightsU, vols,
                                            clipOut, clipXY, lightOut, wposOut, unbillOut, tnrmOut);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[sidx]);
+#ifdef T3D_VERTEX_TRACE
+        if (threadIdx.x == 0) { if (nTaken == 0) vtrace(6); vtrace(7); nTaken++; vtrace_set(8, nTaken); }
+#endif
     }
     if (second) pdl_wait();
 }
@@ -1724,13 +1931,21 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
+int debug_vertex_trace(unsigned long long* out, uint32_t nBlocks) {
+#ifdef T3D_VERTEX_TRACE
+    return cudaMemcpyFromSymbol(out, g_vtrace, sizeof(unsigned long long) * 16 * std::min<uint32_t>(nBlocks, 1024u)) == cudaSuccess ? 0 : -1;
+#else
+    (void)out; (void)nBlocks; return -1;
+#endif
+}
+
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const void* hostTmpl, const void* hostRot, const void* hostRest,
                        const t3d_light* hostLights, void* devDraws, void* devRest, uint32_t nDraws, size_t restBytes, uint32_t nLightsIn,
                        const FrameConst& fc, LightU* lightsU, DrawStat* stats, const uint32_t (*win)[4],
                        const void* hostBones, float* devBones, uint32_t nBones, bool bonesPacked, bool slimPacked,
-                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
+                       uint32_t* devVbase, uint32_t* devTbase, const void* hostRuns, uint32_t runPayload16, const uint32_t* hostBlockRun, uint32_t tmplSpanMax,
                        const PoseBatch* poses, uint32_t nPoseBatches, uint32_t blockBase, uint32_t nBlocksThis, bool firstChunk, uint32_t* tileCtr) {
     if (!nDraws) return;
     cudaFuncSetAttribute(k_prep_draws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM_MAX);     // per device; cheap
@@ -1749,6 +1964,7 @@ void launch_prep_draws(cudaStream_t s, bool pdl, const void* hostSlim, const voi
     pf.slim16 = slimPacked ? SLIM16 - 1 : SLIM16;
     pf.devVbase = devVbase; pf.devTbase = devTbase;
     pf.hostRuns = reinterpret_cast<const uint4*>(hostRuns); pf.hostBlockRun = hostBlockRun; pf.runMode = hostRuns ? 1u : 0u;
+    pf.pay16 = hostRuns ? runPayload16 : 0u;
     pf.tmplCap = std::min<uint32_t>(std::max(tmplSpanMax, 1u), PREP_TEMPLATES);
     pf.lightCap = nLightsIn <= PREP_SMEM_LIGHTS ? nLightsIn : 0u;
 #ifdef T3D_PREP_SMEM_STATIC
@@ -1791,7 +2007,7 @@ static void launch_vertex_class(cudaStream_t s, bool pdl, const DrawRec* draws, 
     if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
     constexpr uint32_t resident = MODE == K1_STATIC ? T3D_K1_FAST_MINBLOCKS : MODE == K1_SKINNED ? T3D_K1_SKINNED_MINBLOCKS : T3D_K1_MINBLOCKS;
     const uint32_t grid = std::min(nTiles, (uint32_t)g_smCount * resident);     // every block resident at once
-    launch_kernel(k_vertex<MODE, APPROX>, grid, VERTEX_THREADS, 0, s, pdl, draws, vbase, tileList, nTiles, tileCtr + MODE, totalV, second, fc,
+    launch_kernel(k_vertex<MODE, APPROX>, grid, VertexShape<MODE>::THREADS, 0, s, pdl, draws, vbase, tileList, nTiles, tileCtr + MODE, totalV, second, fc,
                   lightsU, bones, vols, clip, clipXY, light, wpos, unbill, tnrm);
 }
 

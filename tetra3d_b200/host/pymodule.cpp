@@ -302,6 +302,7 @@ PYBIND11_MODULE(_host, m) {
         .def(py::init<int>(), py::arg("device") = 0)
         .def_readonly("DeviceID", &GeometryDevice::deviceId)
         .def("Stream", [](GeometryDevice& d) { return (uintptr_t)t3d_debug_stream(d.ctx); })
+        .def("Handle", [](GeometryDevice& d) { return (uintptr_t)d.ctx; })      // the t3d_ctx*, for ctypes callers of the C ABI
         .def("SharedAlloc", [](GeometryDevice& d, uint64_t bytes) {
             void* p = nullptr; t3d_shared_handle h;
             const int rc = t3d_shared_alloc(d.ctx, bytes, &p, &h);
@@ -383,6 +384,7 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("DepthMargin", &Camera::DepthMargin)
         .def_readwrite("Device", &Camera::device)
         .def_readwrite("DownloadResults", &Camera::downloadResults)
+        .def_readwrite("UseInstancing", &Camera::UseInstancing)
         .def_readwrite("MaxLightCount", &Camera::MaxLightCount)
         .def_readwrite("MaxLightCountFocusPoint", &Camera::MaxLightCountFocusPoint)
         .def("SetFieldOfView", [](Camera& c, float f) { c.fieldOfView = f; })

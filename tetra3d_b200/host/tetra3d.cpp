@@ -839,6 +839,10 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
 
     renders.clear(); flushes.clear(); localFlushIds.clear();
     std::vector<t3d_draw> draws; draws.reserve(pending.size());
+    // per draw: may it travel as an instance (t3d_submit_instances)?  Its Node-local placement, the Material colour (the
+    // instance carries Model.Color), and what a run of instances has to share beyond the t3d_draw fields
+    struct InstInfo { bool eligible; Node* parent; const Matrix4* rotation; float matColor[4]; t3d_instance inst; };
+    std::vector<InstInfo> instInfo; instInfo.reserve(pending.size());
     std::vector<const PendingDraw*> submitted;
     submitted.reserve(pending.size()); renders.reserve(pending.size());
     const Mesh* lastEnsured = nullptr;
@@ -914,6 +918,17 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             submitted.push_back(nullptr);
             continue;
         }
+        {
+            InstInfo ii; std::memset(&ii, 0, sizeof ii);
+            ii.eligible = UseInstancing && !model->skinned;
+            ii.parent = model->parent; ii.rotation = &model->rotation;
+            ii.matColor[0] = mat ? mat->Color.R : 1.0f; ii.matColor[1] = mat ? mat->Color.G : 1.0f;
+            ii.matColor[2] = mat ? mat->Color.B : 1.0f; ii.matColor[3] = mat ? mat->Color.A : 1.0f;
+            ii.inst.position[0] = model->position.X; ii.inst.position[1] = model->position.Y; ii.inst.position[2] = model->position.Z;
+            ii.inst.scale[0] = model->scale.X; ii.inst.scale[1] = model->scale.Y; ii.inst.scale[2] = model->scale.Z;
+            ii.inst.color[0] = model->Color.R; ii.inst.color[1] = model->Color.G; ii.inst.color[2] = model->Color.B; ii.inst.color[3] = model->Color.A;
+            instInfo.push_back(ii);
+        }
         draws.push_back(d);
         submitted.push_back(&pd);
         renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)draws.size() - 1});
@@ -921,7 +936,42 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     lastBoneOffsets.clear();
     for (auto& kv : boneOffsets) lastBoneOffsets[kv.first->name] = kv.second;
     lap("build t3d_draw records");
-    if (!draws.empty()) check(ctx, t3d_submit_draws(ctx, draws.data(), (uint32_t)draws.size()), "t3d_submit_draws");
+    {
+        // Runs of Models that share everything but position, scale and colour (DynamicBatch children: particles; instanced
+        // scenery) go down as instances -- the device then evaluates their Node.Transform (node.go:577-583) -- everything else
+        // as draws, in render order.
+        auto sameRun = [&](size_t a, size_t b) {        // may draw b continue the instance run that draw a is in?
+            const t3d_draw& x = draws[a]; const t3d_draw& y = draws[b];
+            const InstInfo& p = instInfo[a]; const InstInfo& q = instInfo[b];
+            return q.eligible && (y.flags & T3D_DRAW_CONTINUE_FLUSH) && x.mesh_id == y.mesh_id && x.part == y.part &&
+                   (x.flags | T3D_DRAW_CONTINUE_FLUSH) == y.flags && std::memcmp(x.world_rotation, y.world_rotation, 64) == 0 &&
+                   x.src_w == y.src_w && x.src_h == y.src_h && x.sort_mode == y.sort_mode && x.lighting_mode == y.lighting_mode &&
+                   x.light_volume_mode == y.light_volume_mode && x.light_list == y.light_list && p.parent == q.parent &&
+                   std::memcmp(p.rotation, q.rotation, sizeof(Matrix4)) == 0 && std::memcmp(p.matColor, q.matColor, 16) == 0;
+        };
+        const size_t MIN_RUN = 8;
+        std::vector<t3d_instance> insts;
+        size_t plainFrom = 0;
+        for (size_t i = 0; i < draws.size();) {
+            size_t j = i + 1;
+            if (instInfo[i].eligible) while (j < draws.size() && sameRun(j - 1, j)) j++;
+            if (j - i >= MIN_RUN) {
+                if (i > plainFrom) check(ctx, t3d_submit_draws(ctx, draws.data() + plainFrom, (uint32_t)(i - plainFrom)), "t3d_submit_draws");
+                t3d_draw proto = draws[i];
+                std::memcpy(proto.color, instInfo[i].matColor, 16);
+                insts.resize(j - i);
+                for (size_t k = i; k < j; k++) insts[k - i] = instInfo[k].inst;
+                Matrix4 par = m4_identity();
+                if (instInfo[i].parent) par = instInfo[i].parent->Transform();
+                float rot16[16], par16[16];
+                m4_store(*instInfo[i].rotation, rot16); m4_store(par, par16);
+                check(ctx, t3d_submit_instances(ctx, &proto, rot16, instInfo[i].parent ? par16 : nullptr, insts.data(), (uint32_t)insts.size()), "t3d_submit_instances");
+                plainFrom = j;
+            }
+            i = j;
+        }
+        if (draws.size() > plainFrom) check(ctx, t3d_submit_draws(ctx, draws.data() + plainFrom, (uint32_t)(draws.size() - plainFrom)), "t3d_submit_draws");
+    }
     lap("t3d_submit_draws");
     check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
     lap("t3d_frame_execute");

@@ -356,6 +356,9 @@ struct Camera : Node {
     void Render(Scene& scene, const std::vector<ILight*>& lights, const std::vector<Model*>& models);   // camera.go:1269
     // when false the lists stay on the device (t3d_frame_results_device)
     bool downloadResults = true;
+    // runs of Models that differ only in position, scale and colour are submitted with t3d_submit_instances (the device
+    // evaluates their Node.Transform); false: every render(rp) is a t3d_draw carrying its matrix
+    bool UseInstancing = true;
 
     // results of the last Render (library-owned memory, valid until the next Render)
     t3d_frame_output output{};
