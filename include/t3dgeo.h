@@ -299,6 +299,19 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
  * library.go:206-209): n {DistanceSquared, MaximumTriangleSize} pairs, n <= 8.  Without it (or with n = 0) meshes uploaded
  * with subdivision data draw their base triangles only. */
 int t3d_frame_set_autosubdivision(t3d_ctx* ctx, const float* levels2, uint32_t n);
+/* Replaces: Model.BakeLighting (model.go:1203-1268).  A frame marked this way runs ProcessVertices' transform and the light
+ * loop for every submitted draw and stops there (no cull, no lists): submit the model's MeshParts as T3D_DRAW_LIT draws with
+ * the light list {lights..., World.AmbientLight} (light.go beginRender / beginModel are derived on the device as always) and
+ * read the sums back with t3d_frame_read_vertex_lights.  What differs from a rendered frame, as in the reference: the
+ * arithmetic is always the reference's (t3d_set_exact_lighting is implied); point lights are not skipped by the per-model
+ * range test (camera.go:1625-1629 is not on this path); and a light's contribution is added once per triangle corner that
+ * refers to the vertex (model.go:1254-1258 walks triangles, not vertices), i.e. valence times, light by light.  The caller
+ * writes RGB into VertexColors[targetChannel] (1, 1, 1 for Shadeless parts, model.go:1236-1243).  Meshes with auto-subdivision
+ * data are refused (T3D_E_UNSUPPORTED). */
+int t3d_frame_set_bake_lighting(t3d_ctx* ctx, int enabled);
+/* The per-vertex light sums of draw `draw` of the executed frame (mesh.vertexLights; after a bake frame: the baked colours) for
+ * mesh vertices [vtx_start, vtx_end) of its part: 4 floats per vertex, R G B 1.  Zeros for an unlit draw. */
+int t3d_frame_read_vertex_lights(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end, float* light4);
 /* Replaces: building sceneLights / LightGroup.Lights (camera.go:1275-1303, 1576-1581).  Returns a
  * light-list handle in *list_id; list 0 is always the empty list. */
 int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id);

@@ -1587,6 +1587,96 @@ int orc_render_scene(const orc_scene* sc, int capture, orc_result** out) {
     return ORC_OK;
 }
 
+/* ================================================================================================
+ * Model.BakeLighting (model.go:1203-1268)
+ * ================================================================================================ */
+/* rgb: [n_verts][3] of the model's mesh, in: VertexColors[targetChannel] before the call, out: after it (alpha is untouched by
+ * the reference).  light_ids: the `lights` argument, in order; the scene's World.AmbientLight is appended (model.go:1216-1218). */
+int orc_bake_lighting(const orc_scene* sc, int32_t mi, const int32_t* light_ids, int32_t n_ids, float* rgb) {
+    g_err[0] = 0;
+    if (mi < 0 || mi >= sc->n_models || sc->models[mi].mesh < 0) { snprintf(g_err, sizeof g_err, "orc_bake_lighting: bad model"); return ORC_E_INVALID; }
+    rstate S; memset(&S, 0, sizeof S);
+    S.nodeT = calloc((size_t)(sc->n_nodes > 0 ? sc->n_nodes : 1), sizeof(mat4));
+    S.nodeTValid = calloc((size_t)(sc->n_nodes > 0 ? sc->n_nodes : 1), 1);
+    int maxVerts = 1, maxTris = 1;
+    S.centers = calloc((size_t)sc->n_meshes, sizeof(float*));
+    S.dims = calloc((size_t)sc->n_meshes, sizeof(dims_t));
+    for (int i = 0; i < sc->n_meshes; i++) {
+        const orc_mesh* m = &sc->meshes[i];
+        if (m->n_verts > maxVerts) maxVerts = m->n_verts;
+        if (m->n_tris > maxTris) maxTris = m->n_tris;
+        S.centers[i] = malloc((size_t)(m->n_tris > 0 ? m->n_tris : 1) * 12);
+        if (m->auto_subdivide && m->tri_centers) memcpy(S.centers[i], m->tri_centers, (size_t)m->n_tris * 12);
+        else orc_triangle_centers(m->positions, m->indices, m->n_tris, S.centers[i]);
+        S.dims[i] = mesh_dimensions(m);
+    }
+    S.vertexTransforms = calloc((size_t)maxVerts, sizeof(vec4));
+    S.transformedNormals = calloc((size_t)maxVerts, sizeof(vec3));
+    S.depthUnbillboarded = calloc((size_t)maxVerts, sizeof(float));
+    S.alteredPositions = calloc((size_t)maxVerts, sizeof(vec3));
+    S.alteredNormals = calloc((size_t)maxVerts, sizeof(vec3));
+    S.vertexLights = calloc((size_t)maxVerts, sizeof(vec4));        /* stands in for VertexColors[targetChannel] */
+    S.unsetTris = calloc((size_t)maxTris, sizeof(sorting_tri));
+    S.sortedTris = calloc((size_t)maxTris, sizeof(int));
+    S.binOf = calloc((size_t)maxTris, sizeof(uint16_t));
+    S.binCount = calloc(ORC_BINS, sizeof(int));
+    /* the world's ambient light as one more light slot, as in orc_render_scene */
+    orc_light* lights_copy = malloc((size_t)(sc->n_lights + 1) * sizeof(orc_light));
+    if (sc->n_lights) memcpy(lights_copy, sc->lights, (size_t)sc->n_lights * sizeof(orc_light));
+    const int worldAmbient = sc->n_lights;
+    memset(&lights_copy[worldAmbient], 0, sizeof(orc_light));
+    lights_copy[worldAmbient].type = ORC_LIGHT_AMBIENT; lights_copy[worldAmbient].node = -1;
+    memcpy(lights_copy[worldAmbient].color, sc->world.ambient_color, 12);
+    lights_copy[worldAmbient].energy = sc->world.ambient_energy; lights_copy[worldAmbient].visible = sc->world.ambient_visible;
+    orc_scene sc2 = *sc; sc2.lights = lights_copy; sc2.n_lights = sc->n_lights + 1;
+    S.sc = &sc2; sc = &sc2;
+    S.ambResult = calloc((size_t)sc->n_lights, sizeof(float[3]));
+    S.workingPosition = calloc((size_t)sc->n_lights, sizeof(vec3));
+    S.workingForward = calloc((size_t)sc->n_lights, sizeof(vec3));
+    S.workingModelRotation = calloc((size_t)sc->n_lights, sizeof(mat4));
+    S.res = calloc(1, sizeof(orc_result));
+    camera_setup(&S);
+
+    int* lightsInput = malloc((size_t)(n_ids + 1) * sizeof(int));   /* model.go:1212-1218 */
+    int nIn = 0;
+    for (int i = 0; i < n_ids; i++) lightsInput[nIn++] = light_ids[i];
+    if (sc->world.present) lightsInput[nIn++] = worldAmbient;
+    for (int i = 0; i < nIn; i++)                                   /* model.go:1220-1235 */
+        if (sc->lights[lightsInput[i]].visible) { light_begin_render(&S, lightsInput[i]); light_begin_model(&S, lightsInput[i], mi); }
+
+    const orc_model* model = &sc->models[mi];
+    const orc_mesh* mesh = &sc->meshes[model->mesh];
+    for (int v = 0; v < mesh->n_verts; v++) { S.vertexLights[v].X = rgb[3 * v]; S.vertexLights[v].Y = rgb[3 * v + 1]; S.vertexLights[v].Z = rgb[3 * v + 2]; }
+    for (int pi = 0; pi < mesh->n_parts; pi++) {                    /* model.go:1237-1266 */
+        const orc_part* part = &mesh->parts[pi];
+        const orc_material* mat = &part->material;
+        float mn, mx;
+        process_vertices(&S, mi, pi, &mn, &mx);                     /* ProcessVertices(vp, camera, mp, false, nil) */
+        if (mat->present && mat->shadeless) {
+            for (int v = part->vertex_index_start; v < part->vertex_index_end; v++) { S.vertexLights[v].X = 1; S.vertexLights[v].Y = 1; S.vertexLights[v].Z = 1; }
+            continue;
+        }
+        for (int v = part->vertex_index_start; v < part->vertex_index_end; v++) { S.vertexLights[v].X = 0; S.vertexLights[v].Y = 0; S.vertexLights[v].Z = 0; }
+        for (int i = 0; i < nIn; i++) {
+            if (!sc->lights[lightsInput[i]].visible) continue;
+            for (int ti = part->triangle_start; ti <= part->triangle_end; ti++) {     /* forEachTri(true, ...): light.Light(tri, ...) */
+                const uint32_t* tri = mesh->indices + 3 * (size_t)ti;
+                for (int vi = 0; vi < 3; vi++) vertex_light(&S, lightsInput[i], (int)tri[vi], mi, mat);   /* light.go:260-269 */
+            }
+        }
+    }
+    for (int v = 0; v < mesh->n_verts; v++) { rgb[3 * v] = S.vertexLights[v].X; rgb[3 * v + 1] = S.vertexLights[v].Y; rgb[3 * v + 2] = S.vertexLights[v].Z; }
+
+    free(lightsInput); free(lights_copy); free(S.res);
+    for (int i = 0; i < sc->n_meshes; i++) free(S.centers[i]);
+    free(S.centers); free(S.dims); free(S.nodeT); free(S.nodeTValid);
+    free(S.vertexTransforms); free(S.transformedNormals); free(S.depthUnbillboarded);
+    free(S.alteredPositions); free(S.alteredNormals); free(S.vertexLights);
+    free(S.unsetTris); free(S.sortedTris); free(S.binOf); free(S.binCount);
+    free(S.ambResult); free(S.workingPosition); free(S.workingForward); free(S.workingModelRotation);
+    return ORC_OK;
+}
+
 void orc_free_result(orc_result* r) {
     if (!r) return;
     free(r->renders); free(r->flushes); free(r->color_list); free(r->depth_list); free(r->normal_list);

@@ -247,6 +247,9 @@ enum { ORC_OK = 0, ORC_E_UNSUPPORTED = -3, ORC_E_INVALID = -1 };
 /* Runs Camera.RenderScene on the scene.  capture != 0 fills cap_clip/cap_light. */
 int  orc_render_scene(const orc_scene* scene, int capture, orc_result** out);
 void orc_free_result(orc_result* r);
+/* Model.BakeLighting (model.go:1203-1268) of model `model` with the lights light_ids[0..n) plus the world's ambient light:
+ * rgb = VertexColors[targetChannel] of its mesh, [n_verts][3], in / out. */
+int  orc_bake_lighting(const orc_scene* scene, int32_t model, const int32_t* light_ids, int32_t n, float* rgb);
 const char* orc_last_error(void);
 
 /* ---- math exposed for known-answer tests (matrix.go) ------------------------- */

@@ -337,3 +337,28 @@ def test_instances_reject_what_they_cannot_express(abi):
     proto.flags = 1 << 3     # T3D_DRAW_SKINNED
     assert lib.t3d_submit_instances(ctx, C.byref(proto), None, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED
     assert lib.t3d_frame_execute(ctx) == T3D_OK
+
+
+def test_draws_submitted_one_call_each_equal_one_call(abi):
+    """A shim may call t3d_submit_draws once per render(rp): the frame must not depend on how the calls are cut."""
+    lib, ctx = abi
+    md, keep = _triangle_mesh()
+    assert lib.t3d_mesh_upload(ctx, C.c_uint64(7), C.c_uint32(1), C.byref(md)) == T3D_OK, lib.t3d_last_error(ctx)
+    n = 2200
+    rng = np.random.default_rng(5)
+    arr = (Draw * n)()
+    for i in range(n):
+        d = _draw()
+        d.transform[12], d.transform[13], d.transform[14] = [float(x) for x in rng.uniform((-5, -3, -15), (5, 3, 1))]
+        arr[i] = d
+
+    def one_call():
+        assert lib.t3d_submit_draws(ctx, arr, C.c_uint32(n)) == T3D_OK, lib.t3d_last_error(ctx)
+
+    def many_calls():
+        for i in range(n):
+            assert lib.t3d_submit_draws(ctx, C.byref(arr[i]), C.c_uint32(1)) == T3D_OK, lib.t3d_last_error(ctx)
+
+    c1, d1, r1 = _frame(lib, ctx, one_call)
+    c2, d2, r2 = _frame(lib, ctx, many_calls)
+    assert len(c1) > 0 and np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and r1 == r2

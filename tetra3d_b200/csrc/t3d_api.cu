@@ -119,6 +119,8 @@ struct t3d_ctx {
     // frame staging (pinned)
     bool inFrame = false, executed = false, haveResults = false;
     bool stageTimings = false, stagesTimed = false;
+    bool bakeFrame = false;             // t3d_frame_set_bake_lighting: this frame stops behind k_vertex and lights like Model.BakeLighting
+    DevBuf dValence;
     bool exactLighting = false;         // t3d_set_exact_lighting: the reference's lighting arithmetic operation by operation (bit-exact colours)
     bool forceFullUpload = false;       // t3d_debug_force_full_upload: never pack affine matrices (exercises the 16-float paths)
     FrameConst fc;
@@ -546,6 +548,14 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     for (auto& u : ctx->volumeUse) u.clear();
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
+    ctx->bakeFrame = false;
+    return T3D_OK;
+}
+
+int t3d_frame_set_bake_lighting(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_set_bake_lighting: not between frame_begin and frame_execute");
+    ctx->bakeFrame = enabled != 0;
     return T3D_OK;
 }
 
@@ -851,6 +861,7 @@ static int submit_range(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n, const t
         if (m.subdiv) ctx->anySubdiv = true;
         ctx->hVbase.p[ctx->hDraws.size()] = ctx->vAcc;
         ctx->hTbase.p[ctx->hDraws.size()] = ctx->tAcc;
+        ctx->hVbase.n = ctx->hTbase.n = ctx->hDraws.size() + 1;        // (a later call's reserve keeps the first n entries when it has to move the array)
         ctx->vAcc += pi.nv; ctx->tAcc += R.nt;
         {   // what goes over PCIe: a 112-byte placement record, plus a template whenever anything else changes
             // reuse one of the most recent templates when everything but the placement matches (instances of one
@@ -1012,7 +1023,12 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     ctx->launches = 0;
     ctx->executed = true;
     ctx->stagesTimed = ctx->stageTimings;
-    ctx->fc.approxLighting = ctx->exactLighting ? 0u : 1u;
+    ctx->fc.approxLighting = (ctx->exactLighting || ctx->bakeFrame) ? 0u : 1u;
+    ctx->fc.bakeValence = nullptr;
+    if (ctx->bakeFrame) {
+        if (ctx->anySubdiv) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_execute: BakeLighting of an auto-subdivided mesh (its sub-triangles are lit from stale positions in the reference, model.go:751-755)");
+        if (ctx->gather.active) return fail(ctx, T3D_E_STATE, "t3d_frame_execute: a bake frame cannot be delivered (t3d_gather_detach first)");
+    }
     if (ctx->gather.active) {
         t3d_ctx::Gather& G = ctx->gather;
         G.serial++;
@@ -1033,7 +1049,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->hTileV.resize(nTilesV + 1));
     build_tiles(ctx->hVbase.p, nDraws, nTilesV, VERTEX_TILE, ctx->hTileV.p);
     {   // vertex tiles whose draws all belong to one fast class -> that k_vertex instantiation, the rest -> the generic one
-        const bool frameFast = !(ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS) && !(ctx->fc.snapping > 0);
+        const bool frameFast = !(ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS) && !(ctx->fc.snapping > 0) && !ctx->bakeFrame;
         for (auto& v : ctx->hVClass) { v.clear(); CU(v.reserve(nTilesV)); }
         for (uint32_t b = 0; b < nTilesV; b++) {
             const uint64_t end = std::min<uint64_t>((uint64_t)(b + 1) * VERTEX_TILE, totalV);
@@ -1058,6 +1074,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     CU(ctx->dLightsU.ensure(sizeof(LightU) * std::max<size_t>(ctx->luAcc, 1)));
     CU(ctx->dStats.ensure(sizeof(DrawStat) * nDraws));
     CU(ctx->dTileCtr.ensure(64));
+    if (ctx->bakeFrame) { CU(ctx->dValence.ensure(4ull * std::max(totalV, 4u))); ctx->fc.bakeValence = ctx->dValence.as<uint32_t>(); }
     CU(ctx->dClip.ensure(16ull * std::max(totalV, 4u)));
     CU(ctx->dClipXY.ensure(8ull * std::max(totalV, 4u)));
     CU(ctx->dLight.ensure(16ull * std::max(ctx->anyLit ? totalV : 4u, 4u)));
@@ -1329,11 +1346,23 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     CU(mark(2));
     const uint32_t nVClass[3] = {(uint32_t)ctx->hVClass[0].n, (uint32_t)ctx->hVClass[1].n, (uint32_t)ctx->hVClass[2].n};
-    launch_vertex(s, pdl, ctx->exactLighting, ctx->pDraws, ctx->pVbase, ctx->pVClass, nVClass, ctx->dTileCtr.as<uint32_t>(), totalV, ctx->fc,
+    if (ctx->bakeFrame) {       // corners per vertex, from the records k_prep_draws just wrote
+        CU(cudaMemsetAsync(ctx->dValence.p, 0, 4ull * totalV, s));
+        launch_bake_valence(s, ctx->pDraws, ctx->pTbase, nDraws, totalT, ctx->dValence.as<uint32_t>());
+        ctx->launches += 1;
+    }
+    launch_vertex(s, pdl && !ctx->bakeFrame, ctx->exactLighting || ctx->bakeFrame, ctx->pDraws, ctx->pVbase, ctx->pVClass, nVClass, ctx->dTileCtr.as<uint32_t>(), totalV, ctx->fc,
                   ctx->dLightsU.as<LightU>(), ctx->pBones, ctx->dVolumes.as<VolumeU>(), ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                   ctx->dLight.as<float4>(), ctx->dWpos.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>());
     ctx->launches += 1 + (nVClass[0] ? 1 : 0) + (nVClass[1] ? 1 : 0) + (nVClass[2] ? 1 : 0);
     CU(mark(3));
+    if (ctx->bakeFrame) {       // a bake frame ends here: its product is the per-vertex light sums (t3d_frame_read_vertex_lights)
+        for (int i = 4; i <= 5; i++) CU(mark(i));
+        CU(cudaEventRecord(ctx->ev[9], s)); CU(cudaEventRecord(ctx->ev[6], s));
+        CU(cudaGetLastError());
+        ctx->vertexKernelBytes = 0;
+        return T3D_OK;
+    }
     // K2: cull (small draws are also sorted here)
     launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
                       ctx->dTdepth.as<uint32_t>(), stats, ctx->anySubdiv);
@@ -1405,6 +1434,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
 static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_timings* tm) {
     if (!ctx || !out) return fail(ctx, T3D_E_INVALID, "t3d_frame_results: NULL argument");
     if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_results: frame not executed");
+    if (ctx->bakeFrame) return fail(ctx, T3D_E_STATE, "t3d_frame_results: a bake frame (t3d_frame_set_bake_lighting) emits no lists: read its vertex lights with t3d_frame_read_vertex_lights");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint32_t nDraws = (uint32_t)ctx->hDraws.size();
@@ -1538,6 +1568,18 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
         else memset(light4, 0, n * 16);
     }
     return T3D_OK;
+}
+
+int t3d_frame_read_vertex_lights(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end, float* light4) {
+    if (!ctx || !light4) return fail(ctx, T3D_E_INVALID, "t3d_frame_read_vertex_lights: NULL argument");
+    if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_read_vertex_lights: frame not executed");
+    if (draw >= ctx->hDraws.size() || vtx_start > vtx_end) return fail(ctx, T3D_E_INVALID, "t3d_frame_read_vertex_lights: draw or range out of bounds");
+    const t3d_ctx::HostDraw& R = ctx->hDraws[draw];
+    // vertices of the range that no triangle of the part refers to were never lit: zero
+    for (size_t i = 0; i < (size_t)(vtx_end - vtx_start); i++) { light4[4 * i] = light4[4 * i + 1] = light4[4 * i + 2] = 0.0f; light4[4 * i + 3] = 1.0f; }
+    const uint32_t lo = std::max(vtx_start, R.a0), hi = std::min(vtx_end, R.a0 + R.nv);
+    if (lo >= hi || !(R.flags & T3D_DRAW_LIT)) return T3D_OK;
+    return t3d_debug_read_draw_vertices(ctx, draw, lo, hi, nullptr, light4 + 4 * (size_t)(lo - vtx_start));
 }
 
 int t3d_set_output_target(t3d_ctx* ctx, t3d_vertex* color, t3d_vertex* depth, t3d_vertex* normal, uint64_t vertex_capacity) {

@@ -36,6 +36,9 @@ struct FrameConst {
     // 1: default lighting (approximate reciprocals, colours within 1/255): k_prep_draws folds the per-light constants the fast
     // light loops read and groups every draw's list by light type; 0: t3d_set_exact_lighting (lists stay in submit order)
     uint32_t approxLighting;
+    // Model.BakeLighting frames (t3d_frame_set_bake_lighting): for every arena vertex, how many triangle corners of its draw
+    // refer to it -- the reference's bake adds a light's contribution once per corner (model.go:1246-1262) -- else nullptr
+    const uint32_t* bakeValence;
 };
 
 // Resolved light as seen by one draw: light.beginRender/beginModel products (light.go:110-112,

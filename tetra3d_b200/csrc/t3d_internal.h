@@ -37,6 +37,7 @@ void launch_vertex(cudaStream_t s, bool pdl, bool exactLighting, const DrawRec* 
                    const uint4* const tileLists[3], const uint32_t nTilesOf[3], uint32_t* tileCtr /* [4] zeroed by k_prep_draws */,
                    uint32_t totalV, const FrameConst& fc, const LightU* lightsU, const float* bones,
                    const VolumeU* vols, float4* clip, float2* clipXY, float4* light, float4* wpos, float* unbill, float4* tnrm);
+void launch_bake_valence(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, uint32_t nDraws, uint32_t totalT, uint32_t* valence);
 int debug_vertex_trace(unsigned long long* out, uint32_t nBlocks);      // -DT3D_VERTEX_TRACE builds only (else -1)
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,

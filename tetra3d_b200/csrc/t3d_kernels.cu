@@ -418,7 +418,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const Vec3 modelPos = v3(R.transform[12], R.transform[13], R.transform[14]);
         const float maxSpan = R.maxSpan;
         auto skipped = [&](const t3d_light& L, uint32_t i) -> bool {        // camera.go:1625-1629: only for the list's own lights
-            if (!(L.type == T3D_LIGHT_POINT && L.range > 0 && i < nOwn)) return false;
+            if (!(L.type == T3D_LIGHT_POINT && L.range > 0 && i < nOwn) || fc.bakeValence) return false;     // (BakeLighting lights every vertex with every light)
             const float dist = maxSpan + L.range;
             return v3_dist2(modelPos, v3(L.position[0], L.position[1], L.position[2])) > dist * dist;
         };
@@ -876,6 +876,10 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
         lightOut[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f);
         return;
     }
+    // Model.BakeLighting (model.go:1246-1262) walks light by light over the part's triangles and adds the light's contribution
+    // to a vertex once per corner that refers to it: `rep` additions of the same value, in sequence, per light
+    uint32_t rep = 1;
+    if constexpr (!FAST) { if (fc.bakeValence) rep = fc.bakeValence[slot]; }
     for (uint32_t li = 0; li < nL; li++) {
         const float4 q0 = U.light(4 * li), q1 = U.light(4 * li + 1), q2 = U.light(4 * li + 2);
         const uint32_t type = __float_as_uint(q0.x);
@@ -898,9 +902,8 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
             if (diffuse > 0) {
                 float diffuseFactor = diffuse * (1.0f / (1.0f + (0.1f * distance))) * 2.0f;
                 if (range2 > 0) diffuseFactor *= clampf((range2 - distance) / distance, 0.0f, 1.0f);
-                lr += cR * diffuseFactor * energy;
-                lg += cG * diffuseFactor * energy;
-                lb += cB * diffuseFactor * energy;
+                const float ar = cR * diffuseFactor * energy, ag = cG * diffuseFactor * energy, ab = cB * diffuseFactor * energy;
+                for (uint32_t r = 0; r < rep; r++) { lr += ar; lg += ag; lb += ab; }
             }
         } else if (type == T3D_LIGHT_DIRECTIONAL) {                     // light.go:332-360
             const float4 q3 = U.light(4 * li + 3);
@@ -930,14 +933,16 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
             float diffuseFactor = v3_dot(normal, fwd);
             if (lightingMode == T3D_LIGHTING_DOUBLE_SIDED) diffuseFactor = fabsf(diffuseFactor);
             if (diffuseFactor <= 0) continue;
-            lr += cR * diffuseFactor * energy;
-            lg += cG * diffuseFactor * energy;
-            lb += cB * diffuseFactor * energy;
+            const float ar = cR * diffuseFactor * energy, ag = cG * diffuseFactor * energy, ab = cB * diffuseFactor * energy;
+            for (uint32_t r = 0; r < rep; r++) { lr += ar; lg += ag; lb += ab; }
         } else if (type == T3D_LIGHT_AMBIENT) {                         // light.go:110-120
-            lr += cR * energy; lg += cG * energy; lb += cB * energy;
+            const float ar = cR * energy, ag = cG * energy, ab = cB * energy;
+            for (uint32_t r = 0; r < rep; r++) { lr += ar; lg += ag; lb += ab; }
         } else if (!FAST && type == T3D_LIGHT_VOLUME) {
-            const float3 acc = light_volume(&R, lightsU + R.lightU + li, lightsU + R.lightU, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned, make_float3(lr, lg, lb));
-            lr = acc.x; lg = acc.y; lb = acc.z;
+            for (uint32_t r = 0; r < rep; r++) {
+                const float3 acc = light_volume(&R, lightsU + R.lightU + li, lightsU + R.lightU, vols, P.X, P.Y, P.Z, N.X, N.Y, N.Z, skinned, make_float3(lr, lg, lb));
+                lr = acc.x; lg = acc.y; lb = acc.z;
+            }
         }
     }
     lightOut[slot] = make_float4(lr, lg, lb, 1.0f);
@@ -1926,6 +1931,23 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
         }
     }
     if (threadIdx.x == 0) bulk_wait_read();                             // shared memory must outlive the TMA reads
+}
+
+// Model.BakeLighting frames: corners per arena vertex (see FrameConst.bakeValence).  One thread per arena triangle.
+__global__ void __launch_bounds__(256)
+k_bake_valence(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tbase, uint32_t nDraws, uint32_t totalT, uint32_t* __restrict__ valence) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= totalT) return;
+    const DrawRec& R = draws[find_draw(tbase, 0, nDraws - 1, t)];
+    const uint32_t mt = R.t0 + (t - R.tbase), ts = R.tstride;
+    const uint32_t a = R.idx[mt], b = R.idx[ts + mt], c = R.idx[2 * (size_t)ts + mt];
+    atomicAdd(&valence[R.vbase + (a - R.a0)], 1u);
+    atomicAdd(&valence[R.vbase + (b - R.a0)], 1u);
+    atomicAdd(&valence[R.vbase + (c - R.a0)], 1u);
+}
+void launch_bake_valence(cudaStream_t s, const DrawRec* draws, const uint32_t* tbase, uint32_t nDraws, uint32_t totalT, uint32_t* valence) {
+    if (!totalT) return;
+    launch_kernel(k_bake_valence, (totalT + 255) / 256, 256, 0, s, false, draws, tbase, nDraws, totalT, valence);
 }
 
 // ------------------------------------------------------------------------------------------------

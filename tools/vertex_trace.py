@@ -23,7 +23,7 @@ for _ in range(4):
     flush.add_(1); torch.cuda.synchronize()
     cam.Clear(); cam.RenderScene(scene)
 tm = cam.Timings()
-lib = C.CDLL(t3d.LIB_PATH)
+lib = C.CDLL("libt3dgeo.so")       # the copy the extension module already loaded (LD_LIBRARY_PATH decides which build)
 n = 1024
 buf = (C.c_ulonglong * (16 * n))()
 lib.t3d_debug_vertex_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
