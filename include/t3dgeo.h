@@ -295,6 +295,10 @@ int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id);
 /* ---- per frame ---------------------------------------------------------------------------------- */
 /* Replaces: the prologue of Camera.Render that fixes vpMatrix / camera constants (camera.go:1329-1341). */
 int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world);
+/* Drops a frame that was begun but will not be executed (the caller hit an error while submitting: a draw that needs a host
+ * callback, a missing mesh): nothing runs, the previous frame's results stay valid until the next t3d_frame_begin.  A no-op
+ * when no frame is open.  Replaces: nothing in the reference (its render loop cannot fail half way). */
+int t3d_frame_abort(t3d_ctx* ctx);
 /* Replaces: the autosubdivisionLevels argument of ProcessVertices (camera.go:1547-1553; scene.library.autosubdivisionLevels,
  * library.go:206-209): n {DistanceSquared, MaximumTriangleSize} pairs, n <= 8.  Without it (or with n = 0) meshes uploaded
  * with subdivision data draw their base triangles only. */
@@ -312,6 +316,16 @@ int t3d_frame_set_bake_lighting(t3d_ctx* ctx, int enabled);
 /* The per-vertex light sums of draw `draw` of the executed frame (mesh.vertexLights; after a bake frame: the baked colours) for
  * mesh vertices [vtx_start, vtx_end) of its part: 4 floats per vertex, R G B 1.  Zeros for an unlit draw. */
 int t3d_frame_read_vertex_lights(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start, uint32_t vtx_end, float* light4);
+/* Replaces: Model.BakeAO, its pass over the model's own triangles (model.go:1040-1124).  The mesh must be resident
+ * (t3d_mesh_upload).  tri_normals / tri_max_span: Triangle.Normal and Triangle.MaxSpan (mesh.go:2018-2037) of every triangle;
+ * target_parts: one byte per MeshPart, non-zero = in AOBakeOptions.TargetMeshParts (NULL: every part, as with an empty list);
+ * target_vertices: one byte per vertex for AOBakeOptions.TargetVertices (NULL: every vertex).  colors4: the n_verts x RGBA of
+ * VertexColors[TargetChannel], updated in place exactly as the reference updates it (a corner that shares its position with a
+ * close, sufficiently bent neighbour is pulled to occlusion_color; a vertex is pulled once per corner that refers to it, in
+ * triangle order).  Synchronous.  The inter-model pass (AOBakeOptions.OtherModels, model.go:1128-1196) is not offered: it
+ * indexes VertexColors by vertex where every other line indexes it by channel, so it cannot run in the reference either. */
+int t3d_bake_ao(t3d_ctx* ctx, uint64_t mesh_id, const float* tri_normals3, const float* tri_max_span, const uint8_t* target_parts,
+                const uint8_t* target_vertices, float occlusion_angle, const float occlusion_color[4], float* colors4);
 /* Replaces: building sceneLights / LightGroup.Lights (camera.go:1275-1303, 1576-1581).  Returns a
  * light-list handle in *list_id; list 0 is always the empty list. */
 int t3d_submit_lights(t3d_ctx* ctx, const t3d_light* lights, uint32_t n, uint32_t* list_id);
@@ -432,6 +446,10 @@ int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matri
 int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled);
 /* Number of kernels launched by the last t3d_frame_execute. */
 int t3d_debug_last_launch_count(t3d_ctx* ctx);
+/* Which large draws (9 .. 64 tiles of 1024 triangles) are culled and sorted by the single persistent kernel instead of the
+ * three-kernel segmented sort: 0 none, 1 (default) when all their tiles are resident at once, 2 always.  Both paths produce the
+ * same lists bit for bit; this is a performance heuristic made switchable for tests and measurements. */
+int t3d_debug_set_fused_sort(t3d_ctx* ctx, int mode);
 /* Profiling builds (-DT3D_VERTEX_TRACE) only, T3D_E_UNSUPPORTED otherwise: 16 nanosecond time stamps per block of the last
  * k_vertex launch (t3d_kernels.cu lists them), for the first n_blocks <= 1024 blocks. */
 int t3d_debug_vertex_trace(t3d_ctx* ctx, unsigned long long* out, uint32_t n_blocks);

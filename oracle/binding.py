@@ -149,6 +149,11 @@ def lib():
         L.orc_render_scene.argtypes = [C.POINTER(orc_scene), C.c_int, C.POINTER(C.POINTER(orc_result))]
         L.orc_render_scene.restype = C.c_int
         L.orc_free_result.argtypes = [C.POINTER(orc_result)]
+        L.orc_bake_ao.argtypes = [C.POINTER(orc_mesh), f32p, f32p, u8p, u8p, C.c_float, f32p, f32p]
+        L.orc_bake_ao.restype = C.c_int
+        L.orc_go_acos.argtypes = [C.c_double]; L.orc_go_acos.restype = C.c_double
+        L.orc_bake_lighting.argtypes = [C.POINTER(orc_scene), C.c_int32, i32p, C.c_int32, f32p]
+        L.orc_bake_lighting.restype = C.c_int
         L.orc_last_error.restype = C.c_char_p
         for name in ("orc_mat4_mult",):
             getattr(L, name).argtypes = [f32p, f32p, f32p]
@@ -534,10 +539,54 @@ class _Marshalled:
         sc.world.ambient_energy = float(w.ambient_energy); sc.world.ambient_visible = int(w.ambient_visible)
         self.scene = sc
         self.desc = desc
+        self.light_index = light_index
+        self.model_index = model_index
 
 
 def marshal(desc: SceneDesc) -> _Marshalled:
     return _Marshalled(desc)
+
+
+def bake_ao(desc_or_marshalled, model, tri_normals, tri_max_span, occlusion_angle, occlusion_color, colors4: Optional[np.ndarray] = None,
+            target_parts=None, target_vertices=None) -> np.ndarray:
+    """Model.BakeAO's same-model pass (model.go:1040-1124) on `model`'s mesh: VertexColors[TargetChannel] after the bake,
+    [n_verts][4].  tri_normals / tri_max_span: Triangle.Normal / MaxSpan; target_parts / target_vertices: index lists (None: all)."""
+    m = desc_or_marshalled if isinstance(desc_or_marshalled, _Marshalled) else _Marshalled(desc_or_marshalled)
+    mesh_i = m.scene.models[m.model_index[id(model)]].mesh
+    n = model.mesh.n_verts
+    out = np.ones((n, 4), np.float32) if colors4 is None else np.ascontiguousarray(colors4, np.float32).reshape(n, 4).copy()
+    tn = np.ascontiguousarray(tri_normals, np.float32); ts = np.ascontiguousarray(tri_max_span, np.float32)
+    tp = tv = None
+    if target_parts is not None:
+        tp = np.zeros(len(model.mesh.parts), np.uint8); tp[list(target_parts)] = 1
+    if target_vertices is not None:
+        tv = np.zeros(n, np.uint8); tv[list(target_vertices)] = 1
+    oc = np.asarray(occlusion_color, np.float32)
+    L = lib()
+    rc = L.orc_bake_ao(C.byref(m.scene.meshes[mesh_i]), _fp(tn), _fp(ts), tp.ctypes.data_as(u8p) if tp is not None else None,
+                       tv.ctypes.data_as(u8p) if tv is not None else None, float(occlusion_angle), _fp(oc), _fp(out))
+    if rc != 0:
+        raise RuntimeError("oracle: %s" % L.orc_last_error().decode())
+    return out
+
+
+def go_acos(x: float) -> float:
+    return float(lib().orc_go_acos(float(x)))
+
+
+def bake_lighting(desc_or_marshalled, model, lights, rgb: Optional[np.ndarray] = None) -> np.ndarray:
+    """Model.BakeLighting (model.go:1203-1268) of `model` (a ModelDesc of the scene) with `lights` (LightDescs of the scene, in
+    order; the world's ambient light is added by the oracle): the target channel's RGB, [n_verts][3].  `rgb`: the channel before
+    the call (default: 1, 1, 1 -- a channel that did not exist, mesh.go:543-558)."""
+    m = desc_or_marshalled if isinstance(desc_or_marshalled, _Marshalled) else _Marshalled(desc_or_marshalled)
+    n = model.mesh.n_verts
+    out = np.ones((n, 3), np.float32) if rgb is None else np.ascontiguousarray(rgb, np.float32).reshape(n, 3).copy()
+    ids = np.asarray([m.light_index[id(l)] for l in lights], dtype=np.int32)
+    L = lib()
+    rc = L.orc_bake_lighting(C.byref(m.scene), m.model_index[id(model)], ids.ctypes.data_as(i32p) if len(ids) else None, len(ids), _fp(out))
+    if rc != 0:
+        raise RuntimeError("oracle: %s" % L.orc_last_error().decode())
+    return out
 
 
 def render_scene(desc_or_marshalled, capture: bool = False, copy: bool = True) -> OracleResult:

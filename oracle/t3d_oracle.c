@@ -1904,3 +1904,78 @@ void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playh
     }
     free(world);
 }
+
+/* ================================================================================================
+ * Model.BakeAO, the pass over the model's own triangles (model.go:1040-1124)
+ * ================================================================================================ */
+/* Go's math.Asin / math.Acos for amd64 (pure Go, src/math/asin.go): Asin through satan (atan.go, restated above). */
+static double go_asin(double x) {
+    if (x == 0) return x;
+    int sign = 0;
+    if (x < 0) { x = -x; sign = 1; }
+    if (x > 1) return NAN;
+    double temp = sqrt(1 - x * x);
+    if (x > 0.7) temp = 1.57079632679489661923132169163975144 /* Pi/2 */ - go_satan(temp / x);
+    else temp = go_satan(x / temp);
+    return sign ? -temp : temp;
+}
+static double go_acos(double x) { return 1.57079632679489661923132169163975144 - go_asin(x); }
+double orc_go_acos(double x) { return go_acos(x); }
+
+/* Vector3.Angle (vector.go:468-478) */
+static float v3_angle(vec3 vec, vec3 other) {
+    const float eps = 1e-4f;
+    if (!(m32_abs(other.X) > eps || m32_abs(other.Y) > eps || m32_abs(other.Z) > eps)) return 0;   /* other.IsZero(), vector.go:428-438 */
+    float d = v3_dot(vec, other);
+    d /= (vec.X * vec.X + vec.Y * vec.Y + vec.Z * vec.Z) * (other.X * other.X + other.Y * other.Y + other.Z * other.Z);
+    d = m32_clamp(d, -1, 1);
+    return (float)go_acos((double)d);                     /* math32.Acos */
+}
+
+/* colors4: VertexColors[TargetChannel], [n_verts][4], in / out.  target_parts: one byte per MeshPart (NULL = all, an empty
+ * TargetMeshParts); target_vertices: one byte per vertex (NULL = all, an empty TargetVertices). */
+int orc_bake_ao(const orc_mesh* mesh, const float* tri_normals3, const float* tri_max_span, const uint8_t* target_parts,
+                const uint8_t* target_vertices, float occlusion_angle, const float* occlusion_color4, float* colors4) {
+    const int nt = mesh->n_tris;
+    float* centers = malloc((size_t)(nt > 0 ? nt : 1) * 12);
+    orc_triangle_centers(mesh->positions, mesh->indices, nt, centers);
+    int* partOf = malloc((size_t)(nt > 0 ? nt : 1) * sizeof(int));
+    for (int t = 0; t < nt; t++) partOf[t] = -1;
+    for (int p = 0; p < mesh->n_parts; p++)
+        for (int t = mesh->parts[p].triangle_start; t <= mesh->parts[p].triangle_end && t < nt; t++) partOf[t] = p;
+    const vec3* P = (const vec3*)mesh->positions;
+    for (int ti = 0; ti < nt; ti++) {                         /* model.go:1052 */
+        if (target_parts && !(partOf[ti] >= 0 && target_parts[partOf[ti]])) continue;      /* model.go:1054-1066 */
+        const uint32_t* tri = mesh->indices + 3 * (size_t)ti;
+        float ao[3] = {0, 0, 0};
+        const vec3 triCenter = v3(centers[3 * ti], centers[3 * ti + 1], centers[3 * ti + 2]);
+        const vec3 triNormal = v3(tri_normals3[3 * ti], tri_normals3[3 * ti + 1], tri_normals3[3 * ti + 2]);
+        for (int oi = 0; oi < nt; oi++) {                     /* model.go:1070 */
+            if (oi == ti) continue;
+            const uint32_t* other = mesh->indices + 3 * (size_t)oi;
+            float span = (tri_max_span[ti] > tri_max_span[oi] ? tri_max_span[ti] : tri_max_span[oi]) * 0.66f;
+            if (v3_dist2(triCenter, v3(centers[3 * oi], centers[3 * oi + 1], centers[3 * oi + 2])) > span * span) continue;
+            float angle = v3_angle(triNormal, v3(tri_normals3[3 * oi], tri_normals3[3 * oi + 1], tri_normals3[3 * oi + 2]));
+            if (angle < occlusion_angle) continue;
+            /* SharesVertexPositions, mesh.go:2050-2081 */
+            int shared[3] = {-1, -1, -1}, count = 0;
+            for (int index = 0; index < 3; index++)
+                for (int otherIndex = 0; otherIndex < 3; otherIndex++)
+                    if (v3_equals(P[tri[index]], P[other[otherIndex]])) { shared[index] = otherIndex; count++; break; }
+            if (count > 0) { if (shared[0] >= 0) ao[0] = 1; if (shared[1] >= 0) ao[1] = 1; if (shared[2] >= 0) ao[2] = 1; }
+            if (ao[0] == 1 && ao[1] == 1 && ao[2] == 1) break;
+        }
+        for (int i = 0; i < 3; i++) {                         /* model.go:1101-1116 */
+            float p = m32_clamp(ao[i], 0, 1);
+            int vertexIndex = (int)tri[i];
+            if (target_vertices && !target_vertices[vertexIndex]) continue;
+            float* c = colors4 + 4 * (size_t)vertexIndex;
+            c[0] += (occlusion_color4[0] - c[0]) * p;
+            c[1] += (occlusion_color4[1] - c[1]) * p;
+            c[2] += (occlusion_color4[2] - c[2]) * p;
+            c[3] += (occlusion_color4[3] - c[3]) * p;
+        }
+    }
+    free(centers); free(partOf);
+    return ORC_OK;
+}

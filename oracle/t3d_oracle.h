@@ -249,6 +249,10 @@ int  orc_render_scene(const orc_scene* scene, int capture, orc_result** out);
 void orc_free_result(orc_result* r);
 /* Model.BakeLighting (model.go:1203-1268) of model `model` with the lights light_ids[0..n) plus the world's ambient light:
  * rgb = VertexColors[targetChannel] of its mesh, [n_verts][3], in / out. */
+/* Model.BakeAO, same-model pass (model.go:1040-1124); Triangle.Normal / MaxSpan (mesh.go:2018-2037) are inputs. */
+int  orc_bake_ao(const orc_mesh* mesh, const float* tri_normals3, const float* tri_max_span, const uint8_t* target_parts,
+                 const uint8_t* target_vertices, float occlusion_angle, const float* occlusion_color4, float* colors4);
+double orc_go_acos(double x);                                                             /* Go math.Acos */
 int  orc_bake_lighting(const orc_scene* scene, int32_t model, const int32_t* light_ids, int32_t n, float* rgb);
 const char* orc_last_error(void);
 

@@ -46,7 +46,10 @@ def assert_parity(desc, device, check_capture=True, exact=True, modes=("fast", "
             device.SetExactLighting(mode == "exact")
             out = _check_frame(desc, device, ref, check_capture, exact and mode == "exact", mode)
     finally:
-        device.SetExactLighting(False)
+        try:
+            device.SetExactLighting(False)
+        except Exception:       # (must not mask the failure that brought us here)
+            pass
     return out
 
 

@@ -6,7 +6,7 @@ import scenes
 from compare import assert_parity, render_gpu, bits
 from oracle import binding as O
 from tetra3d_b200 import workloads as W
-from tetra3d_b200.scenedesc import CameraDesc, ModelDesc, NodeDesc, SceneDesc, WorldDesc
+from tetra3d_b200.scenedesc import CameraDesc, MaterialDesc, ModelDesc, NodeDesc, SceneDesc, WorldDesc
 
 pytestmark = pytest.mark.gpu
 
@@ -289,3 +289,25 @@ def test_multi_gpu_sharded_gather_matches_oracle():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_both_sort_paths_of_large_draws(device, mode):
+    """Draws of 9 .. 64 tiles are sorted either by the three-kernel segmented sort or by the single persistent kernel (k_cull_sort:
+    tiles in ticket order, two draw-wide arrivals); which one a frame gets is a heuristic (t3d_debug_set_fused_sort), and both
+    must give the oracle's lists: the 1 M-triangle frame (1000 tiles: more than are resident at once, so tickets wrap), the lit
+    stress scene, a frame that mixes them with draws of more than 64 tiles, and all three sort modes."""
+    try:
+        device.SetFusedSort(mode)
+        assert_parity(W.million_triangle_scene(), device, check_capture=False, modes=("fast",))
+        assert_parity(W.stress_scene(lit=True), device, check_capture=False, modes=("fast",))
+        rng = np.random.default_rng(77)
+        models = []
+        for k, n in enumerate((9000, 70000, 12000, 30000, 8193, 66000, 20000)):
+            mesh = scenes.random_soup(n, 700 + k, n_parts=1, extent=3.0, material=MaterialDesc(triangle_sort_mode=k % 3, backface_culling=bool(k % 2)))
+            models.append(ModelDesc(mesh, NodeDesc(position=tuple(float(x) for x in rng.uniform(-6, 6, 3)), rotation=scenes.random_rotation(rng)),
+                                    frustum_culling=False, name="l%d" % k))
+        sc = SceneDesc(models, scenes.lights_mixed(rng), CameraDesc(node=NodeDesc(position=(0.0, 2.0, 25.0))), WorldDesc(), name="largemix")
+        assert_parity(sc, device, check_capture=False, modes=("fast",))
+    finally:
+        device.SetFusedSort(1)

@@ -171,3 +171,36 @@ def test_oracle_is_deterministic():
     sc = scenes.soup_scene(5)
     a = O.render_scene(sc); b = O.render_scene(sc)
     assert np.array_equal(a.color_list.view(np.uint32), b.color_list.view(np.uint32)) and np.array_equal(a.tri_ids, b.tri_ids)
+
+
+def test_bake_lighting_adds_once_per_corner():
+    """Model.BakeLighting (model.go:1246-1262) walks the part's triangles light by light: a vertex two triangles share receives a
+    light's contribution twice.  A quad of two triangles sharing vertices 0 and 2, one ambient light of 0.25 and the world's ambient
+    light at 0.5 (0.125, 0.25, 0.5 each): corners 1 and 3 get one helping of each, 0 and 2 two."""
+    from tetra3d_b200 import workloads as W
+    from tetra3d_b200.scenedesc import CameraDesc, LightDesc, ModelDesc, NodeDesc, SceneDesc, WorldDesc, LIGHT_AMBIENT
+    mesh = W.plane_mesh(2, 2)
+    amb = LightDesc(LIGHT_AMBIENT, color=(1.0, 0.5, 0.25), energy=0.25)
+    desc = SceneDesc([ModelDesc(mesh, NodeDesc(), name="quad")], [amb], CameraDesc(node=NodeDesc(position=(0, 0, 5))),
+                     WorldDesc(ambient_color=(0.25, 0.5, 1.0), ambient_energy=0.5), name="bake")
+    rgb = O.bake_lighting(desc, desc.models[0], [amb])
+    one = np.array([0.25 + 0.125, 0.125 + 0.25, 0.0625 + 0.5], np.float32)
+    two = np.array([0.25 + 0.25 + 0.125 + 0.125, 0.125 + 0.125 + 0.25 + 0.25, 0.0625 + 0.0625 + 0.5 + 0.5], np.float32)
+    assert np.array_equal(rgb[1], one) and np.array_equal(rgb[3], one)
+    assert np.array_equal(rgb[0], two) and np.array_equal(rgb[2], two)
+    # an invisible light takes no part; a Shadeless part is painted white (model.go:1241-1248)
+    amb.visible = False
+    assert np.array_equal(O.bake_lighting(desc, desc.models[0], [amb])[1], np.array([0.125, 0.25, 0.5], np.float32))
+    mesh.parts[0].material.shadeless = True
+    assert np.array_equal(O.bake_lighting(desc, desc.models[0], [amb]), np.ones((4, 3), np.float32))
+
+
+def test_go_acos_restatement():
+    """math32.Acos is float32(math.Acos(float64(x))); Go's amd64 Acos is pure Go (Pi/2 - Asin, Asin through satan).  The
+    restatement agrees with glibc within 4 ulp of Pi/2 (two subtractions from Pi/2 cancel near |x| = 1) over [-1, 1] and on the special cases asin.go lists."""
+    import math
+    xs = np.concatenate([np.linspace(-1, 1, 4001), [0.7, 0.70000001, -0.7, 1e-300, -1e-300, 0.66]])     # (closer to 1, asin.go's 1 - x*x cancels: Go's own error, not the restatement's)
+    for x in xs:
+        g, r = O.go_acos(float(x)), math.acos(float(x))
+        assert abs(g - r) <= 4 * np.spacing(math.pi / 2), (x, g, r)
+    assert O.go_acos(1.0) == 0.0 and O.go_acos(0.0) == math.pi / 2 and math.isnan(O.go_acos(1.5))

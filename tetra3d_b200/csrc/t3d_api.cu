@@ -133,6 +133,13 @@ struct t3d_ctx {
     PinVec<DrawRec> hTmpl;
     PinVec<float> hRot;
     PinVec<uint32_t> hVbase, hTbase, hTileV, hLarge, hPacked, hMedium, hHuge;
+    PinVec<uint32_t> hFused;        // tiles of the draws of 9 .. HUGE_TILES tiles: culled and sorted by k_cull_sort (hLarge keeps the tiles of larger draws)
+    uint32_t* pFused = nullptr;
+    // k_cull_sort wins when all its tiles are resident at once (one wave: 300 K-triangle frame of 12-tile draws 26.4 -> 21.0 us for
+    // cull + sort); with more tiles than resident blocks, draws that straddle the wave boundary hold their first-wave blocks
+    // until second-wave blocks find a slot, and the three-kernel path is as fast or faster (1 M triangles: 41.4 vs 38.5 us staged,
+    // 102.1 vs 103.4 us chained).  fuseSort: 0 never, 1 when the tiles fit one wave (default), 2 always (T3D_FUSE_SORT, tests).
+    int fuseSort = 1; int smCount = 148; bool frameFused = false;
     PinVec<uint4> hVClass[3];       // vertex tiles by class (0 generic, 1 static fast, 2 skinned fast): {tile, first draw, first draw of the next tile, end of the first draw's vertices}
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
@@ -276,6 +283,9 @@ int t3d_create(t3d_ctx** out, int device_id) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char* fs = getenv("T3D_FUSE_SORT")) ctx->fuseSort = atoi(fs);
+    cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device_id);
+    if (ctx->smCount <= 0) ctx->smCount = 148;
     if (const char* th = getenv("T3D_DMA_THRESHOLD")) ctx->dmaThreshold = (size_t)strtoull(th, nullptr, 10);      // diagnostics: bytes; 0 = always copy, huge = never
     if (const char* cb = getenv("T3D_PREP_CHUNK_BLOCKS")) ctx->prepChunkBlocks = std::max(1u, (uint32_t)strtoul(cb, nullptr, 10));    // diagnostics / tests
     *out = ctx;
@@ -300,7 +310,7 @@ void t3d_destroy(t3d_ctx* ctx) {
                       &ctx->dCount, &ctx->dTileCtr, &ctx->dGatherErr, &ctx->dColor, &ctx->dDepth, &ctx->dNormal, &ctx->dTriIds};
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
-    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release();
+    ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release(); ctx->hFused.release();
     ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
     ctx->hMail.release(); ctx->hGatherStats.release(); ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
@@ -549,6 +559,45 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
     ctx->nVerticesOut = 0;
     ctx->bakeFrame = false;
+    return T3D_OK;
+}
+
+int t3d_bake_ao(t3d_ctx* ctx, uint64_t mesh_id, const float* tri_normals3, const float* tri_max_span, const uint8_t* target_parts,
+                const uint8_t* target_vertices, float occlusion_angle, const float occlusion_color[4], float* colors4) {
+    if (!ctx || !tri_normals3 || !tri_max_span || !occlusion_color || !colors4) return fail(ctx, T3D_E_INVALID, "t3d_bake_ao: NULL argument");
+    auto it = ctx->meshes.find(mesh_id);
+    if (it == ctx->meshes.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_bake_ao: unknown mesh (t3d_mesh_upload first)");
+    const Mesh& m = it->second;
+    if (m.subdiv) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_bake_ao: mesh with auto-subdivision data (its triangle arrays hold the sub-triangles too)");
+    if (!m.nTris || !m.nVerts) return T3D_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<uint8_t> triTarget;
+    if (target_parts) {         // TargetMeshParts (model.go:1054-1066): a triangle takes part when its MeshPart is listed
+        triTarget.assign(m.nTris, 0);
+        for (size_t p = 0; p < m.parts.size(); p++)
+            if (target_parts[p]) for (uint32_t t = m.parts[p].triStart; t < m.parts[p].triEnd && t < m.nTris; t++) triTarget[t] = 1;
+    }
+    DevBuf dN, dS, dTT, dVT, dM, dC;
+    struct Free { DevBuf* b[6]; ~Free() { for (DevBuf* x : b) x->release(); } } guard{{&dN, &dS, &dTT, &dVT, &dM, &dC}};
+    CU(dN.ensure(12ull * m.nTris)); CU(dS.ensure(4ull * m.nTris)); CU(dM.ensure(m.nTris)); CU(dC.ensure(16ull * m.nVerts));
+    CU(cudaMemcpyAsync(dN.p, tri_normals3, 12ull * m.nTris, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dS.p, tri_max_span, 4ull * m.nTris, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dC.p, colors4, 16ull * m.nVerts, cudaMemcpyHostToDevice, s));
+    if (target_parts) { CU(dTT.ensure(m.nTris)); CU(cudaMemcpyAsync(dTT.p, triTarget.data(), m.nTris, cudaMemcpyHostToDevice, s)); }
+    if (target_vertices) { CU(dVT.ensure(m.nVerts)); CU(cudaMemcpyAsync(dVT.p, target_vertices, m.nVerts, cudaMemcpyHostToDevice, s)); }
+    launch_ao(s, m.pos, m.nVertsPad, m.idx, m.ctr, m.nTrisPad, m.nTris, m.nVerts, dN.as<float>(), dS.as<float>(),
+              target_parts ? dTT.as<uint8_t>() : nullptr, target_vertices ? dVT.as<uint8_t>() : nullptr, occlusion_angle, occlusion_color,
+              dM.as<uint8_t>(), dC.as<float4>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(colors4, dC.p, 16ull * m.nVerts, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return T3D_OK;
+}
+
+int t3d_frame_abort(t3d_ctx* ctx) {
+    if (!ctx) return T3D_E_INVALID;
+    if (ctx->inFrame && !ctx->executed) ctx->inFrame = false;      // what was submitted is dropped at the next t3d_frame_begin
     return T3D_OK;
 }
 
@@ -942,8 +991,16 @@ static void build_tiles(const uint32_t* base, uint32_t nDraws, uint32_t nTiles, 
 // exclusive tiles and go through k_cull_large + the segmented counting sort; smaller draws are packed whole
 // into tiles of at most TILE_TRIS triangles and TILE_TRIS draws and are culled and sorted by k_tile_packed.
 static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
-    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear(); ctx->hMedium.clear(); ctx->hHuge.clear();
+    ctx->hTiles.clear(); ctx->hLarge.clear(); ctx->hPacked.clear(); ctx->hMedium.clear(); ctx->hHuge.clear(); ctx->hFused.clear();
     const uint32_t* tb = ctx->hTbase.p;
+    {   // would k_cull_sort's tiles be resident all at once?
+        uint64_t cand = 0;
+        for (uint32_t d = 0; d < nDraws; d++) {
+            const uint32_t nt = tb[d + 1] - tb[d];
+            if (nt > MEDIUM_TRIS && (nt + TILE_TRIS - 1) / TILE_TRIS <= HUGE_TILES) cand += (nt + TILE_TRIS - 1) / TILE_TRIS;
+        }
+        ctx->frameFused = ctx->fuseSort == 2 || (ctx->fuseSort == 1 && cand <= (uint64_t)ctx->smCount * FUSED_RESIDENT_BLOCKS);
+    }
     TriTile cur; memset(&cur, 0, sizeof cur);
     cudaError_t e = cudaSuccess;
     ctx->nHistRows = 0;
@@ -977,7 +1034,7 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
             for (uint32_t j = 0; j < n; j++) {
                 TriTile t; t.start = tb[d] + j * TILE_TRIS; t.count = std::min(TILE_TRIS, nt - j * TILE_TRIS); t.dFirst = d; t.info = TILE_LARGE | j;
                 t.row0 = ctx->nHistRows; t.nTilesOfDraw = n; t.sortMode = ctx->hDraws[d].sortMode; t.tbase = tb[d];
-                if (!medium && (e = ctx->hLarge.push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
+                if (!medium && (e = ((n > HUGE_TILES || !ctx->frameFused) ? ctx->hLarge : ctx->hFused).push((uint32_t)ctx->hTiles.n)) != cudaSuccess) return e;
                 if ((e = ctx->hTiles.push(t)) != cudaSuccess) return e;
             }
             if (!medium) ctx->nHistRows += n + 1;
@@ -1066,7 +1123,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     CU(build_tri_tiles(ctx, nDraws));
     const uint32_t nTiles = (uint32_t)ctx->hTiles.n, nLarge = (uint32_t)ctx->hLarge.n, nPacked = (uint32_t)ctx->hPacked.n;
-    const uint32_t nMedium = (uint32_t)ctx->hMedium.n;
+    const uint32_t nMedium = (uint32_t)ctx->hMedium.n, nFused = (uint32_t)ctx->hFused.n;
 
     const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
 
@@ -1184,13 +1241,13 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                        {ctx->hRuns.data(), runMode ? sizeof(DrawRun) * ctx->hRuns.size() : 0, 0},
                        {ctx->hBlockRun.data(), runMode ? 4ull * ctx->hBlockRun.size() : 0, 0},
                        {ctx->hPoses.p, sizeof(t3d_pose) * ctx->hPoses.n, 0}};       // read by k_pose_bones
-        Seg segs[13] = {
+        Seg segs[14] = {
             {nullptr, 0, 0}, {nullptr, 0, 0} /* vbase / tbase: k_prep_draws writes the device tables from the placement records */,
             {nullptr, 0, 0} /* the vertex-tile table stays on the host: its entries travel inside the class lists */, {ctx->hTiles.p, sizeof(TriTile) * (size_t)nTiles, 0},
             {ctx->hLarge.p, 4ull * nLarge, 0}, {ctx->hPacked.p, 4ull * nPacked, 0},
             {ctx->hLights.p, sizeof(t3d_light) * ctx->hLights.n, 0}, {nullptr, 0, 0} /* bones travel separately, below */,
             {ctx->hMedium.p, 4ull * nMedium, 0}, {ctx->hVClass[0].p, 16ull * ctx->hVClass[0].n, 0}, {ctx->hVClass[1].p, 16ull * ctx->hVClass[1].n, 0},
-            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 16ull * ctx->hVClass[2].n, 0}};
+            {ctx->hHuge.p, 4ull * ctx->hHuge.n, 0}, {ctx->hVClass[2].p, 16ull * ctx->hVClass[2].n, 0}, {ctx->hFused.p, 4ull * nFused, 0}};
         size_t headBytes = 0, restBytes = 0;
         for (Seg& g : head) { g.off = headBytes; headBytes += (g.bytes + 255) & ~(size_t)255; }
         for (Seg& g : segs) { g.off = restBytes; restBytes += (g.bytes + 255) & ~(size_t)255; }
@@ -1257,6 +1314,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->pVClass[1] = reinterpret_cast<uint4*>(rest + segs[10].off);
         ctx->pHuge = reinterpret_cast<uint32_t*>(rest + segs[11].off);
         ctx->pVClass[2] = reinterpret_cast<uint4*>(rest + segs[12].off);
+        ctx->pFused = reinterpret_cast<uint32_t*>(rest + segs[13].off);
         ctx->h2dBytes = 0;
         for (Seg& g : head) ctx->h2dBytes += g.bytes;
         for (Seg& g : segs) ctx->h2dBytes += g.bytes;
@@ -1363,31 +1421,34 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         ctx->vertexKernelBytes = 0;
         return T3D_OK;
     }
-    // K2: cull (small draws are also sorted here)
-    launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
-                      ctx->dTdepth.as<uint32_t>(), stats, ctx->anySubdiv);
+    // K2: cull (small and medium draws are also sorted here; so are the large ones up to HUGE_TILES tiles, by k_cull_sort,
+    // whose extra block also computes where every tile starts in the lists when the frame's tiles fit one scan chunk)
     launch_tile_packed(s, pdl, ctx->pDraws, ctx->pTbase, ctx->pTiles, ctx->pPacked, nPacked, ctx->fc, ctx->dClip.as<float4>(),
                        ctx->dWpos.as<float4>(), ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), stats, ctx->anySubdiv);
     launch_draw_medium(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pMedium, nMedium, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
                        ctx->dSorted.as<uint32_t>(), stats, ctx->anySubdiv);
-    ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0) + (nMedium ? 1 : 0);
+    launch_cull_large(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pLarge, nLarge, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
+                      ctx->dTdepth.as<uint32_t>(), stats, ctx->anySubdiv);
+    const bool oneChunk = nTiles <= SCAN_CHUNK;
+    const bool scanInFused = nFused && oneChunk;
+    launch_cull_sort(s, pdl, ctx->pDraws, ctx->pTiles, ctx->pFused, nFused, ctx->dTileCtr.as<uint32_t>() + 4, ctx->fc, ctx->dClip.as<float4>(), ctx->dWpos.as<float4>(),
+                     stats, ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>(), ctx->anySubdiv, scanInFused ? nTiles : 0u,
+                     ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
+    ctx->launches += (nLarge ? 1 : 0) + (nPacked ? 1 : 0) + (nMedium ? 1 : 0) + (nFused ? 1 : 0);
     CU(mark(4));
     // K3: where every tile starts in the lists (needs only the survivor counts), then the segmented 512-bin
-    // counting sort of the large draws
-    const bool scanRides = nLarge && nTiles <= SCAN_CHUNK;     // one chunk: the scan rides along as k_bin_hist's extra block
-    if (nLarge && !scanRides) {
+    // counting sort of the draws of more than HUGE_TILES tiles
+    const bool scanRides = !scanInFused && nLarge && oneChunk;     // one chunk: the scan rides along as k_bin_hist's extra block
+    if (!scanInFused && !scanRides) {
         launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
         ctx->launches += 1;
     }
-    if (nLarge) {       // the tile scan rides along as k_bin_hist's extra block
+    if (nLarge) {
         launch_bin_hist(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, scanRides ? nTiles : 0xFFFFFFFFu, stats, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(),
                         ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
         launch_hist_scan_huge(s, pdl, ctx->pTiles, ctx->pHuge, (uint32_t)ctx->hHuge.n, ctx->dHist.as<uint32_t>());
         launch_scatter(s, pdl, ctx->pTiles, ctx->pLarge, nLarge, ctx->dTdepth.as<uint32_t>(), ctx->dHist.as<uint32_t>(), ctx->dSorted.as<uint32_t>());
         ctx->launches += 2 + (ctx->hHuge.n ? 1 : 0);
-    } else {
-        launch_tile_scan(s, pdl, ctx->pTiles, nTiles, stats, ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>());
-        ctx->launches += 1;
     }
     CU(mark(5));
     // K4
@@ -1740,6 +1801,11 @@ int t3d_set_stage_timings(t3d_ctx* ctx, int enabled) {
 }
 
 int t3d_debug_last_launch_count(t3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int t3d_debug_set_fused_sort(t3d_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return T3D_E_INVALID;
+    ctx->fuseSort = mode;
+    return T3D_OK;
+}
 int t3d_debug_vertex_trace(t3d_ctx* ctx, unsigned long long* out, uint32_t n_blocks) {
     if (!ctx || !out) return T3D_E_INVALID;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return T3D_E_CUDA;

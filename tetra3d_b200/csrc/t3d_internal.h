@@ -42,6 +42,13 @@ int debug_vertex_trace(unsigned long long* out, uint32_t nBlocks);      // -DT3D
 static const uint32_t VERTEX_FAST_MAX_LIGHTS = 16;      // k_vertex<true> stages the light list: longer lists go to the generic kernel
 void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* largeList, uint32_t nLarge,
                        const FrameConst& fc, const float4* clip, const float4* wpos, uint32_t* tdepth, DrawStat* stats, bool subdiv);
+#ifndef T3D_FUSED_MINBLOCKS
+#define T3D_FUSED_MINBLOCKS 4
+#endif
+static const uint32_t FUSED_RESIDENT_BLOCKS = T3D_FUSED_MINBLOCKS;     // k_cull_sort blocks resident per SM (its launch bounds)
+void launch_cull_sort(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* fusedList, uint32_t nFused, uint32_t* ctr /* [2], zeroed by k_prep_draws */,
+                      const FrameConst& fc, const float4* clip, const float4* wpos, DrawStat* stats, uint32_t* hist, uint32_t* sorted, bool subdiv,
+                      uint32_t scanTiles, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum);
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,
                         const uint32_t* packedList, uint32_t nPacked, const FrameConst& fc, const float4* clip,
                         const float4* wpos, uint32_t* sorted, uint32_t* tileSurv, DrawStat* stats, bool subdiv);
@@ -69,6 +76,11 @@ void launch_scatter(cudaStream_t s, bool pdl, const TriTile* tiles, const uint32
                     const uint32_t* tkeys, const uint32_t* hist, uint32_t* sorted);
 void launch_tile_scan(cudaStream_t s, bool pdl, const TriTile* tiles, uint32_t nTiles, const DrawStat* stats, uint32_t* tileSurv,
                       uint32_t* tileOut, uint32_t* chunkSum);
+
+// t3d_bake.cu -- Model.BakeAO (same-model pass)
+void launch_ao(cudaStream_t s, const float* pos, uint32_t vstride, const uint32_t* idx, const float* ctr, uint32_t tstride, uint32_t nTris, uint32_t nVerts,
+               const float* triNormal, const float* triSpan, const uint8_t* triTarget, const uint8_t* vertTarget, float occlusionAngle,
+               const float* occlusionColor4, uint8_t* marks, float4* colors);
 
 // t3d_pose.cu -- bone poses evaluated on the device
 cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb);

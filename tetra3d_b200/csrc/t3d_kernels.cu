@@ -19,6 +19,7 @@
 // Built with -fmad=false: no multiply-add contraction anywhere (see t3d_device.cuh).
 #include "t3d_device.cuh"
 #include "t3d_pose.cuh"
+#include "t3d_scan.cuh"
 #include "t3d_internal.h"
 #include "../../include/t3dgeo.h"
 #include <algorithm>
@@ -110,7 +111,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
              LightU* __restrict__ lightsU, DrawStat* __restrict__ stats, const __grid_constant__ PrepPoses<POSES> pp) {
     extern __shared__ uint4 prepSmem[];
     pdl_launch();
-    if (pf.tileCtr && blockIdx.x == 0 && threadIdx.x < 4) pf.tileCtr[threadIdx.x] = 0;      // k_vertex's tile counters (one per class)
+    if (pf.tileCtr && blockIdx.x == 0 && threadIdx.x < 8) pf.tileCtr[threadIdx.x] = 0;      // k_vertex's tile counters (one per class), k_cull_sort's ticket and arrival counters
     // Pose blocks come FIRST in the grid (k_prep_draws<true>): they start at once and their float64 arithmetic overlaps the
     // PCIe round trips of the prep blocks, instead of trailing them as a second wave.
     uint32_t bid = blockIdx.x;
@@ -1436,6 +1437,192 @@ k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tile
     }
 }
 
+// ---- k_cull_sort: cull + depth key + the segmented 512-bin sort of the large draws in ONE launch -------------------------
+// A draw of 9 .. HUGE_TILES tiles needs two draw-wide facts before its triangles can be placed: its depth range (the bin
+// expression reads min / max over the survivors, sortingTriangles.go:38-64) and the per-tile bin counts of all its tiles.  The
+// three-kernel path (k_cull_large -> k_bin_hist -> k_scatter, t3d_sort.cu) gets them from kernel boundaries and carries the
+// depth keys through global memory in between.  Here the blocks are persistent and take tiles in ticket order from an atomic
+// counter; a block that has culled its tile publishes min / max / count and arrives on the draw's counter, waits until all
+// tiles of the draw have arrived, bins its survivors (still in registers), publishes its 512 counts, arrives again, waits
+// again, then sums the rows of the draw's tiles itself and scatters.  No depth key and no bin rank ever leaves the SM.
+//   Why the waits cannot deadlock: a block only waits for tiles of its own draw; those hold tickets within HUGE_TILES of its
+//   own; tickets are taken in order by running blocks, and neither arrival needs anything from a later ticket.  So the running
+//   block with the lowest ticket always finds its draw's earlier tiles arrived, and the later ones either running -- they
+//   arrive without waiting -- or not yet taken, in which case a block that is not waiting exists or is about to start (the
+//   grid is sized to be resident at once; blocks still queued behind the previous kernel's tail start as that drains).
+// DrawStat.done counts both arrivals: nTilesOfDraw after the cull, 2 x nTilesOfDraw after the counts.
+// One extra block computes where every tile's triangles start in the lists (t3d_sort.cu: tile_scan_chunk) once every tile of
+// this launch has passed its cull -- the other cull kernels ran before this one.
+__device__ __forceinline__ void spin_until(const uint32_t* word, uint32_t target) {
+    uint32_t v;
+    for (uint32_t polls = 0;; polls++) {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+        if (v >= target) break;
+        __nanosleep(32);
+        // (a frame's tiles arrive within microseconds; a wait of seconds means a broken invariant, and then a wrong frame that the
+        // survivor-count check of t3d_frame_results reports beats a GPU that never comes back)
+        if (polls > (1u << 26)) break;
+    }
+}
+template <bool SUBDIV>
+__global__ void __launch_bounds__(TILE_THREADS, T3D_FUSED_MINBLOCKS)
+k_cull_sort(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ fusedList, uint32_t nFused,
+            uint32_t* __restrict__ ctr /* [0] next ticket, [1] tiles past their cull */, const __grid_constant__ FrameConst fc,
+            const float4* __restrict__ clip, const float4* __restrict__ wpos, DrawStat* __restrict__ stats,
+            uint32_t* __restrict__ hist, uint32_t* __restrict__ sorted,
+            uint32_t scanTiles /* 0: no scan block */, uint32_t* __restrict__ tileSurv, uint32_t* __restrict__ tileOut, uint32_t* __restrict__ chunkSum) {
+    __shared__ __align__(16) uint16_t sCnt[8][BIN_COUNT];
+    __shared__ uint32_t sBase[BIN_COUNT];
+    __shared__ uint32_t sMin[8], sMax[8], sNum[8], sWarp[32];
+    __shared__ uint32_t sTicket, sLo, sHi;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ROUNDS = TILE_ROUNDS;
+    const uint32_t nWorkers = gridDim.x - (scanTiles ? 1u : 0u);
+    if (blockIdx.x == nWorkers) {       // the scan block
+        pdl_wait(); pdl_launch();
+        if (threadIdx.x == 0) { spin_until(&ctr[1], nFused); __threadfence(); }
+        __syncthreads();
+        tile_scan_chunk<TILE_THREADS>(tiles, scanTiles, 0, stats, tileSurv, tileOut, chunkSum, sWarp);      // scanTiles <= SCAN_CHUNK
+        return;
+    }
+    uint32_t t = blockIdx.x;
+    bool first = true;
+    while (t < nFused) {
+        const TriTile T = tiles[__ldg(&fusedList[t])];
+        const uint32_t d = T.dFirst, nT = T.nTilesOfDraw, j = T.info & ~TILE_LARGE;
+        const DrawRec& R = draws[d];
+        const uint32_t flags = R.flags;
+        const bool skinned = flags & T3D_DRAW_SKINNED;
+        const bool backface = (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING);
+        const uint32_t ts = R.tstride;
+        const uint32_t mt0 = R.t0 + (T.start - R.tbase);
+        const uint32_t vb = R.vbase - R.a0;
+        const uint32_t* ip = R.idx + mt0;
+        const float* cp = R.ctr + mt0;
+        const float icx = R.invCam[0], icy = R.invCam[1], icz = R.invCam[2];
+        // ---- cull + depth (model.go:855-969).  Warp w owns slots [w * 128, w * 128 + 128) in rounds of 32: arrival order is
+        //      (warp, round, lane) == arena order, which is what the stable ranks below rest on.
+        uint32_t ia[ROUNDS], ib[ROUNDS], ic[ROUNDS];
+        float cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            const uint32_t i = warp * (ROUNDS * 32) + r * 32 + lane;
+            ia[r] = ib[r] = ic[r] = 0; cx[r] = cy[r] = cz[r] = 0.0f;
+            if (i < T.count) {
+                ia[r] = __ldg(ip + i); ib[r] = __ldg(ip + ts + i); ic[r] = __ldg(ip + 2 * (size_t)ts + i);
+                if (!skinned) { cx[r] = __ldg(cp + i); cy[r] = __ldg(cp + ts + i); cz[r] = __ldg(cp + 2 * (size_t)ts + i); }
+            }
+        }
+        {   // clear the per-warp bin counts for this tile
+            uint4* z = reinterpret_cast<uint4*>(&sCnt[0][0]);
+            z[threadIdx.x] = make_uint4(0, 0, 0, 0); z[threadIdx.x + TILE_THREADS] = make_uint4(0, 0, 0, 0);
+        }
+        if (first) { pdl_wait(); pdl_launch(); first = false; }       // clip / wpos are k_vertex's; everything above is mesh data and k_prep_draws' records
+        uint32_t key[ROUNDS];
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u, cnt = 0u;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            const uint32_t i = warp * (ROUNDS * 32) + r * 32 + lane;
+            key[r] = KEY_CULLED;
+            if (i < T.count) {
+                const float4 c0 = __ldg(&clip[vb + ia[r]]), c1 = __ldg(&clip[vb + ib[r]]), c2 = __ldg(&clip[vb + ic[r]]);
+                bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+                if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt0 + i);       // model.go:753-755
+                float depth = 0.0f;
+                if (keep) {                                                 // model.go:933-955
+                    if (skinned) depth = skinned_depth(__ldg(&wpos[vb + ia[r]]), __ldg(&wpos[vb + ib[r]]), __ldg(&wpos[vb + ic[r]]), fc.camPos);
+                    else { const float dx = icx - cx[r], dy = icy - cy[r], dz = icz - cz[r]; depth = dx * dx + dy * dy + dz * dz; }
+                    if (isnan(depth) || isinf(depth)) keep = false;        // model.go:957-960
+                }
+                if (keep) { key[r] = __float_as_uint(depth); mn = min(mn, key[r]); mx = max(mx, key[r]); cnt++; }
+            }
+        }
+        mn = __reduce_min_sync(full, mn); mx = __reduce_max_sync(full, mx); cnt = __reduce_add_sync(full, cnt);
+        if (lane == 0) { sMin[warp] = mn; sMax[warp] = mx; sNum[warp] = cnt; }
+        __syncthreads();
+        if (warp == 0) {
+            mn = lane < 8 ? sMin[lane] : 0xFFFFFFFFu; mx = lane < 8 ? sMax[lane] : 0u; cnt = lane < 8 ? sNum[lane] : 0u;
+            mn = __reduce_min_sync(full, mn); mx = __reduce_max_sync(full, mx); cnt = __reduce_add_sync(full, cnt);
+            if (lane == 0) {
+                if (cnt) { atomicMin(&stats[d].minBits, mn); atomicMax(&stats[d].maxBits, mx); atomicAdd(&stats[d].survivors, cnt); }
+                __threadfence();
+                atomicAdd(&stats[d].done, 1u);                  // first arrival: this tile's part of min / max / survivors is in
+                atomicAdd(&ctr[1], 1u);
+                spin_until(&stats[d].done, nT);
+                __threadfence();
+                sLo = __ldcg(&stats[d].minBits); sHi = __ldcg(&stats[d].maxBits);
+            }
+        }
+        __syncthreads();
+        // ---- bin (sortingTriangles.go:38-64) and stable rank inside the tile: per-warp counts, round by round
+        const uint32_t minBits = sLo, maxBits = sHi;
+        uint32_t rank[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            if (key[r] != KEY_CULLED) key[r] = bin_key(key[r], minBits, maxBits, T.sortMode);
+            const unsigned peers = __match_any_sync(full, key[r]);
+            const uint32_t inGroup = __popc(peers & ((1u << lane) - 1u));
+            uint32_t before = 0;
+            if (key[r] != KEY_CULLED && inGroup == 0) {
+                before = sCnt[warp][key[r]];
+                sCnt[warp][key[r]] = (uint16_t)(before + __popc(peers));
+            }
+            rank[r] = __shfl_sync(full, before, __ffs(peers) - 1) + inGroup;
+            __syncwarp();
+        }
+        __syncthreads();
+        uint2* rows = reinterpret_cast<uint2*>(hist + (size_t)T.row0 * BIN_COUNT);
+        {   // exclusive prefix over the 8 warps (two adjacent bins per thread in one 32-bit word; counts <= 1024); the totals are
+            // this tile's row of the draw's [tiles x 512] counts
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t* word = reinterpret_cast<uint32_t*>(&sCnt[w][0]) + threadIdx.x;
+                const uint32_t c = *word;
+                *word = run;
+                run += c;
+            }
+            rows[(size_t)j * (BIN_COUNT / 2) + threadIdx.x] = make_uint2(run & 0xFFFFu, run >> 16);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&stats[d].done, 1u); spin_until(&stats[d].done, 2u * nT); __threadfence();
+            // The next ticket is taken only now, when nothing of this tile waits any more: a block that held a second, unprocessed
+            // ticket while it waits could be waiting for itself.  Its round trip hides behind the row sums and the scatter.
+            sTicket = nWorkers + atomicAdd(&ctr[0], 1u);
+        }
+        __syncthreads();
+        {   // where this tile's share of every bin starts: bins in visiting order, tiles in arena order inside a bin.  Thread x
+            // owns bins 2x, 2x + 1; it sums them over the draw's tiles (one 8-byte load per tile row, coalesced over the block).
+            uint2 tot = make_uint2(0u, 0u), mine = make_uint2(0u, 0u);
+            for (uint32_t t0 = 0; t0 < nT; t0 += 8) {
+                uint2 c[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) c[u] = (t0 + u < nT) ? __ldcg(&rows[(size_t)(t0 + u) * (BIN_COUNT / 2) + threadIdx.x]) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (t0 + u == j) mine = tot;
+                    tot.x += c[u].x; tot.y += c[u].y;
+                }
+            }
+            const uint32_t base = block_exclusive_scan_256(tot.x + tot.y, sWarp, nullptr);
+            sBase[2 * threadIdx.x] = T.tbase + base + mine.x;
+            sBase[2 * threadIdx.x + 1] = T.tbase + base + tot.x + mine.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            if (key[r] != KEY_CULLED)
+                sorted[sBase[key[r]] + sCnt[warp][key[r]] + rank[r]] = T.start + warp * (ROUNDS * 32) + r * 32 + lane;
+        }
+        t = sTicket;
+        __syncthreads();            // the shared arrays are reused by the next tile
+    }
+    if (first) { pdl_wait(); pdl_launch(); }
+}
+
 // One stable counting-sort pass over the block's (at most TILE_TRIS) keys in shared memory, on the NB-valued
 // digit (key >> SHIFT) & (NB - 1).  Warp w owns slots [w * 128, w * 128 + 128) and walks them in rounds of 32,
 // so arrival order is (warp, round, lane) == slot order.  Entries at or beyond n, and entries equal to
@@ -2069,6 +2256,17 @@ void launch_cull_large(cudaStream_t s, bool pdl, const DrawRec* draws, const Tri
     if (!nLarge) return;
     if (subdiv) launch_kernel(k_cull_large<true>, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
     else launch_kernel(k_cull_large<false>, nLarge, TILE_THREADS, 0, s, pdl, draws, tiles, largeList, fc, clip, wpos, tdepth, stats);
+}
+
+// One wave of persistent blocks (plus the scan block when scanTiles != 0); ctr = {next ticket, tiles past their cull}, zeroed by k_prep_draws.
+void launch_cull_sort(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, const uint32_t* fusedList, uint32_t nFused, uint32_t* ctr,
+                      const FrameConst& fc, const float4* clip, const float4* wpos, DrawStat* stats, uint32_t* hist, uint32_t* sorted, bool subdiv,
+                      uint32_t scanTiles, uint32_t* tileSurv, uint32_t* tileOut, uint32_t* chunkSum) {
+    if (!nFused) return;
+    if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
+    const uint32_t grid = std::min(nFused, (uint32_t)g_smCount * (uint32_t)T3D_FUSED_MINBLOCKS) + (scanTiles ? 1u : 0u);
+    if (subdiv) launch_kernel(k_cull_sort<true>, grid, TILE_THREADS, 0, s, pdl, draws, tiles, fusedList, nFused, ctr, fc, clip, wpos, stats, hist, sorted, scanTiles, tileSurv, tileOut, chunkSum);
+    else launch_kernel(k_cull_sort<false>, grid, TILE_THREADS, 0, s, pdl, draws, tiles, fusedList, nFused, ctr, fc, clip, wpos, stats, hist, sorted, scanTiles, tileSurv, tileOut, chunkSum);
 }
 
 void launch_tile_packed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* tbase, const TriTile* tiles,

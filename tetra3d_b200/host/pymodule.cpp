@@ -39,6 +39,7 @@ static py::array vertex_list(const t3d_vertex* p, uint64_t n, bool onDevice) {
     return a;
 }
 
+namespace tetra3d { void TriangleNormalsAndSpans(const Mesh& mesh, std::vector<float>& normals3, std::vector<float>& spans); }
 PYBIND11_MODULE(_host, m) {
     m.doc() = "Host-side mirror of the Tetra3D API driving libt3dgeo (B200 geometry stage)";
 
@@ -100,6 +101,12 @@ PYBIND11_MODULE(_host, m) {
     py::class_<Mesh, std::shared_ptr<Mesh>>(m, "Mesh")
         .def(py::init([](const std::string& n) { return NewMesh(n); }), py::arg("name") = "mesh")
         .def_readonly("ID", &Mesh::id)
+        .def("TriangleNormalsAndSpans", [](Mesh& s) {       // Triangle.Normal / Triangle.MaxSpan (mesh.go:2018-2037): load-time products
+            std::vector<float> n, sp; TriangleNormalsAndSpans(s, n, sp);
+            py::array_t<float> a({(py::ssize_t)sp.size(), (py::ssize_t)3}), b((py::ssize_t)sp.size());
+            std::memcpy(a.mutable_data(), n.data(), n.size() * sizeof(float)); std::memcpy(b.mutable_data(), sp.data(), sp.size() * sizeof(float));
+            return py::make_tuple(a, b);
+        })
         .def_readwrite("Name", &Mesh::Name)
         .def_readwrite("VertexActiveColorChannel", &Mesh::VertexActiveColorChannel)
         .def_readonly("MeshParts", &Mesh::MeshParts)
@@ -277,6 +284,23 @@ PYBIND11_MODULE(_host, m) {
         .def("SetBoneInfluences", [](Model& s, const farr& mats) { if (mats.size() % 16) throw std::invalid_argument("need 16 floats per bone"); s.SetBoneInfluences(vec_from<float>(mats)); })
         // bones posed on the device: skeleton, the node its root bones hang from (Model.SkinRoot), the armature's player (or None)
         .def("SetSkeleton", &Model::SetSkeleton, py::arg("skeleton"), py::arg("skin_root"), py::arg("player") = nullptr)
+        .def("BakeAO", [](Model& s, GeometryDevice& dev, int targetChannel, float occlusionAngle, std::vector<float> occlusionColor,
+                          std::vector<int> targetParts, std::vector<int> targetVertices) {
+            if (occlusionColor.size() != 4) throw std::invalid_argument("BakeAO: occlusionColor must have 4 components");
+            std::vector<float> out = s.BakeAO(dev, targetChannel, occlusionAngle, Color4{occlusionColor[0], occlusionColor[1], occlusionColor[2], occlusionColor[3]}, targetParts, targetVertices);
+            py::array_t<float> a({(py::ssize_t)(out.size() / 4), (py::ssize_t)4});
+            std::memcpy(a.mutable_data(), out.data(), out.size() * sizeof(float));
+            return a;
+        }, py::arg("device"), py::arg("targetChannel") = 0, py::arg("occlusionAngle") = 1.0471976f, py::arg("occlusionColor") = std::vector<float>{0.4f, 0.4f, 0.4f, 1.0f},
+           py::arg("targetParts") = std::vector<int>{}, py::arg("targetVertices") = std::vector<int>{})
+        .def("BakeLighting", [](Model& s, int targetChannel, Camera& cam, Scene& scene, py::list lights) {
+            std::vector<std::shared_ptr<ILight>> ls;
+            for (auto l : lights) ls.push_back(l.cast<std::shared_ptr<ILight>>());
+            std::vector<float> out = s.BakeLighting(targetChannel, cam, scene, ls);
+            py::array_t<float> a({(py::ssize_t)(out.size() / 4), (py::ssize_t)4});
+            std::memcpy(a.mutable_data(), out.data(), out.size() * sizeof(float));
+            return a;
+        }, py::arg("targetChannel"), py::arg("camera"), py::arg("scene"), py::arg("lights"))
         .def("DynamicBatchAdd", [](Model& s, int part, py::args models) { std::vector<std::shared_ptr<Model>> v; for (auto k : models) v.push_back(k.cast<std::shared_ptr<Model>>()); s.DynamicBatchAdd(part, v); })
         .def("DynamicBatcher", &Model::DynamicBatcher);
     m.def("NewModel", [](const std::string& n, std::shared_ptr<Mesh> mesh) { return std::make_shared<Model>(n, mesh); });
@@ -302,6 +326,7 @@ PYBIND11_MODULE(_host, m) {
         .def(py::init<int>(), py::arg("device") = 0)
         .def_readonly("DeviceID", &GeometryDevice::deviceId)
         .def("Stream", [](GeometryDevice& d) { return (uintptr_t)t3d_debug_stream(d.ctx); })
+        .def("SetFusedSort", [](GeometryDevice& d, int mode) { if (t3d_debug_set_fused_sort(d.ctx, mode) != T3D_OK) throw std::invalid_argument("SetFusedSort: 0, 1 or 2"); })
         .def("Handle", [](GeometryDevice& d) { return (uintptr_t)d.ctx; })      // the t3d_ctx*, for ctypes callers of the C ABI
         .def("SharedAlloc", [](GeometryDevice& d, uint64_t bytes) {
             void* p = nullptr; t3d_shared_handle h;

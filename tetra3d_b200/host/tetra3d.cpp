@@ -788,6 +788,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     }
     device->frameSerial++;
     check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
+    // anything that throws before the frame is executed (an unsupported draw, a failed upload) must not leave the frame open
+    struct FrameGuard { t3d_ctx* c; bool armed; ~FrameGuard() { if (armed) t3d_frame_abort(c); } } frameGuard{ctx, true};
     if (!scene.autosubdivisionLevels.empty())      // camera.go:1547-1553
         check(ctx, t3d_frame_set_autosubdivision(ctx, scene.autosubdivisionLevels.data(), (uint32_t)(scene.autosubdivisionLevels.size() / 2)), "t3d_frame_set_autosubdivision");
 
@@ -974,6 +976,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     }
     lap("t3d_submit_draws");
     check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
+    frameGuard.armed = false;
     lap("t3d_frame_execute");
     if (downloadResults) check(ctx, t3d_frame_results(ctx, &output, &timings), "t3d_frame_results");
     else check(ctx, t3d_frame_results_device(ctx, &output, &timings), "t3d_frame_results_device");
@@ -1012,6 +1015,117 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         }
     }
     lap("render/flush records");
+}
+
+// Triangle.Normal and Triangle.MaxSpan of every triangle (mesh.go:2018-2037, 2171-2179), load-time products of the reference.
+void TriangleNormalsAndSpans(const Mesh& mesh, std::vector<float>& normals3, std::vector<float>& spans) {
+    const int nt = mesh.TriangleTotal();
+    normals3.resize((size_t)3 * nt); spans.resize((size_t)nt);
+    auto P = [&](uint32_t v) { return v3(mesh.VertexPositions[3 * v], mesh.VertexPositions[3 * v + 1], mesh.VertexPositions[3 * v + 2]); };
+    for (int t = 0; t < nt; t++) {
+        const uint32_t a = mesh.TriangleIndices[3 * t], b = mesh.TriangleIndices[3 * t + 1], c = mesh.TriangleIndices[3 * t + 2];
+        Vector3 n = v3_unit(v3_cross(v3_sub(P(b), P(a)), v3_sub(P(c), P(b))));        // calculateNormal
+        const float eps = 1e-4f;
+        if (!(std::fabs(n.X) > eps || std::fabs(n.Y) > eps || std::fabs(n.Z) > eps))  // IsZero: fall back to the first vertex normal
+            n = v3(mesh.VertexNormals[3 * a], mesh.VertexNormals[3 * a + 1], mesh.VertexNormals[3 * a + 2]);
+        normals3[3 * t] = n.X; normals3[3 * t + 1] = n.Y; normals3[3 * t + 2] = n.Z;
+        spans[t] = std::max(std::max(v3_magnitude(v3_sub(P(a), P(b))), v3_magnitude(v3_sub(P(b), P(c)))), v3_magnitude(v3_sub(P(c), P(a))));
+    }
+}
+
+std::vector<float> Model::BakeAO(GeometryDevice& dev, int targetChannel, float occlusionAngle, const Color4& oc,
+                                 const std::vector<int>& targetParts, const std::vector<int>& targetVertices) {
+    std::vector<float> out;
+    if (!mesh || targetChannel < 0) return out;                            // model.go:1042-1044
+    const int n = mesh->VertexCount();
+    if (mesh->VertexActiveColorChannel == targetChannel && (int)mesh->VertexColors.size() == 4 * n) out = mesh->VertexColors;
+    else out.assign((size_t)4 * n, 1.0f);                                  // ensureEnoughVertexColorChannels
+    std::vector<float> normals, spans;
+    TriangleNormalsAndSpans(*mesh, normals, spans);
+    std::vector<uint8_t> parts, verts;
+    if (!targetParts.empty()) { parts.assign(mesh->MeshParts.size(), 0); for (int p : targetParts) if (p >= 0 && p < (int)parts.size()) parts[p] = 1; }
+    if (!targetVertices.empty()) { verts.assign((size_t)n, 0); for (int v : targetVertices) if (v >= 0 && v < n) verts[v] = 1; }
+    dev.ensureMesh(*mesh);
+    const float c4[4] = {oc.R, oc.G, oc.B, oc.A};
+    check(dev.ctx, t3d_bake_ao(dev.ctx, mesh->id, normals.data(), spans.data(), parts.empty() ? nullptr : parts.data(),
+                               verts.empty() ? nullptr : verts.data(), occlusionAngle, c4, out.data()), "t3d_bake_ao");
+    if (mesh->VertexActiveColorChannel == targetChannel) { mesh->VertexColors = out; mesh->MarkDirty(); }
+    return out;
+}
+
+// ---- Model.BakeLighting (model.go:1203-1268) -------------------------------------------------------------------------
+std::vector<float> Model::BakeLighting(int targetChannel, Camera& camera, Scene& scene, const std::vector<std::shared_ptr<ILight>>& lights) {
+    std::vector<float> out;
+    if (!mesh || targetChannel < 0) return out;                            // model.go:1205-1207
+    if (!camera.device) throw T3DError(T3D_E_STATE, "Camera has no GeometryDevice: the geometry stage has no CPU path");
+    GeometryDevice& dev = *camera.device;
+    t3d_ctx* ctx = dev.ctx;
+    const int n = mesh->VertexCount();
+    // ensureEnoughVertexColorChannels (mesh.go:543-558): a channel that did not exist starts at 1, 1, 1, 1
+    if (mesh->VertexActiveColorChannel == targetChannel && (int)mesh->VertexColors.size() == 4 * n) out = mesh->VertexColors;
+    else out.assign((size_t)4 * n, 1.0f);
+
+    // lightsInput = lights + World.AmbientLight (model.go:1212-1218); the invisible ones take no part (model.go:1227, 1253)
+    std::vector<ILight*> ls;
+    for (auto& l : lights) if (l && l->IsVisible()) ls.push_back(l.get());
+    if (scene.world && scene.world->ambientLight->IsVisible()) ls.push_back(scene.world->ambientLight.get());
+
+    camera.Clear();     // the camera axes ProcessVertices reads (camera.go:1085-1088)
+    t3d_camera cam; std::memset(&cam, 0, sizeof cam);
+    const Matrix4 view = camera.ViewMatrix();
+    m4_store(m4_mult(view, camera.Projection()), cam.vp); m4_store(view, cam.view);
+    const Vector3 cp = camera.WorldPosition();
+    cam.position[0] = cp.X; cam.position[1] = cp.Y; cam.position[2] = cp.Z;
+    cam.up[0] = camera.cameraUp.X; cam.up[1] = camera.cameraUp.Y; cam.up[2] = camera.cameraUp.Z;
+    cam.near_plane = camera.near_; cam.far_plane = camera.far_; cam.width = camera.width; cam.height = camera.height;
+    cam.depth_margin = camera.DepthMargin; cam.vertex_snapping = camera.VertexSnapping;
+    cam.flags = (camera.perspective ? T3D_CAM_PERSPECTIVE : 0) | (camera.RenderDepth ? T3D_CAM_RENDER_DEPTH : 0);
+    t3d_world tw; std::memset(&tw, 0, sizeof tw);
+    tw.present = scene.world ? 1 : 0;
+    dev.frameSerial++;
+    check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
+    struct FrameGuard { t3d_ctx* c; ~FrameGuard() { t3d_frame_abort(c); } } frameGuard{ctx};       // (a no-op once the frame has been executed)
+    check(ctx, t3d_frame_set_bake_lighting(ctx, 1), "t3d_frame_set_bake_lighting");
+    std::vector<t3d_light> recs;
+    for (ILight* l : ls) recs.push_back(toLight(dev, l));
+    uint32_t list = 0;
+    check(ctx, t3d_submit_lights(ctx, recs.data(), (uint32_t)recs.size(), &list), "t3d_submit_lights");
+    dev.ensureMesh(*mesh);
+    uint32_t boneOff = 0;
+    if (skinned) check(ctx, t3d_submit_bones(ctx, boneInfluences.data(), (uint32_t)(boneInfluences.size() / 16), &boneOff), "t3d_submit_bones");
+    std::vector<t3d_draw> draws; std::vector<int> drawPart;
+    for (size_t pi = 0; pi < mesh->MeshParts.size(); pi++) {
+        MeshPart& mp = *mesh->MeshParts[pi];
+        Material* mat = mp.material.get();
+        if (mat && mat->Shadeless) {                                       // model.go:1241-1248
+            for (int v = mp.VertexIndexStart; v < mp.VertexIndexEnd; v++) { out[4 * v] = 1; out[4 * v + 1] = 1; out[4 * v + 2] = 1; }
+            continue;
+        }
+        t3d_draw d; std::memset(&d, 0, sizeof d);
+        d.mesh_id = mesh->id; d.part = (uint32_t)pi;
+        uint32_t f = T3D_DRAW_LIT;
+        if (mat) { f |= T3D_DRAW_HAS_MATERIAL; d.lighting_mode = (uint8_t)mat->LightingMode; d.light_volume_mode = (uint8_t)mat->LightVolumeShadingMode; d.sort_mode = (uint8_t)mat->TriangleSortMode; }
+        if (skinned) { f |= T3D_DRAW_SKINNED; d.bone_offset = boneOff; d.bone_count = (uint32_t)(boneInfluences.size() / 16); }
+        d.flags = f;
+        m4_store(Transform(), d.transform);
+        m4_store(WorldRotation(), d.world_rotation);
+        d.color[0] = d.color[1] = d.color[2] = d.color[3] = 1.0f;
+        d.light_list = list;
+        draws.push_back(d); drawPart.push_back((int)pi);
+    }
+    if (!draws.empty()) check(ctx, t3d_submit_draws(ctx, draws.data(), (uint32_t)draws.size()), "t3d_submit_draws");
+    check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
+    std::vector<float> l4;
+    for (size_t i = 0; i < draws.size(); i++) {
+        MeshPart& mp = *mesh->MeshParts[drawPart[i]];
+        const int v0 = mp.VertexIndexStart, v1 = mp.VertexIndexEnd;       // ForEachVertexIndex (mesh.go:2261-2267)
+        if (v1 <= v0) continue;
+        l4.resize((size_t)4 * (v1 - v0));
+        check(ctx, t3d_frame_read_vertex_lights(ctx, (uint32_t)i, (uint32_t)v0, (uint32_t)v1, l4.data()), "t3d_frame_read_vertex_lights");
+        for (int v = v0; v < v1; v++) { out[4 * v] = l4[4 * (v - v0)]; out[4 * v + 1] = l4[4 * (v - v0) + 1]; out[4 * v + 2] = l4[4 * (v - v0) + 2]; }
+    }
+    if (mesh->VertexActiveColorChannel == targetChannel) { mesh->VertexColors = out; mesh->MarkDirty(); }
+    return out;
 }
 
 }  // namespace tetra3d

@@ -272,6 +272,14 @@ struct Model : Node {
     bool DynamicBatcher() const { return !DynamicBatchModels.empty(); }
     void DynamicBatchAdd(int meshPartIndex, const std::vector<std::shared_ptr<Model>>& models);   // model.go:217
     void SetBoneInfluences(const std::vector<float>& m) { boneInfluences = m; skinned = !m.empty(); }
+    // model.go:1203-1268 on the device (t3d_frame_set_bake_lighting): the baked VertexColors[targetChannel] of the model's mesh,
+    // 4 floats per vertex; also stored in mesh->VertexColors when targetChannel is the mesh's active channel.  `scene` stands in
+    // for model.Scene() (its World.AmbientLight joins the lights).
+    // model.go:1040-1124 on the device (t3d_bake_ao): the same-model pass.  targetParts: MeshPart indices (empty: all);
+    // targetVertices: vertex indices (empty: all).  Returns VertexColors[targetChannel] after the bake, 4 floats per vertex.
+    std::vector<float> BakeAO(struct GeometryDevice& device, int targetChannel, float occlusionAngle, const Color4& occlusionColor,
+                              const std::vector<int>& targetParts, const std::vector<int>& targetVertices);
+    std::vector<float> BakeLighting(int targetChannel, struct Camera& camera, struct Scene& scene, const std::vector<std::shared_ptr<struct ILight>>& lights);
     // Bones posed on the device: the skin's skeleton, the node its root bones are children of (Model.SkinRoot, model.go:33)
     // and the player animating that armature (nullptr: rest pose).
     std::shared_ptr<Skeleton> skeleton;
