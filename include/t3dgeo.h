@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 4      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points; 4: t3d_submit_instances */
+#define T3D_ABI_VERSION 5      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points; 4: t3d_submit_instances; 5: t3d_camera carries the frustum terms, t3d_submit_instances the culling bounds */
 
 enum {
     T3D_OK            =  0,
@@ -138,6 +138,12 @@ typedef struct t3d_camera {
     float    depth_margin;    /* Camera.DepthMargin (camera.go:1339)                               */
     float    vertex_snapping; /* Camera.VertexSnapping (model.go:716, 807-812)                     */
     uint32_t flags;           /* T3D_CAM_*                                                          */
+    /* What Camera.SphereInFrustum reads (camera.go:933-983), verbatim from the Camera's cached fields; only needed when
+     * t3d_submit_instances is given culling bounds (zero otherwise).                                    */
+    float    forward[3];      /* camera.cameraForward (camera.go:1086)                              */
+    float    right[3];        /* camera.cameraRight (camera.go:1087); `up` above is cameraUp        */
+    float    sphere_factor_y, sphere_factor_x, sphere_factor_tang;   /* camera.go:659-665           */
+    float    ortho_scale;     /* camera.orthoScale (camera.go:967)                                  */
 } t3d_camera;
 
 /* scene.World fields the emit loop reads (camera.go:1784-1812). */
@@ -354,8 +360,12 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
  * Material.Color, or ones without a material, in proto->color) and T3D_DRAW_CONTINUE_FLUSH set on every copy but the first
  * (which keeps proto's flag).  proto->transform is ignored; proto->world_rotation is every instance's (they share rotation and
  * parent).  rotation16: the Node.rotation the instances share, NULL = identity; parent16: parent.Transform(), NULL = the
- * Models have no parent (node.go:581).  Both must be affine (column 3 = 0,0,0,1), as every Node.Transform() of a scene graph is. */
-int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16,
+ * Models have no parent (node.go:581).  Both must be affine (column 3 = 0,0,0,1), as every Node.Transform() of a scene graph is.
+ * frustum_bounds9: NULL, or mesh.Dimensions as {Center x y z, Min x y z, Max x y z} for Models with FrustumCulling: the device then
+ * also evaluates Model.onTransformUpdate's culling sphere (model.go:142-182) and Camera.SphereInFrustum (camera.go:933-983,
+ * the test of camera.go:2088-2093 / 1361) per instance, and an instance outside the frustum is not rendered: it emits nothing
+ * and its t3d_draw_result reports total_tris = 0 (the reference never reaches render() for it, camera.go:1532). */
+int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16, const float* frustum_bounds9,
                          const t3d_instance* instances, uint32_t n);
 /* Replaces: Model.ProcessVertices + the lighting and emit loops for all submitted draws.
  * Asynchronous: returns after enqueueing on the context's stream. */

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "libt3dgeo.so does not export %s" % n
-    assert lib.t3d_abi_version() == 4
+    assert lib.t3d_abi_version() == 5
 
 
 def test_struct_sizes_match_header():

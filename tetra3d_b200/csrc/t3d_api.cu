@@ -140,6 +140,7 @@ struct t3d_ctx {
     // until second-wave blocks find a slot, and the three-kernel path is as fast or faster (1 M triangles: 41.4 vs 38.5 us staged,
     // 102.1 vs 103.4 us chained).  fuseSort: 0 never, 1 when the tiles fit one wave (default), 2 always (T3D_FUSE_SORT, tests).
     int fuseSort = 1; int smCount = 148; bool frameFused = false;
+    bool deliverIndexed = true;        // sharded delivery may take the indexed form (T3D_DELIVER_INDEXED=0: always the compact form; A/B measurements)
     PinVec<uint4> hVClass[3];       // vertex tiles by class (0 generic, 1 static fast, 2 skinned fast): {tile, first draw, first draw of the next tile, end of the first draw's vertices}
     PinVec<TriTile> hTiles;
     PinVec<t3d_light> hLights;
@@ -148,7 +149,7 @@ struct t3d_ctx {
     std::vector<uint32_t> drawTotalTris;
     std::vector<uint8_t> drawContinue;
     // t3d_submit_instances: what the instances of one call share.  rot / parent: where the two matrices sit in hRot
-    struct TrsGroup { uint32_t rot, parent; Mat4 rotation, parentT; bool hasParent; };
+    struct TrsGroup { uint32_t rot, parent; Mat4 rotation, parentT; bool hasParent, hasBounds; float bounds[9]; };
     std::vector<TrsGroup> trsGroups;
     uint32_t nTrsDraws = 0; bool trsUniform = true;       // draws submitted as instances; all of them with x == y == z scale
     uint32_t vAcc = 0, tAcc = 0, luAcc = 0, nHistRows = 0;
@@ -183,12 +184,13 @@ struct t3d_ctx {
         uint64_t cap = 0;                       // vertices per rank region
         uint8_t *color = nullptr, *depth = nullptr, *box = nullptr;     // the issuing rank's allocations (mapped over NVLink on the others)
         size_t statsOff = 0, mailOff = 0, boxBytes = 0;
-        uint8_t* inbox(uint32_t r) const { return box + (size_t)r * cap * 40; }
+        // per rank: 32-byte records | depth values | Custom0 values | arena slot per emitted corner (indexed frames), `cap` entries each
+        uint8_t* inbox(uint32_t r) const { return box + (size_t)r * cap * 44; }
         uint8_t* stats(uint32_t r) const { return box + statsOff + (size_t)r * drawCap * sizeof(DrawStat); }
         uint32_t* mail(uint32_t r) const { return reinterpret_cast<uint32_t*>(box + mailOff) + (size_t)r * GATHER_MAIL_WORDS; }
         uint32_t* err() const { return reinterpret_cast<uint32_t*>(box + mailOff) + (size_t)world * GATHER_MAIL_WORDS; }
         void layout() {
-            statsOff = ((size_t)world * cap * 40 + 255) & ~(size_t)255;
+            statsOff = ((size_t)world * cap * 44 + 255) & ~(size_t)255;
             mailOff = (statsOff + (size_t)world * drawCap * sizeof(DrawStat) + 255) & ~(size_t)255;
             boxBytes = mailOff + ((size_t)world + 1) * GATHER_MAIL_WORDS * 4;
         }
@@ -284,6 +286,7 @@ int t3d_create(t3d_ctx** out, int device_id) {
     if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if (const char* fs = getenv("T3D_FUSE_SORT")) ctx->fuseSort = atoi(fs);
+    if (const char* di = getenv("T3D_DELIVER_INDEXED")) ctx->deliverIndexed = di[0] != '0';
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device_id);
     if (ctx->smCount <= 0) ctx->smCount = 148;
     if (const char* th = getenv("T3D_DMA_THRESHOLD")) ctx->dmaThreshold = (size_t)strtoull(th, nullptr, 10);      // diagnostics: bytes; 0 = always copy, huge = never
@@ -539,6 +542,9 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     fc.camSpread = cam->far_plane - cam->near_plane + (fc.depthMargin * 2);        // camera.go:1341
     fc.snapping = cam->vertex_snapping;
     fc.camFlags = cam->flags;
+    memcpy(fc.camForward, cam->forward, 12); memcpy(fc.camRight, cam->right, 12);
+    fc.sphereFactorY = cam->sphere_factor_y; fc.sphereFactorX = cam->sphere_factor_x; fc.sphereFactorTang = cam->sphere_factor_tang;
+    fc.orthoScale = cam->ortho_scale;
     if (world) {
         fc.worldPresent = world->present; fc.fogOn = world->fog_on; fc.fogMode = world->fog_mode;
         memcpy(fc.fogColor, world->fog_color, 12);
@@ -835,7 +841,8 @@ int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n) {
     return submit_range(ctx, draws, n, nullptr, 0);
 }
 
-int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16, const t3d_instance* instances, uint32_t n) {
+int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotation16, const float* parent16, const float* frustum_bounds9,
+                         const t3d_instance* instances, uint32_t n) {
     if (!ctx || !proto || (n && !instances)) return fail(ctx, T3D_E_INVALID, "t3d_submit_instances: NULL argument");
     if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_instances: not between frame_begin and frame_execute");
     if (proto->flags & T3D_DRAW_SKINNED) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_submit_instances: skinned models carry their own bones: submit them with t3d_submit_draws");
@@ -846,11 +853,16 @@ int t3d_submit_instances(t3d_ctx* ctx, const t3d_draw* proto, const float* rotat
     G.rotation = rotation16 ? m4_load(rotation16) : m4_identity();
     G.hasParent = parent16 != nullptr;
     G.parentT = parent16 ? m4_load(parent16) : m4_identity();
-    CU(ctx->hRot.reserve(ctx->hRot.n + 32));
+    CU(ctx->hRot.reserve(ctx->hRot.n + 48));
     G.rot = (uint32_t)(ctx->hRot.n / 16);
     m4_store(G.rotation, ctx->hRot.p + ctx->hRot.n); ctx->hRot.n += 16;
     G.parent = NO_ROTATION;
     if (G.hasParent) { G.parent = (uint32_t)(ctx->hRot.n / 16); m4_store(G.parentT, ctx->hRot.p + ctx->hRot.n); ctx->hRot.n += 16; }
+    G.hasBounds = frustum_bounds9 != nullptr;
+    if (G.hasBounds) {          // the culling bounds ride behind the group's matrices (k_prep_draws finds them there)
+        memcpy(G.bounds, frustum_bounds9, 36);
+        memset(ctx->hRot.p + ctx->hRot.n, 0, 64); memcpy(ctx->hRot.p + ctx->hRot.n, frustum_bounds9, 36); ctx->hRot.n += 16;
+    }
     ctx->trsGroups.push_back(G);
     return submit_range(ctx, proto, n, instances, (uint32_t)ctx->trsGroups.size() - 1);
 }
@@ -939,7 +951,7 @@ static int submit_range(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n, const t
             memcpy(S.transform, R.transform, 64); memcpy(S.color, R.color, 16);
             if (inst) {         // position and scale instead of a matrix: expanded on the device, or at execute time when the frame is not shipped as runs
                 memcpy(S.transform, inst[i].position, 12); memcpy(S.transform + 3, inst[i].scale, 12);
-                S.pad[0] = group + 1;
+                S.pad[0] = (group + 1) | (ctx->trsGroups[group].hasBounds ? 0x80000000u : 0u);
                 ctx->nTrsDraws++;
                 if (!(inst[i].scale[0] == inst[i].scale[1] && inst[i].scale[1] == inst[i].scale[2])) ctx->trsUniform = false;
             } else if (ctx->transformsAffine) {       // Node.Transform() of an ordinary scene graph: column 3 is exactly (0, 0, 0, 1)
@@ -1053,17 +1065,24 @@ static int gather_enqueue(t3d_ctx* ctx, uint32_t nDraws, uint32_t nChunks) {
     t3d_ctx::Gather& G = ctx->gather;
     cudaStream_t s = ctx->stream;
     if (G.rank != G.dst) {
-        launch_gather_post(s, G.mail(G.rank), ctx->dCount.as<uint32_t>(), nChunks, G.serial, ctx->dStats.p, G.stats(G.rank), nDraws);
+        launch_gather_post(s, G.mail(G.rank), ctx->dCount.as<uint32_t>(), nChunks, G.serial, ctx->dStats.p, G.stats(G.rank), nDraws,
+                           (nDraws && ctx->deliverIndexed && ctx->vAcc <= G.cap) ? ctx->vAcc : 0u);
         ctx->launches += 1;
     } else {
         const bool renderDepth = ctx->fc.camFlags & T3D_CAM_RENDER_DEPTH, pcuv = ctx->fc.camFlags & T3D_CAM_PERSP_CORRECT_UV;
+        std::vector<const void*> rec; std::vector<const float*> dsc, cus; std::vector<const uint32_t*> slot;
+        std::vector<t3d_vertex*> col, dep; std::vector<uint32_t*> mail;
         for (uint32_t r = 0; r < G.world; r++) {
             if (r == G.dst) continue;
             const uint8_t* in = G.inbox(r);
-            launch_gather_expand(s, in, reinterpret_cast<const float*>(in + G.cap * 32), reinterpret_cast<const float*>(in + G.cap * 36),
-                                 reinterpret_cast<t3d_vertex*>(G.color) + (size_t)r * G.cap, reinterpret_cast<t3d_vertex*>(G.depth) + (size_t)r * G.cap,
-                                 G.mail(r), G.serial, renderDepth, pcuv, G.err());
-            ctx->launches += 1;
+            rec.push_back(in); dsc.push_back(reinterpret_cast<const float*>(in + G.cap * 32)); cus.push_back(reinterpret_cast<const float*>(in + G.cap * 36));
+            slot.push_back(reinterpret_cast<const uint32_t*>(in + G.cap * 40));
+            col.push_back(reinterpret_cast<t3d_vertex*>(G.color) + (size_t)r * G.cap); dep.push_back(reinterpret_cast<t3d_vertex*>(G.depth) + (size_t)r * G.cap);
+            mail.push_back(G.mail(r));
+        }
+        if (!rec.empty()) {
+            launch_gather_expand(s, (uint32_t)rec.size(), rec.data(), dsc.data(), cus.data(), slot.data(), col.data(), dep.data(), mail.data(), G.serial, renderDepth, pcuv, G.err());
+            ctx->launches += ((int)rec.size() + 14) / 15;
         }
     }
     CU(cudaGetLastError());
@@ -1203,7 +1222,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
                     U.first = d; U.count = 1; U.tmpl = S[d].tmpl; U.vbase = S[d].vbase; U.tbase = S[d].tbase; U.boneOffset = S[d].boneOffset;
                     U.lightU = S[d].lightU; U.rot = S[d].rot;
                     U.pad[0] = S[d].pad[0];         // t3d_submit_instances group + 1: k_prep_draws builds the run's transforms from position and scale
-                    if (U.pad[0]) { U.pad[1] = ctx->trsGroups[U.pad[0] - 1].rot; U.pad[2] = ctx->trsGroups[U.pad[0] - 1].parent; }
+                    if (U.pad[0]) { const t3d_ctx::TrsGroup& G = ctx->trsGroups[(U.pad[0] & 0x7FFFFFFFu) - 1]; U.pad[1] = G.rot; U.pad[2] = G.parent; }
                     ctx->hRuns.push_back(U);
                 }
             }
@@ -1228,10 +1247,20 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             for (uint32_t d = 0; d < nDraws; d++) {
                 DrawSlim& S = ctx->hSlim.p[d];
                 if (!S.pad[0]) continue;
-                const t3d_ctx::TrsGroup& G = ctx->trsGroups[S.pad[0] - 1];
+                const t3d_ctx::TrsGroup& G = ctx->trsGroups[(S.pad[0] & 0x7FFFFFFFu) - 1];
                 float ps[6]; memcpy(ps, S.transform, 24);
-                m4_store(instance_transform(ps, ps + 3, G.rotation, G.hasParent ? &G.parentT : nullptr), S.transform);
+                const Mat4 M = instance_transform(ps, ps + 3, G.rotation, G.hasParent ? &G.parentT : nullptr);
+                m4_store(M, S.transform);
                 S.pad[0] = 0;
+                if (G.hasBounds) {      // the culling sphere test, as k_prep_draws runs it for frames shipped as runs; 1 = outside
+                    const FrameConst& fc = ctx->fc;
+                    FrustumTerms F;
+                    F.camPos = v3(fc.camPos[0], fc.camPos[1], fc.camPos[2]); F.forward = v3(fc.camForward[0], fc.camForward[1], fc.camForward[2]);
+                    F.right = v3(fc.camRight[0], fc.camRight[1], fc.camRight[2]); F.up = v3(fc.camUp[0], fc.camUp[1], fc.camUp[2]);
+                    F.nearP = fc.nearP; F.farP = fc.farP; F.sphereFactorY = fc.sphereFactorY; F.sphereFactorX = fc.sphereFactorX; F.sphereFactorTang = fc.sphereFactorTang;
+                    F.aspect = fc.camW / fc.camH; F.orthoScale = fc.orthoScale; F.perspective = (fc.camFlags & T3D_CAM_PERSPECTIVE) != 0;
+                    if (!m4_instance_in_frustum(M, G.bounds, F)) S.pad[0] = 1;
+                }
             }
             ctx->nTrsDraws = 0;
         }
@@ -1273,7 +1302,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             uint8_t* o = ctx->hFrame.p + slimBytes * (size_t)d - (runMode ? 32 : 0);      // run mode: no header, payload only
             if (!runMode) memcpy(o, &S, 32);                            // header
             float* t = reinterpret_cast<float*>(o + 32);
-            if (S.pad[0]) { memcpy(t, S.transform, 24); memset(t + 6, 0, 24); }        // an instance: {position, scale x | scale y, z, - , - | - }
+            if (runMode && S.pad[0]) { memcpy(t, S.transform, 24); memset(t + 6, 0, 24); }        // an instance: {position, scale x | scale y, z, - , - | - }
             else for (int r = 0; r < 4; r++) { t[3 * r] = S.transform[4 * r]; t[3 * r + 1] = S.transform[4 * r + 1]; t[3 * r + 2] = S.transform[4 * r + 2]; }
             memcpy(o + 32 + 48, S.color, 16);
         }
@@ -1455,6 +1484,8 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     t3d_ctx::Gather& G = ctx->gather;
     const bool shard = G.active && G.rank != G.dst;        // this rank's lists live on the issuing rank: compact emit into its inbox there
     if (G.active && normals) return fail(ctx, T3D_E_UNSUPPORTED, "t3d_frame_execute: sharded delivery with RenderNormals");
+    const uint32_t nScanChunks = (nTiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const bool offerIndexed = shard && ctx->deliverIndexed && totalV <= G.cap;
     if (shard) {
         CU(ctx->dGatherErr.ensure(64));
         launch_gather_wait_ack(s, G.mail(G.rank) + 16, G.serial - 1, ctx->dGatherErr.as<uint32_t>());      // the previous frame has been expanded
@@ -1462,13 +1493,22 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         launch_emit(s, false, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                     ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                     reinterpret_cast<float4*>(in), reinterpret_cast<float4*>(in + G.cap * 32), nullptr, ctx->dTriIds.as<uint32_t>(), true,
-                    reinterpret_cast<float*>(in + G.cap * 36));
+                    reinterpret_cast<float*>(in + G.cap * 36), offerIndexed ? totalV : 0u, nScanChunks);
+        // the indexed form (one record per arena vertex + a slot per emitted corner); each of the three kernels decides on the
+        // device, from the survivor total, which form this frame takes, and the other form's kernels return at once
+        if (offerIndexed) {
+            launch_emit_indexed(s, ctx->pDraws, ctx->pVbase, nDraws, totalV, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(),
+                                ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>(), nScanChunks, ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
+                                ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), reinterpret_cast<float4*>(in), reinterpret_cast<float*>(in + G.cap * 32),
+                                reinterpret_cast<float*>(in + G.cap * 36), reinterpret_cast<uint32_t*>(in + G.cap * 40), ctx->dTriIds.as<uint32_t>());
+            ctx->launches += 2;
+        }
         ctx->launches += 1;
     } else {
         launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                     ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                     reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
-                    normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), false, nullptr);
+                    normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), false, nullptr, 0u, 0u);
     }
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[9], s));
@@ -1521,7 +1561,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
             t3d_draw_result& r = ctx->hResults.p[i];
             r.first_vertex = 3 * acc;
             r.vertex_count = 3 * st.survivors;
-            r.total_tris = ctx->drawTotalTris[i];
+            r.total_tris = st.minBits == DRAW_CULLED_MARK ? 0u : ctx->drawTotalTris[i];      // an instance outside the frustum was never render()ed
             if (st.survivors) { memcpy(&r.min_depth, &st.minBits, 4); memcpy(&r.max_depth, &st.maxBits, 4); }
             else { r.min_depth = FLT_MAX; r.max_depth = -FLT_MAX; }
             acc += st.survivors;

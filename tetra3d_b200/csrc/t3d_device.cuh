@@ -39,6 +39,9 @@ struct FrameConst {
     // Model.BakeLighting frames (t3d_frame_set_bake_lighting): for every arena vertex, how many triangle corners of its draw
     // refer to it -- the reference's bake adds a light's contribution once per corner (model.go:1246-1262) -- else nullptr
     const uint32_t* bakeValence;
+    // Camera.SphereInFrustum's terms (camera.go:933-983), for instances submitted with culling bounds (t3d_submit_instances)
+    float camForward[3], camRight[3];
+    float sphereFactorY, sphereFactorX, sphereFactorTang, orthoScale;
 };
 
 // Resolved light as seen by one draw: light.beginRender/beginModel products (light.go:110-112,
@@ -63,6 +66,10 @@ struct LightU {
     uint32_t pad;
 };
 static const uint32_t LIGHT_SKIP = 0xFFu;
+// DrawRec.flags, set by k_prep_draws: an instance whose culling sphere is outside the frustum (t3d_submit_instances with bounds).
+// Its arena ranges stay (the host laid them out) but nothing of it survives the cull; DrawStat.minBits = DRAW_CULLED_MARK tells the host.
+static const uint32_t T3D_DRAW_FRUSTUM_CULLED = 1u << 31;
+static const uint32_t DRAW_CULLED_MARK = 0xFFFFFFFFu;
 
 // LightVolume on the device.
 struct VolumeU {

@@ -224,6 +224,17 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
                 }
 #pragma unroll
                 for (int r = 0; r < 4; r++) { f[3 * r] = M.m[r][0]; f[3 * r + 1] = M.m[r][1]; f[3 * r + 2] = M.m[r][2]; }
+                if (U.pad[0] & 0x80000000u) {       // culling bounds follow the run's matrices: Model.onTransformUpdate + Camera.SphereInFrustum
+                    const float4* bp = reinterpret_cast<const float4*>(pf.hostRot) + (size_t)((U.pad[2] != NO_ROTATION ? U.pad[2] : U.pad[1]) + 1) * 4;
+                    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+                    const float b9[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x};
+                    FrustumTerms F;
+                    F.camPos = v3(fc.camPos[0], fc.camPos[1], fc.camPos[2]); F.forward = v3(fc.camForward[0], fc.camForward[1], fc.camForward[2]);
+                    F.right = v3(fc.camRight[0], fc.camRight[1], fc.camRight[2]); F.up = v3(fc.camUp[0], fc.camUp[1], fc.camUp[2]);
+                    F.nearP = fc.nearP; F.farP = fc.farP; F.sphereFactorY = fc.sphereFactorY; F.sphereFactorX = fc.sphereFactorX; F.sphereFactorTang = fc.sphereFactorTang;
+                    F.aspect = fc.camW / fc.camH; F.orthoScale = fc.orthoScale; F.perspective = (fc.camFlags & T3D_CAM_PERSPECTIVE) != 0;
+                    if (!m4_instance_in_frustum(M, b9, F)) h[6] = 1u;        // picked up below: T3D_DRAW_FRUSTUM_CULLED
+                }
             }
         }
         __syncthreads();            // the runs are consumed: the rotation window may overwrite them
@@ -320,6 +331,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         const DrawSlim& S = slimOf(k);
         DrawRec& R = sR[k];
         R.vbase = S.vbase; R.tbase = S.tbase; R.lightU = S.lightU;
+        if (S.pad[0] == 1u) R.flags |= T3D_DRAW_FRUSTUM_CULLED;      // an instance outside the frustum (decided above, or by the host for frames not shipped as runs)
         // device-evaluated poses (t3d_submit_poses) sit behind the submitted matrices in the bone arena
         R.boneOffset = (S.boneOffset & POSE_TAG) ? pf.nBones + (S.boneOffset & ~POSE_TAG) : S.boneOffset;
         pf.devVbase[d0 + k] = S.vbase; pf.devTbase[d0 + k] = S.tbase;
@@ -347,7 +359,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
 #pragma unroll
             for (int j = 0; j < 3; j++) o[i * 3 + j] = r.m[i][j];       // rows 0-3, columns 0-2: all m4_multvec reads
         o[12] = invPS.X; o[13] = invPS.Y; o[14] = invPS.Z;
-        DrawStat st; st.minBits = 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
+        DrawStat st; st.minBits = (flags & T3D_DRAW_FRUSTUM_CULLED) ? DRAW_CULLED_MARK : 0x7F7FFFFFu; st.maxBits = 0u; st.survivors = 0; st.done = 0;   // model.go:710-711
         stats[d0 + k] = st;
     } else if (role == 1) {
         const Mat4 vp = m4_load(fc.vp);
@@ -795,6 +807,7 @@ __device__ __forceinline__ void shade_vertex(const DrawRec& R, const uint32_t fl
                                              float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut, float4* __restrict__ wposOut,
                                              float* __restrict__ unbillOut, float4* __restrict__ tnrmOut) {
     constexpr bool FAST = MODE != K1_GENERIC;       // shape keys, snapping, unbillboarded depth, normal pass, volume lights compiled out
+    if (flags & T3D_DRAW_FRUSTUM_CULLED) return;    // an instance outside the frustum: nothing of it is read later
     const bool skinned = MODE == K1_SKINNED || (MODE == K1_GENERIC && (flags & T3D_DRAW_SKINNED));
     const bool lit = (flags & T3D_DRAW_LIT) != 0;
     const bool needN = lit || skinned;
@@ -1004,6 +1017,7 @@ template <> struct __align__(128) VStage<true> {
 // operation (positions exact, lighting through light_loop_fast's formulas).  `hasB`: slot tb exists (a draw's last tile is short).
 __device__ __forceinline__ void shade2_static(const VStage<false>& S, const VStageDesc& D, const uint32_t ta, const uint32_t tb, const bool hasB,
                                               float4* __restrict__ clipOut, float2* __restrict__ clipXY, float4* __restrict__ lightOut) {
+    if (D.flags & T3D_DRAW_FRUSTUM_CULLED) return;
     const bool lit = (D.flags & T3D_DRAW_LIT) != 0;
     const Vec3 Pa = v3(S.pos[0][ta], S.pos[1][ta], S.pos[2][ta]), Pb = v3(S.pos[0][tb], S.pos[1][tb], S.pos[2][tb]);
     {   // clip = [x y z 1] * mvp (model.go:795-798) and the cull's perspective divide (model.go:866-875), as in shade_vertex
@@ -1406,7 +1420,7 @@ k_cull_large(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tile
         const uint32_t i = r * TILE_THREADS + threadIdx.x;
         if (i < T.count) {
             const float4 c0 = __ldg(&clip[vb + ia[r]]), c1 = __ldg(&clip[vb + ib[r]]), c2 = __ldg(&clip[vb + ic[r]]);
-            bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+            bool keep = !(flags & T3D_DRAW_FRUSTUM_CULLED) && cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
             if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt0 + i);       // model.go:753-755
             float depth = 0.0f;
             if (keep) {                                                 // model.go:933-955
@@ -1527,7 +1541,7 @@ k_cull_sort(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles
             key[r] = KEY_CULLED;
             if (i < T.count) {
                 const float4 c0 = __ldg(&clip[vb + ia[r]]), c1 = __ldg(&clip[vb + ib[r]]), c2 = __ldg(&clip[vb + ic[r]]);
-                bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+                bool keep = !(flags & T3D_DRAW_FRUSTUM_CULLED) && cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
                 if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt0 + i);       // model.go:753-755
                 float depth = 0.0f;
                 if (keep) {                                                 // model.go:933-955
@@ -1751,7 +1765,7 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
             const uint32_t vb = R.vbase - R.a0;
             const uint32_t i0 = __ldg(R.idx + mt), i1 = __ldg(R.idx + ts + mt), i2 = __ldg(R.idx + 2 * (size_t)ts + mt);
             const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
-            keep = cull_keep(c0, c1, c2, (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING), fc.nearP, fc.farP);
+            keep = !(flags & T3D_DRAW_FRUSTUM_CULLED) && cull_keep(c0, c1, c2, (flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_BACKFACE_CULLING), fc.nearP, fc.farP);
             if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, mt);
             if (keep) {
                 float depth;
@@ -1856,7 +1870,7 @@ k_draw_medium(const DrawRec* __restrict__ draws, const TriTile* __restrict__ til
     for (uint32_t i = threadIdx.x; i < nt; i += TILE_THREADS) {
         const uint32_t i0 = __ldg(ip + i), i1 = __ldg(ip + ts + i), i2 = __ldg(ip + 2 * (size_t)ts + i);
         const float4 c0 = __ldg(&clip[vb + i0]), c1 = __ldg(&clip[vb + i1]), c2 = __ldg(&clip[vb + i2]);
-        bool keep = cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
+        bool keep = !(R.flags & T3D_DRAW_FRUSTUM_CULLED) && cull_keep(c0, c1, c2, backface, fc.nearP, fc.farP);
         if (SUBDIV && keep && R.subdiv) keep = subdiv_visible(&R, &fc, R.t0 + i);
         float depth = 0.0f;
         if (keep) {                                                     // model.go:933-955
@@ -1967,6 +1981,130 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One corner of the emit loop (camera.go:1646-1814): everything the colour / depth records of a vertex hold, from the draw's
+// record and the per-vertex arenas.  It depends on (draw, vertex) only -- which is what lets a shard ship it once per arena
+// vertex (k_vemit) instead of once per emitted corner.
+__device__ __forceinline__ void emit_record(const DrawRec& R, const FrameConst& fc, const uint32_t slot, const uint32_t vi, const bool persp, const bool pcuv,
+                                            const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
+                                            const float* __restrict__ unbill, float4& a, float4& col, float4& dcol, float& custom0) {
+    const float4 Tc = __ldg(&clip[slot]);
+    float w = Tc.w;                                             // camera.go:1655-1666
+    if (!persp) w = 1.0f;
+    const bool behind = w < 0;
+    if (behind) w = 0.001f;
+    // X/w and Y/w are k_vertex's unless the emit loop's w differs from the cull's (w < 0, orthographic);
+    // Y / -w == -(Y / w) exactly
+    float qx = Tc.x, qy = -Tc.y;
+    if (behind || !persp) {
+        const float2 xy = __ldg(&clipXY[slot]);
+        qx = xy.x / w; qy = xy.y / -w;
+    }
+    const float dx = qx * fc.camW + fc.halfW;                   // camera.go:1674-1675
+    const float dy = qy * fc.camH + fc.halfH;
+
+    const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
+    float uvU, uvV; custom0 = 0.0f;
+    if (pcuv) {                                                 // camera.go:1689-1705
+        uvU = (uv.x / w) * R.srcW;
+        uvV = ((1.0f - uv.y) / w) * R.srcH;
+        custom0 = 1.0f / w;
+    } else {
+        uvU = uv.x * R.srcW;
+        uvV = (1.0f - uv.y) * R.srcH;
+    }
+
+    col = ldg4(R.color);                                        // camera.go:1726-1736
+    if (R.col) {
+        const float4 vc = ldg4(R.col + 4 * (size_t)vi);
+        col.x = vc.x * col.x; col.y = vc.y * col.y; col.z = vc.z * col.z; col.w = vc.w * col.w;
+    }
+    const uint32_t flags = R.flags;
+    if (flags & T3D_DRAW_LIT) {                                 // camera.go:1738-1742
+        const float4 L = __ldg(&light[slot]);
+        col.x *= L.x; col.y *= L.y; col.z *= L.z;
+    }
+
+    dcol = make_float4(0, 0, 0, 0);
+    if (fc.camFlags & T3D_CAM_RENDER_DEPTH) {                   // camera.go:1744-1782
+        float vertexDepth = Tc.z;
+        if ((flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) vertexDepth = __ldg(&unbill[slot]);
+        float depth = (vertexDepth + fc.depthMargin) / fc.camSpread;
+        if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
+        dcol = make_float4(depth, depth, depth, 1.0f);
+    } else if (fc.worldPresent && fc.fogOn) {                   // camera.go:1784-1814
+        float depth = (Tc.z + fc.depthMargin) / fc.camSpread;
+        if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
+        depth = fc.fogRange[0] + ((fc.fogRange[1] - fc.fogRange[0]) * 1.0f - depth);
+        if (fc.fogMode == T3D_FOG_ADD) {
+            col.x += fc.fogColor[0] * depth; col.y += fc.fogColor[1] * depth; col.z += fc.fogColor[2] * depth;
+        } else if (fc.fogMode == T3D_FOG_SUB) {
+            col.x *= fc.fogColor[0] * depth; col.y *= fc.fogColor[1] * depth; col.z *= fc.fogColor[2] * depth;
+        }
+    }
+    a = make_float4(dx, dy, uvU, uvV);
+}
+
+// ---- indexed delivery of a shard's frame ------------------------------------------------------------------------------
+// The compact form (k_emit<.., COMPACT>) ships 36 bytes per EMITTED corner.  A corner's record depends on its (draw, vertex)
+// only, and a mesh vertex is a corner of several triangles, so a shard can instead ship the record once per ARENA vertex plus a
+// 4-byte arena slot per emitted corner: 36 V + 4 C bytes instead of 36 C (1 M-triangle frame: V = 550 550, C = 1 374 564:
+// 25.3 MB instead of 49.5 MB over NVLink).  It only pays when 36 V + 4 C < 36 C, which depends on how many triangles survive,
+// so every kernel of the delivery takes the decision itself from the arena size and the survivor total the tile scan left.
+__device__ __forceinline__ bool delivery_indexed(uint32_t totalV, const uint32_t* __restrict__ chunkSum, uint32_t nChunks) {
+    uint64_t tris = 0;
+    for (uint32_t c = 0; c < nChunks; c++) tris += __ldg(&chunkSum[c]);
+    const uint64_t corners = 3 * tris;
+    return 36ull * totalV + 4ull * corners < 36ull * corners;
+}
+
+// One record per arena vertex, straight into the issuing rank's inbox (coalesced 32-byte stores over NVLink).
+__global__ void __launch_bounds__(256)
+k_vemit(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ vbase, uint32_t nDraws, uint32_t totalV, const uint32_t* __restrict__ chunkSum, uint32_t nChunks,
+        const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
+        const float* __restrict__ unbill, float4* __restrict__ rec32, float* __restrict__ dscal, float* __restrict__ cust) {
+    pdl_wait();
+    pdl_launch();
+    if (!delivery_indexed(totalV, chunkSum, nChunks)) return;
+    const uint32_t slot = blockIdx.x * 256u + threadIdx.x;
+    if (slot >= totalV) return;
+    const uint32_t d = find_draw(vbase, 0, nDraws - 1, slot);
+    const DrawRec& R = draws[d];
+    if (slot >= R.vbase + R.nv) return;        // (cannot happen: the arena is dense)
+    const bool persp = fc.camFlags & T3D_CAM_PERSPECTIVE, pcuv = fc.camFlags & T3D_CAM_PERSP_CORRECT_UV;
+    float4 a, col, dcol; float custom0;
+    emit_record(R, fc, slot, R.a0 + (slot - R.vbase), persp, pcuv, clip, clipXY, light, unbill, a, col, dcol, custom0);
+    rec32[2 * (size_t)slot] = a; rec32[2 * (size_t)slot + 1] = col;
+    dscal[slot] = dcol.x;
+    if (pcuv) cust[slot] = custom0;
+}
+
+// The arena slot of every emitted corner, in list order (what phase A of k_emit resolves), into the inbox.
+__global__ void __launch_bounds__(EMIT_TRIS)
+k_emit_index(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, const uint32_t* __restrict__ sorted,
+             const uint32_t* __restrict__ tileSurv, const uint32_t* __restrict__ tileOut, const uint32_t* __restrict__ chunkSum, uint32_t nChunks, uint32_t totalV,
+             uint32_t* __restrict__ cornerSlot, uint32_t* __restrict__ triIds) {
+    pdl_wait();
+    pdl_launch();
+    if (!delivery_indexed(totalV, chunkSum, nChunks)) return;
+    const uint32_t tileId = blockIdx.x / EMIT_PER_TILE;
+    const uint32_t k0 = (blockIdx.x % EMIT_PER_TILE) * EMIT_TRIS;
+    const uint32_t nSurv = __ldg(&tileSurv[tileId]);
+    if (k0 >= nSurv || threadIdx.x >= min((uint32_t)EMIT_TRIS, nSurv - k0)) return;
+    const TriTile T = tiles[tileId];
+    uint32_t outTri = __ldg(&tileOut[tileId]) + k0 + threadIdx.x;
+    for (uint32_t c = 0; c < tileId / SCAN_CHUNK; c++) outTri += __ldg(&chunkSum[c]);
+    const uint32_t val = __ldg(&sorted[T.start + k0 + threadIdx.x]);
+    uint32_t d, tslot;
+    if (T.info & TILE_LARGE) { d = T.dFirst; tslot = val; }
+    else { d = T.dFirst + (val >> 20); tslot = T.start + (val & 1023u); }
+    const DrawRec& R = draws[d];
+    const uint32_t ts = R.tstride, mt = R.t0 + (tslot - R.tbase), vofs = R.vbase - R.a0;
+    cornerSlot[3 * (size_t)outTri] = vofs + __ldg(R.idx + mt);
+    cornerSlot[3 * (size_t)outTri + 1] = vofs + __ldg(R.idx + ts + mt);
+    cornerSlot[3 * (size_t)outTri + 2] = vofs + __ldg(R.idx + 2 * (size_t)ts + mt);
+    triIds[outTri] = mt;
+}
+
 // COMPACT (sharded frames whose lists live on another GPU): of the 96 bytes a vertex has in the two lists only 36 carry
 // information -- {DstX, DstY, SrcX, SrcY | R, G, B, A}, the depth value d of the depth list's colour (d, d, d, 1), and
 // Custom0 when texture mapping is perspective-corrected (Custom1-3 are zero, camera.go:1689-1705, 1760-1782).  So the emit
@@ -1979,7 +2117,7 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
        const __grid_constant__ FrameConst fc, const float4* __restrict__ clip, const float2* __restrict__ clipXY, const float4* __restrict__ light,
        const float* __restrict__ unbill, const float4* __restrict__ tnrm,
        float4* __restrict__ colorList, float4* __restrict__ depthList, float4* __restrict__ normalList,
-       uint32_t* __restrict__ triIds, float* __restrict__ custom0List) {
+       uint32_t* __restrict__ triIds, float* __restrict__ custom0List, uint32_t deliverIndexedTotalV, uint32_t deliverChunks) {
     extern __shared__ uint4 emitSmem[];
     float4* sCol = reinterpret_cast<float4*>(emitSmem);             // [EMIT_TRIS][3]
     float4* sDep = sCol + 3 * EMIT_TRIS;
@@ -1990,6 +2128,7 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
 
     pdl_wait();
     pdl_launch();
+    if (COMPACT && deliverIndexedTotalV && delivery_indexed(deliverIndexedTotalV, chunkSum, deliverChunks)) return;      // k_vemit + k_emit_index deliver this frame
     const uint32_t tileId = blockIdx.x / EMIT_PER_TILE;
     const uint32_t k0 = (blockIdx.x % EMIT_PER_TILE) * EMIT_TRIS;
     const uint32_t nSurv = __ldg(&tileSurv[tileId]);
@@ -2030,62 +2169,8 @@ k_emit(const DrawRec* __restrict__ draws, const TriTile* __restrict__ tiles, con
             const uint32_t kk = v / 3u;
             const uint32_t vi = sVi[v], slot = sSlot[v];
             const DrawRec& R = draws[sDraw[kk]];
-            const float4 Tc = __ldg(&clip[slot]);
-            float w = Tc.w;                                             // camera.go:1655-1666
-            if (!persp) w = 1.0f;
-            const bool behind = w < 0;
-            if (behind) w = 0.001f;
-            // X/w and Y/w are k_vertex's unless the emit loop's w differs from the cull's (w < 0, orthographic);
-            // Y / -w == -(Y / w) exactly
-            float qx = Tc.x, qy = -Tc.y;
-            if (behind || !persp) {
-                const float2 xy = __ldg(&clipXY[slot]);
-                qx = xy.x / w; qy = xy.y / -w;
-            }
-            const float dx = qx * fc.camW + fc.halfW;                   // camera.go:1674-1675
-            const float dy = qy * fc.camH + fc.halfH;
-
-            const float2 uv = __ldg(reinterpret_cast<const float2*>(R.uv) + vi);
-            float uvU, uvV, custom0 = 0.0f;
-            if (pcuv) {                                                 // camera.go:1689-1705
-                uvU = (uv.x / w) * R.srcW;
-                uvV = ((1.0f - uv.y) / w) * R.srcH;
-                custom0 = 1.0f / w;
-            } else {
-                uvU = uv.x * R.srcW;
-                uvV = (1.0f - uv.y) * R.srcH;
-            }
-
-            float4 col = ldg4(R.color);                                 // camera.go:1726-1736
-            if (R.col) {
-                const float4 vc = ldg4(R.col + 4 * (size_t)vi);
-                col.x = vc.x * col.x; col.y = vc.y * col.y; col.z = vc.z * col.z; col.w = vc.w * col.w;
-            }
-            const uint32_t flags = R.flags;
-            if (flags & T3D_DRAW_LIT) {                                 // camera.go:1738-1742
-                const float4 L = __ldg(&light[slot]);
-                col.x *= L.x; col.y *= L.y; col.z *= L.z;
-            }
-
-            float4 dcol = make_float4(0, 0, 0, 0);
-            if (fc.camFlags & T3D_CAM_RENDER_DEPTH) {                   // camera.go:1744-1782
-                float vertexDepth = Tc.z;
-                if ((flags & T3D_DRAW_HAS_MATERIAL) && (flags & T3D_DRAW_DEPTH_UNBILLBOARDED)) vertexDepth = __ldg(&unbill[slot]);
-                float depth = (vertexDepth + fc.depthMargin) / fc.camSpread;
-                if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
-                dcol = make_float4(depth, depth, depth, 1.0f);
-            } else if (fc.worldPresent && fc.fogOn) {                   // camera.go:1784-1814
-                float depth = (Tc.z + fc.depthMargin) / fc.camSpread;
-                if (depth < 0) depth = 0; else if (depth > 1) depth = 1;
-                depth = fc.fogRange[0] + ((fc.fogRange[1] - fc.fogRange[0]) * 1.0f - depth);
-                if (fc.fogMode == T3D_FOG_ADD) {
-                    col.x += fc.fogColor[0] * depth; col.y += fc.fogColor[1] * depth; col.z += fc.fogColor[2] * depth;
-                } else if (fc.fogMode == T3D_FOG_SUB) {
-                    col.x *= fc.fogColor[0] * depth; col.y *= fc.fogColor[1] * depth; col.z *= fc.fogColor[2] * depth;
-                }
-            }
-
-            const float4 a = make_float4(dx, dy, uvU, uvV);
+            float4 a, col, dcol; float custom0;
+            emit_record(R, fc, slot, vi, persp, pcuv, clip, clipXY, light, unbill, a, col, dcol, custom0);
             const float4 cust = make_float4(custom0, 0.0f, 0.0f, 0.0f);
             if (COMPACT) {
                 float4* C = sCol + 2 * threadIdx.x;
@@ -2287,18 +2372,30 @@ void launch_draw_medium(cudaStream_t s, bool pdl, const DrawRec* draws, const Tr
 void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* tiles, uint32_t nTiles, const uint32_t* sorted,
                  const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, const FrameConst& fc, const float4* clip, const float2* clipXY,
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
-                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth, float* custom0List) {
+                 float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth, float* custom0List,
+                 uint32_t deliverIndexedTotalV, uint32_t deliverChunks) {
     if (!nTiles) return;
     const size_t idx = (size_t)(3 + 3 + 1) * EMIT_TRIS * sizeof(uint32_t);
     if (compactDepth)
         launch_kernel(k_emit<false, true>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List,
+                      deliverIndexedTotalV, deliverChunks);
     else if (normalList)
         launch_kernel(k_emit<true, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 9 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List, 0u, 0u);
     else
         launch_kernel(k_emit<false, false>, nTiles * EMIT_PER_TILE, EMIT_TRIS, 6 * EMIT_TRIS * sizeof(float4) + idx, s, pdl,
-                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List);
+                      draws, tiles, sorted, tileSurv, tileOut, chunkSum, fc, clip, clipXY, light, unbill, tnrm, colorList, depthList, normalList, triIds, custom0List, 0u, 0u);
+}
+
+// The indexed form of a shard's delivery (both kernels return at once when the frame is better off with the compact form).
+void launch_emit_indexed(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, uint32_t nDraws, uint32_t totalV, const TriTile* tiles, uint32_t nTiles,
+                         const uint32_t* sorted, const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, uint32_t nChunks, const FrameConst& fc,
+                         const float4* clip, const float2* clipXY, const float4* light, const float* unbill,
+                         float4* rec32, float* dscal, float* cust, uint32_t* cornerSlot, uint32_t* triIds) {
+    if (!nTiles || !totalV) return;
+    launch_kernel(k_vemit, (totalV + 255) / 256, 256, 0, s, false, draws, vbase, nDraws, totalV, chunkSum, nChunks, fc, clip, clipXY, light, unbill, rec32, dscal, cust);
+    launch_kernel(k_emit_index, nTiles * EMIT_PER_TILE, EMIT_TRIS, 0, s, false, draws, tiles, sorted, tileSurv, tileOut, chunkSum, nChunks, totalV, cornerSlot, triIds);
 }
 
 // ---- delivery of sharded frames to the rank that issues the draws -----------------------------------------
@@ -2327,7 +2424,7 @@ __global__ void k_gather_wait_ack(const uint32_t* __restrict__ ackWord, uint32_t
 // and its serial go to the issuing rank -- statistics and count first, then a system-wide fence, then the serial the owner polls.
 __global__ void __launch_bounds__(256)
 k_gather_post(uint32_t* __restrict__ mail, const uint32_t* __restrict__ chunkSum, uint32_t nChunks, uint32_t serial,
-              const uint4* __restrict__ stats, uint4* __restrict__ statsOut, uint32_t nDraws) {
+              const uint4* __restrict__ stats, uint4* __restrict__ statsOut, uint32_t nDraws, uint32_t totalV) {
     for (uint32_t i = threadIdx.x; i < nDraws; i += 256) statsOut[i] = stats[i];
     __threadfence_system();
     __syncthreads();
@@ -2335,44 +2432,72 @@ k_gather_post(uint32_t* __restrict__ mail, const uint32_t* __restrict__ chunkSum
         uint32_t n = 0;
         for (uint32_t c = 0; c < nChunks; c++) n += chunkSum[c];
         mail[1] = 3u * n;
+        mail[2] = (totalV && delivery_indexed(totalV, chunkSum, nChunks)) ? 1u : 0u;       // the form this frame arrived in
         __threadfence_system();
         mail[0] = serial;
     }
 }
 
-// The issuing rank: waits for a shard's frame, rebuilds its part of colorVertexList / depthVertexList (tetra3d.go:21-23) from the
-// 36-byte compact form, and acknowledges (the last block to finish).  Persistent grid; one thread per 16-byte piece of the
-// 48-byte output records, so that every store instruction of a warp covers 512 contiguous bytes of each list.
-__global__ void __launch_bounds__(256)
-k_gather_expand(const float4* __restrict__ rec32, const float* __restrict__ dscal, const float* __restrict__ cust,
-                float4* __restrict__ color, float4* __restrict__ depth, uint32_t* __restrict__ mail /* {serial, nVerts} | +16: ack | +17: done counter */,
-                uint32_t serial, int renderDepth, int pcuv, uint32_t* __restrict__ errWord) {
-    __shared__ uint32_t sN;
+// The issuing rank: waits for the shards' frames and rebuilds their parts of colorVertexList / depthVertexList (tetra3d.go:21-23)
+// from the compact or indexed form, and acknowledges (the last block of a shard's group to finish).  ONE launch covers every
+// shard: the grid is cut into one group of blocks per shard, each group waits on its own shard's mailbox, so a shard that has
+// arrived is rebuilt while the others are still in flight, and the groups' load latencies overlap (as one launch per shard
+// the rebuilds ran one after the other: 0.36 ms for seven 1.37 M-vertex shards).  One thread per 16-byte piece
+// of the 48-byte output records, four pieces in flight per thread, so that a warp's store covers 512 contiguous bytes of a list.
+struct GatherShard {
+    const float4* rec32; const float* dscal; const float* cust; const uint32_t* cornerSlot;
+    float4* color; float4* depth;
+    uint32_t* mail;     // {serial, nVerts, indexed} | +16: ack | +17: done counter
+};
+static const uint32_t GATHER_MAX_SHARDS = 15;
+struct GatherShards { GatherShard s[GATHER_MAX_SHARDS]; };
+__global__ void __launch_bounds__(256, 4)
+k_gather_expand(const __grid_constant__ GatherShards shards, uint32_t blocksPerShard, uint32_t serial, int renderDepth, int pcuv, uint32_t* __restrict__ errWord) {
+    __shared__ uint32_t sN, sIndexed;
+    const GatherShard& S = shards.s[blockIdx.x / blocksPerShard];
+    const uint32_t blk = blockIdx.x % blocksPerShard;
     if (threadIdx.x == 0) {
-        if (!wait_serial(mail, serial)) { *errWord = 1u; sN = 0; }
-        else sN = ld_volatile_u32(mail + 1);
+        if (!wait_serial(S.mail, serial)) { *errWord = 1u; sN = 0; sIndexed = 0; }
+        else { sN = ld_volatile_u32(S.mail + 1); sIndexed = ld_volatile_u32(S.mail + 2); }
     }
     __syncthreads();
     const uint64_t n3 = 3ull * sN;
-    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n3; i += (uint64_t)gridDim.x * 256) {
-        const uint32_t v = (uint32_t)(i / 3), part = (uint32_t)(i - 3ull * v);
-        float4 c, d;
-        if (part == 0) c = d = __ldcg(rec32 + 2 * (size_t)v);                       // DstX DstY SrcX SrcY
-        else if (part == 1) {
-            c = __ldcg(rec32 + 2 * (size_t)v + 1);                                  // R G B A
-            const float z = __ldcg(dscal + v);
-            d = renderDepth ? make_float4(z, z, z, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        } else c = d = make_float4(pcuv ? __ldcg(cust + v) : 0.0f, 0.0f, 0.0f, 0.0f);    // Custom0..3
-        __stcs(color + i, c);
-        __stcs(depth + i, d);
+    const bool indexed = sIndexed != 0;
+    const uint64_t stride = (uint64_t)blocksPerShard * 256;
+    constexpr int U = 4;
+    for (uint64_t i0 = (uint64_t)blk * 256 + threadIdx.x; i0 < n3; i0 += U * stride) {
+        uint32_t v[U], part[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {       // indexed frames: the record of an output vertex is the one of the arena vertex its corner refers to
+            const uint64_t i = i0 + u * stride;
+            const uint32_t ov = (uint32_t)(i / 3);
+            part[u] = (uint32_t)(i - 3ull * ov);
+            v[u] = (i < n3 && indexed) ? __ldcg(S.cornerSlot + ov) : ov;
+        }
+        float4 c[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (i0 + u * stride >= n3) continue;
+            if (part[u] == 0) c[u] = d[u] = __ldcg(S.rec32 + 2 * (size_t)v[u]);                   // DstX DstY SrcX SrcY
+            else if (part[u] == 1) {
+                c[u] = __ldcg(S.rec32 + 2 * (size_t)v[u] + 1);                                    // R G B A
+                const float z = __ldcg(S.dscal + v[u]);
+                d[u] = renderDepth ? make_float4(z, z, z, 1.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            } else c[u] = d[u] = make_float4(pcuv ? __ldcg(S.cust + v[u]) : 0.0f, 0.0f, 0.0f, 0.0f);    // Custom0..3
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = i0 + u * stride;
+            if (i < n3) { __stcs(S.color + i, c[u]); __stcs(S.depth + i, d[u]); }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(mail + 17, 1u) == gridDim.x - 1) {
-            mail[17] = 0;
+        if (atomicAdd(S.mail + 17, 1u) == blocksPerShard - 1) {
+            S.mail[17] = 0;
             __threadfence_system();
-            mail[16] = serial;          // the shard may overwrite its inbox now
+            S.mail[16] = serial;          // the shard may overwrite its inbox now
         }
     }
 }
@@ -2381,14 +2506,24 @@ void launch_gather_wait_ack(cudaStream_t s, const uint32_t* ackWord, uint32_t se
     launch_kernel(k_gather_wait_ack, 1, 1, 0, s, false, ackWord, serial, errWord);
 }
 void launch_gather_post(cudaStream_t s, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
-                        const void* stats, void* statsOut, uint32_t nDraws) {
-    launch_kernel(k_gather_post, 1, 256, 0, s, false, mail, chunkSum, nChunks, serial, reinterpret_cast<const uint4*>(stats), reinterpret_cast<uint4*>(statsOut), nDraws);
+                        const void* stats, void* statsOut, uint32_t nDraws, uint32_t totalV) {
+    launch_kernel(k_gather_post, 1, 256, 0, s, false, mail, chunkSum, nChunks, serial, reinterpret_cast<const uint4*>(stats), reinterpret_cast<uint4*>(statsOut), nDraws, totalV);
 }
-void launch_gather_expand(cudaStream_t s, const void* rec32, const float* dscal, const float* cust, t3d_vertex* color, t3d_vertex* depth,
-                          uint32_t* mail, uint32_t serial, bool renderDepth, bool pcuv, uint32_t* errWord) {
+void launch_gather_expand(cudaStream_t s, uint32_t nShards, const void* const* rec32, const float* const* dscal, const float* const* cust, const uint32_t* const* cornerSlot,
+                          t3d_vertex* const* color, t3d_vertex* const* depth, uint32_t* const* mail, uint32_t serial, bool renderDepth, bool pcuv, uint32_t* errWord) {
     if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
-    launch_kernel(k_gather_expand, (uint32_t)g_smCount * 8u, 256, 0, s, false, reinterpret_cast<const float4*>(rec32), dscal, cust,
-                  reinterpret_cast<float4*>(color), reinterpret_cast<float4*>(depth), mail, serial, renderDepth ? 1 : 0, pcuv ? 1 : 0, errWord);
+    for (uint32_t first = 0; first < nShards; first += GATHER_MAX_SHARDS) {
+        const uint32_t n = std::min(nShards - first, GATHER_MAX_SHARDS);
+        GatherShards G; memset(&G, 0, sizeof G);
+        for (uint32_t i = 0; i < n; i++) {
+            GatherShard& S = G.s[i];
+            S.rec32 = reinterpret_cast<const float4*>(rec32[first + i]); S.dscal = dscal[first + i]; S.cust = cust[first + i]; S.cornerSlot = cornerSlot[first + i];
+            S.color = reinterpret_cast<float4*>(color[first + i]); S.depth = reinterpret_cast<float4*>(depth[first + i]); S.mail = mail[first + i];
+        }
+        // every group must be resident at once (a group whose shard is late must not keep an earlier group's blocks from starting)
+        const uint32_t per = std::max(1u, (uint32_t)g_smCount * 4u / n);       // (4 blocks per SM: the kernel's launch bounds)
+        launch_kernel(k_gather_expand, n * per, 256, 0, s, false, G, per, serial, renderDepth ? 1 : 0, pcuv ? 1 : 0, errWord);
+    }
 }
 
 }  // namespace t3d

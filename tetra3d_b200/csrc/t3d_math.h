@@ -188,4 +188,39 @@ T3D_HD Mat4 m4_lookat(Vec3 from, Vec3 to, Vec3 up) {                            
     return r;
 }
 
+
+// Model.onTransformUpdate's culling sphere (model.go:142-182) from the model's transform and its mesh's Dimensions
+// {Center, Min, Max}, then Camera.SphereInFrustum (camera.go:933-983).  Host (frames not shipped as runs) and device
+// (k_prep_draws) share this one sequence of operations.
+struct FrustumTerms { Vec3 camPos, forward, right, up; float nearP, farP, sphereFactorY, sphereFactorX, sphereFactorTang, aspect, orthoScale; bool perspective; };
+T3D_HD bool m4_instance_in_frustum(const Mat4& transform, const float* bounds9, const FrustumTerms& F) {
+    Vec3 position, scale; Mat4 rotation;
+    m4_decompose(transform, position, scale, rotation);
+    Vec3 center = m4_multvec(rotation, v3(bounds9[0], bounds9[1], bounds9[2]));
+    position.X += center.X * scale.X; position.Y += center.Y * scale.Y; position.Z += center.Z * scale.Z;
+    const Vec3 mn = v3(bounds9[3] * scale.X, bounds9[4] * scale.Y, bounds9[5] * scale.Z);
+    const Vec3 mx = v3(bounds9[6] * scale.X, bounds9[7] * scale.Y, bounds9[8] * scale.Z);
+    const float radius = v3_magnitude(v3_sub(mx, mn)) / 2;                  // Dimensions.MaxSpan() / 2
+    const Vec3 diff = v3_sub(position, F.camPos);
+    float pcZ = v3_dot(diff, v3_invert(F.forward));
+    if (pcZ > F.farP + radius || pcZ < F.nearP - radius) return false;
+    if (F.perspective) {
+        float d = F.sphereFactorY * radius;
+        pcZ *= F.sphereFactorTang;
+        const float pcY = v3_dot(diff, F.up);
+        if (pcY > pcZ + d || pcY < -pcZ - d) return false;
+        pcZ *= F.aspect;
+        d = F.sphereFactorX * radius;
+        const float pcX = v3_dot(diff, F.right);
+        if (pcX > pcZ + d || pcX < -pcZ - d) return false;
+    } else {
+        const float w = F.orthoScale, h = w / F.aspect;
+        const float pcY = v3_dot(diff, F.up);
+        if (-h / 2 - radius > pcY || pcY > h / 2 + radius) return false;
+        const float pcX = v3_dot(diff, F.right);
+        if (-w / 2 - radius > pcX || pcX > w / 2 + radius) return false;
+    }
+    return true;
+}
+
 }  // namespace t3d
