@@ -149,7 +149,8 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-STAGE_KERNELS = {"vertex": "k_vertex", "cull": "k_cull_large / k_tile_packed / k_draw_medium", "sort": "k_tile_scan + k_bin_hist + k_scatter", "emit": "k_emit"}
+STAGE_KERNELS = {"vertex": "k_vertex", "cull": "k_tile_packed / k_draw_medium / k_cull_large / k_cull_sort (the last also sorts)",
+                 "sort": "k_tile_scan + k_bin_hist + k_scatter (draws the cull kernels did not sort themselves)", "emit": "k_emit"}
 
 
 def algorithmic_bytes(cam, desc, device, n_vertices_out):

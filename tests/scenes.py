@@ -195,6 +195,28 @@ def batch_scene(seed=0, n_children=40, transparent=True) -> SceneDesc:
     return SceneDesc(models, [], CameraDesc(), WorldDesc(), name="batch")
 
 
+def batch_frustum_scene(seed=0, n_children=60, spread=40.0, perspective=True, parent=False, billboard=True) -> SceneDesc:
+    """A dynamic batch whose children are instances of one another (one mesh, one material, one parent, no rotation) with
+    FrustumCulling on, spread far wider than the view: most of them fail Camera.SphereInFrustum (camera.go:2088-2093), which the
+    device evaluates for such batches (t3d_submit_instances with bounds).  Non-uniform scales, mirrored ones included."""
+    rng = np.random.default_rng(seed)
+    child_mat = MaterialDesc(billboard_enabled=billboard, transparency_mode=3, shadeless=True, backface_culling=False)
+    child_mesh = W.cube_mesh(1.0, 0.6, 0.8, material=child_mat) if not billboard else W.plane_mesh(1, 1, material=child_mat, colors=rng.uniform(0.1, 1, (4, 4)).astype(F32))
+    owner_mesh = W.plane_mesh(1, 1, material=MaterialDesc(transparency_mode=3, shadeless=True))
+    owner = ModelDesc(owner_mesh, NodeDesc(position=(0.0, 0.0, -3.0)), frustum_culling=False, name="owner")
+    group = NodeDesc(position=(1.5, -0.5, 0.5), scale=(1.0, 1.25, 1.0), rotation=W.rotation_matrix((0, 1, 0), 0.4), name="group") if parent else None
+    models = [owner]
+    for i in range(n_children):
+        s = rng.uniform(0.3, 2.0, 3)
+        if i % 5 == 0:
+            s[0] = -s[0]
+        models.append(ModelDesc(child_mesh, NodeDesc(position=(float(rng.uniform(-spread, spread)), float(rng.uniform(-spread / 2, spread / 2)), float(rng.uniform(-60, 20))),
+                                                     scale=tuple(float(x) for x in s), parent=group),
+                                color=(1.0, float(rng.uniform(0, 1)), 0.5, 0.7), batch_owner=owner, frustum_culling=True, name="c%d" % i))
+    cam = CameraDesc(perspective=perspective, ortho_scale=30.0) if not perspective else CameraDesc()
+    return SceneDesc(models, [], cam, WorldDesc(), name="batchfrustum")
+
+
 def volume_scene(seed=0, mode=0) -> SceneDesc:
     rng = np.random.default_rng(seed)
     cx, cy, cz = 5, 4, 6

@@ -27,7 +27,9 @@ class MeshDesc(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("vp", C.c_float * 16), ("view", C.c_float * 16), ("position", C.c_float * 3), ("up", C.c_float * 3),
                 ("near_plane", C.c_float), ("far_plane", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
-                ("depth_margin", C.c_float), ("vertex_snapping", C.c_float), ("flags", C.c_uint32)]
+                ("depth_margin", C.c_float), ("vertex_snapping", C.c_float), ("flags", C.c_uint32),
+                ("forward", C.c_float * 3), ("right", C.c_float * 3), ("sphere_factor_y", C.c_float), ("sphere_factor_x", C.c_float),
+                ("sphere_factor_tang", C.c_float), ("ortho_scale", C.c_float)]
 
 
 class World(C.Structure):
@@ -300,7 +302,7 @@ def test_instances_equal_draws_bit_for_bit(abi, n, uniform, with_parent, with_ro
             inst[i].position[:] = pos[i].tolist(); inst[i].scale[:] = scl[i].tolist(); inst[i].color[:] = colr[i].tolist()
         r16 = (C.c_float * 16)(*rot.reshape(-1).tolist())
         p16 = (C.c_float * 16)(*parent.reshape(-1).tolist()) if parent is not None else None
-        assert lib.t3d_submit_instances(ctx, C.byref(proto), r16 if with_rotation else None, p16, inst, C.c_uint32(n)) == T3D_OK, lib.t3d_last_error(ctx)
+        assert lib.t3d_submit_instances(ctx, C.byref(proto), r16 if with_rotation else None, p16, None, inst, C.c_uint32(n)) == T3D_OK, lib.t3d_last_error(ctx)
         if mixed:
             assert lib.t3d_submit_draws(ctx, C.byref(extra), C.c_uint32(1)) == T3D_OK
 
@@ -333,9 +335,9 @@ def test_instances_reject_what_they_cannot_express(abi):
     proto = _draw(); inst = (Instance * 1)()
     bad = np.eye(4, dtype=np.float32); bad[0, 3] = 0.5
     b16 = (C.c_float * 16)(*bad.reshape(-1).tolist())
-    assert lib.t3d_submit_instances(ctx, C.byref(proto), b16, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED and b"affine" in lib.t3d_last_error(ctx)
+    assert lib.t3d_submit_instances(ctx, C.byref(proto), b16, None, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED and b"affine" in lib.t3d_last_error(ctx)
     proto.flags = 1 << 3     # T3D_DRAW_SKINNED
-    assert lib.t3d_submit_instances(ctx, C.byref(proto), None, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED
+    assert lib.t3d_submit_instances(ctx, C.byref(proto), None, None, None, inst, C.c_uint32(1)) == T3D_E_UNSUPPORTED
     assert lib.t3d_frame_execute(ctx) == T3D_OK
 
 

@@ -311,3 +311,20 @@ def test_both_sort_paths_of_large_draws(device, mode):
         assert_parity(sc, device, check_capture=False, modes=("fast",))
     finally:
         device.SetFusedSort(1)
+
+
+@pytest.mark.parametrize("n,perspective,parent,billboard", [(60, True, False, True), (60, False, True, False), (3000, True, False, True), (2600, True, True, False), (2200, False, False, True)])
+def test_device_frustum_culling_of_batch_children(device, n, perspective, parent, billboard):
+    """DynamicBatch children that are instances of one another: their ModelInFrustum test (camera.go:2088-2093: the culling sphere
+    of model.go:142-182 against Camera.SphereInFrustum) runs on the device -- in k_prep_draws for frames shipped as runs (>= 1024
+    draws), on the host through the same function otherwise.  The oracle tests every child on the CPU: same render() calls, same
+    lists; and the host-tested path (DeviceFrustumCulling off) gives the same frame."""
+    import tetra3d_b200 as t3d
+    desc = scenes.batch_frustum_scene(n, n_children=n, perspective=perspective, parent=parent, billboard=billboard)
+    cam, ref = assert_parity(desc, device, check_capture=False, modes=("fast",))
+    col1, n1 = cam.ColorVertexList().copy(), len(cam.Renders())      # (the lists are the library's: the next frame overwrites them)
+    assert 0 < len(ref.renders) < n, "the scene must have children on both sides of the frustum (%d of %d rendered)" % (len(ref.renders), n)
+    scene, cam2, objs = t3d.build_scene(desc, device)
+    cam2.DeviceFrustumCulling = False
+    cam2.Clear(); cam2.RenderScene(scene)
+    assert np.array_equal(bits(col1), bits(cam2.ColorVertexList())) and n1 == len(cam2.Renders())

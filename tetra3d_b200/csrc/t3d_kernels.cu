@@ -1805,6 +1805,7 @@ k_tile_packed(const DrawRec* __restrict__ draws, const uint32_t* __restrict__ tb
     }
     for (uint32_t s = threadIdx.x; s < nSeg; s += TILE_THREADS) {
         DrawStat st; st.minBits = sMin[s]; st.maxBits = sMax[s]; st.survivors = sCntSeg[s]; st.done = 0;
+        if (draws[T.dFirst + s].flags & T3D_DRAW_FRUSTUM_CULLED) st.minBits = DRAW_CULLED_MARK;     // (k_prep_draws' mark for the host survives)
         stats[T.dFirst + s] = st;
     }
     __syncthreads();
@@ -1890,6 +1891,7 @@ k_draw_medium(const DrawRec* __restrict__ draws, const TriTile* __restrict__ til
     for (int w = 0; w < TILE_THREADS / 32; w++) { mn = min(mn, sRed[0][w]); mx = max(mx, sRed[1][w]); cnt += sRed[2][w]; }
     if (threadIdx.x == 0) {
         DrawStat st; st.minBits = cnt ? mn : 0x7F7FFFFFu; st.maxBits = cnt ? mx : 0u; st.survivors = cnt; st.done = 0;
+        if (R.flags & T3D_DRAW_FRUSTUM_CULLED) st.minBits = DRAW_CULLED_MARK;       // (k_prep_draws' mark for the host survives)
         stats[d] = st;
     }
     if (cnt == 0) return;

@@ -410,6 +410,7 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("Device", &Camera::device)
         .def_readwrite("DownloadResults", &Camera::downloadResults)
         .def_readwrite("UseInstancing", &Camera::UseInstancing)
+        .def_readwrite("DeviceFrustumCulling", &Camera::DeviceFrustumCulling)
         .def_readwrite("MaxLightCount", &Camera::MaxLightCount)
         .def_readwrite("MaxLightCountFocusPoint", &Camera::MaxLightCountFocusPoint)
         .def("SetFieldOfView", [](Camera& c, float f) { c.fieldOfView = f; })

@@ -721,7 +721,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
 
     lap("pairs + sorts");
     // ---- walk the passes and collect every render(rp) call, grouped by flush (camera.go:2057-2109) ----
-    struct PendingDraw { Model* model; int part; int flush; bool first; };
+    // deferFrustum: the child's ModelInFrustum test (camera.go:2088-2093) is left to the device (t3d_submit_instances with bounds)
+    struct PendingDraw { Model* model; int part; int flush; bool first; bool deferFrustum; };
     std::vector<PendingDraw> pending;
     std::vector<std::pair<Model*, int>> flushOwners;
     for (auto* pass : {&solids, &transparents}) {
@@ -741,15 +742,24 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                     for (size_t k = 0; k < keyed.size(); k++) sorted[k] = std::move(modelSlice[keyed[k].second]);
                     modelSlice.swap(sorted);
                 }
+                // A batch whose children are instances of one another (one mesh of one part, one material, one parent, one
+                // rotation: particles) is submitted as instances, and then the device also runs the children's frustum test.
+                bool uniform = UseInstancing && DeviceFrustumCulling && modelSlice.size() >= 8;
+                for (size_t k = 0; uniform && k < modelSlice.size(); k++) {
+                    Model& a = *modelSlice[0]; Model& b = *modelSlice[k];
+                    uniform = b.mesh && b.mesh == a.mesh && b.mesh->MeshParts.size() == 1 && !b.skinned && b.parent == a.parent &&
+                              std::memcmp(&b.rotation, &a.rotation, sizeof(Matrix4)) == 0 && b.lightGroup == a.lightGroup && b.Shadeless == a.Shadeless;
+                }
                 for (auto& merged : modelSlice) {
                     if (!merged->visible) continue;
-                    if (merged->FrustumCulling && !ModelInFrustum(*merged)) continue;
+                    const bool defer = uniform && merged->FrustumCulling;
+                    if (merged->FrustumCulling && !defer && !ModelInFrustum(*merged)) continue;
                     if (!merged->mesh) continue;
-                    for (size_t cp = 0; cp < merged->mesh->MeshParts.size(); cp++) { pending.push_back({merged.get(), (int)cp, flushId, first}); first = false; }
+                    for (size_t cp = 0; cp < merged->mesh->MeshParts.size(); cp++) { pending.push_back({merged.get(), (int)cp, flushId, first, defer}); first = false; }
                 }
             } else {
                 if (!pair.model->mesh) continue;
-                pending.push_back({pair.model, pair.part, flushId, true});
+                pending.push_back({pair.model, pair.part, flushId, true, false});
             }
             flushOwners.push_back({pair.model, pair.part});
         }
@@ -780,6 +790,11 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     cam.depth_margin = DepthMargin; cam.vertex_snapping = VertexSnapping;
     cam.flags = (perspective ? T3D_CAM_PERSPECTIVE : 0) | (RenderDepth ? T3D_CAM_RENDER_DEPTH : 0) |
                 (RenderNormals ? T3D_CAM_RENDER_NORMALS : 0) | (PerspectiveCorrectedTextureMapping ? T3D_CAM_PERSP_CORRECT_UV : 0);
+    // what SphereInFrustum reads (camera.go:933-983): the device runs it for instances submitted with culling bounds
+    cam.forward[0] = cameraForward.X; cam.forward[1] = cameraForward.Y; cam.forward[2] = cameraForward.Z;
+    cam.right[0] = cameraRight.X; cam.right[1] = cameraRight.Y; cam.right[2] = cameraRight.Z;
+    cam.sphere_factor_y = sphereFactorY; cam.sphere_factor_x = sphereFactorX; cam.sphere_factor_tang = sphereFactorTang;
+    cam.ortho_scale = orthoScale;
     t3d_world tw; std::memset(&tw, 0, sizeof tw);
     if (world) {
         tw.present = 1; tw.fog_on = world->FogOn; tw.fog_mode = world->FogMode;
@@ -843,7 +858,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     std::vector<t3d_draw> draws; draws.reserve(pending.size());
     // per draw: may it travel as an instance (t3d_submit_instances)?  Its Node-local placement, the Material colour (the
     // instance carries Model.Color), and what a run of instances has to share beyond the t3d_draw fields
-    struct InstInfo { bool eligible; Node* parent; const Matrix4* rotation; float matColor[4]; t3d_instance inst; };
+    struct InstInfo { bool eligible, frustum; Node* parent; const Matrix4* rotation; float matColor[4]; t3d_instance inst; float bounds[9]; };
     std::vector<InstInfo> instInfo; instInfo.reserve(pending.size());
     std::vector<const PendingDraw*> submitted;
     submitted.reserve(pending.size()); renders.reserve(pending.size());
@@ -923,6 +938,12 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         {
             InstInfo ii; std::memset(&ii, 0, sizeof ii);
             ii.eligible = UseInstancing && !model->skinned;
+            ii.frustum = pd.deferFrustum;
+            if (ii.frustum) {       // mesh.Dimensions {Center, Min, Max}: what Model.onTransformUpdate builds the culling sphere from
+                const Dimensions& dm = mesh.dimensions; const Vector3 c = dm.Center();
+                const float b9[9] = {c.X, c.Y, c.Z, dm.Min.X, dm.Min.Y, dm.Min.Z, dm.Max.X, dm.Max.Y, dm.Max.Z};
+                std::memcpy(ii.bounds, b9, sizeof b9);
+            }
             ii.parent = model->parent; ii.rotation = &model->rotation;
             ii.matColor[0] = mat ? mat->Color.R : 1.0f; ii.matColor[1] = mat ? mat->Color.G : 1.0f;
             ii.matColor[2] = mat ? mat->Color.B : 1.0f; ii.matColor[3] = mat ? mat->Color.A : 1.0f;
@@ -948,7 +969,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             return q.eligible && (y.flags & T3D_DRAW_CONTINUE_FLUSH) && x.mesh_id == y.mesh_id && x.part == y.part &&
                    (x.flags | T3D_DRAW_CONTINUE_FLUSH) == y.flags && std::memcmp(x.world_rotation, y.world_rotation, 64) == 0 &&
                    x.src_w == y.src_w && x.src_h == y.src_h && x.sort_mode == y.sort_mode && x.lighting_mode == y.lighting_mode &&
-                   x.light_volume_mode == y.light_volume_mode && x.light_list == y.light_list && p.parent == q.parent &&
+                   x.light_volume_mode == y.light_volume_mode && x.light_list == y.light_list && p.parent == q.parent && p.frustum == q.frustum &&
                    std::memcmp(p.rotation, q.rotation, sizeof(Matrix4)) == 0 && std::memcmp(p.matColor, q.matColor, 16) == 0;
         };
         const size_t MIN_RUN = 8;
@@ -957,7 +978,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         for (size_t i = 0; i < draws.size();) {
             size_t j = i + 1;
             if (instInfo[i].eligible) while (j < draws.size() && sameRun(j - 1, j)) j++;
-            if (j - i >= MIN_RUN) {
+            if (j - i >= MIN_RUN || instInfo[i].frustum) {       // (a child whose frustum test was deferred must go down as an instance, however short its run)
                 if (i > plainFrom) check(ctx, t3d_submit_draws(ctx, draws.data() + plainFrom, (uint32_t)(i - plainFrom)), "t3d_submit_draws");
                 t3d_draw proto = draws[i];
                 std::memcpy(proto.color, instInfo[i].matColor, 16);
@@ -967,7 +988,8 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                 if (instInfo[i].parent) par = instInfo[i].parent->Transform();
                 float rot16[16], par16[16];
                 m4_store(*instInfo[i].rotation, rot16); m4_store(par, par16);
-                check(ctx, t3d_submit_instances(ctx, &proto, rot16, instInfo[i].parent ? par16 : nullptr, insts.data(), (uint32_t)insts.size()), "t3d_submit_instances");
+                check(ctx, t3d_submit_instances(ctx, &proto, rot16, instInfo[i].parent ? par16 : nullptr, instInfo[i].frustum ? instInfo[i].bounds : nullptr,
+                                                insts.data(), (uint32_t)insts.size()), "t3d_submit_instances");
                 plainFrom = j;
             }
             i = j;
@@ -986,10 +1008,13 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     // per-render and per-flush records (what flush() would slice: camera.go:1829-2048)
     size_t di = 0;
     uint64_t lastEnd = 0;
+    std::vector<char> culledOnDevice(renders.size(), 0);
     for (size_t i = 0; i < renders.size(); i++) {
         RenderRecord& r = renders[i];
         if (submitted[i]) {
             const t3d_draw_result& dr = output.draws[di++];
+            // an instance the device found outside the frustum: the reference never calls render() for it (camera.go:2088-2093)
+            if (submitted[i]->deferFrustum && dr.total_tris == 0 && dr.vertex_count == 0) culledOnDevice[i] = 1;
             r.firstVertex = dr.first_vertex; r.vertexCount = dr.vertex_count; r.totalTris = dr.total_tris;
             r.minDepth = dr.min_depth; r.maxDepth = dr.max_depth;
             lastEnd = dr.first_vertex + dr.vertex_count;
@@ -1013,6 +1038,20 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             flushes.push_back(fr);
             localFlushIds.push_back(fId);
         }
+    }
+    {   // instances the device culled were never render()ed in the reference: no record, no DebugInfo counts (camera.go:1532-1536)
+        size_t w = 0;
+        for (size_t i = 0; i < renders.size(); i++) {
+            if (culledOnDevice[i]) {
+                Model* m = submitted[i]->model;
+                debugInfo.totalTris -= m->mesh->MeshParts[submitted[i]->part]->TriangleCount();
+                if (m->DynamicBatchOwner) debugInfo.batchedParts--;
+                continue;
+            }
+            if (w != i) renders[w] = renders[i];
+            w++;
+        }
+        renders.resize(w);
     }
     lap("render/flush records");
 }

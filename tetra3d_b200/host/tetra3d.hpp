@@ -367,6 +367,9 @@ struct Camera : Node {
     // runs of Models that differ only in position, scale and colour are submitted with t3d_submit_instances (the device
     // evaluates their Node.Transform); false: every render(rp) is a t3d_draw carrying its matrix
     bool UseInstancing = true;
+    // with UseInstancing: DynamicBatch children that are instances of one another also get their ModelInFrustum test
+    // (camera.go:2088-2093) on the device; false: the host tests every child, as the reference does
+    bool DeviceFrustumCulling = true;
 
     // results of the last Render (library-owned memory, valid until the next Render)
     t3d_frame_output output{};
