@@ -477,7 +477,7 @@ def run_ours(args):
         "config": base_config(args.workload, desc, copies),
         "details": {"draws_rank0": n_draws, "surviving_triangles_rank0": surv, "l2": "flushed between steps (512 MiB write)",
                     "lighting": "default (MUFU reciprocals, colours within 1/255; t3d_set_exact_lighting restores bit-exact colours)",
-                    "parallelism": ("object-wise flush sharding x%d; every shard's emit kernel stores a 36-byte compact form of its vertices into rank 0's memory over NVLink (CUDA IPC peer memory) and posts to a mailbox there; rank 0's frame ends with the kernels that rebuild the 96-byte colour / depth records (t3d_gather_*); no collective and no host round trip inside the step" % world) if world > 1 else "1 GPU",
+                    "parallelism": ("object-wise flush sharding x%d; every shard's last kernels store its frame into rank 0's memory over NVLink (CUDA IPC peer memory) -- 36 bytes per emitted vertex, or one record per arena vertex + a 4-byte slot per emitted vertex when smaller -- and post to a mailbox there; rank 0's frame ends with the kernel that rebuilds the 96-byte colour / depth records (t3d_gather_*); no collective and no host round trip inside the step" % world) if world > 1 else "1 GPU",
                     "timing": "CUDA events on the library's launch stream around everything the frame enqueues (the first kernel fetches the uniforms over PCIe; at N > 1 the delivery to rank 0 is inside), a barrier before every step, max over ranks; roofline.stages from a second loop with an event between kernels",
                     "wall_ms_per_step_incl_flush_and_host": (wall1 - wall0) / args.steps * 1e3,
                     **({"per_rank": per_rank} if per_rank is not None else {})},

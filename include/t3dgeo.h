@@ -454,6 +454,9 @@ int t3d_debug_read_draw_vertices(t3d_ctx* ctx, uint32_t draw, uint32_t vtx_start
  * (so offsets returned by t3d_submit_poses read the device-evaluated poses). */
 int t3d_debug_read_bones(t3d_ctx* ctx, uint32_t offset, uint32_t n, float* matrices16);
 int t3d_debug_force_full_upload(t3d_ctx* ctx, int enabled);
+/* Host-side helper of the default lighting, exported for tests (needs no device): the largest squared distance d at which
+ * PointLight.VertexLight's energy test `1 / d * energy < 0.001` (light.go:205-210) still lets an unranged light through. */
+float t3d_debug_energy_cutoff(float energy);
 /* Number of kernels launched by the last t3d_frame_execute. */
 int t3d_debug_last_launch_count(t3d_ctx* ctx);
 /* Which large draws (9 .. 64 tiles of 1024 triangles) are culled and sorted by the single persistent kernel instead of the

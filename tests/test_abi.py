@@ -28,11 +28,12 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     """ctypes mirrors of the ABI structs a cgo shim would declare: sizes must match the C compiler's."""
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world), sizeof(t3d_pose), sizeof(t3d_track));return 0;}\n'
+    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world), sizeof(t3d_pose), sizeof(t3d_track));printf("%zu\\n", sizeof(t3d_instance));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "s")]).split()))
+    assert sizes[9] == 40           # t3d_instance: position[3] + scale[3] + color[4]
     assert sizes[0] == 48           # ebiten.Vertex: 12 x float32
     assert sizes[1] == 52 and sizes[5] == 16 and sizes[4] == 24
     assert sizes[2] % 8 == 0
@@ -63,3 +64,28 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", "") or f in ("scenedesc.py", "workloads.py", "build.py") and "import oracle" not in text and "from oracle" not in text, f
                 assert "import oracle" not in text and "from oracle" not in text and "t3d_oracle" not in text, f
+
+
+def test_energy_cutoff_is_the_exact_threshold_of_the_reference_test():
+    """The default lighting decides `1 / d * energy < 0.001` (light.go:205-210) with ONE comparison against a distance the host
+    finds by bisection (t3d_submit_lights).  That distance must be the exact threshold of the reference's float32 expression:
+    the test passes at T and fails at the next float above it -- for any energy, including the degenerate ones."""
+    import numpy as np
+    import tetra3d_b200
+    lib = ctypes.CDLL(tetra3d_b200.LIB_PATH)
+    lib.t3d_debug_energy_cutoff.restype = ctypes.c_float
+    lib.t3d_debug_energy_cutoff.argtypes = [ctypes.c_float]
+
+    def skipped(d, e):          # the reference's expression, float32 with two roundings
+        with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
+            return bool(np.float32(np.float32(1.0) / np.float32(d)) * np.float32(e) < np.float32(0.001))
+
+    rng = np.random.default_rng(3)
+    energies = np.concatenate([rng.uniform(0.01, 50, 200), 10.0 ** rng.uniform(-30, 30, 200), [1.0, 2.0, 40.0, 1e-45, 3e38]]).astype(np.float32)
+    for e in energies:
+        T = np.float32(lib.t3d_debug_energy_cutoff(float(e)))
+        assert T > 0 and not skipped(T, e), (e, T)
+        up = np.nextafter(T, np.float32(np.inf))
+        assert np.isinf(up) or skipped(up, e), (e, T, up)
+    assert lib.t3d_debug_energy_cutoff(0.0) == 0.0 and lib.t3d_debug_energy_cutoff(-2.0) == 0.0        # nothing at a distance passes
+    assert np.isinf(lib.t3d_debug_energy_cutoff(float("nan")))                                           # NaN never compares below

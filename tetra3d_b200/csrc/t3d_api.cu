@@ -1061,11 +1061,11 @@ static cudaError_t build_tri_tiles(t3d_ctx* ctx, uint32_t nDraws) {
 
 // Sharded delivery, enqueued behind the frame's emit.  A shard ships its per-draw statistics and reports the frame's serial
 // and vertex count to the issuing rank's mailbox; the issuing rank rebuilds every shard's part of the lists as it arrives.
-static int gather_enqueue(t3d_ctx* ctx, uint32_t nDraws, uint32_t nChunks) {
+static int gather_enqueue(t3d_ctx* ctx, uint32_t nDraws, uint32_t nChunks, bool pdl) {
     t3d_ctx::Gather& G = ctx->gather;
     cudaStream_t s = ctx->stream;
     if (G.rank != G.dst) {
-        launch_gather_post(s, G.mail(G.rank), ctx->dCount.as<uint32_t>(), nChunks, G.serial, ctx->dStats.p, G.stats(G.rank), nDraws,
+        launch_gather_post(s, pdl, G.mail(G.rank), ctx->dCount.as<uint32_t>(), nChunks, G.serial, ctx->dStats.p, G.stats(G.rank), nDraws,
                            (nDraws && ctx->deliverIndexed && ctx->vAcc <= G.cap) ? ctx->vAcc : 0u);
         ctx->launches += 1;
     } else {
@@ -1081,7 +1081,7 @@ static int gather_enqueue(t3d_ctx* ctx, uint32_t nDraws, uint32_t nChunks) {
             mail.push_back(G.mail(r));
         }
         if (!rec.empty()) {
-            launch_gather_expand(s, (uint32_t)rec.size(), rec.data(), dsc.data(), cus.data(), slot.data(), col.data(), dep.data(), mail.data(), G.serial, renderDepth, pcuv, G.err());
+            launch_gather_expand(s, pdl, (uint32_t)rec.size(), rec.data(), dsc.data(), cus.data(), slot.data(), col.data(), dep.data(), mail.data(), G.serial, renderDepth, pcuv, G.err());
             ctx->launches += ((int)rec.size() + 14) / 15;
         }
     }
@@ -1114,7 +1114,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     if (nDraws == 0 || totalT == 0) {
         for (int i = 0; i < 6; i++) CU(cudaEventRecord(ctx->ev[i], s));
         CU(cudaEventRecord(ctx->ev[9], s));
-        if (ctx->gather.active) { const int rc = gather_enqueue(ctx, 0, 0); if (rc != T3D_OK) return rc; }     // an empty shard still reports in
+        if (ctx->gather.active) { const int rc = gather_enqueue(ctx, 0, 0, false); if (rc != T3D_OK) return rc; }     // an empty shard still reports in
         CU(cudaEventRecord(ctx->ev[6], s));
         ctx->h2dBytes = 0;
         return T3D_OK;
@@ -1488,16 +1488,16 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     const bool offerIndexed = shard && ctx->deliverIndexed && totalV <= G.cap;
     if (shard) {
         CU(ctx->dGatherErr.ensure(64));
-        launch_gather_wait_ack(s, G.mail(G.rank) + 16, G.serial - 1, ctx->dGatherErr.as<uint32_t>());      // the previous frame has been expanded
+        launch_gather_wait_ack(s, pdl, G.mail(G.rank) + 16, G.serial - 1, ctx->dGatherErr.as<uint32_t>());      // the previous frame has been expanded
         uint8_t* in = G.inbox(G.rank);
-        launch_emit(s, false, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
+        launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                     ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                     reinterpret_cast<float4*>(in), reinterpret_cast<float4*>(in + G.cap * 32), nullptr, ctx->dTriIds.as<uint32_t>(), true,
                     reinterpret_cast<float*>(in + G.cap * 36), offerIndexed ? totalV : 0u, nScanChunks);
         // the indexed form (one record per arena vertex + a slot per emitted corner); each of the three kernels decides on the
         // device, from the survivor total, which form this frame takes, and the other form's kernels return at once
         if (offerIndexed) {
-            launch_emit_indexed(s, ctx->pDraws, ctx->pVbase, nDraws, totalV, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(),
+            launch_emit_indexed(s, pdl, ctx->pDraws, ctx->pVbase, nDraws, totalV, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(),
                                 ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>(), nScanChunks, ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                                 ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), reinterpret_cast<float4*>(in), reinterpret_cast<float*>(in + G.cap * 32),
                                 reinterpret_cast<float*>(in + G.cap * 36), reinterpret_cast<uint32_t*>(in + G.cap * 40), ctx->dTriIds.as<uint32_t>());
@@ -1512,7 +1512,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     }
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[9], s));
-    if (G.active) { const int rc = gather_enqueue(ctx, nDraws, ((uint32_t)ctx->hTiles.n + SCAN_CHUNK - 1) / SCAN_CHUNK); if (rc != T3D_OK) return rc; }
+    if (G.active) { const int rc = gather_enqueue(ctx, nDraws, ((uint32_t)ctx->hTiles.n + SCAN_CHUNK - 1) / SCAN_CHUNK, pdl); if (rc != T3D_OK) return rc; }
     CU(cudaEventRecord(ctx->ev[6], s));
     CU(cudaGetLastError());
 
@@ -1841,6 +1841,7 @@ int t3d_set_stage_timings(t3d_ctx* ctx, int enabled) {
 }
 
 int t3d_debug_last_launch_count(t3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+float t3d_debug_energy_cutoff(float energy) { return energy_cutoff(energy); }
 int t3d_debug_set_fused_sort(t3d_ctx* ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return T3D_E_INVALID;
     ctx->fuseSort = mode;

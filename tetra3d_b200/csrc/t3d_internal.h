@@ -59,17 +59,17 @@ void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* 
                  const float4* light, const float* unbill, const float4* tnrm, float4* colorList,
                  float4* depthList, float4* normalList, uint32_t* triIds, bool compactDepth, float* custom0List,
                  uint32_t deliverIndexedTotalV /* compact emit only: 0, or the arena size when launch_emit_indexed runs too */, uint32_t deliverChunks);
-void launch_emit_indexed(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, uint32_t nDraws, uint32_t totalV, const TriTile* tiles, uint32_t nTiles,
+void launch_emit_indexed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, uint32_t nDraws, uint32_t totalV, const TriTile* tiles, uint32_t nTiles,
                          const uint32_t* sorted, const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, uint32_t nChunks, const FrameConst& fc,
                          const float4* clip, const float2* clipXY, const float4* light, const float* unbill,
                          float4* rec32, float* dscal, float* cust, uint32_t* cornerSlot, uint32_t* triIds);
 // delivery of sharded frames (t3d_gather_*): mailbox = 32 words per rank in the issuing rank's memory: [0] serial, [1] vertex count
 // and [2] 1 when the frame arrived in the indexed form (written by the shard), [16] acknowledged serial, [17] block counter (written by the issuing rank)
 static const uint32_t GATHER_MAIL_WORDS = 32;
-void launch_gather_wait_ack(cudaStream_t s, const uint32_t* ackWord, uint32_t serial, uint32_t* errWord);
-void launch_gather_post(cudaStream_t s, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
+void launch_gather_wait_ack(cudaStream_t s, bool pdl, const uint32_t* ackWord, uint32_t serial, uint32_t* errWord);
+void launch_gather_post(cudaStream_t s, bool pdl, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
                         const void* stats, void* statsOut, uint32_t nDraws, uint32_t totalV /* 0: the frame was not offered the indexed form */);
-void launch_gather_expand(cudaStream_t s, uint32_t nShards, const void* const* rec32, const float* const* dscal, const float* const* cust, const uint32_t* const* cornerSlot,
+void launch_gather_expand(cudaStream_t s, bool pdl, uint32_t nShards, const void* const* rec32, const float* const* dscal, const float* const* cust, const uint32_t* const* cornerSlot,
                           t3d_vertex* const* color, t3d_vertex* const* depth, uint32_t* const* mail, uint32_t serial, bool renderDepth, bool pcuv, uint32_t* errWord);
 static const uint32_t VERTEX_TILE = 256;        // vertex slots per k_vertex block (tileFirst granularity)
 

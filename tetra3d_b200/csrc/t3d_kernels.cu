@@ -2391,13 +2391,13 @@ void launch_emit(cudaStream_t s, bool pdl, const DrawRec* draws, const TriTile* 
 }
 
 // The indexed form of a shard's delivery (both kernels return at once when the frame is better off with the compact form).
-void launch_emit_indexed(cudaStream_t s, const DrawRec* draws, const uint32_t* vbase, uint32_t nDraws, uint32_t totalV, const TriTile* tiles, uint32_t nTiles,
+void launch_emit_indexed(cudaStream_t s, bool pdl, const DrawRec* draws, const uint32_t* vbase, uint32_t nDraws, uint32_t totalV, const TriTile* tiles, uint32_t nTiles,
                          const uint32_t* sorted, const uint32_t* tileSurv, const uint32_t* tileOut, const uint32_t* chunkSum, uint32_t nChunks, const FrameConst& fc,
                          const float4* clip, const float2* clipXY, const float4* light, const float* unbill,
                          float4* rec32, float* dscal, float* cust, uint32_t* cornerSlot, uint32_t* triIds) {
     if (!nTiles || !totalV) return;
-    launch_kernel(k_vemit, (totalV + 255) / 256, 256, 0, s, false, draws, vbase, nDraws, totalV, chunkSum, nChunks, fc, clip, clipXY, light, unbill, rec32, dscal, cust);
-    launch_kernel(k_emit_index, nTiles * EMIT_PER_TILE, EMIT_TRIS, 0, s, false, draws, tiles, sorted, tileSurv, tileOut, chunkSum, nChunks, totalV, cornerSlot, triIds);
+    launch_kernel(k_vemit, (totalV + 255) / 256, 256, 0, s, pdl, draws, vbase, nDraws, totalV, chunkSum, nChunks, fc, clip, clipXY, light, unbill, rec32, dscal, cust);
+    launch_kernel(k_emit_index, nTiles * EMIT_PER_TILE, EMIT_TRIS, 0, s, pdl, draws, tiles, sorted, tileSurv, tileOut, chunkSum, nChunks, totalV, cornerSlot, triIds);
 }
 
 // ---- delivery of sharded frames to the rank that issues the draws -----------------------------------------
@@ -2418,7 +2418,10 @@ __device__ __forceinline__ bool wait_serial(const uint32_t* word, uint32_t seria
 }
 
 // A shard's emit may overwrite its inbox on the issuing rank only after that rank has expanded the previous frame.
+// (The delivery kernels are links of the frame's dependent-launch chain like every other kernel: wait, then release.)
 __global__ void k_gather_wait_ack(const uint32_t* __restrict__ ackWord, uint32_t serial, uint32_t* __restrict__ errWord) {
+    pdl_wait();
+    pdl_launch();
     if (!wait_serial(ackWord, serial)) *errWord = 1u;
 }
 
@@ -2427,6 +2430,7 @@ __global__ void k_gather_wait_ack(const uint32_t* __restrict__ ackWord, uint32_t
 __global__ void __launch_bounds__(256)
 k_gather_post(uint32_t* __restrict__ mail, const uint32_t* __restrict__ chunkSum, uint32_t nChunks, uint32_t serial,
               const uint4* __restrict__ stats, uint4* __restrict__ statsOut, uint32_t nDraws, uint32_t totalV) {
+    pdl_wait();         // the emit's stores into the inbox have been performed once it has completed
     for (uint32_t i = threadIdx.x; i < nDraws; i += 256) statsOut[i] = stats[i];
     __threadfence_system();
     __syncthreads();
@@ -2456,6 +2460,7 @@ struct GatherShards { GatherShard s[GATHER_MAX_SHARDS]; };
 __global__ void __launch_bounds__(256, 4)
 k_gather_expand(const __grid_constant__ GatherShards shards, uint32_t blocksPerShard, uint32_t serial, int renderDepth, int pcuv, uint32_t* __restrict__ errWord) {
     __shared__ uint32_t sN, sIndexed;
+    pdl_launch();       // (nothing follows in the frame; the wait for the own emit comes last: the rebuild touches other ranks' regions only)
     const GatherShard& S = shards.s[blockIdx.x / blocksPerShard];
     const uint32_t blk = blockIdx.x % blocksPerShard;
     if (threadIdx.x == 0) {
@@ -2502,16 +2507,17 @@ k_gather_expand(const __grid_constant__ GatherShards shards, uint32_t blocksPerS
             S.mail[16] = serial;          // the shard may overwrite its inbox now
         }
     }
+    pdl_wait();         // this kernel complete => the frame's own emit complete (what the frame's last event stands for)
 }
 
-void launch_gather_wait_ack(cudaStream_t s, const uint32_t* ackWord, uint32_t serial, uint32_t* errWord) {
-    launch_kernel(k_gather_wait_ack, 1, 1, 0, s, false, ackWord, serial, errWord);
+void launch_gather_wait_ack(cudaStream_t s, bool pdl, const uint32_t* ackWord, uint32_t serial, uint32_t* errWord) {
+    launch_kernel(k_gather_wait_ack, 1, 1, 0, s, pdl, ackWord, serial, errWord);
 }
-void launch_gather_post(cudaStream_t s, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
+void launch_gather_post(cudaStream_t s, bool pdl, uint32_t* mail, const uint32_t* chunkSum, uint32_t nChunks, uint32_t serial,
                         const void* stats, void* statsOut, uint32_t nDraws, uint32_t totalV) {
-    launch_kernel(k_gather_post, 1, 256, 0, s, false, mail, chunkSum, nChunks, serial, reinterpret_cast<const uint4*>(stats), reinterpret_cast<uint4*>(statsOut), nDraws, totalV);
+    launch_kernel(k_gather_post, 1, 256, 0, s, pdl, mail, chunkSum, nChunks, serial, reinterpret_cast<const uint4*>(stats), reinterpret_cast<uint4*>(statsOut), nDraws, totalV);
 }
-void launch_gather_expand(cudaStream_t s, uint32_t nShards, const void* const* rec32, const float* const* dscal, const float* const* cust, const uint32_t* const* cornerSlot,
+void launch_gather_expand(cudaStream_t s, bool pdl, uint32_t nShards, const void* const* rec32, const float* const* dscal, const float* const* cust, const uint32_t* const* cornerSlot,
                           t3d_vertex* const* color, t3d_vertex* const* depth, uint32_t* const* mail, uint32_t serial, bool renderDepth, bool pcuv, uint32_t* errWord) {
     if (!g_smCount) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev); if (g_smCount <= 0) g_smCount = 148; }
     for (uint32_t first = 0; first < nShards; first += GATHER_MAX_SHARDS) {
@@ -2524,7 +2530,7 @@ void launch_gather_expand(cudaStream_t s, uint32_t nShards, const void* const* r
         }
         // every group must be resident at once (a group whose shard is late must not keep an earlier group's blocks from starting)
         const uint32_t per = std::max(1u, (uint32_t)g_smCount * 4u / n);       // (4 blocks per SM: the kernel's launch bounds)
-        launch_kernel(k_gather_expand, n * per, 256, 0, s, false, G, per, serial, renderDepth ? 1 : 0, pcuv ? 1 : 0, errWord);
+        launch_kernel(k_gather_expand, n * per, 256, 0, s, pdl, G, per, serial, renderDepth ? 1 : 0, pcuv ? 1 : 0, errWord);
     }
 }
 

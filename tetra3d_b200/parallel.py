@@ -2,10 +2,11 @@
 end up on the rank that issues the draws (no cross-GPU merge is needed: each MeshPart is sorted in isolation,
 model.go:602, 989).  Two ways to get them there:
 
-  DeliveredLists  the library delivers inside the frame (t3d_gather_*): each shard's emit kernel stores a 36-byte
-                  compact form of its vertices straight into the issuing rank's memory over NVLink (TMA bulk stores) and
-                  posts to a mailbox there; the issuing rank's frame ends with the kernels that rebuild the lists.  No
-                  collective, no host round trip per frame.
+  DeliveredLists  the library delivers inside the frame (t3d_gather_*): each shard's last kernels store its frame straight
+                  into the issuing rank's memory over NVLink -- 36 bytes per emitted vertex, or one such record per arena
+                  vertex plus a 4-byte slot per emitted vertex when that is smaller -- and post to a mailbox there; the
+                  issuing rank's frame ends with the kernel that rebuilds the lists.  No collective, no host round trip per
+                  frame.
   gather_lists    the lists stay local and are collected afterwards with NCCL send / recv (also what the gloo
                   CPU tests exercise).
 
@@ -125,9 +126,9 @@ def delivered_flush_table(owners: List[int], draw_flush: List[List[int]], surviv
 
 class DeliveredLists:
     """The draw lists of a sharded frame on the rank `dst` that issues the draws, delivered inside the frame by the library
-    (include/t3dgeo.h: t3d_gather_*): every shard's emit kernel stores a 36-byte compact form of its vertices straight into
-    dst's memory over NVLink and posts the frame to a mailbox there; dst's frame ends with the kernels that rebuild the 96-byte
-    colour / depth records.  No collective and no host round trip per frame: torch.distributed only carries the three CUDA IPC
+    (include/t3dgeo.h: t3d_gather_*): every shard stores a compact or indexed form of its frame straight into dst's memory over
+    NVLink and posts the frame to a mailbox there; dst's frame ends with the kernel that rebuilds the 96-byte colour / depth
+    records.  No collective and no host round trip per frame: torch.distributed only carries the three CUDA IPC
     handles at construction.  All ranks render the same number of frames, in lockstep.
     """
 
