@@ -271,7 +271,9 @@ typedef struct t3d_animation_desc {
 typedef struct t3d_pose {
     float root[16];                 /* Transform() of the node the skeleton's root bones are children of */
     float playhead;                 /* AnimationPlayer playhead the tracks are sampled at (animation.go:686-712) */
-    float reserved[3];
+    float from_playhead;            /* t3d_submit_poses_blended: the playhead the previous animation was last sampled at */
+    float blend;                    /* t3d_submit_poses_blended: `bp`, elapsed time / BlendTime clamped to 1 (animation.go:854-857) */
+    float reserved;
 } t3d_pose;
 
 typedef struct t3d_ctx t3d_ctx;
@@ -344,12 +346,22 @@ int t3d_volume_use_lights(t3d_ctx* ctx, uint32_t volume_id, const t3d_light* lig
  * matrices to the frame's bone arena and returns the offset of the first in *offset. */
 int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset);
 /* Replaces: AnimationTrack.ValueAsVector / ValueAsQuaternion for every channel (animation.go:63-164, 674-722), the
- * SetLocalPosition / Scale / Rotation calls of AnimationPlayer.forceUpdate without blending or relative motion
- * (animation.go:961-980), Node.Transform of every bone and its boneInfluence (node.go:572-594) -- for n armatures
+ * SetLocalPosition / Scale / Rotation calls of AnimationPlayer.forceUpdate without relative motion
+ * (animation.go:961-980; blending: t3d_submit_poses_blended), Node.Transform of every bone and its boneInfluence (node.go:572-594) -- for n armatures
  * playing `animation_id` on `skeleton_id`.  The device evaluates them at t3d_frame_execute; pose i's matrices are
  * bones [*offset + i * n_bones, *offset + (i + 1) * n_bones) of the same arena t3d_submit_bones fills (the
  * returned offset carries a tag bit: pass it through t3d_draw.bone_offset unchanged, adding i * n_bones). */
 int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset);
+/* Replaces: the same for players in the middle of a blend (AnimationPlayer.BlendTime > 0 after Play(), animation.go:548-554,
+ * 852-907).  What the reference blends from is prevAnimatedProperties -- the copy Play() took of the targets of the last
+ * forceUpdate under the previous animation -- which is `from_animation_id` sampled at t3d_pose.from_playhead (0: the previous
+ * state animated nothing); what it blends into is `animation_id` at t3d_pose.playhead; t3d_pose.blend is the elapsed fraction.
+ * Per bone and property: both exist -> start + (target - start) * blend, rotations start.Slerp(target, blend).Unit(); one
+ * exists -> that one; neither -> the skeleton's rest value.  The frame in which blend reaches 1 still goes through here
+ * (animation.go:899-902 ends the blend after using it); later frames use t3d_submit_poses.  A blend that starts from an
+ * unfinished blend has no such closed form (its start is itself a blend result): keep t3d_submit_bones for those frames. */
+int t3d_submit_poses_blended(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t from_animation_id, uint64_t animation_id, const t3d_pose* poses,
+                             uint32_t n, uint32_t* offset);
 /* Replaces: one render(rp) call (camera.go:1507-1827) per element, in render order. */
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
 /* Replaces: n render(rp) calls (camera.go:2083-2100: the children of a DynamicBatch owner; any run of Models sharing mesh,

@@ -174,6 +174,8 @@ def lib():
         L.orc_bin_index.restype = C.c_int
         L.orc_node_transform.argtypes = [C.POINTER(orc_node), C.c_int32, f32p]
         L.orc_pose_bones.argtypes = [C.POINTER(orc_skeleton), C.POINTER(orc_animation), C.c_float, f32p, f32p]
+        L.orc_pose_bones_blended.argtypes = [C.POINTER(orc_skeleton), C.POINTER(orc_animation), C.c_float, C.POINTER(orc_animation), C.c_float,
+                                             C.c_float, f32p, f32p]
         L.orc_quat_slerp.argtypes = [f32p, f32p, C.c_float, f32p]
         L.orc_quat_to_matrix.argtypes = [f32p, f32p]
         L.orc_go_sin.argtypes = [C.c_double]; L.orc_go_sin.restype = C.c_double
@@ -303,22 +305,47 @@ def flatten_animation(anim: AnimationDesc, sk: SkeletonDesc):
     return tracks, np.ascontiguousarray(kt), np.ascontiguousarray(kv)
 
 
-def pose_bones(sk: SkeletonDesc, anim: Optional[AnimationDesc], playhead: float, root16) -> np.ndarray:
-    """boneInfluence of every bone of an armature posed at `playhead`: (n_bones, 16)."""
-    L = lib()
+def _c_skeleton(sk: SkeletonDesc):
     cs = orc_skeleton()
     cs.n_bones = len(sk.parent); cs.parent = sk.parent.ctypes.data_as(i32p); cs.inverse_bind = _fp(sk.inverse_bind)
     cs.rest_position = _fp(sk.rest_position); cs.rest_scale = _fp(sk.rest_scale); cs.rest_rotation = _fp(sk.rest_rotation)
-    ca = None
-    if anim is not None:
-        tracks, kt, kv = flatten_animation(anim, sk)
-        ct = (orc_track * (3 * len(sk.parent)))()
-        for i, (f, n, ip) in enumerate(tracks.reshape(-1, 3)):
-            ct[i].first_key = int(f); ct[i].n_keys = int(n); ct[i].interpolation = int(ip)
-        ca = orc_animation(); ca.n_bones = len(sk.parent); ca.tracks = ct; ca.key_times = _fp(kt); ca.key_values = _fp(kv)
+    return cs
+
+
+def _c_animation(anim: Optional[AnimationDesc], sk: SkeletonDesc):
+    """(orc_animation or None, the arrays it points into)."""
+    if anim is None:
+        return None, None
+    tracks, kt, kv = flatten_animation(anim, sk)
+    ct = (orc_track * (3 * len(sk.parent)))()
+    for i, (f, n, ip) in enumerate(tracks.reshape(-1, 3)):
+        ct[i].first_key = int(f); ct[i].n_keys = int(n); ct[i].interpolation = int(ip)
+    ca = orc_animation(); ca.n_bones = len(sk.parent); ca.tracks = ct; ca.key_times = _fp(kt); ca.key_values = _fp(kv)
+    return ca, (ct, kt, kv)
+
+
+def pose_bones(sk: SkeletonDesc, anim: Optional[AnimationDesc], playhead: float, root16) -> np.ndarray:
+    """boneInfluence of every bone of an armature posed at `playhead`: (n_bones, 16)."""
+    L = lib()
+    cs = _c_skeleton(sk)
+    ca, _keep = _c_animation(anim, sk)
     root = np.ascontiguousarray(root16, np.float32).reshape(16)
     out = np.zeros((len(sk.parent), 16), np.float32)
     L.orc_pose_bones(C.byref(cs), C.byref(ca) if ca is not None else None, float(playhead), _fp(root), _fp(out))
+    return out
+
+
+def pose_bones_blended(sk: SkeletonDesc, anim_from: Optional[AnimationDesc], from_playhead: float, anim: Optional[AnimationDesc],
+                       playhead: float, blend: float, root16) -> np.ndarray:
+    """The same while the AnimationPlayer blends from `anim_from` (frozen at from_playhead) into `anim` (animation.go:852-907)."""
+    L = lib()
+    cs = _c_skeleton(sk)
+    cf, _keep_f = _c_animation(anim_from, sk)
+    ca, _keep_a = _c_animation(anim, sk)
+    root = np.ascontiguousarray(root16, np.float32).reshape(16)
+    out = np.zeros((len(sk.parent), 16), np.float32)
+    L.orc_pose_bones_blended(C.byref(cs), C.byref(cf) if cf is not None else None, float(from_playhead),
+                             C.byref(ca) if ca is not None else None, float(playhead), float(blend), _fp(root), _fp(out))
     return out
 
 
@@ -493,7 +520,11 @@ class _Marshalled:
             cm.shadeless = int(md.shadeless); cm.visible = int(md.visible); cm.frustum_culling = int(md.frustum_culling)
             bi = md.bone_influences
             if md.pose is not None:     # bones posed from a skeleton + animation: the oracle's own restatement of that step
-                bi = pose_bones(md.pose.skeleton, md.pose.animation, md.pose.playhead, node_world_transform(md.pose.root))
+                if md.pose.blend_ms is not None:
+                    bi = pose_bones_blended(md.pose.skeleton, md.pose.blend_from, md.pose.from_playhead, md.pose.animation, md.pose.playhead,
+                                            md.pose.blend_fraction(), node_world_transform(md.pose.root))
+                else:
+                    bi = pose_bones(md.pose.skeleton, md.pose.animation, md.pose.playhead, node_world_transform(md.pose.root))
             if bi is not None:
                 b = np.ascontiguousarray(bi, np.float32).reshape(-1, 16); self.keep.append(b)
                 cm.skinned = 1; cm.n_bones = len(b); cm.bone_influences = _fp(b)

@@ -1874,25 +1874,64 @@ static int m4_is_zero(const mat4* a) {                              /* matrix.go
     return 1;
 }
 
-void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out) {
+/* Quaternion.Unit (quaternion.go:97-104): four divisions by Magnitude (quaternion.go:86-95) */
+static quat quat_unit(quat q) {
+    const float m = m32_sqrt((q.X * q.X) + (q.Y * q.Y) + (q.Z * q.Z) + (q.W * q.W));
+    q.X /= m; q.Y /= m; q.Z /= m; q.W /= m;
+    return q;
+}
+
+/* One bone's local position / scale / rotation after AnimationPlayer.forceUpdate (animation.go:837-985).
+ * `from` != NULL: the player is blending (animation.go:852-903): `from` sampled at from_playhead is what
+ * prevAnimatedProperties holds for the bone -- the copy Play() took of currentProperties (animation.go:548-554), i.e. the
+ * targets of the last forceUpdate under the previous animation -- and bp the blend fraction.  Per property: both exist ->
+ * start + (props - start) * bp (rotation: start.Slerp(props, bp).Unit()); only one exists -> that one; neither -> the bone
+ * keeps what its Node holds (the skeleton's rest values). */
+static void pose_local(const orc_skeleton* sk, int b, const orc_animation* an, float playhead,
+                       const orc_animation* from, float from_playhead, float bp, vec3* pos, vec3* scl, mat4* rot) {
+    *pos = v3(sk->rest_position[3 * b], sk->rest_position[3 * b + 1], sk->rest_position[3 * b + 2]);
+    *scl = v3(sk->rest_scale[3 * b], sk->rest_scale[3 * b + 1], sk->rest_scale[3 * b + 2]);
+    *rot = m4_load(sk->rest_rotation + 16 * (size_t)b);
+    vec3 pv = v3(0, 0, 0), sv = v3(0, 0, 0); quat pq = {0, 0, 0, 0};
+    int pP = 0, pS = 0, pR = 0;
+    if (an && b < an->n_bones) {
+        pP = track_vector(an, &an->tracks[3 * b + 0], playhead, &pv);
+        pS = track_vector(an, &an->tracks[3 * b + 1], playhead, &sv);
+        pR = track_quaternion(an, &an->tracks[3 * b + 2], playhead, &pq);
+    }
+    if (from && b < from->n_bones) {
+        vec3 v; quat q;
+        if (track_vector(from, &from->tracks[3 * b + 0], from_playhead, &v)) {
+            if (pP) { pv.X = v.X + ((pv.X - v.X) * bp); pv.Y = v.Y + ((pv.Y - v.Y) * bp); pv.Z = v.Z + ((pv.Z - v.Z) * bp); }   /* animation.go:863-866 */
+            else { pv = v; pP = 1; }
+        }
+        if (track_vector(from, &from->tracks[3 * b + 1], from_playhead, &v)) {
+            if (pS) { sv.X = v.X + ((sv.X - v.X) * bp); sv.Y = v.Y + ((sv.Y - v.Y) * bp); sv.Z = v.Z + ((sv.Z - v.Z) * bp); }   /* animation.go:875-878 */
+            else { sv = v; pS = 1; }
+        }
+        if (track_quaternion(from, &from->tracks[3 * b + 2], from_playhead, &q)) {
+            if (pR) pq = quat_unit(quat_slerp(q, pq, bp));                                                                      /* animation.go:887-889 */
+            else { pq = q; pR = 1; }
+        }
+    }
+    if (pP) *pos = pv;
+    if (pS) *scl = sv;
+    if (pR) {
+        const mat4 r = quat_to_matrix(pq);
+        if (!m4_is_zero(&r)) *rot = r;             /* SetLocalRotation ignores an all-zero matrix (node.go:906-912) */
+    }
+}
+
+static void pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const orc_animation* from, float from_playhead,
+                       float bp, const float* root16, float* out) {
     const int n = sk->n_bones;
     mat4* world = (mat4*)malloc(sizeof(mat4) * (size_t)(n > 0 ? n : 1));
     const mat4 root = m4_load(root16);
     for (int b = 0; b < n; b++) {
-        /* AnimationPlayer.updateValues + forceUpdate (animation.go:674-722, 961-980): tracks that exist overwrite the
-         * node's local position / scale / rotation; SetLocalRotation ignores an all-zero matrix (node.go:906-912) */
-        vec3 pos = v3(sk->rest_position[3 * b], sk->rest_position[3 * b + 1], sk->rest_position[3 * b + 2]);
-        vec3 scl = v3(sk->rest_scale[3 * b], sk->rest_scale[3 * b + 1], sk->rest_scale[3 * b + 2]);
-        mat4 rot = m4_load(sk->rest_rotation + 16 * (size_t)b);
-        if (an && b < an->n_bones) {
-            vec3 v; quat q;
-            if (track_vector(an, &an->tracks[3 * b + 0], playhead, &v)) pos = v;
-            if (track_vector(an, &an->tracks[3 * b + 1], playhead, &v)) scl = v;
-            if (track_quaternion(an, &an->tracks[3 * b + 2], playhead, &q)) {
-                const mat4 r = quat_to_matrix(q);
-                if (!m4_is_zero(&r)) rot = r;
-            }
-        }
+        /* AnimationPlayer.updateValues + forceUpdate (animation.go:674-722, 837-980): tracks that exist overwrite the
+         * node's local position / scale / rotation */
+        vec3 pos, scl; mat4 rot;
+        pose_local(sk, b, an, playhead, from, from_playhead, bp, &pos, &scl, &rot);
         /* Node.Transform (node.go:572-594) */
         mat4 t = m4_scale(scl.X, scl.Y, scl.Z);
         t = m4_mult(t, rot);
@@ -1903,6 +1942,17 @@ void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playh
         m4_store(&infl, out + 16 * (size_t)b);
     }
     free(world);
+}
+
+void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out) {
+    pose_bones(sk, an, playhead, NULL, 0, 0, root16, out);
+}
+
+/* A player in the middle of a blend (BlendTime > 0, animation.go:852-907): `from` (may be NULL: the previous state animated
+ * nothing) sampled at from_playhead is the start, `an` at `playhead` the target, bp the elapsed fraction. */
+void orc_pose_bones_blended(const orc_skeleton* sk, const orc_animation* from, float from_playhead, const orc_animation* an, float playhead,
+                            float bp, const float* root16, float* out) {
+    pose_bones(sk, an, playhead, from, from_playhead, bp, root16, out);
 }
 
 /* ================================================================================================

@@ -298,6 +298,9 @@ typedef struct orc_animation {
 } orc_animation;
 /* boneInfluence of every bone, posed at `playhead`, with the skeleton's root bones parented to root16. */
 void   orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out);
+/* The same while the player blends from `from` @ from_playhead into `an` @ playhead (animation.go:852-907), bp = blend fraction. */
+void   orc_pose_bones_blended(const orc_skeleton* sk, const orc_animation* from, float from_playhead, const orc_animation* an, float playhead,
+                              float bp, const float* root16, float* out);
 void   orc_quat_slerp(const float* a4, const float* b4, float percent, float* out4);      /* quaternion.go:26-59 */
 void   orc_quat_to_matrix(const float* q4, float* out16);                                 /* quaternion.go:132-178 */
 double orc_go_sin(double x);                                                              /* Go math.Sin (amd64: pure Go) */

@@ -431,9 +431,11 @@ def random_animation(rng, sk, length: float = 3.0) -> "AnimationDesc":
     return AnimationDesc("random", length, channels)
 
 
-def posed_scene(seed=0, n_models=6, n_bones=5, chain=False, playheads=None) -> SceneDesc:
+def posed_scene(seed=0, n_models=6, n_bones=5, chain=False, playheads=None, blends=None) -> SceneDesc:
     """Skinned characters whose bones come from a skeleton + animation sampled at a playhead (PoseDesc): two skeletons, two
-    animations and a rest-pose armature in one frame, next to a model with explicit bone matrices and a static one."""
+    animations and a rest-pose armature in one frame, next to a model with explicit bone matrices and a static one.
+    blends: milliseconds into a one-second blend, cycled over the models (None entries: not blending); a blending player
+    comes from the skeleton's other animation, frozen at a random playhead (every fourth: from nothing)."""
     from tetra3d_b200.scenedesc import PoseDesc
     rng = np.random.default_rng(500 + seed)
     mesh, bone_y = W.tube_character_mesh(rings=9, sides=10, n_bones=n_bones)
@@ -446,7 +448,12 @@ def posed_scene(seed=0, n_models=6, n_bones=5, chain=False, playheads=None) -> S
         ph = float(playheads[i % len(playheads)]) if playheads is not None else float(rng.uniform(-0.2, 3.3))
         root = NodeDesc(position=(1.5 * (i - n_models / 2), -1.0, 0.0), rotation=random_rotation(rng) if i % 3 == 0 else W.rotation_matrix((0, 1, 0), 0.0),
                         scale=(1.0, 1.0 + 0.1 * (i % 2), 1.0))
-        models.append(ModelDesc(mesh, NodeDesc(), pose=PoseDesc(sks[k], anim, ph, root), frustum_culling=False, name="posed%d" % i))
+        pose = PoseDesc(sks[k], anim, ph, root)
+        if blends is not None and anim is not None and blends[i % len(blends)] is not None:
+            pose.blend_ms = int(blends[i % len(blends)])
+            pose.blend_from = None if i % 4 == 2 else anims[k][1 - (i // 2) % 2]
+            pose.from_playhead = float(rng.uniform(-0.2, 3.3))
+        models.append(ModelDesc(mesh, NodeDesc(), pose=pose, frustum_culling=False, name="posed%d" % i))
     bi = W.chain_bone_influences(bone_y, (0.0, 1.5, 0.0), 0.7, 0.3)
     models.append(ModelDesc(mesh, NodeDesc(), bone_influences=bi, frustum_culling=False, name="explicit"))
     models.append(ModelDesc(random_soup(300, seed, n_parts=1), NodeDesc(position=(0.0, 0.0, -2.0)), name="static"))

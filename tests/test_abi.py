@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     assert sizes[0] == 48           # ebiten.Vertex: 12 x float32
     assert sizes[1] == 52 and sizes[5] == 16 and sizes[4] == 24
     assert sizes[2] % 8 == 0
-    assert sizes[7] == 80 and sizes[8] == 12      # t3d_pose: root[16] + playhead + 3 reserved floats; t3d_track: 3 x uint32
+    assert sizes[7] == 80 and sizes[8] == 12      # t3d_pose: root[16] + playhead + from_playhead + blend + 1 reserved float; t3d_track: 3 x uint32
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -21,7 +21,11 @@ def assert_bones_match(desc, device):
     for md in desc.models:
         if md.pose is None:
             continue
-        want = O.pose_bones(md.pose.skeleton, md.pose.animation, md.pose.playhead, O.node_world_transform(md.pose.root))
+        p = md.pose
+        if p.blend_ms is not None:
+            want = O.pose_bones_blended(p.skeleton, p.blend_from, p.from_playhead, p.animation, p.playhead, p.blend_fraction(), O.node_world_transform(p.root))
+        else:
+            want = O.pose_bones(p.skeleton, p.animation, p.playhead, O.node_world_transform(p.root))
         got = device.ReadBones(offsets[md.name], len(want))
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (md.name, np.abs(got - want).max())
         checked += 1
@@ -110,11 +114,111 @@ def test_pose_api_errors(device):
     lib.t3d_destroy(ctx)
 
 
-def test_blending_and_relative_motion_are_refused(device):
+@pytest.mark.parametrize("seed", range(8))
+def test_blended_poses_parity(device, seed):
+    # players in the middle of a blend (animation.go:852-907): at the start (bp = 0), inside, one millisecond before the end, at the
+    # end (bp = 1) and past it (clamped); from the skeleton's other animation or from nothing; next to players that do not blend
+    blends = [[0, 250, 999, 1000, 1500, None, 333], [500], [1, None, 1000], [125, 875, None, None, 640]][seed % 4]
+    desc = scenes.posed_scene(40 + seed, n_models=int([7, 4, 9, 12][seed % 4]), n_bones=[5, 8, 2, 13, 31, 64, 3, 300][seed], chain=bool(seed % 2), blends=blends)
+    assert any(md.pose is not None and md.pose.blend_ms is not None for md in desc.models)
+    assert_bones_match(desc, device)
+    assert_parity(desc, device, check_capture=False)
+
+
+def test_blended_poses_fuzz(device):
+    for seed in range(60, 72):
+        rng = np.random.default_rng(seed)
+        blends = [None if rng.random() < 0.2 else int(rng.integers(0, 1200)) for _ in range(5)]
+        if all(b is None for b in blends):
+            blends[0] = 400
+        desc = scenes.posed_scene(seed, n_models=int(rng.integers(2, 12)), n_bones=int(rng.integers(2, 64)), chain=bool(rng.integers(0, 2)), blends=blends)
+        assert_bones_match(desc, device)
+
+
+def test_blend_through_the_player_frame_by_frame(device):
+    # one armature driven the way a game drives it: walk plays, Play(run) starts a 200 ms blend, frames every 16 ms of a stepped
+    # clock -- every frame's bones against the oracle fed with what the reference's player would hold at that point
+    import tetra3d_b200 as t3d
+    desc = scenes.posed_scene(3, n_models=2, n_bones=6)
+    pose = desc.models[0].pose
+    other = desc.models[2 if len(desc.models) > 4 else 0].pose
+    rng = np.random.default_rng(9)
+    run = scenes.random_animation(rng, pose.skeleton, length=1.0)
+    scene, cam, objs = t3d.build_scene(desc, device)
+    player = objs[id(pose)]
+    anim_run = t3d.build_animation(run)
+    clock = [1000]
+    player.SetClock(lambda: clock[0])
+    player.BlendTime = 0.2
+    root = O.node_world_transform(pose.root)
+    name = desc.models[0].name
+
+    def frame():
+        cam.Clear(); cam.RenderScene(scene)
+        return device.ReadBones(cam.BoneOffsets()[name], len(pose.skeleton.parent))
+
+    player.Update(0.016)                                    # walk, BlendTime > 0: currentProperties is being tracked now
+    walk_ph = player.SampledPlayhead()
+    assert not player.Blending()
+    got = frame()
+    assert np.array_equal(got.view(np.uint32), O.pose_bones(pose.skeleton, pose.animation, walk_ph, root).view(np.uint32))
+    player.Play(anim_run)
+    seen_end = False
+    for step in range(20):
+        clock[0] += 16
+        player.Update(0.016)
+        ph = player.SampledPlayhead()
+        got = frame()
+        if player.Blending():
+            bp = player.BlendFraction()
+            assert bp == float(min(np.float32(16 * (step + 1)) / (np.float32(0.2) * np.float32(1000.0)), np.float32(1.0)))
+            assert player.BlendFromPlayhead() == walk_ph
+            want = O.pose_bones_blended(pose.skeleton, pose.animation, walk_ph, run, ph, bp, root)
+            seen_end = seen_end or bp == 1.0
+        else:
+            assert seen_end                                  # the blend is over: the frame after bp reached 1 is a plain pose again
+            want = O.pose_bones(pose.skeleton, run, ph, root)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), step
+    assert seen_end and not player.Blending()
+
+
+def test_blended_pose_api_errors(device):
+    import tetra3d_b200
+    lib = C.CDLL(tetra3d_b200.LIB_PATH)
+    ctx = C.c_void_p()
+    assert lib.t3d_create(C.byref(ctx), 0) == 0
+    off = C.c_uint32()
+    pose = (C.c_float * 20)()
+    assert lib.t3d_submit_poses_blended(ctx, C.c_uint64(1), C.c_uint64(2), C.c_uint64(3), pose, 1, C.byref(off)) == -5     # no open frame
+    assert lib.t3d_submit_poses_blended(ctx, C.c_uint64(1), C.c_uint64(2), C.c_uint64(3), pose, 1, None) == -1
+    lib.t3d_destroy(ctx)
+
+
+def test_relative_motion_and_nested_blends_are_refused(device):
     import tetra3d_b200 as t3d
     desc = scenes.posed_scene(1, n_models=2)
     scene, cam, objs = t3d.build_scene(desc, device)
-    player = objs[id(desc.models[0].pose)]
-    player.BlendTime = 0.2
-    with pytest.raises(Exception, match="blending"):
+    pose = desc.models[0].pose
+    player = objs[id(pose)]
+    rng = np.random.default_rng(1)
+    a = t3d.build_animation(scenes.random_animation(rng, pose.skeleton))
+    b = t3d.build_animation(scenes.random_animation(rng, pose.skeleton))
+    clock = [0]
+    player.SetClock(lambda: clock[0])
+    player.BlendTime = 0.5
+    player.Update(0.01)
+    player.Play(a)                      # a blend starts ...
+    clock[0] = 100
+    player.Update(0.01)
+    assert player.Blending() and not player.BlendStartIsBlend()
+    cam.Clear(); cam.RenderScene(scene)
+    player.Play(b)                      # ... and is interrupted by the next: its start is a blend result (animation.go:905-908)
+    clock[0] = 150
+    player.Update(0.01)
+    assert player.Blending() and player.BlendStartIsBlend()
+    with pytest.raises(Exception, match="unfinished blend"):
         cam.Clear(); cam.RenderScene(scene)
+    clock[0] = 10_000                   # once that blend has run out the player is an ordinary one again
+    player.Update(0.01); player.Update(0.01)
+    assert not player.Blending()
+    cam.Clear(); cam.RenderScene(scene)

@@ -141,3 +141,104 @@ def test_posed_scenes_render_in_the_oracle():
     for seed in range(3):
         r = O.render_scene(scenes.posed_scene(seed))
         assert r.n_vertices > 0
+
+
+# ---- blending (AnimationPlayer.BlendTime > 0: animation.go:548-554, 852-907) ---------------------------------------------
+def _unit(q):
+    """Quaternion.Unit (quaternion.go:86-104) in float32; math32.Sqrt is float32(math.Sqrt(float64))."""
+    q = np.asarray(q, F32)
+    m = F32(math.sqrt(float((q[0] * q[0]) + (q[1] * q[1]) + (q[2] * q[2]) + (q[3] * q[3]))))
+    return np.array([q[0] / m, q[1] / m, q[2] / m, q[3] / m], F32)
+
+
+def test_blend_formulas_follow_force_update():
+    qa = np.array([0, math.sin(0.2), 0, math.cos(0.2)], F32)
+    qb = np.array([math.sin(0.7), 0, 0, math.cos(0.7)], F32)
+    for bp in [0.0, 0.25, F32(16) / (F32(0.2) * F32(1000)), 0.999, 1.0]:
+        bp = F32(bp)
+        # position (animation.go:863-866): start + (target - start) * bp, component by component in float32
+        sk, start = one_bone({TRACK_POSITION: TrackDesc([0.0], [[1, 2, 3]])})
+        _, target = one_bone({TRACK_POSITION: TrackDesc([0.0], [[5, -6, 7.5]])})
+        got = O.pose_bones_blended(sk, start, 0.0, target, 0.0, float(bp), I16)[0].reshape(4, 4)
+        s, p = np.array([1, 2, 3], F32), np.array([5, -6, 7.5], F32)
+        assert np.array_equal(got[3, :3], s + (p - s) * bp), bp
+        # scale (animation.go:875-878)
+        sk, start = one_bone({TRACK_SCALE: TrackDesc([0.0], [[1, 1, 2]])})
+        _, target = one_bone({TRACK_SCALE: TrackDesc([0.0], [[3, 0.3, 2]])})
+        got = O.pose_bones_blended(sk, start, 0.0, target, 0.0, float(bp), I16)[0].reshape(4, 4)
+        s, p = np.array([1, 1, 2], F32), np.array([3, 0.3, 2], F32)
+        assert np.array_equal(np.diag(got)[:3], s + (p - s) * bp), bp
+        # rotation (animation.go:887-889): start.Slerp(target, bp).Unit(), then ToMatrix4 -- whose [3][3] is x2 + y2 + z2 + w2,
+        # not exactly 1, and the matrix is used as it is
+        sk, start = one_bone({TRACK_ROTATION: TrackDesc([0.0], [qa])})
+        _, target = one_bone({TRACK_ROTATION: TrackDesc([0.0], [qb])})
+        got = O.pose_bones_blended(sk, start, 0.0, target, 0.0, float(bp), I16)[0].reshape(4, 4)
+        assert np.array_equal(got, O.quat_to_matrix(_unit(O.quat_slerp(qa, qb, float(bp))))), bp
+    # the frame in which bp reaches 1 is still a blend: slerp(.., 1).Unit() is not the target quaternion bit for bit in general
+    q1 = _unit(O.quat_slerp(qa, qb, 1.0))
+    assert np.allclose(q1, qb, atol=1e-6)
+
+
+def test_blend_existence_rules():
+    # per property: both exist -> blend; only the target -> target; only the start -> start; neither -> the node's own value
+    sk, start = one_bone({TRACK_POSITION: TrackDesc([0.0], [[1, 2, 3]])})
+    _, target = one_bone({TRACK_SCALE: TrackDesc([0.0], [[2, 3, 4]])})
+    m = O.pose_bones_blended(sk, start, 0.0, target, 0.0, 0.3, I16)[0].reshape(4, 4)
+    assert np.array_equal(m[3, :3], [1, 2, 3]) and np.array_equal(np.diag(m)[:3], [2, 3, 4])
+    # a bone the previous animation did not animate (prevExists false, animation.go:843): the target's values, unblended
+    sk2 = SkeletonDesc(["a", "b"], [-1, -1], np.tile(I16, 2), [[0, 0, 0]] * 2, [[1, 1, 1]] * 2, np.tile(I16, 2))
+    start2 = AnimationDesc("s", 1.0, {"a": {TRACK_POSITION: TrackDesc([0.0], [[1, 1, 1]])}})
+    target2 = AnimationDesc("t", 1.0, {"a": {TRACK_POSITION: TrackDesc([0.0], [[3, 3, 3]])}, "b": {TRACK_POSITION: TrackDesc([0.0], [[9, 9, 9]])}})
+    m = O.pose_bones_blended(sk2, start2, 0.0, target2, 0.0, 0.5, np.tile(I16, 1)).reshape(2, 4, 4)
+    assert np.array_equal(m[0][3, :3], [2, 2, 2]) and np.array_equal(m[1][3, :3], [9, 9, 9])
+    # blending from nothing is the plain pose; a start frozen at its own playhead
+    rng = np.random.default_rng(3)
+    sk3 = scenes.random_skeleton(rng, 9)
+    a, b = scenes.random_animation(rng, sk3), scenes.random_animation(rng, sk3)
+    assert np.array_equal(O.pose_bones_blended(sk3, None, 0.0, b, 1.2, 0.4, I16), O.pose_bones(sk3, b, 1.2, I16))
+    assert not np.array_equal(O.pose_bones_blended(sk3, a, 0.5, b, 1.2, 0.4, I16), O.pose_bones_blended(sk3, a, 2.5, b, 1.2, 0.4, I16))
+
+
+def test_animation_player_blend_bookkeeping():
+    import tetra3d_b200 as t3d
+    walk = t3d.NewAnimation("walk"); walk.SetLength(2.0)
+    run = t3d.NewAnimation("run"); run.SetLength(1.0)
+    jump = t3d.NewAnimation("jump"); jump.SetLength(1.0)
+    clock = [5000]
+    ap = t3d.NewAnimationPlayer(t3d.Node("armature"))
+    ap.SetClock(lambda: clock[0])
+    # BlendTime 0: Play() copies nothing (animation.go:548) and nothing is tracked
+    ap.Play(walk); ap.Update(0.5)
+    assert not ap.Blending()
+    ap.BlendTime = 0.2
+    ap.Play(run)                                   # currentProperties is empty (never tracked): prevAnimatedProperties stays empty
+    clock[0] += 50; ap.Update(0.1)
+    assert not ap.Blending()
+    sampled_run = ap.SampledPlayhead()
+    ap.Play(jump)                                  # run's targets were tracked by the last update: this one blends
+    clock[0] += 48; ap.Update(0.016)
+    assert ap.Blending() and not ap.BlendStartIsBlend() and ap.BlendFrom() is run
+    assert ap.BlendFromPlayhead() == sampled_run
+    assert ap.BlendFraction() == float(F32(48) / (F32(0.2) * F32(1000)))
+    ap.Play(walk)                                  # in the middle of that blend: the start is a blend result
+    clock[0] += 16; ap.Update(0.016)
+    assert ap.Blending() and ap.BlendStartIsBlend()
+    clock[0] += 400; ap.Update(0.016)              # bp clamps to 1 (animation.go:855-857): the blend is used once more, then ends
+    assert ap.Blending() and ap.BlendFraction() == 1.0
+    ap.Update(0.016)
+    assert not ap.Blending()
+    ap.Play(run)                                   # walk alone was tracked by the last update: an ordinary blend again
+    clock[0] += 100; ap.Update(0.016)
+    assert ap.Blending() and not ap.BlendStartIsBlend() and ap.BlendFrom() is walk
+    # a player that stopped playing drops its blend at the next Update (animation.go:815-818)
+    ap.Pause(); ap.Update(0.016)
+    assert not ap.Blending()
+    # playing the animation that is already playing changes nothing (animation.go:533-536)
+    ap.Resume(); ap.Play(run); clock[0] += 10; ap.Update(0.016)
+    assert not ap.Blending()
+
+
+def test_blended_posed_scenes_render_in_the_oracle():
+    plain = O.render_scene(scenes.posed_scene(0, n_models=8))
+    mixed = O.render_scene(scenes.posed_scene(0, n_models=8, blends=[0, 250, 999, 1000, 1500, None, 333]))
+    assert mixed.n_vertices > 0 and plain.n_vertices > 0

@@ -28,10 +28,10 @@ def _load_host():
 def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
-    if name == "build_scene":
-        from .build import build_scene
-        globals()[name] = build_scene
-        return build_scene
+    if name in ("build_scene", "build_animation"):
+        from . import build as _build
+        globals()[name] = getattr(_build, name)
+        return globals()[name]
     if name in ("workloads", "parallel", "build", "glb"):
         import importlib
         return importlib.import_module("." + name, __name__)

@@ -60,6 +60,21 @@ def _apply_node(obj, nd: NodeDesc):
     obj.SetLocalRotation(np.asarray(nd.rotation, dtype=np.float32))
 
 
+def build_animation(ad):
+    """An Animation of the host mirror from an AnimationDesc (channels keyed by bone name, animation.go:204-222)."""
+    anim = t3d.NewAnimation(ad.name)
+    anim.SetLength(float(ad.length))
+    anim.SetLoopMode(int(ad.loop_mode))
+    for ch_name, tracks in ad.channels.items():
+        ch = anim.AddChannel(ch_name)
+        for ttype, td in tracks.items():
+            tr = ch.AddTrack(int(ttype))
+            tr.Interpolation = int(td.interpolation)
+            for t, v in zip(td.times, td.values):
+                tr.AddKeyframe(float(t), [float(x) for x in (v if int(ttype) == 2 else v[:3])])
+    return anim
+
+
 def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera", Dict[int, object]]:
     """Returns (scene, camera, objects) where objects maps id(desc object) -> host object.
 
@@ -154,19 +169,6 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
                 joints[int(p)].AddChildren(joints[b])
         return t3d.NewSkeletonFromJoints(joints, np.asarray(sd.inverse_bind, np.float32).reshape(-1))
 
-    def build_animation(ad):
-        anim = t3d.NewAnimation(ad.name)
-        anim.SetLength(float(ad.length))
-        anim.SetLoopMode(int(ad.loop_mode))
-        for ch_name, tracks in ad.channels.items():
-            ch = anim.AddChannel(ch_name)
-            for ttype, td in tracks.items():
-                tr = ch.AddTrack(int(ttype))
-                tr.Interpolation = int(td.interpolation)
-                for t, v in zip(td.times, td.values):
-                    tr.AddKeyframe(float(t), [float(x) for x in (v if int(ttype) == 2 else v[:3])])
-        return anim
-
     models = []
     for md in desc.models:
         if id(md.mesh) not in meshes:
@@ -190,8 +192,23 @@ def build_scene(desc: SceneDesc, device=None) -> Tuple["t3d.Scene", "t3d.Camera"
                 if id(pose.animation) not in animations:
                     animations[id(pose.animation)] = build_animation(pose.animation)
                 player = t3d.NewAnimationPlayer(armature)
-                player.Play(animations[id(pose.animation)])
-                player.SetPlayhead(float(pose.playhead))
+                if pose.blend_ms is not None:
+                    # drive the player the way a game would: play the previous animation with BlendTime set, Play() the next
+                    # one (the blend starts: animation.go:548-554), let blend_ms milliseconds of a stepped clock pass
+                    clock = [0]
+                    player.SetClock(lambda clock=clock: clock[0])
+                    player.BlendTime = float(pose.blend_time)
+                    if pose.blend_from is not None:
+                        if id(pose.blend_from) not in animations:
+                            animations[id(pose.blend_from)] = build_animation(pose.blend_from)
+                        player.Play(animations[id(pose.blend_from)])
+                        player.SetPlayhead(float(pose.from_playhead))
+                    player.Play(animations[id(pose.animation)])
+                    clock[0] = int(pose.blend_ms)
+                    player.SetPlayhead(float(pose.playhead))
+                else:
+                    player.Play(animations[id(pose.animation)])
+                    player.SetPlayhead(float(pose.playhead))
                 objs[id(pose)] = player
             model.SetSkeleton(skeletons[id(pose.skeleton)], armature, player)
         attach(model, md.node)

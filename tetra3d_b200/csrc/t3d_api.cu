@@ -75,7 +75,7 @@ struct Animation {
     void* block = nullptr;
     t3d_track* tracks = nullptr; float* keyTimes = nullptr; float4* keyValues = nullptr;
 };
-struct PoseCall { uint64_t skeleton, animation; uint32_t firstPose, nPoses, firstBone; };      // one t3d_submit_poses call of the frame
+struct PoseCall { uint64_t skeleton, animation; uint32_t firstPose, nPoses, firstBone; uint64_t fromAnimation; bool blended; };      // one t3d_submit_poses[_blended] call of the frame
 
 
 struct Mesh {
@@ -780,18 +780,23 @@ int t3d_animation_release(t3d_ctx* ctx, uint64_t animation_id) {
     return T3D_OK;
 }
 
-int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset) {
-    if (!ctx || !offset || (n && !poses)) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: NULL argument");
-    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_poses: not between frame_begin and frame_execute");
+static int submit_poses(t3d_ctx* ctx, const char* who, uint64_t skeleton_id, bool blended, uint64_t from_animation_id, uint64_t animation_id,
+                        const t3d_pose* poses, uint32_t n, uint32_t* offset) {
+    char msg[160];
+    auto bad = [&](int code, const char* what) { snprintf(msg, sizeof msg, "%s: %s", who, what); return fail(ctx, code, msg); };
+    if (!ctx || !offset || (n && !poses)) return bad(T3D_E_INVALID, "NULL argument");
+    if (!ctx->inFrame || ctx->executed) return bad(T3D_E_STATE, "not between frame_begin and frame_execute");
     auto sk = ctx->skeletons.find(skeleton_id);
-    if (sk == ctx->skeletons.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_poses: unknown skeleton");
-    if (animation_id) {
-        auto an = ctx->animations.find(animation_id);
-        if (an == ctx->animations.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_poses: unknown animation");
-        if (an->second.nBones > sk->second.nBones) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: the animation has more bones than the skeleton");
+    if (sk == ctx->skeletons.end()) return bad(T3D_E_NOTFOUND, "unknown skeleton");
+    for (uint64_t id : {animation_id, blended ? from_animation_id : 0}) {
+        if (!id) continue;
+        auto an = ctx->animations.find(id);
+        if (an == ctx->animations.end()) return bad(T3D_E_NOTFOUND, "unknown animation");
+        if (an->second.nBones > sk->second.nBones) return bad(T3D_E_INVALID, "the animation has more bones than the skeleton");
     }
-    if ((uint64_t)ctx->posedBones + (uint64_t)n * sk->second.nBones >= POSE_TAG) return fail(ctx, T3D_E_INVALID, "t3d_submit_poses: too many posed bones in one frame");
+    if ((uint64_t)ctx->posedBones + (uint64_t)n * sk->second.nBones >= POSE_TAG) return bad(T3D_E_INVALID, "too many posed bones in one frame");
     PoseCall c; c.skeleton = skeleton_id; c.animation = animation_id; c.firstPose = (uint32_t)ctx->hPoses.n; c.nPoses = n; c.firstBone = ctx->posedBones;
+    c.fromAnimation = blended ? from_animation_id : 0; c.blended = blended;
     CU(ctx->hPoses.reserve(ctx->hPoses.n + n));
     memcpy(ctx->hPoses.p + ctx->hPoses.n, poses, sizeof(t3d_pose) * (size_t)n);
     ctx->hPoses.n += n;
@@ -799,6 +804,15 @@ int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, 
     *offset = POSE_TAG | ctx->posedBones;
     ctx->posedBones += n * sk->second.nBones;
     return T3D_OK;
+}
+
+int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, const t3d_pose* poses, uint32_t n, uint32_t* offset) {
+    return submit_poses(ctx, "t3d_submit_poses", skeleton_id, false, 0, animation_id, poses, n, offset);
+}
+
+int t3d_submit_poses_blended(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t from_animation_id, uint64_t animation_id, const t3d_pose* poses,
+                             uint32_t n, uint32_t* offset) {
+    return submit_poses(ctx, "t3d_submit_poses_blended", skeleton_id, true, from_animation_id, animation_id, poses, n, offset);
 }
 
 int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset) {
@@ -1408,7 +1422,15 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             pb.out = ctx->pBones + 16 * ((size_t)ctx->frameBoneCount + c.firstBone);
             // small skeletons (every ordinary character) ride as extra blocks of k_prep_draws: no launch of their own, and
             // their PCIe round trip and double-precision Slerp overlap the draw records' fetch
-            if (nFused < PREP_POSE_BATCHES && pose_batch_smem(pb.nBones) <= PREP_POSE_SMEM) fused[nFused++] = pb;
+            if (c.blended) {      // players in the middle of a blend: k_pose_bones<true>, a launch of its own (transitions are short and rare)
+                PoseBlend bl; memset(&bl, 0, sizeof bl);
+                if (c.fromAnimation) {
+                    const Animation& F = ctx->animations.at(c.fromAnimation);
+                    bl.fromBones = F.nBones; bl.tracks = F.tracks; bl.keyTimes = F.keyTimes; bl.keyValues = F.keyValues;
+                }
+                CU(launch_pose_bones(s, pb, &bl)); ctx->launches += 1;
+            }
+            else if (nFused < PREP_POSE_BATCHES && pose_batch_smem(pb.nBones) <= PREP_POSE_SMEM) fused[nFused++] = pb;
             else { CU(launch_pose_bones(s, pb)); ctx->launches += 1; }
         }
         for (uint32_t b0 = 0, k = 0; b0 < nPrepBlocks; k++) {

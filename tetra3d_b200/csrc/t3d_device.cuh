@@ -278,5 +278,11 @@ struct PoseBatch {
     const t3d_pose* poses;                              // [nPoses] pinned host memory (UVA)
     float* out;                                         // first matrix of pose 0 in the frame's bone arena
 };
+// t3d_submit_poses_blended: the animation the player blends from (stand-alone k_pose_bones<true> only, so that the pose blocks
+// riding in k_prep_draws keep their size)
+struct PoseBlend {
+    uint32_t fromBones;                                 // 0: the previous state animated nothing
+    const t3d_track* tracks; const float* keyTimes; const float4* keyValues;
+};
 
 }  // namespace t3d

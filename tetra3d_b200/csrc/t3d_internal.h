@@ -88,7 +88,7 @@ void launch_ao(cudaStream_t s, const float* pos, uint32_t vstride, const uint32_
                const float* occlusionColor4, uint8_t* marks, float4* colors);
 
 // t3d_pose.cu -- bone poses evaluated on the device
-cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb);
+cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb, const PoseBlend* blend = nullptr);
 size_t pose_batch_smem(uint32_t nBones);        // shared memory a block needs for a skeleton of nBones
 
 }  // namespace t3d

@@ -1,6 +1,6 @@
 // t3d_pose.cu -- bone poses evaluated on the device (the step before the geometry stage).
 //
-// Replaces, for armatures driven by an AnimationPlayer without blending or relative motion:
+// Replaces, for armatures driven by an AnimationPlayer without relative motion (blends: k_pose_bones<true>, animation.go:852-907):
 //   AnimationTrack.ValueAsVector / ValueAsQuaternion      animation.go:63-164
 //   Quaternion.Slerp / ToMatrix4                          quaternion.go:26-59, 132-178
 //   AnimationPlayer.forceUpdate's SetLocal* calls         animation.go:961-980
@@ -19,19 +19,26 @@
 
 namespace t3d {
 
+template <bool BLEND>
 __global__ void __launch_bounds__(POSE_THREADS)
-k_pose_bones(const __grid_constant__ PoseBatch pb) {
+k_pose_bones(const __grid_constant__ PoseBatch pb, const __grid_constant__ PoseBlend bl) {
     extern __shared__ float poseSmem[];
-    pose_block(pb, blockIdx.x, poseSmem);
+    pose_block<BLEND>(pb, bl, blockIdx.x, poseSmem);
 }
 
 size_t pose_batch_smem(uint32_t nBones) { return pose_smem_bytes(nBones); }
 
-cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb) {
+cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb, const PoseBlend* blend) {
     if (!pb.nPoses || !pb.nBones) return cudaSuccess;
     const uint32_t ipb = pose_armatures_per_block(pb.nBones);
-    cudaFuncSetAttribute(k_pose_bones, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
-    return launch_kernel(k_pose_bones, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb);
+    PoseBlend bl; memset(&bl, 0, sizeof bl);
+    if (blend) {        // players in the middle of a blend (t3d_submit_poses_blended)
+        bl = *blend;
+        cudaFuncSetAttribute(k_pose_bones<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
+        return launch_kernel(k_pose_bones<true>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
+    }
+    cudaFuncSetAttribute(k_pose_bones<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
+    return launch_kernel(k_pose_bones<false>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
 }
 
 }  // namespace t3d

@@ -134,9 +134,61 @@ __device__ inline int track_keys(const t3d_track tr, const float* __restrict__ t
     return tr.interpolation == T3D_INTERPOLATION_CONSTANT ? 1 : 2;
 }
 
+__device__ inline Quat quat_unit(Quat q) {                                     // quaternion.go:86-104
+    const float m = sqrtf((q.X * q.X) + (q.Y * q.Y) + (q.Z * q.Z) + (q.W * q.W));
+    q.X /= m; q.Y /= m; q.Z /= m; q.W /= m;
+    return q;
+}
+
+// What AnimationPlayer.updateValues records for one bone (AnimationValues, animation.go:674-722): the three tracks of the
+// bone's channel sampled at `time`, and which of them exist.
+struct BoneSample { float px, py, pz, sx, sy, sz; Quat q; bool P, S, R; };
+__device__ inline BoneSample sample_bone(const t3d_track* __restrict__ tracks, const float* __restrict__ keyTimes,
+                                         const float4* __restrict__ keyValues, uint32_t bone, float time) {
+    BoneSample o;
+    o.px = o.py = o.pz = o.sx = o.sy = o.sz = 0.0f; o.q.X = o.q.Y = o.q.Z = o.q.W = 0.0f;
+    uint32_t a = 0, b = 0;
+    int k = track_keys(tracks[3 * bone + 0], keyTimes, time, a, b);
+    o.P = k != 0;
+    if (k) {                                                    // ValueAsVector + Vector3.Lerp (vector.go:559-565)
+        const float4 fa = keyValues[a];
+        o.px = fa.x; o.py = fa.y; o.pz = fa.z;
+        if (k == 2) {
+            const float4 fb = keyValues[b];
+            const float t = (time - keyTimes[a]) / (keyTimes[b] - keyTimes[a]);
+            o.px = o.px + ((fb.x - o.px) * t); o.py = o.py + ((fb.y - o.py) * t); o.pz = o.pz + ((fb.z - o.pz) * t);
+        }
+    }
+    k = track_keys(tracks[3 * bone + 1], keyTimes, time, a, b);
+    o.S = k != 0;
+    if (k) {
+        const float4 fa = keyValues[a];
+        o.sx = fa.x; o.sy = fa.y; o.sz = fa.z;
+        if (k == 2) {
+            const float4 fb = keyValues[b];
+            const float t = (time - keyTimes[a]) / (keyTimes[b] - keyTimes[a]);
+            o.sx = o.sx + ((fb.x - o.sx) * t); o.sy = o.sy + ((fb.y - o.sy) * t); o.sz = o.sz + ((fb.z - o.sz) * t);
+        }
+    }
+    k = track_keys(tracks[3 * bone + 2], keyTimes, time, a, b);
+    o.R = k != 0;
+    if (k) {                                                    // ValueAsQuaternion
+        const float4 fa = keyValues[a];
+        o.q.X = fa.x; o.q.Y = fa.y; o.q.Z = fa.z; o.q.W = fa.w;
+        if (k == 2) {
+            const float4 fb = keyValues[b];
+            Quat e; e.X = fb.x; e.Y = fb.y; e.Z = fb.z; e.W = fb.w;
+            const float t = (time - keyTimes[a]) / (keyTimes[b] - keyTimes[a]);
+            o.q = quat_slerp(o.q, e, t);
+        }
+    }
+    return o;
+}
+
 // The armatures [block * ipb, (block + 1) * ipb) of one batch, by the POSE_THREADS threads of a block (k_pose_bones, or the
-// pose blocks at the end of k_prep_draws' grid).
-__device__ inline void pose_block(const PoseBatch& pb, const uint32_t block, float* poseSmem) {
+// pose blocks at the start of k_prep_draws' grid).  BLEND: the players are in the middle of a blend (animation.go:852-907).
+template <bool BLEND>
+__device__ inline void pose_block(const PoseBatch& pb, const PoseBlend& bl, const uint32_t block, float* poseSmem) {
     // shared: local / world matrices as 16 planes of `slots` floats each (a thread's matrix is a column: no bank
     // conflicts), then the block's pose records
     const uint32_t nb = pb.nBones;
@@ -159,44 +211,35 @@ __device__ inline void pose_block(const PoseBatch& pb, const uint32_t block, flo
         float px = pb.restPos[3 * bone], py = pb.restPos[3 * bone + 1], pz = pb.restPos[3 * bone + 2];
         float sx = pb.restScale[3 * bone], sy = pb.restScale[3 * bone + 1], sz = pb.restScale[3 * bone + 2];
         Mat4 rot = m4_load(pb.restRot + 16 * (size_t)bone);
-        if (bone < pb.animBones) {
-            uint32_t a = 0, b = 0;
-            int k = track_keys(pb.tracks[3 * bone + 0], pb.keyTimes, time, a, b);
-            if (k) {                                                    // ValueAsVector + Vector3.Lerp (vector.go:559-565)
-                const float4 fa = pb.keyValues[a];
-                px = fa.x; py = fa.y; pz = fa.z;
-                if (k == 2) {
-                    const float4 fb = pb.keyValues[b];
-                    const float t = (time - pb.keyTimes[a]) / (pb.keyTimes[b] - pb.keyTimes[a]);
-                    px = px + ((fb.x - px) * t); py = py + ((fb.y - py) * t); pz = pz + ((fb.z - pz) * t);
+        BoneSample v;
+        v.P = v.S = v.R = false;
+        if (bone < pb.animBones) v = sample_bone(pb.tracks, pb.keyTimes, pb.keyValues, bone, time);
+        if (BLEND) {
+            if (bone < bl.fromBones) {                                  // prevAnimatedProperties[node] (animation.go:859)
+                const float bp = sPose[inst * 20 + 18];
+                const BoneSample f = sample_bone(bl.tracks, bl.keyTimes, bl.keyValues, bone, sPose[inst * 20 + 17]);
+                if (f.P) {                                              // animation.go:861-872
+                    if (v.P) { v.px = f.px + ((v.px - f.px) * bp); v.py = f.py + ((v.py - f.py) * bp); v.pz = f.pz + ((v.pz - f.pz) * bp); }
+                    else { v.px = f.px; v.py = f.py; v.pz = f.pz; v.P = true; }
+                }
+                if (f.S) {                                              // animation.go:874-884
+                    if (v.S) { v.sx = f.sx + ((v.sx - f.sx) * bp); v.sy = f.sy + ((v.sy - f.sy) * bp); v.sz = f.sz + ((v.sz - f.sz) * bp); }
+                    else { v.sx = f.sx; v.sy = f.sy; v.sz = f.sz; v.S = true; }
+                }
+                if (f.R) {                                              // animation.go:886-896
+                    if (v.R) v.q = quat_unit(quat_slerp(f.q, v.q, bp));
+                    else { v.q = f.q; v.R = true; }
                 }
             }
-            k = track_keys(pb.tracks[3 * bone + 1], pb.keyTimes, time, a, b);
-            if (k) {
-                const float4 fa = pb.keyValues[a];
-                sx = fa.x; sy = fa.y; sz = fa.z;
-                if (k == 2) {
-                    const float4 fb = pb.keyValues[b];
-                    const float t = (time - pb.keyTimes[a]) / (pb.keyTimes[b] - pb.keyTimes[a]);
-                    sx = sx + ((fb.x - sx) * t); sy = sy + ((fb.y - sy) * t); sz = sz + ((fb.z - sz) * t);
-                }
-            }
-            k = track_keys(pb.tracks[3 * bone + 2], pb.keyTimes, time, a, b);
-            if (k) {                                                    // ValueAsQuaternion
-                const float4 fa = pb.keyValues[a];
-                Quat q; q.X = fa.x; q.Y = fa.y; q.Z = fa.z; q.W = fa.w;
-                if (k == 2) {
-                    const float4 fb = pb.keyValues[b];
-                    Quat e; e.X = fb.x; e.Y = fb.y; e.Z = fb.z; e.W = fb.w;
-                    const float t = (time - pb.keyTimes[a]) / (pb.keyTimes[b] - pb.keyTimes[a]);
-                    q = quat_slerp(q, e, t);
-                }
-                const Mat4 r = quat_to_matrix(q);
-                bool zero = true;                                       // SetLocalRotation ignores an all-zero matrix (node.go:906-912)
+        }
+        if (v.P) { px = v.px; py = v.py; pz = v.pz; }
+        if (v.S) { sx = v.sx; sy = v.sy; sz = v.sz; }
+        if (v.R) {
+            const Mat4 r = quat_to_matrix(v.q);
+            bool zero = true;                                           // SetLocalRotation ignores an all-zero matrix (node.go:906-912)
 #pragma unroll
-                for (int i = 0; i < 16; i++) zero = zero && (r.m[i >> 2][i & 3] == 0.0f);
-                if (!zero) rot = r;
-            }
+            for (int i = 0; i < 16; i++) zero = zero && (r.m[i >> 2][i & 3] == 0.0f);
+            if (!zero) rot = r;
         }
         // Node.Transform (node.go:577-579): Scale x rotation x Translate
         Mat4 t = m4_mult(m4_scale(sx, sy, sz), rot);

@@ -267,7 +267,16 @@ PYBIND11_MODULE(_host, m) {
         .def("Pause", &AnimationPlayer::Pause)
         .def("Resume", &AnimationPlayer::Resume)
         .def("LoopCount", [](AnimationPlayer& a) { return a.loopCount; })
-        .def("SampledPlayhead", [](AnimationPlayer& a) { return a.sampledPlayhead; });
+        .def("SampledPlayhead", [](AnimationPlayer& a) { return a.sampledPlayhead; })
+        .def("Blending", &AnimationPlayer::Blending)
+        .def("BlendStartIsBlend", &AnimationPlayer::BlendStartIsBlend)
+        .def("BlendFraction", &AnimationPlayer::BlendFraction)
+        .def("BlendFromPlayhead", [](AnimationPlayer& a) { return a.sampledFromPlayhead; })
+        .def("BlendFrom", [](AnimationPlayer& a) { return a.sampledFrom; })
+        .def("SetClock", [](AnimationPlayer& a, py::object fn) {      // time.Now() in milliseconds, for deterministic tests (None: the steady clock)
+            if (fn.is_none()) a.NowMs = nullptr;
+            else a.NowMs = [fn]() { py::gil_scoped_acquire g; return fn().cast<int64_t>(); };
+        });
     m.def("NewAnimationPlayer", [](std::shared_ptr<Node> n) { return std::make_shared<AnimationPlayer>(n); });
 
     py::class_<Model, Node, std::shared_ptr<Model>>(m, "Model")

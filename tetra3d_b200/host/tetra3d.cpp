@@ -10,6 +10,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <tuple>
 #include <unordered_map>
 
 namespace tetra3d {
@@ -412,17 +413,34 @@ std::shared_ptr<Skeleton> Skeleton::FromJoints(const std::vector<std::shared_ptr
     return sk;
 }
 
+int64_t AnimationPlayer::now() const {
+    if (NowMs) return NowMs();
+    return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void AnimationPlayer::Play(std::shared_ptr<Animation> anim) {                               // animation.go:517-566
     if (!anim) return;
     if (animation == anim && playing) return;
+    std::shared_ptr<Animation> previous = animation;
     animation = std::move(anim);
     playing = true;
     loopCount = 0;
     playhead = PlaySpeed > 0 ? 0.0f : animation->length;
+    if (BlendTime > 0) {                    // animation.go:548-554: prevAnimatedProperties = copy of currentProperties
+        prevHas = currentHas;
+        prevAnimation = currentHas ? previous : nullptr;
+        prevPlayhead_ = sampledPlayhead;
+        prevIsBlend = currentHas && currentIsBlend;
+        blendStarted = true;
+        blendStartMs = now();
+    }
+    // assignChannels (animation.go:618-672) runs at the next updateValues because ChannelsUpdated is false now, and clears currentProperties
+    currentHas = false; currentIsBlend = false;
 }
 
 void AnimationPlayer::Update(float dt) {                                                    // animation.go:810-824
     finished = false;
+    if (!playing && blendStarted) { blendStarted = false; prevHas = false; prevAnimation = nullptr; prevIsBlend = false; }
     forceUpdate(dt);
 }
 
@@ -430,6 +448,16 @@ void AnimationPlayer::forceUpdate(float dt) {                                   
     if (!animation) return;
     sampledPlayhead = playhead;             // the tracks are sampled here (animation.go:686-712): on the device, at the next Render
     sampled = true;
+    // the blend this frame's targets go through (animation.go:852-907); `prevExists` per node is the device's business
+    sampledBlending = false; sampledBlendUnsupported = false; sampledFrom = nullptr;
+    if (blendStarted && prevHas) {
+        float bp = (float)(now() - blendStartMs) / (BlendTime * 1000.0f);
+        if (bp > 1) bp = 1;
+        sampledBlending = true; sampledBlend = bp; sampledFrom = prevAnimation; sampledFromPlayhead = prevPlayhead_;
+        sampledBlendUnsupported = prevIsBlend;
+        if (bp == 1) { blendStarted = false; prevHas = false; prevAnimation = nullptr; prevIsBlend = false; }   // animation.go:899-902
+    }
+    if (BlendTime > 0) { currentHas = true; currentIsBlend = sampledBlending; }            // animation.go:909-937
     playhead += dt * PlaySpeed;
     float ph = playhead;
     prevPlayhead = ph;
@@ -819,37 +847,46 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         return id;
     };
     std::unordered_map<Model*, uint32_t> boneOffsets;
-    {   // armatures posed on the device: one t3d_submit_poses call per (skeleton, animation), in first-use order
-        struct Group { Skeleton* sk; uint64_t anim; std::vector<t3d_pose> poses; std::vector<Model*> models; };
+    {   // armatures posed on the device: one t3d_submit_poses[_blended] call per (skeleton, animation[, animation blended from]), in first-use order
+        struct Group { Skeleton* sk; uint64_t anim, from; bool blended; std::vector<t3d_pose> poses; std::vector<Model*> models; };
         std::vector<Group> groups;
-        std::map<std::pair<uint64_t, uint64_t>, size_t> groupOf;
+        std::map<std::tuple<uint64_t, uint64_t, uint64_t, bool>, size_t> groupOf;
         for (auto& pd : pending) {
             if (flushOwnerRank[pd.flush] != shardRank) continue;
             Model* model = pd.model;
             if (!model->skinned || !model->skeleton || boneOffsets.count(model)) continue;
             Skeleton& sk = *model->skeleton;
             device->ensureSkeleton(sk);
-            uint64_t anim = 0;
+            uint64_t anim = 0, from = 0; bool blended = false;
             t3d_pose P; std::memset(&P, 0, sizeof P);
             if (AnimationPlayer* ap = model->posePlayer.get()) {
                 if (ap->animation && ap->sampled) {
-                    if (ap->BlendTime > 0 || ap->animation->relativeMotion)
-                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer blending / relative motion (animation.go:850-907, 962-984) is not evaluated on the device");
+                    if (ap->animation->relativeMotion)
+                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer relative motion (animation.go:962-984) is not evaluated on the device");
+                    if (ap->sampledBlending && ap->sampledBlendUnsupported)
+                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer: a blend that starts from an unfinished blend (animation.go:905-908) is not evaluated on the device");
                     anim = device->ensureAnimation(*ap->animation, sk);
                     P.playhead = ap->sampledPlayhead;
+                    if (ap->sampledBlending) {
+                        blended = true;
+                        if (ap->sampledFrom) from = device->ensureAnimation(*ap->sampledFrom, sk);
+                        P.from_playhead = ap->sampledFromPlayhead;
+                        P.blend = ap->sampledBlend;
+                    }
                 }
             }
             m4_store(model->SkinRoot ? model->SkinRoot->Transform() : m4_identity(), P.root);
-            auto key = std::make_pair(sk.id, anim);
+            auto key = std::make_tuple(sk.id, anim, from, blended);
             auto it = groupOf.find(key);
-            if (it == groupOf.end()) { it = groupOf.emplace(key, groups.size()).first; groups.push_back(Group{&sk, anim, {}, {}}); }
+            if (it == groupOf.end()) { it = groupOf.emplace(key, groups.size()).first; groups.push_back(Group{&sk, anim, from, blended, {}, {}}); }
             Group& g = groups[it->second];
             g.poses.push_back(P); g.models.push_back(model);
             boneOffsets.emplace(model, 0u);        // filled in below
         }
         for (Group& g : groups) {
             uint32_t off = 0;
-            check(ctx, t3d_submit_poses(ctx, g.sk->id, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses");
+            if (g.blended) check(ctx, t3d_submit_poses_blended(ctx, g.sk->id, g.from, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses_blended");
+            else check(ctx, t3d_submit_poses(ctx, g.sk->id, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses");
             for (size_t i = 0; i < g.models.size(); i++) boneOffsets[g.models[i]] = off + (uint32_t)(i * g.sk->BoneCount());
         }
     }

@@ -10,6 +10,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -228,8 +229,13 @@ struct Skeleton {
 
 // AnimationPlayer (animation.go:437-480) for armatures whose bone poses are evaluated on the device: it keeps the
 // playhead logic of updateValues (animation.go:724-806) on the host and records the playhead the tracks were last
-// sampled at; the sampling itself, the bones' Transform() and boneInfluence run in k_pose_bones.  Blending
-// (BlendTime > 0), relative motion, markers and sequence callbacks need the host path and are refused.
+// sampled at; the sampling itself, the bones' Transform() and boneInfluence run in k_pose_bones.
+//
+// Blending (BlendTime > 0, animation.go:548-554, 852-907): the player also records what the reference's
+// prevAnimatedProperties would hold -- the previous animation and the playhead its tracks were last sampled at -- and the
+// blend fraction of the frame; Camera::Render ships such armatures through t3d_submit_poses_blended.  A Play() in the middle
+// of an unfinished blend starts from a blend *result*, which has no (animation, playhead) form: the player says so
+// (BlendStartIsBlend) and Render refuses it.  Relative motion, markers and sequence callbacks need the host path and are refused.
 struct AnimationPlayer {
     std::shared_ptr<Node> RootNode;
     std::shared_ptr<Animation> animation;
@@ -237,6 +243,20 @@ struct AnimationPlayer {
     bool playing = false, finished = false, justLooped = false, sampled = false;
     int loopCount = 0;
     float sampledPlayhead = 0;                  // the playhead updateValues evaluated the tracks at (animation.go:686-712)
+    // time.Now() in milliseconds (animation.go:553, 854); replaceable so that tests can step the clock
+    std::function<int64_t()> NowMs;
+    // ---- blend bookkeeping ----
+    bool blendStarted = false;                  // !blendStart.IsZero()
+    int64_t blendStartMs = 0;
+    bool prevHas = false;                       // prevAnimatedProperties is not empty
+    std::shared_ptr<Animation> prevAnimation;   // ... and holds this animation's targets
+    float prevPlayhead_ = 0;                    //     as sampled at this playhead
+    bool prevIsBlend = false;                   //     -- or a blend result, which has no such form
+    bool currentHas = false, currentIsBlend = false;    // currentProperties (animation.go:909-937): filled only while BlendTime > 0
+    // what the last forceUpdate applied, for Camera::Render
+    bool sampledBlending = false, sampledBlendUnsupported = false;
+    float sampledBlend = 0, sampledFromPlayhead = 0;
+    std::shared_ptr<Animation> sampledFrom;
     explicit AnimationPlayer(std::shared_ptr<Node> root) : RootNode(std::move(root)) {}
     void Play(std::shared_ptr<Animation> anim);         // animation.go:517-566
     void Update(float dt);                              // animation.go:810-824
@@ -247,6 +267,10 @@ struct AnimationPlayer {
     void Pause() { playing = false; }
     void Resume() { playing = true; }
     void forceUpdate(float dt);                         // animation.go:837 -> updateValues 674-806
+    bool Blending() const { return sampledBlending; }
+    bool BlendStartIsBlend() const { return sampledBlendUnsupported; }
+    float BlendFraction() const { return sampledBlend; }
+    int64_t now() const;
 };
 
 // ---- model.go -----------------------------------------------------------------------------------------

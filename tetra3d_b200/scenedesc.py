@@ -201,6 +201,17 @@ class PoseDesc:
     animation: Optional[AnimationDesc] = None
     playhead: float = 0.0
     root: NodeDesc = field(default_factory=NodeDesc)
+    # The player is in the middle of a blend (AnimationPlayer.BlendTime > 0, animation.go:548-554, 852-907): blend_ms
+    # milliseconds after Play(animation), coming from `blend_from` last sampled at from_playhead (None: nothing was animated).
+    blend_ms: Optional[int] = None
+    blend_time: float = 1.0
+    blend_from: Optional[AnimationDesc] = None
+    from_playhead: float = 0.0
+
+    def blend_fraction(self) -> float:
+        """bp of animation.go:854-857: float32(milliseconds) / (BlendTime * 1000), clamped to 1."""
+        bp = np.float32(int(self.blend_ms)) / (np.float32(self.blend_time) * np.float32(1000.0))
+        return float(min(bp, np.float32(1.0)))
 
 
 @dataclass(eq=False)
