@@ -386,6 +386,7 @@ def run_ours(args):
                          "note": "every rank's lists stay in its own HBM (no delivery to the issuing rank), max over ranks"}
 
     # ---- e2e through the public API with host buffers ----
+    # (a) one frame at a time: Camera.RenderScene returns with the lists complete in pinned host memory
     cam.DownloadResults = True
     for _ in range(3):
         cam.Clear(); cam.RenderScene(scene)
@@ -397,13 +398,45 @@ def run_ours(args):
         cam.RenderScene(scene)
         h2d, d2h = device.FrameBytes()
     barrier()
-    e2e_s = time.perf_counter() - e0
-    clocks = sampler.stop()      # sampled every 20 ms across both timed loops (device-resident + e2e)
+    sync_s = time.perf_counter() - e0
+    ts = torch.tensor([sync_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sync_ms = float(ts.item()) / args.steps * 1e3
+    # (b) two frames in flight (Camera.AsyncDownload): RenderScene(k) starts the copy of frame k's lists and returns; the loop
+    # consumes frame k - 1 (waits until ITS lists are complete in host memory) while that copy runs, as a game loop that hands frame
+    # k - 1 to DrawTriangles while frame k renders.  Every step still moves one full frame of lists over PCIe; the last frame's
+    # copy is inside the timed region.  This is the figure reported as `e2e.value`; (a) stays next to it.
+    e2e_s, frames_in_flight, async_note = sync_s, 1, None
+    try:
+        cam.AsyncDownload = True
+        for k in range(4):
+            cam.Clear(); cam.RenderScene(scene)
+            if k:
+                cam.WaitDownload(1)
+        cam.WaitDownload(0)
+        barrier()
+        e0 = time.perf_counter()
+        for k in range(args.steps):
+            cam.Clear()
+            cam.RenderScene(scene)
+            if k:
+                cam.WaitDownload(1)
+        cam.WaitDownload(0)
+        barrier()
+        e2e_s, frames_in_flight = time.perf_counter() - e0, 2
+        h2d, d2h = device.FrameBytes()
+    except Exception as e:      # the synchronous figure stands in
+        async_note = "two frames in flight failed (%s): e2e.value is the one-frame-at-a-time figure" % (repr(e)[:160],)
+    finally:
+        cam.AsyncDownload = False
+    clocks = sampler.stop()      # sampled every 20 ms across the timed loops (device-resident + e2e)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = tris_total * args.steps / float(te.item())
     e2e_ms = float(te.item()) / args.steps * 1e3
+    cam.Clear(); cam.RenderScene(scene)      # a synchronous frame for the parity check below
     if world == 1:
         flushes = cam.Flushes()
         col, dep = cam.ColorVertexList(), cam.DepthVertexList()
@@ -485,7 +518,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "d2h_gbs_all_ranks": d2h_gbs, "d2h_ceiling_gbs_all_ranks": ceil_total, "frac_of_d2h_ceiling": d2h_gbs / ceil_total if ceil_total else None,
                 "ceiling": "plain pinned cudaMemcpy device->host of 256 MiB, best of 5, every rank at the same time, summed",
-                "path": "Camera.RenderScene -> t3d_frame_begin/submit/execute/results (pinned H2D of uniforms, pinned D2H of colour+depth lists); meshes resident"},
+                "frames_in_flight": frames_in_flight,
+                "one_frame_at_a_time": {"value": tris_total / (sync_ms * 1e-3), "ms_per_step": sync_ms,
+                                        "frac_of_d2h_ceiling": (d2h * world / (sync_ms * 1e-3) / 1e9) / ceil_total if ceil_total else None},
+                **({"note": async_note} if async_note else {}),
+                "path": "Camera.RenderScene -> t3d_frame_begin/submit/execute/results (pinned H2D of uniforms, pinned D2H of colour+depth lists); meshes resident; "
+                        "two frames in flight: frame k's lists cross PCIe while frame k+1 is built and executed (t3d_set_async_download), the loop waits for frame k-1's lists every step"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "parity_check": parity,

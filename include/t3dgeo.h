@@ -387,6 +387,16 @@ int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings)
 /* Waits for the frame and returns DEVICE pointers (no D2H of the lists; `draws` is still host memory).
  * For device-resident consumers (NCCL gather, interop rasterisers). */
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
+/* Two frames in flight.  With this on, t3d_frame_results still waits for the frame's kernels and returns counts, per-draw
+ * results and list pointers, but only STARTS the device -> host copy of the lists (on a stream of its own, into one of two sets
+ * of pinned buffers; the kernels alternate between two sets of device lists likewise): the caller builds, submits and executes
+ * the next frame while the copy runs, and reads frame k's lists after t3d_frame_download_wait.  The pointers of frame k stay
+ * valid until t3d_frame_results of frame k + 2.  This is the order the reference's game loop allows: Camera.flush's
+ * DrawTriangles calls (camera.go:1829-2048) of frame k are issued while Camera.Render of frame k + 1 runs.
+ * Ignored (the lists are complete on return, as without it) for frames written to an output target or delivered to another rank. */
+int t3d_set_async_download(t3d_ctx* ctx, int enabled);
+/* Blocks until the lists of the last frame whose results were requested (frames_back = 0) or of the one before (1) have arrived. */
+int t3d_frame_download_wait(t3d_ctx* ctx, uint32_t frames_back);
 
 /* ---- output placement ------------------------------------------------------------------------------ */
 /* Makes the emit kernel write colorVertexList / depthVertexList / normalVertexList (tetra3d.go:21-23) into

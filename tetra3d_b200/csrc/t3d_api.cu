@@ -174,6 +174,16 @@ struct t3d_ctx {
     DevBuf dTdepth, dSorted, dHist, dTileSurv, dTileOut, dCount;
     DevBuf dTileCtr;        // k_vertex's tile counters (one per vertex-tile class), zeroed by k_prep_draws every frame
     DevBuf dColor, dDepth, dNormal, dTriIds;
+    // Two frames in flight (t3d_set_async_download): frame k's lists travel to the host on dlStream while frame k + 1 is built and
+    // executed, so frames alternate between two sets of device lists and of pinned host buffers (set 1 below; set 0 are the
+    // ordinary ones).  A set's device lists are not written again before its last copy has left them (a stream wait on
+    // evCopyDone), its host buffers not before that copy has arrived (t3d_frame_results of frame k + 2 waits for it).
+    bool asyncDownload = false;
+    uint32_t nextSet = 0, frameSet = 0, lastCopySet = 0;
+    bool copyPending[2] = {false, false};
+    DevBuf dColorB, dDepthB, dNormalB, dTriIdsB;
+    cudaStream_t dlStream = nullptr; cudaEvent_t evFrameDone = nullptr, evCopyDone[2] = {nullptr, nullptr};
+    uint32_t* oTriIds = nullptr;
     // external output target (t3d_set_output_target): the emit kernel writes the lists there -- another GPU's
     // memory over NVLink, or an interop buffer of the rasteriser -- instead of into dColor / dDepth / dNormal
     t3d_vertex *xColor = nullptr, *xDepth = nullptr, *xNormal = nullptr;
@@ -205,8 +215,8 @@ struct t3d_ctx {
     PinVec<DrawStat> hStats;
     PinVec<uint32_t> hCount;
     PinVec<t3d_draw_result> hResults;
-    PinVec<t3d_vertex> hColor, hDepth, hNormal;
-    PinVec<uint32_t> hTriIds;
+    PinVec<t3d_vertex> hColor, hDepth, hNormal, hColorB, hDepthB, hNormalB;
+    PinVec<uint32_t> hTriIds, hTriIdsB;
     PinVec<uint16_t> hIndex;
     uint64_t nVerticesOut = 0;
 
@@ -303,6 +313,12 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (float* c : ctx->volumeCells) if (c) cudaFree(c);
     for (uint32_t* c : ctx->volumeCsr) if (c) cudaFree(c);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); cudaEventDestroy(ctx->evFork); }
+    if (ctx->dlStream) {
+        cudaStreamSynchronize(ctx->dlStream); cudaStreamDestroy(ctx->dlStream);
+        cudaEventDestroy(ctx->evFrameDone); cudaEventDestroy(ctx->evCopyDone[0]); cudaEventDestroy(ctx->evCopyDone[1]);
+    }
+    ctx->dColorB.release(); ctx->dDepthB.release(); ctx->dNormalB.release(); ctx->dTriIdsB.release();
+    ctx->hColorB.release(); ctx->hDepthB.release(); ctx->hNormalB.release(); ctx->hTriIdsB.release();
     for (cudaEvent_t e : ctx->evChunk) cudaEventDestroy(e);
     for (auto& kv : ctx->skeletons) if (kv.second.block) cudaFree(kv.second.block);
     for (auto& kv : ctx->animations) if (kv.second.block) cudaFree(kv.second.block);
@@ -1187,15 +1203,23 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     if (external) {
         if (3ull * totalT > ctx->xCapacity) return fail(ctx, T3D_E_NOMEM, "t3d_frame_execute: the output target is smaller than the frame's worst case (3 vertices per submitted triangle)");
         if (normals && !ctx->xNormal) return fail(ctx, T3D_E_INVALID, "t3d_frame_execute: RenderNormals needs a normal list in the output target");
-    } else {
-        CU(ctx->dColor.ensure(144ull * totalT));
-        CU(ctx->dDepth.ensure(144ull * totalT));
-        CU(ctx->dNormal.ensure(normals ? 144ull * totalT : 16));
     }
-    ctx->oColor = external ? ctx->xColor : ctx->dColor.as<t3d_vertex>();
-    ctx->oDepth = external ? ctx->xDepth : ctx->dDepth.as<t3d_vertex>();
-    ctx->oNormal = external ? ctx->xNormal : ctx->dNormal.as<t3d_vertex>();
-    CU(ctx->dTriIds.ensure(4ull * totalT));
+    // which set of lists this frame writes: alternating while two frames are in flight, set 0 otherwise
+    const uint32_t set = (ctx->asyncDownload && !external && !ctx->gather.active) ? ctx->nextSet : 0u;
+    ctx->frameSet = set;
+    DevBuf &bColor = set ? ctx->dColorB : ctx->dColor, &bDepth = set ? ctx->dDepthB : ctx->dDepth, &bNormal = set ? ctx->dNormalB : ctx->dNormal,
+           &bTriIds = set ? ctx->dTriIdsB : ctx->dTriIds;
+    if (!external) {
+        CU(bColor.ensure(144ull * totalT));
+        CU(bDepth.ensure(144ull * totalT));
+        CU(bNormal.ensure(normals ? 144ull * totalT : 16));
+    }
+    ctx->oColor = external ? ctx->xColor : bColor.as<t3d_vertex>();
+    ctx->oDepth = external ? ctx->xDepth : bDepth.as<t3d_vertex>();
+    ctx->oNormal = external ? ctx->xNormal : bNormal.as<t3d_vertex>();
+    CU(bTriIds.ensure(4ull * totalT));
+    ctx->oTriIds = bTriIds.as<uint32_t>();
+    if (ctx->copyPending[set]) CU(cudaStreamWaitEvent(s, ctx->evCopyDone[set], 0));     // the set's previous lists are still leaving: the kernels queue up behind that copy
     if (ctx->volumesDirty) {
         CU(ctx->dVolumes.ensure(sizeof(VolumeU) * std::max<size_t>(ctx->volumes.size(), 1)));
         if (!ctx->volumes.empty())
@@ -1514,7 +1538,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         uint8_t* in = G.inbox(G.rank);
         launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                     ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
-                    reinterpret_cast<float4*>(in), reinterpret_cast<float4*>(in + G.cap * 32), nullptr, ctx->dTriIds.as<uint32_t>(), true,
+                    reinterpret_cast<float4*>(in), reinterpret_cast<float4*>(in + G.cap * 32), nullptr, ctx->oTriIds, true,
                     reinterpret_cast<float*>(in + G.cap * 36), offerIndexed ? totalV : 0u, nScanChunks);
         // the indexed form (one record per arena vertex + a slot per emitted corner); each of the three kernels decides on the
         // device, from the survivor total, which form this frame takes, and the other form's kernels return at once
@@ -1522,7 +1546,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             launch_emit_indexed(s, pdl, ctx->pDraws, ctx->pVbase, nDraws, totalV, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(),
                                 ctx->dTileOut.as<uint32_t>(), ctx->dCount.as<uint32_t>(), nScanChunks, ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(),
                                 ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), reinterpret_cast<float4*>(in), reinterpret_cast<float*>(in + G.cap * 32),
-                                reinterpret_cast<float*>(in + G.cap * 36), reinterpret_cast<uint32_t*>(in + G.cap * 40), ctx->dTriIds.as<uint32_t>());
+                                reinterpret_cast<float*>(in + G.cap * 36), reinterpret_cast<uint32_t*>(in + G.cap * 40), ctx->oTriIds);
             ctx->launches += 2;
         }
         ctx->launches += 1;
@@ -1530,7 +1554,7 @@ int t3d_frame_execute(t3d_ctx* ctx) {
         launch_emit(s, pdl, ctx->pDraws, ctx->pTiles, nTiles, ctx->dSorted.as<uint32_t>(), ctx->dTileSurv.as<uint32_t>(), ctx->dTileOut.as<uint32_t>(),
                     ctx->dCount.as<uint32_t>(), ctx->fc, ctx->dClip.as<float4>(), ctx->dClipXY.as<float2>(), ctx->dLight.as<float4>(), ctx->dUnbill.as<float>(), ctx->dTnrm.as<float4>(),
                     reinterpret_cast<float4*>(ctx->oColor), reinterpret_cast<float4*>(ctx->oDepth),
-                    normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->dTriIds.as<uint32_t>(), false, nullptr, 0u, 0u);
+                    normals ? reinterpret_cast<float4*>(ctx->oNormal) : nullptr, ctx->oTriIds, false, nullptr, 0u, 0u);
     }
     ctx->launches += nTiles ? 1 : 0;
     CU(cudaEventRecord(ctx->ev[9], s));
@@ -1623,27 +1647,49 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     if (download && compactDepth)
         return fail(ctx, T3D_E_STATE, "t3d_frame_results: this rank's lists were delivered to the issuing rank (t3d_gather_attach); use t3d_frame_results_device here and t3d_gather_results there");
     if (download) {
+        const uint32_t set = ctx->frameSet;
+        const bool async = ctx->asyncDownload && !ctx->gather.active && !ctx->xColor;
+        PinVec<t3d_vertex> &hC = set ? ctx->hColorB : ctx->hColor, &hD = set ? ctx->hDepthB : ctx->hDepth, &hN = set ? ctx->hNormalB : ctx->hNormal;
+        PinVec<uint32_t>& hT = set ? ctx->hTriIdsB : ctx->hTriIds;
+        // this set's host buffers are about to be resized and overwritten: its previous copy (two frames ago) has to have arrived
+        if (ctx->copyPending[set]) { CU(cudaEventSynchronize(ctx->evCopyDone[set])); ctx->copyPending[set] = false; }
         if (nVerts) {
             cudaEvent_t e0 = ctx->ev[7], e1 = ctx->ev[8];
-            CU(ctx->hColor.resize(nVerts)); CU(ctx->hDepth.resize(nVerts)); CU(ctx->hTriIds.resize(nVerts / 3));
-            if (normals) CU(ctx->hNormal.resize(nVerts));
-            CU(cudaEventRecord(e0, s));
-            CU(cudaMemcpyAsync(ctx->hColor.p, ctx->oColor, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(ctx->hDepth.p, ctx->oDepth, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
-            if (normals) CU(cudaMemcpyAsync(ctx->hNormal.p, ctx->oNormal, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(ctx->hTriIds.p, ctx->dTriIds.p, (nVerts / 3) * 4, cudaMemcpyDeviceToHost, s));
-            CU(cudaEventRecord(e1, s));
-            CU(cudaStreamSynchronize(s));
-            cudaEventElapsedTime(&ctx->downloadMs, e0, e1);
+            CU(hC.resize(nVerts)); CU(hD.resize(nVerts)); CU(hT.resize(nVerts / 3));
+            if (normals) CU(hN.resize(nVerts));
+            cudaStream_t cs = s;
+            if (async) {        // the copies run on a stream of their own, behind the frame; the caller goes on to the next frame
+                if (!ctx->dlStream) {
+                    CU(cudaStreamCreateWithFlags(&ctx->dlStream, cudaStreamNonBlocking));
+                    CU(cudaEventCreateWithFlags(&ctx->evFrameDone, cudaEventDisableTiming));
+                    CU(cudaEventCreateWithFlags(&ctx->evCopyDone[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ctx->evCopyDone[1], cudaEventDisableTiming));
+                }
+                cs = ctx->dlStream;
+                CU(cudaEventRecord(ctx->evFrameDone, s));
+                CU(cudaStreamWaitEvent(cs, ctx->evFrameDone, 0));
+            } else CU(cudaEventRecord(e0, s));
+            CU(cudaMemcpyAsync(hC.p, ctx->oColor, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
+            CU(cudaMemcpyAsync(hD.p, ctx->oDepth, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
+            if (normals) CU(cudaMemcpyAsync(hN.p, ctx->oNormal, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
+            CU(cudaMemcpyAsync(hT.p, ctx->oTriIds, (nVerts / 3) * 4, cudaMemcpyDeviceToHost, cs));
+            if (async) {
+                CU(cudaEventRecord(ctx->evCopyDone[set], cs));
+                ctx->copyPending[set] = true;
+            } else {
+                CU(cudaEventRecord(e1, s));
+                CU(cudaStreamSynchronize(s));
+                cudaEventElapsedTime(&ctx->downloadMs, e0, e1);
+            }
             ctx->d2hBytes += nVerts * sizeof(t3d_vertex) * (normals ? 3 : 2) + (nVerts / 3) * 4;
         }
-        out->color_list = ctx->hColor.p; out->depth_list = ctx->hDepth.p;
-        out->normal_list = normals ? ctx->hNormal.p : nullptr;
-        out->tri_ids = ctx->hTriIds.p;
+        if (async) { ctx->lastCopySet = set; ctx->nextSet = set ^ 1u; }
+        out->color_list = hC.p; out->depth_list = hD.p;
+        out->normal_list = normals ? hN.p : nullptr;
+        out->tri_ids = hT.p;
     } else {
         out->color_list = compactDepth ? nullptr : ctx->oColor; out->depth_list = compactDepth ? nullptr : ctx->oDepth;
         out->normal_list = normals ? ctx->oNormal : nullptr;
-        out->tri_ids = ctx->dTriIds.as<uint32_t>();
+        out->tri_ids = ctx->oTriIds;
     }
     if (tm) {
         memset(tm, 0, sizeof *tm);
@@ -1665,6 +1711,29 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
 
 int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, true, out, timings); }
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, false, out, timings); }
+
+int t3d_set_async_download(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    if (!enabled && ctx->asyncDownload) {       // drain: nothing may still be in flight when the ordinary set is used again
+        CU(cudaSetDevice(ctx->device));
+        for (int k = 0; k < 2; k++) if (ctx->copyPending[k]) { CU(cudaEventSynchronize(ctx->evCopyDone[k])); ctx->copyPending[k] = false; }
+        ctx->nextSet = 0;
+    }
+    ctx->asyncDownload = enabled != 0;
+    return T3D_OK;
+}
+
+int t3d_frame_download_wait(t3d_ctx* ctx, uint32_t frames_back) {
+    if (!ctx) return T3D_E_INVALID;
+    if (frames_back > 1) return fail(ctx, T3D_E_INVALID, "t3d_frame_download_wait: only the last two frames' lists exist");
+    const uint32_t set = frames_back ? ctx->lastCopySet ^ 1u : ctx->lastCopySet;
+    if (ctx->copyPending[set]) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventSynchronize(ctx->evCopyDone[set]));
+        ctx->copyPending[set] = false;
+    }
+    return T3D_OK;
+}
 
 // ---- introspection ---------------------------------------------------------------------------------
 

@@ -418,6 +418,8 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("DepthMargin", &Camera::DepthMargin)
         .def_readwrite("Device", &Camera::device)
         .def_readwrite("DownloadResults", &Camera::downloadResults)
+        .def_readwrite("AsyncDownload", &Camera::AsyncDownload)
+        .def("WaitDownload", [](Camera& c, int framesBack) { py::gil_scoped_release rel; c.WaitDownload(framesBack); }, py::arg("frames_back") = 0)
         .def_readwrite("UseInstancing", &Camera::UseInstancing)
         .def_readwrite("DeviceFrustumCulling", &Camera::DeviceFrustumCulling)
         .def_readwrite("MaxLightCount", &Camera::MaxLightCount)
@@ -435,9 +437,10 @@ PYBIND11_MODULE(_host, m) {
         .def("Clear", &Camera::Clear)
         .def("RenderScene", [](Camera& c, Scene& s) { py::gil_scoped_release rel; c.RenderScene(s); })
         .def("RenderNodes", [](Camera& c, Scene& s, Node& root) { py::gil_scoped_release rel; c.RenderNodes(s, root); })
-        .def("ColorVertexList", [](Camera& c) { return vertex_list(c.output.color_list, c.output.n_vertices, !c.downloadResults); })
-        .def("DepthVertexList", [](Camera& c) { return vertex_list(c.output.depth_list, c.output.n_vertices, !c.downloadResults); })
-        .def("NormalVertexList", [](Camera& c) { return vertex_list(c.output.normal_list, c.output.normal_list ? c.output.n_vertices : 0, !c.downloadResults); })
+        // frames_back = 1: the lists of the Render before the last one (AsyncDownload keeps them valid for one more frame)
+        .def("ColorVertexList", [](Camera& c, int fb) { c.WaitDownload(fb); const t3d_frame_output& o = fb ? c.prevOutput : c.output; return vertex_list(o.color_list, o.n_vertices, !c.downloadResults); }, py::arg("frames_back") = 0)
+        .def("DepthVertexList", [](Camera& c, int fb) { c.WaitDownload(fb); const t3d_frame_output& o = fb ? c.prevOutput : c.output; return vertex_list(o.depth_list, o.n_vertices, !c.downloadResults); }, py::arg("frames_back") = 0)
+        .def("NormalVertexList", [](Camera& c, int fb) { c.WaitDownload(fb); const t3d_frame_output& o = fb ? c.prevOutput : c.output; return vertex_list(o.normal_list, o.normal_list ? o.n_vertices : 0, !c.downloadResults); }, py::arg("frames_back") = 0)
         .def("IndexList", [](Camera& c, uint64_t n) {
             py::array_t<uint16_t> a((py::ssize_t)n);
             for (uint64_t i = 0; i < n; i++) a.mutable_data()[i] = c.output.index_list ? c.output.index_list[i] : (uint16_t)i;
@@ -445,6 +448,7 @@ PYBIND11_MODULE(_host, m) {
         })
         .def("TriangleIDs", [](Camera& c) {
             if (!c.downloadResults) throw std::runtime_error("lists are device-resident");
+            c.WaitDownload(0);
             py::array_t<uint32_t> a((py::ssize_t)(c.output.n_vertices / 3));
             if (c.output.n_vertices) std::memcpy(a.mutable_data(), c.output.tri_ids, (c.output.n_vertices / 3) * 4);
             return a;

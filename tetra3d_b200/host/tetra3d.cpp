@@ -499,6 +499,11 @@ std::vector<int> AssignFlushesToRanks(const std::vector<uint64_t>& flushTris, in
 // ---- Camera -------------------------------------------------------------------------------------------
 Camera::Camera(const std::string& n, int w, int h) : Node(n), width(w), height(h) {}
 
+void Camera::WaitDownload(int framesBack) {
+    if (!device) return;
+    check(device->ctx, t3d_frame_download_wait(device->ctx, (uint32_t)framesBack), "t3d_frame_download_wait");
+}
+
 Matrix4 Camera::ViewMatrix() {                                            // camera.go:638-648
     Vector3 camPos = v3_invert(WorldPosition());
     Matrix4 transform = NewMatrix4Translate(camPos.X, camPos.Y, camPos.Z);
@@ -830,6 +835,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         tw.fog_range[0] = world->FogRange[0]; tw.fog_range[1] = world->FogRange[1];
     }
     device->frameSerial++;
+    check(ctx, t3d_set_async_download(ctx, AsyncDownload && downloadResults), "t3d_set_async_download");
     check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
     // anything that throws before the frame is executed (an unsupported draw, a failed upload) must not leave the frame open
     struct FrameGuard { t3d_ctx* c; bool armed; ~FrameGuard() { if (armed) t3d_frame_abort(c); } } frameGuard{ctx, true};
@@ -1037,6 +1043,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     check(ctx, t3d_frame_execute(ctx), "t3d_frame_execute");
     frameGuard.armed = false;
     lap("t3d_frame_execute");
+    prevOutput = output;
     if (downloadResults) check(ctx, t3d_frame_results(ctx, &output, &timings), "t3d_frame_results");
     else check(ctx, t3d_frame_results_device(ctx, &output, &timings), "t3d_frame_results_device");
     launchCount = t3d_debug_last_launch_count(ctx);

@@ -388,6 +388,11 @@ struct Camera : Node {
     void Render(Scene& scene, const std::vector<ILight*>& lights, const std::vector<Model*>& models);   // camera.go:1269
     // when false the lists stay on the device (t3d_frame_results_device)
     bool downloadResults = true;
+    // Two frames in flight (t3d_set_async_download): Render returns once the frame's kernels are done and the lists' copy to the
+    // host has been STARTED; the game loop goes on to the next frame and calls WaitDownload(1) before it hands the previous frame's
+    // lists to DrawTriangles (camera.go:1829-2048), or WaitDownload(0) for the frame just rendered.
+    bool AsyncDownload = false;
+    void WaitDownload(int framesBack = 0);
     // runs of Models that differ only in position, scale and colour are submitted with t3d_submit_instances (the device
     // evaluates their Node.Transform); false: every render(rp) is a t3d_draw carrying its matrix
     bool UseInstancing = true;
@@ -397,6 +402,7 @@ struct Camera : Node {
 
     // results of the last Render (library-owned memory, valid until the next Render)
     t3d_frame_output output{};
+    t3d_frame_output prevOutput{};      // the Render before (AsyncDownload: its lists stay valid until the next Render's results)
     t3d_timings timings{};
     std::vector<RenderRecord> renders;
     std::vector<FlushRecord> flushes;
