@@ -55,6 +55,50 @@ def scenes():
     nodepth = glb.load_glb(light, camera=look_from((2.0, 14.0, 34.0), pitch_deg=-22.0, far=200.0, field_of_view=55.0, render_depth=False),
                            animation_for={"Armature": "ArmatureAction"}, playheads={"Armature": 0.0}, name="lighting_nodepth")
     out["lighting_nodepth"] = nodepth          # RenderDepth off: the solids are sorted by distance (camera.go:1460-1469)
+    out.update(example_scenes())
+    return out
+
+
+# Every other GLB under /root/reference/examples, each once: with the file's own camera when it sees something, else framed from
+# the scene's bounds.  What they add over the two files above: vertex colours and several materials per mesh (shapes, baking,
+# blendmodes), transparent / alpha-clip materials with render orders (transparency, blendmodes), orthographic file cameras
+# (orthographic), 50-model scenes (animatedTextures, autobatch), a 2-D skinned sprite (skeletal2d), world / fog settings exported
+# from Blender (worlds), sun + point + cube-light mixes (baking, rays, sectors).
+EXAMPLES = ["3dSprite/assets/scene.glb", "animatedTextures/assets/animatedTextures.glb", "animation_queueing/assets/anim_queueing.glb",
+            "autoBatch/autobatch.glb", "baking/assets/baking.glb", "blendmodes/blendmodes.glb", "cameraTest/cameraTest.glb",
+            "collections/assets/collections.glb", "collections/assets/cone.glb", "colliders/colliders.glb", "engine/engine.glb",
+            "grids/grids.glb", "grids2/grids.glb", "lightgroups/lighting.glb", "lightvolume/lightvolume.glb", "offscreen/offscreen.glb",
+            "orthographic/orthographic.glb", "particles/particles.glb", "paths/paths.glb", "properties/properties.glb", "rays/rays.glb",
+            "sectors/sectors.glb", "shapes/shapes.glb", "skeletal2d/skeletal2d.glb", "text/text.glb", "transparency/transparency.glb",
+            "vertexSelection/vertexSelection.glb", "worlds/worlds.glb"]
+
+
+def frame_camera(sc):
+    """A camera that sees the whole scene: above and in front of the bounds of every model's world-space vertices."""
+    from oracle import binding as O
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for m in sc.models:
+        w = O.node_world_transform(m.node).reshape(4, 4).astype(np.float64)
+        p = np.concatenate([m.mesh.positions.astype(np.float64), np.ones((len(m.mesh.positions), 1))], axis=1) @ w
+        lo, hi = np.minimum(lo, p[:, :3].min(axis=0)), np.maximum(hi, p[:, :3].max(axis=0))
+    c, r = (lo + hi) / 2, max(float(np.linalg.norm(hi - lo)) / 2, 1.0)
+    pos = np.round(c + np.array([0.15 * r, 0.6 * r, 1.5 * r]), 2)
+    d = c - pos
+    pitch = np.degrees(np.arctan2(d[1], np.hypot(d[0], d[2])))
+    yaw = np.degrees(np.arctan2(-d[0], -d[2]))
+    return look_from(pos, pitch_deg=round(float(pitch), 1), yaw_deg=round(float(-yaw), 1), far=float(np.ceil(4 * r + 10)))
+
+
+def example_scenes():
+    from oracle import binding as O
+    out = {}
+    for rel in EXAMPLES:
+        name = "ex_" + rel.split("/")[0].lower() + ("_" + os.path.basename(rel)[:-4].lower() if rel.startswith("collections") else "")
+        data = open(os.path.join(REF, rel), "rb").read()
+        sc = glb.load_glb(data, name=name)
+        if O.render_scene(sc).n_vertices < 3 * max(sc.total_triangles() // 20, 1):       # the file's camera (or the default) sees next to nothing
+            sc = glb.load_glb(data, camera=frame_camera(sc), name=name)
+        out[name] = sc
     return out
 
 

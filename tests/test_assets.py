@@ -1,8 +1,10 @@
 """The reference's own example assets as parity inputs.
 
-tests/golden/assets/*.pkl.gz are SceneDescs built from /root/reference/examples/{animation,lighting}/assets/*.glb by
-tests/golden/make_asset_fixtures.py through tetra3d_b200.glb (gltf.go's load rules): real skins with the influences the loader
-keeps, morph targets, an 18-channel armature animation, KHR_lights_punctual lights, the exporter's world / camera settings.
+tests/golden/assets/*.pkl.gz are SceneDescs built from /root/reference/examples/{animation,lighting}/assets/*.glb -- and, as
+ex_*.pkl.gz, from every other GLB under /root/reference/examples (28 files: shapes, transparency, blendmodes, baking, orthographic,
+skeletal2d, worlds, ...) -- by tests/golden/make_asset_fixtures.py through tetra3d_b200.glb (gltf.go's load rules): real skins
+with the influences the loader keeps, morph targets, an 18-channel armature animation, KHR_lights_punctual lights, vertex colours,
+several materials per mesh, transparent materials, the exporter's world / camera settings.
 CPU: the oracle reproduces the committed digests, and (where /root/reference exists) the loader reproduces the fixtures.
 GPU: the CUDA path against the oracle on the same inputs, bit for bit."""
 import gzip
