@@ -387,6 +387,11 @@ int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings)
 /* Waits for the frame and returns DEVICE pointers (no D2H of the lists; `draws` is still host memory).
  * For device-resident consumers (NCCL gather, interop rasterisers). */
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings);
+/* With this on, t3d_frame_results of a frame whose camera has T3D_CAM_RENDER_DEPTH off does not copy the depth list to the host
+ * and returns depth_list = NULL: Camera.flush only draws it when RenderDepth is on (camera.go:1880-1934), and without RenderDepth
+ * the reference's depthVertexList holds positions and the colours of an earlier frame (camera.go:1681-1708 vs 1744-1782).  Halves
+ * the bytes such a frame moves over PCIe.  Off by default (both lists always come back). */
+int t3d_set_skip_unused_depth_list(t3d_ctx* ctx, int enabled);
 /* Two frames in flight.  With this on, t3d_frame_results still waits for the frame's kernels and returns counts, per-draw
  * results and list pointers, but only STARTS the device -> host copy of the lists (on a stream of its own, into one of two sets
  * of pinned buffers; the kernels alternate between two sets of device lists likewise): the caller builds, submits and executes

@@ -93,3 +93,24 @@ def test_async_download_api(device):
     assert lib.t3d_set_async_download(ctx, 0) == 0
     assert lib.t3d_set_async_download(None, 1) == -1
     lib.t3d_destroy(ctx)
+
+
+def test_depth_list_is_not_copied_when_render_depth_is_off(device):
+    from tetra3d_b200.scenedesc import CameraDesc, WorldDesc
+    desc = scenes.soup_scene(7, cam=CameraDesc(render_depth=False), world=WorldDesc(fog_mode=0, fog_color=(0.3, 0.2, 0.1, 1), fog_range=(0.1, 0.9)))
+    scene, cam, _ = t3d.build_scene(desc, device)
+    cam.Clear(); cam.RenderScene(scene)
+    col, dep = cam.ColorVertexList().copy(), cam.DepthVertexList()
+    _, d2h_full = device.FrameBytes()
+    assert len(dep) == len(col) > 0
+    cam.SkipUnusedDepthList = True
+    cam.Clear(); cam.RenderScene(scene)
+    _, d2h_skip = device.FrameBytes()
+    assert np.array_equal(bits(cam.ColorVertexList()), bits(col)) and len(cam.DepthVertexList()) == 0
+    assert d2h_full - d2h_skip == 48 * len(col)
+    # a camera that renders depth is not affected by the switch
+    desc2 = scenes.soup_scene(7)
+    scene2, cam2, _ = t3d.build_scene(desc2, device)
+    cam2.SkipUnusedDepthList = True
+    cam2.Clear(); cam2.RenderScene(scene2)
+    assert len(cam2.DepthVertexList()) == len(cam2.ColorVertexList()) > 0

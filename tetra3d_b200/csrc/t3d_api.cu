@@ -179,6 +179,7 @@ struct t3d_ctx {
     // ordinary ones).  A set's device lists are not written again before its last copy has left them (a stream wait on
     // evCopyDone), its host buffers not before that copy has arrived (t3d_frame_results of frame k + 2 waits for it).
     bool asyncDownload = false;
+    bool skipUnusedDepth = false;       // t3d_set_skip_unused_depth_list: no D2H of the depth list when Camera.RenderDepth is off
     uint32_t nextSet = 0, frameSet = 0, lastCopySet = 0;
     bool copyPending[2] = {false, false};
     DevBuf dColorB, dDepthB, dNormalB, dTriIdsB;
@@ -1651,11 +1652,14 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
         const bool async = ctx->asyncDownload && !ctx->gather.active && !ctx->xColor;
         PinVec<t3d_vertex> &hC = set ? ctx->hColorB : ctx->hColor, &hD = set ? ctx->hDepthB : ctx->hDepth, &hN = set ? ctx->hNormalB : ctx->hNormal;
         PinVec<uint32_t>& hT = set ? ctx->hTriIdsB : ctx->hTriIds;
+        // flush() draws the depth list only when Camera.RenderDepth is on (camera.go:1880-1934); without it the list holds positions
+        // and stale colours that nothing reads
+        const bool wantDepth = !ctx->skipUnusedDepth || (ctx->fc.camFlags & T3D_CAM_RENDER_DEPTH);
         // this set's host buffers are about to be resized and overwritten: its previous copy (two frames ago) has to have arrived
         if (ctx->copyPending[set]) { CU(cudaEventSynchronize(ctx->evCopyDone[set])); ctx->copyPending[set] = false; }
         if (nVerts) {
             cudaEvent_t e0 = ctx->ev[7], e1 = ctx->ev[8];
-            CU(hC.resize(nVerts)); CU(hD.resize(nVerts)); CU(hT.resize(nVerts / 3));
+            CU(hC.resize(nVerts)); if (wantDepth) CU(hD.resize(nVerts)); CU(hT.resize(nVerts / 3));
             if (normals) CU(hN.resize(nVerts));
             cudaStream_t cs = s;
             if (async) {        // the copies run on a stream of their own, behind the frame; the caller goes on to the next frame
@@ -1669,7 +1673,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
                 CU(cudaStreamWaitEvent(cs, ctx->evFrameDone, 0));
             } else CU(cudaEventRecord(e0, s));
             CU(cudaMemcpyAsync(hC.p, ctx->oColor, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
-            CU(cudaMemcpyAsync(hD.p, ctx->oDepth, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
+            if (wantDepth) CU(cudaMemcpyAsync(hD.p, ctx->oDepth, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
             if (normals) CU(cudaMemcpyAsync(hN.p, ctx->oNormal, nVerts * sizeof(t3d_vertex), cudaMemcpyDeviceToHost, cs));
             CU(cudaMemcpyAsync(hT.p, ctx->oTriIds, (nVerts / 3) * 4, cudaMemcpyDeviceToHost, cs));
             if (async) {
@@ -1680,10 +1684,10 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
                 CU(cudaStreamSynchronize(s));
                 cudaEventElapsedTime(&ctx->downloadMs, e0, e1);
             }
-            ctx->d2hBytes += nVerts * sizeof(t3d_vertex) * (normals ? 3 : 2) + (nVerts / 3) * 4;
+            ctx->d2hBytes += nVerts * sizeof(t3d_vertex) * ((normals ? 2 : 1) + (wantDepth ? 1 : 0)) + (nVerts / 3) * 4;
         }
         if (async) { ctx->lastCopySet = set; ctx->nextSet = set ^ 1u; }
-        out->color_list = hC.p; out->depth_list = hD.p;
+        out->color_list = hC.p; out->depth_list = wantDepth ? hD.p : nullptr;
         out->normal_list = normals ? hN.p : nullptr;
         out->tri_ids = hT.p;
     } else {
@@ -1711,6 +1715,12 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
 
 int t3d_frame_results(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, true, out, timings); }
 int t3d_frame_results_device(t3d_ctx* ctx, t3d_frame_output* out, t3d_timings* timings) { return finish_frame(ctx, false, out, timings); }
+
+int t3d_set_skip_unused_depth_list(t3d_ctx* ctx, int enabled) {
+    if (!ctx) return T3D_E_INVALID;
+    ctx->skipUnusedDepth = enabled != 0;
+    return T3D_OK;
+}
 
 int t3d_set_async_download(t3d_ctx* ctx, int enabled) {
     if (!ctx) return T3D_E_INVALID;

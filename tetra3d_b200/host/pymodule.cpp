@@ -34,6 +34,7 @@ template <class T> static std::vector<T> vec_from(const py::array_t<T, py::array
 // numpy view over library-owned vertex lists (copied: the memory dies at the next Render)
 static py::array vertex_list(const t3d_vertex* p, uint64_t n, bool onDevice) {
     if (onDevice) throw std::runtime_error("lists are device-resident (downloadResults=False); use DevicePointers()");
+    if (!p) n = 0;          // a list the frame did not produce (normals off; depth skipped with RenderDepth off)
     farr a({(py::ssize_t)n, (py::ssize_t)12});
     if (n && p) std::memcpy(a.mutable_data(), p, n * sizeof(t3d_vertex));
     return a;
@@ -419,6 +420,7 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("Device", &Camera::device)
         .def_readwrite("DownloadResults", &Camera::downloadResults)
         .def_readwrite("AsyncDownload", &Camera::AsyncDownload)
+        .def_readwrite("SkipUnusedDepthList", &Camera::SkipUnusedDepthList)
         .def("WaitDownload", [](Camera& c, int framesBack) { py::gil_scoped_release rel; c.WaitDownload(framesBack); }, py::arg("frames_back") = 0)
         .def_readwrite("UseInstancing", &Camera::UseInstancing)
         .def_readwrite("DeviceFrustumCulling", &Camera::DeviceFrustumCulling)

@@ -836,6 +836,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     }
     device->frameSerial++;
     check(ctx, t3d_set_async_download(ctx, AsyncDownload && downloadResults), "t3d_set_async_download");
+    check(ctx, t3d_set_skip_unused_depth_list(ctx, SkipUnusedDepthList), "t3d_set_skip_unused_depth_list");
     check(ctx, t3d_frame_begin(ctx, &cam, &tw), "t3d_frame_begin");
     // anything that throws before the frame is executed (an unsupported draw, a failed upload) must not leave the frame open
     struct FrameGuard { t3d_ctx* c; bool armed; ~FrameGuard() { if (armed) t3d_frame_abort(c); } } frameGuard{ctx, true};

@@ -392,6 +392,8 @@ struct Camera : Node {
     // host has been STARTED; the game loop goes on to the next frame and calls WaitDownload(1) before it hands the previous frame's
     // lists to DrawTriangles (camera.go:1829-2048), or WaitDownload(0) for the frame just rendered.
     bool AsyncDownload = false;
+    // t3d_set_skip_unused_depth_list: with RenderDepth off the depth list is not copied to the host (flush never draws it then)
+    bool SkipUnusedDepthList = false;
     void WaitDownload(int framesBack = 0);
     // runs of Models that differ only in position, scale and colour are submitted with t3d_submit_instances (the device
     // evaluates their Node.Transform); false: every render(rp) is a t3d_draw carrying its matrix
