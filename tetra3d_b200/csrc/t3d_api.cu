@@ -1579,6 +1579,18 @@ int t3d_frame_execute(t3d_ctx* ctx) {
     return T3D_OK;
 }
 
+// Per-draw statistics and scan totals stored straight into pinned host memory by the SMs.  With two frames in flight the copy
+// engine is busy with the previous frame's lists for milliseconds, and a small cudaMemcpyAsync of this frame's statistics would
+// queue behind them -- t3d_frame_results would then return only after the previous frame's lists had arrived, and the next copy
+// could not follow the previous one without a gap.
+__global__ void __launch_bounds__(256)
+k_publish_stats(const uint4* __restrict__ stats, uint32_t nDraws, const uint32_t* __restrict__ count, uint32_t nChunks,
+                uint4* __restrict__ hostStats, uint32_t* __restrict__ hostCount) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < nDraws) hostStats[i] = stats[i];
+    if (i < nChunks) hostCount[i] = count[i];
+}
+
 static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_timings* tm) {
     if (!ctx || !out) return fail(ctx, T3D_E_INVALID, "t3d_frame_results: NULL argument");
     if (!ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_frame_results: frame not executed");
@@ -1595,11 +1607,21 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     ctx->d2hBytes = 0;
     uint64_t nVerts = 0;
     if (nDraws && totalT) {
+        ctx->hStats.mapped = true; ctx->hCount.mapped = true;       // k_publish_stats stores into them
         CU(ctx->hStats.resize(nDraws));
         const uint32_t nChunks = ((uint32_t)ctx->hTiles.n + SCAN_CHUNK - 1) / SCAN_CHUNK;
         CU(ctx->hCount.resize(std::max(nChunks, 1u)));
-        CU(cudaMemcpyAsync(ctx->hStats.p, ctx->dStats.p, sizeof(DrawStat) * nDraws, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(ctx->hCount.p, ctx->dCount.p, 4ull * std::max(nChunks, 1u), cudaMemcpyDeviceToHost, s));
+        if (ctx->asyncDownload && (ctx->copyPending[0] || ctx->copyPending[1])) {
+            static_assert(sizeof(DrawStat) == sizeof(uint4), "k_publish_stats moves a DrawStat as one 16-byte word");
+            const uint32_t nc = std::max(nChunks, 1u), n = std::max(nDraws, nc);
+            k_publish_stats<<<(n + 255) / 256, 256, 0, s>>>(ctx->dStats.as<uint4>(), nDraws, ctx->dCount.as<uint32_t>(), nc,
+                                                          reinterpret_cast<uint4*>(ctx->hStats.p), ctx->hCount.p);
+            CU(cudaGetLastError());
+            ctx->launches += 1;
+        } else {
+            CU(cudaMemcpyAsync(ctx->hStats.p, ctx->dStats.p, sizeof(DrawStat) * nDraws, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(ctx->hCount.p, ctx->dCount.p, 4ull * std::max(nChunks, 1u), cudaMemcpyDeviceToHost, s));
+        }
         CU(cudaStreamSynchronize(s));
         ctx->d2hBytes += sizeof(DrawStat) * (uint64_t)nDraws + 4;
         uint64_t acc = 0;
