@@ -246,10 +246,27 @@ def measure_workload(t3d, device, torch, name, peak, steps, flush_l2):
         cam.Clear(); cam.RenderScene(scene)
     e2e_ms = (time.perf_counter() - e0) / max(steps // 2, 2) * 1e3
     h2d, d2h = device.FrameBytes()
+    # the same with two frames in flight (the lists of frame k cross PCIe while frame k + 1 is built and executed)
+    e2e_async_ms = None
+    try:
+        cam.AsyncDownload = True
+        cam.Clear(); cam.RenderScene(scene)
+        n_async = max(steps // 2, 2)
+        e0 = time.perf_counter()
+        for _ in range(n_async):
+            cam.Clear(); cam.RenderScene(scene)
+            cam.WaitDownload(1)
+        cam.WaitDownload(0)
+        e2e_async_ms = (time.perf_counter() - e0) / n_async * 1e3
+    except Exception:
+        e2e_async_ms = None
+    finally:
+        cam.AsyncDownload = False
     tris = desc.total_triangles()
     out = {"triangles_per_frame": tris, "vertices": desc.total_vertices(), "draws": len([r for r in cam.Renders() if r["draw_index"] >= 0]),
            "surviving_triangles": surv, "device_ms": ms / steps, "triangles_per_s": tris / (ms / steps * 1e-3), "launches_per_frame": launches,
            "e2e_ms": e2e_ms, "e2e_triangles_per_s": tris / (e2e_ms * 1e-3), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
+           "e2e_two_frames_in_flight_ms": e2e_async_ms,
            "stages": {k: ({"ms": v["ms"], "frac": v["frac"]} if "frac" in v else {"ms": v["ms"]}) for k, v in stages.items()},
            "build_s": None}
     del scene, cam, objs

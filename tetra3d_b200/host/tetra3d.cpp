@@ -755,7 +755,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     lap("pairs + sorts");
     // ---- walk the passes and collect every render(rp) call, grouped by flush (camera.go:2057-2109) ----
     // deferFrustum: the child's ModelInFrustum test (camera.go:2088-2093) is left to the device (t3d_submit_instances with bounds)
-    struct PendingDraw { Model* model; int part; int flush; bool first; bool deferFrustum; };
+    struct PendingDraw { Model* model; int part; int flush; bool first; bool deferFrustum; bool uniformRun; };
     std::vector<PendingDraw> pending;
     std::vector<std::pair<Model*, int>> flushOwners;
     for (auto* pass : {&solids, &transparents}) {
@@ -770,6 +770,21 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                 {
                     std::vector<std::pair<float, uint32_t>> keyed(modelSlice.size());
                     for (size_t k = 0; k < modelSlice.size(); k++) keyed[k] = {v3_dist2(cameraPos, modelSlice[k]->WorldPosition()), (uint32_t)k};
+                    bool radix = keyed.size() >= 4096;
+                    for (size_t k = 0; radix && k < keyed.size(); k++) radix = keyed[k].first >= 0.0f;      // (also false for NaN)
+                    if (radix) {
+                        // large batches: the same order from a stable LSD radix sort -- squared distances are non-negative floats, whose
+                        // bit patterns order like the values; descending = ascending on the complement; equal keys keep their order
+                        std::vector<std::pair<float, uint32_t>> tmp(keyed.size());
+                        auto key = [](const std::pair<float, uint32_t>& e) { uint32_t u; std::memcpy(&u, &e.first, 4); return ~u; };
+                        for (int shift = 0; shift < 32; shift += 11) {
+                            uint32_t count[2049] = {0};
+                            for (auto& e : keyed) count[((key(e) >> shift) & 2047u) + 1]++;
+                            for (int b = 0; b < 2048; b++) count[b + 1] += count[b];
+                            for (auto& e : keyed) tmp[count[(key(e) >> shift) & 2047u]++] = e;
+                            keyed.swap(tmp);
+                        }
+                    } else
                     std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<float, uint32_t>& a, const std::pair<float, uint32_t>& b) { return a.first > b.first; });
                     std::vector<std::shared_ptr<Model>> sorted(modelSlice.size());
                     for (size_t k = 0; k < keyed.size(); k++) sorted[k] = std::move(modelSlice[keyed[k].second]);
@@ -777,7 +792,7 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                 }
                 // A batch whose children are instances of one another (one mesh of one part, one material, one parent, one
                 // rotation: particles) is submitted as instances, and then the device also runs the children's frustum test.
-                bool uniform = UseInstancing && DeviceFrustumCulling && modelSlice.size() >= 8;
+                bool uniform = UseInstancing && modelSlice.size() >= 8;
                 for (size_t k = 0; uniform && k < modelSlice.size(); k++) {
                     Model& a = *modelSlice[0]; Model& b = *modelSlice[k];
                     uniform = b.mesh && b.mesh == a.mesh && b.mesh->MeshParts.size() == 1 && !b.skinned && b.parent == a.parent &&
@@ -785,14 +800,14 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
                 }
                 for (auto& merged : modelSlice) {
                     if (!merged->visible) continue;
-                    const bool defer = uniform && merged->FrustumCulling;
+                    const bool defer = uniform && DeviceFrustumCulling && merged->FrustumCulling;
                     if (merged->FrustumCulling && !defer && !ModelInFrustum(*merged)) continue;
                     if (!merged->mesh) continue;
-                    for (size_t cp = 0; cp < merged->mesh->MeshParts.size(); cp++) { pending.push_back({merged.get(), (int)cp, flushId, first, defer}); first = false; }
+                    for (size_t cp = 0; cp < merged->mesh->MeshParts.size(); cp++) { pending.push_back({merged.get(), (int)cp, flushId, first, defer, uniform}); first = false; }
                 }
             } else {
                 if (!pair.model->mesh) continue;
-                pending.push_back({pair.model, pair.part, flushId, true, false});
+                pending.push_back({pair.model, pair.part, flushId, true, false, false});
             }
             flushOwners.push_back({pair.model, pair.part});
         }
@@ -902,8 +917,16 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
     std::vector<t3d_draw> draws; draws.reserve(pending.size());
     // per draw: may it travel as an instance (t3d_submit_instances)?  Its Node-local placement, the Material colour (the
     // instance carries Model.Color), and what a run of instances has to share beyond the t3d_draw fields
-    struct InstInfo { bool eligible, frustum; Node* parent; const Matrix4* rotation; float matColor[4]; t3d_instance inst; float bounds[9]; };
+    struct InstInfo { bool eligible, frustum; Node* parent; const Matrix4* rotation; float matColor[4]; t3d_instance inst; float bounds[9];
+                      size_t extraFirst, extraCount; };
     std::vector<InstInfo> instInfo; instInfo.reserve(pending.size());
+    // Children of a uniform DynamicBatch (uniformRun: instances of the batch's first child by construction -- one mesh of one
+    // part, one material, parent, rotation, light group) do not get a t3d_draw of their own: only their t3d_instance is kept, behind
+    // the draw of the child that opened the run (InstInfo.extraFirst / extraCount).  A 2 M-particle frame builds one 200-byte
+    // record per batch instead of one per particle.
+    std::vector<t3d_instance> extraInsts;
+    int runHeadDraw = -1, runHeadFlush = -1; bool runHeadDefer = false;
+    uint32_t drawCounter = 0;
     std::vector<const PendingDraw*> submitted;
     submitted.reserve(pending.size()); renders.reserve(pending.size());
     const Mesh* lastEnsured = nullptr;
@@ -918,6 +941,20 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         if (model->DynamicBatchOwner) debugInfo.batchedParts++;            // camera.go:1534-1536
         // ProcessVertices early-out (model.go:604): nothing is transformed or emitted
         const bool skip = (model->Color.A == 0 && model->isTransparent(meshPart)) || !model->visible;
+        if (pd.uniformRun && !skip && runHeadDraw >= 0 && runHeadFlush == pd.flush && runHeadDefer == pd.deferFrustum && !pd.first) {
+            // one more instance of the run its batch's first child opened: everything but position, scale and colour is the head's
+            InstInfo& head = instInfo[(size_t)runHeadDraw];
+            t3d_instance in;
+            in.position[0] = model->position.X; in.position[1] = model->position.Y; in.position[2] = model->position.Z;
+            in.scale[0] = model->scale.X; in.scale[1] = model->scale.Y; in.scale[2] = model->scale.Z;
+            in.color[0] = model->Color.R; in.color[1] = model->Color.G; in.color[2] = model->Color.B; in.color[3] = model->Color.A;
+            extraInsts.push_back(in);
+            head.extraCount++;
+            debugInfo.totalTris += meshPart.TriangleCount();               // camera.go:1532
+            submitted.push_back(&pd);
+            renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)drawCounter++});
+            continue;
+        }
 
         if (&mesh != lastEnsured) { device->ensureMesh(mesh); lastEnsured = &mesh; }     // runs of instances share a mesh
         bool lighting = false;                                             // camera.go:1521-1528
@@ -994,11 +1031,15 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
             ii.inst.position[0] = model->position.X; ii.inst.position[1] = model->position.Y; ii.inst.position[2] = model->position.Z;
             ii.inst.scale[0] = model->scale.X; ii.inst.scale[1] = model->scale.Y; ii.inst.scale[2] = model->scale.Z;
             ii.inst.color[0] = model->Color.R; ii.inst.color[1] = model->Color.G; ii.inst.color[2] = model->Color.B; ii.inst.color[3] = model->Color.A;
+            ii.extraFirst = extraInsts.size(); ii.extraCount = 0;
             instInfo.push_back(ii);
         }
         draws.push_back(d);
+        // a deferred child opens (or, after an early-out sibling, re-opens) a run that the following deferred children of its flush join;
+        // extras always hang off the LAST materialised draw, so the submission order stays the render order
+        if (pd.uniformRun) { runHeadDraw = (int)draws.size() - 1; runHeadFlush = pd.flush; runHeadDefer = pd.deferFrustum; } else runHeadDraw = -1;
         submitted.push_back(&pd);
-        renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)draws.size() - 1});
+        renders.push_back({model, pd.part, pd.flush, 0, 0, 0, 0, 0, (int)drawCounter++});
     }
     lastBoneOffsets.clear();
     for (auto& kv : boneOffsets) lastBoneOffsets[kv.first->name] = kv.second;
@@ -1022,12 +1063,18 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         for (size_t i = 0; i < draws.size();) {
             size_t j = i + 1;
             if (instInfo[i].eligible) while (j < draws.size() && sameRun(j - 1, j)) j++;
-            if (j - i >= MIN_RUN || instInfo[i].frustum) {       // (a child whose frustum test was deferred must go down as an instance, however short its run)
+            bool extras = false;
+            for (size_t k = i; k < j; k++) extras = extras || instInfo[k].extraCount != 0;
+            // (a child whose frustum test was deferred, and one that carries further children of its batch, must go down as instances, however short the run)
+            if (j - i >= MIN_RUN || instInfo[i].frustum || extras) {
                 if (i > plainFrom) check(ctx, t3d_submit_draws(ctx, draws.data() + plainFrom, (uint32_t)(i - plainFrom)), "t3d_submit_draws");
                 t3d_draw proto = draws[i];
                 std::memcpy(proto.color, instInfo[i].matColor, 16);
-                insts.resize(j - i);
-                for (size_t k = i; k < j; k++) insts[k - i] = instInfo[k].inst;
+                insts.clear();
+                for (size_t k = i; k < j; k++) {
+                    insts.push_back(instInfo[k].inst);
+                    insts.insert(insts.end(), extraInsts.begin() + (ptrdiff_t)instInfo[k].extraFirst, extraInsts.begin() + (ptrdiff_t)(instInfo[k].extraFirst + instInfo[k].extraCount));
+                }
                 Matrix4 par = m4_identity();
                 if (instInfo[i].parent) par = instInfo[i].parent->Transform();
                 float rot16[16], par16[16];
