@@ -277,8 +277,8 @@ int   orc_bin_index(float depth, float min_depth, float max_depth, int sort_mode
 
 /* ---- bone poses: the step before the path --------------------------------------------
  * AnimationTrack.ValueAsVector / ValueAsQuaternion (animation.go:63-164), Quaternion.Slerp / ToMatrix4
- * (quaternion.go:26-59, 132-178), AnimationPlayer.forceUpdate without blending or relative motion
- * (animation.go:961-980), Node.Transform + boneInfluence (node.go:572-594).  Slerp goes through Go's float64
+ * (quaternion.go:26-59, 132-178), AnimationPlayer.forceUpdate without relative motion (animation.go:837-980; the blend of
+ * animation.go:852-907 is orc_pose_bones_blended), Node.Transform + boneInfluence (node.go:572-594).  Slerp goes through Go's float64
  * math.Sin / math.Atan2 (math32/math32.go:137-139, 204-206), which are pure Go on amd64 (Cephes-derived,
  * src/math/sin.go, atan.go, atan2.go of the Go standard library): restated below as orc_go_sin / orc_go_atan2. */
 typedef struct orc_track { int32_t first_key, n_keys, interpolation; } orc_track;    /* 0 linear, 1 constant, 2 cubic (evaluated as linear: animation.go:107) */
