@@ -276,6 +276,16 @@ typedef struct t3d_pose {
     float reserved;
 } t3d_pose;
 
+/* A player whose blends were interrupted by further Play() calls (t3d_submit_pose_chains): level i's animation sampled at
+ * playhead[i]; blend[i] (i >= 1) the fraction of the blend into level i.  For the levels below the last, both are the values of the
+ * level's last update before the next Play(). */
+#define T3D_POSE_CHAIN_MAX 4
+typedef struct t3d_pose_chain {
+    float root[16];
+    float playhead[T3D_POSE_CHAIN_MAX];
+    float blend[T3D_POSE_CHAIN_MAX];    /* blend[0] is not read */
+} t3d_pose_chain;
+
 typedef struct t3d_ctx t3d_ctx;
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */
@@ -359,9 +369,19 @@ int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, 
  * Per bone and property: both exist -> start + (target - start) * blend, rotations start.Slerp(target, blend).Unit(); one
  * exists -> that one; neither -> the skeleton's rest value.  The frame in which blend reaches 1 still goes through here
  * (animation.go:899-902 ends the blend after using it); later frames use t3d_submit_poses.  A blend that starts from an
- * unfinished blend has no such closed form (its start is itself a blend result): keep t3d_submit_bones for those frames. */
+ * unfinished blend starts from a blend result: t3d_submit_pose_chains. */
 int t3d_submit_poses_blended(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t from_animation_id, uint64_t animation_id, const t3d_pose* poses,
                              uint32_t n, uint32_t* offset);
+/* Replaces: the same when the blend was itself started in the middle of an unfinished blend, any number of times (animation.go:
+ * 905-908: prevAnimatedProperties then holds blend RESULTS).  The history since the last finished blend is a chain of animations
+ * animation_ids[0 .. n_levels), in the order they were Play()ed, the last one playing; the device folds it the way the reference's
+ * two maps do: per bone, level i's targets are blend(targets of level i - 1, samples of level i, blend[i]) by the per-property rules
+ * of t3d_submit_poses_blended where level i - 1's animation has a channel for the bone (currentProperties is rebuilt from the
+ * playing animation's channels after every Play(), animation.go:618-626), the plain samples where it has not; a property no later
+ * level sets keeps the value the earlier level gave the bone's Node.  "Has a channel" is taken to mean that one of the bone's three
+ * tracks holds keyframes.  n_levels = 1 is t3d_submit_poses, 2 is t3d_submit_poses_blended; up to T3D_POSE_CHAIN_MAX. */
+int t3d_submit_pose_chains(t3d_ctx* ctx, uint64_t skeleton_id, const uint64_t* animation_ids, uint32_t n_levels, const t3d_pose_chain* poses,
+                           uint32_t n, uint32_t* offset);
 /* Replaces: one render(rp) call (camera.go:1507-1827) per element, in render order. */
 int t3d_submit_draws(t3d_ctx* ctx, const t3d_draw* draws, uint32_t n);
 /* Replaces: n render(rp) calls (camera.go:2083-2100: the children of a DynamicBatch owner; any run of Models sharing mesh,

@@ -176,6 +176,10 @@ def lib():
         L.orc_pose_bones.argtypes = [C.POINTER(orc_skeleton), C.POINTER(orc_animation), C.c_float, f32p, f32p]
         L.orc_pose_bones_blended.argtypes = [C.POINTER(orc_skeleton), C.POINTER(orc_animation), C.c_float, C.POINTER(orc_animation), C.c_float,
                                              C.c_float, f32p, f32p]
+        _anp = C.POINTER(C.POINTER(orc_animation))
+        L.orc_pose_bones_chain.argtypes = [C.POINTER(orc_skeleton), C.c_int, _anp, f32p, f32p, f32p, f32p]
+        L.orc_pose_locals_chain.argtypes = [C.POINTER(orc_skeleton), C.c_int, _anp, f32p, f32p, f32p, f32p, f32p, C.POINTER(C.c_int32)]
+        L.orc_sample_bone.argtypes = [C.POINTER(orc_animation), C.c_int, C.c_float, C.POINTER(C.c_int32), f32p, f32p, f32p]
         L.orc_quat_slerp.argtypes = [f32p, f32p, C.c_float, f32p]
         L.orc_quat_to_matrix.argtypes = [f32p, f32p]
         L.orc_go_sin.argtypes = [C.c_double]; L.orc_go_sin.restype = C.c_double
@@ -347,6 +351,48 @@ def pose_bones_blended(sk: SkeletonDesc, anim_from: Optional[AnimationDesc], fro
     L.orc_pose_bones_blended(C.byref(cs), C.byref(cf) if cf is not None else None, float(from_playhead),
                              C.byref(ca) if ca is not None else None, float(playhead), float(blend), _fp(root), _fp(out))
     return out
+
+
+def _c_chain(sk: SkeletonDesc, anims, playheads, blends):
+    keep, ptrs = [], (C.POINTER(orc_animation) * len(anims))()
+    for i, a in enumerate(anims):
+        ca, k = _c_animation(a, sk)
+        keep.append((ca, k))
+        ptrs[i] = C.pointer(ca) if ca is not None else None
+    ph = np.ascontiguousarray(playheads, np.float32); bp = np.ascontiguousarray(blends, np.float32)
+    assert len(ph) == len(anims) == len(bp)
+    return ptrs, ph, bp, keep
+
+
+def pose_bones_chain(sk: SkeletonDesc, anims, playheads, blends, root16) -> np.ndarray:
+    """boneInfluence of every bone for a player whose blends were interrupted by further Play() calls: `anims` in the order they
+    were played (the last one playing), playheads[i] / blends[i] the values of level i's last update (blends[0] unused)."""
+    cs = _c_skeleton(sk)
+    ptrs, ph, bp, _keep = _c_chain(sk, anims, playheads, blends)
+    root = np.ascontiguousarray(root16, np.float32).reshape(16)
+    out = np.zeros((len(sk.parent), 16), np.float32)
+    lib().orc_pose_bones_chain(C.byref(cs), len(anims), ptrs, _fp(ph), _fp(bp), _fp(root), _fp(out))
+    return out
+
+
+def pose_locals_chain(sk: SkeletonDesc, anims, playheads, blends):
+    """The bones' local position (n, 3), scale (n, 3) and rotation (n, 16) after the same fold, and which of the three a level of
+    the chain set, (n, 3) bool (the others are the skeleton's rest values)."""
+    cs = _c_skeleton(sk)
+    ptrs, ph, bp, _keep = _c_chain(sk, anims, playheads, blends)
+    n = len(sk.parent)
+    pos, scl, rot = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 16), np.float32)
+    was_set = np.zeros((n, 3), np.int32)
+    lib().orc_pose_locals_chain(C.byref(cs), len(anims), ptrs, _fp(ph), _fp(bp), _fp(pos), _fp(scl), _fp(rot), was_set.ctypes.data_as(C.POINTER(C.c_int32)))
+    return pos, scl, rot, was_set.astype(bool)
+
+
+def sample_bone(sk: SkeletonDesc, anim: AnimationDesc, bone: int, time: float):
+    """(flags[3], position[3], scale[3], quaternion[4]) of one bone's channel sampled at `time` (animation.go:674-722)."""
+    ca, _keep = _c_animation(anim, sk)
+    flags = np.zeros(3, np.int32); pos = np.zeros(3, np.float32); scl = np.zeros(3, np.float32); q = np.zeros(4, np.float32)
+    lib().orc_sample_bone(C.byref(ca), int(bone), float(time), flags.ctypes.data_as(C.POINTER(C.c_int32)), _fp(pos), _fp(scl), _fp(q))
+    return flags.astype(bool), pos, scl, q
 
 
 def bin_index(depth, mn, mx, sort_mode) -> int:

@@ -1881,45 +1881,75 @@ static quat quat_unit(quat q) {
     return q;
 }
 
-/* One bone's local position / scale / rotation after AnimationPlayer.forceUpdate (animation.go:837-985).
- * `from` != NULL: the player is blending (animation.go:852-903): `from` sampled at from_playhead is what
- * prevAnimatedProperties holds for the bone -- the copy Play() took of currentProperties (animation.go:548-554), i.e. the
- * targets of the last forceUpdate under the previous animation -- and bp the blend fraction.  Per property: both exist ->
- * start + (props - start) * bp (rotation: start.Slerp(props, bp).Unit()); only one exists -> that one; neither -> the bone
- * keeps what its Node holds (the skeleton's rest values). */
-static void pose_local(const orc_skeleton* sk, int b, const orc_animation* an, float playhead,
-                       const orc_animation* from, float from_playhead, float bp, vec3* pos, vec3* scl, mat4* rot) {
+/* What AnimationPlayer.updateValues records for one node (AnimationValues, animation.go:674-722). */
+typedef struct bone_sample { vec3 p, s; quat q; int P, S, R; } bone_sample;
+
+static int has_channel(const orc_animation* an, int b) {      /* a channel exists for the bone: any of its tracks holds keyframes */
+    if (!an || b >= an->n_bones) return 0;
+    return an->tracks[3 * b].n_keys > 0 || an->tracks[3 * b + 1].n_keys > 0 || an->tracks[3 * b + 2].n_keys > 0;
+}
+static bone_sample sample_bone(const orc_animation* an, int b, float time) {
+    bone_sample v; memset(&v, 0, sizeof v);
+    if (!an || b >= an->n_bones) return v;
+    v.P = track_vector(an, &an->tracks[3 * b + 0], time, &v.p);
+    v.S = track_vector(an, &an->tracks[3 * b + 1], time, &v.s);
+    v.R = track_quaternion(an, &an->tracks[3 * b + 2], time, &v.q);
+    return v;
+}
+/* forceUpdate's blend of one node (animation.go:859-897): start = prevAnimatedProperties[node], props = this frame's samples. */
+static bone_sample blend_sample(bone_sample start, bone_sample props, float bp) {
+    bone_sample r = props;
+    if (start.P) {
+        if (props.P) { r.p.X = start.p.X + ((props.p.X - start.p.X) * bp); r.p.Y = start.p.Y + ((props.p.Y - start.p.Y) * bp); r.p.Z = start.p.Z + ((props.p.Z - start.p.Z) * bp); }   /* :863-866 */
+        else { r.p = start.p; r.P = 1; }
+    }
+    if (start.S) {
+        if (props.S) { r.s.X = start.s.X + ((props.s.X - start.s.X) * bp); r.s.Y = start.s.Y + ((props.s.Y - start.s.Y) * bp); r.s.Z = start.s.Z + ((props.s.Z - start.s.Z) * bp); }   /* :875-878 */
+        else { r.s = start.s; r.S = 1; }
+    }
+    if (start.R) {
+        if (props.R) r.q = quat_unit(quat_slerp(start.q, props.q, bp));                                                                                                       /* :887-889 */
+        else { r.q = start.q; r.R = 1; }
+    }
+    return r;
+}
+
+/* One bone's local position / scale / rotation after AnimationPlayer.forceUpdate (animation.go:837-985), for a player whose
+ * state is the chain of animations levels[0 .. n): levels[n - 1] is playing; every level i >= 1 was Play()ed with BlendTime > 0
+ * while level i - 1's targets were in currentProperties, and -- for i < n - 1 -- was itself interrupted by the next Play() before
+ * its blend ended, with playheads[i] / bps[i] the values of its last update.  The reference keeps two things per node, and so
+ * does this fold: what currentProperties holds (`cur`: defined only for nodes the level's animation has a channel for, because
+ * assignChannels clears the map after every Play(), animation.go:618-626) and what the Node itself holds (every property a level
+ * set stays until a later level sets it again).  Level i's targets are blend(cur, samples of level i, bps[i]) where cur is defined,
+ * the plain samples where it is not (prevExists false, animation.go:843).  With one level this is the plain pose; with two, a blend
+ * between two animations. */
+static void pose_local_chain(const orc_skeleton* sk, int b, int n, const orc_animation* const* levels, const float* playheads, const float* bps,
+                             vec3* pos, vec3* scl, mat4* rot, int32_t* set3 /* NULL, or: which of the three a level of the chain set */) {
+    if (set3) set3[0] = set3[1] = set3[2] = 0;
     *pos = v3(sk->rest_position[3 * b], sk->rest_position[3 * b + 1], sk->rest_position[3 * b + 2]);
     *scl = v3(sk->rest_scale[3 * b], sk->rest_scale[3 * b + 1], sk->rest_scale[3 * b + 2]);
     *rot = m4_load(sk->rest_rotation + 16 * (size_t)b);
-    vec3 pv = v3(0, 0, 0), sv = v3(0, 0, 0); quat pq = {0, 0, 0, 0};
-    int pP = 0, pS = 0, pR = 0;
-    if (an && b < an->n_bones) {
-        pP = track_vector(an, &an->tracks[3 * b + 0], playhead, &pv);
-        pS = track_vector(an, &an->tracks[3 * b + 1], playhead, &sv);
-        pR = track_quaternion(an, &an->tracks[3 * b + 2], playhead, &pq);
-    }
-    if (from && b < from->n_bones) {
-        vec3 v; quat q;
-        if (track_vector(from, &from->tracks[3 * b + 0], from_playhead, &v)) {
-            if (pP) { pv.X = v.X + ((pv.X - v.X) * bp); pv.Y = v.Y + ((pv.Y - v.Y) * bp); pv.Z = v.Z + ((pv.Z - v.Z) * bp); }   /* animation.go:863-866 */
-            else { pv = v; pP = 1; }
-        }
-        if (track_vector(from, &from->tracks[3 * b + 1], from_playhead, &v)) {
-            if (pS) { sv.X = v.X + ((sv.X - v.X) * bp); sv.Y = v.Y + ((sv.Y - v.Y) * bp); sv.Z = v.Z + ((sv.Z - v.Z) * bp); }   /* animation.go:875-878 */
-            else { sv = v; pS = 1; }
-        }
-        if (track_quaternion(from, &from->tracks[3 * b + 2], from_playhead, &q)) {
-            if (pR) pq = quat_unit(quat_slerp(q, pq, bp));                                                                      /* animation.go:887-889 */
-            else { pq = q; pR = 1; }
+    bone_sample cur; memset(&cur, 0, sizeof cur);
+    int curDefined = 0;
+    for (int k = 0; k < n; k++) {
+        if (!has_channel(levels[k], b)) { curDefined = 0; continue; }
+        bone_sample v = sample_bone(levels[k], b, playheads[k]);
+        if (k > 0 && curDefined) v = blend_sample(cur, v, bps[k]);
+        cur = v; curDefined = 1;                                /* animation.go:909-937 */
+        if (v.P) { *pos = v.p; if (set3) set3[0] = 1; }         /* animation.go:939-983 without relative motion */
+        if (v.S) { *scl = v.s; if (set3) set3[1] = 1; }
+        if (v.R) {
+            const mat4 r = quat_to_matrix(v.q);
+            if (!m4_is_zero(&r)) { *rot = r; if (set3) set3[2] = 1; }   /* SetLocalRotation ignores an all-zero matrix (node.go:906-912) */
         }
     }
-    if (pP) *pos = pv;
-    if (pS) *scl = sv;
-    if (pR) {
-        const mat4 r = quat_to_matrix(pq);
-        if (!m4_is_zero(&r)) *rot = r;             /* SetLocalRotation ignores an all-zero matrix (node.go:906-912) */
-    }
+}
+
+static void pose_local(const orc_skeleton* sk, int b, const orc_animation* an, float playhead,
+                       const orc_animation* from, float from_playhead, float bp, vec3* pos, vec3* scl, mat4* rot) {
+    const orc_animation* levels[2] = {from, an};
+    const float playheads[2] = {from_playhead, playhead}, bps[2] = {0, bp};
+    pose_local_chain(sk, b, 2, levels, playheads, bps, pos, scl, rot, NULL);
 }
 
 static void pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const orc_animation* from, float from_playhead,
@@ -1946,6 +1976,48 @@ static void pose_bones(const orc_skeleton* sk, const orc_animation* an, float pl
 
 void orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float playhead, const float* root16, float* out) {
     pose_bones(sk, an, playhead, NULL, 0, 0, root16, out);
+}
+
+/* A player whose blends were interrupted by further Play() calls: see pose_local_chain. */
+void orc_pose_bones_chain(const orc_skeleton* sk, int n_levels, const orc_animation* const* levels, const float* playheads, const float* bps,
+                          const float* root16, float* out) {
+    const int n = sk->n_bones;
+    mat4* world = (mat4*)malloc(sizeof(mat4) * (size_t)(n > 0 ? n : 1));
+    const mat4 root = m4_load(root16);
+    for (int b = 0; b < n; b++) {
+        vec3 pos, scl; mat4 rot;
+        pose_local_chain(sk, b, n_levels, levels, playheads, bps, &pos, &scl, &rot, NULL);
+        mat4 t = m4_scale(scl.X, scl.Y, scl.Z);                 /* Node.Transform (node.go:572-594) */
+        t = m4_mult(t, rot);
+        t = m4_mult(t, m4_translate(pos.X, pos.Y, pos.Z));
+        t = m4_mult(t, sk->parent[b] >= 0 ? world[sk->parent[b]] : root);
+        world[b] = t;
+        const mat4 infl = m4_mult(m4_load(sk->inverse_bind + 16 * (size_t)b), t);
+        m4_store(&infl, out + 16 * (size_t)b);
+    }
+    free(world);
+}
+/* The same fold, stopping at the bones' local values: position[3], scale[3], rotation[16] per bone (what the Node holds), and
+ * set3[3] per bone: whether a level of the chain set the property (otherwise the value is the skeleton's rest value, where the
+ * reference's Node keeps whatever an animation before the chain left there). */
+void orc_pose_locals_chain(const orc_skeleton* sk, int n_levels, const orc_animation* const* levels, const float* playheads, const float* bps,
+                           float* pos3, float* scale3, float* rot16, int32_t* set3) {
+    for (int b = 0; b < sk->n_bones; b++) {
+        vec3 pos, scl; mat4 rot;
+        pose_local_chain(sk, b, n_levels, levels, playheads, bps, &pos, &scl, &rot, set3 ? set3 + 3 * b : NULL);
+        pos3[3 * b] = pos.X; pos3[3 * b + 1] = pos.Y; pos3[3 * b + 2] = pos.Z;
+        scale3[3 * b] = scl.X; scale3[3 * b + 1] = scl.Y; scale3[3 * b + 2] = scl.Z;
+        m4_store(&rot, rot16 + 16 * (size_t)b);
+    }
+}
+/* One bone's three tracks sampled at `time` (AnimationValues of animation.go:674-722): flags3 = {PositionExists, ScaleExists,
+ * RotationExists}, then position, scale, quaternion (x y z w). */
+void orc_sample_bone(const orc_animation* an, int bone, float time, int32_t* flags3, float* pos3, float* scale3, float* quat4) {
+    const bone_sample v = sample_bone(an, bone, time);
+    flags3[0] = v.P; flags3[1] = v.S; flags3[2] = v.R;
+    pos3[0] = v.p.X; pos3[1] = v.p.Y; pos3[2] = v.p.Z;
+    scale3[0] = v.s.X; scale3[1] = v.s.Y; scale3[2] = v.s.Z;
+    quat4[0] = v.q.X; quat4[1] = v.q.Y; quat4[2] = v.q.Z; quat4[3] = v.q.W;
 }
 
 /* A player in the middle of a blend (BlendTime > 0, animation.go:852-907): `from` (may be NULL: the previous state animated

@@ -301,6 +301,14 @@ void   orc_pose_bones(const orc_skeleton* sk, const orc_animation* an, float pla
 /* The same while the player blends from `from` @ from_playhead into `an` @ playhead (animation.go:852-907), bp = blend fraction. */
 void   orc_pose_bones_blended(const orc_skeleton* sk, const orc_animation* from, float from_playhead, const orc_animation* an, float playhead,
                               float bp, const float* root16, float* out);
+/* Blends interrupted by further Play() calls: levels[0 .. n) in the order they were played, the last one playing; playheads[i] /
+ * bps[i] are level i's values at its last update (bps[0] unused).  See pose_local_chain in t3d_oracle.c for what the reference's
+ * currentProperties / prevAnimatedProperties maps make of such a history. */
+void   orc_pose_bones_chain(const orc_skeleton* sk, int n_levels, const orc_animation* const* levels, const float* playheads, const float* bps,
+                            const float* root16, float* out);
+void   orc_pose_locals_chain(const orc_skeleton* sk, int n_levels, const orc_animation* const* levels, const float* playheads, const float* bps,
+                             float* pos3, float* scale3, float* rot16, int32_t* set3);
+void   orc_sample_bone(const orc_animation* an, int bone, float time, int32_t* flags3, float* pos3, float* scale3, float* quat4);
 void   orc_quat_slerp(const float* a4, const float* b4, float percent, float* out4);      /* quaternion.go:26-59 */
 void   orc_quat_to_matrix(const float* q4, float* out16);                                 /* quaternion.go:132-178 */
 double orc_go_sin(double x);                                                              /* Go math.Sin (amd64: pure Go) */

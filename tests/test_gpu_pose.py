@@ -194,31 +194,58 @@ def test_blended_pose_api_errors(device):
     lib.t3d_destroy(ctx)
 
 
-def test_relative_motion_and_nested_blends_are_refused(device):
+def test_interrupted_blends_through_the_player(device):
+    # Play() in the middle of unfinished blends, again and again: every frame's bones against the oracle's fold of the chain the
+    # player reports (t3d_submit_pose_chains / k_pose_chain for three and four levels; two levels and one go the usual ways)
     import tetra3d_b200 as t3d
-    desc = scenes.posed_scene(1, n_models=2)
-    scene, cam, objs = t3d.build_scene(desc, device)
-    pose = desc.models[0].pose
-    player = objs[id(pose)]
-    rng = np.random.default_rng(1)
-    a = t3d.build_animation(scenes.random_animation(rng, pose.skeleton))
-    b = t3d.build_animation(scenes.random_animation(rng, pose.skeleton))
-    clock = [0]
-    player.SetClock(lambda: clock[0])
-    player.BlendTime = 0.5
-    player.Update(0.01)
-    player.Play(a)                      # a blend starts ...
-    clock[0] = 100
-    player.Update(0.01)
-    assert player.Blending() and not player.BlendStartIsBlend()
-    cam.Clear(); cam.RenderScene(scene)
-    player.Play(b)                      # ... and is interrupted by the next: its start is a blend result (animation.go:905-908)
-    clock[0] = 150
-    player.Update(0.01)
-    assert player.Blending() and player.BlendStartIsBlend()
-    with pytest.raises(Exception, match="unfinished blend"):
-        cam.Clear(); cam.RenderScene(scene)
-    clock[0] = 10_000                   # once that blend has run out the player is an ordinary one again
-    player.Update(0.01); player.Update(0.01)
-    assert not player.Blending()
-    cam.Clear(); cam.RenderScene(scene)
+    for seed in range(4):
+        desc = scenes.posed_scene(10 + seed, n_models=2, n_bones=[6, 11, 3, 40][seed], chain=bool(seed % 2))
+        pose = desc.models[0].pose
+        rng = np.random.default_rng(70 + seed)
+        anim_descs = [pose.animation] + [scenes.random_animation(rng, pose.skeleton, length=30.0) for _ in range(3)]
+        scene, cam, objs = t3d.build_scene(desc, device)
+        player = objs[id(pose)]
+        host = [player.SampledChain()[-1][0]] + [t3d.build_animation(a) for a in anim_descs[1:]]
+        clock = [0]
+        player.SetClock(lambda: clock[0])
+        player.BlendTime = 0.4
+        root = O.node_world_transform(pose.root)
+        name = desc.models[0].name
+        depths = set()
+        cur = 0
+        for step in range(36):
+            if step % 3 == 2:                       # a new animation every third frame: 48 ms into a 400 ms blend
+                cur = (cur + 1 + int(rng.integers(0, 3))) % 4
+                player.Play(host[cur])
+            clock[0] += 16
+            player.Update(0.016)
+            chain = player.SampledChain()
+            if len(chain) > 4:
+                with pytest.raises(Exception, match="T3D_POSE_CHAIN_MAX"):
+                    cam.Clear(); cam.RenderScene(scene)
+                clock[0] += 1000                    # let that blend run out: one more frame at bp = 1, then a plain pose again
+                player.Update(0.016); player.Update(0.016)
+                chain = player.SampledChain()
+                assert len(chain) == 1
+            depths.add(len(chain))
+            cam.Clear(); cam.RenderScene(scene)
+            got = device.ReadBones(cam.BoneOffsets()[name], len(pose.skeleton.parent))
+            anims = [anim_descs[[i for i, h in enumerate(host) if h is a][0]] for a, _, _ in chain]
+            want = O.pose_bones_chain(pose.skeleton, anims, [p for _, p, _ in chain], [b for _, _, b in chain], root)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, step, len(chain))
+        assert {1, 2, 3, 4} <= depths, depths
+
+
+def test_pose_chain_api_errors(device):
+    import tetra3d_b200
+    lib = C.CDLL(tetra3d_b200.LIB_PATH)
+    ctx = C.c_void_p()
+    assert lib.t3d_create(C.byref(ctx), 0) == 0
+    off = C.c_uint32()
+    pose = (C.c_float * 24)()
+    ids = (C.c_uint64 * 4)(1, 2, 3, 4)
+    assert lib.t3d_submit_pose_chains(ctx, C.c_uint64(1), ids, 3, pose, 1, C.byref(off)) == -5      # no open frame
+    assert lib.t3d_submit_pose_chains(ctx, C.c_uint64(1), None, 3, pose, 1, C.byref(off)) == -1
+    lib.t3d_destroy(ctx)
+
+

@@ -242,3 +242,139 @@ def test_blended_posed_scenes_render_in_the_oracle():
     plain = O.render_scene(scenes.posed_scene(0, n_models=8))
     mixed = O.render_scene(scenes.posed_scene(0, n_models=8, blends=[0, 250, 999, 1000, 1500, None, 333]))
     assert mixed.n_vertices > 0 and plain.n_vertices > 0
+
+
+# ---- blends interrupted by further Play() calls: the closed form against a literal, stateful transcription of forceUpdate ----------
+class LiteralPlayer:
+    """AnimationPlayer as animation.go writes it, maps and all: AnimatedProperties / currentProperties / prevAnimatedProperties keyed
+    by node, assignChannels clearing the first two after every Play(), forceUpdate's per-node blend.  Nodes are the skeleton's
+    bones (local position / scale / rotation matrix, starting at rest); track sampling is the oracle's (orc_sample_bone), the blend
+    arithmetic float32 numpy.  One deliberate difference: the reference ends the blend INSIDE its loop over the node map when bp
+    reaches 1 (animation.go:899-902), which makes that frame depend on Go's map order; here the blend ends after the loop."""
+
+    def __init__(self, sk, clock):
+        self.sk, self.clock = sk, clock
+        n = len(sk.parent)
+        self.pos = sk.rest_position.astype(F32).copy(); self.scl = sk.rest_scale.astype(F32).copy()
+        self.rot = np.asarray(sk.rest_rotation, F32).reshape(n, 16).copy()
+        self.animated, self.current, self.prev = {}, {}, {}
+        self.animation, self.playing, self.playhead, self.channels_updated = None, False, F32(0), False
+        self.BlendTime, self.blend_start = F32(0), None
+
+    def Play(self, anim):                                               # animation.go:517-566
+        if anim is self.animation and self.playing:
+            return
+        self.animation, self.playing, self.playhead, self.channels_updated = anim, True, F32(0), False
+        if self.BlendTime > 0:
+            self.prev = {k: dict(v) for k, v in self.current.items()}
+            self.blend_start = self.clock[0]
+
+    def Update(self, dt):                                               # animation.go:810-824, 674-722, 837-985
+        if not self.playing and self.blend_start is not None:
+            self.blend_start = None; self.prev = {}
+        if not self.channels_updated:                                   # assignChannels, animation.go:618-672
+            self.animated, self.current = {}, {}
+            for name in self.animation.channels:
+                self.animated[self.sk.names.index(name)] = dict(P=False, S=False, R=False, p=None, s=None, q=None)
+            self.channels_updated = True
+        for node, n in self.animated.items():
+            flags, p, s, q = O.sample_bone(self.sk, self.animation, node, float(self.playhead))
+            if flags[0]: n["p"], n["P"] = p, True
+            if flags[1]: n["s"], n["S"] = s, True
+            if flags[2]: n["q"], n["R"] = q, True
+        self.playhead = F32(self.playhead + F32(dt))
+        ended = False
+        for node, props in self.animated.items():
+            tp = ts = tq = None
+            if self.blend_start is not None and node in self.prev:
+                bp = F32(self.clock[0] - self.blend_start) / (self.BlendTime * F32(1000))
+                bp = min(bp, F32(1))
+                start = self.prev[node]
+                if start["P"] and props["P"]: tp = start["p"] + (props["p"] - start["p"]) * bp
+                elif props["P"]: tp = props["p"]
+                elif start["P"]: tp = start["p"]
+                if start["S"] and props["S"]: ts = start["s"] + (props["s"] - start["s"]) * bp
+                elif props["S"]: ts = props["s"]
+                elif start["S"]: ts = start["s"]
+                if start["R"] and props["R"]: tq = _unit(O.quat_slerp(start["q"], props["q"], float(bp)))
+                elif props["R"]: tq = props["q"]
+                elif start["R"]: tq = start["q"]
+                ended = ended or bp == 1
+            else:
+                tp = props["p"] if props["P"] else None
+                ts = props["s"] if props["S"] else None
+                tq = props["q"] if props["R"] else None
+            if self.BlendTime > 0:                                      # animation.go:909-937
+                self.current[node] = dict(P=tp is not None, S=ts is not None, R=tq is not None, p=tp, s=ts, q=tq)
+            if tp is not None: self.pos[node] = tp                      # animation.go:939-983 (no relative motion)
+            if ts is not None: self.scl[node] = ts
+            if tq is not None:
+                m = O.quat_to_matrix(tq).reshape(16)
+                if m.any(): self.rot[node] = m                          # node.go:906-912
+        if ended:
+            self.blend_start = None; self.prev = {}
+
+
+def _no_empty_channels(anim):
+    anim.channels = {k: v for k, v in anim.channels.items() if v}
+    return anim
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_chain_closed_form_matches_a_literal_stateful_player(seed):
+    # random histories of Play() calls and updates under a stepped clock: after every update, the bones' local values from the
+    # host mirror's chain bookkeeping + the oracle's fold must equal the literal player's nodes, bit for bit
+    import tetra3d_b200 as t3d
+    rng = np.random.default_rng(900 + seed)
+    sk = scenes.random_skeleton(rng, int(rng.integers(3, 12)))
+    descs = [_no_empty_channels(scenes.random_animation(rng, sk, length=50.0)) for _ in range(4)]
+    for i, d in enumerate(descs):
+        d.name = "anim%d" % i
+    host = [t3d.build_animation(d) for d in descs]
+    by_id = {id(h): d for h, d in zip(host, descs)}
+    clock = [1000]
+    lit = LiteralPlayer(sk, clock)
+    ap = t3d.NewAnimationPlayer(t3d.Node("armature")); ap.SetClock(lambda: clock[0])
+    blend_time = float(rng.choice([0.1, 0.25, 0.5]))
+    lit.BlendTime = F32(blend_time); ap.BlendTime = blend_time
+    deepest = checked = nested = 0
+    cur = int(rng.integers(0, 4))
+    lit.Play(descs[cur]); ap.Play(host[cur])
+    for step in range(40):
+        if rng.random() < 0.2:                                           # switch animation, often in the middle of a blend
+            cur = int(rng.choice([k for k in range(4) if k != cur]))
+            lit.Play(descs[cur]); ap.Play(host[cur])
+        clock[0] += int(rng.integers(5, 90))
+        dt = float(F32(rng.uniform(0.01, 0.2)))
+        lit.Update(dt); ap.Update(dt)
+        chain = ap.SampledChain()
+        deepest = max(deepest, len(chain))
+        if len(chain) > 4:
+            continue                                                     # refused by Camera.Render (T3D_POSE_CHAIN_MAX); the literal player carries on
+        anims = [by_id_lookup(by_id, host, a) for a, _, _ in chain]
+        pos, scl, rot, was_set = O.pose_locals_chain(sk, anims, [p for _, p, _ in chain], [b for _, _, b in chain])
+        # a property no animation of the chain sets keeps, in the reference, whatever an earlier animation left in the Node (the
+        # closed form has the skeleton's rest value there -- DESIGN.md 4a); everything the chain sets must agree bit for bit
+        for b in range(len(sk.parent)):
+            if was_set[b, 0]: assert np.array_equal(pos[b].view(np.uint32), lit.pos[b].view(np.uint32)), (seed, step, len(chain), b)
+            if was_set[b, 1]: assert np.array_equal(scl[b].view(np.uint32), lit.scl[b].view(np.uint32)), (seed, step, len(chain), b)
+            if was_set[b, 2]: assert np.array_equal(rot[b].view(np.uint32), lit.rot[b].view(np.uint32)), (seed, step, len(chain), b)
+        checked += int(was_set.sum())
+        nested += int(was_set.sum()) if len(chain) >= 3 else 0
+    assert deepest >= 2 and checked > 50
+    NESTED_SEEN[seed] = nested
+
+
+NESTED_SEEN = {}
+
+
+def test_chain_cases_included_interrupted_blends():
+    # (runs after the parametrised test above) the random histories did contain blends started from unfinished blends
+    assert sum(NESTED_SEEN.values()) > 200, NESTED_SEEN
+
+
+def by_id_lookup(by_id, host, a):
+    for h in host:
+        if h is a:
+            return by_id[id(h)]
+    raise KeyError(a)

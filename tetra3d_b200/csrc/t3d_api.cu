@@ -75,7 +75,8 @@ struct Animation {
     void* block = nullptr;
     t3d_track* tracks = nullptr; float* keyTimes = nullptr; float4* keyValues = nullptr;
 };
-struct PoseCall { uint64_t skeleton, animation; uint32_t firstPose, nPoses, firstBone; uint64_t fromAnimation; bool blended; };      // one t3d_submit_poses[_blended] call of the frame
+struct PoseCall { uint64_t skeleton, animation; uint32_t firstPose, nPoses, firstBone; uint64_t fromAnimation; bool blended;
+                  uint32_t nLevels; uint64_t chain[T3D_POSE_CHAIN_MAX]; };      // nLevels != 0: t3d_submit_pose_chains (firstPose indexes hPoseChains)      // one t3d_submit_poses[_blended] call of the frame
 
 
 struct Mesh {
@@ -113,6 +114,7 @@ struct t3d_ctx {
     DevBuf dVolumes; bool volumesDirty = true;
     std::unordered_map<uint64_t, Skeleton> skeletons;
     std::unordered_map<uint64_t, Animation> animations;
+    PinVec<t3d_pose_chain> hPoseChains;     // records of t3d_submit_pose_chains: read by k_pose_chain straight from pinned memory
     PinVec<t3d_pose> hPoses; std::vector<PoseCall> poseCalls; uint32_t posedBones = 0;     // this frame's t3d_submit_poses calls
     size_t framePosesOff = 0;
 
@@ -323,7 +325,7 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (cudaEvent_t e : ctx->evChunk) cudaEventDestroy(e);
     for (auto& kv : ctx->skeletons) if (kv.second.block) cudaFree(kv.second.block);
     for (auto& kv : ctx->animations) if (kv.second.block) cudaFree(kv.second.block);
-    ctx->hPoses.release();
+    ctx->hPoses.release(); ctx->hPoseChains.release();
     DevBuf* bufs[] = {&ctx->dVolumes, &ctx->dFrame, &ctx->dStage,
                       &ctx->dLightsU, &ctx->dStats, &ctx->dClip, &ctx->dClipXY, &ctx->dLight, &ctx->dWpos, &ctx->dUnbill,
                       &ctx->dTnrm, &ctx->dTdepth, &ctx->dSorted, &ctx->dHist, &ctx->dTileSurv, &ctx->dTileOut,
@@ -576,7 +578,7 @@ int t3d_frame_begin(t3d_ctx* ctx, const t3d_camera* cam, const t3d_world* world)
     ctx->anyLit = ctx->anySkinned = ctx->anyUnbill = ctx->anySubdiv = false;
     ctx->bonesAffine = ctx->transformsAffine = !ctx->forceFullUpload;
     ctx->tmplSpanMax = 1;
-    ctx->hPoses.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
+    ctx->hPoses.clear(); ctx->hPoseChains.clear(); ctx->poseCalls.clear(); ctx->posedBones = 0;
     ctx->trsGroups.clear(); ctx->nTrsDraws = 0; ctx->trsUniform = true;
     for (auto& u : ctx->volumeUse) u.clear();
     ctx->inFrame = true; ctx->executed = false; ctx->haveResults = false;
@@ -813,7 +815,7 @@ static int submit_poses(t3d_ctx* ctx, const char* who, uint64_t skeleton_id, boo
     }
     if ((uint64_t)ctx->posedBones + (uint64_t)n * sk->second.nBones >= POSE_TAG) return bad(T3D_E_INVALID, "too many posed bones in one frame");
     PoseCall c; c.skeleton = skeleton_id; c.animation = animation_id; c.firstPose = (uint32_t)ctx->hPoses.n; c.nPoses = n; c.firstBone = ctx->posedBones;
-    c.fromAnimation = blended ? from_animation_id : 0; c.blended = blended;
+    c.fromAnimation = blended ? from_animation_id : 0; c.blended = blended; c.nLevels = 0;
     CU(ctx->hPoses.reserve(ctx->hPoses.n + n));
     memcpy(ctx->hPoses.p + ctx->hPoses.n, poses, sizeof(t3d_pose) * (size_t)n);
     ctx->hPoses.n += n;
@@ -830,6 +832,32 @@ int t3d_submit_poses(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t animation_id, 
 int t3d_submit_poses_blended(t3d_ctx* ctx, uint64_t skeleton_id, uint64_t from_animation_id, uint64_t animation_id, const t3d_pose* poses,
                              uint32_t n, uint32_t* offset) {
     return submit_poses(ctx, "t3d_submit_poses_blended", skeleton_id, true, from_animation_id, animation_id, poses, n, offset);
+}
+
+int t3d_submit_pose_chains(t3d_ctx* ctx, uint64_t skeleton_id, const uint64_t* animation_ids, uint32_t n_levels, const t3d_pose_chain* poses,
+                           uint32_t n, uint32_t* offset) {
+    if (!ctx || !offset || !animation_ids || (n && !poses)) return fail(ctx, T3D_E_INVALID, "t3d_submit_pose_chains: NULL argument");
+    if (!ctx->inFrame || ctx->executed) return fail(ctx, T3D_E_STATE, "t3d_submit_pose_chains: not between frame_begin and frame_execute");
+    if (n_levels < 1 || n_levels > T3D_POSE_CHAIN_MAX) return fail(ctx, T3D_E_INVALID, "t3d_submit_pose_chains: n_levels must be 1 .. T3D_POSE_CHAIN_MAX");
+    auto sk = ctx->skeletons.find(skeleton_id);
+    if (sk == ctx->skeletons.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_pose_chains: unknown skeleton");
+    for (uint32_t k = 0; k < n_levels; k++) {
+        auto an = ctx->animations.find(animation_ids[k]);
+        if (an == ctx->animations.end()) return fail(ctx, T3D_E_NOTFOUND, "t3d_submit_pose_chains: unknown animation");
+        if (an->second.nBones > sk->second.nBones) return fail(ctx, T3D_E_INVALID, "t3d_submit_pose_chains: the animation has more bones than the skeleton");
+    }
+    if ((uint64_t)ctx->posedBones + (uint64_t)n * sk->second.nBones >= POSE_TAG) return fail(ctx, T3D_E_INVALID, "t3d_submit_pose_chains: too many posed bones in one frame");
+    PoseCall c; memset(&c, 0, sizeof c);
+    c.skeleton = skeleton_id; c.firstPose = (uint32_t)ctx->hPoseChains.n; c.nPoses = n; c.firstBone = ctx->posedBones; c.nLevels = n_levels;
+    for (uint32_t k = 0; k < n_levels; k++) c.chain[k] = animation_ids[k];
+    ctx->hPoseChains.mapped = true;
+    CU(ctx->hPoseChains.reserve(ctx->hPoseChains.n + n));
+    memcpy(ctx->hPoseChains.p + ctx->hPoseChains.n, poses, sizeof(t3d_pose_chain) * (size_t)n);
+    ctx->hPoseChains.n += n;
+    ctx->poseCalls.push_back(c);
+    *offset = POSE_TAG | ctx->posedBones;
+    ctx->posedBones += n * sk->second.nBones;
+    return T3D_OK;
 }
 
 int t3d_submit_bones(t3d_ctx* ctx, const float* matrices16, uint32_t n, uint32_t* offset) {
@@ -1447,7 +1475,17 @@ int t3d_frame_execute(t3d_ctx* ctx) {
             pb.out = ctx->pBones + 16 * ((size_t)ctx->frameBoneCount + c.firstBone);
             // small skeletons (every ordinary character) ride as extra blocks of k_prep_draws: no launch of their own, and
             // their PCIe round trip and double-precision Slerp overlap the draw records' fetch
-            if (c.blended) {      // players in the middle of a blend: k_pose_bones<true>, a launch of its own (transitions are short and rare)
+            if (c.nLevels) {      // blends interrupted by further Play() calls: k_pose_chain reads its 96-byte records from pinned memory
+                PoseChain ch; memset(&ch, 0, sizeof ch);
+                ch.nLevels = c.nLevels;
+                for (uint32_t k = 0; k < c.nLevels; k++) {
+                    const Animation& A = ctx->animations.at(c.chain[k]);
+                    ch.level[k].bones = A.nBones; ch.level[k].tracks = A.tracks; ch.level[k].keyTimes = A.keyTimes; ch.level[k].keyValues = A.keyValues;
+                }
+                pb.poses = reinterpret_cast<const t3d_pose*>(ctx->hPoseChains.p + c.firstPose);
+                CU(launch_pose_chain(s, pb, ch)); ctx->launches += 1;
+            }
+            else if (c.blended) {      // players in the middle of a blend: k_pose_bones<true>, a launch of its own (transitions are short and rare)
                 PoseBlend bl; memset(&bl, 0, sizeof bl);
                 if (c.fromAnimation) {
                     const Animation& F = ctx->animations.at(c.fromAnimation);

@@ -284,5 +284,9 @@ struct PoseBlend {
     uint32_t fromBones;                                 // 0: the previous state animated nothing
     const t3d_track* tracks; const float* keyTimes; const float4* keyValues;
 };
+// t3d_submit_pose_chains: the animations played since the last finished blend (stand-alone k_pose_chain only); the batch's pose
+// records are t3d_pose_chain (24 floats)
+struct PoseChainLevel { uint32_t bones; const t3d_track* tracks; const float* keyTimes; const float4* keyValues; };
+struct PoseChain { uint32_t nLevels; PoseChainLevel level[T3D_POSE_CHAIN_MAX]; };
 
 }  // namespace t3d

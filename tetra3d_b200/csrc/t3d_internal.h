@@ -89,6 +89,7 @@ void launch_ao(cudaStream_t s, const float* pos, uint32_t vstride, const uint32_
 
 // t3d_pose.cu -- bone poses evaluated on the device
 cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb, const PoseBlend* blend = nullptr);
+cudaError_t launch_pose_chain(cudaStream_t s, const PoseBatch& pb, const PoseChain& ch);
 size_t pose_batch_smem(uint32_t nBones);        // shared memory a block needs for a skeleton of nBones
 
 }  // namespace t3d

@@ -120,7 +120,7 @@ k_prep_draws(const __grid_constant__ PrepFrame pf, const __grid_constant__ Frame
         if (bid < nPoseBlocks) {
             uint32_t i = 0;
             while (i + 1 < pp.nPoseBatches && bid >= pp.poseBlock[i + 1]) i++;
-            pose_block<false>(pp.pose[i], PoseBlend(), bid - pp.poseBlock[i], reinterpret_cast<float*>(prepSmem));
+            pose_block<POSE_PLAIN>(pp.pose[i], PoseBlend(), PoseChain(), bid - pp.poseBlock[i], reinterpret_cast<float*>(prepSmem));
             return;
         }
         bid -= nPoseBlocks;

@@ -19,11 +19,17 @@
 
 namespace t3d {
 
-template <bool BLEND>
+template <int MODE>
 __global__ void __launch_bounds__(POSE_THREADS)
 k_pose_bones(const __grid_constant__ PoseBatch pb, const __grid_constant__ PoseBlend bl) {
     extern __shared__ float poseSmem[];
-    pose_block<BLEND>(pb, bl, blockIdx.x, poseSmem);
+    pose_block<MODE>(pb, bl, PoseChain(), blockIdx.x, poseSmem);
+}
+// t3d_submit_pose_chains: blends interrupted by further Play() calls
+__global__ void __launch_bounds__(POSE_THREADS)
+k_pose_chain(const __grid_constant__ PoseBatch pb, const __grid_constant__ PoseChain ch) {
+    extern __shared__ float poseSmem[];
+    pose_block<POSE_CHAIN>(pb, PoseBlend(), ch, blockIdx.x, poseSmem);
 }
 
 size_t pose_batch_smem(uint32_t nBones) { return pose_smem_bytes(nBones); }
@@ -34,11 +40,18 @@ cudaError_t launch_pose_bones(cudaStream_t s, const PoseBatch& pb, const PoseBle
     PoseBlend bl; memset(&bl, 0, sizeof bl);
     if (blend) {        // players in the middle of a blend (t3d_submit_poses_blended)
         bl = *blend;
-        cudaFuncSetAttribute(k_pose_bones<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
-        return launch_kernel(k_pose_bones<true>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
+        cudaFuncSetAttribute(k_pose_bones<POSE_BLEND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
+        return launch_kernel(k_pose_bones<POSE_BLEND>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
     }
-    cudaFuncSetAttribute(k_pose_bones<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
-    return launch_kernel(k_pose_bones<false>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
+    cudaFuncSetAttribute(k_pose_bones<POSE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_smem_bytes(POSE_MAX_BONES));
+    return launch_kernel(k_pose_bones<POSE_PLAIN>, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_smem_bytes(pb.nBones), s, false, pb, bl);
+}
+
+cudaError_t launch_pose_chain(cudaStream_t s, const PoseBatch& pb, const PoseChain& ch) {
+    if (!pb.nPoses || !pb.nBones) return cudaSuccess;
+    const uint32_t ipb = pose_armatures_per_block(pb.nBones);
+    cudaFuncSetAttribute(k_pose_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pose_chain_smem_bytes(POSE_MAX_BONES));
+    return launch_kernel(k_pose_chain, (pb.nPoses + ipb - 1) / ipb, POSE_THREADS, pose_chain_smem_bytes(pb.nBones), s, false, pb, ch);
 }
 
 }  // namespace t3d

@@ -185,10 +185,45 @@ __device__ inline BoneSample sample_bone(const t3d_track* __restrict__ tracks, c
     return o;
 }
 
+// forceUpdate's blend of one node (animation.go:859-897): f = prevAnimatedProperties[node], v = this frame's samples.
+__device__ inline BoneSample blend_sample(const BoneSample f, BoneSample v, const float bp) {
+    if (f.P) {                                              // animation.go:861-872
+        if (v.P) { v.px = f.px + ((v.px - f.px) * bp); v.py = f.py + ((v.py - f.py) * bp); v.pz = f.pz + ((v.pz - f.pz) * bp); }
+        else { v.px = f.px; v.py = f.py; v.pz = f.pz; v.P = true; }
+    }
+    if (f.S) {                                              // animation.go:874-884
+        if (v.S) { v.sx = f.sx + ((v.sx - f.sx) * bp); v.sy = f.sy + ((v.sy - f.sy) * bp); v.sz = f.sz + ((v.sz - f.sz) * bp); }
+        else { v.sx = f.sx; v.sy = f.sy; v.sz = f.sz; v.S = true; }
+    }
+    if (f.R) {                                              // animation.go:886-896
+        if (v.R) v.q = quat_unit(quat_slerp(f.q, v.q, bp));
+        else { v.q = f.q; v.R = true; }
+    }
+    return v;
+}
+// SetLocalRotation(q.ToMatrix4()) (animation.go:976, node.go:906-912): an all-zero matrix is ignored
+__device__ inline void apply_rotation(const Quat q, Mat4& rot) {
+    const Mat4 r = quat_to_matrix(q);
+    bool zero = true;
+#pragma unroll
+    for (int i = 0; i < 16; i++) zero = zero && (r.m[i >> 2][i & 3] == 0.0f);
+    if (!zero) rot = r;
+}
+
+// pose_block modes
+static const int POSE_PLAIN = 0, POSE_BLEND = 1, POSE_CHAIN = 2;
+// shared memory of a block evaluating t3d_pose_chain records (24 floats per armature)
+__host__ __device__ inline size_t pose_chain_smem_bytes(uint32_t nBones) {
+    const uint32_t ipb = pose_armatures_per_block(nBones);
+    return ((size_t)32 * ipb * nBones + (size_t)24 * ipb) * sizeof(float);
+}
+
 // The armatures [block * ipb, (block + 1) * ipb) of one batch, by the POSE_THREADS threads of a block (k_pose_bones, or the
-// pose blocks at the start of k_prep_draws' grid).  BLEND: the players are in the middle of a blend (animation.go:852-907).
-template <bool BLEND>
-__device__ inline void pose_block(const PoseBatch& pb, const PoseBlend& bl, const uint32_t block, float* poseSmem) {
+// pose blocks at the start of k_prep_draws' grid).  POSE_BLEND: the players are in the middle of a blend between two animations
+// (animation.go:852-907); POSE_CHAIN: of blends interrupted by further Play() calls (pb.poses then points at t3d_pose_chain records).
+template <int MODE>
+__device__ inline void pose_block(const PoseBatch& pb, const PoseBlend& bl, const PoseChain& ch, const uint32_t block, float* poseSmem) {
+    constexpr uint32_t PS = MODE == POSE_CHAIN ? 24u : 20u;             // floats per pose record
     // shared: local / world matrices as 16 planes of `slots` floats each (a thread's matrix is a column: no bank
     // conflicts), then the block's pose records
     const uint32_t nb = pb.nBones;
@@ -196,50 +231,49 @@ __device__ inline void pose_block(const PoseBatch& pb, const PoseBlend& bl, cons
     const uint32_t slots = ipb * nb;
     float* sLocal = poseSmem;
     float* sWorld = poseSmem + 16 * (size_t)slots;
-    float* sPose = sWorld + 16 * (size_t)slots;            // [ipb][20]
+    float* sPose = sWorld + 16 * (size_t)slots;            // [ipb][PS]
     const uint32_t inst0 = block * ipb;
     const uint32_t nInst = min(ipb, pb.nPoses - inst0);
     {   // this block's pose records, straight from the pinned frame block (one PCIe round trip)
-        const float* src = reinterpret_cast<const float*>(pb.poses + inst0);
-        for (uint32_t i = threadIdx.x; i < nInst * 20; i += POSE_THREADS) sPose[i] = src[i];
+        const float* src = reinterpret_cast<const float*>(pb.poses) + (size_t)inst0 * PS;
+        for (uint32_t i = threadIdx.x; i < nInst * PS; i += POSE_THREADS) sPose[i] = src[i];
     }
     __syncthreads();
     const uint32_t live = nInst * nb;
     for (uint32_t s = threadIdx.x; s < live; s += POSE_THREADS) {
         const uint32_t inst = s / nb, bone = s - inst * nb;
-        const float time = sPose[inst * 20 + 16];
         float px = pb.restPos[3 * bone], py = pb.restPos[3 * bone + 1], pz = pb.restPos[3 * bone + 2];
         float sx = pb.restScale[3 * bone], sy = pb.restScale[3 * bone + 1], sz = pb.restScale[3 * bone + 2];
         Mat4 rot = m4_load(pb.restRot + 16 * (size_t)bone);
-        BoneSample v;
-        v.P = v.S = v.R = false;
-        if (bone < pb.animBones) v = sample_bone(pb.tracks, pb.keyTimes, pb.keyValues, bone, time);
-        if (BLEND) {
-            if (bone < bl.fromBones) {                                  // prevAnimatedProperties[node] (animation.go:859)
-                const float bp = sPose[inst * 20 + 18];
-                const BoneSample f = sample_bone(bl.tracks, bl.keyTimes, bl.keyValues, bone, sPose[inst * 20 + 17]);
-                if (f.P) {                                              // animation.go:861-872
-                    if (v.P) { v.px = f.px + ((v.px - f.px) * bp); v.py = f.py + ((v.py - f.py) * bp); v.pz = f.pz + ((v.pz - f.pz) * bp); }
-                    else { v.px = f.px; v.py = f.py; v.pz = f.pz; v.P = true; }
-                }
-                if (f.S) {                                              // animation.go:874-884
-                    if (v.S) { v.sx = f.sx + ((v.sx - f.sx) * bp); v.sy = f.sy + ((v.sy - f.sy) * bp); v.sz = f.sz + ((v.sz - f.sz) * bp); }
-                    else { v.sx = f.sx; v.sy = f.sy; v.sz = f.sz; v.S = true; }
-                }
-                if (f.R) {                                              // animation.go:886-896
-                    if (v.R) v.q = quat_unit(quat_slerp(f.q, v.q, bp));
-                    else { v.q = f.q; v.R = true; }
-                }
+        if (MODE == POSE_CHAIN) {
+            // the fold of the reference's two maps over the animations played since the last finished blend (t3dgeo.h): `cur` is
+            // currentProperties[node], px .. rot what the Node holds
+            BoneSample cur; cur.P = cur.S = cur.R = false;
+            bool curDefined = false;
+            for (uint32_t k = 0; k < ch.nLevels; k++) {
+                const PoseChainLevel& L = ch.level[k];
+                bool has = false;
+                if (bone < L.bones) has = L.tracks[3 * bone].n_keys != 0 || L.tracks[3 * bone + 1].n_keys != 0 || L.tracks[3 * bone + 2].n_keys != 0;
+                if (!has) { curDefined = false; continue; }
+                BoneSample v = sample_bone(L.tracks, L.keyTimes, L.keyValues, bone, sPose[inst * PS + 16 + k]);
+                if (k > 0 && curDefined) v = blend_sample(cur, v, sPose[inst * PS + 20 + k]);
+                cur = v; curDefined = true;
+                if (v.P) { px = v.px; py = v.py; pz = v.pz; }
+                if (v.S) { sx = v.sx; sy = v.sy; sz = v.sz; }
+                if (v.R) apply_rotation(v.q, rot);
             }
-        }
-        if (v.P) { px = v.px; py = v.py; pz = v.pz; }
-        if (v.S) { sx = v.sx; sy = v.sy; sz = v.sz; }
-        if (v.R) {
-            const Mat4 r = quat_to_matrix(v.q);
-            bool zero = true;                                           // SetLocalRotation ignores an all-zero matrix (node.go:906-912)
-#pragma unroll
-            for (int i = 0; i < 16; i++) zero = zero && (r.m[i >> 2][i & 3] == 0.0f);
-            if (!zero) rot = r;
+        } else {
+            const float time = sPose[inst * PS + 16];
+            BoneSample v;
+            v.P = v.S = v.R = false;
+            if (bone < pb.animBones) v = sample_bone(pb.tracks, pb.keyTimes, pb.keyValues, bone, time);
+            if (MODE == POSE_BLEND) {
+                if (bone < bl.fromBones)                                // prevAnimatedProperties[node] (animation.go:859)
+                    v = blend_sample(sample_bone(bl.tracks, bl.keyTimes, bl.keyValues, bone, sPose[inst * PS + 17]), v, sPose[inst * PS + 18]);
+            }
+            if (v.P) { px = v.px; py = v.py; pz = v.pz; }
+            if (v.S) { sx = v.sx; sy = v.sy; sz = v.sz; }
+            if (v.R) apply_rotation(v.q, rot);
         }
         // Node.Transform (node.go:577-579): Scale x rotation x Translate
         Mat4 t = m4_mult(m4_scale(sx, sy, sz), rot);
@@ -260,7 +294,7 @@ __device__ inline void pose_block(const PoseBatch& pb, const PoseBlend& bl, cons
             const int32_t par = pb.parent[bone];
             if (par < 0) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) p.m[i >> 2][i & 3] = sPose[inst * 20 + i];
+                for (int i = 0; i < 16; i++) p.m[i >> 2][i & 3] = sPose[inst * PS + i];
             } else {
                 const uint32_t ps = inst * nb + (uint32_t)par;
 #pragma unroll

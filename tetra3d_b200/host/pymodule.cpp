@@ -272,8 +272,14 @@ PYBIND11_MODULE(_host, m) {
         .def("Blending", &AnimationPlayer::Blending)
         .def("BlendStartIsBlend", &AnimationPlayer::BlendStartIsBlend)
         .def("BlendFraction", &AnimationPlayer::BlendFraction)
-        .def("BlendFromPlayhead", [](AnimationPlayer& a) { return a.sampledFromPlayhead; })
-        .def("BlendFrom", [](AnimationPlayer& a) { return a.sampledFrom; })
+        .def("BlendFromPlayhead", [](AnimationPlayer& a) { return a.sampledChain.size() >= 2 ? a.sampledChain[a.sampledChain.size() - 2].playhead : 0.0f; })
+        .def("BlendFrom", [](AnimationPlayer& a) { return a.sampledChain.size() >= 2 ? a.sampledChain[a.sampledChain.size() - 2].anim : std::shared_ptr<Animation>(); })
+        // what the last update applied: [(Animation, playhead, blend fraction)], in the order the animations were played
+        .def("SampledChain", [](AnimationPlayer& a) {
+            py::list out;
+            for (auto& L : a.sampledChain) out.append(py::make_tuple(L.anim, L.playhead, L.bp));
+            return out;
+        })
         .def("SetClock", [](AnimationPlayer& a, py::object fn) {      // time.Now() in milliseconds, for deterministic tests (None: the steady clock)
             if (fn.is_none()) a.NowMs = nullptr;
             else a.NowMs = [fn]() { py::gil_scoped_acquire g; return fn().cast<int64_t>(); };

@@ -421,26 +421,22 @@ int64_t AnimationPlayer::now() const {
 void AnimationPlayer::Play(std::shared_ptr<Animation> anim) {                               // animation.go:517-566
     if (!anim) return;
     if (animation == anim && playing) return;
-    std::shared_ptr<Animation> previous = animation;
     animation = std::move(anim);
     playing = true;
     loopCount = 0;
     playhead = PlaySpeed > 0 ? 0.0f : animation->length;
     if (BlendTime > 0) {                    // animation.go:548-554: prevAnimatedProperties = copy of currentProperties
-        prevHas = currentHas;
-        prevAnimation = currentHas ? previous : nullptr;
-        prevPlayhead_ = sampledPlayhead;
-        prevIsBlend = currentHas && currentIsBlend;
+        if (currentHas) prevChain = curChain; else prevChain.clear();
         blendStarted = true;
         blendStartMs = now();
     }
     // assignChannels (animation.go:618-672) runs at the next updateValues because ChannelsUpdated is false now, and clears currentProperties
-    currentHas = false; currentIsBlend = false;
+    currentHas = false; curChain.clear();
 }
 
 void AnimationPlayer::Update(float dt) {                                                    // animation.go:810-824
     finished = false;
-    if (!playing && blendStarted) { blendStarted = false; prevHas = false; prevAnimation = nullptr; prevIsBlend = false; }
+    if (!playing && blendStarted) { blendStarted = false; prevChain.clear(); }
     forceUpdate(dt);
 }
 
@@ -449,15 +445,17 @@ void AnimationPlayer::forceUpdate(float dt) {                                   
     sampledPlayhead = playhead;             // the tracks are sampled here (animation.go:686-712): on the device, at the next Render
     sampled = true;
     // the blend this frame's targets go through (animation.go:852-907); `prevExists` per node is the device's business
-    sampledBlending = false; sampledBlendUnsupported = false; sampledFrom = nullptr;
-    if (blendStarted && prevHas) {
+    sampledChain.clear();
+    if (blendStarted && !prevChain.empty()) {
         float bp = (float)(now() - blendStartMs) / (BlendTime * 1000.0f);
         if (bp > 1) bp = 1;
-        sampledBlending = true; sampledBlend = bp; sampledFrom = prevAnimation; sampledFromPlayhead = prevPlayhead_;
-        sampledBlendUnsupported = prevIsBlend;
-        if (bp == 1) { blendStarted = false; prevHas = false; prevAnimation = nullptr; prevIsBlend = false; }   // animation.go:899-902
+        sampledChain = prevChain;
+        sampledChain.push_back(BlendLevel{animation, sampledPlayhead, bp});
+        if (bp == 1) { blendStarted = false; prevChain.clear(); }                           // animation.go:899-902
+    } else {
+        sampledChain.push_back(BlendLevel{animation, sampledPlayhead, 0.0f});
     }
-    if (BlendTime > 0) { currentHas = true; currentIsBlend = sampledBlending; }            // animation.go:909-937
+    if (BlendTime > 0) { curChain = sampledChain; currentHas = true; }                     // animation.go:909-937
     playhead += dt * PlaySpeed;
     float ph = playhead;
     prevPlayhead = ph;
@@ -869,46 +867,55 @@ void Camera::Render(Scene& scene, const std::vector<ILight*>& lights, const std:
         return id;
     };
     std::unordered_map<Model*, uint32_t> boneOffsets;
-    {   // armatures posed on the device: one t3d_submit_poses[_blended] call per (skeleton, animation[, animation blended from]), in first-use order
-        struct Group { Skeleton* sk; uint64_t anim, from; bool blended; std::vector<t3d_pose> poses; std::vector<Model*> models; };
+    {   // armatures posed on the device: one call per (skeleton, chain of animations), in first-use order
+        struct Group { Skeleton* sk; std::vector<uint64_t> anims; std::vector<t3d_pose_chain> poses; std::vector<Model*> models; };
         std::vector<Group> groups;
-        std::map<std::tuple<uint64_t, uint64_t, uint64_t, bool>, size_t> groupOf;
+        std::map<std::pair<uint64_t, std::vector<uint64_t>>, size_t> groupOf;
         for (auto& pd : pending) {
             if (flushOwnerRank[pd.flush] != shardRank) continue;
             Model* model = pd.model;
             if (!model->skinned || !model->skeleton || boneOffsets.count(model)) continue;
             Skeleton& sk = *model->skeleton;
             device->ensureSkeleton(sk);
-            uint64_t anim = 0, from = 0; bool blended = false;
-            t3d_pose P; std::memset(&P, 0, sizeof P);
+            std::vector<uint64_t> anims;           // empty: rest pose
+            t3d_pose_chain P; std::memset(&P, 0, sizeof P);
             if (AnimationPlayer* ap = model->posePlayer.get()) {
                 if (ap->animation && ap->sampled) {
                     if (ap->animation->relativeMotion)
                         throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer relative motion (animation.go:962-984) is not evaluated on the device");
-                    if (ap->sampledBlending && ap->sampledBlendUnsupported)
-                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer: a blend that starts from an unfinished blend (animation.go:905-908) is not evaluated on the device");
-                    anim = device->ensureAnimation(*ap->animation, sk);
-                    P.playhead = ap->sampledPlayhead;
-                    if (ap->sampledBlending) {
-                        blended = true;
-                        if (ap->sampledFrom) from = device->ensureAnimation(*ap->sampledFrom, sk);
-                        P.from_playhead = ap->sampledFromPlayhead;
-                        P.blend = ap->sampledBlend;
+                    if (ap->sampledChain.size() > T3D_POSE_CHAIN_MAX)
+                        throw T3DError(T3D_E_UNSUPPORTED, "AnimationPlayer: a blend interrupted by more than T3D_POSE_CHAIN_MAX - 1 further Play() calls (animation.go:905-908) is not evaluated on the device");
+                    for (size_t k = 0; k < ap->sampledChain.size(); k++) {
+                        const BlendLevel& L = ap->sampledChain[k];
+                        anims.push_back(device->ensureAnimation(*L.anim, sk));
+                        P.playhead[k] = L.playhead; P.blend[k] = L.bp;
                     }
                 }
             }
             m4_store(model->SkinRoot ? model->SkinRoot->Transform() : m4_identity(), P.root);
-            auto key = std::make_tuple(sk.id, anim, from, blended);
+            auto key = std::make_pair(sk.id, anims);
             auto it = groupOf.find(key);
-            if (it == groupOf.end()) { it = groupOf.emplace(key, groups.size()).first; groups.push_back(Group{&sk, anim, from, blended, {}, {}}); }
+            if (it == groupOf.end()) { it = groupOf.emplace(key, groups.size()).first; groups.push_back(Group{&sk, anims, {}, {}}); }
             Group& g = groups[it->second];
             g.poses.push_back(P); g.models.push_back(model);
             boneOffsets.emplace(model, 0u);        // filled in below
         }
         for (Group& g : groups) {
             uint32_t off = 0;
-            if (g.blended) check(ctx, t3d_submit_poses_blended(ctx, g.sk->id, g.from, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses_blended");
-            else check(ctx, t3d_submit_poses(ctx, g.sk->id, g.anim, g.poses.data(), (uint32_t)g.poses.size(), &off), "t3d_submit_poses");
+            const uint32_t n = (uint32_t)g.poses.size();
+            if (g.anims.size() <= 2) {          // plain poses and blends between two animations: the 80-byte record
+                std::vector<t3d_pose> poses(n);
+                for (uint32_t i = 0; i < n; i++) {
+                    std::memset(&poses[i], 0, sizeof(t3d_pose));
+                    std::memcpy(poses[i].root, g.poses[i].root, 64);
+                    if (g.anims.size() == 2) { poses[i].from_playhead = g.poses[i].playhead[0]; poses[i].playhead = g.poses[i].playhead[1]; poses[i].blend = g.poses[i].blend[1]; }
+                    else poses[i].playhead = g.poses[i].playhead[0];
+                }
+                if (g.anims.size() == 2) check(ctx, t3d_submit_poses_blended(ctx, g.sk->id, g.anims[0], g.anims[1], poses.data(), n, &off), "t3d_submit_poses_blended");
+                else check(ctx, t3d_submit_poses(ctx, g.sk->id, g.anims.empty() ? 0 : g.anims[0], poses.data(), n, &off), "t3d_submit_poses");
+            } else {
+                check(ctx, t3d_submit_pose_chains(ctx, g.sk->id, g.anims.data(), (uint32_t)g.anims.size(), g.poses.data(), n, &off), "t3d_submit_pose_chains");
+            }
             for (size_t i = 0; i < g.models.size(); i++) boneOffsets[g.models[i]] = off + (uint32_t)(i * g.sk->BoneCount());
         }
     }

@@ -231,11 +231,14 @@ struct Skeleton {
 // playhead logic of updateValues (animation.go:724-806) on the host and records the playhead the tracks were last
 // sampled at; the sampling itself, the bones' Transform() and boneInfluence run in k_pose_bones.
 //
-// Blending (BlendTime > 0, animation.go:548-554, 852-907): the player also records what the reference's
-// prevAnimatedProperties would hold -- the previous animation and the playhead its tracks were last sampled at -- and the
-// blend fraction of the frame; Camera::Render ships such armatures through t3d_submit_poses_blended.  A Play() in the middle
-// of an unfinished blend starts from a blend *result*, which has no (animation, playhead) form: the player says so
-// (BlendStartIsBlend) and Render refuses it.  Relative motion, markers and sequence callbacks need the host path and are refused.
+// Blending (BlendTime > 0, animation.go:548-554, 852-907): the reference blends from prevAnimatedProperties -- the copy Play()
+// took of currentProperties, i.e. of the targets of the last update -- into the playing animation's samples.  Those targets
+// are a function of a short history: the animations played since the last blend ended, each with the playhead and blend
+// fraction of its last update.  The player keeps that history (a chain of BlendLevels) instead of sampled values, and
+// Camera::Render ships it: t3d_submit_poses for a chain of one, t3d_submit_poses_blended for two (a blend between two
+// animations), t3d_submit_pose_chains for blends that were interrupted by further Play() calls (up to T3D_POSE_CHAIN_MAX levels;
+// longer ones are refused).  Relative motion, markers and sequence callbacks need the host path and are refused.
+struct BlendLevel { std::shared_ptr<Animation> anim; float playhead; float bp; };
 struct AnimationPlayer {
     std::shared_ptr<Node> RootNode;
     std::shared_ptr<Animation> animation;
@@ -248,15 +251,10 @@ struct AnimationPlayer {
     // ---- blend bookkeeping ----
     bool blendStarted = false;                  // !blendStart.IsZero()
     int64_t blendStartMs = 0;
-    bool prevHas = false;                       // prevAnimatedProperties is not empty
-    std::shared_ptr<Animation> prevAnimation;   // ... and holds this animation's targets
-    float prevPlayhead_ = 0;                    //     as sampled at this playhead
-    bool prevIsBlend = false;                   //     -- or a blend result, which has no such form
-    bool currentHas = false, currentIsBlend = false;    // currentProperties (animation.go:909-937): filled only while BlendTime > 0
-    // what the last forceUpdate applied, for Camera::Render
-    bool sampledBlending = false, sampledBlendUnsupported = false;
-    float sampledBlend = 0, sampledFromPlayhead = 0;
-    std::shared_ptr<Animation> sampledFrom;
+    std::vector<BlendLevel> prevChain;          // what prevAnimatedProperties holds (empty: nothing)
+    std::vector<BlendLevel> curChain;           // what currentProperties holds: filled only by updates with BlendTime > 0 (animation.go:909-937)
+    bool currentHas = false;                    //   ... and cleared by assignChannels at the first update after a Play() (animation.go:624)
+    std::vector<BlendLevel> sampledChain;       // what the last forceUpdate applied, for Camera::Render: the last level is the playing animation
     explicit AnimationPlayer(std::shared_ptr<Node> root) : RootNode(std::move(root)) {}
     void Play(std::shared_ptr<Animation> anim);         // animation.go:517-566
     void Update(float dt);                              // animation.go:810-824
@@ -267,9 +265,9 @@ struct AnimationPlayer {
     void Pause() { playing = false; }
     void Resume() { playing = true; }
     void forceUpdate(float dt);                         // animation.go:837 -> updateValues 674-806
-    bool Blending() const { return sampledBlending; }
-    bool BlendStartIsBlend() const { return sampledBlendUnsupported; }
-    float BlendFraction() const { return sampledBlend; }
+    bool Blending() const { return sampledChain.size() >= 2; }
+    bool BlendStartIsBlend() const { return sampledChain.size() >= 3; }       // the blend started from an unfinished blend (animation.go:905-908)
+    float BlendFraction() const { return sampledChain.empty() ? 0.0f : sampledChain.back().bp; }
     int64_t now() const;
 };
 
