@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 5      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points; 4: t3d_submit_instances; 5: t3d_camera carries the frustum terms, t3d_submit_instances the culling bounds */
+#define T3D_ABI_VERSION 6      /* 2: t3d_mesh_desc (auto-subdivision arrays) and t3d_volume_desc (cell lights) grew; 3: t3d_set_exact_lighting and the round-2 entry points; 4: t3d_submit_instances; 5: t3d_camera carries the frustum terms, t3d_submit_instances the culling bounds; 6: t3d_pose.from_playhead / blend (were reserved), t3d_submit_poses_blended, t3d_submit_pose_chains, t3d_set_async_download, t3d_frame_download_wait, t3d_set_skip_unused_depth_list */
 
 enum {
     T3D_OK            =  0,

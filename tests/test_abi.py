@@ -22,18 +22,19 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "libt3dgeo.so does not export %s" % n
-    assert lib.t3d_abi_version() == 5
+    assert lib.t3d_abi_version() == 6
 
 
 def test_struct_sizes_match_header():
     """ctypes mirrors of the ABI structs a cgo shim would declare: sizes must match the C compiler's."""
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world), sizeof(t3d_pose), sizeof(t3d_track));printf("%zu\\n", sizeof(t3d_instance));return 0;}\n'
+    src = '#include <stdio.h>\n#include "t3dgeo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(t3d_vertex), sizeof(t3d_light), sizeof(t3d_draw), sizeof(t3d_camera), sizeof(t3d_draw_result), sizeof(t3d_part_range), sizeof(t3d_world), sizeof(t3d_pose), sizeof(t3d_track));printf("%zu %zu\\n", sizeof(t3d_instance), sizeof(t3d_pose_chain));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "s")]).split()))
     assert sizes[9] == 40           # t3d_instance: position[3] + scale[3] + color[4]
+    assert sizes[10] == 96          # t3d_pose_chain: root[16] + playhead[4] + blend[4]
     assert sizes[0] == 48           # ebiten.Vertex: 12 x float32
     assert sizes[1] == 52 and sizes[5] == 16 and sizes[4] == 24
     assert sizes[2] % 8 == 0
