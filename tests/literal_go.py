@@ -1,0 +1,760 @@
+"""A second restatement of the hot path, written separately from oracle/t3d_oracle.c and structured like the Go source.
+
+TEST INFRASTRUCTURE ONLY (tests/test_literal_restatement.py).  Where the oracle is flat C over arrays, this file keeps the
+reference's own shape: `process_vertices` walks `meshPart.forEachTri` and fills `globalVertexTransforms` /
+`globalMeshAlteredVertexPositions` exactly as model.go:600-995 does, `SortingTriangleBucket` is the 512-bin bucket of
+sortingTriangles.go with its bins as Python lists, the lights are objects with `beginRender` / `beginModel` / `Light` /
+`VertexLight` (light.go:110-127, 175-269, 322-372), and `render` is the closure of camera.go:1507-1827 (lighting loop over
+the bucket, then the emit loop).  Arithmetic is numpy float32 scalars, one operation per Go operation, left to right.
+
+What it covers: static and skinned models (skinVertex, shape keys), billboards with their locks and the unbillboarded depth mode,
+the children of dynamic batches (each is its own render(rp)); no host callbacks or auto-subdivision; perspective
+and orthographic cameras; RenderDepth on or off (fog add / sub); vertex colours; texture sizes; perspective-corrected texture
+mapping; ambient, point (ranged and unranged), directional and LightVolume lights (all shading modes, cells with lights of their own),
+all three lighting modes, LightGroups; every sort mode.
+What it borrows from the oracle's binding: Matrix4.Mult / Inverted / the projection matrices / Node.Transform (pinned on their
+own: TestMatrixInversion, the numpy check of matrix_none.go) and Triangle.Center (load-time data).  It does not order the
+render pairs: results are compared per render(rp) call.
+"""
+import math
+
+import numpy as np
+
+from oracle import binding as O
+
+F = np.float32
+MAXF = F(np.finfo(np.float32).max)
+
+
+# ---- vector.go / matrix.go --------------------------------------------------------------------------------------------
+def sqrt32(x):                      # math32.Sqrt: float32(math.Sqrt(float64(x)))
+    return F(math.sqrt(float(x))) if x >= 0 else F(np.nan)
+
+
+def magnitude(v):                   # vector.go:191-193
+    return sqrt32(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+
+def unit(v):                        # vector.go:258-266 (also Vector4.Unit, vector.go:1869-1877: W is left alone)
+    l = magnitude(v)
+    if l < F(1e-8) or l == F(1):
+        return v
+    out = list(v)
+    out[0], out[1], out[2] = v[0] / l, v[1] / l, v[2] / l
+    return out
+
+
+def dot(a, b):                      # vector.go:526-528
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+
+
+def distance_squared_to(a, b):      # vector.go:242-247
+    x, y, z = a[0] - b[0], a[1] - b[1], a[2] - b[2]
+    return x * x + y * y + z * z
+
+
+def clamp(v, lo, hi):               # math32.Clamp
+    if v < lo:
+        return lo
+    if v > hi:
+        return hi
+    return v
+
+
+def mult_vec(m, v):                 # matrix.go:619-627
+    return [m[0][0] * v[0] + m[1][0] * v[1] + m[2][0] * v[2] + m[3][0],
+            m[0][1] * v[0] + m[1][1] * v[1] + m[2][1] * v[2] + m[3][1],
+            m[0][2] * v[0] + m[1][2] * v[1] + m[2][2] * v[2] + m[3][2]]
+
+
+def mat(a):
+    return np.asarray(a, F).reshape(4, 4)
+
+
+def go_round(x):                    # math32.Round = float32(math.Round(float64(x))): half away from zero
+    x = float(x)
+    if math.isnan(x) or math.isinf(x):
+        return F(x)
+    return F(math.copysign(math.floor(abs(x) + 0.5), x))
+
+
+def orthographic(near, far, right, left, top, bottom):      # NewProjectionMatrix4Orthographic through the oracle's matrix helper
+    out = np.zeros(16, F)
+    O.lib().orc_mat4_orthographic(float(near), float(far), float(right), float(left), float(top), float(bottom), O._fp(out))
+    return out.reshape(4, 4)
+
+
+def transposed(m):                  # matrix.go:218-230
+    return mat(m).T.copy()
+
+
+def decompose_rotation(m):          # matrix.go:202-208
+    r = np.eye(4, dtype=F)
+    for i in range(3):
+        r[i] = unit([m[i][0], m[i][1], m[i][2], m[i][3]])
+    return r
+
+
+def decompose(m):                   # matrix.go:181-196
+    position = [m[3][0], m[3][1], m[3][2]]
+    rotation = decompose_rotation(m)
+    inn = O.mat4_mult(m, transposed(rotation))
+    scale = [magnitude(inn[0]), magnitude(inn[1]), magnitude(inn[2])]
+    return position, scale, rotation
+
+
+def vec_equals(a, b):               # vector.go:415-425
+    eps = F(1e-4)
+    return not (abs(a[0] - b[0]) > eps or abs(a[1] - b[1]) > eps or abs(a[2] - b[2]) > eps)
+
+
+def cross(v, o):                    # vector.go:164-179
+    z = v[0] * o[1] - o[0] * v[1]
+    y = v[2] * o[0] - o[2] * v[0]
+    x = v[1] * o[2] - o[1] * v[2]
+    return [x, y, z]
+
+
+def look_at(frm, to, up):           # matrix.go:788-815
+    if vec_equals(frm, to):
+        return np.eye(4, dtype=F)
+    z = unit([to[0] - frm[0], to[1] - frm[1], to[2] - frm[2]])
+    up = unit(list(up))
+    if vec_equals(z, up) or vec_equals(z, [-up[0], -up[1], -up[2]]):
+        if not vec_equals(up, [F(1), F(0), F(0)]):
+            up = [F(1), F(0), F(0)]             # WorldRight
+        else:
+            up = [F(0), F(0), F(1)]             # WorldBackward
+    x = unit(cross(up, z))
+    y = cross(z, x)
+    return np.array([[x[0], x[1], x[2], 0], [y[0], y[1], y[2], 0], [z[0], z[1], z[2], 0], [0, 0, 0, 1]], F)
+
+
+def up_vector(m):                   # matrix.go:161-167
+    return unit([m[1][0], m[1][1], m[1][2]])
+
+
+def forward(m):                     # matrix.go:170-176
+    return unit([m[2][0], m[2][1], m[2][2]])
+
+
+def world_rotation(node):           # node.go:916-938: decompose only when an ancestor is rotated
+    parent = node.parent
+    while parent is not None:
+        if not O.mat4_equals(mat(parent.rotation), np.eye(4, dtype=F)):
+            return decompose_rotation(O.node_world_transform(node).reshape(4, 4))
+        parent = parent.parent
+    return mat(node.rotation)
+
+
+def world_position(node):           # node.go:737-739
+    t = O.node_world_transform(node).reshape(4, 4)
+    return [t[3][0], t[3][1], t[3][2]]
+
+
+# ---- sortingTriangles.go -----------------------------------------------------------------------------------------------
+SORT_BACK_TO_FRONT, SORT_FRONT_TO_BACK, SORT_NONE = 0, 1, 2
+
+
+class SortingTriangleBucket:
+    def __init__(self, bin_count=512):
+        self.bins = [[] for _ in range(bin_count)]
+        self.unset = []
+        self.sort_mode = SORT_BACK_TO_FRONT
+
+    def clear(self):
+        for b in self.bins:
+            del b[:]
+        del self.unset[:]
+
+    def add_triangle(self, tri, depth):
+        self.unset.append((tri, depth))
+
+    def sort(self, min_range, max_range):                   # sortingTriangles.go:38-64
+        bin_count = len(self.bins)
+        range_diff = max_range - min_range
+        if range_diff == 0:
+            max_range = max_range + F(0.001)
+            range_diff = range_diff + F(0.001)
+        for tri, d in self.unset:
+            target = 0
+            if self.sort_mode != SORT_NONE and bin_count > 1:
+                depth = (d - min_range) / range_diff * F(bin_count)
+                t = clamp(depth, F(0), F(bin_count - 1))
+                target = int(t)
+            self.bins[target].append(tri)
+
+    def for_each(self, fn):                                 # sortingTriangles.go:93-125
+        if not self.unset:
+            return
+        order = range(len(self.bins) - 1, -1, -1) if self.sort_mode == SORT_BACK_TO_FRONT else range(len(self.bins))
+        i = 0
+        for b in order:
+            for tri in self.bins[b]:
+                fn(i, tri)
+                i += 1
+
+
+# ---- light.go ------------------------------------------------------------------------------------------------------------
+LIGHTING_DEFAULT, LIGHTING_FIXED_NORMALS, LIGHTING_DOUBLE_SIDED = 0, 1, 2
+
+
+class Globals:
+    """tetra3d.go:21-40: the scratch arrays ProcessVertices fills and the lights / emit loop read."""
+
+    def __init__(self, n):
+        self.transforms = [[F(0)] * 4 for _ in range(n)]
+        self.altered_positions = [[F(0)] * 3 for _ in range(n)]
+        self.altered_normals = [[F(0)] * 3 for _ in range(n)]
+        self.vertex_lights = [[F(0), F(0), F(0), F(1)] for _ in range(n)]
+        self.depth_unbillboarded = [F(0)] * n
+
+
+class AmbientLight:
+    def __init__(self, color, energy):
+        self.color, self.energy = [F(c) for c in color], F(energy)
+
+    def begin_render(self):                                 # light.go:110-112
+        self.result = [self.color[0] * self.energy, self.color[1] * self.energy, self.color[2] * self.energy]
+
+    def begin_model(self, model):
+        pass
+
+    def vertex_light(self, index, tri, model, g):           # light.go:116-120
+        c = g.vertex_lights[index]
+        c[0] = c[0] + self.result[0]; c[1] = c[1] + self.result[1]; c[2] = c[2] + self.result[2]
+
+    def light(self, tri, model, g):
+        for vi in tri.indices:
+            self.vertex_light(vi, tri, model, g)
+
+
+class PointLight:
+    def __init__(self, desc):
+        self.desc = desc
+        self.color, self.energy = [F(c) for c in desc.color], F(desc.energy)
+        self.light_range = F(desc.range)
+        self.light_range_squared = self.light_range * self.light_range
+
+    def world_position(self):
+        return world_position(self.desc.node)
+
+    def begin_render(self):
+        pass
+
+    def begin_model(self, model):                           # light.go:177-191
+        if model.skinned:
+            self.working_position = self.world_position()
+            return
+        pos, sca, rot = decompose(O.mat4_inverted(model.transform))
+        rp = mult_vec(rot, self.world_position())
+        inv = [F(1) / sca[0], F(1) / sca[1], F(1) / sca[2]]
+        self.working_position = [rp[0] + pos[0] * inv[0], rp[1] + pos[1] * inv[1], rp[2] + pos[2] * inv[2]]
+
+    def vertex_light(self, index, tri, model, g):           # light.go:193-258
+        vert_pos, vert_normal = g.altered_positions[index], g.altered_normals[index]
+        distance = distance_squared_to(self.working_position, vert_pos)
+        if self.light_range > 0:
+            if distance > self.light_range_squared:
+                return
+        else:
+            if F(1) / distance * self.energy < F(0.001):
+                return
+        light_vec = unit([self.working_position[0] - vert_pos[0], self.working_position[1] - vert_pos[1], self.working_position[2] - vert_pos[2]])
+        mat_ = tri.part.material
+        if mat_ is not None and mat_.lighting_mode == LIGHTING_FIXED_NORMALS:
+            vert_normal = light_vec
+        diffuse = dot(vert_normal, light_vec)
+        if mat_ is not None and mat_.lighting_mode == LIGHTING_DOUBLE_SIDED:
+            diffuse = F(abs(diffuse))
+        if diffuse > 0:
+            diffuse_factor = diffuse * (F(1.0) / (F(1.0) + (F(0.1) * distance))) * F(2)
+            if self.light_range_squared > 0:
+                dist_clamp = clamp((self.light_range_squared - distance) / distance, F(0), F(1))
+                diffuse_factor = diffuse_factor * dist_clamp
+            c = g.vertex_lights[index]
+            c[0] = c[0] + self.color[0] * diffuse_factor * self.energy
+            c[1] = c[1] + self.color[1] * diffuse_factor * self.energy
+            c[2] = c[2] + self.color[2] * diffuse_factor * self.energy
+
+    def light(self, tri, model, g):
+        for vi in tri.indices:
+            self.vertex_light(vi, tri, model, g)
+
+
+class DirectionalLight:
+    def __init__(self, desc):
+        self.desc = desc
+        self.color, self.energy = [F(c) for c in desc.color], F(desc.energy)
+
+    def begin_render(self):                                 # light.go:322-324
+        self.working_forward = forward(world_rotation(self.desc.node))
+
+    def begin_model(self, model):                           # light.go:326-330
+        if not model.skinned:
+            self.working_model_rotation = transposed(O.mat4_inverted(model.world_rotation))
+
+    def vertex_light(self, index, tri, model, g):           # light.go:332-360
+        mat_ = tri.part.material
+        if mat_ is not None and mat_.lighting_mode == LIGHTING_FIXED_NORMALS:
+            normal = self.working_forward
+        elif model.skinned:
+            normal = g.altered_normals[index]
+        else:
+            normal = mult_vec(self.working_model_rotation, g.altered_normals[index])
+        diffuse_factor = dot(normal, self.working_forward)
+        if mat_ is not None and mat_.lighting_mode == LIGHTING_DOUBLE_SIDED:
+            diffuse_factor = F(abs(diffuse_factor))
+        if diffuse_factor <= 0:
+            return
+        c = g.vertex_lights[index]
+        c[0] = c[0] + self.color[0] * diffuse_factor * self.energy
+        c[1] = c[1] + self.color[1] * diffuse_factor * self.energy
+        c[2] = c[2] + self.color[2] * diffuse_factor * self.energy
+
+    def light(self, tri, model, g):
+        for vi in tri.indices:
+            self.vertex_light(vi, tri, model, g)
+
+
+LV_PER_VERTEX_WITHOUT_NORMAL, LV_PER_VERTEX_WITH_NORMAL, LV_PER_OBJECT, LV_OFF = 0, 1, 2, 3
+
+
+class LightVolume:
+    """light.go:376-396, 567-680, 717-728, 1267-1272: a grid of cell colours in world space; cells may carry lights of their own."""
+
+    def __init__(self, desc):
+        v = desc.volume
+        self.color, self.energy = [F(c) for c in desc.color], F(desc.energy)
+        self.dim_min, self.dim_max = [F(c) for c in v.dim_min], [F(c) for c in v.dim_max]
+        self.cell_size = [F(c) for c in v.cell_size]
+        self.cell_count = [int(c) for c in v.cell_count]
+        self.colors = np.asarray(v.colors, F).reshape(-1, 3)
+        self.offset, self.light_bias = [F(c) for c in v.offset], [F(c) for c in v.light_bias]
+        self.cell_lights = {}
+        self.use_lights_render_set = []
+        for key, lights in (v.cell_lights or {}).items():
+            objs = [make_light(ld) for ld in lights]
+            self.cell_lights[tuple(int(k) for k in key)] = objs
+            self.use_lights_render_set.extend(objs)
+
+    def begin_render(self):
+        for l in self.use_lights_render_set:
+            l.begin_render()
+
+    def begin_model(self, model):
+        for l in self.use_lights_render_set:
+            l.begin_model(model)
+
+    def convert_to_xyz_indices(self, w):                    # light.go:717-724
+        out = []
+        for k in range(3):
+            out.append(int(go_round((w[k] - self.offset[k] - self.dim_min[k] - (self.cell_size[k] / F(2))) / self.cell_size[k])))
+        return out
+
+    def get_light_cell(self, x, y, z):                      # light.go:1267-1272: (colour, lights) or None
+        cx, cy, cz = self.cell_count
+        if x < 0 or y < 0 or z < 0 or x >= cx or y >= cy or z >= cz:
+            return None
+        return self.colors[x + (y * cx) + (z * cx * cy)], self.cell_lights.get((x, y, z), [])
+
+    def contains(self, p):                                  # mesh.go:82-84
+        return all(p[k] >= self.dim_min[k] for k in range(3)) and all(p[k] <= self.dim_max[k] for k in range(3))
+
+    def vertex_light(self, vi, tri, model, g):              # light.go:583-663
+        object_shading_mode = 0
+        cell_color = [F(0), F(0), F(0)]
+        transform = model.transform
+        cell_size = [self.cell_size[0] / F(2), self.cell_size[1] / F(2), self.cell_size[2] / F(2)]
+        mat_ = tri.part.material
+        if mat_ is not None:
+            object_shading_mode = mat_.light_volume_shading_mode
+        if mat_ is not None and mat_.light_volume_shading_mode == LV_PER_OBJECT:
+            x, y, z = self.convert_to_xyz_indices([model.transform[3][0], model.transform[3][1], model.transform[3][2]])
+            cell = self.get_light_cell(x, y, z)
+            if cell is not None:
+                cell_color = [cell[0][0], cell[0][1], cell[0][2]]
+        else:
+            vert_pos = [F(0), F(0), F(0)]
+            vert_pos_with_normal = [F(0), F(0), F(0)]
+            ap, an = g.altered_positions[vi], g.altered_normals[vi]
+            if model.skinned:
+                if object_shading_mode == LV_PER_VERTEX_WITH_NORMAL:
+                    vert_pos_with_normal = [vert_pos[k] + an[k] * cell_size[k] + self.light_bias[k] for k in range(3)]
+                else:
+                    vert_pos = [ap[k] + self.light_bias[k] for k in range(3)]
+            else:
+                if object_shading_mode == LV_PER_VERTEX_WITH_NORMAL:
+                    t = mult_vec(transform, [ap[k] + an[k] * cell_size[k] for k in range(3)])
+                    vert_pos_with_normal = [t[k] + self.light_bias[k] for k in range(3)]
+                else:
+                    t = mult_vec(transform, ap)
+                    vert_pos = [t[k] + self.light_bias[k] for k in range(3)]
+            if not self.contains(vert_pos):                 # (the unshifted position even in the with-normal mode, where it is still zero)
+                return
+            cell_color = [F(0), F(0), F(0)]
+            if object_shading_mode == LV_PER_VERTEX_WITH_NORMAL:
+                x, y, z = self.convert_to_xyz_indices(vert_pos_with_normal)
+            else:
+                x, y, z = self.convert_to_xyz_indices(vert_pos)
+            cell = self.get_light_cell(x, y, z)
+            if cell is not None:
+                cell_color = [cell[0][0], cell[0][1], cell[0][2]]
+                for l in cell[1]:
+                    l.vertex_light(vi, tri, model, g)
+        c = g.vertex_lights[vi]
+        c[0] = c[0] + self.color[0] * cell_color[0] * self.energy
+        c[1] = c[1] + self.color[1] * cell_color[1] * self.energy
+        c[2] = c[2] + self.color[2] * cell_color[2] * self.energy
+
+    def light(self, tri, model, g):                         # light.go:667-680
+        mat_ = tri.part.material
+        if mat_ is not None and mat_.light_volume_shading_mode == LV_OFF:
+            return
+        for vi in tri.indices:
+            self.vertex_light(vi, tri, model, g)
+
+
+def make_light(desc):
+    if desc.type == 0:
+        return AmbientLight(desc.color, desc.energy)
+    if desc.type == 1:
+        return PointLight(desc)
+    if desc.type == 2:
+        return DirectionalLight(desc)
+    return LightVolume(desc)
+
+
+# ---- mesh.go / model.go ----------------------------------------------------------------------------------------------------
+class Triangle:
+    def __init__(self, tid, indices, center, part):
+        self.id, self.indices, self.center, self.part = tid, [int(i) for i in indices], [F(c) for c in center], part
+
+
+class Model:
+    def __init__(self, desc):
+        self.desc = desc
+        self.transform = O.node_world_transform(desc.node).reshape(4, 4)
+        self.world_rotation = world_rotation(desc.node)
+        self.color = [F(c) for c in desc.color]
+        mesh = desc.mesh
+        centers = O.triangle_centers(mesh.positions, mesh.indices)
+        self.parts = []
+        for p in mesh.parts:
+            self.parts.append([Triangle(t, mesh.indices[t], centers[t], p) for t in range(p.tri_start, p.tri_end + 1)])
+        # skinned models (model.go:33-40): boneInfluence of every joint, given directly or posed from a skeleton + animation
+        self.bone_influences = None
+        if desc.bone_influences is not None:
+            self.bone_influences = np.asarray(desc.bone_influences, F).reshape(-1, 4, 4)
+        elif desc.pose is not None:
+            p = desc.pose
+            if p.blend_ms is not None:
+                bi = O.pose_bones_blended(p.skeleton, p.blend_from, p.from_playhead, p.animation, p.playhead, p.blend_fraction(), O.node_world_transform(p.root))
+            else:
+                bi = O.pose_bones(p.skeleton, p.animation, p.playhead, O.node_world_transform(p.root))
+            self.bone_influences = bi.reshape(-1, 4, 4)
+        self.skinned = self.bone_influences is not None
+        lo, hi = mesh.positions.min(axis=0), mesh.positions.max(axis=0)         # Dimensions (mesh.go:718-752): bounds of the vertices
+        self.max_span = magnitude([hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]])
+
+    def is_transparent(self, part):                         # model.go:1274-1284 (TransparencyMode: 0 auto, 1 opaque, 2 alpha clip, 3 transparent)
+        m = part.material
+        if m is not None:
+            mat_transparent = m.transparency_mode == 3 or not m.blend_source_over or (m.transparency_mode == 0 and F(m.color[3]) < F(0.999))
+            model_transparent = m.transparency_mode != 1 and self.color[3] < F(0.999)
+            return mat_transparent or model_transparent
+        return self.color[3] < F(0.999)
+
+
+def vertex_position_with_shape_keys(mesh, vi):             # mesh.go:796-807
+    out = [mesh.positions[vi][0], mesh.positions[vi][1], mesh.positions[vi][2]]
+    if mesh.key_weights is not None and len(mesh.key_weights) > 0:
+        for k in range(len(mesh.key_weights)):
+            w = mesh.key_weights[k]
+            out[0] = out[0] + mesh.key_positions[k][vi][0] * w
+            out[1] = out[1] + mesh.key_positions[k][vi][1] * w
+            out[2] = out[2] + mesh.key_positions[k][vi][2] * w
+    return out
+
+
+def vertex_normal_with_shape_keys(mesh, vi):               # mesh.go:811-822
+    out = [mesh.normals[vi][0], mesh.normals[vi][1], mesh.normals[vi][2]]
+    if mesh.key_weights is not None and len(mesh.key_weights) > 0:
+        for k in range(len(mesh.key_weights)):
+            w = mesh.key_weights[k]
+            out[0] = out[0] + mesh.key_normals[k][vi][0] * w
+            out[1] = out[1] + mesh.key_normals[k][vi][1] * w
+            out[2] = out[2] + mesh.key_normals[k][vi][2] * w
+    return out
+
+
+def skin_vertex(model, vi):                                 # model.go:559-596
+    mesh = model.desc.mesh
+    skin = np.zeros((4, 4), F)                              # skinMatrix.Clear()
+    for b in range(int(mesh.n_influences[vi])):             # model.bones[vertID]: one entry per influence the loader kept
+        weight = F(mesh.weights[vi][b])
+        if weight == 0:
+            continue
+        influence = model.bone_influences[int(mesh.bones[vi][b])]
+        if weight == 1:
+            skin = influence.copy()
+            break
+        skin = skin + influence * weight                    # Add(Scale(weight)): element by element
+    vert_out = mult_vec(skin, vertex_position_with_shape_keys(mesh, vi))
+    skin = skin.copy()
+    skin[3][0] = F(0); skin[3][1] = F(0); skin[3][2] = F(0); skin[3][3] = F(1)
+    normal = mult_vec(skin, vertex_normal_with_shape_keys(mesh, vi))
+    return vert_out, normal
+
+
+class Camera:
+    def __init__(self, desc):
+        self.desc = desc
+        self.near, self.far = F(desc.near), F(desc.far)
+        self.position = world_position(desc.node)
+        cam_pos = [-self.position[0], -self.position[1], -self.position[2]]                    # camera.go:638-648
+        self.view = O.mat4_mult(O.mat4_translate(*cam_pos), transposed(world_rotation(desc.node)))
+        if desc.perspective:                                                                   # camera.go:651-680
+            self.projection = O.mat4_perspective(desc.field_of_view, desc.near, desc.far, desc.width, desc.height)
+        else:
+            asr = F(desc.height) / F(desc.width)
+            s = F(desc.ortho_scale)
+            self.projection = orthographic(desc.near, desc.far, F(1) * s, F(-1) * s, asr * s, -asr * s)
+        self.vp = O.mat4_mult(self.view, self.projection)                                      # camera.go:1329
+        self.camera_up = up_vector(world_rotation(desc.node))                                  # camera.go:1085-1088 (Camera.Clear)
+
+
+def process_vertices(model, part_index, camera, bucket, g):
+    """model.go:600-995 with processOnlyVisible = true, for a model without billboarding or callbacks.
+    Returns False for the early-out of model.go:604-606."""
+    bucket.clear()
+    part = model.desc.mesh.parts[part_index]
+    if (model.color[3] == 0 and model.is_transparent(part)) or not model.desc.visible:
+        return False
+    mesh = model.desc.mesh
+    model_transform = model.transform
+    cam_pos = camera.position
+    p, s, r = decompose(O.mat4_inverted(model_transform))                                      # model.go:627-628
+    rc = mult_vec(r, cam_pos)
+    inv = [F(1) / s[0], F(1) / s[1], F(1) / s[2]]
+    inverted_cam_pos = [rc[0] + p[0] * inv[0], rc[1] + p[1] * inv[1], rc[2] + p[2] * inv[2]]
+    mat_ = part.material
+    base = model_transform
+    if mat_ is not None and mat_.billboard_enabled:                                            # model.go:634-695
+        up = [F(0), F(1), F(0)]
+        if mat_.billboard_up_direction == 1:                                                   # BillboardYUpCameraY
+            up = camera.camera_up
+        model_world_position = [model_transform[3][0], model_transform[3][1], model_transform[3][2]]
+        lookat = look_at(model_world_position, cam_pos, up)
+        if mat_.billboard_lock_x:
+            lookat[0] = [1, 0, 0, 0]
+            row = list(lookat[1]); row[0] = F(0); lookat[1] = unit(row)
+            row = list(lookat[2]); row[0] = F(0); lookat[2] = unit(row)
+        if mat_.billboard_lock_y:
+            lookat[1] = [0, 1, 0, 0]
+            row = list(lookat[0]); row[1] = F(0); lookat[0] = unit(row)
+            row = list(lookat[2]); row[1] = F(0); lookat[2] = unit(row)
+        if mat_.billboard_lock_z:
+            lookat[2] = [0, 0, 1, 0]
+            row = list(lookat[0]); row[2] = F(0); lookat[0] = unit(row)
+            row = list(lookat[1]); row[2] = F(0); lookat[1] = unit(row)
+        bp, bs, br = decompose(base)
+        base = O.mat4_mult(O.mat4_mult(br, O.mat4_scale(bs[0], bs[1], bs[2])), lookat)
+        base[3] = [bp[0], bp[1], bp[2], F(1)]
+    mvp = O.mat4_mult(base, camera.vp)
+    unbillboarded = mat_ is not None and mat_.billboarded_depth_mode == 1                      # model.go:699-705
+    unaltered_mvp = O.mat4_mult(model_transform, camera.vp) if unbillboarded else None
+    min_depth, max_depth = MAXF, -MAXF
+    snapping = F(camera.desc.vertex_snapping)
+    for tri in model.parts[part_index]:
+        for vi in tri.indices:
+            if model.skinned:                                                                  # model.go:760-776: world space, vpMatrix
+                vert, normal = skin_vertex(model, vi)
+                m = camera.vp
+            else:                                                                              # model.go:778-800
+                vert = vertex_position_with_shape_keys(mesh, vi)
+                normal = vertex_normal_with_shape_keys(mesh, vi)
+                m = mvp
+            g.altered_positions[vi] = vert
+            g.altered_normals[vi] = normal
+            t = g.transforms[vi]
+            t[0] = m[0][0] * vert[0] + m[1][0] * vert[1] + m[2][0] * vert[2] + m[3][0]
+            t[1] = m[0][1] * vert[0] + m[1][1] * vert[1] + m[2][1] * vert[2] + m[3][1]
+            t[2] = m[0][2] * vert[0] + m[1][2] * vert[1] + m[2][2] * vert[2] + m[3][2]
+            t[3] = m[0][3] * vert[0] + m[1][3] * vert[1] + m[2][3] * vert[2] + m[3][3]
+            if unbillboarded and not model.skinned:                                            # model.go:802-805
+                u = unaltered_mvp
+                g.depth_unbillboarded[vi] = u[0][2] * vert[0] + u[1][2] * vert[1] + u[2][2] * vert[2] + u[3][2]
+            if snapping > 0:                                                                   # model.go:812-817
+                for k in range(3):
+                    t[k] = go_round(t[k] * snapping) / snapping
+        out_of_bounds = True
+        tv = []
+        for vi in tri.indices:
+            w = g.transforms[vi][3]
+            if w < 0:
+                w = F(0.000001)
+            tv.append((g.transforms[vi][0] / w, g.transforms[vi][1] / w))
+            if g.transforms[vi][2] + F(1) >= camera.near and g.transforms[vi][2] < camera.far:
+                out_of_bounds = False
+        if out_of_bounds:
+            continue
+        h = F(0.5)
+        if (tv[0][0] < -h and tv[1][0] < -h and tv[2][0] < -h) or (tv[0][0] > h and tv[1][0] > h and tv[2][0] > h) or \
+           (tv[0][1] < -h and tv[1][1] < -h and tv[2][1] < -h) or (tv[0][1] > h and tv[1][1] > h and tv[2][1] > h):
+            continue
+        if mat_ is not None and mat_.backface_culling:                                         # model.go:893-916
+            n0x, n0y = tv[0][0] - tv[1][0], tv[0][1] - tv[1][1]
+            n1x, n1y = tv[1][0] - tv[2][0], tv[1][1] - tv[2][1]
+            nor = (n0x * n1y) - (n1x * n0y)
+            if nor < 0:
+                continue
+        if model.skinned:                                                                      # model.go:839-856, 934-940
+            cx = cy = cz = F(0)
+            for vi in tri.indices:
+                cx = cx + g.altered_positions[vi][0]; cy = cy + g.altered_positions[vi][1]; cz = cz + g.altered_positions[vi][2]
+            dx, dy, dz = cam_pos[0] - (cx / F(3)), cam_pos[1] - (cy / F(3)), cam_pos[2] - (cz / F(3))
+        else:                                                                                  # model.go:942-948
+            dx, dy, dz = inverted_cam_pos[0] - tri.center[0], inverted_cam_pos[1] - tri.center[1], inverted_cam_pos[2] - tri.center[2]
+        depth = dx * dx + dy * dy + dz * dz
+        if np.isnan(depth) or np.isinf(depth):
+            continue
+        if depth < min_depth:
+            min_depth = depth
+        if depth > max_depth:
+            max_depth = depth
+        bucket.add_triangle(tri, depth)
+    bucket.sort(min_depth, max_depth)
+    return True
+
+
+def render_scene(desc):
+    """Camera.Render's light set-up (camera.go:1275-1303) and the render closure (camera.go:1507-1827) for every visible
+    (model, part); returns {(model index, part index): (triangle ids in emitted order, colour records (n, 12), depth records (n, 12))}."""
+    cam = Camera(desc.camera)
+    world = desc.world
+    scene_lights = []
+    if world.present and world.lighting_on and world.ambient_visible:
+        amb = AmbientLight(world.ambient_color, world.ambient_energy)
+        amb.begin_render()
+        scene_lights.append(amb)
+    for ld in desc.lights:
+        if not ld.in_scene:
+            continue
+        if (not world.present or world.lighting_on) and ld.visible:
+            l = make_light(ld)
+            l.begin_render()
+            scene_lights.append(l)
+    cam_w, cam_h = desc.camera.width, desc.camera.height
+    depth_margin = (cam.far - cam.near) * F(desc.camera.depth_margin)                          # camera.go:1339
+    cam_spread = cam.far - cam.near + (depth_margin * F(2))                                    # camera.go:1341
+    bucket = SortingTriangleBucket()
+    out = {}
+    for mi, md in enumerate(desc.models):
+        if not md.visible:
+            continue
+        model = Model(md)
+        mesh = md.mesh
+        g = Globals(mesh.n_verts)
+        for pi, part in enumerate(mesh.parts):
+            mat_ = part.material
+            if mat_ is not None and not mat_.visible:
+                continue
+            lighting = False                                                                   # camera.go:1521-1528
+            if world.present:
+                if mat_ is not None:
+                    lighting = world.lighting_on and not mat_.shadeless and not md.shadeless
+                else:
+                    lighting = world.lighting_on and not md.shadeless
+            bucket.sort_mode = SORT_BACK_TO_FRONT if mat_ is None else mat_.triangle_sort_mode
+            if not process_vertices(model, pi, cam, bucket, g):
+                out[(mi, pi)] = ([], np.zeros((0, 12), F), np.zeros((0, 12), F))
+                continue
+            src_w = src_h = F(0)
+            if mat_ is not None and mat_.use_texture and mat_.tex_w > 0:
+                src_w, src_h = F(mat_.tex_w), F(mat_.tex_h)
+            lights = scene_lights
+            if lighting:
+                if md.light_group is not None and md.light_group.active:                       # camera.go:1573-1579
+                    lights = [make_light(ld) for ld in md.light_group.lights]
+                    for l in lights:
+                        l.begin_render()
+                for l in lights:
+                    l.begin_model(model)
+            model_pos = [model.transform[3][0], model.transform[3][1], model.transform[3][2]]
+            mp_color = list(model.color)                                                       # camera.go:1597-1601
+            if mat_ is not None:
+                mp_color = [mp_color[k] * F(mat_.color[k]) for k in range(4)]
+            half_w, half_h = F(cam_w) / F(2), F(cam_h) / F(2)
+            if lighting:                                                                       # camera.go:1610-1641
+
+                def light_tri(i, tri):
+                    for vi in tri.indices:
+                        g.vertex_lights[vi] = [F(0), F(0), F(0), F(1)]
+                    for l in lights:
+                        if isinstance(l, PointLight) and l.light_range > 0:
+                            dist = model.max_span + l.light_range
+                            if distance_squared_to(model_pos, l.world_position()) > dist * dist:
+                                continue
+                        l.light(tri, model, g)
+
+                bucket.for_each(light_tri)
+            tri_ids, col_rows, dep_rows = [], [], []
+
+            def emit_tri(i, tri):                                                              # camera.go:1646-1820
+                tri_ids.append(tri.id)
+                for vi in tri.indices:
+                    w = g.transforms[vi][3]
+                    if not desc.camera.perspective:
+                        w = F(1.0)
+                    if w < 0:
+                        w = F(0.001)
+                    target = g.transforms[vi]
+                    dx = (target[0] / w) * F(cam_w) + half_w
+                    dy = (target[1] / -w) * F(cam_h) + half_h
+                    custom0 = F(0)
+                    if desc.camera.perspective_corrected_texture_mapping:
+                        uv_u = (mesh.uvs[vi][0] / w) * src_w
+                        uv_v = ((F(1) - mesh.uvs[vi][1]) / w) * src_h
+                        custom0 = F(1.0) / w
+                    else:
+                        uv_u = mesh.uvs[vi][0] * src_w
+                        uv_v = (F(1) - mesh.uvs[vi][1]) * src_h
+                    if mesh.active_color_channel >= 0 and mesh.colors is not None:
+                        col = [mesh.colors[vi][k] * mp_color[k] for k in range(4)]
+                    else:
+                        col = list(mp_color)
+                    if lighting:
+                        col[0] = col[0] * g.vertex_lights[vi][0]
+                        col[1] = col[1] * g.vertex_lights[vi][1]
+                        col[2] = col[2] * g.vertex_lights[vi][2]
+                    dcol = [F(0)] * 4
+                    if desc.camera.render_depth:                                               # camera.go:1744-1782
+                        if mat_ is not None and mat_.billboarded_depth_mode == 1:
+                            vertex_depth = g.depth_unbillboarded[vi]
+                        else:
+                            vertex_depth = g.transforms[vi][2]
+                        depth = (vertex_depth + depth_margin) / cam_spread
+                        if depth < 0:
+                            depth = F(0)
+                        elif depth > 1:
+                            depth = F(1)
+                        dcol = [depth, depth, depth, F(1)]
+                    elif world.present and world.fog_on:                                       # camera.go:1784-1814
+                        depth = (g.transforms[vi][2] + depth_margin) / cam_spread
+                        if depth < 0:
+                            depth = F(0)
+                        elif depth > 1:
+                            depth = F(1)
+                        depth = F(world.fog_range[0]) + ((F(world.fog_range[1]) - F(world.fog_range[0])) * F(1) - depth)
+                        fc = [F(c) for c in world.fog_color]
+                        if world.fog_mode == 0:
+                            col[0] = col[0] + fc[0] * depth; col[1] = col[1] + fc[1] * depth; col[2] = col[2] + fc[2] * depth
+                        elif world.fog_mode == 1:
+                            col[0] = col[0] * (fc[0] * depth); col[1] = col[1] * (fc[1] * depth); col[2] = col[2] * (fc[2] * depth)
+                    col_rows.append([dx, dy, uv_u, uv_v] + col + [custom0, F(0), F(0), F(0)])
+                    dep_rows.append([dx, dy, uv_u, uv_v] + dcol + [custom0, F(0), F(0), F(0)])
+
+            bucket.for_each(emit_tri)
+            out[(mi, pi)] = (tri_ids, np.asarray(col_rows, F).reshape(-1, 12), np.asarray(dep_rows, F).reshape(-1, 12))
+    return out
