@@ -12,7 +12,10 @@
  * the only assertion-bearing test in the reference, TestMatrixInversion
  * (matrix_test.go:36-55), is reproduced as a known-answer test against
  * orc_mat4_* (tests/test_oracle_kat.py).  No Go toolchain exists in the build
- * image, so the reference cannot be executed here.  Everything else follows the
+ * image, so the reference cannot be executed here.  A second restatement of the
+ * path, written separately and shaped like the Go source (tests/literal_go.py),
+ * agrees with this one bit for bit on the parity scenes and on scenes built from
+ * the reference's own GLB assets (tests/test_literal_restatement.py).  Everything else follows the
  * cited reference lines operation by operation: float32 everywhere, no FMA
  * contraction (-ffp-contract=off), left-to-right evaluation as Go/amd64
  * (GOAMD64=v1) does.
