@@ -8,7 +8,8 @@ sortingTriangles.go with its bins as Python lists, the lights are objects with `
 the bucket, then the emit loop).  Arithmetic is numpy float32 scalars, one operation per Go operation, left to right.
 
 What it covers: static and skinned models (skinVertex, shape keys), billboards with their locks and the unbillboarded depth mode,
-the children of dynamic batches (each is its own render(rp)); no host callbacks or auto-subdivision; perspective
+the children of dynamic batches (each is its own render(rp)), auto-subdivision (handleSubdivision with closestPointOnTri);
+no host callbacks; perspective
 and orthographic cameras; RenderDepth on or off (fog add / sub); vertex colours; texture sizes; perspective-corrected texture
 mapping; ambient, point (ranged and unranged), directional and LightVolume lights (all shading modes, cells with lights of their own),
 all three lighting modes, LightGroups; every sort mode.
@@ -429,6 +430,96 @@ def make_light(desc):
 class Triangle:
     def __init__(self, tid, indices, center, part):
         self.id, self.indices, self.center, self.part = tid, [int(i) for i in indices], [F(c) for c in center], part
+        self.visible = True
+        self.is_base = True
+        self.subdivision_levels = []        # base triangles: [[Triangle, ...] per level] (mesh.go:1758-1864 builds them at load time)
+        self.normal, self.max_span = None, None
+
+
+# ---- colliderTriangles.go:177-182, 206-281 (closestPointOnTri, as Triangle.handleSubdivision uses it) ----------------------
+def sub(a, b):
+    return [a[0] - b[0], a[1] - b[1], a[2] - b[2]]
+
+
+def closest_point_on_line(point, start, end):
+    diff = sub(end, start)
+    dot_a = dot(sub(point, start), diff)
+    dot_b = dot(diff, diff)
+    d = dot_a / dot_b
+    if d > 1:
+        d = F(1)
+    elif d < 0:
+        d = F(0)
+    return [start[0] + diff[0] * d, start[1] + diff[1] * d, start[2] + diff[2] * d]
+
+
+def point_inside_triangle(point, v0, v1, v2):
+    ca, ba, pa = sub(v2, v0), sub(v1, v0), sub(point, v0)
+    dot00, dot01, dot02 = dot(ca, ca), dot(ca, ba), dot(ca, pa)
+    dot11, dot12 = dot(ba, ba), dot(ba, pa)
+    inv_denom = F(1.0) / ((dot00 * dot11) - (dot01 * dot01))
+    u = ((dot11 * dot02) - (dot01 * dot12)) * inv_denom
+    v = ((dot00 * dot12) - (dot01 * dot02)) * inv_denom
+    return u, v
+
+
+def closest_point_on_tri(point, v0, v1, v2, normal):
+    distance = dot(normal, v0)
+    dist = dot(normal, point) - distance
+    plane_point = [point[0] - normal[0] * dist, point[1] - normal[1] * dist, point[2] - normal[2] * dist]
+    u, v = point_inside_triangle(plane_point, v0, v1, v2)
+    if u >= 0 and v >= 0 and u + v < 1:
+        return plane_point
+    ab = closest_point_on_line(point, v0, v1)
+    bc = closest_point_on_line(point, v1, v2)
+    ca = closest_point_on_line(point, v2, v0)
+    closest, closest_dist = ab, distance_squared_to(point, ab)
+    bc_dist, ca_dist = distance_squared_to(point, bc), distance_squared_to(point, ca)
+    if bc_dist < closest_dist:
+        closest, closest_dist = bc, bc_dist
+    if ca_dist < closest_dist:
+        closest = ca
+    return closest
+
+
+def disable_subdivision(t):                                 # mesh.go:1866-1875
+    if not t.visible:
+        t.visible = True
+        for level in t.subdivision_levels:
+            for s_ in level:
+                s_.visible = False
+
+
+def handle_subdivision(t, camera_pos, mesh, levels):        # mesh.go:1877-1935
+    t.visible = False
+    if len(t.subdivision_levels) == 0:
+        t.visible = True
+        return
+    for level in t.subdivision_levels:
+        for s_ in level:
+            s_.visible = False
+    active, closest_distance = -1, MAXF
+    P = mesh.positions
+    a, b, c = t.indices
+    dist = distance_squared_to(camera_pos, closest_point_on_tri(camera_pos, list(P[a]), list(P[b]), list(P[c]), t.normal))
+    for i, (distance_squared, _max_size) in enumerate(levels):
+        if dist < F(distance_squared) and F(distance_squared) < closest_distance:
+            closest_distance = F(distance_squared)
+            active = i
+    if active == -1:
+        t.visible = True
+    else:
+        ms, sub_index = t.max_span, -1
+        while ms > F(levels[active][1]):
+            ms = ms / F(2)
+            sub_index += 1
+        if sub_index >= len(t.subdivision_levels):
+            sub_index = len(t.subdivision_levels) - 1
+        if sub_index >= 0:
+            for s_ in t.subdivision_levels[sub_index]:
+                s_.visible = True
+        else:
+            t.visible = True
 
 
 class Model:
@@ -438,10 +529,23 @@ class Model:
         self.world_rotation = world_rotation(desc.node)
         self.color = [F(c) for c in desc.color]
         mesh = desc.mesh
-        centers = O.triangle_centers(mesh.positions, mesh.indices)
+        centers = mesh.tri_centers if mesh.auto_subdivide else O.triangle_centers(mesh.positions, mesh.indices)
         self.parts = []
         for p in mesh.parts:
-            self.parts.append([Triangle(t, mesh.indices[t], centers[t], p) for t in range(p.tri_start, p.tri_end + 1)])
+            tris = [Triangle(t, mesh.indices[t], centers[t], p) for t in range(p.tri_start, p.tri_end + 1)]
+            if mesh.auto_subdivide:     # the entries behind a base triangle are its sub-triangles, level by level (MeshPart.forEachTri(true, ..))
+                by_slot = {tr.id: tr for tr in tris}
+                for tr in tris:
+                    lvl = int(mesh.tri_sub_level[tr.id])
+                    if lvl < 0:
+                        tr.normal = [F(x) for x in mesh.tri_normal[tr.id]]
+                        tr.max_span = F(mesh.tri_max_span[tr.id])
+                        tr.subdivision_levels = [[] for _ in range(int(mesh.tri_n_levels[tr.id]))]
+                    else:
+                        tr.is_base = False
+                        tr.visible = False
+                        by_slot[int(mesh.tri_sub_base[tr.id])].subdivision_levels[lvl].append(tr)
+            self.parts.append(tris)
         # skinned models (model.go:33-40): boneInfluence of every joint, given directly or posed from a skeleton + animation
         self.bone_influences = None
         if desc.bone_influences is not None:
@@ -524,7 +628,7 @@ class Camera:
         self.camera_up = up_vector(world_rotation(desc.node))                                  # camera.go:1085-1088 (Camera.Clear)
 
 
-def process_vertices(model, part_index, camera, bucket, g):
+def process_vertices(model, part_index, camera, bucket, g, autosubdivision_levels=()):
     """model.go:600-995 with processOnlyVisible = true, for a model without billboarding or callbacks.
     Returns False for the early-out of model.go:604-606."""
     bucket.clear()
@@ -566,7 +670,17 @@ def process_vertices(model, part_index, camera, bucket, g):
     unaltered_mvp = O.mat4_mult(model_transform, camera.vp) if unbillboarded else None
     min_depth, max_depth = MAXF, -MAXF
     snapping = F(camera.desc.vertex_snapping)
+    if not model.skinned:                                                                      # model.go:727-741
+        for tri in model.parts[part_index]:
+            if not tri.is_base:
+                continue
+            if mesh.auto_subdivide and len(autosubdivision_levels) > 0:
+                handle_subdivision(tri, inverted_cam_pos, mesh, autosubdivision_levels)
+            else:
+                disable_subdivision(tri)
     for tri in model.parts[part_index]:
+        if mesh.auto_subdivide and not tri.visible:                                            # model.go:753-755
+            continue
         for vi in tri.indices:
             if model.skinned:                                                                  # model.go:760-776: world space, vpMatrix
                 vert, normal = skin_vertex(model, vi)
@@ -667,7 +781,7 @@ def render_scene(desc):
                 else:
                     lighting = world.lighting_on and not md.shadeless
             bucket.sort_mode = SORT_BACK_TO_FRONT if mat_ is None else mat_.triangle_sort_mode
-            if not process_vertices(model, pi, cam, bucket, g):
+            if not process_vertices(model, pi, cam, bucket, g, desc.autosubdivision_levels):
                 out[(mi, pi)] = ([], np.zeros((0, 12), F), np.zeros((0, 12), F))
                 continue
             src_w = src_h = F(0)
@@ -758,3 +872,85 @@ def render_scene(desc):
             bucket.for_each(emit_tri)
             out[(mi, pi)] = (tri_ids, np.asarray(col_rows, F).reshape(-1, 12), np.asarray(dep_rows, F).reshape(-1, 12))
     return out
+
+
+# ---- camera.go:933-989, model.go:142-182, camera.go:1343-1469, 2050-2055: which render pairs there are, and in which order ----------
+def frustum_sphere(model):                                  # Model.onTransformUpdate (model.go:142-182)
+    position, scale, rotation = decompose(model.transform)
+    mesh = model.desc.mesh
+    lo, hi = mesh.positions.min(axis=0), mesh.positions.max(axis=0)
+    center = [F(0), F(0), F(0)]
+    if not model.skinned:
+        center = [(hi[0] + lo[0]) / F(2), (hi[1] + lo[1]) / F(2), (hi[2] + lo[2]) / F(2)]           # Dimensions.Center (mesh.go:46-52)
+    center = mult_vec(rotation, center)
+    position = [position[0] + center[0] * scale[0], position[1] + center[1] * scale[1], position[2] + center[2] * scale[2]]
+    mn = [lo[0] * scale[0], lo[1] * scale[1], lo[2] * scale[2]]
+    mx = [hi[0] * scale[0], hi[1] * scale[1], hi[2] * scale[2]]
+    radius = magnitude([mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]]) / F(2)
+    return position, radius
+
+
+def sphere_in_frustum(cam, position, radius):               # camera.go:933-983
+    d_ = cam.desc
+    rot = world_rotation(d_.node)
+    cam_forward, cam_up = forward(rot), up_vector(rot)
+    cam_right = unit([rot[0][0], rot[0][1], rot[0][2]])                                             # Matrix4.Right
+    diff = sub(position, cam.position)
+    pc_z = dot(diff, [-cam_forward[0], -cam_forward[1], -cam_forward[2]])
+    if pc_z > cam.far + radius or pc_z < cam.near - radius:
+        return False
+    aspect = F(d_.width) / F(d_.height)
+    if d_.perspective:
+        angle = F(d_.field_of_view) * F(3.1415) / F(360)                                            # camera.go:660-666
+        tang = F(math.tan(float(angle)))
+        factor_y = F(1.0) / F(math.cos(float(angle)))
+        factor_x = F(1.0) / F(math.cos(float(F(math.atan(float(tang * aspect))))))
+        d = factor_y * radius
+        pc_z = pc_z * tang
+        pc_y = dot(diff, cam_up)
+        if pc_y > pc_z + d or pc_y < -pc_z - d:
+            return False
+        pc_z = pc_z * aspect
+        d = factor_x * radius
+        pc_x = dot(diff, cam_right)
+        if pc_x > pc_z + d or pc_x < -pc_z - d:
+            return False
+    else:
+        width = F(d_.ortho_scale)
+        height = width / aspect
+        pc_y = dot(diff, cam_up)
+        if -height / F(2) - radius > pc_y or pc_y > height / F(2) + radius:
+            return False
+        pc_x = dot(diff, cam_right)
+        if -width / F(2) - radius > pc_x or pc_x > width / F(2) + radius:
+            return False
+    return True
+
+
+def render_order(desc):
+    """The (model index, part index) of every render(rp) call in the order Camera.Render makes them, for scenes without dynamic
+    batches whose solids need no sorting or sort consistently (camera.go:1460-1469 hands sort.SliceStable a comparator that is not
+    a strict weak ordering when RenderOrder values differ; with equal orders it is 'farther first')."""
+    cam = Camera(desc.camera)
+    solids, transparents = [], []
+    for mi, md in enumerate(desc.models):
+        if not md.visible:
+            continue
+        model = Model(md)
+        if md.frustum_culling:
+            pos, radius = frustum_sphere(model)
+            if not sphere_in_frustum(cam, pos, radius):
+                continue
+        for pi, part in enumerate(md.mesh.parts):
+            mat_ = part.material
+            if mat_ is not None and not mat_.visible:
+                continue
+            depth = distance_squared_to(cam.position, [model.transform[3][0], model.transform[3][1], model.transform[3][2]])
+            order = mat_.render_order if mat_ is not None else 0
+            (transparents if model.is_transparent(part) else solids).append((order, depth, mi, pi))
+    if not desc.camera.render_depth:
+        assert len({o for o, _, _, _ in solids}) <= 1, "the solids comparator is only an ordering when the render orders are equal"
+        solids = sorted(solids, key=lambda r: -float(r[1]))                                          # stable, farther first
+    transparents = sorted(transparents, key=lambda r: (r[0], -float(r[1])))                          # camera.go:2050-2055
+    return [(mi, pi) for _, _, mi, pi in solids + transparents]
+

@@ -22,12 +22,10 @@ ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ass
 
 def covered(desc):
     """Scenes the literal code restates: static and skinned models, shape keys, billboards, dynamic-batch children, every light
-    type; no auto-subdivision, no MaxLightCount."""
+    type, auto-subdivision; no MaxLightCount."""
     if desc.camera.max_light_count or desc.camera.vertex_snapping < 0:
         return False
     for m in desc.models:
-        if m.mesh.auto_subdivide:
-            return False
         skinned = m.bone_influences is not None or m.pose is not None
         for p in m.mesh.parts:      # (the reference reads a never-written global for unbillboarded depth on skinned models, model.go:800)
             if skinned and p.material is not None and p.material.billboarded_depth_mode:
@@ -49,6 +47,12 @@ def check(desc):
         assert np.array_equal(ref.color_list[a:a + n].view(np.uint32), col.view(np.uint32)), (desc.name, r["model"], r["part"], "colour list")
         assert np.array_equal(ref.depth_list[a:a + n].view(np.uint32), dep.view(np.uint32)), (desc.name, r["model"], r["part"], "depth list")
         n_checked += n
+    # which render pairs there are (visibility, the frustum test of every model) and the order they are rendered in
+    if not any(m.batch_owner is not None for m in desc.models) and \
+            (desc.camera.render_depth or len({(p.material.render_order if p.material else 0) for m in desc.models for p in m.mesh.parts}) <= 1):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            assert LG.render_order(desc) == [(r["model"], r["part"]) for r in ref.renders], (desc.name, "render pairs / order")
     return n_checked
 
 
@@ -80,6 +84,8 @@ SYNTHETIC = {
     "volume_cell_lights": lambda: scenes.volume_cell_lights_scene(5, 0),
     "volume_cell_lights_normal": lambda: scenes.volume_cell_lights_scene(6, 1, skinned=True),
     "volume_cell_lights_object": lambda: scenes.volume_cell_lights_scene(7, 2),
+    "subdivision": lambda: scenes.subdivision_scene(0),
+    "subdivision_no_levels": lambda: scenes.subdivision_scene(1, with_levels=False),
     "skinned": lambda: scenes.skinned_scene(1, n=4, rings=6, sides=7),
     "shape_keys": lambda: scenes.shape_key_scene(1),
     "posed": lambda: scenes.posed_scene(0, n_models=4),
