@@ -13,9 +13,9 @@ no host callbacks; perspective
 and orthographic cameras; RenderDepth on or off (fog add / sub); vertex colours; texture sizes; perspective-corrected texture
 mapping; ambient, point (ranged and unranged), directional and LightVolume lights (all shading modes, cells with lights of their own),
 all three lighting modes, LightGroups; every sort mode.
-What it borrows from the oracle's binding: Matrix4.Mult / Inverted / the projection matrices / Node.Transform (pinned on their
-own: TestMatrixInversion, the numpy check of matrix_none.go) and Triangle.Center (load-time data).  It does not order the
-render pairs: results are compared per render(rp) call.
+What it borrows from the oracle's binding: Triangle.Center (load-time data) and, for posed armatures, the bone matrices
+(tests/test_pose_oracle.py has their own literal check).  Matrix4.Mult / Inverted / Decompose, Node.Transform, the view and
+projection matrices and everything else are restated here.
 """
 import math
 
@@ -72,6 +72,86 @@ def mat(a):
     return np.asarray(a, F).reshape(4, 4)
 
 
+def mat4_mult(a, b):                # matrix_amd64.s (amd64) == matrix_none.go: ret[i][j] = ((a[i][0]*b[0][j] + a[i][1]*b[1][j]) + a[i][2]*b[2][j]) + a[i][3]*b[3][j]
+    a, b = mat(a), mat(b)
+    out = np.zeros((4, 4), F)
+    for i in range(4):
+        for j in range(4):
+            out[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j] + a[i][3] * b[3][j]
+    return out
+
+
+def mat4_inverted(m):               # matrix.go:255-307, derived rather than typed off: the cofactor expansion the Go code spells out
+    """Every entry (r, c) of the source is  det * +-(m[s][k0]*A0 - m[s][k1]*A1 + m[s][k2]*A2)  where s = 1 for c == 0 and 0 otherwise,
+    k0 < k1 < k2 are the columns other than r, each A is the 2x2 minor over the two remaining columns and the two rows other than
+    c and s -- A(c0, c1, r0, r1) = m[r0][c0]*m[r1][c1] - m[r0][c1]*m[r1][c0], the source's Ac0c1r0r1 -- and the sign is (-1)^(r+c),
+    applied as a negation before the multiplication by det.  det is the same expression for column 0, folded left to right."""
+    m = mat(m)
+
+    def minor(c0, c1, r0, r1):
+        return m[r0][c0] * m[r1][c1] - m[r0][c1] * m[r1][c0]
+
+    def inner(r, c):
+        s_ = 1 if c == 0 else 0
+        ks = [k for k in range(4) if k != r]
+        rows = [q for q in range(4) if q not in (c, s_)]
+        terms = []
+        for k in ks:
+            cols = [q for q in ks if q != k]
+            terms.append(m[s_][k] * minor(cols[0], cols[1], rows[0], rows[1]))
+        return terms[0] - terms[1] + terms[2]
+
+    det = m[0][0] * inner(0, 0) - m[0][1] * inner(1, 0) + m[0][2] * inner(2, 0) - m[0][3] * inner(3, 0)
+    det = F(1) / det
+    out = np.zeros((4, 4), F)
+    for r in range(4):
+        for c in range(4):
+            v = inner(r, c)
+            out[r][c] = det * (v if (r + c) % 2 == 0 else -v)
+    return out
+
+
+def mat4_scale(x, y, z):            # matrix.go:90-96
+    m = np.eye(4, dtype=F)
+    m[0][0], m[1][1], m[2][2] = F(x), F(y), F(z)
+    return m
+
+
+def mat4_translate(x, y, z):        # matrix.go:81-87
+    m = np.eye(4, dtype=F)
+    m[3][0], m[3][1], m[3][2] = F(x), F(y), F(z)
+    return m
+
+
+def mat4_is_identity(m):            # matrix.go:511-529
+    eps = F(0.0001)
+    ident = np.eye(4, dtype=F)
+    return not any(abs(m[i][j] - ident[i][j]) > eps for i in range(4) for j in range(4))
+
+
+def node_transform(node):           # node.go:572-583: Scale x rotation x Translate [x parent.Transform()]
+    t = mat4_scale(*[F(c) for c in node.scale])
+    t = mat4_mult(t, mat(node.rotation))
+    t = mat4_mult(t, mat4_translate(*[F(c) for c in node.position]))
+    if node.parent is not None:
+        t = mat4_mult(t, node_transform(node.parent))
+    return t
+
+
+def perspective(fovy, near, far, view_w, view_h):           # matrix.go:588-604; math32.Tan = float32(math.Tan(float64(x)))
+    fovy, near, far = F(fovy), F(near), F(far)
+    aspect = F(view_w) / F(view_h)
+    t = F(math.tan(float(fovy * F(math.pi) / F(360))))
+    b = -t
+    r = t * aspect
+    l = -r
+    z = F(0)
+    return np.array([[(F(2) * near) / (r - l), z, (r + l) / (r - l), z],
+                     [z, (F(2) * near) / (t - b), (t + b) / (t - b), z],
+                     [z, z, -((far + near) / (far - near)), -((F(2) * far * near) / (far - near))],
+                     [z, z, F(-1), z]], F)
+
+
 def go_round(x):                    # math32.Round = float32(math.Round(float64(x))): half away from zero
     x = float(x)
     if math.isnan(x) or math.isinf(x):
@@ -79,10 +159,14 @@ def go_round(x):                    # math32.Round = float32(math.Round(float64(
     return F(math.copysign(math.floor(abs(x) + 0.5), x))
 
 
-def orthographic(near, far, right, left, top, bottom):      # NewProjectionMatrix4Orthographic through the oracle's matrix helper
-    out = np.zeros(16, F)
-    O.lib().orc_mat4_orthographic(float(near), float(far), float(right), float(left), float(top), float(bottom), O._fp(out))
-    return out.reshape(4, 4)
+def orthographic(near, far, right, left, top, bottom):      # matrix.go:609-616
+    near, far, right, left, top, bottom = F(near), F(far), F(right), F(left), F(top), F(bottom)
+    m = np.zeros((4, 4), F)
+    m[0][0] = F(2) / (right - left)
+    m[1][1] = F(2) / (top - bottom)
+    m[2][2] = F(-2) / (far - near)
+    m[3][3] = F(1)
+    return m
 
 
 def transposed(m):                  # matrix.go:218-230
@@ -99,7 +183,7 @@ def decompose_rotation(m):          # matrix.go:202-208
 def decompose(m):                   # matrix.go:181-196
     position = [m[3][0], m[3][1], m[3][2]]
     rotation = decompose_rotation(m)
-    inn = O.mat4_mult(m, transposed(rotation))
+    inn = mat4_mult(m, transposed(rotation))
     scale = [magnitude(inn[0]), magnitude(inn[1]), magnitude(inn[2])]
     return position, scale, rotation
 
@@ -142,14 +226,14 @@ def forward(m):                     # matrix.go:170-176
 def world_rotation(node):           # node.go:916-938: decompose only when an ancestor is rotated
     parent = node.parent
     while parent is not None:
-        if not O.mat4_equals(mat(parent.rotation), np.eye(4, dtype=F)):
-            return decompose_rotation(O.node_world_transform(node).reshape(4, 4))
+        if not mat4_is_identity(mat(parent.rotation)):
+            return decompose_rotation(node_transform(node))
         parent = parent.parent
     return mat(node.rotation)
 
 
 def world_position(node):           # node.go:737-739
-    t = O.node_world_transform(node).reshape(4, 4)
+    t = node_transform(node)
     return [t[3][0], t[3][1], t[3][2]]
 
 
@@ -247,7 +331,7 @@ class PointLight:
         if model.skinned:
             self.working_position = self.world_position()
             return
-        pos, sca, rot = decompose(O.mat4_inverted(model.transform))
+        pos, sca, rot = decompose(mat4_inverted(model.transform))
         rp = mult_vec(rot, self.world_position())
         inv = [F(1) / sca[0], F(1) / sca[1], F(1) / sca[2]]
         self.working_position = [rp[0] + pos[0] * inv[0], rp[1] + pos[1] * inv[1], rp[2] + pos[2] * inv[2]]
@@ -293,7 +377,7 @@ class DirectionalLight:
 
     def begin_model(self, model):                           # light.go:326-330
         if not model.skinned:
-            self.working_model_rotation = transposed(O.mat4_inverted(model.world_rotation))
+            self.working_model_rotation = transposed(mat4_inverted(model.world_rotation))
 
     def vertex_light(self, index, tri, model, g):           # light.go:332-360
         mat_ = tri.part.material
@@ -525,7 +609,7 @@ def handle_subdivision(t, camera_pos, mesh, levels):        # mesh.go:1877-1935
 class Model:
     def __init__(self, desc):
         self.desc = desc
-        self.transform = O.node_world_transform(desc.node).reshape(4, 4)
+        self.transform = node_transform(desc.node)
         self.world_rotation = world_rotation(desc.node)
         self.color = [F(c) for c in desc.color]
         mesh = desc.mesh
@@ -617,14 +701,14 @@ class Camera:
         self.near, self.far = F(desc.near), F(desc.far)
         self.position = world_position(desc.node)
         cam_pos = [-self.position[0], -self.position[1], -self.position[2]]                    # camera.go:638-648
-        self.view = O.mat4_mult(O.mat4_translate(*cam_pos), transposed(world_rotation(desc.node)))
+        self.view = mat4_mult(mat4_translate(*cam_pos), transposed(world_rotation(desc.node)))
         if desc.perspective:                                                                   # camera.go:651-680
-            self.projection = O.mat4_perspective(desc.field_of_view, desc.near, desc.far, desc.width, desc.height)
+            self.projection = perspective(desc.field_of_view, desc.near, desc.far, desc.width, desc.height)
         else:
             asr = F(desc.height) / F(desc.width)
             s = F(desc.ortho_scale)
             self.projection = orthographic(desc.near, desc.far, F(1) * s, F(-1) * s, asr * s, -asr * s)
-        self.vp = O.mat4_mult(self.view, self.projection)                                      # camera.go:1329
+        self.vp = mat4_mult(self.view, self.projection)                                      # camera.go:1329
         self.camera_up = up_vector(world_rotation(desc.node))                                  # camera.go:1085-1088 (Camera.Clear)
 
 
@@ -638,7 +722,7 @@ def process_vertices(model, part_index, camera, bucket, g, autosubdivision_level
     mesh = model.desc.mesh
     model_transform = model.transform
     cam_pos = camera.position
-    p, s, r = decompose(O.mat4_inverted(model_transform))                                      # model.go:627-628
+    p, s, r = decompose(mat4_inverted(model_transform))                                      # model.go:627-628
     rc = mult_vec(r, cam_pos)
     inv = [F(1) / s[0], F(1) / s[1], F(1) / s[2]]
     inverted_cam_pos = [rc[0] + p[0] * inv[0], rc[1] + p[1] * inv[1], rc[2] + p[2] * inv[2]]
@@ -663,11 +747,11 @@ def process_vertices(model, part_index, camera, bucket, g, autosubdivision_level
             row = list(lookat[0]); row[2] = F(0); lookat[0] = unit(row)
             row = list(lookat[1]); row[2] = F(0); lookat[1] = unit(row)
         bp, bs, br = decompose(base)
-        base = O.mat4_mult(O.mat4_mult(br, O.mat4_scale(bs[0], bs[1], bs[2])), lookat)
+        base = mat4_mult(mat4_mult(br, mat4_scale(bs[0], bs[1], bs[2])), lookat)
         base[3] = [bp[0], bp[1], bp[2], F(1)]
-    mvp = O.mat4_mult(base, camera.vp)
+    mvp = mat4_mult(base, camera.vp)
     unbillboarded = mat_ is not None and mat_.billboarded_depth_mode == 1                      # model.go:699-705
-    unaltered_mvp = O.mat4_mult(model_transform, camera.vp) if unbillboarded else None
+    unaltered_mvp = mat4_mult(model_transform, camera.vp) if unbillboarded else None
     min_depth, max_depth = MAXF, -MAXF
     snapping = F(camera.desc.vertex_snapping)
     if not model.skinned:                                                                      # model.go:727-741

@@ -123,3 +123,22 @@ def test_fuzz_scenes_the_literal_code_covers():
         if covered(desc) and desc.total_triangles() <= 6000:
             check(desc); n += 1
     assert n >= 4, n
+
+
+def test_matrix_primitives_of_both_restatements_agree():
+    # Matrix4.Mult (matrix_amd64.s order), Inverted (derived from the cofactor pattern, not typed off), Node.Transform, projections
+    from tetra3d_b200.scenedesc import NodeDesc
+    rng = np.random.default_rng(0)
+    with np.errstate(all="ignore"):
+        for i in range(200):
+            a, b = rng.standard_normal((4, 4)).astype(np.float32), rng.standard_normal((4, 4)).astype(np.float32)
+            if i % 3 == 0:
+                a[:, 3] = [0, 0, 0, 1]
+            assert np.array_equal(LG.mat4_mult(a, b).view(np.uint32), np.asarray(O.mat4_mult(a, b), np.float32).reshape(4, 4).view(np.uint32))
+            assert np.array_equal(LG.mat4_inverted(a).view(np.uint32), np.asarray(O.mat4_inverted(a), np.float32).reshape(4, 4).view(np.uint32))
+    for i in range(20):
+        parent = NodeDesc(position=tuple(rng.uniform(-3, 3, 3)), scale=tuple(rng.uniform(0.5, 2, 3)), rotation=scenes.random_rotation(rng))
+        node = NodeDesc(position=tuple(rng.uniform(-3, 3, 3)), scale=tuple(rng.uniform(0.5, 2, 3)), rotation=scenes.random_rotation(rng), parent=parent if i % 2 else None)
+        assert np.array_equal(LG.node_transform(node).view(np.uint32), O.node_world_transform(node).reshape(4, 4).view(np.uint32))
+    for fov, near, far, w, h in [(60.0, 0.1, 100.0, 640, 360), (75.0, 0.05, 250.0, 1920, 1080), (30.0, 1.0, 20.0, 100, 100)]:
+        assert np.array_equal(LG.perspective(fov, near, far, w, h).view(np.uint32), np.asarray(O.mat4_perspective(fov, near, far, w, h), np.float32).reshape(4, 4).view(np.uint32))
