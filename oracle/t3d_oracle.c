@@ -1347,6 +1347,17 @@ void orc_test_go_stable_sort(int n, const float* keys, int* perm) {
     go_stable_sort(n, gst_less, gst_swap, &c);
 }
 
+/* The same with an arbitrary "less" relation given as an n x n table over the ORIGINAL positions: less(i, j) = table[perm[i] * n + perm[j]].
+ * Lets a test compare this restatement of package sort's algorithm with another one on comparators that are not orderings at all. */
+typedef struct { const uint8_t* table; int n; int* perm; } gtt_ctx;
+static int gtt_less(void* cv, int i, int j) { gtt_ctx* c = (gtt_ctx*)cv; return c->table[(size_t)c->perm[i] * c->n + c->perm[j]] != 0; }
+static void gtt_swap(void* cv, int i, int j) { gtt_ctx* c = (gtt_ctx*)cv; int t = c->perm[i]; c->perm[i] = c->perm[j]; c->perm[j] = t; }
+void orc_test_go_stable_sort_table(int n, const uint8_t* table, int* perm) {
+    gtt_ctx c; c.table = table; c.n = n; c.perm = perm;
+    for (int i = 0; i < n; i++) perm[i] = i;
+    go_stable_sort(n, gtt_less, gtt_swap, &c);
+}
+
 /* camera.go:1460-1469 through sort.SliceStable */
 typedef struct { render_pair_t* a; } rp_ctx;
 static int rp_less_solids(void* cv, int i, int j) { rp_ctx* c = (rp_ctx*)cv; return less_solids(&c->a[i], &c->a[j]); }

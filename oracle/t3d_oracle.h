@@ -322,5 +322,7 @@ double orc_go_atan2(double y, double x);                                        
 #endif
 /* Test hook: perm = stable argsort of keys, computed with the restated sort.SliceStable (go_stable_sort). */
 void orc_test_go_stable_sort(int n, const float* keys, int* perm);
+/* The same under an arbitrary relation: less(i, j) = table[perm[i] * n + perm[j]] (not necessarily an ordering). */
+void orc_test_go_stable_sort_table(int n, const uint8_t* table, int* perm);
 
 #endif

@@ -843,6 +843,26 @@ def render_scene(desc):
             l = make_light(ld)
             l.begin_render()
             scene_lights.append(l)
+    if desc.camera.max_light_count > 0:                                                        # camera.go:1474-1497
+        focus = desc.camera.max_light_focus
+        pos = world_position(focus) if focus is not None else cam.position
+
+        def light_pos(l):
+            return l.world_position() if isinstance(l, PointLight) else (world_position(l.desc.node) if hasattr(l, "desc") else [F(0), F(0), F(0)])
+
+        def less_light(i, j):
+            if isinstance(i, AmbientLight):
+                return True
+            elif isinstance(j, AmbientLight):
+                return False
+            elif isinstance(i, DirectionalLight):
+                return True
+            elif isinstance(j, DirectionalLight):
+                return False
+            return distance_squared_to(pos, light_pos(i)) < distance_squared_to(pos, light_pos(j))
+
+        scene_lights = slice_stable(scene_lights, less_light)
+        scene_lights = scene_lights[:min(desc.camera.max_light_count, len(scene_lights))]
     cam_w, cam_h = desc.camera.width, desc.camera.height
     depth_margin = (cam.far - cam.near) * F(desc.camera.depth_margin)                          # camera.go:1339
     cam_spread = cam.far - cam.near + (depth_margin * F(2))                                    # camera.go:1341
@@ -1013,8 +1033,7 @@ def sphere_in_frustum(cam, position, radius):               # camera.go:933-983
 
 def render_order(desc):
     """The (model index, part index) of every render(rp) call in the order Camera.Render makes them, for scenes without dynamic
-    batches whose solids need no sorting or sort consistently (camera.go:1460-1469 hands sort.SliceStable a comparator that is not
-    a strict weak ordering when RenderOrder values differ; with equal orders it is 'farther first')."""
+    batches."""
     cam = Camera(desc.camera)
     solids, transparents = [], []
     for mi, md in enumerate(desc.models):
@@ -1032,9 +1051,112 @@ def render_order(desc):
             depth = distance_squared_to(cam.position, [model.transform[3][0], model.transform[3][1], model.transform[3][2]])
             order = mat_.render_order if mat_ is not None else 0
             (transparents if model.is_transparent(part) else solids).append((order, depth, mi, pi))
-    if not desc.camera.render_depth:
-        assert len({o for o, _, _, _ in solids}) <= 1, "the solids comparator is only an ordering when the render orders are equal"
-        solids = sorted(solids, key=lambda r: -float(r[1]))                                          # stable, farther first
+    if not desc.camera.render_depth:                                                                 # camera.go:1460-1469 (not an ordering when orders differ:
+        def less(i, j):                                                                              #  the outcome is whatever sort.SliceStable's algorithm makes of it)
+            if i[0] < j[0]:
+                return True
+            return i[1] > j[1]
+        solids = slice_stable(solids, less)
     transparents = sorted(transparents, key=lambda r: (r[0], -float(r[1])))                          # camera.go:2050-2055
     return [(mi, pi) for _, _, mi, pi in solids + transparents]
+
+
+# ---- package sort: sort.SliceStable (the algorithm of Go's sort.Stable: insertion sort on blocks of 20, then SymMerge) -----------
+def go_stable_sort(n, less, swap):
+    """stable_func of Go's sort package over an abstract (less, swap) pair, as sort.SliceStable drives it."""
+
+    def insertion_sort(a, b):
+        for i in range(a + 1, b):
+            j = i
+            while j > a and less(j, j - 1):
+                swap(j, j - 1)
+                j -= 1
+
+    def swap_range(a, b, count):
+        for i in range(count):
+            swap(a + i, b + i)
+
+    def rotate(a, m, b):
+        i, j = m - a, b - m
+        while i != j:
+            if i > j:
+                swap_range(m - i, m, j)
+                i -= j
+            else:
+                swap_range(m - i, m + j - i, i)
+                j -= i
+        swap_range(m - i, m, i)
+
+    def sym_merge(a, m, b):
+        if m - a == 1:
+            i, j = m, b
+            while i < j:
+                h = (i + j) >> 1
+                if less(h, a):
+                    i = h + 1
+                else:
+                    j = h
+            for k in range(a, i - 1):
+                swap(k, k + 1)
+            return
+        if b - m == 1:
+            i, j = a, m
+            while i < j:
+                h = (i + j) >> 1
+                if not less(m, h):
+                    i = h + 1
+                else:
+                    j = h
+            for k in range(m, i, -1):
+                swap(k, k - 1)
+            return
+        mid = (a + b) >> 1
+        nn = mid + m
+        if m > mid:
+            start, r = nn - b, mid
+        else:
+            start, r = a, m
+        p = nn - 1
+        while start < r:
+            c = (start + r) >> 1
+            if not less(p - c, c):
+                start = c + 1
+            else:
+                r = c
+        end = nn - start
+        if start < m and m < end:
+            rotate(start, m, end)
+        if a < start and start < mid:
+            sym_merge(a, start, mid)
+        if mid < end and end < b:
+            sym_merge(mid, end, b)
+
+    block = 20
+    a, b = 0, block
+    while b <= n:
+        insertion_sort(a, b)
+        a = b
+        b += block
+    insertion_sort(a, n)
+    while block < n:
+        a, b = 0, 2 * block
+        while b <= n:
+            sym_merge(a, a + block, b)
+            a = b
+            b += 2 * block
+        m = a + block
+        if m < n:
+            sym_merge(a, m, n)
+        block *= 2
+
+
+def slice_stable(items, less_items):
+    """sort.SliceStable(items, less): returns the sorted list."""
+    items = list(items)
+
+    def swap(i, j):
+        items[i], items[j] = items[j], items[i]
+
+    go_stable_sort(len(items), lambda i, j: less_items(items[i], items[j]), swap)
+    return items
 

@@ -22,9 +22,7 @@ ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ass
 
 def covered(desc):
     """Scenes the literal code restates: static and skinned models, shape keys, billboards, dynamic-batch children, every light
-    type, auto-subdivision; no MaxLightCount."""
-    if desc.camera.max_light_count or desc.camera.vertex_snapping < 0:
-        return False
+    type, auto-subdivision, MaxLightCount."""
     for m in desc.models:
         skinned = m.bone_influences is not None or m.pose is not None
         for p in m.mesh.parts:      # (the reference reads a never-written global for unbillboarded depth on skinned models, model.go:800)
@@ -48,8 +46,7 @@ def check(desc):
         assert np.array_equal(ref.depth_list[a:a + n].view(np.uint32), dep.view(np.uint32)), (desc.name, r["model"], r["part"], "depth list")
         n_checked += n
     # which render pairs there are (visibility, the frustum test of every model) and the order they are rendered in
-    if not any(m.batch_owner is not None for m in desc.models) and \
-            (desc.camera.render_depth or len({(p.material.render_order if p.material else 0) for m in desc.models for p in m.mesh.parts}) <= 1):
+    if not any(m.batch_owner is not None for m in desc.models):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", RuntimeWarning)
             assert LG.render_order(desc) == [(r["model"], r["part"]) for r in ref.renders], (desc.name, "render pairs / order")
@@ -84,6 +81,10 @@ SYNTHETIC = {
     "volume_cell_lights": lambda: scenes.volume_cell_lights_scene(5, 0),
     "volume_cell_lights_normal": lambda: scenes.volume_cell_lights_scene(6, 1, skinned=True),
     "volume_cell_lights_object": lambda: scenes.volume_cell_lights_scene(7, 2),
+    "max_light_count": lambda: scenes.max_light_count_scene(51),
+    "max_light_count_focus": lambda: scenes.max_light_count_scene(52, n_lights=9, max_count=4, focus=True),
+    "max_light_count_many": lambda: scenes.max_light_count_scene(53, n_lights=47, max_count=6),
+    "render_order_45_solids": lambda: scenes.render_order_scene(0, n=45),
     "subdivision": lambda: scenes.subdivision_scene(0),
     "subdivision_no_levels": lambda: scenes.subdivision_scene(1, with_levels=False),
     "skinned": lambda: scenes.skinned_scene(1, n=4, rings=6, sides=7),
@@ -142,3 +143,20 @@ def test_matrix_primitives_of_both_restatements_agree():
         assert np.array_equal(LG.node_transform(node).view(np.uint32), O.node_world_transform(node).reshape(4, 4).view(np.uint32))
     for fov, near, far, w, h in [(60.0, 0.1, 100.0, 640, 360), (75.0, 0.05, 250.0, 1920, 1080), (30.0, 1.0, 20.0, 100, 100)]:
         assert np.array_equal(LG.perspective(fov, near, far, w, h).view(np.uint32), np.asarray(O.mat4_perspective(fov, near, far, w, h), np.float32).reshape(4, 4).view(np.uint32))
+
+
+def test_both_restatements_of_go_stable_sort_agree_on_arbitrary_relations():
+    # sort.SliceStable is handed comparators that are not orderings (camera.go:1460-1469, 1484-1495), so its outcome is defined by
+    # the algorithm alone; the oracle's C restatement and literal_go's Python one must make the same sequence of decisions
+    import ctypes
+    lib = O.lib()
+    lib.orc_test_go_stable_sort_table.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int)]
+    lib.orc_test_go_stable_sort_table.restype = None
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(0, 130))
+        table = (rng.random((max(n, 1), max(n, 1))) < rng.uniform(0.1, 0.9)).astype(np.uint8)
+        perm = np.zeros(max(n, 1), np.int32)
+        lib.orc_test_go_stable_sort_table(n, table.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+        assert list(perm[:n]) == LG.slice_stable(list(range(n)), lambda x, y: bool(table[x][y])), trial
+
