@@ -1160,3 +1160,126 @@ def slice_stable(items, less_items):
     go_stable_sort(len(items), lambda i, j: less_items(items[i], items[j]), swap)
     return items
 
+
+# ---- animation.go:63-164, quaternion.go:26-59, 86-104, 132-178, node.go:572-594: the bone poses ------------------------------------
+def _key_pair(times, time):
+    """The keyframes around `time` as the loops of animation.go:77-86 / 130-139 find them: (first, last) indices."""
+    first = last = None
+    for k in range(len(times)):
+        if times[k] < time:
+            first = k
+        else:
+            last = k
+            break
+    return first, last
+
+
+def value_as_vector(track, time):                           # animation.go:63-112: (value, exists)
+    time = F(time)
+    times, values = track.times, track.values
+    if len(times) == 0:
+        return None, False
+    if time <= times[0]:
+        return [values[0][0], values[0][1], values[0][2]], True
+    if time >= times[-1]:
+        return [values[-1][0], values[-1][1], values[-1][2]], True
+    first, last = _key_pair(times, time)
+    if time == times[first]:
+        return list(values[first][:3]), True
+    if time == times[last]:
+        return list(values[last][:3]), True
+    fd, ld = values[first], values[last]
+    if track.interpolation == 1:                            # InterpolationConstant
+        return [fd[0], fd[1], fd[2]], True
+    t = (time - times[first]) / (times[last] - times[first])
+    return [fd[0] + ((ld[0] - fd[0]) * t), fd[1] + ((ld[1] - fd[1]) * t), fd[2] + ((ld[2] - fd[2]) * t)], True      # Vector3.Lerp
+
+
+def quat_slerp(q, end, percent):                            # quaternion.go:26-59 (x y z w); math32.Sqrt / Atan2 / Sin go through Go's float64 functions
+    q, end, percent = [F(c) for c in q], [F(c) for c in end], F(percent)
+    cos_omega = q[0] * end[0] + q[1] * end[1] + q[2] * end[2] + q[3] * end[3]
+    if cos_omega < 0:
+        end = [end[0] * F(-1), end[1] * F(-1), end[2] * F(-1), end[3] * F(-1)]
+        cos_omega = cos_omega * F(-1)
+    if cos_omega > F(0.9999):
+        k0, k1 = F(1) - percent, percent
+    else:
+        sin_omega = sqrt32(F(1) - (cos_omega * cos_omega))
+        omega = F(O.go_atan2(float(sin_omega), float(cos_omega)))
+        one_over = F(1) / sin_omega
+        k0 = F(O.go_sin(float((F(1) - percent) * omega))) * one_over
+        k1 = F(O.go_sin(float(percent * omega))) * one_over
+    w = q[3] * k0 + end[3] * k1
+    x = q[0] * k0 + end[0] * k1
+    y = q[1] * k0 + end[1] * k1
+    z = q[2] * k0 + end[2] * k1
+    return [x, y, z, w]
+
+
+def quat_unit(q):                                           # quaternion.go:86-104
+    m = sqrt32((q[0] * q[0]) + (q[1] * q[1]) + (q[2] * q[2]) + (q[3] * q[3]))
+    return [q[0] / m, q[1] / m, q[2] / m, q[3] / m]
+
+
+def quat_to_matrix4(q):                                     # quaternion.go:132-178
+    x, y, z, w = [F(c) for c in q]
+    m1 = np.array([[w, z, -y, x], [-z, w, x, y], [y, -x, w, z], [-x, -y, -z, w]], F)
+    m2 = np.array([[w, z, -y, -x], [-z, w, x, -y], [y, -x, w, -z], [x, y, z, w]], F)
+    return mat4_mult(m1, m2)
+
+
+def value_as_quaternion(track, time):                       # animation.go:116-164
+    time = F(time)
+    times, values = track.times, track.values
+    if len(times) == 0:
+        return None, False
+    if time <= times[0]:
+        return list(values[0]), True
+    if time >= times[-1]:
+        return list(values[-1]), True
+    first, last = _key_pair(times, time)
+    if time == times[first]:
+        return list(values[first]), True
+    if time == times[last]:
+        return list(values[last]), True
+    if track.interpolation == 1:
+        return list(values[first]), True
+    t = (time - times[first]) / (times[last] - times[first])
+    return quat_slerp(values[first], values[last], t), True
+
+
+def pose_bones(sk, anim, playhead, root16):
+    """AnimationPlayer.updateValues + forceUpdate without blending (animation.go:674-722, 939-983) on an armature at rest, then every
+    bone's Transform() and boneInfluence (node.go:572-594): (n_bones, 16)."""
+    n = len(sk.parent)
+    root = mat(root16)
+    world = [None] * n
+    out = np.zeros((n, 16), F)
+    for b in range(n):
+        pos = [F(c) for c in sk.rest_position[b]]
+        scl = [F(c) for c in sk.rest_scale[b]]
+        rot = mat(sk.rest_rotation[b])
+        channel = anim.channels.get(sk.names[b]) if anim is not None else None
+        if channel:
+            if 0 in channel:
+                v, exists = value_as_vector(channel[0], playhead)
+                if exists:
+                    pos = v
+            if 1 in channel:
+                v, exists = value_as_vector(channel[1], playhead)
+                if exists:
+                    scl = v
+            if 2 in channel:
+                q, exists = value_as_quaternion(channel[2], playhead)
+                if exists:
+                    r = quat_to_matrix4(q)
+                    if r.any():                             # SetLocalRotation ignores an all-zero matrix (node.go:906-912)
+                        rot = r
+        t = mat4_scale(scl[0], scl[1], scl[2])
+        t = mat4_mult(t, rot)
+        t = mat4_mult(t, mat4_translate(pos[0], pos[1], pos[2]))
+        t = mat4_mult(t, world[int(sk.parent[b])] if sk.parent[b] >= 0 else root)
+        world[b] = t
+        out[b] = mat4_mult(mat(sk.inverse_bind[b]), t).reshape(16)
+    return out
+

@@ -248,8 +248,8 @@ def test_blended_posed_scenes_render_in_the_oracle():
 class LiteralPlayer:
     """AnimationPlayer as animation.go writes it, maps and all: AnimatedProperties / currentProperties / prevAnimatedProperties keyed
     by node, assignChannels clearing the first two after every Play(), forceUpdate's per-node blend.  Nodes are the skeleton's
-    bones (local position / scale / rotation matrix, starting at rest); track sampling is the oracle's (orc_sample_bone), the blend
-    arithmetic float32 numpy.  One deliberate difference: the reference ends the blend INSIDE its loop over the node map when bp
+    bones (local position / scale / rotation matrix, starting at rest); track sampling, Slerp, Unit and ToMatrix4 are the literal
+    restatements of tests/literal_go.py (only Go's float64 math.Sin / math.Atan2 are the oracle's), the blend arithmetic float32 numpy.  One deliberate difference: the reference ends the blend INSIDE its loop over the node map when bp
     reaches 1 (animation.go:899-902), which makes that frame depend on Go's map order; here the blend ends after the loop."""
 
     def __init__(self, sk, clock):
@@ -277,11 +277,18 @@ class LiteralPlayer:
             for name in self.animation.channels:
                 self.animated[self.sk.names.index(name)] = dict(P=False, S=False, R=False, p=None, s=None, q=None)
             self.channels_updated = True
-        for node, n in self.animated.items():
-            flags, p, s, q = O.sample_bone(self.sk, self.animation, node, float(self.playhead))
-            if flags[0]: n["p"], n["P"] = p, True
-            if flags[1]: n["s"], n["S"] = s, True
-            if flags[2]: n["q"], n["R"] = q, True
+        import literal_go as LG
+        for node, n in self.animated.items():               # updateValues, animation.go:686-718: the channel's tracks, sampled literally
+            tracks = self.animation.channels[self.sk.names[node]]
+            if 0 in tracks:
+                v, exists = LG.value_as_vector(tracks[0], self.playhead)
+                if exists: n["p"], n["P"] = np.asarray(v, F32), True
+            if 1 in tracks:
+                v, exists = LG.value_as_vector(tracks[1], self.playhead)
+                if exists: n["s"], n["S"] = np.asarray(v, F32), True
+            if 2 in tracks:
+                v, exists = LG.value_as_quaternion(tracks[2], self.playhead)
+                if exists: n["q"], n["R"] = np.asarray(v, F32), True
         self.playhead = F32(self.playhead + F32(dt))
         ended = False
         for node, props in self.animated.items():
@@ -296,7 +303,7 @@ class LiteralPlayer:
                 if start["S"] and props["S"]: ts = start["s"] + (props["s"] - start["s"]) * bp
                 elif props["S"]: ts = props["s"]
                 elif start["S"]: ts = start["s"]
-                if start["R"] and props["R"]: tq = _unit(O.quat_slerp(start["q"], props["q"], float(bp)))
+                if start["R"] and props["R"]: tq = np.asarray(LG.quat_unit(LG.quat_slerp(start["q"], props["q"], bp)), F32)
                 elif props["R"]: tq = props["q"]
                 elif start["R"]: tq = start["q"]
                 ended = ended or bp == 1
@@ -309,7 +316,7 @@ class LiteralPlayer:
             if tp is not None: self.pos[node] = tp                      # animation.go:939-983 (no relative motion)
             if ts is not None: self.scl[node] = ts
             if tq is not None:
-                m = O.quat_to_matrix(tq).reshape(16)
+                m = LG.quat_to_matrix4(tq).reshape(16)
                 if m.any(): self.rot[node] = m                          # node.go:906-912
         if ended:
             self.blend_start = None; self.prev = {}
@@ -378,3 +385,27 @@ def by_id_lookup(by_id, host, a):
         if h is a:
             return by_id[id(h)]
     raise KeyError(a)
+
+
+def test_pose_bones_equal_the_literal_restatement():
+    # track sampling (both loops of animation.go), Slerp on both branches, ToMatrix4, SetLocalRotation's zero-matrix rule, the bone
+    # hierarchy and boneInfluence, restated separately in tests/literal_go.py: bit for bit on random skeletons, animations, playheads
+    import literal_go as LG
+    checked = 0
+    for seed in range(24):
+        rng = np.random.default_rng(300 + seed)
+        sk = scenes.random_skeleton(rng, int(rng.integers(2, 20)), chain=bool(seed % 2))
+        anim = scenes.random_animation(rng, sk)
+        root = scenes.random_rotation(rng).astype(F32).reshape(16).copy(); root[12:15] = rng.uniform(-2, 2, 3)
+        times = np.concatenate([rng.uniform(-0.3, 3.4, 6), [0.0, 3.0]])
+        for ch in anim.channels.values():               # ... and exactly on keyframe times
+            for tr in ch.values():
+                times = np.concatenate([times, tr.times[:2]])
+        for ph in times[:14]:
+            want = O.pose_bones(sk, anim, float(ph), root)
+            got = LG.pose_bones(sk, anim, float(F32(ph)), root)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, float(ph))
+            checked += 1
+        assert np.array_equal(LG.pose_bones(sk, None, 0.0, root).view(np.uint32), O.pose_bones(sk, None, 0.0, root).view(np.uint32))
+    assert checked > 200
+
