@@ -712,12 +712,12 @@ class Camera:
         self.camera_up = up_vector(world_rotation(desc.node))                                  # camera.go:1085-1088 (Camera.Clear)
 
 
-def process_vertices(model, part_index, camera, bucket, g, autosubdivision_levels=()):
+def process_vertices(model, part_index, camera, bucket, g, autosubdivision_levels=(), process_only_visible=True):
     """model.go:600-995 with processOnlyVisible = true, for a model without billboarding or callbacks.
     Returns False for the early-out of model.go:604-606."""
     bucket.clear()
     part = model.desc.mesh.parts[part_index]
-    if (model.color[3] == 0 and model.is_transparent(part)) or not model.desc.visible:
+    if process_only_visible and ((model.color[3] == 0 and model.is_transparent(part)) or not model.desc.visible):
         return False
     mesh = model.desc.mesh
     model_transform = model.transform
@@ -795,17 +795,17 @@ def process_vertices(model, part_index, camera, bucket, g, autosubdivision_level
             tv.append((g.transforms[vi][0] / w, g.transforms[vi][1] / w))
             if g.transforms[vi][2] + F(1) >= camera.near and g.transforms[vi][2] < camera.far:
                 out_of_bounds = False
-        if out_of_bounds:
+        if process_only_visible and out_of_bounds:
             continue
         h = F(0.5)
-        if (tv[0][0] < -h and tv[1][0] < -h and tv[2][0] < -h) or (tv[0][0] > h and tv[1][0] > h and tv[2][0] > h) or \
-           (tv[0][1] < -h and tv[1][1] < -h and tv[2][1] < -h) or (tv[0][1] > h and tv[1][1] > h and tv[2][1] > h):
+        if process_only_visible and ((tv[0][0] < -h and tv[1][0] < -h and tv[2][0] < -h) or (tv[0][0] > h and tv[1][0] > h and tv[2][0] > h) or \
+           (tv[0][1] < -h and tv[1][1] < -h and tv[2][1] < -h) or (tv[0][1] > h and tv[1][1] > h and tv[2][1] > h)):
             continue
         if mat_ is not None and mat_.backface_culling:                                         # model.go:893-916
             n0x, n0y = tv[0][0] - tv[1][0], tv[0][1] - tv[1][1]
             n1x, n1y = tv[1][0] - tv[2][0], tv[1][1] - tv[2][1]
             nor = (n0x * n1y) - (n1x * n0y)
-            if nor < 0:
+            if process_only_visible and nor < 0:
                 continue
         if model.skinned:                                                                      # model.go:839-856, 934-940
             cx = cy = cz = F(0)
@@ -815,7 +815,7 @@ def process_vertices(model, part_index, camera, bucket, g, autosubdivision_level
         else:                                                                                  # model.go:942-948
             dx, dy, dz = inverted_cam_pos[0] - tri.center[0], inverted_cam_pos[1] - tri.center[1], inverted_cam_pos[2] - tri.center[2]
         depth = dx * dx + dy * dy + dz * dz
-        if np.isnan(depth) or np.isinf(depth):
+        if process_only_visible and (np.isnan(depth) or np.isinf(depth)):
             continue
         if depth < min_depth:
             min_depth = depth
@@ -1282,4 +1282,98 @@ def pose_bones(sk, anim, playhead, root16):
         world[b] = t
         out[b] = mat4_mult(mat(sk.inverse_bind[b]), t).reshape(16)
     return out
+
+
+# ---- model.go:1203-1268 ------------------------------------------------------------------------------------------------------------
+def bake_lighting(desc, model_desc, light_descs, rgb=None):
+    """Model.BakeLighting into a colour channel that starts as `rgb` (default: ones, a channel that did not exist): (n_verts, 3).
+    Every visible light of the argument list plus the world's ambient light lights the model: ProcessVertices with
+    processOnlyVisible = false, then, light by light, light.Light(tri) for every triangle of the part -- so a vertex receives a
+    light once per corner that refers to it."""
+    cam = Camera(desc.camera)
+    model = Model(model_desc)
+    mesh = model_desc.mesh
+    g = Globals(mesh.n_verts)
+    init = np.ones((mesh.n_verts, 3), F) if rgb is None else np.asarray(rgb, F).reshape(-1, 3)
+    g.vertex_lights = [[init[i][0], init[i][1], init[i][2], F(1)] for i in range(mesh.n_verts)]      # VertexColors[targetChannel]
+    lights = [make_light(ld) for ld in light_descs if ld.visible]
+    if desc.world.present and desc.world.ambient_visible:                                            # model.Scene().World.AmbientLight
+        lights.append(AmbientLight(desc.world.ambient_color, desc.world.ambient_energy))
+    for l in lights:
+        l.begin_render()
+        l.begin_model(model)
+    bucket = SortingTriangleBucket()
+    for pi, part in enumerate(mesh.parts):
+        process_vertices(model, pi, cam, bucket, g, (), process_only_visible=False)
+        if part.material is not None and part.material.shadeless:
+            for v in range(part.vertex_start, part.vertex_end):
+                g.vertex_lights[v][0] = g.vertex_lights[v][1] = g.vertex_lights[v][2] = F(1)
+            continue
+        for v in range(part.vertex_start, part.vertex_end):
+            g.vertex_lights[v][0] = g.vertex_lights[v][1] = g.vertex_lights[v][2] = F(0)
+        for l in lights:
+            for tri in model.parts[pi]:                                                              # forEachTri(true, ..)
+                l.light(tri, model, g)
+    return np.asarray([c[:3] for c in g.vertex_lights], F)
+
+
+# ---- model.go:1040-1124 (the pass over the model's own triangles) ------------------------------------------------------------------
+def vec_angle(v, other):                                    # vector.go:468-478; math32.Acos goes through Go's float64 math.Acos
+    eps = F(1e-4)
+    if not (abs(other[0]) > eps or abs(other[1]) > eps or abs(other[2]) > eps):
+        return F(0)
+    d = dot(v, other)
+    d = d / ((v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) * (other[0] * other[0] + other[1] * other[1] + other[2] * other[2]))
+    d = clamp(d, F(-1), F(1))
+    return F(O.go_acos(float(d)))
+
+
+def bake_ao(mesh, tri_normals, tri_max_span, occlusion_angle, occlusion_color, colors4=None, target_parts=None, target_vertices=None):
+    """Model.BakeAO without OtherModels: VertexColors[TargetChannel] after the bake, (n_verts, 4)."""
+    n = mesh.n_verts
+    colors = np.ones((n, 4), F) if colors4 is None else np.asarray(colors4, F).reshape(n, 4).copy()
+    centers = O.triangle_centers(mesh.positions, mesh.indices)
+    part_of = {}
+    for pi, p in enumerate(mesh.parts):
+        for t in range(p.tri_start, p.tri_end + 1):
+            part_of[t] = pi
+    P = mesh.positions
+    oc = [F(c) for c in occlusion_color]
+    angle_limit = F(occlusion_angle)
+    nt = mesh.n_tris
+    for ti in range(nt):
+        if target_parts is not None and len(target_parts) > 0 and part_of.get(ti) not in target_parts:
+            continue
+        tri = [int(i) for i in mesh.indices[ti]]
+        ao = [F(0), F(0), F(0)]
+        for oi in range(nt):
+            if oi == ti:
+                continue
+            other = [int(i) for i in mesh.indices[oi]]
+            span = max(F(tri_max_span[ti]), F(tri_max_span[oi])) * F(0.66)
+            if distance_squared_to(centers[ti], centers[oi]) > span * span:
+                continue
+            if vec_angle(tri_normals[ti], tri_normals[oi]) < angle_limit:
+                continue
+            shared, count = [-1, -1, -1], 0                 # SharesVertexPositions, mesh.go:2050-2081
+            for index in range(3):
+                for other_index in range(3):
+                    if vec_equals(P[tri[index]], P[other[other_index]]):
+                        shared[index] = other_index
+                        count += 1
+                        break
+            if count > 0:
+                for k in range(3):
+                    if shared[k] >= 0:
+                        ao[k] = F(1)
+            if ao[0] == 1 and ao[1] == 1 and ao[2] == 1:
+                break
+        for i in range(3):
+            p = clamp(ao[i], F(0), F(1))
+            vi = tri[i]
+            if target_vertices is not None and len(target_vertices) > 0 and vi not in target_vertices:
+                continue
+            for k in range(4):
+                colors[vi][k] = colors[vi][k] + (oc[k] - colors[vi][k]) * p
+    return colors
 

@@ -160,3 +160,30 @@ def test_both_restatements_of_go_stable_sort_agree_on_arbitrary_relations():
         lib.orc_test_go_stable_sort_table(n, table.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
         assert list(perm[:n]) == LG.slice_stable(list(range(n)), lambda x, y: bool(table[x][y])), trial
 
+
+def test_bakes_equal_the_literal_restatement():
+    # Model.BakeLighting (model.go:1203-1268: every light once per corner, nothing culled) and Model.BakeAO's same-model pass
+    # (model.go:1040-1124), restated in literal_go.py
+    import tetra3d_b200 as t3d
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for desc in (scenes.soup_scene(1), scenes.soup_scene(3, ranged=True), scenes.soup_scene(4, parent=True), scenes.skinned_scene(1, n=3, rings=6, sides=7),
+                     scenes.volume_scene(1, 0), scenes.volume_scene(2, 1), scenes.volume_scene(3, 2)):
+            for md in desc.models[:2]:
+                a = O.bake_lighting(desc, md, list(desc.lights))
+                b = LG.bake_lighting(desc, md, list(desc.lights))
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (desc.name, md.name)
+            md = desc.models[0]
+            sub = list(desc.lights)[:1]
+            assert np.array_equal(O.bake_lighting(desc, md, sub).view(np.uint32), LG.bake_lighting(desc, md, sub).view(np.uint32))
+        for desc, angle, parts, verts in ((scenes.soup_scene(4, n_models=1, n_tris=250), 0.5, None, None), (scenes.soup_scene(6, n_models=1, n_tris=200), 1.2, [0], None),
+                                          (scenes.skinned_scene(1, n=1, rings=5, sides=6), 0.8, None, [0, 1, 2, 5, 7, 11])):
+            md = desc.models[0]
+            scene, cam, objs = t3d.build_scene(desc, None)
+            normals, spans = objs[id(md.mesh)].TriangleNormalsAndSpans()
+            oc = [0.1, 0.2, 0.3, 0.9]
+            a = O.bake_ao(desc, md, normals, spans, angle, oc, target_parts=parts, target_vertices=verts)
+            b = LG.bake_ao(md.mesh, np.asarray(normals, np.float32).reshape(-1, 3), np.asarray(spans, np.float32), angle, oc, target_parts=parts, target_vertices=verts)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (desc.name, angle)
+            assert not np.array_equal(a, np.ones_like(a))
+
