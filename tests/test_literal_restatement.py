@@ -187,3 +187,34 @@ def test_bakes_equal_the_literal_restatement():
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (desc.name, angle)
             assert not np.array_equal(a, np.ones_like(a))
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["soup_lit", "soup_ranged", "billboard_locks", "skinned", "volume_cell_lights", "subdivision", "max_light_count"])
+def test_gpu_lists_equal_the_literal_restatement(device, name):
+    # the CUDA path against the second restatement directly (exact-lighting mode: colours bit for bit too)
+    import tetra3d_b200 as t3d
+    desc = SYNTHETIC[name]()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        lit = LG.render_scene(desc)
+    scene, cam, objs = t3d.build_scene(desc, device)
+    device.SetExactLighting(True)
+    try:
+        cam.Clear(); cam.RenderScene(scene)
+    finally:
+        device.SetExactLighting(False)
+    col, dep, tri = cam.ColorVertexList(), cam.DepthVertexList(), cam.TriangleIDs()
+    n_checked = 0
+    ref_renders = O.render_scene(desc).renders              # (only for the model index of every render(rp) call: same calls, same order)
+    renders = cam.Renders()
+    assert len(renders) == len(ref_renders)
+    for r, rr in zip(renders, ref_renders):
+        assert r["model"] == desc.models[rr["model"]].name and r["part"] == rr["part"]
+        ids, lcol, ldep = lit[(rr["model"], rr["part"])]
+        a, n = r["first_vertex"], r["vertex_count"]
+        assert n == len(lcol)
+        assert list(tri[a // 3:(a + n) // 3]) == ids
+        assert np.array_equal(col[a:a + n].view(np.uint32), lcol.view(np.uint32)) and np.array_equal(dep[a:a + n].view(np.uint32), ldep.view(np.uint32))
+        n_checked += n
+    assert n_checked > 0
