@@ -1032,25 +1032,59 @@ def sphere_in_frustum(cam, position, radius):               # camera.go:933-983
 
 
 def render_order(desc):
-    """The (model index, part index) of every render(rp) call in the order Camera.Render makes them, for scenes without dynamic
-    batches."""
+    """The (model index, part index) of every render(rp) call in the order Camera.Render makes them.  Dynamic batches
+    (camera.go:1398-1453, 2075-2100): the owner's MeshPart groups are visited in ascending part order (a Go map in the reference:
+    the contract fixes the order), the children far to near (sort.Slice; distinct distances assumed), each child's frustum test
+    applied, every MeshPart of a child rendered."""
     cam = Camera(desc.camera)
     solids, transparents = [], []
+    models = [Model(md) for md in desc.models]
+    children = {}
+    for ci, md in enumerate(desc.models):
+        if md.batch_owner is not None:
+            oi = [k for k, o in enumerate(desc.models) if o is md.batch_owner][0]
+            children.setdefault((oi, md.batch_owner_part), []).append(ci)
+
+    def in_frustum(model):
+        pos, radius = frustum_sphere(model)
+        return sphere_in_frustum(cam, pos, radius)
+
     for mi, md in enumerate(desc.models):
-        if not md.visible:
+        if not md.visible or md.batch_owner is not None:
             continue
-        model = Model(md)
-        if md.frustum_culling:
-            pos, radius = frustum_sphere(model)
-            if not sphere_in_frustum(cam, pos, radius):
+        model = models[mi]
+        model_pos = [model.transform[3][0], model.transform[3][1], model.transform[3][2]]
+        batcher = any(k[0] == mi for k in children)
+        if not batcher:
+            if md.frustum_culling and not in_frustum(model):
                 continue
-        for pi, part in enumerate(md.mesh.parts):
-            mat_ = part.material
-            if mat_ is not None and not mat_.visible:
-                continue
-            depth = distance_squared_to(cam.position, [model.transform[3][0], model.transform[3][1], model.transform[3][2]])
-            order = mat_.render_order if mat_ is not None else 0
-            (transparents if model.is_transparent(part) else solids).append((order, depth, mi, pi))
+            for pi, part in enumerate(md.mesh.parts):
+                mat_ = part.material
+                if mat_ is not None and not mat_.visible:
+                    continue
+                depth = distance_squared_to(cam.position, model_pos)
+                order = mat_.render_order if mat_ is not None else 0
+                (transparents if model.is_transparent(part) else solids).append((order, depth, mi, pi, None))
+        else:
+            transparent = False
+            for pi in sorted(k[1] for k in children if k[0] == mi):
+                part = md.mesh.parts[pi]
+                if part.material is not None and not part.material.visible:
+                    continue
+                for ci in children[(mi, pi)]:
+                    cd = desc.models[ci]
+                    if not cd.visible:
+                        continue
+                    if not transparent:
+                        for cp in cd.mesh.parts:
+                            if (cp.material is None or cp.material.visible) and models[ci].is_transparent(cp):
+                                transparent = True
+                                break
+                depth = F(0)
+                if transparent or not desc.camera.render_depth:
+                    depth = distance_squared_to(cam.position, model_pos)
+                order = part.material.render_order if part.material is not None else 0
+                (transparents if transparent else solids).append((order, depth, mi, pi, children[(mi, pi)]))
     if not desc.camera.render_depth:                                                                 # camera.go:1460-1469 (not an ordering when orders differ:
         def less(i, j):                                                                              #  the outcome is whatever sort.SliceStable's algorithm makes of it)
             if i[0] < j[0]:
@@ -1058,7 +1092,21 @@ def render_order(desc):
             return i[1] > j[1]
         solids = slice_stable(solids, less)
     transparents = sorted(transparents, key=lambda r: (r[0], -float(r[1])))                          # camera.go:2050-2055
-    return [(mi, pi) for _, _, mi, pi in solids + transparents]
+    out = []
+    for _, _, mi, pi, kids in solids + transparents:
+        if kids is None:
+            out.append((mi, pi))
+            continue
+        dist = {ci: distance_squared_to(cam.position, [models[ci].transform[3][0], models[ci].transform[3][1], models[ci].transform[3][2]]) for ci in kids}
+        for ci in sorted(kids, key=lambda c: -float(dist[c])):                                       # camera.go:2078-2080
+            cd = desc.models[ci]
+            if not cd.visible:
+                continue
+            if cd.frustum_culling and not in_frustum(models[ci]):
+                continue
+            for cp in range(len(cd.mesh.parts)):
+                out.append((ci, cp))
+    return out
 
 
 # ---- package sort: sort.SliceStable (the algorithm of Go's sort.Stable: insertion sort on blocks of 20, then SymMerge) -----------

@@ -46,10 +46,9 @@ def check(desc):
         assert np.array_equal(ref.depth_list[a:a + n].view(np.uint32), dep.view(np.uint32)), (desc.name, r["model"], r["part"], "depth list")
         n_checked += n
     # which render pairs there are (visibility, the frustum test of every model) and the order they are rendered in
-    if not any(m.batch_owner is not None for m in desc.models):
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", RuntimeWarning)
-            assert LG.render_order(desc) == [(r["model"], r["part"]) for r in ref.renders], (desc.name, "render pairs / order")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        assert LG.render_order(desc) == [(r["model"], r["part"]) for r in ref.renders], (desc.name, "render pairs / order")
     return n_checked
 
 
