@@ -31,6 +31,12 @@ def covered(desc):
     return True
 
 
+def same_bits(a, b):
+    """Bit for bit, any NaN equal to any NaN (payload bits are not part of the contract)."""
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
 def check(desc):
     ref = O.render_scene(desc)
     with warnings.catch_warnings():
@@ -42,8 +48,8 @@ def check(desc):
         a, n = r["first_vertex"], r["vertex_count"]
         assert n == len(col) == len(dep) == 3 * len(ids), (desc.name, r, len(ids))
         assert list(ref.tri_ids[a // 3:(a + n) // 3]) == ids, (desc.name, r["model"], r["part"], "triangle set / order")
-        assert np.array_equal(ref.color_list[a:a + n].view(np.uint32), col.view(np.uint32)), (desc.name, r["model"], r["part"], "colour list")
-        assert np.array_equal(ref.depth_list[a:a + n].view(np.uint32), dep.view(np.uint32)), (desc.name, r["model"], r["part"], "depth list")
+        assert same_bits(ref.color_list[a:a + n], col), (desc.name, r["model"], r["part"], "colour list")
+        assert same_bits(ref.depth_list[a:a + n], dep), (desc.name, r["model"], r["part"], "depth list")
         n_checked += n
     # which render pairs there are (visibility, the frustum test of every model) and the order they are rendered in
     with warnings.catch_warnings():
@@ -217,3 +223,42 @@ def test_gpu_lists_equal_the_literal_restatement(device, name):
         assert np.array_equal(col[a:a + n].view(np.uint32), lcol.view(np.uint32)) and np.array_equal(dep[a:a + n].view(np.uint32), ldep.view(np.uint32))
         n_checked += n
     assert n_checked > 0
+
+
+def test_edge_cases_equal_the_literal_restatement():
+    # the corners where a restatement goes wrong first: vertices behind the camera (both w clamps), zero and mirrored scales
+    # (divisions by zero in Decompose), a point light sitting on a vertex (1 / 0, Unit of a zero vector), the 0.001 energy cut-off, a
+    # range that just misses, NaN and Inf positions, a scale of 1e18, one triangle (rangeDiff == 0), nothing surviving, a camera under
+    # rotated parents with an orthographic projection, snapping and the fog mode that does nothing, alpha 0 and invisible materials
+    from tetra3d_b200 import workloads as W
+    from tetra3d_b200.scenedesc import LIGHT_DIRECTIONAL, LIGHT_POINT, LightDesc, ModelDesc, NodeDesc, SceneDesc
+    rng = np.random.default_rng(0)
+    lights = lambda: scenes.lights_mixed(np.random.default_rng(1), ranged=False)
+    soup = lambda seed, **kw: scenes.random_soup(120, seed, **kw)
+    cases = [SceneDesc([ModelDesc(soup(1, extent=12.0), NodeDesc(position=(0, 0, 9.5)), frustum_culling=False, name="m")], lights(), CameraDesc(),
+                       WorldDesc(ambient_energy=0.2), name="straddle"),
+             SceneDesc([ModelDesc(soup(2), NodeDesc(scale=(1.0, 0.0, 1.0)), frustum_culling=False, name="flat"),
+                        ModelDesc(soup(3), NodeDesc(position=(2, 0, 0), scale=(-1.0, 1.0, 1.5)), name="mirror")], lights(), CameraDesc(), WorldDesc(ambient_energy=0.2), name="scales")]
+    m = soup(4)
+    L = [LightDesc(LIGHT_POINT, NodeDesc(position=tuple(float(x) for x in m.positions[0])), color=(1, 0.5, 0.25), energy=2.0, name="onvertex"),
+         LightDesc(LIGHT_POINT, NodeDesc(position=(30, 0, 0)), energy=0.0005, name="tiny"),
+         LightDesc(LIGHT_POINT, NodeDesc(position=(0, 3, 0)), energy=3.0, range=2.5, name="ranged"),
+         LightDesc(LIGHT_DIRECTIONAL, NodeDesc(rotation=W.rotation_matrix((1, 0, 0), 0.7)), energy=0.0, name="darksun")]
+    cases.append(SceneDesc([ModelDesc(m, NodeDesc(), name="m")], L, CameraDesc(), WorldDesc(ambient_energy=0.0), name="lights"))
+    m = soup(5); m.positions[3] = [np.nan, 0, 0]; m.positions[10] = [np.inf, 1, 1]
+    cases.append(SceneDesc([ModelDesc(m, NodeDesc(), frustum_culling=False, name="nan")], lights(), CameraDesc(), WorldDesc(ambient_energy=0.3), name="nan"))
+    cases.append(SceneDesc([ModelDesc(soup(6), NodeDesc(scale=(1e18, 1e18, 1e18)), frustum_culling=False, name="huge")], lights(), CameraDesc(far=1e30),
+                           WorldDesc(ambient_energy=0.3), name="huge"))
+    cases.append(SceneDesc([ModelDesc(scenes.single_triangle(z=0.0), NodeDesc(), name="t")], lights(), CameraDesc(), WorldDesc(ambient_energy=0.5), name="one"))
+    cases.append(SceneDesc([ModelDesc(scenes.single_triangle(z=0.0, flip=True), NodeDesc(), name="t")], lights(), CameraDesc(), WorldDesc(), name="culled"))
+    par = NodeDesc(position=(1, 2, 3), rotation=scenes.random_rotation(rng), scale=(1.0, 2.0, 0.5))
+    cam = CameraDesc(node=NodeDesc(position=(0, 0, 10), rotation=scenes.random_rotation(rng), parent=NodeDesc(rotation=scenes.random_rotation(rng))),
+                     perspective=False, ortho_scale=30.0, vertex_snapping=4.0, render_depth=False)
+    cases.append(SceneDesc([ModelDesc(soup(7), NodeDesc(position=(0, 1, 0), parent=par), frustum_culling=False, name="p")], lights(), cam,
+                           WorldDesc(fog_mode=2, fog_color=(0.2, 0.3, 0.4, 1.0), ambient_energy=0.4), name="ortho"))
+    cases.append(SceneDesc([ModelDesc(scenes.random_soup(60, 8, material=MaterialDesc(transparency_mode=3)), NodeDesc(), color=(1, 1, 1, 0.0), name="a0"),
+                            ModelDesc(scenes.random_soup(60, 9, n_parts=2, material=MaterialDesc(visible=False)), NodeDesc(position=(1, 0, 0)), name="inv")],
+                           lights(), CameraDesc(), WorldDesc(ambient_energy=0.4), name="early"))
+    emitted = sum(check(c) for c in cases)
+    assert emitted > 500
+
