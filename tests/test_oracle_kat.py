@@ -1,5 +1,8 @@
 """Pins the oracle's math against the only assertion-bearing test of the reference (matrix_test.go:36-55)
 and against an independent numpy float32 evaluation of the cited formulas."""
+import math
+import struct
+
 import numpy as np
 import pytest
 
@@ -133,3 +136,62 @@ def test_go_stable_sort_restatement_is_a_stable_sort():
             perm = np.zeros(max(n, 1), np.int32)
             lib.orc_test_go_stable_sort(n, keys.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
             assert np.array_equal(perm[:n], np.argsort(keys, kind="stable")), (n, distinct)
+
+# ---- the camera's trigonometry: Go's pure-Go math.Tan / math.Cos / math.Atan (Cephes-derived, src/math/tan.go, sin.go, atan.go)
+# against the C library's, which the oracle and the host mirror call for the projection matrix (matrix.go:592) and the frustum
+# sphere factors (camera.go:660-666).  The two differ by up to 2 ulp in float64; what matters is the value after math32's
+# conversion to float32.
+def f64(bits): return struct.unpack('<d', struct.pack('<Q', bits))[0]
+PI4A, PI4B, PI4C = f64(0x3fe921fb40000000), f64(0x3e64442d00000000), f64(0x3ce8469898cc5170)
+M4PI = 4/math.pi  # Go: 4 / Pi constant (exact constant arithmetic then rounded to float64)
+SIN = [f64(0x3de5d8fd1fd19ccd), f64(0xbe5ae5e5a9291f5d), f64(0x3ec71de3567d48a1), f64(0xbf2a01a019bfdf03), f64(0x3f8111111110f7d0), f64(0xbfc5555555555548)]
+COS = [f64(0xbda8fa49a0861a9b), f64(0x3e21ee9d7b4e3f05), f64(0xbe927e4f7eac4bc6), f64(0x3efa01a019c844f5), f64(0xbf56c16c16c14f91), f64(0x3fa555555555554b)]
+TANP = [-1.30936939181383777646e4, 1.15351664838587416140e6, -1.79565251976484877988e7]
+TANQ = [1.0, 1.36812963470692954678e4, -1.32089234440210967447e6, 2.50083801823357915839e7, -5.38695755929454629881e7]
+def go_tan(x):
+    sign = False
+    if x < 0: x = -x; sign = True
+    j = int(x * M4PI); y = float(j)
+    if j & 1: j += 1; y += 1
+    z = ((x - y*PI4A) - y*PI4B) - y*PI4C
+    zz = z*z
+    if zz > 1e-14:
+        y = z + z*(zz*(((TANP[0]*zz)+TANP[1])*zz+TANP[2])/((((zz+TANQ[1])*zz+TANQ[2])*zz+TANQ[3])*zz+TANQ[4]))
+    else:
+        y = z
+    if j & 2: y = -1/y
+    return -y if sign else y
+def go_cos(x):
+    sign = False
+    x = abs(x)
+    j = int(x * M4PI); y = float(j)
+    if j & 1: j += 1; y += 1
+    j &= 7
+    z = ((x - y*PI4A) - y*PI4B) - y*PI4C
+    if j > 3: j -= 4; sign = not sign
+    if j > 1: sign = not sign
+    zz = z*z
+    if j == 1 or j == 2:
+        y = z + z*zz*((((((SIN[0]*zz)+SIN[1])*zz+SIN[2])*zz+SIN[3])*zz+SIN[4])*zz+SIN[5])
+    else:
+        y = 1.0 - 0.5*zz + zz*zz*((((((COS[0]*zz)+COS[1])*zz+COS[2])*zz+COS[3])*zz+COS[4])*zz+COS[5])
+    return -y if sign else y
+
+
+def test_libm_trigonometry_equals_go_for_every_camera_angle():
+    import math
+    from oracle import binding as O
+    F = np.float32
+    worst = 0.0
+    for fov10 in range(5, 1795, 5):                      # fields of view 0.5 .. 179 degrees in half-degree steps
+        fov = F(fov10 / 10)
+        for a in (float(fov * F(math.pi) / F(360)), float(fov * F(3.1415) / F(360))):          # matrix.go:592, camera.go:660
+            t_go, t_c, c_go, c_c = go_tan(a), math.tan(a), go_cos(a), math.cos(a)
+            worst = max(worst, abs(t_go - t_c) / math.ulp(t_c), abs(c_go - c_c) / math.ulp(c_c))
+            assert F(t_go) == F(t_c) and F(c_go) == F(c_c), (fov, a)
+            for aspect in (16 / 9, 4 / 3, 1.0, 21 / 9, 2.0):
+                x = float(F(t_c) * F(aspect))
+                at_go, at_c = O.go_atan2(x, 1.0), math.atan(x)
+                assert F(at_go) == F(at_c) and F(go_cos(float(F(at_go)))) == F(math.cos(float(F(at_c)))), (fov, aspect)
+    assert worst <= 4.0          # a mistyped Cephes coefficient would be off by many orders of magnitude more
+
