@@ -415,8 +415,9 @@ int t3d_set_skip_unused_depth_list(t3d_ctx* ctx, int enabled);
 /* Two frames in flight.  With this on, t3d_frame_results still waits for the frame's kernels and returns counts, per-draw
  * results and list pointers, but only STARTS the device -> host copy of the lists (on a stream of its own, into one of two sets
  * of pinned buffers; the kernels alternate between two sets of device lists likewise): the caller builds, submits and executes
- * the next frame while the copy runs, and reads frame k's lists after t3d_frame_download_wait.  The pointers of frame k stay
- * valid until t3d_frame_results of frame k + 2.  This is the order the reference's game loop allows: Camera.flush's
+ * the next frame while the copy runs, and reads frame k's lists after t3d_frame_download_wait.  The pointers of frame k (lists
+ * and `draws`) stay valid until t3d_frame_results of frame k + 2; `index_list` is one table for all frames, an identity that only
+ * ever grows (it may move when a later frame has a larger flush: take it from the latest output).  This is the order the reference's game loop allows: Camera.flush's
  * DrawTriangles calls (camera.go:1829-2048) of frame k are issued while Camera.Render of frame k + 1 runs.
  * Ignored (the lists are complete on return, as without it) for frames written to an output target or delivered to another rank. */
 int t3d_set_async_download(t3d_ctx* ctx, int enabled);

@@ -217,7 +217,7 @@ struct t3d_ctx {
     // results (pinned)
     PinVec<DrawStat> hStats;
     PinVec<uint32_t> hCount;
-    PinVec<t3d_draw_result> hResults;
+    PinVec<t3d_draw_result> hResults, hResultsB;      // B: frames of the second set while two frames are in flight (their results outlive the next frame's)
     PinVec<t3d_vertex> hColor, hDepth, hNormal, hColorB, hDepthB, hNormalB;
     PinVec<uint32_t> hTriIds, hTriIdsB;
     PinVec<uint16_t> hIndex;
@@ -333,7 +333,7 @@ void t3d_destroy(t3d_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->hSlim.release(); ctx->hTmpl.release(); ctx->hRot.release();
     ctx->hFrame.release(); ctx->hVbase.release(); ctx->hTbase.release(); ctx->hTileV.release(); ctx->hLarge.release(); ctx->hPacked.release(); ctx->hMedium.release(); for (auto& v : ctx->hVClass) v.release(); ctx->hHuge.release(); ctx->hTiles.release(); ctx->hFused.release();
-    ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release();
+    ctx->hLights.release(); ctx->hBones.release(); ctx->hStats.release(); ctx->hCount.release(); ctx->hResults.release(); ctx->hResultsB.release();
     ctx->hMail.release(); ctx->hGatherStats.release(); ctx->hColor.release(); ctx->hDepth.release(); ctx->hNormal.release(); ctx->hTriIds.release(); ctx->hIndex.release();
     for (void* q : ctx->sharedOpened) cudaIpcCloseMemHandle(q);
     for (void* q : ctx->sharedAllocs) cudaFree(q);
@@ -1640,7 +1640,8 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     const bool normals = ctx->fc.camFlags & T3D_CAM_RENDER_NORMALS;
     memset(out, 0, sizeof *out);
     out->n_draws = nDraws;
-    CU(ctx->hResults.resize(nDraws));
+    PinVec<t3d_draw_result>& hRes = (download && ctx->frameSet) ? ctx->hResultsB : ctx->hResults;
+    CU(hRes.resize(nDraws));
     ctx->downloadMs = 0;
     ctx->d2hBytes = 0;
     uint64_t nVerts = 0;
@@ -1665,7 +1666,7 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
         uint64_t acc = 0;
         for (uint32_t i = 0; i < nDraws; i++) {
             const DrawStat& st = ctx->hStats.p[i];
-            t3d_draw_result& r = ctx->hResults.p[i];
+            t3d_draw_result& r = hRes.p[i];
             r.first_vertex = 3 * acc;
             r.vertex_count = 3 * st.survivors;
             r.total_tris = st.minBits == DRAW_CULLED_MARK ? 0u : ctx->drawTotalTris[i];      // an instance outside the frustum was never render()ed
@@ -1680,19 +1681,19 @@ static int finish_frame(t3d_ctx* ctx, bool download, t3d_frame_output* out, t3d_
     } else {
         CU(cudaStreamSynchronize(s));
         for (uint32_t i = 0; i < nDraws; i++) {
-            t3d_draw_result& r = ctx->hResults.p[i];
+            t3d_draw_result& r = hRes.p[i];
             r.first_vertex = 0; r.vertex_count = 0; r.total_tris = ctx->drawTotalTris[i]; r.min_depth = FLT_MAX; r.max_depth = -FLT_MAX;
         }
     }
     ctx->nVerticesOut = nVerts;
     out->n_vertices = nVerts;
-    out->draws = ctx->hResults.p;
+    out->draws = hRes.p;
 
     // identity index table (camera.go:1816), sized for the largest flush
     uint64_t maxFlush = 0, cur = 0;
     for (uint32_t i = 0; i < nDraws; i++) {
         if (!ctx->drawContinue[i]) cur = 0;
-        cur += ctx->hResults.p[i].vertex_count;
+        cur += hRes.p[i].vertex_count;
         maxFlush = std::max(maxFlush, cur);
     }
     if (ctx->hIndex.n < maxFlush || ctx->hIndex.n == 0) {
